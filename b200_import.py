@@ -1,0 +1,20 @@
+"""Import helper: the package directory is named `ordinarydiffeq.jl_b200` (with a dot),
+which Python's import statement cannot spell.  `load()` registers it as
+`ordinarydiffeq_jl_b200` and returns the module."""
+import importlib.util
+import os
+import sys
+
+_NAME = "ordinarydiffeq_jl_b200"
+
+
+def load():
+    if _NAME in sys.modules:
+        return sys.modules[_NAME]
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ordinarydiffeq.jl_b200")
+    spec = importlib.util.spec_from_file_location(_NAME, os.path.join(root, "__init__.py"),
+                                                  submodule_search_locations=[root])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[_NAME] = mod
+    spec.loader.exec_module(mod)
+    return mod

@@ -1,0 +1,570 @@
+// oracle.cpp — CPU restatement of the reference's ensemble ODE path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under ordinarydiffeq.jl_b200/ may include, link
+// or call this file; it is used by tests/, __graft_entry__.smoke() and the
+// cpu_baseline / --impl reference legs of bench.py as the checker and the CPU baseline.
+//
+// PARITY UNPINNED: the reference is Julia and no Julia runtime exists in this
+// environment, and the reference's own tests hold no golden vectors for ensemble
+// step counts.  What pins this file is (1) every
+// known-answer / property test the reference's suite offers for this path
+// (tests/test_oracle_properties.py lists them with file:line) and (2) a function-by-
+// function correspondence with the reference source, cited below.  Arithmetic that
+// lives in un-vendored Julia packages is restated from their published algorithms:
+//   FastPower.jl 1.x      fastpower (Float32 pipeline)       -> fastpower()
+//   MuladdMacro.jl 0.2.x  @muladd nesting                     -> explicit std::fma
+//   StaticArrays.jl 1.9   sum(abs2,·) left fold, inv 3x3       -> rms(), inv3()
+//   Julia Base            eps, nextfloat, log10, ^, exp2(Float32)
+//
+// Each trajectory is the out-of-place / SVector form of the reference
+// (ConstantCache steppers), forward time, adaptive, PI controller, no callbacks.
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp ... -lquadmath).
+
+#include <quadmath.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORACLE_MAXN 64
+
+// ---------------------------------------------------------------------------
+// Julia Base scalar helpers
+template <typename R> struct Bits;
+template <> struct Bits<double> {
+    typedef uint64_t U;
+    static U to(double x) { U u; memcpy(&u, &x, 8); return u; }
+    static double from(U u) { double x; memcpy(&x, &u, 8); return x; }
+    static bool finite(double x) { return ((to(x) >> 52) & 0x7FF) != 0x7FF; }
+};
+template <> struct Bits<float> {
+    typedef uint32_t U;
+    static U to(float x) { U u; memcpy(&u, &x, 4); return u; }
+    static float from(U u) { float x; memcpy(&x, &u, 4); return x; }
+    static bool finite(float x) { return ((to(x) >> 23) & 0xFF) != 0xFF; }
+};
+
+// eps(x::AbstractFloat) (Base float.jl): ulp above |x|; eps(0)=nextfloat(0); NaN if non-finite
+template <typename R> static R jl_eps(R x) {
+    R ax = std::fabs(x);
+    if (!Bits<R>::finite(ax)) return std::numeric_limits<R>::quiet_NaN();
+    return Bits<R>::from(Bits<R>::to(ax) + 1) - ax;
+}
+template <typename R> static R jl_nextfloat(R x) { return Bits<R>::from(Bits<R>::to(x) + 1); }  // x >= 0 finite
+// Base.max/min propagate NaN
+template <typename R> static R jl_max(R a, R b) { return std::isnan(a) ? a : (std::isnan(b) ? b : (a > b ? a : b)); }
+template <typename R> static R jl_min(R a, R b) { return std::isnan(a) ? a : (std::isnan(b) ? b : (a < b ? a : b)); }
+// Base.FastMath.max_fast(x,y) = ifelse(y > x, y, x)
+template <typename R> static R jl_max_fast(R x, R y) { return y > x ? y : x; }
+static inline double jl_fma(double a, double b, double c) { return std::fma(a, b, c); }
+static inline float jl_fma(float a, float b, float c) { return std::fmaf(a, b, c); }
+
+// log10 / 10^x: correctly rounded through binary128 (libquadmath); for Float32 the
+// double result is rounded once more (Julia computes these in the working type to
+// < 1 ulp; correctly rounded is the modal value — see DESIGN.md "initial dt").
+static double cr_log10(double x) { return (double)log10q((__float128)x); }
+static double cr_exp10(double x) { return (double)powq((__float128)10, (__float128)x); }
+
+// ---------------------------------------------------------------------------
+// FastPower.fastpower — Float32 pipeline (EXT FastPower.jl; call sites
+// lib/OrdinaryDiffEqCore/src/integrators/controllers.jl:815-816)
+static float fp_fastlog2(float x) {
+    const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+    uint32_t ux1i = Bits<float>::to(x);
+    uint32_t exp = (ux1i & 0x7F800000u) >> 23;
+    uint32_t greater = ux1i & 0x00400000u;
+    float signif, fexp;
+    if (greater != 0u) {
+        uint32_t ux2i = (ux1i & 0x007FFFFFu) | 0x3f000000u;
+        signif = Bits<float>::from(ux2i);
+        fexp = (float)exp - 126.0f;
+    } else {
+        uint32_t ux2i = (ux1i & 0x007FFFFFu) | 0x3f800000u;
+        signif = Bits<float>::from(ux2i);
+        fexp = (float)exp - 127.0f;
+    }
+    signif = signif - 1.0f;
+    float t = a * signif;
+    t = t + b;
+    t = signif * t;
+    float d = signif + c;
+    t = t / d;
+    return fexp + t;
+}
+// Base.Math.exp2_fast(::Float32) = exp_impl_fast(x, Val(2)) (base/special/exp.jl)
+static float jl_exp2_fast_f32(float x) {
+    if (x >= 128.0f) return std::numeric_limits<float>::infinity();
+    if (x <= -150.0f) return 0.0f;
+    float N_float = std::nearbyintf(x);      // round(x), RoundNearest (ties to even)
+    int32_t N = (int32_t)N_float;
+    float r = std::fmaf(N_float, -1.0f, x);  // LogBU(Val(2),Float32) = -1
+    r = std::fmaf(N_float, 0.0f, r);         // LogBL(Val(2),Float32) = 0
+    static const float c[8] = {1.0f, 0.6931472f, 0.2402265f, 0.05550411f, 0.009618025f,
+                               0.0013333423f, 0.00015469732f, 1.5316464e-5f};
+    float small_part = c[7];
+    for (int i = 6; i >= 0; --i) small_part = std::fmaf(r, small_part, c[i]);   // evalpoly = Horner with muladd
+    float twopk = Bits<float>::from((uint32_t)(N + 127) << 23);
+    return twopk * small_part;
+}
+static double fastpower(double x, double y) {
+    if (x == 0.0) return 0.0;
+    if (std::isinf(x) && std::isinf(y)) return std::numeric_limits<double>::infinity();
+    return (double)jl_exp2_fast_f32((float)y * fp_fastlog2((float)x));
+}
+static float fastpower(float x, float y) {
+    if (x == 0.0f) return 0.0f;
+    if (std::isinf(x) && std::isinf(y)) return std::numeric_limits<float>::infinity();
+    return jl_exp2_fast_f32(y * fp_fastlog2(x));
+}
+
+// ---------------------------------------------------------------------------
+template <typename R> struct Fn {
+    typedef void (*rhs_t)(R* du, const R* u, const R* p, const R t);
+};
+
+enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4 };
+enum { RC_DEFAULT = 0, RC_SUCCESS = 1, RC_MAXITERS = 2, RC_DTLESSTHANMIN = 3, RC_UNSTABLE = 4, RC_DTNAN = 5 };
+
+template <typename R> struct Opts {
+    R reltol, abstol, dt, dtmin, dtmax;
+    long long maxiters;
+    const R* saveat; int nsaveat;
+    bool save_start, save_end, save_end_user;
+    int linsolve;      // 0: StaticWOperator inverse (n<=3), 1: partial-pivot LU
+};
+
+// ODE_DEFAULT_NORM(u::StaticArray, t) = sqrt_fast(real(sum(abs2,u)) / max(length(u),1))
+// (lib/DiffEqBase/src/common_defaults.jl:102-107); StaticArrays mapreduce is a left fold.
+template <typename R> static R rms(const R* v, int n) {
+    R acc = v[0] * v[0];
+    for (int i = 1; i < n; ++i) acc = acc + v[i] * v[i];
+    return std::sqrt(acc / (R)(n > 1 ? n : 1));
+}
+
+// calculate_residuals(ũ::Number, u₀, u₁, α, ρ, internalnorm, t)
+// (lib/DiffEqBase/src/calculate_residuals.jl:9-14): @muladd @fastmath ũ/(α+max(|u₀|,|u₁|)*ρ)
+template <typename R> static R residual(R ut, R u0, R u1, R abstol, R reltol) {
+    return ut / jl_fma(jl_max_fast(std::fabs(u0), std::fabs(u1)), reltol, abstol);
+}
+
+// ---------------------------------------------------------------------------
+// Steppers.  Each provides: order, fsal, qsteady_max, init, attempt, accept, dense, interp.
+template <typename R> struct Stats { int nf = 0, njacs = 0, nw = 0, nsolve = 0; };
+
+template <typename R> struct ProblemFns {
+    typename Fn<R>::rhs_t f = nullptr, jac = nullptr, tgrad = nullptr;
+    int n = 0, np = 0;
+};
+
+// Tsit5 — lib/OrdinaryDiffEqTsit5/src/tsit_perform_step.jl:125-186 (ConstantCache),
+// tableau tsit_tableaus.jl:52-92, interpolant interpolants.jl:32-57 + tsit_tableaus.jl:244-276
+template <typename R> struct Tsit5 {
+    static constexpr int order = 5;
+    static constexpr bool is_rosenbrock = false;
+    R k[7][ORACLE_MAXN];
+    const ProblemFns<R>* P;
+
+    void initialize(const R* uprev, const R* p, R t, Stats<R>& st) {
+        P->f(k[0], uprev, p, t);      // fsalfirst = f(uprev, p, t)
+        st.nf += 1;
+    }
+    R perform_step(const R* uprev, R* u, const R* p, R t, R dt, const Opts<R>& o, Stats<R>& st, bool) {
+        const int n = P->n;
+        const R c1 = (R)0.161, c2 = (R)0.327, c3 = (R)0.9, c4 = (R)0.9800255409045097;
+        const R a21 = (R)0.161, a31 = (R)-0.008480655492356989, a32 = (R)0.335480655492357,
+                a41 = (R)2.8971530571054935, a42 = (R)-6.359448489975075, a43 = (R)4.3622954328695815,
+                a51 = (R)5.325864828439257, a52 = (R)-11.748883564062828, a53 = (R)7.4955393428898365,
+                a54 = (R)-0.09249506636175525, a61 = (R)5.86145544294642, a62 = (R)-12.92096931784711,
+                a63 = (R)8.159367898576159, a64 = (R)-0.071584973281401, a65 = (R)-0.028269050394068383,
+                a71 = (R)0.09646076681806523, a72 = (R)0.01, a73 = (R)0.4798896504144996,
+                a74 = (R)1.379008574103742, a75 = (R)-3.290069515436081, a76 = (R)2.324710524099774;
+        const R btilde1 = (R)-0.00178001105222577714, btilde2 = (R)-0.0008164344596567469,
+                btilde3 = (R)0.007880878010261995, btilde4 = (R)-0.1447110071732629,
+                btilde5 = (R)0.5823571654525552, btilde6 = (R)-0.45808210592918697,
+                btilde7 = (R)0.015151515151515152;
+        R *k1 = k[0], *k2 = k[1], *k3 = k[2], *k4 = k[3], *k5 = k[4], *k6 = k[5], *k7 = k[6];
+        R tmp[ORACLE_MAXN], g6[ORACLE_MAXN];
+        R a = dt * a21;
+        // k2 = f(uprev + a*k1, p, t + c1*dt)
+        for (int i = 0; i < n; ++i) tmp[i] = jl_fma(a, k1[i], uprev[i]);
+        P->f(k2, tmp, p, jl_fma(c1, dt, t));
+        // k3 = f(uprev + dt*(a31*k1 + a32*k2), p, t + c2*dt)
+        for (int i = 0; i < n; ++i) tmp[i] = jl_fma(dt, jl_fma(a32, k2[i], a31 * k1[i]), uprev[i]);
+        P->f(k3, tmp, p, jl_fma(c2, dt, t));
+        for (int i = 0; i < n; ++i)
+            tmp[i] = jl_fma(dt, jl_fma(a43, k3[i], jl_fma(a42, k2[i], a41 * k1[i])), uprev[i]);
+        P->f(k4, tmp, p, jl_fma(c3, dt, t));
+        for (int i = 0; i < n; ++i)
+            tmp[i] = jl_fma(dt, jl_fma(a54, k4[i], jl_fma(a53, k3[i], jl_fma(a52, k2[i], a51 * k1[i]))), uprev[i]);
+        P->f(k5, tmp, p, jl_fma(c4, dt, t));
+        for (int i = 0; i < n; ++i)
+            g6[i] = jl_fma(dt, jl_fma(a65, k5[i], jl_fma(a64, k4[i], jl_fma(a63, k3[i], jl_fma(a62, k2[i], a61 * k1[i])))),
+                           uprev[i]);
+        P->f(k6, g6, p, t + dt);
+        for (int i = 0; i < n; ++i)
+            u[i] = jl_fma(dt,
+                          jl_fma(a76, k6[i],
+                                 jl_fma(a75, k5[i], jl_fma(a74, k4[i], jl_fma(a73, k3[i], jl_fma(a72, k2[i], a71 * k1[i]))))),
+                          uprev[i]);
+        P->f(k7, u, p, t + dt);       // fsallast
+        st.nf += 6;
+        R atmp[ORACLE_MAXN];
+        for (int i = 0; i < n; ++i) {
+            R utilde = dt * jl_fma(btilde7, k7[i],
+                                   jl_fma(btilde6, k6[i],
+                                          jl_fma(btilde5, k5[i],
+                                                 jl_fma(btilde4, k4[i],
+                                                        jl_fma(btilde3, k3[i], jl_fma(btilde2, k2[i], btilde1 * k1[i]))))));
+            atmp[i] = residual(utilde, uprev[i], u[i], o.abstol, o.reltol);
+        }
+        return rms(atmp, n);
+    }
+    void update_fsal() { memcpy(k[0], k[6], sizeof(R) * P->n); }   // fsalfirst = fsallast
+    void addsteps(const R*, const R*, const R*, R, R) {}            // length(k) >= 7: nothing to add
+    void interpolant(R Theta, R dt, const R* y0, const R*, R* out) const {
+        const int n = P->n;
+        const R r11 = (R)1.0, r12 = (R)-2.763706197274826, r13 = (R)2.9132554618219126, r14 = (R)-1.0530884977290216,
+                r22 = (R)0.13169999999999998, r23 = (R)-0.2234, r24 = (R)0.1017,
+                r32 = (R)3.9302962368947516, r33 = (R)-5.941033872131505, r34 = (R)2.490627285651253,
+                r42 = (R)-12.411077166933676, r43 = (R)30.33818863028232, r44 = (R)-16.548102889244902,
+                r52 = (R)37.50931341651104, r53 = (R)-88.1789048947664, r54 = (R)47.37952196281928,
+                r62 = (R)-27.896526289197286, r63 = (R)65.09189467479366, r64 = (R)-34.87065786149661,
+                r72 = (R)1.5, r73 = (R)-4.0, r74 = (R)2.5;
+        R Theta2 = Theta * Theta;
+        R b1 = Theta * jl_fma(Theta, jl_fma(Theta, jl_fma(Theta, r14, r13), r12), r11);
+        R b2 = Theta2 * jl_fma(Theta, jl_fma(Theta, r24, r23), r22);
+        R b3 = Theta2 * jl_fma(Theta, jl_fma(Theta, r34, r33), r32);
+        R b4 = Theta2 * jl_fma(Theta, jl_fma(Theta, r44, r43), r42);
+        R b5 = Theta2 * jl_fma(Theta, jl_fma(Theta, r54, r53), r52);
+        R b6 = Theta2 * jl_fma(Theta, jl_fma(Theta, r64, r63), r62);
+        R b7 = Theta2 * jl_fma(Theta, jl_fma(Theta, r74, r73), r72);
+        for (int i = 0; i < n; ++i)
+            out[i] = jl_fma(dt,
+                            jl_fma(k[6][i], b7,
+                                   jl_fma(k[5][i], b6,
+                                          jl_fma(k[4][i], b5,
+                                                 jl_fma(k[3][i], b4, jl_fma(k[2][i], b3, jl_fma(k[1][i], b2, k[0][i] * b1)))))),
+                            y0[i]);
+    }
+    static R qsteady_max() { return (R)1; }
+    static bool fsal_init() { return true; }
+};
+
+#if __has_include("oracle_vern7.inc")
+#include "oracle_vern7.inc"
+#define ORACLE_HAVE_VERN7 1
+#endif
+#if __has_include("oracle_rosenbrock.inc")
+#include "oracle_rosenbrock.inc"
+#define ORACLE_HAVE_ROSENBROCK 1
+#endif
+
+// ---------------------------------------------------------------------------
+// _ode_initdt_oop — lib/OrdinaryDiffEqCore/src/initdt.jl:346-459 (g === nothing, tdir = +1)
+template <typename R>
+static R ode_initdt(const ProblemFns<R>& P, const R* u0, const R* p, R t, R dtmax, R abstol, R reltol, R opts_dtmin,
+                    int order) {
+    const int n = P.n;
+    R dtmax_tdir = dtmax;
+    R dtmin = jl_nextfloat(jl_max(opts_dtmin, jl_eps(t)));
+    R smalldt = jl_max(dtmin, (R)1e-6);                 // convert(_tType, 1//10^6)
+    R sk[ORACLE_MAXN], tmp[ORACLE_MAXN], f0[ORACLE_MAXN], f1[ORACLE_MAXN], u1[ORACLE_MAXN];
+    for (int i = 0; i < n; ++i) sk[i] = jl_fma(std::fabs(u0[i]), reltol, abstol);     // abstol + |u0|*reltol (@muladd)
+    for (int i = 0; i < n; ++i) tmp[i] = u0[i] / sk[i];
+    R d0 = rms(tmp, n);
+    P.f(f0, u0, p, t);
+    for (int i = 0; i < n; ++i) if (std::isnan(f0[i])) return dtmin;                 // NAN_CHECK(f₀)
+    for (int i = 0; i < n; ++i) tmp[i] = f0[i] / sk[i];
+    R d1 = rms(tmp, n);
+    if (std::isnan(d1)) return dtmin;
+    R dt0;
+    // d₀ < 1//10^5: the binary64 literal 1e-5 lies above the rational, so for any
+    // binary64/binary32 operand "x < 1//10^5" == "(double)x < 1e-5"
+    if ((double)d0 < 1e-5 || (double)d1 < 1e-5) dt0 = smalldt;
+    else dt0 = (d0 / d1) / (R)100;
+    dt0 = jl_min(dt0, dtmax_tdir);
+    R dt0_tdir = dt0;
+    for (int i = 0; i < n; ++i) u1[i] = jl_fma(dt0_tdir, f0[i], u0[i]);
+    P.f(f1, u1, p, t + dt0_tdir);
+    bool eq = true;
+    for (int i = 0; i < n; ++i) eq = eq && (f0[i] == f1[i]);
+    if (eq) return jl_max(dtmin, (R)100 * dt0);
+    for (int i = 0; i < n; ++i) tmp[i] = (f1[i] - f0[i]) / sk[i];
+    R d2 = rms(tmp, n) / dt0;
+    R max_d1d2 = jl_max(d1, d2);
+    R dt1;
+    // max_d₁d₂ <= 1//Int64(10)^15: binary64 1e-15 lies above the rational => "<" on doubles
+    if ((double)max_d1d2 < 1e-15) dt1 = jl_max(smalldt, dt0 * (R)0.001);             // dt₀ * 1//10^3
+    else if (std::isinf(max_d1d2)) dt1 = (R)0;
+    else {
+        R l = (R)cr_log10((double)max_d1d2);
+        R e = -((R)2 + l) / (R)order;
+        dt1 = (R)cr_exp10((double)e);
+    }
+    return jl_max(dtmin, jl_min(jl_min((R)100 * dt0, dt1), dtmax_tdir));
+}
+
+// ---------------------------------------------------------------------------
+template <typename R> struct Out {
+    R* u_final; R* t_final; R* us; int nslots;
+    int *nsaved, *naccept, *nreject, *nf, *njacs, *nw, *nsolve, *retcode;
+};
+
+// One trajectory: __init + solve! + postamble!
+template <typename R, typename Alg>
+static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R tf, const Opts<R>& o, long long idx,
+                      const Out<R>& out) {
+    const int n = P.n;
+    Alg cache; cache.P = &P;
+    Stats<R> stats;
+    R u[ORACLE_MAXN], uprev[ORACLE_MAXN];
+    for (int i = 0; i < n; ++i) { u[i] = u0[i]; uprev[i] = u0[i]; }
+    R t = t0, tprev = t0;
+    const R dtmax = o.dtmax, opts_dtmin = o.dtmin;
+    int nsaved = 0, save_idx = 0;
+    R last_saved_t = t0;
+    auto emit = [&](R ts, const R* v) {
+        if (out.us && nsaved < out.nslots) {
+            R* dst = out.us + ((size_t)idx * out.nslots + nsaved) * n;
+            for (int i = 0; i < n; ++i) dst[i] = v[i];
+        }
+        nsaved += 1; last_saved_t = ts;
+    };
+    // save_start (solve.jl:809-824)
+    if (o.save_start) emit(t, u);
+    // initialize!(integrator, cache) (solve.jl:831)
+    if (Alg::fsal_init()) cache.initialize(uprev, p, t, stats);
+    // handle_dt! (solve.jl:968-985): automatic dt when dt == 0 and adaptive
+    R dt;
+    if (o.dt == (R)0) {
+        R dtmax_init = jl_min(std::fabs(dtmax), std::fabs(tf - t));     // _determine_initdt
+        dt = ode_initdt(P, u, p, t, dtmax_init, o.abstol, o.reltol, opts_dtmin, Alg::order);
+        stats.nf += 2;
+    } else dt = o.dt;
+    R dtpropose = dt;
+    // PIControllerCache (controllers.jl:793-803) and PIController defaults (alg_utils.jl)
+    const R beta2 = (R)(2.0 / (5.0 * Alg::order)), beta1 = (R)(7.0 / (10.0 * Alg::order));
+    const R qmin = (R)0.2, qmax = (R)10, gamma = (R)0.9, qoldinit = (R)1e-4, qmax_first_step = (R)10000;
+    const R qsteady_min = (R)1, qsteady_max = Alg::qsteady_max();
+    R q11 = (R)1, errold = qoldinit, EEst = (R)1;
+    long long iter = 0; int success_iter = 0, naccept = 0, nreject = 0;
+    bool accept_step = false, next_step_tstop = false;
+    R tstop_target = tf;
+    int retcode = RC_DEFAULT;
+
+    // modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch
+    auto modify_dt_for_tstops = [&]() {
+        R tdir_t = t, tdir_tstop = tf;
+        R distance_to_tstop = std::fabs(tdir_tstop - tdir_t);
+        R tstop_tol = (R)100 * jl_eps(jl_max(std::fabs(t), std::fabs(tdir_tstop)));
+        R original_dt = std::fabs(dt);
+        dtpropose = original_dt;
+        if (original_dt + tstop_tol < distance_to_tstop) next_step_tstop = false;
+        else { next_step_tstop = true; tstop_target = tdir_tstop; }
+        dt = jl_min(original_dt, distance_to_tstop);
+    };
+
+    // solve! (solve.jl:904-946); tstops = {tf}
+    while (t < tf) {
+        // ---- loopheader! (integrator_utils.jl:84-127)
+        if (iter > 0) {
+            if (accept_step) {
+                success_iter += 1;
+                // apply_step! (:175-203)
+                for (int i = 0; i < n; ++i) uprev[i] = u[i];
+                dt = dtpropose;
+                cache.update_fsal();
+                modify_dt_for_tstops();
+            } else {
+                // handle_step_rejection! -> step_reject_controller! (controllers.jl:838-843)
+                dt = dt / jl_min((R)1 / qmin, q11 / gamma);
+            }
+        }
+        iter += 1;
+        // fix_dt_at_bounds! (:1243-1256); timedepentdtmin = max(eps(t), dtmin)
+        dt = jl_min(dtmax, dt);
+        dt = jl_max(dt, jl_max(jl_eps(t), opts_dtmin));
+        modify_dt_for_tstops();
+        // ---- check_error (lib/DiffEqBase/src/check_error.jl:70-118)
+        {
+            int code = RC_SUCCESS;
+            if (std::isnan(dt)) code = RC_DTNAN;
+            else if (iter > o.maxiters) code = RC_MAXITERS;
+            else if (std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < tf)) code = RC_DTLESSTHANMIN;
+            else if (!accept_step && std::fabs(dt) <= std::fabs(jl_eps(t))) code = RC_UNSTABLE;
+            else if (accept_step) {
+                for (int i = 0; i < n; ++i) if (!Bits<R>::finite(u[i])) code = RC_UNSTABLE;
+            }
+            if (code != RC_SUCCESS) { retcode = code; break; }
+        }
+        // ---- perform_step! or handle_tstop_step! (:326-333)
+        if (next_step_tstop && std::fabs(dt) < jl_eps(std::fabs(t))) {
+            accept_step = true;
+        } else {
+            EEst = cache.perform_step(uprev, u, p, t, dt, o, stats, o.nsaveat > 0);
+        }
+        // ---- loopfooter! (:597-677)
+        R ttmp = t + dt;
+        // stepsize_controller!(integrator, ::PIControllerCache, alg) (controllers.jl:805-821)
+        R qmax_cur = (success_iter == 0) ? qmax_first_step : qmax;      // get_current_qmax (:288-293)
+        R q;
+        if (EEst == (R)0) q = (R)1 / qmax_cur;
+        else {
+            R q11_new = fastpower(EEst, beta1);
+            q = q11_new / fastpower(errold, beta2);
+            q11 = q11_new;
+            q = q / gamma;
+            R lo = (R)1 / qmax_cur, hi = (R)1 / qmin;
+            q = q < lo ? lo : (q > hi ? hi : q);
+        }
+        accept_step = (EEst <= (R)1);                                  // accept_step_controller (:245-250)
+        if (accept_step) {
+            naccept += 1;
+            tprev = t;
+            if (next_step_tstop) dt = dtpropose;                       // (:629-633)
+            if (next_step_tstop) { next_step_tstop = false; t = tstop_target; } else t = ttmp;   // fixed_t_for_tstop_error!
+            // step_accept_controller! (controllers.jl:823-836)
+            if (qsteady_min <= q && q <= qsteady_max) q = (R)1;
+            errold = jl_max(EEst, qoldinit);
+            R dtnew = dt / q;
+            // calc_dt_propose! (:1199-1210)
+            dtpropose = jl_min(std::fabs(dtmax), std::fabs(dtnew));
+            dtpropose = jl_max(std::fabs(dtpropose), jl_max(jl_eps(t), opts_dtmin));
+            // handle_callbacks! -> savevalues! (:340-414)
+            bool added = false;
+            while (save_idx < o.nsaveat && o.saveat[save_idx] <= t) {
+                R curt = o.saveat[save_idx++];
+                if (curt != t) {
+                    R Theta = (curt - tprev) / dt;
+                    if (!added) { cache.addsteps(uprev, u, p, tprev, dt); added = true; }
+                    R val[ORACLE_MAXN];
+                    cache.interpolant(Theta, dt, uprev, u, val);
+                    emit(curt, val);
+                } else {
+                    if (curt == tf && !o.save_end) continue;           // skip_saveat_at_tspan_end
+                    emit(t, u);
+                }
+            }
+        } else {
+            nreject += 1;
+        }
+    }
+    // postamble! -> solution_endpoint_match_cur_integrator! (:540-587)
+    if (o.save_end &&
+        (nsaved == 0 || (last_saved_t != t && (o.save_end_user || t == tf || o.nsaveat == 0))))
+        emit(t, u);
+    if (retcode == RC_DEFAULT) retcode = RC_SUCCESS;
+    for (int i = 0; i < n; ++i) out.u_final[(size_t)idx * n + i] = u[i];
+    if (out.t_final) out.t_final[idx] = t;
+    if (out.nsaved) out.nsaved[idx] = nsaved;
+    if (out.naccept) out.naccept[idx] = naccept;
+    if (out.nreject) out.nreject[idx] = nreject;
+    if (out.nf) out.nf[idx] = stats.nf;
+    if (out.njacs) out.njacs[idx] = stats.njacs;
+    if (out.nw) out.nw[idx] = stats.nw;
+    if (out.nsolve) out.nsolve[idx] = stats.nsolve;
+    if (out.retcode) out.retcode[idx] = retcode;
+}
+
+template <typename R, typename Alg>
+static void solve_batch(const ProblemFns<R>& P, long long N, const R* u0, int u0_shared, const R* p, int p_shared, R t0,
+                        R tf, const Opts<R>& o, const Out<R>& out, int nthreads) {
+    // the structural analogue of EnsembleThreads' Threads.@threads over trajectories
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+    for (long long i = 0; i < N; ++i) {
+        const R* ui = u0_shared ? u0 : u0 + (size_t)i * P.n;
+        const R* pi = p_shared ? p : p + (size_t)i * P.np;
+        solve_one<R, Alg>(P, ui, pi, t0, tf, o, i, out);
+    }
+}
+
+struct OracleArgs {
+    int alg, dtype, n, np;
+    void *rhs, *jac, *tgrad;
+    long long N;
+    const void* u0; int u0_shared;
+    const void* p; int p_shared;
+    double t0, tf;
+    double reltol, abstol, dt, dtmin, dtmax;
+    long long maxiters;
+    const double* saveat; int nsaveat;
+    int save_start, save_end;     // -1 default
+    int linsolve;
+    int nthreads;
+    // outputs
+    void* u_final; void* t_final; void* us; int nslots;
+    int *nsaved, *naccept, *nreject, *nf, *njacs, *nw, *nsolve, *retcode;
+};
+
+template <typename R> static int run(const OracleArgs& a) {
+    ProblemFns<R> P;
+    P.f = (typename Fn<R>::rhs_t)a.rhs; P.jac = (typename Fn<R>::rhs_t)a.jac; P.tgrad = (typename Fn<R>::rhs_t)a.tgrad;
+    P.n = a.n; P.np = a.np;
+    std::vector<R> grid(a.nsaveat > 0 ? a.nsaveat : 0);
+    for (int i = 0; i < a.nsaveat; ++i) grid[i] = (R)a.saveat[i];
+    Opts<R> o;
+    o.reltol = (R)(a.reltol > 0 ? a.reltol : 1e-3);
+    o.abstol = (R)(a.abstol > 0 ? a.abstol : 1e-6);
+    o.dt = (R)a.dt; o.dtmin = (R)a.dtmin;
+    o.dtmax = (R)(a.dtmax > 0 ? a.dtmax : (a.tf - a.t0));
+    o.maxiters = a.maxiters > 0 ? a.maxiters : 1000000;
+    o.saveat = grid.data(); o.nsaveat = a.nsaveat;
+    o.save_start = a.save_start != 0;
+    o.save_end = a.save_end != 0;
+    o.save_end_user = a.save_end > 0;
+    o.linsolve = a.linsolve;
+    Out<R> out;
+    out.u_final = (R*)a.u_final; out.t_final = (R*)a.t_final; out.us = (R*)a.us; out.nslots = a.nslots;
+    out.nsaved = a.nsaved; out.naccept = a.naccept; out.nreject = a.nreject; out.nf = a.nf;
+    out.njacs = a.njacs; out.nw = a.nw; out.nsolve = a.nsolve; out.retcode = a.retcode;
+    const R* u0 = (const R*)a.u0; const R* p = (const R*)a.p;
+    switch (a.alg) {
+        case ALG_TSIT5: solve_batch<R, Tsit5<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
+#ifdef ORACLE_HAVE_VERN7
+        case ALG_VERN7: solve_batch<R, Vern7<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
+#endif
+#ifdef ORACLE_HAVE_ROSENBROCK
+        case ALG_ROS23: solve_batch<R, Rosenbrock23<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
+        case ALG_RODAS5P: solve_batch<R, Rodas5P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
+#endif
+        default: return -2;
+    }
+    return 0;
+}
+
+extern "C" {
+int oracle_solve(const OracleArgs* a) {
+    if (!a || a->n < 1 || a->n > ORACLE_MAXN || !a->rhs) return -1;
+    return a->dtype == 1 ? run<float>(*a) : run<double>(*a);
+}
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+// scalar entry points for the known-answer tests
+double oracle_fastpower(double x, double y) { return fastpower(x, y); }
+float oracle_fastpower_f32(float x, float y) { return fastpower(x, y); }
+double oracle_norm(const double* v, int n) { return rms(v, n); }
+double oracle_eps(double x) { return jl_eps(x); }
+double oracle_log10(double x) { return cr_log10(x); }
+double oracle_exp10(double x) { return cr_exp10(x); }
+double oracle_initdt(void* rhs, int n, int np, const double* u0, const double* p, double t0, double tf, double abstol,
+                     double reltol, int order) {
+    ProblemFns<double> P; P.f = (Fn<double>::rhs_t)rhs; P.n = n; P.np = np;
+    return ode_initdt<double>(P, u0, p, t0, tf - t0, abstol, reltol, 0.0, order);
+}
+}

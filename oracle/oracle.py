@@ -1,0 +1,178 @@
+"""ctypes front end of the CPU oracle (oracle.cpp).  TEST INFRASTRUCTURE ONLY — see the
+header of oracle.cpp.  Imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by the package.
+
+The user's RHS/Jacobian C source (the same text the GPU path hands to NVRTC) is compiled
+here with gcc, without floating-point contraction, into a small shared object whose
+function pointers are passed to oracle_solve.
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_BUILD = os.path.join(_HERE, "_build")
+_GCC_B = "-B/usr/lib/gcc/x86_64-linux-gnu/13"
+
+ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P = 1, 2, 3, 4
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".inc"))]
+    if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT)
+    return _LIB
+
+
+class OracleArgs(C.Structure):
+    _fields_ = [("alg", C.c_int), ("dtype", C.c_int), ("n", C.c_int), ("np", C.c_int),
+                ("rhs", C.c_void_p), ("jac", C.c_void_p), ("tgrad", C.c_void_p),
+                ("N", C.c_longlong),
+                ("u0", C.c_void_p), ("u0_shared", C.c_int),
+                ("p", C.c_void_p), ("p_shared", C.c_int),
+                ("t0", C.c_double), ("tf", C.c_double),
+                ("reltol", C.c_double), ("abstol", C.c_double), ("dt", C.c_double), ("dtmin", C.c_double),
+                ("dtmax", C.c_double), ("maxiters", C.c_longlong),
+                ("saveat", C.c_void_p), ("nsaveat", C.c_int),
+                ("save_start", C.c_int), ("save_end", C.c_int),
+                ("linsolve", C.c_int), ("nthreads", C.c_int),
+                ("u_final", C.c_void_p), ("t_final", C.c_void_p), ("us", C.c_void_p), ("nslots", C.c_int),
+                ("nsaved", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p), ("nf", C.c_void_p),
+                ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.oracle_solve.argtypes = [C.POINTER(OracleArgs)]
+        L.oracle_fastpower.restype = C.c_double
+        L.oracle_fastpower.argtypes = [C.c_double, C.c_double]
+        L.oracle_fastpower_f32.restype = C.c_float
+        L.oracle_fastpower_f32.argtypes = [C.c_float, C.c_float]
+        L.oracle_norm.restype = C.c_double
+        L.oracle_norm.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_eps.restype = C.c_double
+        L.oracle_eps.argtypes = [C.c_double]
+        L.oracle_log10.restype = C.c_double
+        L.oracle_log10.argtypes = [C.c_double]
+        L.oracle_exp10.restype = C.c_double
+        L.oracle_exp10.argtypes = [C.c_double]
+        L.oracle_initdt.restype = C.c_double
+        L.oracle_initdt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                    C.c_double, C.c_double, C.c_int]
+        _lib = L
+    return _lib
+
+
+_user_libs = {}
+
+
+def compile_user(sources):
+    """sources: list of C source strings.  Returns a CDLL with the functions."""
+    text = "\n".join(s for s in sources if s)
+    key = hashlib.sha1(text.encode()).hexdigest()[:16]
+    if key in _user_libs:
+        return _user_libs[key]
+    os.makedirs(_BUILD, exist_ok=True)
+    c_path = os.path.join(_BUILD, "user_%s.c" % key)
+    so_path = os.path.join(_BUILD, "user_%s.so" % key)
+    if not os.path.exists(so_path):
+        with open(c_path, "w") as f:
+            f.write("#include <math.h>\n" + text)
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-o", so_path,
+                        c_path, "-lm"], check=True)
+    L = C.CDLL(so_path)
+    _user_libs[key] = L
+    return L
+
+
+def fn_ptr(user_lib, name):
+    return C.cast(getattr(user_lib, name), C.c_void_p).value
+
+
+def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
+    """Rows per trajectory (mirrors solve.jl:141-142,596-599 + skip_saveat_at_tspan_end)."""
+    if saveat is None or len(saveat) == 0:
+        return 0
+    ss = 1 if (save_start is None or save_start) else 0
+    se = 1 if (save_end is None or save_end) else 0
+    has_tf = (saveat[-1] == tf)
+    slots = ss + len(saveat)
+    if has_tf and not se:
+        slots -= 1
+    if not has_tf and se:
+        slots += 1
+    return slots
+
+
+def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
+          abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
+          linsolve=0, nthreads=0):
+    """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host."""
+    L = lib()
+    rdt = np.float32 if f32 else np.float64
+    user = compile_user([rhs[0], jac[0] if jac else None, tgrad[0] if tgrad else None])
+    u0 = np.ascontiguousarray(u0, dtype=rdt)
+    u0_shared = u0.ndim == 1
+    p_arr = None if p is None else np.ascontiguousarray(p, dtype=rdt)
+    p_shared = True if p_arr is None else p_arr.ndim == 1
+    if trajectories is None:
+        trajectories = u0.shape[0] if not u0_shared else p_arr.shape[0]
+    N = int(trajectories)
+    t0, tf = float(tspan[0]), float(tspan[1])
+    grid = None if saveat is None or len(saveat) == 0 else np.ascontiguousarray(saveat, dtype=np.float64)
+    nslots = nslots_for(t0, tf, grid, save_start, save_end)
+    out = {
+        "u_final": np.zeros((N, n), dtype=rdt), "t_final": np.zeros((N,), dtype=rdt),
+        "us": np.zeros((N, nslots, n), dtype=rdt) if nslots > 0 else None,
+    }
+    for k in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
+        out[k] = np.zeros((N,), dtype=np.int32)
+    a = OracleArgs()
+    a.alg, a.dtype, a.n, a.np = alg, int(f32), n, np_
+    a.rhs = fn_ptr(user, rhs[1])
+    a.jac = fn_ptr(user, jac[1]) if jac else None
+    a.tgrad = fn_ptr(user, tgrad[1]) if tgrad else None
+    a.N = N
+    a.u0 = u0.ctypes.data; a.u0_shared = int(u0_shared)
+    a.p = p_arr.ctypes.data if p_arr is not None else None; a.p_shared = int(p_shared)
+    a.t0, a.tf = t0, tf
+    a.reltol = reltol or 0.0; a.abstol = abstol or 0.0; a.dt = dt or 0.0; a.dtmin = dtmin or 0.0
+    a.dtmax = dtmax or 0.0; a.maxiters = maxiters or 0
+    a.saveat = grid.ctypes.data if grid is not None else None
+    a.nsaveat = 0 if grid is None else len(grid)
+    a.save_start = -1 if save_start is None else int(bool(save_start))
+    a.save_end = -1 if save_end is None else int(bool(save_end))
+    a.linsolve = linsolve; a.nthreads = nthreads
+    a.u_final = out["u_final"].ctypes.data; a.t_final = out["t_final"].ctypes.data
+    a.us = out["us"].ctypes.data if out["us"] is not None else None
+    a.nslots = nslots
+    for k in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
+        setattr(a, k, out[k].ctypes.data)
+    rc = L.oracle_solve(C.byref(a))
+    if rc != 0:
+        raise RuntimeError("oracle_solve failed: %d" % rc)
+    out["nslots"] = nslots
+    if nslots > 0:
+        ts = []
+        if save_start is None or save_start:
+            ts.append(t0)
+        for s in grid:
+            if s == tf and not (save_end is None or save_end):
+                continue
+            ts.append(float(rdt(s)))
+        if len(ts) < nslots:
+            ts.append(tf)
+        out["ts"] = np.array(ts)
+    out["t_final"] = out["t_final"].astype(np.float64)
+    return out

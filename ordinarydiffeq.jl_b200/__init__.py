@@ -1,0 +1,9 @@
+"""ordinarydiffeq.jl_b200 — B200-native ensemble ODE path behind the reference's
+`solve(EnsembleProblem, alg, ensemblealg; ...)` interface.
+
+The directory name contains a dot, so it is imported through `b200_import.load()`
+(repo root) which registers it as the module `ordinarydiffeq_jl_b200`.
+"""
+from . import _lib, codegen, lowlevel, problems_library  # noqa: F401
+from ._lib import (ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P, F32, F64, B200Error, Handle,  # noqa: F401
+                   compile_only)

@@ -1,0 +1,221 @@
+"""ctypes binding of include/b200ode.h (libb200ode.so, built in-tree by csrc/build.py).
+
+There is deliberately no fallback: if the shared library is missing, or no sm_100
+device is present when a solve is requested, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200ode.so")
+
+ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P = 1, 2, 3, 4
+F64, F32 = 0, 1
+LAYOUT_AOS, LAYOUT_SOA = 0, 1
+FLAG_STATIC_SCHEDULE = 1
+RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN = range(6)
+RETCODE_NAMES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "DtLessThanMin", 4: "Unstable", 5: "DtNaN"}
+OK, EINVAL, ECOMPILE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200ode error %d: %s" % (code, msg))
+        self.code = code
+
+
+class B200Problem(C.Structure):
+    _fields_ = [("trajectories", C.c_int64), ("u0", C.c_void_p), ("u0_shared", C.c_int32),
+                ("p", C.c_void_p), ("p_shared", C.c_int32), ("t0", C.c_double), ("tf", C.c_double)]
+
+
+class B200Opts(C.Structure):
+    _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("dt", C.c_double), ("dtmin", C.c_double),
+                ("dtmax", C.c_double), ("maxiters", C.c_int64), ("saveat", C.POINTER(C.c_double)),
+                ("nsaveat", C.c_int32), ("save_start", C.c_int32), ("save_end", C.c_int32),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class B200Result(C.Structure):
+    _fields_ = [("u_final", C.c_void_p), ("t_final", C.c_void_p), ("us", C.c_void_p), ("ts", C.c_void_p),
+                ("nsaved", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p), ("nf", C.c_void_p),
+                ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p),
+                ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+
+
+class B200DeviceProblem(C.Structure):
+    _fields_ = [("trajectories", C.c_int64), ("u0", C.c_void_p), ("u0_shared", C.c_int32), ("u0_layout", C.c_int32),
+                ("p", C.c_void_p), ("p_shared", C.c_int32), ("p_layout", C.c_int32),
+                ("t0", C.c_double), ("tf", C.c_double)]
+
+
+class B200DeviceResult(C.Structure):
+    _fields_ = [("u_final", C.c_void_p), ("u_final_layout", C.c_int32), ("pad0", C.c_int32),
+                ("t_final", C.c_void_p), ("us", C.c_void_p),
+                ("nsaved", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p), ("nf", C.c_void_p),
+                ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p)]
+
+
+class B200ProgramInfo(C.Structure):
+    _fields_ = [("regs_integrate", C.c_int32), ("regs_initdt", C.c_int32),
+                ("local_bytes_integrate", C.c_int32), ("local_bytes_initdt", C.c_int32),
+                ("smem_bytes_integrate", C.c_int32), ("block", C.c_int32), ("blocks_per_sm", C.c_int32),
+                ("grid", C.c_int32), ("cubin_bytes", C.c_int64), ("compile_ms", C.c_double)]
+
+
+# every symbol include/b200ode.h declares (tests/test_abi.py checks the export list)
+EXPORTS = [
+    "b200ode_create", "b200ode_destroy", "b200ode_last_error", "b200ode_version",
+    "b200ode_compile", "b200ode_program_destroy", "b200ode_program_info",
+    "b200ode_compile_only", "b200ode_free", "b200ode_nslots", "b200ode_solve", "b200ode_solve_device",
+    "b200ode_reduce_sum_device", "b200ode_host_register", "b200ode_host_unregister",
+    "b200ode_measure_fma_peak",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libb200ode.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libb200ode.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, cp, i32, i64, dbl = C.c_void_p, C.c_char_p, C.c_int, C.c_int64, C.c_double
+    L.b200ode_create.argtypes = [C.POINTER(vp), i32]
+    L.b200ode_destroy.argtypes = [vp]
+    L.b200ode_last_error.argtypes = [vp]
+    L.b200ode_last_error.restype = cp
+    L.b200ode_version.restype = cp
+    L.b200ode_compile.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, cp, cp, cp, cp, cp, cp, cp]
+    L.b200ode_program_destroy.argtypes = [vp]
+    L.b200ode_program_info.argtypes = [vp, C.POINTER(B200ProgramInfo)]
+    L.b200ode_compile_only.argtypes = [i32, i32, i32, i32, cp, cp, cp, cp, cp, cp, cp,
+                                       C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
+    L.b200ode_free.argtypes = [vp]
+    L.b200ode_free.restype = None
+    L.b200ode_nslots.argtypes = [C.POINTER(B200Problem), C.POINTER(B200Opts)]
+    L.b200ode_solve.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(B200Result)]
+    L.b200ode_solve_device.argtypes = [vp, vp, C.POINTER(B200DeviceProblem), C.POINTER(B200Opts),
+                                       C.POINTER(B200DeviceResult), vp]
+    L.b200ode_reduce_sum_device.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp]
+    L.b200ode_host_register.argtypes = [vp, C.c_size_t]
+    L.b200ode_host_unregister.argtypes = [vp]
+    L.b200ode_measure_fma_peak.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().b200ode_last_error(None)
+        raise B200Error(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def _b(s):
+    return None if s is None else s.encode("utf-8")
+
+
+def compile_only(alg, dtype, n, np_, rhs_src, rhs_name, jac_src=None, jac_name=None, tgrad_src=None,
+                 tgrad_name=None, extra_options=None):
+    """NVRTC-compile without a GPU; returns (cubin_bytes, log)."""
+    L = lib()
+    cubin = C.c_void_p()
+    size = C.c_size_t()
+    log = C.c_void_p()
+    rc = L.b200ode_compile_only(alg, dtype, n, np_, _b(rhs_src), _b(rhs_name), _b(jac_src), _b(jac_name),
+                                _b(tgrad_src), _b(tgrad_name), _b(extra_options),
+                                C.byref(cubin), C.byref(size), C.byref(log))
+    log_s = C.string_at(log.value).decode("utf-8", "replace") if log.value else ""
+    if log.value:
+        L.b200ode_free(log)
+    if rc != 0:
+        if cubin.value:
+            L.b200ode_free(cubin)
+        raise B200Error(rc, log_s or L.b200ode_last_error(None).decode())
+    data = C.string_at(cubin.value, size.value)
+    L.b200ode_free(cubin)
+    return data, log_s
+
+
+class Handle:
+    """One per process per GPU (b200ode_create)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib().b200ode_create(C.byref(self._h), int(device)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            lib().b200ode_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compile(self, alg, dtype, n, np_, rhs_src, rhs_name, jac_src=None, jac_name=None, tgrad_src=None,
+                tgrad_name=None, extra_options=None):
+        return Program(self, alg, dtype, n, np_, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
+                       extra_options)
+
+    def measure_fma_peak(self, dtype=F64):
+        tf, mhz = C.c_double(), C.c_double()
+        check(lib().b200ode_measure_fma_peak(self._h, dtype, C.byref(tf), C.byref(mhz)))
+        return tf.value, mhz.value
+
+
+class Program:
+    def __init__(self, handle, alg, dtype, n, np_, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
+                 extra_options):
+        self.handle = handle
+        self.alg, self.dtype, self.n, self.np = alg, dtype, n, np_
+        self._p = C.c_void_p()
+        check(lib().b200ode_compile(handle._h, C.byref(self._p), alg, dtype, n, np_, _b(rhs_src), _b(rhs_name),
+                                    _b(jac_src), _b(jac_name), _b(tgrad_src), _b(tgrad_name), _b(extra_options)))
+        info = B200ProgramInfo()
+        check(lib().b200ode_program_info(self._p, C.byref(info)))
+        self.info = {k: getattr(info, k) for k, _ in B200ProgramInfo._fields_}
+
+    def close(self):
+        if self._p:
+            lib().b200ode_program_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_opts(reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None,
+              save_start=None, save_end=None, flags=0):
+    """Returns (B200Opts, keepalive)."""
+    import numpy as np
+    o = B200Opts()
+    o.reltol = float(reltol) if reltol is not None else 0.0
+    o.abstol = float(abstol) if abstol is not None else 0.0
+    o.dt = float(dt) if dt is not None else 0.0
+    o.dtmin = float(dtmin) if dtmin is not None else 0.0
+    o.dtmax = float(dtmax) if dtmax is not None else 0.0
+    o.maxiters = int(maxiters) if maxiters is not None else 0
+    keep = None
+    if saveat is not None and len(saveat) > 0:
+        keep = np.ascontiguousarray(saveat, dtype=np.float64)
+        o.saveat = keep.ctypes.data_as(C.POINTER(C.c_double))
+        o.nsaveat = int(keep.shape[0])
+    else:
+        o.saveat = None
+        o.nsaveat = 0
+    o.save_start = -1 if save_start is None else int(bool(save_start))
+    o.save_end = -1 if save_end is None else int(bool(save_end))
+    o.flags = int(flags)
+    return o, keep

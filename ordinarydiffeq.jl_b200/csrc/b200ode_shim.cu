@@ -1,0 +1,699 @@
+// b200ode_shim.cu — the C ABI of include/b200ode.h.
+//
+// Host side of the ensemble hot path: NVRTC-compiles the user's RHS/Jacobian C
+// source together with the stepper kernels (device/*.cuh, embedded at build time
+// in device_sources.inc), loads the cubin through the CUDA runtime's library API,
+// lays the ensemble out in HBM and launches b200_initdt + b200_integrate.
+// There is no CPU fallback anywhere in this file: without a device every solving
+// entry point fails with B200ODE_ECUDA.
+#include "../../include/b200ode.h"
+
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_sources.inc"   // k_b200_header_names[], k_b200_header_sources[], k_b200_num_headers
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(B200ODE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+// Mirror of struct B200Params in device/b200_ensemble.cuh (same member order and types).
+template <typename R>
+struct Params {
+    long long N;
+    const R* u0; long long u0_ts, u0_cs;
+    const R* p; long long p_ts, p_cs;
+    R t0, tf;
+    R reltol, abstol;
+    R dt_user;
+    R dtmin, dtmax;
+    long long maxiters;
+    const R* saveat;
+    int nsaveat;
+    int save_start, save_end;
+    int nslots;
+    R* dt0;
+    R* u_final; long long uf_ts, uf_cs;
+    R* t_final;
+    R* us;
+    int* naccept; int* nreject; int* nf; int* retcode; int* nsaved;
+    int* njacs; int* nw; int* nsolve;
+    unsigned long long* work_counter;
+    int flags;
+};
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&ptr, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct b200ode_handle_s {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;       // compute + H2D
+    cudaStream_t copy_stream = nullptr;  // D2H of finished chunks
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    // scratch owned by the handle (grow-only)
+    DevBuf counter, dt0, saveat, scratch_t;
+    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial;
+};
+
+struct b200ode_program_s {
+    b200ode_handle h = nullptr;
+    int alg = 0, dtype = 0, n = 0, np = 0;
+    std::vector<char> cubin;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t k_integrate = nullptr, k_initdt = nullptr;
+    B200ProgramInfo info{};
+};
+
+namespace {
+
+std::string strip_includes(const char* src) {
+    std::string out;
+    if (!src) return out;
+    const char* s = src;
+    while (*s) {
+        const char* e = strchr(s, '\n');
+        size_t len = e ? (size_t)(e - s) : strlen(s);
+        std::string line(s, len);
+        size_t i = line.find_first_not_of(" \t");
+        bool is_inc = (i != std::string::npos && line.compare(i, 1, "#") == 0 &&
+                       line.find("include", i) != std::string::npos);
+        if (!is_inc) { out += line; }
+        out += '\n';
+        if (!e) break;
+        s = e + 1;
+    }
+    return out;
+}
+
+bool is_identifier(const char* s) {
+    if (!s || !*s) return false;
+    if (!(isalpha((unsigned char)s[0]) || s[0] == '_')) return false;
+    for (const char* c = s; *c; ++c)
+        if (!(isalnum((unsigned char)*c) || *c == '_')) return false;
+    return true;
+}
+
+int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
+                          const char* jac_src, const char* jac_name, const char* tgrad_src,
+                          const char* tgrad_name) {
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS5P)
+        return fail(B200ODE_EINVAL, "alg must be one of B200ODE_ALG_{TSIT5,VERN7,ROSENBROCK23,RODAS5P}");
+    if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
+    if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");
+    if (np < 0 || np > 256) return fail(B200ODE_EINVAL, "parameter dimension np must be in 0..256");
+    if (!rhs_src || !is_identifier(rhs_name)) return fail(B200ODE_EINVAL, "rhs_src and a valid rhs_name are required");
+    bool stiff = (alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_RODAS5P);
+    if (stiff) {
+        if (!jac_src || !is_identifier(jac_name))
+            return fail(B200ODE_EINVAL, "Rosenbrock algorithms need jac_src/jac_name (ODEFunction(f; jac, tgrad))");
+        if (tgrad_src && !is_identifier(tgrad_name)) return fail(B200ODE_EINVAL, "tgrad_name is not an identifier");
+    }
+    return B200ODE_OK;
+}
+
+// Assemble the translation unit and run NVRTC.
+int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
+                const char* jac_src, const char* jac_name, const char* tgrad_src, const char* tgrad_name,
+                const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms) {
+    int rc = validate_compile_args(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name);
+    if (rc) return rc;
+    bool stiff = (alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_RODAS5P);
+    auto t_begin = std::chrono::steady_clock::now();
+
+    std::string tu;
+    tu += "#define B200_N " + std::to_string(n) + "\n";
+    tu += "#define B200_NP " + std::to_string(np) + "\n";
+    tu += "#define B200_F32 " + std::to_string(dtype == B200ODE_F32 ? 1 : 0) + "\n";
+    tu += "#define B200_ALG " + std::to_string(alg) + "\n";
+    tu += "#include \"b200_base.cuh\"\n";
+    // forward declarations make the user's functions __device__ __forceinline__
+    // (their definitions carry no execution-space annotation: -default-device)
+    tu += std::string("__device__ __forceinline__ void ") + rhs_name +
+          "(real* du, const real* u, const real* p, const real t);\n";
+    if (stiff) {
+        tu += std::string("__device__ __forceinline__ void ") + jac_name +
+              "(real* J, const real* u, const real* p, const real t);\n";
+        if (tgrad_src)
+            tu += std::string("__device__ __forceinline__ void ") + tgrad_name +
+                  "(real* dT, const real* u, const real* p, const real t);\n";
+    }
+    tu += "// ---- user source (RHS) ----\n";
+    tu += strip_includes(rhs_src);
+    if (stiff) {
+        tu += "// ---- user source (Jacobian) ----\n";
+        tu += strip_includes(jac_src);
+        if (tgrad_src) {
+            tu += "// ---- user source (time gradient) ----\n";
+            tu += strip_includes(tgrad_src);
+        }
+    }
+    tu += "// ---- steppers ----\n";
+    tu += std::string("#define B200_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
+    if (stiff) {
+        tu += std::string("#define B200_JAC(J,u,p,t) ") + jac_name + "((J),(u),(p),(t))\n";
+        if (tgrad_src) tu += std::string("#define B200_TGRAD(dT,u,p,t) ") + tgrad_name + "((dT),(u),(p),(t))\n";
+    }
+    tu += "#include \"b200_ensemble.cuh\"\n";
+
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, tu.c_str(), "b200_ensemble_tu.cu", k_b200_num_headers,
+                                       k_b200_header_sources, k_b200_header_names);
+    if (r != NVRTC_SUCCESS) return fail(B200ODE_ECOMPILE, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
+
+    std::vector<std::string> opts = {
+        "--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-default-device",
+        "-lineinfo", "--ptxas-options=-v",
+    };
+    // launch bounds: small systems keep everything in registers at 4 CTAs x 128 threads per SM
+    bool has_block = false, has_minb = false;
+    if (extra_options) {
+        std::string eo(extra_options);
+        size_t pos = 0;
+        while (pos < eo.size()) {
+            size_t sp = eo.find(' ', pos);
+            std::string tok = eo.substr(pos, sp == std::string::npos ? std::string::npos : sp - pos);
+            if (!tok.empty()) {
+                opts.push_back(tok);
+                if (tok.rfind("-DB200_BLOCK=", 0) == 0) has_block = true;
+                if (tok.rfind("-DB200_MINBLOCKS=", 0) == 0) has_minb = true;
+            }
+            if (sp == std::string::npos) break;
+            pos = sp + 1;
+        }
+    }
+    int words = n * (dtype == B200ODE_F32 ? 1 : 2);
+    if (!has_block) opts.push_back("-DB200_BLOCK=128");
+    if (!has_minb) {
+        // registers available per thread at k CTAs of 128 threads: 65536/(128k)
+        int minb = 4;
+        if (stiff) minb = (words <= 8) ? 3 : 1;
+        else if (alg == B200ODE_ALG_VERN7) minb = (words <= 6) ? 3 : 1;
+        else minb = (words <= 8) ? 4 : (words <= 16 ? 2 : 1);
+        opts.push_back("-DB200_MINBLOCKS=" + std::to_string(minb));
+    }
+    std::vector<const char*> copts;
+    for (auto& o : opts) copts.push_back(o.c_str());
+    r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+    size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    log.assign(log_size > 0 ? log_size : 1, '\0');
+    if (log_size > 0) nvrtcGetProgramLog(prog, &log[0]);
+    while (!log.empty() && log.back() == '\0') log.pop_back();
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return fail(B200ODE_ECOMPILE, std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + log);
+    }
+    size_t sz = 0;
+    r = nvrtcGetCUBINSize(prog, &sz);
+    if (r != NVRTC_SUCCESS || sz == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(B200ODE_ECOMPILE, "NVRTC produced no cubin");
+    }
+    cubin.resize(sz);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return B200ODE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// AOT kernels (compiled by nvcc into this library)
+
+// deterministic per-component sum: fixed grid, fixed tree order
+template <typename R>
+__global__ void __launch_bounds__(256) k_reduce_partial(const R* __restrict__ x, long long ts, long long cs,
+                                                        long long count, int n, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    for (int c = 0; c < n; ++c) {
+        double acc = 0.0;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+             i += (long long)gridDim.x * blockDim.x)
+            acc += (double)x[i * ts + c * cs];
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) partial[(size_t)blockIdx.x * n + c] = sh[0];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__ partial, int nblocks, int n,
+                                                      double* __restrict__ out) {
+    __shared__ double sh[256];
+    for (int c = 0; c < n; ++c) {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc += partial[(size_t)b * n + c];
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[c] = sh[0];
+        __syncthreads();
+    }
+}
+
+// FMA-pipe peak: 8 independent dependent chains per thread, register resident
+template <typename R>
+__global__ void __launch_bounds__(256) k_fma_peak(R* out, int iters, R a, R b) {
+    R x0 = (R)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    R s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (R)123456789) out[0] = s;   // never true; keeps the chains alive
+}
+
+template <typename R>
+int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
+                 B200DeviceResult* dr, cudaStream_t stream) {
+    const int n = prog->n, np = prog->np;
+    const long long N = dp->trajectories;
+    Params<R> P{};
+    P.N = N;
+    P.u0 = (const R*)dp->u0;
+    if (dp->u0_shared) { P.u0_ts = 0; P.u0_cs = 1; }
+    else if (dp->u0_layout == B200ODE_LAYOUT_SOA) { P.u0_ts = 1; P.u0_cs = N; }
+    else { P.u0_ts = n; P.u0_cs = 1; }
+    P.p = (const R*)dp->p;
+    if (dp->p_shared) { P.p_ts = 0; P.p_cs = 1; }
+    else if (dp->p_layout == B200ODE_LAYOUT_SOA) { P.p_ts = 1; P.p_cs = N; }
+    else { P.p_ts = np; P.p_cs = 1; }
+    P.t0 = (R)dp->t0; P.tf = (R)dp->tf;
+    P.reltol = (R)(o->reltol > 0 ? o->reltol : 1e-3);
+    P.abstol = (R)(o->abstol > 0 ? o->abstol : 1e-6);
+    P.dt_user = (R)o->dt;
+    P.dtmin = (R)o->dtmin;
+    P.dtmax = (R)(o->dtmax > 0 ? o->dtmax : (dp->tf - dp->t0));
+    P.maxiters = o->maxiters > 0 ? o->maxiters : 1000000;
+    P.nsaveat = o->saveat ? o->nsaveat : 0;
+    P.save_start = (o->save_start != 0) ? 1 : 0;
+    P.save_end = (o->save_end < 0) ? 1 : (o->save_end ? 2 : 0);
+    B200Problem hp{}; hp.t0 = dp->t0; hp.tf = dp->tf;
+    P.nslots = dr->us ? b200ode_nslots(&hp, o) : 0;
+    P.saveat = nullptr;
+    if (P.nsaveat > 0) {
+        // the grid travels as real[] in the handle's scratch
+        std::vector<R> grid(P.nsaveat);
+        for (int i = 0; i < P.nsaveat; ++i) grid[i] = (R)o->saveat[i];
+        CUDA_TRY(h->saveat.ensure(sizeof(R) * P.nsaveat));
+        CUDA_TRY(cudaMemcpyAsync(h->saveat.ptr, grid.data(), sizeof(R) * P.nsaveat, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));   // grid is a stack-lifetime host vector
+        P.saveat = (const R*)h->saveat.ptr;
+    }
+    CUDA_TRY(h->dt0.ensure(sizeof(R) * (size_t)N));
+    P.dt0 = (R*)h->dt0.ptr;
+    P.u_final = (R*)dr->u_final;
+    if (dr->u_final_layout == B200ODE_LAYOUT_SOA) { P.uf_ts = 1; P.uf_cs = N; } else { P.uf_ts = n; P.uf_cs = 1; }
+    P.t_final = (R*)dr->t_final;
+    P.us = (R*)dr->us;
+    P.naccept = dr->naccept; P.nreject = dr->nreject; P.nf = dr->nf; P.retcode = dr->retcode; P.nsaved = dr->nsaved;
+    P.njacs = dr->njacs; P.nw = dr->nw; P.nsolve = dr->nsolve;
+    CUDA_TRY(h->counter.ensure(sizeof(unsigned long long)));
+    P.work_counter = (unsigned long long*)h->counter.ptr;
+    P.flags = o->flags;
+    CUDA_TRY(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned long long), stream));
+
+    void* args[] = {&P};
+    if (o->dt == 0.0) {
+        unsigned g = (unsigned)((N + 255) / 256);
+        CUDA_TRY(cudaLaunchKernel((const void*)prog->k_initdt, dim3(g), dim3(256), args, 0, stream));
+    }
+    unsigned grid;
+    if (o->flags & B200ODE_FLAG_STATIC_SCHEDULE) grid = (unsigned)((N + prog->info.block - 1) / prog->info.block);
+    else {
+        grid = (unsigned)prog->info.grid;
+        long long need = (N + prog->info.block - 1) / prog->info.block;
+        if ((long long)grid > need) grid = (unsigned)(need > 0 ? need : 1);
+    }
+    CUDA_TRY(cudaLaunchKernel((const void*)prog->k_integrate, dim3(grid), dim3(prog->info.block), args, 0, stream));
+    return B200ODE_OK;
+}
+
+int check_problem(int64_t N, const void* u0, const void* p, int np, double t0, double tf, const B200Opts* o) {
+    if (N < 0) return fail(B200ODE_EINVAL, "trajectories must be >= 0");
+    if (!u0) return fail(B200ODE_EINVAL, "u0 is NULL");
+    if (np > 0 && !p) return fail(B200ODE_EINVAL, "p is NULL but the program has np > 0");
+    if (!(tf > t0)) return fail(B200ODE_EUNSUPPORTED, "only forward time integration (tf > t0) is supported");
+    if (!o) return fail(B200ODE_EINVAL, "opts is NULL");
+    if (o->nsaveat < 0) return fail(B200ODE_EINVAL, "nsaveat < 0");
+    if (o->saveat) {
+        double prev = t0;
+        for (int i = 0; i < o->nsaveat; ++i) {
+            double s = o->saveat[i];
+            if (!(s > prev) || !(s <= tf))
+                return fail(B200ODE_EINVAL, "saveat must be strictly ascending with every entry in (t0, tf]");
+            prev = s;
+        }
+    }
+    if (o->dt < 0) return fail(B200ODE_EINVAL, "dt must be >= 0 (0 = automatic)");
+    if (o->dtmin < 0) return fail(B200ODE_EINVAL, "dtmin must be >= 0");
+    return B200ODE_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+const char* b200ode_version(void) { return "b200ode 0.1.0 (sm_100a, NVRTC " "12.x" ")"; }
+
+const char* b200ode_last_error(b200ode_handle) { return g_last_error.c_str(); }
+
+int b200ode_create(b200ode_handle* out, int device_id) {
+    if (!out) return fail(B200ODE_EINVAL, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B200ODE_ECUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                       "); this library has no CPU fallback");
+    if (device_id < 0 || device_id >= count) return fail(B200ODE_EINVAL, "device_id out of range");
+    CUDA_TRY(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10)
+        return fail(B200ODE_EUNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                              "; this library contains sm_100a code only");
+    b200ode_handle h = new b200ode_handle_s();
+    h->device = device_id;
+    h->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev0)); CUDA_TRY(cudaEventCreate(&h->ev1));
+    CUDA_TRY(cudaEventCreate(&h->ev2)); CUDA_TRY(cudaEventCreate(&h->ev3));
+    *out = h;
+    return B200ODE_OK;
+}
+
+int b200ode_destroy(b200ode_handle h) {
+    if (!h) return B200ODE_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&h->counter, &h->dt0, &h->saveat, &h->scratch_t, &h->in_u0, &h->in_p, &h->out_uf, &h->out_tf,
+                      &h->out_us, &h->out_i32, &h->red_partial})
+        b->release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3}) if (e) cudaEventDestroy(e);
+    delete h;
+    return B200ODE_OK;
+}
+
+void b200ode_free(void* p) { free(p); }
+
+int b200ode_compile_only(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
+                         const char* jac_src, const char* jac_name, const char* tgrad_src, const char* tgrad_name,
+                         const char* extra_options, void** cubin, size_t* cubin_bytes, char** log) {
+    std::vector<char> cb; std::string lg;
+    if (cubin) *cubin = nullptr;
+    if (cubin_bytes) *cubin_bytes = 0;
+    if (log) *log = nullptr;
+    int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
+                         extra_options, cb, lg, nullptr);
+    if (log) {
+        const std::string& src = (rc == B200ODE_ECOMPILE) ? g_last_error : lg;
+        *log = (char*)malloc(src.size() + 1);
+        memcpy(*log, src.c_str(), src.size() + 1);
+    }
+    if (rc) return rc;
+    if (cubin) { *cubin = malloc(cb.size()); memcpy(*cubin, cb.data(), cb.size()); }
+    if (cubin_bytes) *cubin_bytes = cb.size();
+    return B200ODE_OK;
+}
+
+int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, int n, int np,
+                    const char* rhs_src, const char* rhs_name, const char* jac_src, const char* jac_name,
+                    const char* tgrad_src, const char* tgrad_name, const char* extra_options) {
+    if (!h || !out) return fail(B200ODE_EINVAL, "handle/out is NULL");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(h->device));
+    b200ode_program prog = new b200ode_program_s();
+    prog->h = h; prog->alg = alg; prog->dtype = dtype; prog->n = n; prog->np = np;
+    std::string log; double ms = 0;
+    int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
+                         extra_options, prog->cubin, log, &ms);
+    if (rc) { delete prog; return rc; }
+    cudaError_t e = cudaLibraryLoadData(&prog->lib, prog->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }
+    e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&prog->k_initdt, prog->lib, "b200_initdt");
+    if (e != cudaSuccess) {
+        cudaLibraryUnload(prog->lib); delete prog;
+        return fail(B200ODE_ECUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
+    }
+    cudaFuncAttributes fa{};
+    e = cudaFuncGetAttributes(&fa, (const void*)prog->k_integrate);
+    if (e != cudaSuccess) { cudaLibraryUnload(prog->lib); delete prog; return fail(B200ODE_ECUDA, std::string("cudaFuncGetAttributes: ") + cudaGetErrorString(e)); }
+    prog->info.regs_integrate = fa.numRegs;
+    prog->info.local_bytes_integrate = (int)fa.localSizeBytes;
+    prog->info.smem_bytes_integrate = (int)fa.sharedSizeBytes;
+    prog->info.block = fa.maxThreadsPerBlock > 0 ? std::min(fa.maxThreadsPerBlock, 1024) : 128;
+    // maxThreadsPerBlock reflects __launch_bounds__(B200_BLOCK, …)
+    cudaFuncAttributes fb{};
+    if (cudaFuncGetAttributes(&fb, (const void*)prog->k_initdt) == cudaSuccess) {
+        prog->info.regs_initdt = fb.numRegs;
+        prog->info.local_bytes_initdt = (int)fb.localSizeBytes;
+    }
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)prog->k_integrate, prog->info.block, 0);
+    if (e != cudaSuccess || nb < 1) nb = 1;
+    prog->info.blocks_per_sm = nb;
+    prog->info.grid = nb * h->num_sms;
+    prog->info.cubin_bytes = (int64_t)prog->cubin.size();
+    prog->info.compile_ms = ms;
+    *out = prog;
+    return B200ODE_OK;
+}
+
+int b200ode_program_destroy(b200ode_program prog) {
+    if (!prog) return B200ODE_OK;
+    if (prog->lib) cudaLibraryUnload(prog->lib);
+    delete prog;
+    return B200ODE_OK;
+}
+
+int b200ode_program_info(b200ode_program prog, B200ProgramInfo* info) {
+    if (!prog || !info) return fail(B200ODE_EINVAL, "NULL argument");
+    *info = prog->info;
+    return B200ODE_OK;
+}
+
+int b200ode_nslots(const B200Problem* prob, const B200Opts* o) {
+    if (!prob || !o || !o->saveat || o->nsaveat <= 0) return 0;
+    int save_start = (o->save_start != 0) ? 1 : 0;
+    int save_end = (o->save_end != 0) ? 1 : 0;
+    bool grid_has_tf = (o->saveat[o->nsaveat - 1] == prob->tf);
+    int slots = save_start + o->nsaveat;
+    if (grid_has_tf && !save_end) slots -= 1;          // skip_saveat_at_tspan_end
+    if (!grid_has_tf && save_end) slots += 1;          // solution_endpoint_match_cur_integrator!
+    return slots;
+}
+
+int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
+                         B200DeviceResult* dr, void* stream) {
+    if (!h || !prog || !dp || !o || !dr) return fail(B200ODE_EINVAL, "NULL argument");
+    if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
+    int rc = check_problem(dp->trajectories, dp->u0, dp->p, prog->np, dp->t0, dp->tf, o);
+    if (rc) return rc;
+    if (!dr->u_final || !dr->t_final || !dr->naccept || !dr->nreject || !dr->nf || !dr->retcode || !dr->nsaved)
+        return fail(B200ODE_EINVAL, "device result arrays u_final,t_final,naccept,nreject,nf,retcode,nsaved are required");
+    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    if (stiff && (!dr->njacs || !dr->nw || !dr->nsolve))
+        return fail(B200ODE_EINVAL, "Rosenbrock programs need njacs,nw,nsolve result arrays");
+    if (dp->trajectories == 0) return B200ODE_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream
+    if (prog->dtype == B200ODE_F32) return launch_solve<float>(h, prog, dp, o, dr, s);
+    return launch_solve<double>(h, prog, dp, o, dr, s);
+}
+
+int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res) {
+    if (!h || !prog || !hp || !o || !res) return fail(B200ODE_EINVAL, "NULL argument");
+    if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
+    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, hp->t0, hp->tf, o);
+    if (rc) return rc;
+    if (!res->u_final) return fail(B200ODE_EINVAL, "result.u_final is required");
+    const long long N = hp->trajectories;
+    if (N == 0) return B200ODE_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = prog->n, np = prog->np;
+    const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
+    const int nslots = res->us ? b200ode_nslots(hp, o) : 0;
+    cudaStream_t s = h->stream;
+
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    size_t u0_bytes = rs * n * (hp->u0_shared ? 1 : (size_t)N);
+    size_t p_bytes = rs * np * (hp->p_shared ? 1 : (size_t)N);
+    CUDA_TRY(h->in_u0.ensure(u0_bytes));
+    CUDA_TRY(cudaMemcpyAsync(h->in_u0.ptr, hp->u0, u0_bytes, cudaMemcpyHostToDevice, s));
+    if (np > 0) {
+        CUDA_TRY(h->in_p.ensure(p_bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->in_p.ptr, hp->p, p_bytes, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(h->out_uf.ensure(rs * n * (size_t)N));
+    CUDA_TRY(h->out_tf.ensure(rs * (size_t)N));
+    CUDA_TRY(h->out_i32.ensure(sizeof(int32_t) * 8 * (size_t)N));
+    size_t us_bytes = rs * (size_t)n * (size_t)nslots * (size_t)N;
+    if (nslots > 0) CUDA_TRY(h->out_us.ensure(us_bytes));
+
+    B200DeviceProblem dp{};
+    dp.trajectories = N;
+    dp.u0 = h->in_u0.ptr; dp.u0_shared = hp->u0_shared; dp.u0_layout = B200ODE_LAYOUT_AOS;
+    dp.p = np > 0 ? h->in_p.ptr : nullptr; dp.p_shared = hp->p_shared; dp.p_layout = B200ODE_LAYOUT_AOS;
+    dp.t0 = hp->t0; dp.tf = hp->tf;
+    B200DeviceResult dr{};
+    int32_t* i32 = (int32_t*)h->out_i32.ptr;
+    dr.u_final = h->out_uf.ptr; dr.u_final_layout = B200ODE_LAYOUT_AOS;
+    dr.t_final = (double*)h->out_tf.ptr;
+    dr.us = nslots > 0 ? h->out_us.ptr : nullptr;
+    dr.nsaved = i32 + 0 * N; dr.naccept = i32 + 1 * N; dr.nreject = i32 + 2 * N; dr.nf = i32 + 3 * N;
+    dr.njacs = i32 + 4 * N; dr.nw = i32 + 5 * N; dr.nsolve = i32 + 6 * N; dr.retcode = i32 + 7 * N;
+    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    if (!stiff) CUDA_TRY(cudaMemsetAsync(i32 + 4 * N, 0, sizeof(int32_t) * 3 * (size_t)N, s));
+    // A trajectory that fails writes fewer than nslots rows; the rest stay zero.
+    if (nslots > 0) CUDA_TRY(cudaMemsetAsync(h->out_us.ptr, 0, us_bytes, s));
+
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    rc = b200ode_solve_device(h, prog, &dp, o, &dr, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev2, s));
+
+    CUDA_TRY(cudaMemcpyAsync(res->u_final, h->out_uf.ptr, rs * n * (size_t)N, cudaMemcpyDeviceToHost, s));
+    if (nslots > 0) CUDA_TRY(cudaMemcpyAsync(res->us, h->out_us.ptr, us_bytes, cudaMemcpyDeviceToHost, s));
+    std::vector<char> tf_host;
+    if (res->t_final) {
+        tf_host.resize(rs * (size_t)N);
+        CUDA_TRY(cudaMemcpyAsync(tf_host.data(), h->out_tf.ptr, rs * (size_t)N, cudaMemcpyDeviceToHost, s));
+    }
+    struct { int32_t* dst; int slot; } outs[] = {
+        {res->nsaved, 0}, {res->naccept, 1}, {res->nreject, 2}, {res->nf, 3},
+        {res->njacs, 4}, {res->nw, 5}, {res->nsolve, 6}, {res->retcode, 7}};
+    for (auto& oo : outs)
+        if (oo.dst) CUDA_TRY(cudaMemcpyAsync(oo.dst, i32 + (size_t)oo.slot * N, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(h->ev3, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(B200ODE_ECUDA, std::string("kernel failure: ") + cudaGetErrorString(le));
+    if (res->t_final) {
+        if (rs == 8) memcpy(res->t_final, tf_host.data(), 8 * (size_t)N);
+        else for (long long i = 0; i < N; ++i) res->t_final[i] = (double)((const float*)tf_host.data())[i];
+    }
+    if (res->ts && nslots > 0) {
+        int k = 0;
+        if (o->save_start != 0) res->ts[k++] = hp->t0;
+        for (int i = 0; i < o->nsaveat && k < nslots; ++i) {
+            if (o->saveat[i] == hp->tf && o->save_end == 0) continue;
+            // the grid is stored in the program's real type
+            res->ts[k++] = (rs == 8) ? o->saveat[i] : (double)(float)o->saveat[i];
+        }
+        if (k < nslots) res->ts[k++] = hp->tf;
+    }
+    float kms = 0, tms = 0;
+    cudaEventElapsedTime(&kms, h->ev1, h->ev2);
+    cudaEventElapsedTime(&tms, h->ev0, h->ev3);
+    res->kernel_ms = kms; res->total_ms = tms;
+    return B200ODE_OK;
+}
+
+int b200ode_reduce_sum_device(b200ode_handle h, int dtype, const void* x, int layout, int64_t count, int n,
+                              double* out, void* stream) {
+    if (!h || !x || !out) return fail(B200ODE_EINVAL, "NULL argument");
+    if (n < 1 || count < 0) return fail(B200ODE_EINVAL, "bad n/count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nblocks = 2 * h->num_sms;
+    CUDA_TRY(h->red_partial.ensure(sizeof(double) * (size_t)nblocks * n));
+    long long ts = layout == B200ODE_LAYOUT_SOA ? 1 : n, cs = layout == B200ODE_LAYOUT_SOA ? count : 1;
+    if (dtype == B200ODE_F32)
+        k_reduce_partial<float><<<nblocks, 256, 0, s>>>((const float*)x, ts, cs, count, n, (double*)h->red_partial.ptr);
+    else
+        k_reduce_partial<double><<<nblocks, 256, 0, s>>>((const double*)x, ts, cs, count, n, (double*)h->red_partial.ptr);
+    k_reduce_final<<<1, 256, 0, s>>>((const double*)h->red_partial.ptr, nblocks, n, out);
+    CUDA_TRY(cudaGetLastError());
+    return B200ODE_OK;
+}
+
+int b200ode_host_register(void* ptr, size_t bytes) {
+    if (!ptr) return fail(B200ODE_EINVAL, "NULL pointer");
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return B200ODE_OK;
+}
+int b200ode_host_unregister(void* ptr) {
+    if (!ptr) return fail(B200ODE_EINVAL, "NULL pointer");
+    CUDA_TRY(cudaHostUnregister(ptr));
+    return B200ODE_OK;
+}
+
+int b200ode_measure_fma_peak(b200ode_handle h, int dtype, double* tflops, double* sm_clock_mhz) {
+    if (!h || !tflops) return fail(B200ODE_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(h->scratch_t.ensure(64));
+    const int iters = dtype == B200ODE_F32 ? 8192 : 4096;
+    const int blocks = h->num_sms * 8, threads = 256;
+    auto launch = [&]() {
+        if (dtype == B200ODE_F32) k_fma_peak<float><<<blocks, threads, 0, h->stream>>>((float*)h->scratch_t.ptr, iters, 1.0000001f, 1e-7f);
+        else k_fma_peak<double><<<blocks, threads, 0, h->stream>>>((double*)h->scratch_t.ptr, iters, 1.0000000001, 1e-10);
+    };
+    for (int w = 0; w < 3; ++w) launch();
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    const int reps = 5;
+    for (int r = 0; r < reps; ++r) launch();
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads * reps;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    if (sm_clock_mhz) {
+        int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    return B200ODE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,443 @@
+// b200_ensemble.cuh — the per-trajectory integrator loop and the two kernels of
+// the ensemble hot path.
+//
+//   b200_initdt     one thread per trajectory, no divergence: Hairer initial step
+//                   (lib/OrdinaryDiffEqCore/src/initdt.jl:346-459, OOP form).
+//   b200_integrate  persistent warps; every lane owns one trajectory at a time and
+//                   pulls the next index from a warp-local pool that is refilled
+//                   from one global counter (guided chunking), so lanes stay busy
+//                   although trajectories take different numbers of adaptive steps.
+//
+// The loop body follows the reference's solve! / loopheader! / check_error /
+// perform_step! / loopfooter! / savevalues! sequence
+//   lib/OrdinaryDiffEqCore/src/solve.jl:904-946
+//   lib/OrdinaryDiffEqCore/src/integrators/integrator_utils.jl:84-127,130-150,175-203,
+//       268-333,340-414,597-677,1027-1034,1199-1256
+//   lib/OrdinaryDiffEqCore/src/integrators/controllers.jl:245-250,288-293,805-843
+//   lib/DiffEqBase/src/check_error.jl:70-118
+// for forward time, adaptive stepping, PI controller, no callbacks, tstops = {tf}.
+//
+// Compile-time configuration (set by the shim before this file):
+//   B200_N, B200_NP      state / parameter dimension
+//   B200_F32             0: double, 1: float
+//   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P
+//   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
+//   B200_BLOCK, B200_MINBLOCKS   launch bounds
+#pragma once
+#include "b200_base.cuh"
+#include "b200_detmath.cuh"
+
+#define B200_ALG_TSIT5 1
+#define B200_ALG_VERN7 2
+#define B200_ALG_ROS23 3
+#define B200_ALG_RODAS5P 4
+
+#if B200_ALG == B200_ALG_TSIT5
+#include "b200_tsit5.cuh"
+typedef B200Tsit5 B200Stepper;
+#elif B200_ALG == B200_ALG_VERN7
+#include "b200_vern7.cuh"
+typedef B200Vern7 B200Stepper;
+#elif B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#include "b200_rosenbrock.cuh"
+#if B200_ALG == B200_ALG_ROS23
+typedef B200Ros23 B200Stepper;
+#else
+typedef B200Rodas5P B200Stepper;
+#endif
+#endif
+
+// ReturnCode values exported to the host (include/b200ode.h)
+#define B200_RC_DEFAULT 0
+#define B200_RC_SUCCESS 1
+#define B200_RC_MAXITERS 2
+#define B200_RC_DTLESSTHANMIN 3
+#define B200_RC_UNSTABLE 4
+#define B200_RC_DTNAN 5
+
+struct B200Params {
+    long long N;              // trajectories handled by this launch
+    const real* u0;           // element (i,c) at u0[i*u0_ts + c*u0_cs]; u0_ts = 0 when shared
+    long long u0_ts, u0_cs;
+    const real* p;
+    long long p_ts, p_cs;
+    real t0, tf;
+    real reltol, abstol;
+    real dt_user;             // 0 => automatic (dt0[] filled by b200_initdt)
+    real dtmin, dtmax;
+    long long maxiters;
+    const real* saveat;       // grid times in (t0, tf], ascending
+    int nsaveat;
+    int save_start, save_end;
+    int nslots;               // rows per trajectory in us (0 => no time series output)
+    real* dt0;                // [N]
+    real* u_final;            // element (i,c) at u_final[i*uf_ts + c*uf_cs]
+    long long uf_ts, uf_cs;
+    real* t_final;            // [N]
+    real* us;                 // [N][nslots][n]
+    int* naccept; int* nreject; int* nf; int* retcode; int* nsaved;
+    int* njacs; int* nw; int* nsolve;
+    unsigned long long* work_counter;
+    int flags;
+};
+
+#define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
+
+// ---------------------------------------------------------------------------
+// ODE_DEFAULT_NORM for a static vector: sqrt(sum(abs2,u)/n), left fold, no fusion
+// (lib/DiffEqBase/src/common_defaults.jl:102-107).
+B200_D real b200_rms(const real* v) {
+    real acc = v[0] * v[0];
+#pragma unroll
+    for (int i = 1; i < B200_N; ++i) acc = acc + v[i] * v[i];
+    return b200_sqrt(acc / (real)B200_N);
+}
+
+// _ode_initdt_oop (initdt.jl:346-459), g === nothing, forward time.
+B200_D real b200_initdt_one(const real* u0, const real* p, real t, real dtmax_tdir, real abstol, real reltol,
+                            real opts_dtmin, int order) {
+    real dtmin = b200_nextfloat(b200_max(opts_dtmin, b200_eps(t)));
+    real smalldt = b200_max(dtmin, (real)1e-6);
+    real sk[B200_N], f0[B200_N], tmp[B200_N];
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) sk[i] = b200_fma(b200_abs(u0[i]), reltol, abstol);
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) tmp[i] = u0[i] / sk[i];
+    real d0 = b200_rms(tmp);
+    B200_RHS(f0, u0, p, t);
+    bool anynan = false;
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) anynan = anynan || b200_isnan(f0[i]);
+    if (anynan) return dtmin;
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) tmp[i] = f0[i] / sk[i];
+    real d1 = b200_rms(tmp);
+    if (b200_isnan(d1)) return dtmin;
+    real dt0;
+    // comparisons against the exact rationals 1//10^5 (both binary64 and binary32
+    // operands, widened exactly to double, compare like this against the double literal)
+    if ((double)d0 < 1e-5 || (double)d1 < 1e-5) dt0 = smalldt;
+    else dt0 = (d0 / d1) / (real)100;
+    dt0 = b200_min(dt0, dtmax_tdir);
+    real u1[B200_N], f1[B200_N];
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) u1[i] = b200_fma(dt0, f0[i], u0[i]);
+    B200_RHS(f1, u1, p, t + dt0);
+    bool alleq = true;
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) alleq = alleq && (f0[i] == f1[i]);
+    if (alleq) return b200_max(dtmin, (real)100 * dt0);
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) tmp[i] = (f1[i] - f0[i]) / sk[i];
+    real d2 = b200_rms(tmp) / dt0;
+    real m = b200_max(d1, d2);
+    real dt1;
+    if ((double)m < 1e-15) {            // m <= 1//10^15 (exact rational)
+        dt1 = b200_max(smalldt, dt0 * (real)0.001);
+    } else if (!b200_isfinite(m)) {
+        dt1 = (real)0;                  // log10(Inf)=Inf -> 10^-Inf = 0
+    } else {
+        real l = (real)b200_log10_cr((double)m);
+        real e = -((real)2 + l) / (real)order;
+        dt1 = (real)b200_exp10_cr((double)e);
+    }
+    return b200_max(dtmin, b200_min(b200_min((real)100 * dt0, dt1), dtmax_tdir));
+}
+
+extern "C" __global__ void __launch_bounds__(256) b200_initdt(B200Params P) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    real u0[B200_N], p[B200_NP > 0 ? B200_NP : 1];
+#pragma unroll
+    for (int c = 0; c < B200_N; ++c) u0[c] = P.u0[i * P.u0_ts + c * P.u0_cs];
+#pragma unroll
+    for (int c = 0; c < B200_NP; ++c) p[c] = P.p[i * P.p_ts + c * P.p_cs];
+    // _determine_initdt: dtmax = min(|opts.dtmax|, |first_tstop - t|)
+    real dtmax = b200_min(b200_abs(P.dtmax), b200_abs(P.tf - P.t0));
+    P.dt0[i] = b200_initdt_one(u0, p, P.t0, dtmax, P.abstol, P.reltol, P.dtmin, B200Stepper::order());
+}
+
+// ---------------------------------------------------------------------------
+struct B200Traj {
+    real u[B200_N], uprev[B200_N];
+    real p[B200_NP > 0 ? B200_NP : 1];
+    B200Stepper st;
+    real t, tprev, dt, dtpropose;
+    real q11, errold, EEst;
+    long long iter;
+    int success_iter, naccept, nreject, nf;
+    int save_idx, nsaved;
+    int retcode;
+    bool accept, tstop_flag;
+#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+    int njacs, nw, nsolve;
+#endif
+};
+
+B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, const real* v) {
+    if (P.nslots > 0 && T.nsaved < P.nslots) {
+        real* dst = P.us + ((size_t)idx * (size_t)P.nslots + (size_t)T.nsaved) * B200_N;
+#pragma unroll
+        for (int c = 0; c < B200_N; ++c) dst[c] = v[c];
+    }
+    T.nsaved += 1;
+}
+
+// modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch, tstops={tf}
+B200_D void b200_modify_dt_for_tstops(const B200Params& P, B200Traj& T) {
+    real dist = b200_abs(P.tf - T.t);
+    real tol = (real)100 * b200_eps(b200_max(b200_abs(T.t), b200_abs(P.tf)));
+    real orig = b200_abs(T.dt);
+    T.dtpropose = orig;
+    T.tstop_flag = !(orig + tol < dist);
+    T.dt = b200_min(orig, dist);
+}
+
+B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
+#pragma unroll
+    for (int c = 0; c < B200_N; ++c) {
+        real v = P.u0[idx * P.u0_ts + c * P.u0_cs];
+        T.u[c] = v; T.uprev[c] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < B200_NP; ++c) T.p[c] = P.p[idx * P.p_ts + c * P.p_cs];
+    T.t = P.t0; T.tprev = P.t0;
+    T.nf = 0;
+#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+    T.njacs = 0; T.nw = 0; T.nsolve = 0;
+#endif
+    T.nsaved = 0; T.save_idx = 0;
+    if (P.save_start) b200_emit(P, idx, T, T.u);      // solve.jl:809-824
+    T.st.init(T.u, T.p, T.t, T.nf);                   // initialize!(integrator, cache)
+    if (P.dt_user == (real)0) { T.dt = P.dt0[idx]; T.nf += 2; }   // auto_dt_reset!: nf += 2
+    else T.dt = P.dt_user;
+    T.dtpropose = T.dt;
+    T.q11 = (real)1; T.errold = (real)1e-4; T.EEst = (real)1;     // setup_controller_cache (controllers.jl:793-803)
+    T.iter = 0; T.success_iter = 0; T.naccept = 0; T.nreject = 0;
+    T.accept = false; T.tstop_flag = false;
+    T.retcode = B200_RC_DEFAULT;
+}
+
+// One pass of the while-loop body of solve!.  Returns true when the trajectory is finished.
+B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T) {
+    const real qmin = (real)0.2, qmax = (real)10, gamma = (real)0.9;
+    const real beta1 = (real)(7.0 / (10.0 * B200Stepper::order()));   // QT(7//(10 order)): both are correctly rounded
+    const real beta2 = (real)(2.0 / (5.0 * B200Stepper::order()));
+    // ---- loopheader! ----
+    if (T.iter > 0) {
+        if (T.accept) {
+            T.success_iter += 1;
+            // apply_step!: update_uprev!, dt = dtpropose, update_fsal!, modify_dt_for_tstops!
+#pragma unroll
+            for (int c = 0; c < B200_N; ++c) T.uprev[c] = T.u[c];
+            T.dt = T.dtpropose;
+            T.st.accept();
+            b200_modify_dt_for_tstops(P, T);
+        } else {
+            // step_reject_controller!: dt /= min(inv(qmin), q11/gamma)
+            T.dt = T.dt / b200_min((real)1 / qmin, T.q11 / gamma);
+        }
+    }
+    T.iter += 1;
+    // fix_dt_at_bounds!
+    T.dt = b200_min(P.dtmax, T.dt);
+    T.dt = b200_max(T.dt, b200_max(b200_eps(T.t), P.dtmin));
+    b200_modify_dt_for_tstops(P, T);
+    // ---- check_error ----
+    {
+        int rc = B200_RC_SUCCESS;
+        if (b200_isnan(T.dt)) rc = B200_RC_DTNAN;
+        else if (T.iter > P.maxiters) rc = B200_RC_MAXITERS;
+        else if (b200_abs(T.dt) <= b200_abs(P.dtmin) && (!T.accept || T.t + T.dt < P.tf)) rc = B200_RC_DTLESSTHANMIN;
+        else if (!T.accept && b200_abs(T.dt) <= b200_abs(b200_eps(T.t))) rc = B200_RC_UNSTABLE;
+        else if (T.accept) {
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < B200_N; ++c) bad = bad || !b200_isfinite(T.u[c]);
+            if (bad) rc = B200_RC_UNSTABLE;
+        }
+        if (rc != B200_RC_SUCCESS) { T.retcode = rc; return true; }
+    }
+    // ---- perform_step! / handle_tstop_step! ----
+    if (T.tstop_flag && b200_abs(T.dt) < b200_eps(b200_abs(T.t))) {
+        T.accept = true;        // skipped step; EEst stale (integrator_utils.jl:326-333)
+    } else {
+#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+        T.EEst = T.st.attempt(T.uprev, T.u, T.p, T.t, T.dt, P.reltol, P.abstol, T.nf, T.njacs, T.nw, T.nsolve,
+                              P.nslots > 0 && P.nsaveat > 0);
+#else
+        T.EEst = T.st.attempt(T.uprev, T.u, T.p, T.t, T.dt, P.reltol, P.abstol, T.nf);
+#endif
+    }
+    // ---- loopfooter! ----
+    const real ttmp = T.t + T.dt;
+    // stepsize_controller!(integrator, ::PIControllerCache, alg)
+    const real qmax_eff = (T.success_iter == 0) ? (real)10000 : qmax;
+    real q;
+    if (T.EEst == (real)0) {
+        q = (real)1 / qmax_eff;
+    } else {
+        real q11 = b200_fastpower(T.EEst, beta1);
+        q = q11 / b200_fastpower(T.errold, beta2);
+        T.q11 = q11;
+        q = q / gamma;
+        const real lo = (real)1 / qmax_eff, hi = (real)1 / qmin;
+        q = q < lo ? lo : (q > hi ? hi : q);       // clamp under @fastmath
+    }
+    T.accept = (T.EEst <= (real)1);
+    if (T.accept) {
+        T.naccept += 1;
+        T.tprev = T.t;
+        if (T.tstop_flag) T.dt = T.dtpropose;       // restore un-clipped dt (integrator_utils.jl:629-633)
+        T.t = T.tstop_flag ? P.tf : ttmp;           // fixed_t_for_tstop_error!
+        T.tstop_flag = false;
+        // step_accept_controller!
+        if (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) q = (real)1;
+        T.errold = b200_max(T.EEst, (real)1e-4);
+        const real dtnew = T.dt / q;
+        // calc_dt_propose!
+        T.dtpropose = b200_max(b200_min(b200_abs(P.dtmax), b200_abs(dtnew)), b200_max(b200_eps(T.t), P.dtmin));
+        // handle_callbacks! -> savevalues!
+        if (P.nsaveat > 0) {
+            bool dense_ready = false;
+            while (T.save_idx < P.nsaveat) {
+                const real curt = P.saveat[T.save_idx];
+                if (!(curt <= T.t)) break;
+                T.save_idx += 1;
+                if (curt != T.t) {
+                    if (!dense_ready) {
+                        T.st.dense_prepare(T.uprev, T.u, T.p, T.tprev, T.dt);
+                        dense_ready = true;
+                    }
+                    const real th = (curt - T.tprev) / T.dt;
+                    real out[B200_N];
+                    T.st.interp(th, T.dt, T.uprev, T.u, out);
+                    b200_emit(P, idx, T, out);
+                } else {
+                    if (curt == P.tf && !P.save_end) continue;   // skip_saveat_at_tspan_end
+                    b200_emit(P, idx, T, T.u);
+                }
+            }
+        }
+    } else {
+        T.nreject += 1;
+    }
+    // while tdir*t < first_tstop
+    return !(T.t < P.tf);
+}
+
+// postamble! (+ writing the per-trajectory results)
+B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
+    if (T.retcode == B200_RC_DEFAULT) T.retcode = B200_RC_SUCCESS;
+    // solution_endpoint_match_cur_integrator! (integrator_utils.jl:540-587):
+    //   save_end && (saveiter == 0 || sol.t[saveiter] != t &&
+    //                (save_end_user === true || t in saveat || t == tspan[2] || isempty(saveat)))
+    // P.save_end: 0 false, 1 default true, 2 explicit true.  A grid point equal to t
+    // would already be the last saved row, so `t in saveat` adds nothing here.
+    if (P.save_end) {
+        bool emit;
+        if (T.nsaved == 0) emit = true;
+        else {
+            const real last_t = (T.save_idx > 0) ? P.saveat[T.save_idx - 1] : P.t0;
+            emit = (last_t != T.t) && (P.save_end == 2 || T.t == P.tf || P.nsaveat == 0);
+        }
+        if (emit) b200_emit(P, idx, T, T.u);
+    }
+#pragma unroll
+    for (int c = 0; c < B200_N; ++c) P.u_final[idx * P.uf_ts + c * P.uf_cs] = T.u[c];
+    P.t_final[idx] = T.t;
+    P.naccept[idx] = T.naccept;
+    P.nreject[idx] = T.nreject;
+    P.nf[idx] = T.nf;
+    P.retcode[idx] = T.retcode;
+    P.nsaved[idx] = T.nsaved;
+#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+    P.njacs[idx] = T.njacs; P.nw[idx] = T.nw; P.nsolve[idx] = T.nsolve;
+#endif
+}
+
+#ifndef B200_BLOCK
+#define B200_BLOCK 128
+#endif
+#ifndef B200_MINBLOCKS
+#define B200_MINBLOCKS 1
+#endif
+#ifndef B200_CHUNK_MAX
+#define B200_CHUNK_MAX 64
+#endif
+
+extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_integrate(B200Params P) {
+    B200Traj T;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    if (P.flags & B200_FLAG_STATIC_SCHEDULE) {
+        long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx >= P.N) return;
+        b200_traj_begin(P, idx, T);
+        bool done = !(T.t < P.tf);
+        while (!done) done = b200_traj_iterate(P, idx, T);
+        b200_traj_end(P, idx, T);
+        return;
+    }
+
+    const long long total_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    long long pool_next = 0, pool_end = 0;     // warp-uniform
+    long long idx = -1;
+    bool active = false;
+    bool exhausted = false;                    // warp-uniform: global counter ran past N
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (need != 0u && !exhausted) {
+            const int want = __popc(need);
+            if (pool_end - pool_next < want) {
+                // refill the warp pool: guided chunk (large while plenty of work remains,
+                // shrinking towards the tail so warps finish together)
+                long long base = 0, got_end = 0;
+                if (lane == 0) {
+                    unsigned long long cur = *((volatile unsigned long long*)P.work_counter);
+                    long long rem = P.N - (long long)cur;
+                    long long chunk = rem / (2 * total_warps);
+                    if (chunk > B200_CHUNK_MAX) chunk = B200_CHUNK_MAX;
+                    long long short_by = want - (pool_end - pool_next);
+                    if (chunk < short_by) chunk = short_by;
+                    base = (long long)atomicAdd(P.work_counter, (unsigned long long)chunk);
+                    got_end = base + chunk;
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                got_end = __shfl_sync(0xffffffffu, got_end, 0);
+                // the old pool (if any) is a contiguous range that ends where this one
+                // may not begin; keep both ranges by handing out the old one first
+                long long old_left = pool_end - pool_next;
+                if (!active) {
+                    int rank = __popc(need & lt_mask);
+                    long long cand = (rank < old_left) ? (pool_next + rank) : (base + (rank - old_left));
+                    if (cand < P.N) { idx = cand; active = true; b200_traj_begin(P, idx, T); }
+                }
+                pool_next = base + (want - old_left);
+                pool_end = got_end;
+                if (base >= P.N) exhausted = true;
+                if (pool_end > P.N) pool_end = P.N > pool_next ? P.N : pool_next;
+            } else {
+                if (!active) {
+                    int rank = __popc(need & lt_mask);
+                    idx = pool_next + rank; active = true;
+                    b200_traj_begin(P, idx, T);
+                }
+                pool_next += want;
+            }
+            // trajectories that are already finished at t0 >= tf
+            if (active && !(T.t < P.tf)) { b200_traj_end(P, idx, T); active = false; }
+        }
+        if (!__any_sync(0xffffffffu, active)) {
+            if (exhausted || need == 0u) break;
+            continue;
+        }
+        if (active) {
+            if (b200_traj_iterate(P, idx, T)) {
+                b200_traj_end(P, idx, T);
+                active = false;
+            }
+        }
+    }
+}

@@ -1,0 +1,138 @@
+// b200_tsit5.cuh — Tsit5 stage loop, embedded error estimate and free 4th-order
+// interpolant, one trajectory per thread, all stage vectors in registers.
+//
+// Reference behaviour reproduced (arithmetic order and fusion included):
+//   perform_step!(…, ::Tsit5ConstantCache)  lib/OrdinaryDiffEqTsit5/src/tsit_perform_step.jl:140-186
+//   initialize!                              …/tsit_perform_step.jl:125-138
+//   tableau (Float64 literals, convert(T,·)) …/tsit_tableaus.jl:52-92
+//   interpolant b_i(Θ), y0 + dt*Σ k_i b_i    …/interpolants.jl:32-57, coefficients tsit_tableaus.jl:244-276
+// Fusion follows MuladdMacro: in a sum the last product is the outermost muladd
+// (SURVEY §8 T2), `dt * (Σ)` of the error estimate is a plain multiply.
+#pragma once
+#include "b200_base.cuh"
+
+#define B200_TSIT5_ORDER 5
+
+struct B200Tsit5 {
+    real k1[B200_N], k2[B200_N], k3[B200_N], k4[B200_N], k5[B200_N], k6[B200_N], k7[B200_N];
+
+    static B200_D int order() { return 5; }
+    static B200_D bool fsal() { return true; }
+    // qsteady_min/max defaults for explicit methods (alg_utils.jl:833,853)
+    static B200_D real qsteady_min() { return (real)1; }
+    static B200_D real qsteady_max() { return (real)1; }
+
+    // initialize!: fsalfirst = f(uprev, p, t); nf += 1
+    B200_D void init(const real* u, const real* p, real t, int& nf) {
+        B200_RHS(k1, u, p, t);
+        nf += 1;
+    }
+
+    // one attempted step; returns EEst
+    B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt,
+                        real reltol, real abstol, int& nf) {
+        const real c1 = (real)0.161, c2 = (real)0.327, c3 = (real)0.9, c4 = (real)0.9800255409045097;
+        const real a21 = (real)0.161;
+        const real a31 = (real)-0.008480655492356989, a32 = (real)0.335480655492357;
+        const real a41 = (real)2.8971530571054935, a42 = (real)-6.359448489975075, a43 = (real)4.3622954328695815;
+        const real a51 = (real)5.325864828439257, a52 = (real)-11.748883564062828, a53 = (real)7.4955393428898365,
+                   a54 = (real)-0.09249506636175525;
+        const real a61 = (real)5.86145544294642, a62 = (real)-12.92096931784711, a63 = (real)8.159367898576159,
+                   a64 = (real)-0.071584973281401, a65 = (real)-0.028269050394068383;
+        const real a71 = (real)0.09646076681806523, a72 = (real)0.01, a73 = (real)0.4798896504144996,
+                   a74 = (real)1.379008574103742, a75 = (real)-3.290069515436081, a76 = (real)2.324710524099774;
+        const real bt1 = (real)-0.00178001105222577714, bt2 = (real)-0.0008164344596567469,
+                   bt3 = (real)0.007880878010261995, bt4 = (real)-0.1447110071732629,
+                   bt5 = (real)0.5823571654525552, bt6 = (real)-0.45808210592918697,
+                   bt7 = (real)0.015151515151515152;
+        real tmp[B200_N];
+        const real a = dt * a21;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) tmp[i] = b200_fma(a, k1[i], uprev[i]);
+        B200_RHS(k2, tmp, p, b200_fma(c1, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt, b200_fma(a32, k2[i], a31 * k1[i]), uprev[i]);
+        B200_RHS(k3, tmp, p, b200_fma(c2, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt, b200_fma(a43, k3[i], b200_fma(a42, k2[i], a41 * k1[i])), uprev[i]);
+        B200_RHS(k4, tmp, p, b200_fma(c3, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt, b200_fma(a54, k4[i], b200_fma(a53, k3[i], b200_fma(a52, k2[i], a51 * k1[i]))),
+                              uprev[i]);
+        B200_RHS(k5, tmp, p, b200_fma(c4, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt,
+                              b200_fma(a65, k5[i],
+                                       b200_fma(a64, k4[i], b200_fma(a63, k3[i], b200_fma(a62, k2[i], a61 * k1[i])))),
+                              uprev[i]);
+        B200_RHS(k6, tmp, p, t + dt);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            u[i] = b200_fma(dt,
+                            b200_fma(a76, k6[i],
+                                     b200_fma(a75, k5[i],
+                                              b200_fma(a74, k4[i],
+                                                       b200_fma(a73, k3[i], b200_fma(a72, k2[i], a71 * k1[i]))))),
+                            uprev[i]);
+        B200_RHS(k7, u, p, t + dt);
+        nf += 6;
+        // utilde = dt*(Σ btilde_i k_i); atmp = calculate_residuals; EEst = internalnorm(atmp)
+        real acc = (real)0;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) {
+            real ut = dt * b200_fma(bt7, k7[i],
+                                    b200_fma(bt6, k6[i],
+                                             b200_fma(bt5, k5[i],
+                                                      b200_fma(bt4, k4[i],
+                                                               b200_fma(bt3, k3[i],
+                                                                        b200_fma(bt2, k2[i], bt1 * k1[i]))))));
+            real r = ut / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
+            real r2 = r * r;
+            acc = (i == 0) ? r2 : (acc + r2);
+        }
+        return b200_sqrt(acc / (real)B200_N);
+    }
+
+    // apply_step!/update_fsal!: fsalfirst = fsallast
+    B200_D void accept() {
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) k1[i] = k7[i];
+    }
+
+    // nothing to prepare: all 7 stages are kept (ode_addsteps! is a no-op once length(k) >= 7)
+    B200_D void dense_prepare(const real*, const real*, const real*, real, real) {}
+
+    // _ode_interpolant(Θ, dt, y0, y1, k, ::Tsit5ConstantCache, nothing, Val{0})
+    B200_D void interp(real th, real dt, const real* y0, const real* /*y1*/, real* out) const {
+        const real r11 = (real)1.0, r12 = (real)-2.763706197274826, r13 = (real)2.9132554618219126,
+                   r14 = (real)-1.0530884977290216;
+        const real r22 = (real)0.13169999999999998, r23 = (real)-0.2234, r24 = (real)0.1017;
+        const real r32 = (real)3.9302962368947516, r33 = (real)-5.941033872131505, r34 = (real)2.490627285651253;
+        const real r42 = (real)-12.411077166933676, r43 = (real)30.33818863028232, r44 = (real)-16.548102889244902;
+        const real r52 = (real)37.50931341651104, r53 = (real)-88.1789048947664, r54 = (real)47.37952196281928;
+        const real r62 = (real)-27.896526289197286, r63 = (real)65.09189467479366, r64 = (real)-34.87065786149661;
+        const real r72 = (real)1.5, r73 = (real)-4.0, r74 = (real)2.5;
+        const real th2 = th * th;
+        const real b1 = th * b200_fma(th, b200_fma(th, b200_fma(th, r14, r13), r12), r11);
+        const real b2 = th2 * b200_fma(th, b200_fma(th, r24, r23), r22);
+        const real b3 = th2 * b200_fma(th, b200_fma(th, r34, r33), r32);
+        const real b4 = th2 * b200_fma(th, b200_fma(th, r44, r43), r42);
+        const real b5 = th2 * b200_fma(th, b200_fma(th, r54, r53), r52);
+        const real b6 = th2 * b200_fma(th, b200_fma(th, r64, r63), r62);
+        const real b7 = th2 * b200_fma(th, b200_fma(th, r74, r73), r72);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            out[i] = b200_fma(dt,
+                              b200_fma(k7[i], b7,
+                                       b200_fma(k6[i], b6,
+                                                b200_fma(k5[i], b5,
+                                                         b200_fma(k4[i], b4,
+                                                                  b200_fma(k3[i], b3,
+                                                                           b200_fma(k2[i], b2, k1[i] * b1)))))),
+                              y0[i]);
+    }
+};

@@ -1,0 +1,145 @@
+"""Array-level entry points over the C ABI: host buffers (numpy) and device buffers (torch).
+
+`solve_host` is what `solve(EnsembleProblem, alg, EnsembleB200(); ...)` lowers to once
+`prob_func` has been harvested into flat (u0, p) tables; `solve_device` is the same call
+with everything already resident in HBM (torch tensors are used purely as device
+memory owners here).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _np_real(dtype):
+    return np.float32 if dtype == _lib.F32 else np.float64
+
+
+def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None,
+               maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None):
+    """Host arrays in, host arrays out (b200ode_solve).
+
+    u0: (N, n) or (n,) shared; p: (N, np) or (np,) shared or None.
+    saveat: explicit ascending grid in (t0, tf] or None.
+    out: optional dict of preallocated (e.g. pinned) numpy arrays keyed like the result.
+    """
+    L = _lib.lib()
+    rdt = _np_real(program.dtype)
+    n, npar = program.n, program.np
+    u0 = np.ascontiguousarray(u0, dtype=rdt)
+    u0_shared = (u0.ndim == 1)
+    if p is None:
+        p_arr, p_shared = None, True
+    else:
+        p_arr = np.ascontiguousarray(p, dtype=rdt)
+        p_shared = (p_arr.ndim == 1)
+    if trajectories is None:
+        if not u0_shared:
+            trajectories = u0.shape[0]
+        elif p_arr is not None and not p_shared:
+            trajectories = p_arr.shape[0]
+        else:
+            raise ValueError("trajectories must be given when both u0 and p are shared")
+    N = int(trajectories)
+    if u0.shape[-1] != n or (not u0_shared and u0.shape[0] != N):
+        raise ValueError("u0 has shape %s, expected (%d, %d) or (%d,)" % (u0.shape, N, n, n))
+    if npar > 0:
+        if p_arr is None or p_arr.shape[-1] != npar or (not p_shared and p_arr.shape[0] != N):
+            raise ValueError("p has wrong shape for np=%d" % npar)
+    t0, tf = float(tspan[0]), float(tspan[1])
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags)
+    prob = _lib.B200Problem()
+    prob.trajectories = N
+    prob.u0 = u0.ctypes.data
+    prob.u0_shared = int(u0_shared)
+    prob.p = p_arr.ctypes.data if p_arr is not None else None
+    prob.p_shared = int(p_shared)
+    prob.t0, prob.tf = t0, tf
+    nslots = L.b200ode_nslots(C.byref(prob), C.byref(opts))
+    out = {} if out is None else out
+
+    def buf(name, shape, dtype):
+        a = out.get(name)
+        if a is None:
+            a = np.empty(shape, dtype=dtype)
+            out[name] = a
+        assert a.shape == tuple(shape) and a.dtype == dtype and a.flags["C_CONTIGUOUS"], name
+        return a
+
+    res = _lib.B200Result()
+    res.u_final = buf("u_final", (N, n), rdt).ctypes.data
+    res.t_final = buf("t_final", (N,), np.float64).ctypes.data
+    if nslots > 0:
+        res.us = buf("us", (N, nslots, n), rdt).ctypes.data
+        res.ts = buf("ts", (nslots,), np.float64).ctypes.data
+    for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
+        setattr(res, name, buf(name, (N,), np.int32).ctypes.data)
+    _lib.check(L.b200ode_solve(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res)))
+    out["kernel_ms"] = res.kernel_ms
+    out["total_ms"] = res.total_ms
+    out["nslots"] = nslots
+    return out
+
+
+def nslots_for(tspan, saveat, save_start=None, save_end=None):
+    L = _lib.lib()
+    opts, keep = _lib.make_opts(saveat=saveat, save_start=save_start, save_end=save_end)
+    prob = _lib.B200Problem()
+    prob.t0, prob.tf = float(tspan[0]), float(tspan[1])
+    return L.b200ode_nslots(C.byref(prob), C.byref(opts))
+
+
+class DeviceBuffers:
+    """Device-resident inputs/outputs for `solve_device` (torch tensors own the memory)."""
+
+    def __init__(self, program, N, nslots, device, u0_shared=False, p_shared=False, layout=_lib.LAYOUT_AOS):
+        import torch
+        rt = torch.float32 if program.dtype == _lib.F32 else torch.float64
+        n, npar = program.n, program.np
+        self.N, self.nslots, self.layout = N, nslots, layout
+        self.u0_shared, self.p_shared = u0_shared, p_shared
+        shape_u0 = (n,) if u0_shared else ((N, n) if layout == _lib.LAYOUT_AOS else (n, N))
+        shape_p = (max(npar, 1),) if p_shared else ((N, max(npar, 1)) if layout == _lib.LAYOUT_AOS else (max(npar, 1), N))
+        self.u0 = torch.empty(shape_u0, dtype=rt, device=device)
+        self.p = torch.empty(shape_p, dtype=rt, device=device)
+        self.u_final = torch.empty((N, n) if layout == _lib.LAYOUT_AOS else (n, N), dtype=rt, device=device)
+        self.t_final = torch.empty((N,), dtype=rt, device=device)
+        self.us = torch.empty((N, nslots, n), dtype=rt, device=device) if nslots > 0 else None
+        self.i32 = torch.zeros((8, N), dtype=torch.int32, device=device)
+        names = ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode")
+        for k, name in enumerate(names):
+            setattr(self, name, self.i32[k])
+
+
+def solve_device(program, bufs, tspan, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None,
+                 saveat=None, save_start=None, save_end=None, flags=0, stream=None):
+    """Launch the ensemble on buffers already in HBM (b200ode_solve_device); asynchronous."""
+    L = _lib.lib()
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags)
+    dp = _lib.B200DeviceProblem()
+    dp.trajectories = bufs.N
+    dp.u0 = bufs.u0.data_ptr(); dp.u0_shared = int(bufs.u0_shared); dp.u0_layout = bufs.layout
+    dp.p = bufs.p.data_ptr(); dp.p_shared = int(bufs.p_shared); dp.p_layout = bufs.layout
+    dp.t0, dp.tf = float(tspan[0]), float(tspan[1])
+    dr = _lib.B200DeviceResult()
+    dr.u_final = bufs.u_final.data_ptr(); dr.u_final_layout = bufs.layout
+    dr.t_final = bufs.t_final.data_ptr()
+    dr.us = bufs.us.data_ptr() if bufs.us is not None else None
+    for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
+        setattr(dr, name, getattr(bufs, name).data_ptr())
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.b200ode_solve_device(program.handle._h, program._p, C.byref(dp), C.byref(opts), C.byref(dr),
+                                      C.c_void_p(stream)))
+
+
+def reduce_sum_device(handle, dtype, x, layout, count, n, out, stream=None):
+    """out (torch float64 [n], device) = per-component sum over trajectories of x."""
+    L = _lib.lib()
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.b200ode_reduce_sum_device(handle._h, dtype, C.c_void_p(x.data_ptr()), layout, int(count), int(n),
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(stream)))

@@ -1,0 +1,128 @@
+"""C sources of the benchmark right-hand sides named by BASELINE.json's configs, written
+operation-for-operation like the reference's Julia definitions, plus the deterministic
+synthetic parameter tables.
+
+    Lorenz     /root/reference/lib/OrdinaryDiffEqCore/src/precompilation_setup.jl:1-10, with
+               (sigma, rho, beta) as parameters so prob_func can randomise rho
+    Robertson  /root/reference/benchmark/benchmarks.jl:93-107   (+ analytic jac, tgrad = 0)
+    Pleiades   /root/reference/benchmark/benchmarks.jl:29-67    (standard RHS: accelerations
+               accumulate from zero — the file's `fill!(du[15:21], 0.0)` zero-fills copies)
+"""
+import numpy as np
+
+
+def _ty(f32):
+    return "float" if f32 else "double"
+
+
+def lorenz_source(f32=False, name="lorenz_rhs"):
+    T = _ty(f32)
+    return ("void %s(%s* du, const %s* u, const %s* p, const %s t) {\n"
+            "  du[0] = p[0] * (u[1] - u[0]);\n"
+            "  du[1] = u[0] * (p[1] - u[2]) - u[1];\n"
+            "  du[2] = u[0] * u[1] - p[2] * u[2];\n"
+            "}\n" % (name, T, T, T, T)), name
+
+
+def robertson_sources(f32=False):
+    T = _ty(f32)
+    sig = "(%s* %%s, const %s* u, const %s* p, const %s t)" % (T, T, T, T)
+    rhs = ("void rober_rhs" + sig % "du" + " {\n"
+           "  du[0] = -p[0] * u[0] + p[2] * u[1] * u[2];\n"
+           "  du[1] = p[0] * u[0] - p[1] * (u[1] * u[1]) - p[2] * u[1] * u[2];\n"
+           "  du[2] = p[1] * (u[1] * u[1]);\n"
+           "}\n")
+    zero = "0.0f" if f32 else "0.0"
+    two = "2.0f" if f32 else "2.0"
+    # column-major 3x3: J[i + 3*j] = d f_i / d u_j
+    jac = ("void rober_jac" + sig % "J" + " {\n"
+           "  J[0] = -p[0];\n"
+           "  J[1] = p[0];\n"
+           "  J[2] = %s;\n"
+           "  J[3] = p[2] * u[2];\n"
+           "  J[4] = -%s * p[1] * u[1] - p[2] * u[2];\n"
+           "  J[5] = %s * p[1] * u[1];\n"
+           "  J[6] = p[2] * u[1];\n"
+           "  J[7] = -p[2] * u[1];\n"
+           "  J[8] = %s;\n"
+           "}\n" % (zero, two, two, zero))
+    tgrad = ("void rober_tgrad" + sig % "dT" + " {\n"
+             "  dT[0] = %s; dT[1] = %s; dT[2] = %s;\n"
+             "}\n" % (zero, zero, zero))
+    return (rhs, "rober_rhs"), (jac, "rober_jac"), (tgrad, "rober_tgrad")
+
+
+def pleiades_source(f32=False, name="pleiades_rhs"):
+    """Straight-line code (all indices static so the state stays in registers)."""
+    T = _ty(f32)
+    sq = "sqrtf" if f32 else "sqrt"
+    suf = "f" if f32 else ""
+    L = ["void %s(%s* du, const %s* u, const %s* p, const %s t) {" % (name, T, T, T, T)]
+    for i in range(7):
+        L.append("  du[%d] = u[%d];" % (i, 14 + i))
+    for i in range(7):
+        L.append("  du[%d] = u[%d];" % (7 + i, 21 + i))
+    L.append("  %s dx, dy, r, r3, ax, ay;" % T)
+    for i in range(7):
+        L.append("  ax = 0.0%s; ay = 0.0%s;" % (suf, suf))
+        for j in range(7):
+            if i == j:
+                continue
+            L.append("  dx = u[%d] - u[%d]; dy = u[%d] - u[%d];" % (j, i, 7 + j, 7 + i))
+            L.append("  r = %s(dx * dx + dy * dy); r3 = r * r * r;" % sq)
+            L.append("  ax = ax + %d.0%s * dx / r3; ay = ay + %d.0%s * dy / r3;" % (j + 1, suf, j + 1, suf))
+        L.append("  du[%d] = ax; du[%d] = ay;" % (14 + i, 21 + i))
+    L.append("}")
+    return "\n".join(L) + "\n", name
+
+
+PLEIADES_U0 = np.array([3.0, 3.0, -1.0, -3.0, 2.0, -2.0, 2.0, 3.0, -3.0, 2.0, 0, 0, -4.0, 4.0,
+                        0, 0, 0, 0, 0, 1.75, -1.5, 0, 0, 0, -1.25, 1, 0, 0], dtype=np.float64)
+
+
+# ---- deterministic synthetic inputs ---------------------------------
+def splitmix64_uniform(i, j):
+    """U(i,j) = top 53 bits of SplitMix64(seed = 0x9E3779B97F4A7C15 xor (4 i + j)) / 2^53.
+
+    i may be a numpy array of trajectory indices."""
+    with np.errstate(over="ignore"):
+        x = np.uint64(0x9E3779B97F4A7C15) ^ (np.asarray(i, dtype=np.uint64) * np.uint64(4) + np.uint64(j))
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def lorenz_params(N, offset=0, f32=False, sweep_total=None):
+    """p[i] = (10, rho_i, 8/3); rho_i = 28 (0.5 + U(i,0)) in [14, 42), or the pure sweep
+    rho_i = 14 + 28 i / sweep_total of config 5."""
+    idx = np.arange(offset, offset + N, dtype=np.uint64)
+    if sweep_total is None:
+        rho = 28.0 * (0.5 + splitmix64_uniform(idx, 0))
+    else:
+        rho = 14.0 + 28.0 * idx.astype(np.float64) / float(sweep_total)
+    p = np.empty((N, 3), dtype=np.float64)
+    p[:, 0] = 10.0
+    p[:, 1] = rho
+    p[:, 2] = 8.0 / 3.0
+    return p.astype(np.float32) if f32 else p
+
+
+def robertson_params(N, offset=0, f32=False):
+    idx = np.arange(offset, offset + N, dtype=np.uint64)
+    base = np.array([0.04, 3.0e7, 1.0e4])
+    p = np.empty((N, 3), dtype=np.float64)
+    for j in range(3):
+        p[:, j] = base[j] * (0.5 + splitmix64_uniform(idx, j))
+    return p.astype(np.float32) if f32 else p
+
+
+def pleiades_u0(N, offset=0, f32=False):
+    """positions (components 0..13) += 0.01 (2 U(i,j) - 1)."""
+    idx = np.arange(offset, offset + N, dtype=np.uint64)
+    u0 = np.tile(PLEIADES_U0, (N, 1))
+    for j in range(14):
+        # U(i,j) is defined for j < 4 by the 4 i + j packing; use a disjoint stream per j
+        u0[:, j] += 0.01 * (2.0 * splitmix64_uniform(idx * np.uint64(4) + np.uint64(j // 4), j % 4) - 1.0)
+    return u0.astype(np.float32) if f32 else u0
