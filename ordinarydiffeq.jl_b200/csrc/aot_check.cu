@@ -4,15 +4,15 @@
 // libb200ode.so.
 #include "b200_base.cuh"
 
-#if AOT_PROBLEM == 1
-// Lorenz, parameters p = (sigma, rho, beta)
-// (/root/reference/lib/OrdinaryDiffEqCore/src/precompilation_setup.jl:1-10 form)
-__device__ __forceinline__ void aot_rhs(real* du, const real* u, const real* p, const real t) {
-    du[0] = p[0] * (u[1] - u[0]);
-    du[1] = u[0] * (p[1] - u[2]) - u[1];
-    du[2] = u[0] * u[1] - p[2] * u[2];
-}
-#endif
+// The right-hand sides are the package's own problem library sources
+// (problems_library.py), written to build/aot_problems_gen.inc by build.py.
+#define AOT_STR2(x) #x
+#define AOT_STR(x) AOT_STR2(x)
+#include AOT_STR(AOT_PROBLEM_INC)
 
-#define B200_RHS(du, u, p, t) aot_rhs((du), (u), (p), (t))
+#define B200_RHS(du, u, p, t) AOT_RHS_NAME((du), (u), (p), (t))
+#ifdef AOT_JAC_NAME
+#define B200_JAC(J, u, p, t) AOT_JAC_NAME((J), (u), (p), (t))
+#define B200_TGRAD(dT, u, p, t) AOT_TGRAD_NAME((dT), (u), (p), (t))
+#endif
 #include "b200_ensemble.cuh"

@@ -90,7 +90,7 @@ B200_D real b200_rms(const real* v) {
     real acc = v[0] * v[0];
 #pragma unroll
     for (int i = 1; i < B200_N; ++i) acc = acc + v[i] * v[i];
-    return b200_sqrt(acc / (real)B200_N);
+    return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
 }
 
 // _ode_initdt_oop (initdt.jl:346-459), g === nothing, forward time.
@@ -164,8 +164,7 @@ struct B200Traj {
     B200Stepper st;
     real t, tprev, dt, dtpropose;
     real q11, errold, EEst;
-    long long iter;
-    int success_iter, naccept, nreject, nf;
+    int naccept, nreject, nf;      // iter = naccept+nreject(+1), success_iter = naccept (see iterate)
     int save_idx, nsaved;
     int retcode;
     bool accept, tstop_flag;
@@ -183,14 +182,18 @@ B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, const rea
     T.nsaved += 1;
 }
 
-// modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch, tstops={tf}
-B200_D void b200_modify_dt_for_tstops(const B200Params& P, B200Traj& T) {
-    real dist = b200_abs(P.tf - T.t);
-    real tol = (real)100 * b200_eps(b200_max(b200_abs(T.t), b200_abs(P.tf)));
+// min/max against an operand that is known not to be NaN (c): a NaN in x propagates,
+// exactly like Base.min/max, at the cost of one compare.
+B200_D real b200_min_c(real c, real x) { return (c < x) ? c : x; }
+B200_D real b200_max_c(real c, real x) { return (c > x) ? c : x; }
+
+// modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch, tstops={tf}.
+// tol100 = 100*eps(max(|t|,|tf|)) and dist = |tf - t| depend only on t.
+B200_D void b200_modify_dt_for_tstops(B200Traj& T, real dist, real tol100) {
     real orig = b200_abs(T.dt);
     T.dtpropose = orig;
-    T.tstop_flag = !(orig + tol < dist);
-    T.dt = b200_min(orig, dist);
+    T.tstop_flag = !(orig + tol100 < dist);
+    T.dt = b200_min_c(dist, orig);
 }
 
 B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
@@ -213,55 +216,66 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     else T.dt = P.dt_user;
     T.dtpropose = T.dt;
     T.q11 = (real)1; T.errold = (real)1e-4; T.EEst = (real)1;     // setup_controller_cache (controllers.jl:793-803)
-    T.iter = 0; T.success_iter = 0; T.naccept = 0; T.nreject = 0;
+    T.naccept = 0; T.nreject = 0;
     T.accept = false; T.tstop_flag = false;
     T.retcode = B200_RC_DEFAULT;
 }
 
 // One pass of the while-loop body of solve!.  Returns true when the trajectory is finished.
-B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T) {
+// `amask` = the lanes of this warp that execute this call; the short accept/reject
+// branches of loopheader! are re-converged explicitly before the stage loop (otherwise
+// a single rejecting lane makes the warp run perform_step! twice).
+B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, unsigned amask) {
     const real qmin = (real)0.2, qmax = (real)10, gamma = (real)0.9;
     const real beta1 = (real)(7.0 / (10.0 * B200Stepper::order()));   // QT(7//(10 order)): both are correctly rounded
     const real beta2 = (real)(2.0 / (5.0 * B200Stepper::order()));
+    // quantities of modify_dt_for_tstops! that depend only on t (t is finite here)
+    // integrator.iter (before its increment) and integrator.success_iter are not stored:
+    // iter = naccept + nreject and success_iter = naccept at every point they are read.
+    const int iter0 = T.naccept + T.nreject;
+    const real dist = b200_abs(P.tf - T.t);
+    const real at = b200_abs(T.t), atf = b200_abs(P.tf);
+    real tol100;
+    if (!(b200_abs(P.t0) > atf)) tol100 = (real)100 * b200_eps(atf);   // |t| <= |tf| on all of [t0, tf]: loop invariant
+    else tol100 = (real)100 * b200_eps(at > atf ? at : atf);
+    const real eps_t = b200_eps(T.t);
+    const real dtmin_t = eps_t > P.dtmin ? eps_t : P.dtmin;          // timedepentdtmin
     // ---- loopheader! ----
-    if (T.iter > 0) {
+    if (iter0 > 0) {
         if (T.accept) {
-            T.success_iter += 1;
             // apply_step!: update_uprev!, dt = dtpropose, update_fsal!, modify_dt_for_tstops!
 #pragma unroll
             for (int c = 0; c < B200_N; ++c) T.uprev[c] = T.u[c];
             T.dt = T.dtpropose;
             T.st.accept();
-            b200_modify_dt_for_tstops(P, T);
+            b200_modify_dt_for_tstops(T, dist, tol100);
         } else {
             // step_reject_controller!: dt /= min(inv(qmin), q11/gamma)
-            T.dt = T.dt / b200_min((real)1 / qmin, T.q11 / gamma);
+            T.dt = T.dt / b200_min_c((real)1 / qmin, b200_div_const(T.q11, gamma, (real)1 / gamma));
         }
     }
-    T.iter += 1;
     // fix_dt_at_bounds!
-    T.dt = b200_min(P.dtmax, T.dt);
-    T.dt = b200_max(T.dt, b200_max(b200_eps(T.t), P.dtmin));
-    b200_modify_dt_for_tstops(P, T);
+    T.dt = b200_min_c(P.dtmax, T.dt);
+    T.dt = b200_max_c(dtmin_t, T.dt);
+    b200_modify_dt_for_tstops(T, dist, tol100);
     // ---- check_error ----
-    {
-        int rc = B200_RC_SUCCESS;
-        if (b200_isnan(T.dt)) rc = B200_RC_DTNAN;
-        else if (T.iter > P.maxiters) rc = B200_RC_MAXITERS;
-        else if (b200_abs(T.dt) <= b200_abs(P.dtmin) && (!T.accept || T.t + T.dt < P.tf)) rc = B200_RC_DTLESSTHANMIN;
-        else if (!T.accept && b200_abs(T.dt) <= b200_abs(b200_eps(T.t))) rc = B200_RC_UNSTABLE;
-        else if (T.accept) {
-            bool bad = false;
+    int rc = B200_RC_SUCCESS;
+    if (b200_isnan(T.dt)) rc = B200_RC_DTNAN;
+    else if ((long long)iter0 + 1 > P.maxiters) rc = B200_RC_MAXITERS;
+    else if (b200_abs(T.dt) <= b200_abs(P.dtmin) && (!T.accept || T.t + T.dt < P.tf)) rc = B200_RC_DTLESSTHANMIN;
+    else if (!T.accept && b200_abs(T.dt) <= eps_t) rc = B200_RC_UNSTABLE;
+    else if (T.accept) {
+        bool bad = false;
 #pragma unroll
-            for (int c = 0; c < B200_N; ++c) bad = bad || !b200_isfinite(T.u[c]);
-            if (bad) rc = B200_RC_UNSTABLE;
-        }
-        if (rc != B200_RC_SUCCESS) { T.retcode = rc; return true; }
+        for (int c = 0; c < B200_N; ++c) bad = bad || !b200_isfinite(T.u[c]);
+        if (bad) rc = B200_RC_UNSTABLE;
     }
+    const bool ok = (rc == B200_RC_SUCCESS);
+    if (!ok) T.retcode = rc;
     // ---- perform_step! / handle_tstop_step! ----
-    if (T.tstop_flag && b200_abs(T.dt) < b200_eps(b200_abs(T.t))) {
-        T.accept = true;        // skipped step; EEst stale (integrator_utils.jl:326-333)
-    } else {
+    const bool skip = T.tstop_flag && b200_abs(T.dt) < eps_t;   // integrator_utils.jl:326-333 (eps(|t|) == eps(t))
+    __syncwarp(amask);
+    if (ok && !skip) {
 #if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
         T.EEst = T.st.attempt(T.uprev, T.u, T.p, T.t, T.dt, P.reltol, P.abstol, T.nf, T.njacs, T.nw, T.nsolve,
                               P.nslots > 0 && P.nsaveat > 0);
@@ -269,10 +283,12 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T) {
         T.EEst = T.st.attempt(T.uprev, T.u, T.p, T.t, T.dt, P.reltol, P.abstol, T.nf);
 #endif
     }
+    __syncwarp(amask);
+    if (!ok) return true;
     // ---- loopfooter! ----
     const real ttmp = T.t + T.dt;
     // stepsize_controller!(integrator, ::PIControllerCache, alg)
-    const real qmax_eff = (T.success_iter == 0) ? (real)10000 : qmax;
+    const real qmax_eff = (T.naccept == 0) ? (real)10000 : qmax;
     real q;
     if (T.EEst == (real)0) {
         q = (real)1 / qmax_eff;
@@ -280,7 +296,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T) {
         real q11 = b200_fastpower(T.EEst, beta1);
         q = q11 / b200_fastpower(T.errold, beta2);
         T.q11 = q11;
-        q = q / gamma;
+        q = b200_div_const(q, gamma, (real)1 / gamma);
         const real lo = (real)1 / qmax_eff, hi = (real)1 / qmin;
         q = q < lo ? lo : (q > hi ? hi : q);       // clamp under @fastmath
     }
@@ -293,10 +309,11 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T) {
         T.tstop_flag = false;
         // step_accept_controller!
         if (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) q = (real)1;
-        T.errold = b200_max(T.EEst, (real)1e-4);
+        T.errold = b200_max_c((real)1e-4, T.EEst);
         const real dtnew = T.dt / q;
-        // calc_dt_propose!
-        T.dtpropose = b200_max(b200_min(b200_abs(P.dtmax), b200_abs(dtnew)), b200_max(b200_eps(T.t), P.dtmin));
+        // calc_dt_propose!: eps at the NEW t
+        const real eps_n = b200_eps(T.t);
+        T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
         // handle_callbacks! -> savevalues!
         if (P.nsaveat > 0) {
             bool dense_ready = false;
@@ -373,11 +390,17 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
 
     if (P.flags & B200_FLAG_STATIC_SCHEDULE) {
         long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        if (idx >= P.N) return;
-        b200_traj_begin(P, idx, T);
-        bool done = !(T.t < P.tf);
-        while (!done) done = b200_traj_iterate(P, idx, T);
-        b200_traj_end(P, idx, T);
+        bool live = idx < P.N;
+        if (live) {
+            b200_traj_begin(P, idx, T);
+            live = (T.t < P.tf);
+            if (!live) b200_traj_end(P, idx, T);
+        }
+        for (;;) {
+            const unsigned am = __ballot_sync(0xffffffffu, live);
+            if (am == 0u) break;
+            if (live && b200_traj_iterate(P, idx, T, am)) { b200_traj_end(P, idx, T); live = false; }
+        }
         return;
     }
 
@@ -429,12 +452,13 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
             // trajectories that are already finished at t0 >= tf
             if (active && !(T.t < P.tf)) { b200_traj_end(P, idx, T); active = false; }
         }
-        if (!__any_sync(0xffffffffu, active)) {
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (am == 0u) {
             if (exhausted || need == 0u) break;
             continue;
         }
         if (active) {
-            if (b200_traj_iterate(P, idx, T)) {
+            if (b200_traj_iterate(P, idx, T, am)) {
                 b200_traj_end(P, idx, T);
                 active = false;
             }

@@ -1,0 +1,340 @@
+// b200_rosenbrock.cuh — Rosenbrock23 and Rodas5P, one trajectory per thread: analytic
+// Jacobian (user source), W = J - I/(dt*gamma), small dense solve in registers.
+//
+// Reference behaviour reproduced (out-of-place / SVector forms):
+//   Rosenbrock23  perform_step!(…, ::Rosenbrock23ConstantCache)  lib/OrdinaryDiffEqRosenbrock/src/rosenbrock_perform_step.jl:249-332
+//                 tableau d = 1/(2+√2), c32 = 6+√2                …/rosenbrock_tableaus.jl:6-10
+//                 interpolant                                     …/rosenbrock_interpolants.jl:46-61
+//   Rodas5P       perform_step!(…, ::RosenbrockCombinedConstantCache) …/rosenbrock_perform_step.jl:431-559
+//                 tableau                                         …/rosenbrock_tableaus.jl:23-71
+//                 interpolant (interp_order 3)                    …/rosenbrock_interpolants.jl:175-205
+//   J, dT, W      calc_rosenbrock_differentiation / calc_W / calc_J / calc_tderivative
+//                 lib/OrdinaryDiffEqDifferentiation/src/derivative_utils.jl:1050-1110,937-1002,304-355,235-265
+//                 (has_jac / has_tgrad branches; every attempt gets a fresh J: the W-method
+//                 reuse logic :46-171 returns (true,true) for max_jac_age = 1 and for non-W methods;
+//                 stats: nw += 1 and njacs += 2 per attempt — calc_W's calc_J plus the
+//                 `jac_reuse.cached_J = calc_J(...)` re-evaluation at :1078)
+//   linear solve  W is a StaticWOperator (EXT SciMLOperators): for n <= 7 it stores inv(W) and
+//                 `W \ v` is a mat-vec.  Restated for n = 3 with StaticArrays' 3x3 `inv`
+//                 (cross-product form); other n use partial-pivot LU (documented deviation,
+//                 DESIGN.md).  issuccess_W(::StaticWOperator) is always true (T11).
+#pragma once
+#include "b200_base.cuh"
+#include "b200_tableaus_gen.cuh"
+
+#ifndef B200_LINSOLVE_LU
+#if B200_N == 3 || B200_N == 1
+#define B200_LINSOLVE_LU 0
+#else
+#define B200_LINSOLVE_LU 1
+#endif
+#endif
+
+// ---- W factor object: either the explicit inverse (n = 1, 3) or LU with partial pivoting
+struct B200WFact {
+#if !B200_LINSOLVE_LU
+    real inv[B200_N * B200_N];     // row-major inverse
+#else
+    real lu[B200_N * B200_N];      // row-major, unit-lower L below the diagonal, U on and above
+    int piv[B200_N];
+#endif
+    bool ok;
+
+    // W (column-major n×n, as f.jac returns it) -> factor
+    B200_D void factor(const real* W) {
+        ok = true;
+#if !B200_LINSOLVE_LU
+#if B200_N == 1
+        inv[0] = (real)1 / W[0];
+#else
+        // StaticArrays _inv(::Size{(3,3)}, A): x0,x1,x2 = columns; y0 = x1 × x2; d = x0·y0;
+        // x0 /= d; y0 /= d; y1 = x2 × x0; y2 = x0 × x1; rows of A^-1 are y0, y1, y2.
+        real x0[3] = {W[0], W[1], W[2]}, x1[3] = {W[3], W[4], W[5]}, x2[3] = {W[6], W[7], W[8]};
+        real y0[3], y1[3], y2[3];
+        y0[0] = x1[1] * x2[2] - x1[2] * x2[1];
+        y0[1] = x1[2] * x2[0] - x1[0] * x2[2];
+        y0[2] = x1[0] * x2[1] - x1[1] * x2[0];
+        const real d = (x0[0] * y0[0] + x0[1] * y0[1]) + x0[2] * y0[2];
+        x0[0] = x0[0] / d; x0[1] = x0[1] / d; x0[2] = x0[2] / d;
+        y0[0] = y0[0] / d; y0[1] = y0[1] / d; y0[2] = y0[2] / d;
+        y1[0] = x2[1] * x0[2] - x2[2] * x0[1];
+        y1[1] = x2[2] * x0[0] - x2[0] * x0[2];
+        y1[2] = x2[0] * x0[1] - x2[1] * x0[0];
+        y2[0] = x0[1] * x1[2] - x0[2] * x1[1];
+        y2[1] = x0[2] * x1[0] - x0[0] * x1[2];
+        y2[2] = x0[0] * x1[1] - x0[1] * x1[0];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { inv[0 * 3 + j] = y0[j]; inv[1 * 3 + j] = y1[j]; inv[2 * 3 + j] = y2[j]; }
+#endif
+#else
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+#pragma unroll
+            for (int j = 0; j < B200_N; ++j) lu[i * B200_N + j] = W[i + B200_N * j];
+        for (int k = 0; k < B200_N; ++k) {
+            int pr = k; real best = b200_abs(lu[k * B200_N + k]);
+            for (int i = k + 1; i < B200_N; ++i) {
+                real v = b200_abs(lu[i * B200_N + k]);
+                if (v > best) { best = v; pr = i; }
+            }
+            piv[k] = pr;
+            if (pr != k)
+                for (int j = 0; j < B200_N; ++j) {
+                    real tswap = lu[k * B200_N + j]; lu[k * B200_N + j] = lu[pr * B200_N + j]; lu[pr * B200_N + j] = tswap;
+                }
+            const real pivot = lu[k * B200_N + k];
+            if (pivot == (real)0) { ok = false; continue; }
+            for (int i = k + 1; i < B200_N; ++i) {
+                const real l = lu[i * B200_N + k] / pivot;
+                lu[i * B200_N + k] = l;
+                for (int j = k + 1; j < B200_N; ++j) lu[i * B200_N + j] = lu[i * B200_N + j] - l * lu[k * B200_N + j];
+            }
+        }
+#endif
+    }
+
+    // x = W \ b
+    B200_D void solve(const real* b, real* x) const {
+#if !B200_LINSOLVE_LU
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) {
+            real s = inv[i * B200_N + 0] * b[0];
+#pragma unroll
+            for (int j = 1; j < B200_N; ++j) s = s + inv[i * B200_N + j] * b[j];
+            x[i] = s;
+        }
+#else
+        real y[B200_N];
+        for (int i = 0; i < B200_N; ++i) y[i] = b[i];
+        for (int k = 0; k < B200_N; ++k) {
+            const int pr = piv[k];
+            if (pr != k) { real tswap = y[k]; y[k] = y[pr]; y[pr] = tswap; }
+            for (int i = k + 1; i < B200_N; ++i) y[i] = y[i] - lu[i * B200_N + k] * y[k];
+        }
+        for (int i = B200_N - 1; i >= 0; --i) {
+            real s = y[i];
+            for (int j = i + 1; j < B200_N; ++j) s = s - lu[i * B200_N + j] * y[j];
+            y[i] = s / lu[i * B200_N + i];
+        }
+        for (int i = 0; i < B200_N; ++i) x[i] = y[i];
+#endif
+    }
+};
+
+// J, dT at (uprev, t); W = J - I * inv(dtgamma)
+B200_D void b200_build_W(const real* uprev, const real* p, real t, real dtgamma, real* dT, B200WFact& F,
+                         int& njacs, int& nw) {
+    real J[B200_N * B200_N];
+    B200_JAC(J, uprev, p, t);
+#ifdef B200_TGRAD
+    B200_TGRAD(dT, uprev, p, t);
+#else
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) dT[i] = (real)0;     // autonomous system
+#endif
+    njacs += 2;
+    nw += 1;
+    const real lam = (real)1 / dtgamma;
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) J[i + B200_N * i] = J[i + B200_N * i] - lam;
+    F.factor(J);
+}
+
+B200_D real b200_err_norm(const real* ut, const real* uprev, const real* u, real reltol, real abstol) {
+    real acc = (real)0;
+#pragma unroll
+    for (int i = 0; i < B200_N; ++i) {
+        real r = ut[i] / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
+        real r2 = r * r;
+        acc = (i == 0) ? r2 : (acc + r2);
+    }
+    return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
+}
+
+// ---------------------------------------------------------------------------
+struct B200Ros23 {
+    real k1[B200_N], k2[B200_N];       // dense output rows (integrator.k[1], k[2])
+    real f0[B200_N], f2[B200_N];       // fsalfirst, fsallast
+
+    static B200_D int order() { return 2; }
+    static B200_D real qsteady_min() { return (real)1; }
+    static B200_D real qsteady_max() { return (real)1.2; }     // 6//5 for implicit methods (alg_utils.jl:857)
+
+    B200_D void init(const real* u, const real* p, real t, int& nf) {
+        B200_RHS(f0, u, p, t);
+        nf += 1;
+    }
+
+    B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt, real reltol, real abstol,
+                        int& nf, int& njacs, int& nw, int& nsolve, bool /*calck*/) {
+        const real d = (real)0.2928932188134525;       // convert(T, 1/(2+sqrt(2)))
+        const real c32 = (real)7.414213562373095;      // convert(T, 6+sqrt(2))
+        const real dtg = dt * d;
+        const real ninv = -((real)1 / dtg);
+        const real dto2 = dt / (real)2;
+        const real dto6 = dt / (real)6;
+        real dT[B200_N], rhs[B200_N], tmp[B200_N], f1[B200_N], k3[B200_N];
+        B200WFact F;
+        b200_build_W(uprev, p, t, dtg, dT, F, njacs, nw);
+        if (!F.ok) return (real)2;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) rhs[i] = b200_fma(dtg, dT[i], f0[i]);
+        F.solve(rhs, k1);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) k1[i] = k1[i] * ninv;
+        nsolve += 1;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) tmp[i] = b200_fma(dto2, k1[i], uprev[i]);
+        B200_RHS(f1, tmp, p, t + dto2);
+        nf += 1;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) rhs[i] = f1[i] - k1[i];
+        F.solve(rhs, k2);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) k2[i] = b200_fma(k2[i], ninv, k1[i]);
+        nsolve += 1;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) u[i] = b200_fma(dt, k2[i], uprev[i]);
+        B200_RHS(f2, u, p, t + dt);
+        nf += 1;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            rhs[i] = b200_fma(dt, dT[i],
+                              b200_fma((real)-2, k1[i] - f0[i], b200_fma(-c32, k2[i] - f1[i], f2[i])));
+        F.solve(rhs, k3);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) k3[i] = k3[i] * ninv;
+        nsolve += 1;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) tmp[i] = dto6 * (b200_fma((real)-2, k2[i], k1[i]) + k3[i]);
+        return b200_err_norm(tmp, uprev, u, reltol, abstol);
+    }
+
+    B200_D void accept() {
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) f0[i] = f2[i];
+    }
+    B200_D void dense_prepare(const real*, const real*, const real*, real, real) {}
+
+    B200_D void interp(real th, real dt, const real* y0, const real* /*y1*/, real* out) const {
+        const real d = (real)0.2928932188134525;
+        const real den = b200_fma((real)-2, d, (real)1);          // 1 - 2d
+        const real c1 = th * ((real)1 - th) / den;
+        const real c2 = th * b200_fma((real)-2, d, th) / den;     // Θ(Θ - 2d)/(1 - 2d)
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) out[i] = b200_fma(dt, b200_fma(c2, k2[i], c1 * k1[i]), y0[i]);
+    }
+};
+
+// ---------------------------------------------------------------------------
+struct B200Rodas5PCoeffs {
+    real A[8][8];
+    real C[8][7];
+    real c[8];
+    real d[8];
+    real H[3][8];
+    real gamma;
+};
+__constant__ B200Rodas5PCoeffs B200_RODAS5P_TAB = {B200_RODAS5P_A, B200_RODAS5P_C, B200_RODAS5P_c, B200_RODAS5P_d,
+                                                 B200_RODAS5P_H, B200_RODAS5P_GAMMA};
+
+struct B200Rodas5P {
+    real dense[3][B200_N];             // integrator.k[1..3] (only filled when saveat is used)
+
+    static B200_D int order() { return 5; }
+    static B200_D real qsteady_min() { return (real)1; }
+    static B200_D real qsteady_max() { return (real)1.2; }
+
+    B200_D void init(const real*, const real*, real, int&) {}    // not FSAL (alg_utils.jl:60)
+
+    B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt, real reltol, real abstol,
+                        int& nf, int& njacs, int& nw, int& nsolve, bool calck) {
+        const B200Rodas5PCoeffs& T = B200_RODAS5P_TAB;
+        const real dtgamma = dt * T.gamma;
+        real dT[B200_N], du[B200_N], lt[B200_N], us[B200_N];
+        real ks[8][B200_N];
+        B200WFact F;
+        b200_build_W(uprev, p, t, dtgamma, dT, F, njacs, nw);
+        if (!F.ok) return (real)2;
+        // dtC = C ./ dt : all quotients share the divisor, so one correctly rounded
+        // reciprocal + the exact residual correction gives each correctly rounded quotient
+        // (same bits as IEEE division; see b200_div_const).
+        const real rdt = (real)1 / dt;
+        const bool fast_div = (b200_abs(dt) >= (real)1e-30 && b200_abs(dt) <= (real)1e30);
+        B200_RHS(du, uprev, p, t);
+        nf += 1;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) lt[i] = -b200_fma(dt * T.d[0], dT[i], du[i]);
+        F.solve(lt, ks[0]);
+#pragma unroll
+        for (int s = 1; s < 8; ++s) {
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) us[i] = uprev[i];
+#pragma unroll
+            for (int j = 0; j < s; ++j)
+#pragma unroll
+                for (int i = 0; i < B200_N; ++i) us[i] = b200_fma(T.A[s][j], ks[j][i], us[i]);
+            B200_RHS(du, us, p, b200_fma(T.c[s], dt, t));
+            nf += 1;
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) lt[i] = (real)0;
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                real q;
+                if (fast_div) {
+                    const real q0 = T.C[s][j] * rdt;
+                    const real r = b200_fma(-dt, q0, T.C[s][j]);
+                    q = b200_fma(r, rdt, q0);
+                } else q = T.C[s][j] / dt;
+#pragma unroll
+                for (int i = 0; i < B200_N; ++i) lt[i] = b200_fma(q, ks[j][i], lt[i]);
+            }
+            const real dtd = dt * T.d[s];
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) lt[i] = -b200_fma(dtd, dT[i], du[i] + lt[i]);
+            F.solve(lt, ks[s]);
+            nsolve += 1;
+        }
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) u[i] = uprev[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const real b = (j < 7) ? T.A[7][j] : (real)1;      // b = [A[8,1:7]; 1]
+            if (j < 7 && T.A[7][j] == (real)0) continue;
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) u[i] = b200_fma(b, ks[j][i], u[i]);
+        }
+        // btilde = e_8: du = 0 + 1*ks[8]
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) du[i] = b200_fma((real)1, ks[7][i], (real)0);
+        const real EEst = b200_err_norm(du, uprev, u, reltol, abstol);
+        if (calck) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < B200_N; ++i) dense[r][i] = (real)0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int i = 0; i < B200_N; ++i) dense[r][i] = b200_fma(T.H[r][j], ks[j][i], dense[r][i]);
+        }
+        return EEst;
+    }
+
+    B200_D void accept() {}
+    B200_D void dense_prepare(const real*, const real*, const real*, real, real) {}
+
+    // Θ1*y0 + Θ*(y1 + Θ1*(k1 + Θ*(k2 + Θ*k3)))
+    B200_D void interp(real th, real /*dt*/, const real* y0, const real* y1, real* out) const {
+        const real th1 = (real)1 - th;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) {
+            real in = b200_fma(th, dense[2][i], dense[1][i]);
+            in = b200_fma(th, in, dense[0][i]);
+            in = b200_fma(th1, in, y1[i]);
+            out[i] = b200_fma(th, in, th1 * y0[i]);
+        }
+    }
+};

@@ -13,6 +13,34 @@
 
 #define B200_TSIT5_ORDER 5
 
+// Tableau in constant memory: DFMA/FFMA take a constant-bank operand directly, so a
+// coefficient costs no instruction (immediates would cost two UMOVs per double).
+struct B200Tsit5Coeffs {
+    real c1, c2, c3, c4;
+    real a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65, a71, a72, a73, a74, a75, a76;
+    real bt1, bt2, bt3, bt4, bt5, bt6, bt7;
+    real r11, r12, r13, r14, r22, r23, r24, r32, r33, r34, r42, r43, r44, r52, r53, r54, r62, r63, r64, r72, r73, r74;
+};
+__constant__ B200Tsit5Coeffs B200_TSIT5_C = {
+    (real)0.161, (real)0.327, (real)0.9, (real)0.9800255409045097,
+    (real)0.161, (real)-0.008480655492356989, (real)0.335480655492357,
+    (real)2.8971530571054935, (real)-6.359448489975075, (real)4.3622954328695815,
+    (real)5.325864828439257, (real)-11.748883564062828, (real)7.4955393428898365, (real)-0.09249506636175525,
+    (real)5.86145544294642, (real)-12.92096931784711, (real)8.159367898576159, (real)-0.071584973281401,
+    (real)-0.028269050394068383,
+    (real)0.09646076681806523, (real)0.01, (real)0.4798896504144996, (real)1.379008574103742,
+    (real)-3.290069515436081, (real)2.324710524099774,
+    (real)-0.00178001105222577714, (real)-0.0008164344596567469, (real)0.007880878010261995,
+    (real)-0.1447110071732629, (real)0.5823571654525552, (real)-0.45808210592918697, (real)0.015151515151515152,
+    (real)1.0, (real)-2.763706197274826, (real)2.9132554618219126, (real)-1.0530884977290216,
+    (real)0.13169999999999998, (real)-0.2234, (real)0.1017,
+    (real)3.9302962368947516, (real)-5.941033872131505, (real)2.490627285651253,
+    (real)-12.411077166933676, (real)30.33818863028232, (real)-16.548102889244902,
+    (real)37.50931341651104, (real)-88.1789048947664, (real)47.37952196281928,
+    (real)-27.896526289197286, (real)65.09189467479366, (real)-34.87065786149661,
+    (real)1.5, (real)-4.0, (real)2.5,
+};
+
 struct B200Tsit5 {
     real k1[B200_N], k2[B200_N], k3[B200_N], k4[B200_N], k5[B200_N], k6[B200_N], k7[B200_N];
 
@@ -31,20 +59,14 @@ struct B200Tsit5 {
     // one attempted step; returns EEst
     B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt,
                         real reltol, real abstol, int& nf) {
-        const real c1 = (real)0.161, c2 = (real)0.327, c3 = (real)0.9, c4 = (real)0.9800255409045097;
-        const real a21 = (real)0.161;
-        const real a31 = (real)-0.008480655492356989, a32 = (real)0.335480655492357;
-        const real a41 = (real)2.8971530571054935, a42 = (real)-6.359448489975075, a43 = (real)4.3622954328695815;
-        const real a51 = (real)5.325864828439257, a52 = (real)-11.748883564062828, a53 = (real)7.4955393428898365,
-                   a54 = (real)-0.09249506636175525;
-        const real a61 = (real)5.86145544294642, a62 = (real)-12.92096931784711, a63 = (real)8.159367898576159,
-                   a64 = (real)-0.071584973281401, a65 = (real)-0.028269050394068383;
-        const real a71 = (real)0.09646076681806523, a72 = (real)0.01, a73 = (real)0.4798896504144996,
-                   a74 = (real)1.379008574103742, a75 = (real)-3.290069515436081, a76 = (real)2.324710524099774;
-        const real bt1 = (real)-0.00178001105222577714, bt2 = (real)-0.0008164344596567469,
-                   bt3 = (real)0.007880878010261995, bt4 = (real)-0.1447110071732629,
-                   bt5 = (real)0.5823571654525552, bt6 = (real)-0.45808210592918697,
-                   bt7 = (real)0.015151515151515152;
+        const real c1 = B200_TSIT5_C.c1, c2 = B200_TSIT5_C.c2, c3 = B200_TSIT5_C.c3, c4 = B200_TSIT5_C.c4;
+#define B200_T5(name) const real name = B200_TSIT5_C.name
+        B200_T5(a21); B200_T5(a31); B200_T5(a32); B200_T5(a41); B200_T5(a42); B200_T5(a43);
+        B200_T5(a51); B200_T5(a52); B200_T5(a53); B200_T5(a54);
+        B200_T5(a61); B200_T5(a62); B200_T5(a63); B200_T5(a64); B200_T5(a65);
+        B200_T5(a71); B200_T5(a72); B200_T5(a73); B200_T5(a74); B200_T5(a75); B200_T5(a76);
+        B200_T5(bt1); B200_T5(bt2); B200_T5(bt3); B200_T5(bt4); B200_T5(bt5); B200_T5(bt6); B200_T5(bt7);
+#undef B200_T5
         real tmp[B200_N];
         const real a = dt * a21;
 #pragma unroll
@@ -94,7 +116,7 @@ struct B200Tsit5 {
             real r2 = r * r;
             acc = (i == 0) ? r2 : (acc + r2);
         }
-        return b200_sqrt(acc / (real)B200_N);
+        return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
     }
 
     // apply_step!/update_fsal!: fsalfirst = fsallast
@@ -108,14 +130,12 @@ struct B200Tsit5 {
 
     // _ode_interpolant(Θ, dt, y0, y1, k, ::Tsit5ConstantCache, nothing, Val{0})
     B200_D void interp(real th, real dt, const real* y0, const real* /*y1*/, real* out) const {
-        const real r11 = (real)1.0, r12 = (real)-2.763706197274826, r13 = (real)2.9132554618219126,
-                   r14 = (real)-1.0530884977290216;
-        const real r22 = (real)0.13169999999999998, r23 = (real)-0.2234, r24 = (real)0.1017;
-        const real r32 = (real)3.9302962368947516, r33 = (real)-5.941033872131505, r34 = (real)2.490627285651253;
-        const real r42 = (real)-12.411077166933676, r43 = (real)30.33818863028232, r44 = (real)-16.548102889244902;
-        const real r52 = (real)37.50931341651104, r53 = (real)-88.1789048947664, r54 = (real)47.37952196281928;
-        const real r62 = (real)-27.896526289197286, r63 = (real)65.09189467479366, r64 = (real)-34.87065786149661;
-        const real r72 = (real)1.5, r73 = (real)-4.0, r74 = (real)2.5;
+#define B200_T5(name) const real name = B200_TSIT5_C.name
+        B200_T5(r11); B200_T5(r12); B200_T5(r13); B200_T5(r14); B200_T5(r22); B200_T5(r23); B200_T5(r24);
+        B200_T5(r32); B200_T5(r33); B200_T5(r34); B200_T5(r42); B200_T5(r43); B200_T5(r44);
+        B200_T5(r52); B200_T5(r53); B200_T5(r54); B200_T5(r62); B200_T5(r63); B200_T5(r64);
+        B200_T5(r72); B200_T5(r73); B200_T5(r74);
+#undef B200_T5
         const real th2 = th * th;
         const real b1 = th * b200_fma(th, b200_fma(th, b200_fma(th, r14, r13), r12), r11);
         const real b2 = th2 * b200_fma(th, b200_fma(th, r24, r23), r22);
