@@ -82,7 +82,7 @@ typedef struct {
     double dtmin;         /* default 0 */
     double dtmax;         /* <= 0: tf - t0 */
     int64_t maxiters;     /* <= 0: 1000000 */
-    const double* saveat; /* explicit ascending grid, every entry in (t0, tf]; NULL/0: final state only.
+    const double* saveat; /* explicit ascending (non-decreasing) grid, every entry in (t0, tf]; NULL/0: final state only.
                              (The caller expands `saveat = h` with the reference's range arithmetic,
                              solve.jl:1103-1124.) */
     int32_t nsaveat;

@@ -385,8 +385,8 @@ int check_problem(int64_t N, const void* u0, const void* p, int np, double t0, d
         double prev = t0;
         for (int i = 0; i < o->nsaveat; ++i) {
             double s = o->saveat[i];
-            if (!(s > prev) || !(s <= tf))
-                return fail(B200ODE_EINVAL, "saveat must be strictly ascending with every entry in (t0, tf]");
+            if (!(s >= prev) || !(s > t0) || !(s <= tf))
+                return fail(B200ODE_EINVAL, "saveat must be ascending with every entry in (t0, tf]");
             prev = s;
         }
     }

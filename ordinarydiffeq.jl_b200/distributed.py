@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink).
+
+Trajectories are independent, so integration needs no communication at all.
+The ensemble is dealt to the ranks in interleaved blocks — a contiguous split would hand each GPU
+a different band of the swept parameter and therefore a different amount of adaptive-step work.
+Only the optional end-of-solve exchange uses a collective:
+  * `gather_in_order`: all-gather of the final states back into global trajectory order,
+  * `allreduce_mean`: ensemble mean from per-GPU partial sums (the device-side `reduction`).
+The reference's analogue is EnsembleDistributed's pmap over worker processes (SciMLBase, EXT;
+exercised at /root/reference/lib/DiffEqBase/test/downstream/distributed_ensemble.jl:43-51).
+"""
+import numpy as np
+
+BLOCK = 1024
+
+
+def shard_indices(N, world, rank, block=BLOCK):
+    """Global trajectory indices (0-based, ascending) owned by `rank`: blocks b with b % world == rank."""
+    nblocks = (N + block - 1) // block
+    mine = np.arange(rank, nblocks, world, dtype=np.int64)
+    idx = (mine[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).ravel()
+    return idx[idx < N]
+
+
+def shard_sizes(N, world, block=BLOCK):
+    return [int(shard_indices(N, world, r, block).shape[0]) for r in range(world)]
+
+
+def gather_in_order(local, N, block=BLOCK, group=None):
+    """local: tensor [m_rank, ...] holding this rank's trajectories in shard order.
+    Returns the tensor [N, ...] in global trajectory order on every rank (all_gather)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(N, world, block)
+    mmax = max(sizes)
+    pad = torch.zeros((mmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * mmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    full = torch.empty((N,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(world):
+        idx = torch.from_numpy(shard_indices(N, world, r, block)).to(local.device)
+        full[idx] = out[r * mmax: r * mmax + sizes[r]]
+    return full
+
+
+def allreduce_mean(local_sum, N, group=None):
+    """local_sum: float64 tensor [n] = sum of this rank's trajectories (b200ode_reduce_sum_device).
+    Returns the ensemble mean [n] on every rank."""
+    import torch.distributed as dist
+    total = local_sum.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total / float(N)

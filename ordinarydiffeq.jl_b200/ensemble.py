@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's ensemble interface for the B200 path.
+
+    prob  = ODEProblem(ODEFunction(f; jac, tgrad), u0, tspan, p)
+    eprob = EnsembleProblem(prob; prob_func, output_func, reduction, u_init, safetycopy)
+    sim   = solve(eprob, Tsit5(), EnsembleB200(); trajectories, batch_size, saveat, reltol, abstol, ...)
+
+mirrors `solve(::EnsembleProblem, alg, ensemblealg; kw...)` of SciMLBase (EXT; the contract the
+reference exercises at /root/reference/lib/DiffEqBase/test/downstream/ensemble.jl:51-112 and
+documents at /root/reference/NEWS.md:209-224): batches of `batch_size`, `prob_func(prob, ctx)`
+per trajectory, `output_func(sol, ctx) -> (out, rerun)`, `reduction(u, batch, I) -> (u, converged)`.
+
+What changes behind `EnsembleB200()`: nothing is solved on the host.  `prob_func` is evaluated
+only to harvest (u0_i, p_i) into flat tables (or is a `TableProbFunc` that already is a table),
+and one C-ABI call integrates the whole batch on the GPU.  There is no CPU fallback: any other
+ensemble algorithm raises.
+"""
+import time
+
+import numpy as np
+
+from . import _lib, codegen, lowlevel, ranges
+
+
+# ---- algorithms (names and traits of the reference) -------------------------------------------
+class _Alg:
+    alg_id = 0
+    order = 0
+    stiff = False
+
+    def __repr__(self):
+        return type(self).__name__ + "()"
+
+
+class Tsit5(_Alg):          # lib/OrdinaryDiffEqTsit5
+    alg_id, order = _lib.ALG_TSIT5, 5
+
+
+class Vern7(_Alg):          # lib/OrdinaryDiffEqVerner (lazy = true)
+    alg_id, order = _lib.ALG_VERN7, 7
+
+
+class Rosenbrock23(_Alg):   # lib/OrdinaryDiffEqRosenbrock
+    alg_id, order, stiff = _lib.ALG_ROSENBROCK23, 2, True
+
+
+class Rodas5P(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS5P, 5, True
+
+
+class EnsembleAlgorithm:
+    pass
+
+
+class EnsembleB200(EnsembleAlgorithm):
+    """The drop-in ensemble algorithm: all trajectories of a batch in one GPU launch."""
+
+    def __init__(self, device=None):
+        self.device = device
+
+
+class _NoCPU(EnsembleAlgorithm):
+    def __init__(self, *a, **k):
+        raise NotImplementedError(
+            type(self).__name__ + " is the reference's CPU path; this package only provides EnsembleB200() "
+            "and has no CPU fallback")
+
+
+class EnsembleSerial(_NoCPU):
+    pass
+
+
+class EnsembleThreads(_NoCPU):
+    pass
+
+
+class EnsembleDistributed(_NoCPU):
+    pass
+
+
+# ---- problem types ----------------------------------------------------------------------------
+class CSource:
+    """C source of a function `void name(real* out, const real* u, const real* p, const real t)`."""
+
+    def __init__(self, source, name):
+        self.source, self.name = source, name
+
+
+class ODEFunction:
+    """ODEFunction(f; jac, tgrad).  `f` is either a Python callable f(u, p, t) -> [exprs] traced with
+    sympy (stand-in for Symbolics tracing) or a CSource; jac/tgrad likewise, or None to have them
+    derived symbolically from a traceable f."""
+
+    def __init__(self, f, jac=None, tgrad=None, iip=False):
+        self.f, self.jac, self.tgrad, self.iip = f, jac, tgrad, iip
+
+    def sources(self, n, np_, f32, need_jac):
+        def one(obj, builder, fname):
+            if obj is None:
+                return None
+            if isinstance(obj, CSource):
+                return (obj.source, obj.name)
+            return builder(obj, n, np_, fname=fname, f32=f32, iip=self.iip)
+        rhs = one(self.f, codegen.build_function_c, "diffeqf")
+        jac = tg = None
+        if need_jac:
+            if self.jac is not None:
+                jac = one(self.jac, codegen.build_function_c, "diffeqjac")
+            elif not isinstance(self.f, CSource):
+                jac = codegen.build_jacobian_c(self.f, n, np_, f32=f32, iip=self.iip)
+            else:
+                raise ValueError("Rosenbrock methods need a Jacobian: ODEFunction(f; jac=...) with a CSource f")
+            if self.tgrad is not None:
+                tg = one(self.tgrad, codegen.build_function_c, "diffeqtgrad")
+            elif not isinstance(self.f, CSource):
+                tg = codegen.build_tgrad_c(self.f, n, np_, f32=f32, iip=self.iip)
+        return rhs, jac, tg
+
+
+class ODEProblem:
+    def __init__(self, f, u0, tspan, p=None, **kwargs):
+        self.f = f if isinstance(f, ODEFunction) else ODEFunction(f)
+        self.u0 = np.asarray(u0)
+        self.tspan = (tspan[0], tspan[1])
+        self.p = None if p is None else np.asarray(p)
+        self.kwargs = dict(kwargs)      # prob.kwargs are merged under solve's (lib/DiffEqBase/src/solve.jl:49-74)
+
+
+def remake(prob, u0=None, p=None, tspan=None):
+    return ODEProblem(prob.f, prob.u0 if u0 is None else u0, prob.tspan if tspan is None else tspan,
+                      prob.p if p is None else p, **prob.kwargs)
+
+
+class EnsembleContext:
+    def __init__(self, sim_id, repeat=1, rng=None):
+        self.sim_id, self.repeat, self.rng = sim_id, repeat, rng
+
+
+class TableProbFunc:
+    """prob_func given as tables: trajectory i (1-based sim_id) gets u0[i-1] and/or p[i-1].
+    Equivalent to `(prob, ctx) -> remake(prob; u0 = U0[ctx.sim_id], p = P[ctx.sim_id])` without
+    a million host-side calls."""
+
+    def __init__(self, u0=None, p=None):
+        self.u0 = None if u0 is None else np.asarray(u0)
+        self.p = None if p is None else np.asarray(p)
+
+    def __call__(self, prob, ctx):
+        i = ctx.sim_id - 1
+        return remake(prob, u0=None if self.u0 is None else self.u0[i], p=None if self.p is None else self.p[i])
+
+
+class EnsembleProblem:
+    def __init__(self, prob, prob_func=None, output_func=None, reduction=None, u_init=None, safetycopy=None):
+        self.prob = prob
+        self.prob_func = prob_func
+        self.output_func = output_func
+        self.reduction = reduction
+        self.u_init = u_init
+        self.safetycopy = safetycopy    # irrelevant here: the problem is never mutated
+
+
+# ---- solutions --------------------------------------------------------------------------------
+class DEStats:
+    def __init__(self, nf, naccept, nreject, njacs=0, nw=0, nsolve=0):
+        self.nf, self.naccept, self.nreject = int(nf), int(naccept), int(nreject)
+        self.njacs, self.nw, self.nsolve = int(njacs), int(nw), int(nsolve)
+
+
+class ODESolution:
+    def __init__(self, t, u, retcode, stats, prob=None, alg=None):
+        self.t, self.u, self.retcode, self.stats, self.prob, self.alg = t, u, retcode, stats, prob, alg
+
+    def __getitem__(self, i):
+        return self.u[i]
+
+    def __len__(self):
+        return len(self.t)
+
+
+class _LazySolutions:
+    """Vector{ODESolution} over the flat result arrays (materialised per index on demand)."""
+
+    def __init__(self, res, t0, alg, has_grid, u0=None, save_start=True, save_end=True):
+        self.res, self.t0, self.alg, self.has_grid = res, t0, alg, has_grid
+        self.u0, self.save_start, self.save_end = u0, save_start, save_end
+
+    def __len__(self):
+        return self.res["u_final"].shape[0]
+
+    def __getitem__(self, i):
+        r = self.res
+        if i < 0:
+            i += len(self)
+        if self.has_grid:
+            k = int(r["nsaved"][i])
+            t = np.array(r["ts"][:k])
+            u = r["us"][i, :k]
+            if k > 0 and r["retcode"][i] != _lib.RC_SUCCESS:
+                t[-1] = min(t[-1], r["t_final"][i])
+        else:
+            # save_everystep = false and no saveat: sol.t = [t0, t_end] (save_start / save_end)
+            ts, us = [], []
+            if self.save_start:
+                ts.append(self.t0)
+                us.append(self.u0 if self.u0.ndim == 1 else self.u0[i])
+            if self.save_end:
+                ts.append(r["t_final"][i])
+                us.append(r["u_final"][i])
+            t = np.array(ts)
+            u = np.stack(us) if us else np.zeros((0, r["u_final"].shape[1]), dtype=r["u_final"].dtype)
+        st = DEStats(r["nf"][i], r["naccept"][i], r["nreject"][i], r["njacs"][i], r["nw"][i], r["nsolve"][i])
+        return ODESolution(t, u, _lib.RETCODE_NAMES[int(r["retcode"][i])], st, alg=self.alg)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+class EnsembleSolution:
+    def __init__(self, u, elapsed, converged, arrays=None):
+        self.u, self.elapsed_time, self.converged, self.arrays = u, elapsed, converged, arrays
+
+    def __getitem__(self, i):
+        return self.u[i]
+
+    def __len__(self):
+        return len(self.u)
+
+
+# ---- solve ------------------------------------------------------------------------------------
+_ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "reltol",
+               "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags"}
+_program_cache = {}
+_handles = {}
+
+
+def _handle(device):
+    import torch
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if device not in _handles:
+        _handles[device] = _lib.Handle(device)
+    return _handles[device]
+
+
+def get_program(handle, alg, fn, n, np_, f32):
+    rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
+    key = (handle.device, alg.alg_id, f32, n, np_, rhs, jac, tg)
+    if key not in _program_cache:
+        _program_cache[key] = handle.compile(alg.alg_id, _lib.F32 if f32 else _lib.F64, n, np_, rhs[0], rhs[1],
+                                             jac[0] if jac else None, jac[1] if jac else None,
+                                             tg[0] if tg else None, tg[1] if tg else None)
+    return _program_cache[key]
+
+
+def _harvest(eprob, I, repeat=1):
+    """Evaluate prob_func for sim_ids in I -> (u0 table or shared vector, p table or shared vector)."""
+    prob, pf = eprob.prob, eprob.prob_func
+    if pf is None:
+        return prob.u0, prob.p
+    if isinstance(pf, TableProbFunc):
+        idx = np.asarray(I) - 1
+        u0 = prob.u0 if pf.u0 is None else pf.u0[idx]
+        p = prob.p if pf.p is None else pf.p[idx]
+        return u0, p
+    u0s, ps = [], []
+    for i in I:
+        q = pf(prob, EnsembleContext(int(i), repeat))
+        if tuple(q.tspan) != tuple(prob.tspan):
+            raise NotImplementedError("EnsembleB200: prob_func must not change tspan (all trajectories share it)")
+        u0s.append(np.asarray(q.u0))
+        ps.append(None if q.p is None else np.asarray(q.p))
+    u0 = np.stack(u0s)
+    p = None if ps[0] is None else np.stack(ps)
+    return u0, p
+
+
+def solve(eprob, alg, ensemblealg=None, **kw):
+    """solve(EnsembleProblem, alg, EnsembleB200(); trajectories, ...) -> EnsembleSolution."""
+    if not isinstance(eprob, EnsembleProblem):
+        raise TypeError("this package accelerates the EnsembleProblem path only")
+    if not isinstance(ensemblealg, EnsembleB200):
+        raise NotImplementedError("only EnsembleB200() is provided (no CPU fallback)")
+    if not isinstance(alg, _Alg):
+        raise TypeError("alg must be one of Tsit5(), Vern7(), Rosenbrock23(), Rodas5P()")
+    prob = eprob.prob
+    kw = dict(prob.kwargs, **kw)                      # merge_problem_kwargs: solve's kwargs win
+    bad = set(kw) - _ALLOWED_KW
+    if bad:
+        # the reference throws for unrecognised keywords (lib/DiffEqBase/src/solve.jl:79-93)
+        raise TypeError("unsupported keyword arguments for the EnsembleB200 path: %s" % sorted(bad))
+    if "trajectories" not in kw:
+        raise TypeError("trajectories is required")
+    has_saveat = kw.get("saveat", None) is not None and not (hasattr(kw["saveat"], "__len__") and len(kw["saveat"]) == 0)
+    if kw.get("save_everystep", not has_saveat):
+        # the reference's default is save_everystep = isempty(saveat) (solve.jl:138): ragged per-step output
+        raise NotImplementedError("save_everystep=true (ragged per-step output) is not on this path; "
+                                  "pass saveat=... or save_everystep=False")
+    if not kw.get("adaptive", True):
+        raise NotImplementedError("adaptive=false is not on this path")
+    if kw.get("dense", False):
+        raise NotImplementedError("dense=true is not on this path")
+    N = int(kw["trajectories"])
+    batch_size = int(kw.get("batch_size", N)) if N > 0 else 1
+    f32 = kw.get("dtype", None)
+    if f32 is None:
+        f32 = (prob.u0.dtype == np.float32)
+    else:
+        f32 = (np.dtype(f32) == np.float32)
+    n = int(prob.u0.shape[-1])
+    np_ = 0 if prob.p is None else int(np.asarray(prob.p).shape[-1])
+    grid = ranges.saveat_grid(kw.get("saveat", None), prob.tspan)
+    handle = _handle(ensemblealg.device)
+    program = get_program(handle, alg, prob.f, n, np_, f32)
+
+    t_start = time.perf_counter()
+    reduction, output_func = eprob.reduction, eprob.output_func
+    u_acc = [] if eprob.u_init is None else eprob.u_init
+    converged = False
+    all_arrays = []
+    for b0 in range(0, N, max(batch_size, 1)):
+        I = np.arange(b0 + 1, min(b0 + batch_size, N) + 1)
+        u0, p = _harvest(eprob, I)
+        res = lowlevel.solve_host(program, u0, p, prob.tspan, trajectories=len(I), reltol=kw.get("reltol"),
+                                  abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"),
+                                  maxiters=kw.get("maxiters"), saveat=grid if grid else None,
+                                  save_start=kw.get("save_start"), save_end=kw.get("save_end"),
+                                  flags=kw.get("flags", 0))
+        all_arrays.append(res)
+        ss = kw.get("save_start"); se = kw.get("save_end")
+        mk = lambda r, u0_: _LazySolutions(r, prob.tspan[0], alg, bool(grid), np.asarray(u0_),
+                                           True if ss is None else bool(ss), True if se is None else bool(se))
+        sols = mk(res, u0)
+        if output_func is None:
+            batch = sols
+        else:
+            batch = []
+            for k, i in enumerate(I):
+                out, rerun = output_func(sols[k], EnsembleContext(int(i), 1))
+                repeat = 1
+                while rerun:
+                    # re-solve this trajectory alone with repeat+1 (the driver's rerun loop)
+                    repeat += 1
+                    u0r, pr = _harvest(eprob, [int(i)], repeat)
+                    r1 = lowlevel.solve_host(program, u0r, pr, prob.tspan, trajectories=1, reltol=kw.get("reltol"),
+                                             abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
+                                             dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
+                                             saveat=grid if grid else None, save_start=kw.get("save_start"),
+                                             save_end=kw.get("save_end"))
+                    out, rerun = output_func(mk(r1, u0r)[0], EnsembleContext(int(i), repeat))
+                batch.append(out)
+        if reduction is None:
+            if isinstance(u_acc, list) and not u_acc and output_func is None and b0 + batch_size >= N and b0 == 0:
+                u_acc = batch                      # single batch, default reduction: keep the lazy view
+            else:
+                u_acc = list(u_acc) + list(batch)
+        else:
+            u_acc, converged = reduction(u_acc, batch, I)
+            if converged:
+                break
+    elapsed = time.perf_counter() - t_start
+    return EnsembleSolution(u_acc, elapsed, converged, arrays=all_arrays)

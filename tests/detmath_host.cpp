@@ -9,3 +9,7 @@ float t_fastpower_f(float x, float y) { return b200_fastpower(x, y); }
 double t_eps(double x) { return b200_eps(x); }
 float t_eps_f(float x) { return b200_eps(x); }
 }
+extern "C" {
+double t_div_const(double a, double b) { return b200_div_const(a, b, 1.0 / b); }
+float t_div_const_f(float a, float b) { return b200_div_const(a, b, 1.0f / b); }
+}

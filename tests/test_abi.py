@@ -1,0 +1,102 @@
+"""The C-ABI library loads, exports every symbol include/b200ode.h declares, validates its
+arguments, compiles through NVRTC without a GPU, and fails loudly when no device exists."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "b200ode.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200ode_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported(pkg):
+    L = pkg._lib.lib()
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), "libb200ode.so does not export %s" % n
+    assert sorted(pkg._lib.EXPORTS) == names, "ctypes binding and header disagree"
+
+
+def test_version_string(pkg):
+    assert b"b200ode" in pkg._lib.lib().b200ode_version()
+
+
+def test_nvrtc_compiles_all_algorithms_without_gpu(pkg):
+    pl = pkg.problems_library
+    for f32 in (False, True):
+        src, name = pl.lorenz_source(f32)
+        for alg in (pkg.ALG_TSIT5, pkg.ALG_VERN7):
+            cubin, log = pkg.compile_only(alg, pkg.F32 if f32 else pkg.F64, 3, 3, src, name)
+            assert len(cubin) > 1000 and "b200_integrate" in log
+        (r, j, tg) = pl.robertson_sources(f32)
+        for alg in (pkg.ALG_ROSENBROCK23, pkg.ALG_RODAS5P):
+            cubin, log = pkg.compile_only(alg, pkg.F32 if f32 else pkg.F64, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1])
+            assert len(cubin) > 1000
+
+
+def test_headline_kernel_has_no_spills(pkg):
+    src, name = pkg.problems_library.lorenz_source(False)
+    _, log = pkg.compile_only(pkg.ALG_TSIT5, pkg.F64, 3, 3, src, name)
+    m = re.search(r"Function properties for b200_integrate\s*\n\s*ptxas\s*\.\s*(\d+) bytes stack frame, (\d+) bytes spill stores", log)
+    assert m, log
+    assert int(m.group(2)) <= 16
+    regs = int(re.search(r"b200_integrate.*?Used (\d+) registers", log, re.S).group(1))
+    assert regs <= 128      # 4 CTAs x 128 threads per SM
+
+
+def test_symbolics_style_source_with_include_line(pkg):
+    src = "#include <math.h>\nvoid diffeqf(double* du, const double* RHS1, const double* RHS2, const double RHS3) {\n" \
+          "  du[0] = RHS2[0] * RHS1[0] + sqrt(RHS1[0] * RHS1[0]);\n}\n"
+    cubin, _ = pkg.compile_only(pkg.ALG_TSIT5, pkg.F64, 1, 1, src, "diffeqf")
+    assert len(cubin) > 1000
+
+
+def test_compile_errors_are_reported(pkg):
+    with pytest.raises(pkg.B200Error) as e:
+        pkg.compile_only(pkg.ALG_TSIT5, pkg.F64, 3, 3, "void f(double* du, const double* u, const double* p, const double t) { du[0] = nope; }", "f")
+    assert e.value.code == pkg._lib.ECOMPILE and "nope" in str(e.value)
+    with pytest.raises(pkg.B200Error) as e:
+        pkg.compile_only(99, pkg.F64, 3, 3, "x", "f")
+    assert e.value.code == pkg._lib.EINVAL
+    with pytest.raises(pkg.B200Error) as e:
+        pkg.compile_only(pkg.ALG_TSIT5, pkg.F64, 0, 3, "x", "f")
+    assert e.value.code == pkg._lib.EINVAL
+    with pytest.raises(pkg.B200Error) as e:     # Rosenbrock without a Jacobian
+        src, name = pkg.problems_library.lorenz_source(False)
+        pkg.compile_only(pkg.ALG_RODAS5P, pkg.F64, 3, 3, src, name)
+    assert e.value.code == pkg._lib.EINVAL
+
+
+def test_nslots_matches_reference_save_rules(pkg):
+    ll = pkg.lowlevel
+    # saveat=4.0 on (0,15): t == [0,4,8,12,15]  (test/InterfaceI/ode_saveat_tests.jl)
+    assert ll.nslots_for((0.0, 15.0), [4.0, 8.0, 12.0]) == 5
+    assert ll.nslots_for((0.0, 15.0), [4.0, 8.0, 12.0], save_end=False) == 4
+    assert ll.nslots_for((0.0, 15.0), [4.0, 8.0, 12.0], save_start=False, save_end=False) == 3
+    assert ll.nslots_for((0.0, 10.0), [5.0, 10.0]) == 3
+    assert ll.nslots_for((0.0, 10.0), [5.0, 10.0], save_end=False) == 2     # skip_saveat_at_tspan_end
+    assert ll.nslots_for((0.0, 10.0), None) == 0
+
+
+def test_no_gpu_fails_loudly(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.B200Error) as e:
+        pkg.Handle(0)
+    assert e.value.code == pkg._lib.ECUDA and "no CPU fallback" in str(e.value)
+
+
+def test_package_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "ordinarydiffeq.jl_b200")
+    for dp, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".jl")):
+                text = open(os.path.join(dp, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f

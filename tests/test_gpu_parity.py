@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs — bit-exact step counts, stats, final states and saveat rows, FP64 and FP32 — plus
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerances: none.  Oracle and kernel perform the same IEEE operations in the same order (explicit
+fma where the reference's @muladd fuses, no contraction elsewhere), so every comparison below is
+equality of bits; this is stronger than north_star's 1e-10 (FP64) / reltol-scaled (FP32) bounds."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_result, bits, linear_source
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def progs(pkg, handle):
+    cache = {}
+
+    def get(alg, f32, problem):
+        key = (alg, f32, problem)
+        if key not in cache:
+            pl = pkg.problems_library
+            dt = pkg.F32 if f32 else pkg.F64
+            if problem == "lorenz":
+                s, n = pl.lorenz_source(f32)
+                cache[key] = handle.compile(alg, dt, 3, 3, s, n)
+            elif problem == "robertson":
+                (r, j, tg) = pl.robertson_sources(f32)
+                cache[key] = handle.compile(alg, dt, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1])
+            elif problem == "pleiades":
+                s, n = pl.pleiades_source(f32)
+                cache[key] = handle.compile(alg, dt, 28, 0, s, n)
+            elif problem == "linear":
+                s, n = linear_source(f32)
+                cache[key] = handle.compile(alg, dt, 1, 0, s, n)
+        return cache[key]
+    return get
+
+
+U0 = np.array([1.0, 0.0, 0.0])
+GRID = [k / 10 for k in range(1, 101)]
+
+
+# ---- configs[0]: Lorenz Tsit5 10k trajectories, reltol 1e-8 -------------------------------------
+def test_config1_lorenz_tsit5_10k(pkg, progs, oracle):
+    N = 10000
+    p = pkg.problems_library.lorenz_params(N)
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), U0, p, (0.0, 10.0), reltol=1e-8)
+    o = oracle.solve(oracle.ALG_TSIT5, pkg.problems_library.lorenz_source(), U0, p, (0.0, 10.0), 3, 3, reltol=1e-8)
+    assert_same_result(g, o)
+    assert (g["retcode"] == 1).all() and (g["t_final"] == 10.0).all()
+
+
+@pytest.mark.parametrize("f32", [False, True])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_config2_lorenz_tsit5_saveat(pkg, progs, oracle, f32, flags):
+    N = 4096
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N, f32=f32)
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, f32, "lorenz"), U0, p, (0.0, 10.0), saveat=GRID, flags=flags)
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(f32), U0, p, (0.0, 10.0), 3, 3, f32=f32, saveat=GRID)
+    assert g["nslots"] == 101
+    assert_same_result(g, o)
+
+
+@pytest.mark.parametrize("alg_name", ["ros23", "rodas5p"])
+@pytest.mark.parametrize("f32", [False, True])
+def test_config3_robertson(pkg, progs, oracle, alg_name, f32):
+    N = 2048
+    pl = pkg.problems_library
+    alg, oalg = {"ros23": (pkg.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK23),
+                 "rodas5p": (pkg.ALG_RODAS5P, oracle.ALG_RODAS5P)}[alg_name]
+    r, j, tg = pl.robertson_sources(f32)
+    p = pl.robertson_params(N, f32=f32)
+    tf = 1e5 if not f32 else 1e3
+    tol = dict(reltol=1e-6, abstol=1e-8) if not f32 else dict(reltol=1e-3, abstol=1e-5)
+    for extra in ({}, {"saveat": [tf * 1e-3, tf * 1e-2, tf * 0.5]}):
+        kw = dict(tol, **extra)
+        g = pkg.lowlevel.solve_host(progs(alg, f32, "robertson"), U0, p, (0.0, tf), **kw)
+        o = oracle.solve(oalg, r, U0, p, (0.0, tf), 3, 3, f32=f32, jac=j, tgrad=tg, **kw)
+        assert_same_result(g, o)
+        assert (g["retcode"] == 1).all()
+        assert (g["njacs"] == 2 * (g["naccept"] + g["nreject"])).all()
+        assert np.abs(g["u_final"].astype(np.float64).sum(axis=1) - 1.0).max() < (1e-9 if not f32 else 1e-3)
+
+
+def test_config4_pleiades_vern7(pkg, progs, oracle):
+    N = 512
+    pl = pkg.problems_library
+    u0 = pl.pleiades_u0(N)
+    kw = dict(reltol=1e-6, abstol=1e-8)
+    for extra in ({}, {"saveat": [0.5, 1.0, 1.5, 2.0, 2.5, 3.0]}):
+        g = pkg.lowlevel.solve_host(progs(pkg.ALG_VERN7, False, "pleiades"), u0, None, (0.0, 3.0), **dict(kw, **extra))
+        o = oracle.solve(oracle.ALG_VERN7, pl.pleiades_source(), u0, None, (0.0, 3.0), 28, 0, **dict(kw, **extra))
+        assert_same_result(g, o)
+        assert (g["nf"] == 2 + 10 * (g["naccept"] + g["nreject"])).all()
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_vern7_lorenz_with_lazy_interpolation(pkg, progs, oracle, f32):
+    N = 2048
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N, f32=f32)
+    grid = [k / 2 for k in range(1, 21)]
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_VERN7, f32, "lorenz"), U0, p, (0.0, 10.0), saveat=grid)
+    o = oracle.solve(oracle.ALG_VERN7, pl.lorenz_source(f32), U0, p, (0.0, 10.0), 3, 3, f32=f32, saveat=grid)
+    assert_same_result(g, o)
+
+
+# ---- edge cases the reference tests exercise -----------------------------------------------------
+@pytest.mark.parametrize("N", [1, 31, 33, 1000])
+def test_ragged_trajectory_counts(pkg, progs, oracle, N):
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N)
+    for flags in (0, 1):
+        g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), U0, p, (0.0, 3.0), saveat=[1.0, 2.5], flags=flags)
+        o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, p, (0.0, 3.0), 3, 3, saveat=[1.0, 2.5])
+        assert_same_result(g, o)
+
+
+def test_zero_trajectories(pkg, progs):
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), np.zeros((0, 3)), np.zeros((0, 3)), (0.0, 1.0))
+    assert g["u_final"].shape == (0, 3)
+
+
+@pytest.mark.parametrize("save_start,save_end,grid,expect_ts", [
+    (None, None, [4.0, 8.0, 12.0], [0.0, 4.0, 8.0, 12.0, 15.0]),      # test/InterfaceI/ode_saveat_tests.jl
+    (False, None, [4.0, 8.0, 12.0], [4.0, 8.0, 12.0, 15.0]),
+    (None, False, [4.0, 8.0, 12.0], [0.0, 4.0, 8.0, 12.0]),
+    (False, False, [4.0, 8.0, 12.0], [4.0, 8.0, 12.0]),
+    (None, None, [5.0, 15.0], [0.0, 5.0, 15.0]),
+    (None, False, [5.0, 15.0], [0.0, 5.0]),                            # skip_saveat_at_tspan_end
+    (None, None, [5.0, 5.0, 7.0], [0.0, 5.0, 5.0, 7.0, 15.0]),         # duplicates are saved twice (heap order)
+])
+def test_saveat_bookkeeping(pkg, progs, oracle, save_start, save_end, grid, expect_ts):
+    pl = pkg.problems_library
+    N = 64
+    p = pl.lorenz_params(N)
+    kw = dict(saveat=grid, save_start=save_start, save_end=save_end)
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), U0, p, (0.0, 15.0), **kw)
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, p, (0.0, 15.0), 3, 3, **kw)
+    assert list(g["ts"]) == expect_ts
+    assert_same_result(g, o)
+
+
+def test_shared_and_per_trajectory_inputs(pkg, progs, oracle):
+    pl = pkg.problems_library
+    N = 257
+    rng = np.random.default_rng(5)
+    u0 = np.array([1.0, 0, 0]) + 0.1 * rng.standard_normal((N, 3))
+    pshared = np.array([10.0, 28.0, 8 / 3])
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), u0, pshared, (0.0, 2.0))
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), u0, pshared, (0.0, 2.0), 3, 3)
+    assert_same_result(g, o)
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), U0, pshared, (0.0, 2.0), trajectories=5)
+    assert (bits(g["u_final"]) == bits(g["u_final"][0])).all()
+
+
+def test_user_dt_dtmax_and_negative_t0(pkg, progs, oracle):
+    pl = pkg.problems_library
+    N = 128
+    p = pl.lorenz_params(N)
+    for kw, tspan in ((dict(dt=0.01), (0.0, 2.0)), (dict(dtmax=0.05), (0.0, 2.0)), (dict(), (-5.0, -3.0)),
+                      (dict(saveat=[-4.5, -3.25]), (-5.0, -3.0)), (dict(dtmin=1e-4), (0.0, 2.0))):
+        g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), U0, p, tspan, **kw)
+        o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, p, tspan, 3, 3, **kw)
+        assert_same_result(g, o)
+
+
+def test_failure_retcodes_do_not_stall_the_warp(pkg, handle, progs, oracle):
+    """A failing trajectory gets a retcode and leaves its lane; its warp mates finish normally
+    (check_error.jl:77-117).  maxiters: MaxIters.  RHS with a pole: Unstable/DtLessThanMin/DtNaN."""
+    pl = pkg.problems_library
+    N = 200
+    p = pl.lorenz_params(N)
+    g = pkg.lowlevel.solve_host(progs(pkg.ALG_TSIT5, False, "lorenz"), U0, p, (0.0, 10.0), maxiters=100, saveat=[5.0])
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, p, (0.0, 10.0), 3, 3, maxiters=100, saveat=[5.0])
+    assert_same_result(g, o)
+    assert set(np.unique(g["retcode"])) == {1, 2}
+    assert (g["t_final"][g["retcode"] == 2] < 10.0).all()
+    # blow-up in finite time: u' = u^2, u0 = p => pole at t = 1/p; some trajectories reach tf first
+    src = ("void blow(double* du, const double* u, const double* p, const double t) { du[0] = u[0] * u[0]; }\n", "blow")
+    prog = handle.compile(pkg.ALG_TSIT5, pkg.F64, 1, 1, src[0], src[1])
+    u0 = np.linspace(0.5, 2.0, 64).reshape(64, 1)
+    pp = np.zeros((64, 1))
+    g = pkg.lowlevel.solve_host(prog, u0, pp, (0.0, 1.0))
+    o = oracle.solve(oracle.ALG_TSIT5, src, u0, pp, (0.0, 1.0), 1, 1)
+    assert_same_result(g, o)
+    assert (g["retcode"][u0[:, 0] < 0.9] == 1).all() and (g["retcode"][u0[:, 0] > 1.1] != 1).all()
+
+
+def test_device_api_soa_layout(pkg, progs, oracle):
+    import torch
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    N = 3000
+    prog = progs(pkg.ALG_TSIT5, False, "lorenz")
+    p = pl.lorenz_params(N)
+    nslots = ll.nslots_for((0.0, 10.0), GRID)
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, p, (0.0, 10.0), 3, 3, saveat=GRID)
+    for layout in (pkg._lib.LAYOUT_AOS, pkg._lib.LAYOUT_SOA):
+        b = ll.DeviceBuffers(prog, N, nslots, "cuda:0", u0_shared=True, layout=layout)
+        b.u0.copy_(torch.from_numpy(U0))
+        pt = torch.from_numpy(p)
+        b.p.copy_(pt if layout == pkg._lib.LAYOUT_AOS else pt.t().contiguous())
+        ll.solve_device(prog, b, (0.0, 10.0), saveat=GRID)
+        torch.cuda.synchronize()
+        uf = b.u_final.cpu().numpy()
+        uf = uf if layout == pkg._lib.LAYOUT_AOS else uf.T
+        assert np.array_equal(bits(np.ascontiguousarray(uf)), bits(o["u_final"]))
+        assert np.array_equal(bits(b.us.cpu().numpy()), bits(o["us"]))
+        assert np.array_equal(b.naccept.cpu().numpy(), o["naccept"])
+        # deterministic on-device reduction == host sum in the same order class
+        out = torch.zeros(3, dtype=torch.float64, device="cuda:0")
+        ll.reduce_sum_device(prog.handle, pkg.F64, b.u_final, layout, N, 3, out)
+        torch.cuda.synchronize()
+        assert np.allclose(out.cpu().numpy(), o["u_final"].sum(axis=0), rtol=1e-12)
+
+
+# ---- full-size properties (BASELINE sizes; the oracle checks a seeded subsample) ------------------
+def test_full_size_1M_lorenz_properties(pkg, progs, oracle):
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    N = 1 << 20
+    p = pl.lorenz_params(N)
+    prog = progs(pkg.ALG_TSIT5, False, "lorenz")
+    g = ll.solve_host(prog, U0, p, (0.0, 10.0), saveat=GRID)
+    assert (g["retcode"] == 1).all() and (g["nsaved"] == 101).all() and (g["t_final"] == 10.0).all()
+    assert (g["nf"] == 3 + 6 * (g["naccept"] + g["nreject"])).all()
+    assert np.array_equal(bits(g["us"][:, -1, :]), bits(g["u_final"]))          # last row is u(tf)
+    assert (g["us"][:, 0, :] == U0).all()
+    # schedule independence: lane refill vs one-thread-per-trajectory give identical bits
+    s = ll.solve_host(prog, U0, p, (0.0, 10.0), saveat=GRID, flags=pkg._lib.FLAG_STATIC_SCHEDULE)
+    for k in ("naccept", "nreject", "nf", "retcode", "nsaved"):
+        assert np.array_equal(g[k], s[k])
+    assert np.array_equal(bits(g["us"]), bits(s["us"]))
+    # permutation equivariance: shuffled inputs give the shuffled outputs
+    perm = np.random.default_rng(7).permutation(N)
+    q = ll.solve_host(prog, U0, p[perm], (0.0, 10.0))
+    assert np.array_equal(bits(q["u_final"]), bits(g["u_final"][perm]))
+    assert np.array_equal(q["naccept"], g["naccept"][perm])
+    # oracle on a seeded subsample of the full run
+    idx = np.sort(np.random.default_rng(8).choice(N, 3000, replace=False))
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, p[idx], (0.0, 10.0), 3, 3, saveat=GRID)
+    assert np.array_equal(g["naccept"][idx], o["naccept"]) and np.array_equal(g["nreject"][idx], o["nreject"])
+    assert np.array_equal(bits(g["us"][idx]), bits(o["us"]))
+
+
+def test_high_level_solve_api(pkg, oracle):
+    P = pkg
+    pl = P.problems_library
+    N = 500
+    table = pl.lorenz_params(N)
+    prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (0.0, 10.0), table[0])
+    # prob_func as a Python closure (harvested on the host) and as a table give the same ensemble
+    ep1 = P.EnsembleProblem(prob, prob_func=lambda pr, ctx: P.remake(pr, p=table[ctx.sim_id - 1]))
+    ep2 = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table))
+    s1 = P.solve(ep1, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.1)
+    s2 = P.solve(ep2, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.1)
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (0.0, 10.0), 3, 3, saveat=GRID)
+    assert len(s1) == N and s1.converged is False
+    for i in (0, 17, N - 1):
+        assert s1[i].retcode == "Success" and len(s1[i].t) == 101 and s1[i].t[3] == 0.3
+        assert np.array_equal(bits(np.ascontiguousarray(s1[i].u)), bits(o["us"][i]))
+        assert np.array_equal(bits(np.ascontiguousarray(s2[i].u)), bits(o["us"][i]))
+        assert s1[i].stats.naccept == o["naccept"][i] and s1[i].stats.nf == o["nf"][i]
+    # reduction with batches and early stop (lib/DiffEqBase/test/downstream/ensemble.jl:51-112)
+    seen = []
+
+    def reduction(u, batch, I):
+        seen.append(list(I))
+        u = u + [float(np.mean([b for b in batch]))]
+        return u, len(u) >= 3
+    ep3 = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table), output_func=lambda sol, ctx: (sol.u[-1][0], False),
+                            reduction=reduction, u_init=[])
+    s3 = P.solve(ep3, P.Tsit5(), P.EnsembleB200(), trajectories=N, batch_size=100, save_everystep=False)
+    assert s3.converged is True and len(s3.u) == 3 and seen[0] == list(range(1, 101)) and len(seen) == 3
+    assert s3.u[0] == pytest.approx(float(o["u_final"][:100, 0].mean()), rel=1e-13)
+    # sympy-traced RHS (stand-in for Symbolics build_function) through the same entry point
+    f = lambda u, p, t: [p[0] * (u[1] - u[0]), u[0] * (p[1] - u[2]) - u[1], u[0] * u[1] - p[2] * u[2]]
+    ep4 = P.EnsembleProblem(P.ODEProblem(f, U0, (0.0, 10.0), table[0]), prob_func=P.TableProbFunc(p=table))
+    s4 = P.solve(ep4, P.Tsit5(), P.EnsembleB200(), trajectories=N, save_everystep=False)
+    assert np.allclose(np.stack([s4[i].u[-1] for i in range(N)]), o["u_final"], rtol=1e-6, atol=1e-6)
+    # Rosenbrock with a symbolically derived Jacobian
+    rob = lambda u, p, t: [-p[0] * u[0] + p[2] * u[1] * u[2], p[0] * u[0] - p[1] * u[1] ** 2 - p[2] * u[1] * u[2],
+                           p[1] * u[1] ** 2]
+    ktab = pl.robertson_params(64)
+    ep5 = P.EnsembleProblem(P.ODEProblem(rob, U0, (0.0, 1e5), ktab[0]), prob_func=P.TableProbFunc(p=ktab))
+    s5 = P.solve(ep5, P.Rodas5P(), P.EnsembleB200(), trajectories=64, save_everystep=False, reltol=1e-6, abstol=1e-8)
+    assert all(s5[i].retcode == "Success" for i in range(64))
+    assert abs(float(s5[3].u[-1].sum()) - 1.0) < 1e-9

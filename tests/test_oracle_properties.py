@@ -1,0 +1,305 @@
+"""Pins the CPU oracle against every known-answer / property test the reference's own suite
+offers for this path.  The reference holds no golden vectors for ensemble
+step counts, so these — plus the regression pins in tests/golden — are what anchors the oracle.
+Each test cites the reference test it replays."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from helpers import counting_source, linear2d_source, linear_jac_sources, linear_source
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---- scalar known answers -------------------------------------------------------------------
+def test_default_norm_known_answers():
+    # lib/DiffEqBase/test/ode_default_norm.jl:13-16: ODE_DEFAULT_NORM(ones(3), 0.0) == 1.0
+    # (:50-54's 1.2909944487358056 is the norm of nested Duals — 20/12 under the root — not of plain [1,2,3])
+    L = oracle.lib()
+    one = np.ones(3)
+    assert L.oracle_norm(one.ctypes.data, 3) == 1.0
+    v = np.array([1.0, 2.0, 3.0])
+    assert L.oracle_norm(v.ctypes.data, 3) == math.sqrt(14.0 / 3.0)
+    w = np.array([1.0, 2.0, 3.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0])   # values and partials of u8
+    assert L.oracle_norm(w.ctypes.data, 12) == pytest.approx(1.2909944487358056, rel=1e-15)
+
+
+def test_julia_eps():
+    L = oracle.lib()
+    assert L.oracle_eps(1.0) == 2.0 ** -52
+    assert L.oracle_eps(0.0) == 5e-324
+    assert L.oracle_eps(10.0) == 2.0 ** -49
+    assert L.oracle_eps(-3.0) == 2.0 ** -51
+    assert math.isnan(L.oracle_eps(float("inf")))
+
+
+def test_fastpower_is_a_float32_approximation_of_pow():
+    # FastPower.jl contract: |fastpower(x,y) - x^y| small relative error, exact special cases
+    L = oracle.lib()
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        x = 10 ** rng.uniform(-8, 3)
+        y = rng.uniform(0.02, 0.4)
+        assert L.oracle_fastpower(x, y) == pytest.approx(x ** y, rel=2e-4)
+    assert L.oracle_fastpower(0.0, 0.14) == 0.0
+    assert L.oracle_fastpower(1.0, 0.14) == 1.0
+
+
+def test_log10_exp10_correctly_rounded():
+    import mpmath as mp
+    mp.mp.prec = 300
+    L = oracle.lib()
+    rng = np.random.default_rng(1)
+    for _ in range(3000):
+        x = float(10 ** rng.uniform(-15, 12))
+        assert L.oracle_log10(x) == float(mp.log10(mp.mpf(x)))
+        y = float(rng.uniform(-20, 4))
+        assert L.oracle_exp10(y) == float(mp.power(10, mp.mpf(y)))
+
+
+# ---- saveat grids ---------------------------------------------------------------------------
+def test_saveat_grid_known_answers(pkg):
+    # test/InterfaceI/ode_saveat_tests.jl:38-41,185-190,246-253
+    rhs = linear_source()
+    grid = pkg.ranges.saveat_grid(4.0, (0.0, 15.0))
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([0.5]), None, (0.0, 15.0), 1, 0, trajectories=1, saveat=grid)
+    assert list(o["ts"]) == [0.0, 4.0, 8.0, 12.0, 15.0] and o["nsaved"][0] == 5
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([0.5]), None, (0.0, 15.0), 1, 0, trajectories=1, saveat=grid,
+                     save_start=False, save_end=False)
+    assert list(o["ts"]) == [4.0, 8.0, 12.0]
+    grid = pkg.ranges.saveat_grid(0.1, (0.0, 1.0))
+    assert grid == [0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]      # i/10 correctly rounded, not i*0.1
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, saveat=grid)
+    assert o["nsaved"][0] == 11 and o["ts"][-1] == 1.0
+    exact = 0.5 * np.exp(1.01 * o["ts"])
+    assert np.abs(o["us"][0, :, 0] - exact).max() < 2e-4
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, saveat=grid,
+                     save_end=False)
+    assert o["nsaved"][0] == 10 and o["ts"][-1] == 0.9                      # skip_saveat_at_tspan_end
+
+
+# ---- nf accounting --------------------------------------------------------------------------
+def test_nf_equals_number_of_rhs_calls():
+    # test/InterfaceIII/stats_tests.jl:22-43
+    rhs = counting_source()
+    user = oracle.compile_user([rhs[0]])
+    user.b200_test_get_calls.restype = __import__("ctypes").c_long
+    p = np.array([10.0, 28.0, 8.0 / 3.0])
+    for alg, per_attempt, init in ((oracle.ALG_TSIT5, 6, 3), (oracle.ALG_VERN7, 10, 2)):
+        user.b200_test_reset_calls()
+        o = oracle.solve(alg, rhs, np.array([1.0, 0.0, 0.0]), p, (0.0, 5.0), 3, 3, trajectories=1, nthreads=1)
+        calls = user.b200_test_get_calls()
+        assert o["nf"][0] == calls
+        assert o["nf"][0] == init + per_attempt * (o["naccept"][0] + o["nreject"][0])
+    # lazy Vern7 interpolation stages are evaluated but NOT counted (verner_addsteps.jl has no increment_nf!)
+    user.b200_test_reset_calls()
+    o = oracle.solve(oracle.ALG_VERN7, rhs, np.array([1.0, 0.0, 0.0]), p, (0.0, 5.0), 3, 3, trajectories=1, nthreads=1,
+                     saveat=[1.0, 2.5, 4.0])
+    assert user.b200_test_get_calls() > o["nf"][0]
+    assert (user.b200_test_get_calls() - o["nf"][0]) % 6 == 0
+
+
+# ---- convergence order on u' = 1.01 u -------------------------------------------------------
+def _fixed_step_l2_error(alg, h, stiff=False):
+    """Fixed step size through the adaptive code: tolerances so loose every step is accepted,
+    dt = dtmax = h (the controller's growth is clamped by dtmax).  Returns the l2 error over the
+    step end points, DiffEqDevTools.test_convergence's `:l2`."""
+    jac, tg = linear_jac_sources()
+    kw = dict(jac=jac, tgrad=tg) if stiff else {}
+    pts = [k * h for k in range(1, round(1 / h) + 1)]
+    o = oracle.solve(alg, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, dt=h, dtmax=h,
+                     reltol=1e12, abstol=1e12, saveat=pts, **kw)
+    assert o["nreject"][0] == 0 and o["naccept"][0] == round(1.0 / h)
+    e = o["us"][0, :, 0] - 0.5 * np.exp(1.01 * o["ts"])
+    return math.sqrt(np.mean(e * e))
+
+
+@pytest.mark.parametrize("alg,order,exps,tol,stiff", [
+    # dts and tolerances of the reference tests; the estimate is the mean log2 ratio like 𝒪est
+    (oracle.ALG_TSIT5, 5, (7, 6, 5, 4, 3), 0.4, False),    # test/Regression_II/ode_unrolled_comparison_tests.jl:70-77
+    (oracle.ALG_VERN7, 7, (3, 2, 1), 0.4, False),          # lib/OrdinaryDiffEqVerner/test/ode_verner_tests.jl:61-65 (BigFloat there; larger dts in binary64)
+    (oracle.ALG_ROSENBROCK23, 2, (6, 5, 4, 3), 0.2, True),  # lib/OrdinaryDiffEqRosenbrock/test/ode_rosenbrock_tests.jl:15-23
+])
+def test_convergence_order(alg, order, exps, tol, stiff):
+    errs = [_fixed_step_l2_error(alg, 0.5 ** k, stiff) for k in exps]
+    rates = [math.log2(errs[i + 1] / errs[i]) for i in range(len(errs) - 1)]
+    assert abs(np.mean(rates) - order) < tol, (errs, rates)
+
+
+def test_rodas5p_is_at_least_fifth_order():
+    errs = [_fixed_step_l2_error(oracle.ALG_RODAS5P, 0.5 ** k, True) for k in (4, 3, 2)]
+    rates = [math.log2(errs[i + 1] / errs[i]) for i in range(len(errs) - 1)]
+    assert np.mean(rates) > 4.8, (errs, rates)
+
+
+def test_2d_linear_matches_scalar():
+    # prob_ode_2Dlinear: every component is the scalar problem
+    rhs8 = linear2d_source(8)
+    o8 = oracle.solve(oracle.ALG_TSIT5, rhs8, np.full(8, 0.5), None, (0.0, 1.0), 8, 0, trajectories=1)
+    o1 = oracle.solve(oracle.ALG_TSIT5, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1)
+    assert o8["naccept"][0] == o1["naccept"][0]
+    assert np.allclose(o8["u_final"][0], o1["u_final"][0, 0], rtol=1e-14)
+
+
+# ---- cross-implementation: unrolled stepper vs a generic tableau RK ---------------------------
+def _tsit5_butcher():
+    c = [0, 0.161, 0.327, 0.9, 0.9800255409045097, 1, 1]
+    A = [[], [0.161], [-0.008480655492356989, 0.335480655492357],
+         [2.8971530571054935, -6.359448489975075, 4.3622954328695815],
+         [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525],
+         [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383],
+         [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774]]
+    return c, A
+
+
+def test_unrolled_tsit5_agrees_with_generic_tableau_rk():
+    # test/Regression_II/ode_unrolled_comparison_tests.jl:79-96: fixed dt, agreement to 1e-10
+    c, A = _tsit5_butcher()
+    import mpmath as mp
+    for i in range(1, 7):
+        assert abs(sum(A[i]) - c[i]) < 1e-15                  # row sums = c
+    h = 1 / 16
+    u = 0.5
+    for _ in range(16):
+        k = []
+        for i in range(7):
+            ui = u + h * sum(a * kk for a, kk in zip(A[i], k))
+            k.append(1.01 * ui)
+        u = u + h * sum(a * kk for a, kk in zip(A[6], k[:6]))
+    o = oracle.solve(oracle.ALG_TSIT5, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1,
+                     dt=h, dtmax=h, reltol=1e12, abstol=1e12)
+    assert abs(o["u_final"][0, 0] - u) < 1e-10
+
+
+def test_tableau_consistency():
+    # Σ b̃ = 0 (error estimator annihilates constants), interpolant b_i(1) = a_7i
+    bt = [-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+          0.5823571654525552, -0.45808210592918697, 0.015151515151515152]
+    assert abs(sum(bt)) < 1e-15
+    text = open(os.path.join(HERE, "..", "oracle", "oracle_tableaus_gen.inc")).read()
+    import re
+    vals = dict(re.findall(r"X\((\w+), ([-+0-9.eE]+)\)", text))
+    v = {k: float(x) for k, x in vals.items()}
+    cs = {2: ["a021"], 3: ["a031", "a032"], 4: ["a041", "a043"], 5: ["a051", "a053", "a054"],
+          6: ["a061", "a063", "a064", "a065"], 7: ["a071", "a073", "a074", "a075", "a076"],
+          8: ["a081", "a083", "a084", "a085", "a086", "a087"]}
+    for i, names in cs.items():
+        assert abs(sum(v[n] for n in names) - v["c%d" % i]) < 1e-13          # Vern7 row sums = c
+    assert abs(sum(v[n] for n in ["a091", "a093", "a094", "a095", "a096", "a097", "a098"]) - 1) < 1e-13
+    assert abs(sum(v[n] for n in ["b1", "b4", "b5", "b6", "b7", "b8", "b9"]) - 1) < 1e-14
+    assert abs(sum(v["btilde%d" % i] for i in (1, 4, 5, 6, 7, 8, 9, 10))) < 1e-15
+    for i, cc in ((11, 1.0), (12, 0.29), (13, 0.125), (14, 0.25), (15, 0.53), (16, 0.79)):
+        row = sum(x for k, x in v.items() if k.startswith("a%d" % i) and len(k) == 5)
+        assert abs(row - cc) < 1e-9, (i, row)
+        assert v["c%d" % i] == cc
+
+
+# ---- dense output regression bounds -----------------------------------------------------------
+@pytest.mark.parametrize("alg,bound", [
+    (oracle.ALG_TSIT5, 2e-6), (oracle.ALG_VERN7, 3e-9), (oracle.ALG_ROSENBROCK23, 3e-3), (oracle.ALG_RODAS5P, 2e-5)])
+def test_dense_output_regression_bounds(alg, bound):
+    # test/Regression_I/ode_dense_tests.jl:56-75 with the per-algorithm tolerances at
+    # :369-370 (Tsit5), :429-433 (Vern7), :452-453 (Rosenbrock23), :479-480 (Rodas5P):
+    # interpolant of the adaptive dt0 = 1/4 solve vs the fixed dt = 1/16 solve, at k/16.
+    jac, tg = linear_jac_sources()
+    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_RODAS5P)
+    kw = dict(jac=jac, tgrad=tg) if stiff else {}
+    pts = [k / 16 for k in range(1, 17)]
+    a = oracle.solve(alg, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, dt=0.25,
+                     saveat=pts, **kw)
+    b = oracle.solve(alg, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, dt=1 / 16,
+                     dtmax=1 / 16, reltol=1e12, abstol=1e12, saveat=pts, **kw)
+    assert b["naccept"][0] == 16
+    assert np.abs(a["us"][0, :, 0] - b["us"][0, :, 0]).max() < bound
+
+
+# ---- initial step ----------------------------------------------------------------------------
+def test_initdt_zero_state_gives_1e_minus_6():
+    # test/Regression_I/ode_adaptive_tests.jl:115-118 (d0 < 1e-5 branch: dt0 = smalldt = 1e-6)
+    rhs = ("void z_rhs(double* du, const double* u, const double* p, const double t) { du[0] = u[0]; }\n", "z_rhs")
+    user = oracle.compile_user([rhs[0]])
+    L = oracle.lib()
+    u0 = np.zeros(1)
+    dt = L.oracle_initdt(oracle.fn_ptr(user, "z_rhs"), 1, 0, u0.ctypes.data, None, 0.0, 1.0, 1e-6, 1e-3, 5)
+    # u0 = 0 => f0 == f1 == 0 => return max(dtmin, 100*dt0) with dt0 = 1e-6
+    assert dt == pytest.approx(1e-4, rel=1e-12)
+
+
+def test_initdt_hairer_formula_lorenz(pkg):
+    rhs = pkg.problems_library.lorenz_source()
+    user = oracle.compile_user([rhs[0]])
+    L = oracle.lib()
+    u0 = np.array([1.0, 0.0, 0.0]); p = np.array([10.0, 28.0, 8.0 / 3.0])
+    dt = L.oracle_initdt(oracle.fn_ptr(user, rhs[1]), 3, 3, u0.ctypes.data, p.ctypes.data, 0.0, 10.0, 1e-6, 1e-3, 5)
+    # independent evaluation of Hairer's recipe in numpy
+    sk = 1e-6 + np.abs(u0) * 1e-3
+    f = lambda u: np.array([p[0] * (u[1] - u[0]), u[0] * (p[1] - u[2]) - u[1], u[0] * u[1] - p[2] * u[2]])
+    nrm = lambda v: math.sqrt(np.sum(v * v) / 3)
+    d0, f0 = nrm(u0 / sk), f(u0)
+    d1 = nrm(f0 / sk)
+    dt0 = min((d0 / d1) / 100, 10.0)
+    d2 = nrm((f(u0 + dt0 * f0) - f0) / sk) / dt0
+    dt1 = 10 ** (-(2 + math.log10(max(d1, d2))) / 5)
+    assert dt == pytest.approx(min(100 * dt0, dt1), rel=1e-13)
+
+
+def test_float32_robertson_rosenbrock23_succeeds(pkg):
+    # test/InterfaceI/ode_initdt_tests.jl:37-49
+    r, j, tg = pkg.problems_library.robertson_sources(True)
+    o = oracle.solve(oracle.ALG_ROSENBROCK23, r, np.array([1.0, 0.0, 0.0]), np.array([4e-2, 3e7, 1e4]), (0.0, 1e5), 3, 3,
+                     trajectories=1, f32=True, jac=j, tgrad=tg)
+    assert o["retcode"][0] == 1 and abs(float(o["u_final"][0].sum()) - 1.0) < 1e-3
+
+
+def test_rosenbrock_step_count_ceiling():
+    # lib/OrdinaryDiffEqRosenbrock/test/ode_rosenbrock_tests.jl:25-27,34-36: length(sol.t) < 20 on prob_ode_linear
+    jac, tg = linear_jac_sources()
+    for alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_RODAS5P):
+        o = oracle.solve(alg, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, jac=jac, tgrad=tg)
+        assert o["naccept"][0] + 1 < 20 and o["retcode"][0] == 1
+
+
+def test_failure_retcodes():
+    # check_error.jl:77-117
+    rhs = linear_source()
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, maxiters=3)
+    assert o["retcode"][0] == 2 and o["t_final"][0] < 1.0                      # MaxIters
+    nan_rhs = ("void nan_rhs(double* du, const double* u, const double* p, const double t) { du[0] = u[0] / (t - t); }\n", "nan_rhs")
+    o = oracle.solve(oracle.ALG_TSIT5, nan_rhs, np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, dt=0.1)
+    assert o["retcode"][0] in (3, 4, 5)                                        # never Success
+
+
+# ---- regression pins of the oracle itself -----------------------------------------------------
+def test_golden_regression_pins(pkg):
+    """tests/golden/oracle_pins.json was written by tests/golden/make_pins.py from this oracle;
+    it detects unintended changes of the restatement (it is NOT a reference-produced vector)."""
+    pins = json.load(open(os.path.join(HERE, "golden", "oracle_pins.json")))
+    pl = pkg.problems_library
+    for case in pins["cases"]:
+        o = _run_pin_case(pl, case)
+        assert [int(x) for x in o["naccept"]] == case["naccept"], case["name"]
+        assert [int(x) for x in o["nreject"]] == case["nreject"], case["name"]
+        got = [float(x).hex() for x in o["u_final"].astype(np.float64).ravel()]
+        assert got == case["u_final_hex"], case["name"]
+
+
+def _run_pin_case(pl, case):
+    alg = {"tsit5": oracle.ALG_TSIT5, "vern7": oracle.ALG_VERN7, "ros23": oracle.ALG_ROSENBROCK23,
+           "rodas5p": oracle.ALG_RODAS5P}[case["alg"]]
+    f32 = case["f32"]
+    N = case["N"]
+    if case["problem"] == "lorenz":
+        return oracle.solve(alg, pl.lorenz_source(f32), np.array([1.0, 0, 0]), pl.lorenz_params(N, f32=f32), (0.0, 10.0),
+                            3, 3, f32=f32, **case["kw"])
+    if case["problem"] == "robertson":
+        r, j, tg = pl.robertson_sources(f32)
+        return oracle.solve(alg, r, np.array([1.0, 0, 0]), pl.robertson_params(N, f32=f32), (0.0, case["tf"]), 3, 3,
+                            f32=f32, jac=j, tgrad=tg, **case["kw"])
+    if case["problem"] == "pleiades":
+        return oracle.solve(alg, pl.pleiades_source(f32), pl.pleiades_u0(N, f32=f32), None, (0.0, 3.0), 28, 0, f32=f32,
+                            **case["kw"])
+    raise ValueError(case["problem"])
