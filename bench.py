@@ -66,38 +66,53 @@ def inputs(pl, w, N, offset):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / power / throttle reasons sampled DURING the timed region (NVML, ~2 ms period;
+    the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            try:
+                phys = int(vis.split(",")[index])
+            except Exception:
+                phys = index
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
 
     def run(self):
+        nv = self.nv
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((float(sm), pw, int(rs)))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def summary(self):
+        nv = self.nv
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = set()
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
         for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
-                "samples": len(self.samples), "power_w_max": max(float(s[2]) for s in self.samples)}
+            bits |= s[2]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons = sorted(k for k, v in names.items() if bits & v)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(s[1] for s in self.samples)}
 
 
 def cpu_oracle_rate(pl, w, seconds, nthreads=0):
@@ -130,8 +145,8 @@ def cpu_oracle_rate(pl, w, seconds, nthreads=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="lorenz_tsit5_saveat_1m")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -1,0 +1,158 @@
+# EnsembleB200.jl — the reference-side binding of include/b200ode.h.
+#
+# Drop-in ensemble algorithm for
+#     solve(EnsembleProblem(prob; prob_func), alg, EnsembleB200(); trajectories, saveat, reltol, abstol, …)
+# It adds ONE method to SciMLBase.__solve (the dispatch point of
+# `solve(::AbstractEnsembleProblem, alg, ensemblealg)`), harvests (u0_i, p_i) from prob_func,
+# emits the RHS / Jacobian as C with Symbolics `build_function(...; target = CTarget())`, and
+# `ccall`s libb200ode.so.  Nothing below constructs an ODEIntegrator.
+#
+# NOTE: this file could not be executed in the build environment (no Julia toolchain there);
+# the same ABI is exercised end-to-end by the Python host mirror (ordinarydiffeq.jl_b200/ensemble.py),
+# whose structs mirror the ones below field by field.
+module EnsembleB200Mod
+
+using SciMLBase, Symbolics, StaticArrays
+import SciMLBase: __solve, AbstractEnsembleProblem, EnsembleAlgorithm, EnsembleSolution, build_solution
+using OrdinaryDiffEqTsit5: Tsit5
+using OrdinaryDiffEqVerner: Vern7
+using OrdinaryDiffEqRosenbrock: Rosenbrock23, Rodas5P
+
+export EnsembleB200
+
+const LIB = get(ENV, "B200ODE_LIB", "libb200ode.so")
+
+struct EnsembleB200 <: EnsembleAlgorithm
+    device::Int
+end
+EnsembleB200() = EnsembleB200(0)
+
+# ---- C structs (include/b200ode.h) ----------------------------------------------------------
+struct B200Problem
+    trajectories::Int64
+    u0::Ptr{Cvoid}; u0_shared::Int32
+    p::Ptr{Cvoid}; p_shared::Int32
+    t0::Float64; tf::Float64
+end
+struct B200Opts
+    reltol::Float64; abstol::Float64; dt::Float64; dtmin::Float64; dtmax::Float64
+    maxiters::Int64
+    saveat::Ptr{Float64}; nsaveat::Int32
+    save_start::Int32; save_end::Int32; flags::Int32; reserved::Int32
+end
+mutable struct B200Result
+    u_final::Ptr{Cvoid}; t_final::Ptr{Float64}; us::Ptr{Cvoid}; ts::Ptr{Float64}
+    nsaved::Ptr{Int32}; naccept::Ptr{Int32}; nreject::Ptr{Int32}; nf::Ptr{Int32}
+    njacs::Ptr{Int32}; nw::Ptr{Int32}; nsolve::Ptr{Int32}; retcode::Ptr{Int32}
+    kernel_ms::Float64; total_ms::Float64
+end
+
+alg_id(::Tsit5) = 1; alg_id(::Vern7) = 2; alg_id(::Rosenbrock23) = 3; alg_id(::Rodas5P) = 4
+isstiff(alg) = alg isa Union{Rosenbrock23, Rodas5P}
+const RETCODES = (ReturnCode.Default, ReturnCode.Success, ReturnCode.MaxIters, ReturnCode.DtLessThanMin,
+                  ReturnCode.Unstable, ReturnCode.DtNaN)
+
+function check(rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:b200ode_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))
+    rc == -1 ? throw(ArgumentError(msg)) : error("b200ode ($rc): $msg")
+end
+
+# ---- code generation: Symbolics traces f(u,p,t) and emits C ------------------------------------
+function c_sources(prob, alg, ::Type{T}) where {T}
+    n, np = length(prob.u0), prob.p === nothing ? 0 : length(prob.p)
+    @variables u[1:n] p[1:max(np, 1)] t
+    us, ps = collect(u), collect(p)
+    du = SciMLBase.isinplace(prob) ? (d = similar(us, Num); prob.f.f(d, us, ps, t); d) : collect(prob.f.f(us, ps, t))
+    fix(s) = T === Float32 ? replace(s, "double" => "float") : s
+    rhs = fix(build_function(du, us, ps, t; target = Symbolics.CTarget(), fname = :diffeqf))
+    jac = tgr = nothing
+    if isstiff(alg)
+        J = Symbolics.jacobian(du, us)
+        jac = fix(build_function(vec(J), us, ps, t; target = Symbolics.CTarget(), fname = :diffeqjac))  # column major
+        tgr = fix(build_function(Symbolics.derivative.(du, t), us, ps, t; target = Symbolics.CTarget(), fname = :diffeqtgrad))
+    end
+    return n, np, rhs, jac, tgr
+end
+
+const HANDLES = Dict{Int, Ptr{Cvoid}}()
+function handle(dev)
+    get!(HANDLES, dev) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b200ode_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), h, dev))
+        h[]
+    end
+end
+
+const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :reltol, :abstol,
+                 :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense)
+
+function __solve(eprob::AbstractEnsembleProblem, alg::Union{Tsit5, Vern7, Rosenbrock23, Rodas5P}, ens::EnsembleB200;
+                 trajectories, batch_size = trajectories, kwargs...)
+    prob = eprob.prob
+    kw = merge(NamedTuple(prob.kwargs), NamedTuple(kwargs))          # merge_problem_kwargs
+    for k in keys(kw)
+        k in ALLOWED || throw(ArgumentError("EnsembleB200 does not support the keyword $k"))
+    end
+    T = eltype(prob.u0)
+    T <: Union{Float32, Float64} || throw(ArgumentError("EnsembleB200 supports Float32/Float64 states"))
+    t0, tf = Float64.(prob.tspan)
+    tf > t0 || throw(ArgumentError("EnsembleB200 integrates forward in time only"))
+    saveat = get(kw, :saveat, ())
+    grid = saveat isa Number ? collect(Float64, (t0 + abs(saveat)):abs(saveat):tf) :
+           sort!(Float64[s for s in saveat if t0 < s <= tf])
+    get(kw, :save_everystep, isempty(grid)) && throw(ArgumentError("save_everystep=true is not supported; pass saveat or save_everystep=false"))
+    n, np, rhs, jac, tgr = c_sources(prob, alg, T)
+    h = handle(ens.device)
+    prog = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b200ode_compile, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring),
+                h, prog, alg_id(alg), T === Float32 ? 1 : 0, n, np, rhs, "diffeqf",
+                jac === nothing ? C_NULL : jac, "diffeqjac", tgr === nothing ? C_NULL : tgr, "diffeqtgrad", C_NULL))
+    ss = get(kw, :save_start, nothing); se = get(kw, :save_end, nothing)
+    opts = B200Opts(get(kw, :reltol, 0.0), get(kw, :abstol, 0.0), something(get(kw, :dt, nothing), 0.0),
+                    get(kw, :dtmin, 0.0), get(kw, :dtmax, 0.0), get(kw, :maxiters, 0),
+                    isempty(grid) ? Ptr{Float64}(C_NULL) : pointer(grid), length(grid),
+                    ss === nothing ? -1 : Int32(ss), se === nothing ? -1 : Int32(se), 0, 0)
+    tstart = time()
+    u = eprob.u_init === nothing ? [] : eprob.u_init
+    converged = false
+    for b0 in 1:batch_size:trajectories
+        I = b0:min(b0 + batch_size - 1, trajectories)
+        N = length(I)
+        # harvest prob_func on the host: flat AoS tables (Vector{SVector{n,T}} is already this layout)
+        U0 = Matrix{T}(undef, n, N); P = Matrix{T}(undef, max(np, 1), N)
+        for (k, i) in enumerate(I)
+            q = eprob.prob_func(prob, SciMLBase.EnsembleContext(i, 1, nothing))
+            U0[:, k] .= q.u0
+            np > 0 && (P[:, k] .= q.p)
+        end
+        cprob = B200Problem(N, pointer(U0), 0, pointer(P), 0, t0, tf)
+        nslots = ccall((:b200ode_nslots, LIB), Cint, (Ref{B200Problem}, Ref{B200Opts}), cprob, opts)
+        uf = Matrix{T}(undef, n, N); tfin = Vector{Float64}(undef, N)
+        us = Array{T, 3}(undef, n, max(nslots, 1), N); ts = Vector{Float64}(undef, max(nslots, 1))
+        cnt = [Vector{Int32}(undef, N) for _ in 1:8]
+        res = B200Result(pointer(uf), pointer(tfin), nslots > 0 ? pointer(us) : C_NULL, pointer(ts),
+                         pointer.(cnt)..., 0.0, 0.0)
+        GC.@preserve U0 P grid uf tfin us ts cnt begin
+            check(ccall((:b200ode_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}),
+                        h, prog[], cprob, opts, res))
+        end
+        nsaved, naccept, nreject, nf, njacs, nw, nsolve, rc = cnt
+        batch = map(1:N) do k
+            tk = nslots > 0 ? ts[1:nsaved[k]] : [t0, tfin[k]]
+            uk = nslots > 0 ? [SVector{n, T}(us[:, s, k]) for s in 1:nsaved[k]] : [SVector{n, T}(U0[:, k]), SVector{n, T}(uf[:, k])]
+            stats = SciMLBase.DEStats(Int(nf[k]), 0, 0, Int(nw[k]), Int(nsolve[k]), Int(njacs[k]), 0, 0, 0, 0,
+                                      Int(naccept[k]), Int(nreject[k]), 0.0)
+            sol = build_solution(prob, alg, tk, uk; dense = false, stats, retcode = RETCODES[rc[k] + 1])
+            out, rerun = eprob.output_func(sol, SciMLBase.EnsembleContext(I[k], 1, nothing))
+            rerun && error("rerun is served by re-submitting the trajectory; see ensemble.py for the loop")
+            out
+        end
+        u, converged = eprob.reduction(u, batch, I)
+        converged && break
+    end
+    return EnsembleSolution(u, time() - tstart, converged)
+end
+
+end # module
