@@ -125,7 +125,13 @@ def cpu_oracle_rate(pl, w, seconds, nthreads=0):
     import b200_import
     pkg = b200_import.load()
     grid = pkg.ranges.saveat_grid(w["saveat"], w["tspan"]) if w["saveat"] is not None else None
-    threads = oracle.lib().oracle_num_threads() if nthreads == 0 else nthreads
+    if nthreads == 0:
+        # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; override it)
+        try:
+            nthreads = len(os.sched_getaffinity(0))
+        except Exception:
+            nthreads = os.cpu_count() or 1
+    threads = nthreads
 
     def run(N):
         u0, p = inputs(pl, w, N, 0)

@@ -86,8 +86,11 @@ struct b200ode_handle_s {
     cudaStream_t stream = nullptr;       // compute + H2D
     cudaStream_t copy_stream = nullptr;  // D2H of finished chunks
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
     // scratch owned by the handle (grow-only)
     DevBuf counter, dt0, saveat, scratch_t;
+    std::vector<double> saveat_cached;   // grid currently resident in `saveat` ...
+    int saveat_cached_dtype = -1;        // ... in this real type
     DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial;
 };
 
@@ -337,12 +340,18 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     P.nslots = dr->us ? b200ode_nslots(&hp, o) : 0;
     P.saveat = nullptr;
     if (P.nsaveat > 0) {
-        // the grid travels as real[] in the handle's scratch
-        std::vector<R> grid(P.nsaveat);
-        for (int i = 0; i < P.nsaveat; ++i) grid[i] = (R)o->saveat[i];
-        CUDA_TRY(h->saveat.ensure(sizeof(R) * P.nsaveat));
-        CUDA_TRY(cudaMemcpyAsync(h->saveat.ptr, grid.data(), sizeof(R) * P.nsaveat, cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));   // grid is a stack-lifetime host vector
+        // the grid travels as real[] in the handle's scratch; re-uploaded only when it changes
+        const bool same = (h->saveat_cached_dtype == (int)sizeof(R)) && (int)h->saveat_cached.size() == P.nsaveat &&
+                          std::equal(h->saveat_cached.begin(), h->saveat_cached.end(), o->saveat);
+        if (!same) {
+            std::vector<R> grid(P.nsaveat);
+            for (int i = 0; i < P.nsaveat; ++i) grid[i] = (R)o->saveat[i];
+            CUDA_TRY(cudaDeviceSynchronize());          // no launch may still be reading the old grid
+            CUDA_TRY(h->saveat.ensure(sizeof(R) * P.nsaveat));
+            CUDA_TRY(cudaMemcpy(h->saveat.ptr, grid.data(), sizeof(R) * P.nsaveat, cudaMemcpyHostToDevice));
+            h->saveat_cached.assign(o->saveat, o->saveat + P.nsaveat);
+            h->saveat_cached_dtype = (int)sizeof(R);
+        }
         P.saveat = (const R*)h->saveat.ptr;
     }
     CUDA_TRY(h->dt0.ensure(sizeof(R) * (size_t)N));
@@ -440,6 +449,7 @@ int b200ode_destroy(b200ode_handle h) {
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
     delete h;
     return B200ODE_OK;
 }
@@ -581,30 +591,54 @@ int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp,
     size_t us_bytes = rs * (size_t)n * (size_t)nslots * (size_t)N;
     if (nslots > 0) CUDA_TRY(h->out_us.ensure(us_bytes));
 
-    B200DeviceProblem dp{};
-    dp.trajectories = N;
-    dp.u0 = h->in_u0.ptr; dp.u0_shared = hp->u0_shared; dp.u0_layout = B200ODE_LAYOUT_AOS;
-    dp.p = np > 0 ? h->in_p.ptr : nullptr; dp.p_shared = hp->p_shared; dp.p_layout = B200ODE_LAYOUT_AOS;
-    dp.t0 = hp->t0; dp.tf = hp->tf;
-    B200DeviceResult dr{};
     int32_t* i32 = (int32_t*)h->out_i32.ptr;
-    dr.u_final = h->out_uf.ptr; dr.u_final_layout = B200ODE_LAYOUT_AOS;
-    dr.t_final = (double*)h->out_tf.ptr;
-    dr.us = nslots > 0 ? h->out_us.ptr : nullptr;
-    dr.nsaved = i32 + 0 * N; dr.naccept = i32 + 1 * N; dr.nreject = i32 + 2 * N; dr.nf = i32 + 3 * N;
-    dr.njacs = i32 + 4 * N; dr.nw = i32 + 5 * N; dr.nsolve = i32 + 6 * N; dr.retcode = i32 + 7 * N;
     bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
     if (!stiff) CUDA_TRY(cudaMemsetAsync(i32 + 4 * N, 0, sizeof(int32_t) * 3 * (size_t)N, s));
-    // A trajectory that fails writes fewer than nslots rows; the rest stay zero.
-    if (nslots > 0) CUDA_TRY(cudaMemsetAsync(h->out_us.ptr, 0, us_bytes, s));
+    // (rows a failed trajectory does not reach are zero-filled by the kernel itself)
 
+    // Chunked pipeline: the D2H of the saveat rows of chunk c (copy stream) overlaps the
+    // kernels of chunk c+1 (compute stream).  Final-state-only solves are a single chunk.
+    long long chunk = N;
+    if (nslots > 0 && N > 131072) {
+        chunk = (N + 7) / 8;
+        chunk = ((chunk + 1023) / 1024) * 1024;
+        if (chunk < 65536) chunk = 65536;
+    }
     CUDA_TRY(cudaEventRecord(h->ev1, s));
-    rc = b200ode_solve_device(h, prog, &dp, o, &dr, s);
-    if (rc) return rc;
+    const size_t row_bytes = rs * (size_t)n * (size_t)nslots;
+    for (long long c0 = 0; c0 < N; c0 += chunk) {
+        const long long cn = std::min(chunk, N - c0);
+        B200DeviceProblem dp{};
+        dp.trajectories = cn;
+        dp.u0 = (char*)h->in_u0.ptr + (hp->u0_shared ? 0 : rs * n * (size_t)c0);
+        dp.u0_shared = hp->u0_shared; dp.u0_layout = B200ODE_LAYOUT_AOS;
+        dp.p = np > 0 ? (char*)h->in_p.ptr + (hp->p_shared ? 0 : rs * np * (size_t)c0) : nullptr;
+        dp.p_shared = hp->p_shared; dp.p_layout = B200ODE_LAYOUT_AOS;
+        dp.t0 = hp->t0; dp.tf = hp->tf;
+        B200DeviceResult dr{};
+        dr.u_final = (char*)h->out_uf.ptr + rs * n * (size_t)c0; dr.u_final_layout = B200ODE_LAYOUT_AOS;
+        dr.t_final = (double*)((char*)h->out_tf.ptr + rs * (size_t)c0);
+        dr.us = nslots > 0 ? (char*)h->out_us.ptr + row_bytes * (size_t)c0 : nullptr;
+        dr.nsaved = i32 + 0 * N + c0; dr.naccept = i32 + 1 * N + c0; dr.nreject = i32 + 2 * N + c0; dr.nf = i32 + 3 * N + c0;
+        dr.njacs = i32 + 4 * N + c0; dr.nw = i32 + 5 * N + c0; dr.nsolve = i32 + 6 * N + c0; dr.retcode = i32 + 7 * N + c0;
+        rc = b200ode_solve_device(h, prog, &dp, o, &dr, s);
+        if (rc) return rc;
+        if (nslots > 0) {
+            // per-chunk events are created on demand and kept in the handle
+            size_t ci = (size_t)(c0 / chunk);
+            while (h->chunk_events.size() <= ci) {
+                cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->chunk_events.push_back(e);
+            }
+            CUDA_TRY(cudaEventRecord(h->chunk_events[ci], s));
+            CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_events[ci], 0));
+            CUDA_TRY(cudaMemcpyAsync((char*)res->us + row_bytes * (size_t)c0, (char*)h->out_us.ptr + row_bytes * (size_t)c0,
+                                     row_bytes * (size_t)cn, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+    }
     CUDA_TRY(cudaEventRecord(h->ev2, s));
 
     CUDA_TRY(cudaMemcpyAsync(res->u_final, h->out_uf.ptr, rs * n * (size_t)N, cudaMemcpyDeviceToHost, s));
-    if (nslots > 0) CUDA_TRY(cudaMemcpyAsync(res->us, h->out_us.ptr, us_bytes, cudaMemcpyDeviceToHost, s));
     std::vector<char> tf_host;
     if (res->t_final) {
         tf_host.resize(rs * (size_t)N);
@@ -615,6 +649,7 @@ int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp,
         {res->njacs, 4}, {res->nw, 5}, {res->nsolve, 6}, {res->retcode, 7}};
     for (auto& oo : outs)
         if (oo.dst) CUDA_TRY(cudaMemcpyAsync(oo.dst, i32 + (size_t)oo.slot * N, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
     CUDA_TRY(cudaEventRecord(h->ev3, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     cudaError_t le = cudaGetLastError();

@@ -163,7 +163,9 @@ struct B200Traj {
     real p[B200_NP > 0 ? B200_NP : 1];
     B200Stepper st;
     real t, tprev, dt, dtpropose;
-    real q11, errold, EEst;
+    real q11, EEst;
+    real fpe, rfpe;             // fastpower(errold, beta2) and its correctly rounded reciprocal (see iterate)
+    real next_save;             // saveat[save_idx] (or +Inf when the grid is exhausted)
     int naccept, nreject, nf;      // iter = naccept+nreject(+1), success_iter = naccept (see iterate)
     int save_idx, nsaved;
     int retcode;
@@ -215,7 +217,13 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     if (P.dt_user == (real)0) { T.dt = P.dt0[idx]; T.nf += 2; }   // auto_dt_reset!: nf += 2
     else T.dt = P.dt_user;
     T.dtpropose = T.dt;
-    T.q11 = (real)1; T.errold = (real)1e-4; T.EEst = (real)1;     // setup_controller_cache (controllers.jl:793-803)
+    T.q11 = (real)1; T.EEst = (real)1;                            // setup_controller_cache (controllers.jl:793-803)
+    {   // errold = qoldinit = 1e-4; only fastpower(errold, beta2) is ever used
+        const real beta2 = (real)(2.0 / (5.0 * B200Stepper::order()));
+        T.fpe = b200_fastpower((real)1e-4, beta2);
+        T.rfpe = (real)1 / T.fpe;
+    }
+    T.next_save = (P.nsaveat > 0) ? P.saveat[0] : b200_inf();
     T.naccept = 0; T.nreject = 0;
     T.accept = false; T.tstop_flag = false;
     T.retcode = B200_RC_DEFAULT;
@@ -294,7 +302,9 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         q = (real)1 / qmax_eff;
     } else {
         real q11 = b200_fastpower(T.EEst, beta1);
-        q = q11 / b200_fastpower(T.errold, beta2);
+        // q = q11 / fastpower(errold, beta2): the divisor was computed when errold was set, together
+        // with RN(1/divisor), so the quotient is the 3-operation exact form (b200_div_const)
+        q = b200_div_const(q11, T.fpe, T.rfpe);
         T.q11 = q11;
         q = b200_div_const(q, gamma, (real)1 / gamma);
         const real lo = (real)1 / qmax_eff, hi = (real)1 / qmin;
@@ -309,18 +319,22 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         T.tstop_flag = false;
         // step_accept_controller!
         if (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) q = (real)1;
-        T.errold = b200_max_c((real)1e-4, T.EEst);
+        {   // errold = max(EEst, qoldinit); its fastpower is all later steps need
+            const real errold = b200_max_c((real)1e-4, T.EEst);
+            T.fpe = b200_fastpower(errold, beta2);
+            T.rfpe = (real)1 / T.fpe;
+        }
         const real dtnew = T.dt / q;
         // calc_dt_propose!: eps at the NEW t
         const real eps_n = b200_eps(T.t);
         T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
         // handle_callbacks! -> savevalues!
-        if (P.nsaveat > 0) {
+        {
             bool dense_ready = false;
-            while (T.save_idx < P.nsaveat) {
-                const real curt = P.saveat[T.save_idx];
-                if (!(curt <= T.t)) break;
+            while (T.next_save <= T.t) {
+                const real curt = T.next_save;
                 T.save_idx += 1;
+                T.next_save = (T.save_idx < P.nsaveat) ? P.saveat[T.save_idx] : b200_inf();
                 if (curt != T.t) {
                     if (!dense_ready) {
                         T.st.dense_prepare(T.uprev, T.u, T.p, T.tprev, T.dt);
@@ -343,6 +357,14 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     return !(T.t < P.tf);
 }
 
+// cold path (failed trajectories only): kept out of line so it costs the hot loop no registers
+__device__ __noinline__ void b200_zero_rows(real* us, long long idx, int from, int nslots) {
+    for (int s = from; s < nslots; ++s) {
+        real* dst = us + ((size_t)idx * (size_t)nslots + (size_t)s) * B200_N;
+        for (int c = 0; c < B200_N; ++c) dst[c] = (real)0;
+    }
+}
+
 // postamble! (+ writing the per-trajectory results)
 B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
     if (T.retcode == B200_RC_DEFAULT) T.retcode = B200_RC_SUCCESS;
@@ -360,6 +382,8 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
         }
         if (emit) b200_emit(P, idx, T, T.u);
     }
+    // a trajectory that failed leaves its remaining rows zero (the host does not pre-clear `us`)
+    if (P.nslots > 0 && T.nsaved < P.nslots) b200_zero_rows(P.us, idx, T.nsaved, P.nslots);
 #pragma unroll
     for (int c = 0; c < B200_N; ++c) P.u_final[idx * P.uf_ts + c * P.uf_cs] = T.u[c];
     P.t_final[idx] = T.t;

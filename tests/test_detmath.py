@@ -77,6 +77,13 @@ def test_constant_divisor_division_is_exact(host):
         af = af[np.isfinite(af) & (af != 0)]
         for x in af:
             assert host.t_div_const_f(x, np.float32(b)) == np.float32(x) / np.float32(b)
+    # variable divisor with its correctly rounded reciprocal (q11 / fastpower(errold), C ./ dt)
+    for _ in range(40000):
+        b = float(rng.uniform(1, 2) * 2.0 ** rng.integers(-60, 60))
+        x = float(rng.uniform(1, 2) * 2.0 ** rng.integers(-200, 200))
+        assert host.t_div_const(x, b) == x / b
+        bf, xf = np.float32(b), np.float32(rng.uniform(1, 2) * 2.0 ** rng.integers(-40, 40))
+        assert host.t_div_const_f(xf, bf) == xf / bf
     for x in (0.0, float("inf"), 5e-324, 1e-310, 1e305):
         assert host.t_div_const(x, 3.0) == x / 3.0
     assert np.isnan(host.t_div_const(float("nan"), 3.0))
