@@ -166,8 +166,15 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     tu += "#define B200_ALG " + std::to_string(alg) + "\n";
     tu += "#include \"b200_base.cuh\"\n";
     // forward declarations make the user's functions __device__ __forceinline__
-    // (their definitions carry no execution-space annotation: -default-device)
-    tu += std::string("__device__ __forceinline__ void ") + rhs_name +
+    // (their definitions carry no execution-space annotation: -default-device).
+    // -DB200_RHS_INLINE=0 keeps the RHS out of line (one copy instead of one per stage).  Measured
+    // on Pleiades/Vern7 (n = 28): the out-of-line / rolled variants are slower (230-310 ms vs
+    // 177-220 ms for 2^18 trajectories) although the fully inlined loop body (470 KB) misses the
+    // instruction cache — dynamic indexing forces every stage vector through local memory.
+    bool rhs_inline = true;
+    if (extra_options && strstr(extra_options, "-DB200_RHS_INLINE=1")) rhs_inline = true;
+    if (extra_options && strstr(extra_options, "-DB200_RHS_INLINE=0")) rhs_inline = false;
+    tu += std::string(rhs_inline ? "__device__ __forceinline__ void " : "__device__ __noinline__ void ") + rhs_name +
           "(real* du, const real* u, const real* p, const real t);\n";
     if (stiff) {
         tu += std::string("__device__ __forceinline__ void ") + jac_name +

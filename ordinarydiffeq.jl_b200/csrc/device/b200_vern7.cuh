@@ -43,8 +43,16 @@ __constant__ B200Vern7Coeffs B200_VERN7_C = {
     b200_fma(C.a9, x9[i], B200_V7_8(a1, x1, a2, x2, a3, x3, a4, x4, a5, x5, a6, x6, a7, x7, a8, x8))
 #define B200_V7_10(a1, x1, a2, x2, a3, x3, a4, x4, a5, x5, a6, x6, a7, x7, a8, x8, a9, x9, a10, x10) \
     b200_fma(C.a10, x10[i], B200_V7_9(a1, x1, a2, x2, a3, x3, a4, x4, a5, x5, a6, x6, a7, x7, a8, x8, a9, x9))
+// Component loops are fully unrolled by default; -DB200_STAGE_UNROLL=k rolls them (smaller code,
+// but stage vectors are then indexed dynamically and live in local memory).
+#ifndef B200_STAGE_UNROLL
+#define B200_STAGE_UNROLL B200_N      // measured best also for n = 28 (see b200ode_shim.cu)
+#endif
+#define B200_PRAGMA_(x) _Pragma(#x)
+#define B200_PRAGMA(x) B200_PRAGMA_(x)
+#define B200_UNROLL_STAGE B200_PRAGMA(unroll B200_STAGE_UNROLL)
 #define B200_V7_STAGE(dst, expr)                                                  \
-    _Pragma("unroll") for (int i = 0; i < B200_N; ++i) dst[i] = b200_fma(dt, (expr), uprev[i]);
+    B200_UNROLL_STAGE for (int i = 0; i < B200_N; ++i) dst[i] = b200_fma(dt, (expr), uprev[i]);
 
 struct B200Vern7 {
     real k1[B200_N], k2[B200_N], k3[B200_N], k4[B200_N], k5[B200_N], k6[B200_N], k7[B200_N], k8[B200_N],
@@ -64,7 +72,7 @@ struct B200Vern7 {
         real tmp[B200_N];
         B200_RHS(k1, uprev, p, t);
         const real a = dt * C.a021;
-#pragma unroll
+        B200_UNROLL_STAGE
         for (int i = 0; i < B200_N; ++i) tmp[i] = b200_fma(a, k1[i], uprev[i]);
         B200_RHS(k2, tmp, p, b200_fma(C.c2, dt, t));
         B200_V7_STAGE(tmp, B200_V7_2(a031, k1, a032, k2))
@@ -86,7 +94,7 @@ struct B200Vern7 {
         nf += 10;
         B200_V7_STAGE(u, B200_V7_7(b1, k1, b4, k4, b5, k5, b6, k6, b7, k7, b8, k8, b9, k9))
         real acc = (real)0;
-#pragma unroll
+        B200_UNROLL_STAGE
         for (int i = 0; i < B200_N; ++i) {
             real ut = dt * B200_V7_8(btilde1, k1, btilde4, k4, btilde5, k5, btilde6, k6, btilde7, k7, btilde8, k8,
                                      btilde9, k9, btilde10, k10);
@@ -141,7 +149,7 @@ struct B200Vern7 {
         const real b15 = th2 * B200_P6(r152, r153, r154, r155, r156, r157);
         const real b16 = th2 * B200_P6(r162, r163, r164, r165, r166, r167);
 #undef B200_P6
-#pragma unroll
+        B200_UNROLL_STAGE
         for (int i = 0; i < B200_N; ++i) {
             real s = k1[i] * b1;
             s = b200_fma(k4[i], b4, s);

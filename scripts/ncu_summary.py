@@ -57,9 +57,10 @@ print("== executed opcode mix (warp instructions)", file=out)
 for k, v in c.most_common(28):
     print("  %-10s %12d %5.1f%%" % (k, v, 100.0 * v / tot), file=out)
 pop = Counter()
+nmax = max(int(x[ix["Instructions Executed"]]) for x in data)
 for r in data:
     n = int(r[ix["Instructions Executed"]])
-    if n * 50 > max(int(x[ix["Instructions Executed"]]) for x in data):
+    if n * 50 > nmax:
         pop[(n, r[ix["Avg. Threads Executed"]])] += 1
 print("== regions: (executions, avg threads) -> #SASS instructions", file=out)
 for k, v in sorted(pop.items(), key=lambda kv: -kv[0][0] * kv[1])[:16]:

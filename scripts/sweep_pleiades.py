@@ -1,0 +1,25 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import b200_import
+pkg = b200_import.load()
+from oracle import oracle
+pl, ll = pkg.problems_library, pkg.lowlevel
+h = pkg.Handle(0)
+N = 1 << 18
+rhs = pl.pleiades_source(False); u0 = pl.pleiades_u0(N)
+kw = dict(reltol=1e-6, abstol=1e-8)
+o = oracle.solve(oracle.ALG_VERN7, rhs, u0[:512], None, (0.0, 3.0), 28, 0, **kw)
+variants = sys.argv[1:] or ["", "-DB200_STAGE_UNROLL=1", "-DB200_STAGE_UNROLL=2", "-DB200_STAGE_UNROLL=7",
+                            "-DB200_MINBLOCKS=3", "-DB200_MINBLOCKS=4 -DB200_STAGE_UNROLL=2", "-DB200_BLOCK=64 -DB200_MINBLOCKS=6",
+                            "-DB200_BLOCK=64 -DB200_MINBLOCKS=8 -DB200_STAGE_UNROLL=2", "-DB200_RHS_INLINE=1"]
+for v in variants:
+    prog = h.compile(pkg.ALG_VERN7, pkg.F64, 28, 0, rhs[0], rhs[1], extra_options=v or None)
+    best = 1e9
+    for _ in range(2):
+        g = ll.solve_host(prog, u0, None, (0.0, 3.0), **kw)
+        best = min(best, g["kernel_ms"])
+    ok = np.array_equal(g["naccept"][:512], o["naccept"]) and np.array_equal(g["u_final"][:512].view(np.uint64), o["u_final"].view(np.uint64))
+    print(repr(v), "regs", prog.info["regs_integrate"], "local", prog.info["local_bytes_integrate"], "blocks/SM", prog.info["blocks_per_sm"],
+          "block", prog.info["block"], "kernel_ms %.2f" % best, "-> %.2f M traj/s" % (N / best / 1e3), "parity", ok, "compile_s %.1f" % (prog.info["compile_ms"] / 1e3), flush=True)
+    prog.close()
