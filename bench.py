@@ -39,6 +39,9 @@ WORKLOADS = {
                                  tol=dict(reltol=1e-6, abstol=1e-8)),
     "robertson_rosenbrock23_1m": dict(problem="robertson", alg="ros23", f32=False, N=1 << 20, saveat=None, tspan=(0.0, 1e5),
                                       tol=dict(reltol=1e-6, abstol=1e-8)),
+    # BASELINE.json configs[4]: one 64 Mi-trajectory parameter sweep sharded over the ranks (strong scaling),
+    # NCCL all-gather of the final states into trajectory order + ensemble mean (all-reduce of partial sums)
+    "lorenz_sweep_64m": dict(problem="lorenz_sweep", alg="tsit5", f32=False, N=1 << 26, saveat=None, tspan=(0.0, 10.0), tol={}),
     "pleiades_vern7_256k": dict(problem="pleiades", alg="vern7", f32=False, N=1 << 18, saveat=None, tspan=(0.0, 3.0),
                                 tol=dict(reltol=1e-6, abstol=1e-8)),
 }
@@ -46,7 +49,7 @@ WORKLOADS = {
 
 def sources(pl, w):
     f32 = w["f32"]
-    if w["problem"] == "lorenz":
+    if w["problem"] in ("lorenz", "lorenz_sweep"):
         return pl.lorenz_source(f32), None, None, 3, 3
     if w["problem"] == "robertson":
         r, j, tg = pl.robertson_sources(f32)
@@ -148,6 +151,74 @@ def cpu_oracle_rate(pl, w, seconds, nthreads=0):
     return sample / dt, sample, threads, float((o["naccept"] + o["nreject"]).mean())
 
 
+def sweep_main(args, w, pkg, rank, world, local_rank, metric, config):
+    """configs[4]: 64 Mi-trajectory rho sweep, interleaved shards, gather + mean over NCCL."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    d = importlib.import_module("ordinarydiffeq_jl_b200.distributed")
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = w["N"]
+    h = pkg.Handle(local_rank)
+    rhs = pl.lorenz_source(False)
+    prog = h.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1])
+    idx = d.shard_indices(N, world, rank)
+    m = int(idx.shape[0])
+    p = np.empty((m, 3), dtype=np.float64)
+    p[:, 0] = 10.0
+    p[:, 1] = 14.0 + 28.0 * idx.astype(np.float64) / float(N)
+    p[:, 2] = 8.0 / 3.0
+    bufs = ll.DeviceBuffers(prog, m, 0, dev, u0_shared=True)
+    bufs.u0.copy_(torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64))
+    bufs.p.copy_(torch.from_numpy(p))
+    part = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def step():
+        ll.solve_device(prog, bufs, w["tspan"])
+        ll.reduce_sum_device(h, pkg.F64, bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
+        if world > 1:
+            full = d.gather_in_order(bufs.u_final, N)
+            mean = d.allreduce_mean(part, N)
+        else:
+            full, mean = bufs.u_final, part / float(N)
+        return full, mean
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        full, mean = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    assert full.shape[0] == N and bool((bufs.retcode == 1).all())
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": N * args.steps / (ms * 1e-3), "unit": "trajectories/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": dict(config, trajectories_total=N, trajectories_per_gpu=m,
+                                         partition="interleaved blocks of 1024 trajectories; NCCL all-gather of final states + all-reduce mean"),
+                          "ensemble_mean_u_tf": [float(x) for x in mean.cpu()], "gpu_launches": 4 * args.steps}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +266,9 @@ def main():
                 "e2e": {"value": v, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
+
+    if w["problem"] == "lorenz_sweep":
+        return sweep_main(args, w, pkg, rank, world, local_rank, metric, config)
 
     # ------------------------------------------------------------------ B200 arm
     import torch

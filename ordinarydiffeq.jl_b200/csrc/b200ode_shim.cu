@@ -232,7 +232,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     if (!has_minb) {
         // registers available per thread at k CTAs of 128 threads: 65536/(128k)
         int minb = 4;
-        if (stiff) minb = (words <= 8) ? 3 : 1;
+        if (stiff) minb = (words <= 8) ? (alg == B200ODE_ALG_ROSENBROCK23 ? 5 : 4) : 1;   // measured (scripts/sweep_rober.py)
         else if (alg == B200ODE_ALG_VERN7) minb = (words <= 6) ? 3 : 1;
         else minb = (words <= 8) ? 4 : (words <= 16 ? 2 : 1);
         opts.push_back("-DB200_MINBLOCKS=" + std::to_string(minb));

@@ -55,8 +55,18 @@ struct B200WFact {
         y0[1] = x1[2] * x2[0] - x1[0] * x2[2];
         y0[2] = x1[0] * x2[1] - x1[1] * x2[0];
         const real d = (x0[0] * y0[0] + x0[1] * y0[1]) + x0[2] * y0[2];
-        x0[0] = x0[0] / d; x0[1] = x0[1] / d; x0[2] = x0[2] / d;
-        y0[0] = y0[0] / d; y0[1] = y0[1] / d; y0[2] = y0[2] / d;
+        // six quotients by the same d: one correctly rounded reciprocal + the exact residual
+        // correction each (b200_div_const; bit-identical to IEEE x / d), true division when d is
+        // outside the safe exponent window (singular or badly scaled W)
+        const real ad = b200_abs(d);
+        if (ad >= (real)1e-30 && ad <= (real)1e30) {
+            const real rd = (real)1 / d;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { x0[i] = b200_div_const(x0[i], d, rd); y0[i] = b200_div_const(y0[i], d, rd); }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { x0[i] = x0[i] / d; y0[i] = y0[i] / d; }
+        }
         y1[0] = x2[1] * x0[2] - x2[2] * x0[1];
         y1[1] = x2[2] * x0[0] - x2[0] * x0[2];
         y1[2] = x2[0] * x0[1] - x2[1] * x0[0];

@@ -26,22 +26,35 @@ def shard_sizes(N, world, block=BLOCK):
     return [int(shard_indices(N, world, r, block).shape[0]) for r in range(world)]
 
 
+_idx_cache = {}
+
+
 def gather_in_order(local, N, block=BLOCK, group=None):
     """local: tensor [m_rank, ...] holding this rank's trajectories in shard order.
-    Returns the tensor [N, ...] in global trajectory order on every rank (all_gather)."""
+    Returns the tensor [N, ...] in global trajectory order on every rank (one all_gather; the
+    un-interleave is a strided device copy when N is a multiple of world*block)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    tail = tuple(local.shape[1:])
+    if N % (world * block) == 0:
+        nb = N // (world * block)
+        out = torch.empty((world,) + (nb, block) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view((world * nb * block,) + tail), local.contiguous(), group=group)
+        # out[r, b] is global block b*world + r
+        return out.permute(1, 0, 2, *range(3, out.dim())).reshape((N,) + tail)
     sizes = shard_sizes(N, world, block)
     mmax = max(sizes)
-    pad = torch.zeros((mmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad = torch.zeros((mmax,) + tail, dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    out = torch.empty((world * mmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    out = torch.empty((world * mmax,) + tail, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
-    full = torch.empty((N,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    full = torch.empty((N,) + tail, dtype=local.dtype, device=local.device)
     for r in range(world):
-        idx = torch.from_numpy(shard_indices(N, world, r, block)).to(local.device)
-        full[idx] = out[r * mmax: r * mmax + sizes[r]]
+        key = (N, world, r, block, str(local.device))
+        if key not in _idx_cache:
+            _idx_cache[key] = torch.from_numpy(shard_indices(N, world, r, block)).to(local.device)
+        full[_idx_cache[key]] = out[r * mmax: r * mmax + sizes[r]]
     return full
 
 
