@@ -417,6 +417,20 @@ def main():
                "d2h_bytes_per_step": int(d2h), "steps": k_e2e, "api": "b200ode_solve (C ABI, pinned host buffers)",
                "device_ms_per_step": r["total_ms"], "kernel_ms_per_step": r["kernel_ms"]}
 
+        # informational: the same ensemble when only EnsembleAnalysis statistics are wanted
+        # (b200ode_solve_meanvar: rows stay in HBM, mean/var per saved row come back)
+        if nslots > 0:
+            out2 = {k: v for k, v in out.items() if k not in ("us",)}
+            ll.solve_host(prog, u0_h, p_pin, w["tspan"], trajectories=N, out=out2, _meanvar=(True, True), **kw)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                ll.solve_host(prog, u0_h, p_pin, w["tspan"], trajectories=N, out=out2, _meanvar=(True, True), **kw)
+            barrier()
+            e2e["stats_only"] = {"value": world * N * k_e2e / (time.perf_counter() - t0), "unit": "trajectories/s",
+                                 "api": "b200ode_solve_meanvar (timeseries mean/var reduced on the device)",
+                                 "d2h_bytes_per_step": int(sum(v.nbytes for k, v in out2.items() if isinstance(v, np.ndarray) and k != "ts"))}
+
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -193,6 +193,21 @@ int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200Devic
 int b200ode_reduce_sum_device(b200ode_handle h, int dtype, const void* x, int layout, int64_t count, int n,
                               double* out, void* stream);
 
+/* EnsembleAnalysis.timeseries_steps_meanvar on the device (SciMLBase.EnsembleAnalysis, EXT; exercised at
+ * /root/reference/lib/DiffEqBase/test/downstream/ensemble_analysis.jl:12-33): for every saved row s and
+ * component c, mean[s][c] and the corrected sample variance var[s][c] over the trajectories of
+ * us = real[count][nslots][n] (device).  mean/var are device arrays double[nslots][n]; var may be NULL.
+ * Two passes in fixed order (deterministic).  This is SURVEY §8(f) row 1: ensemble statistics without
+ * moving the trajectories across PCIe. */
+int b200ode_timeseries_meanvar_device(b200ode_handle h, int dtype, const void* us, int64_t count, int nslots, int n,
+                                      double* mean, double* var, void* stream);
+
+/* b200ode_solve + the reduction above, host buffers: `result->us` is ignored (the rows stay in HBM);
+ * mean/var are host arrays double[nslots][n].  Only the statistics and the per-trajectory scalars
+ * cross PCIe. */
+int b200ode_solve_meanvar(b200ode_handle h, b200ode_program prog, const B200Problem* prob, const B200Opts* opts,
+                          B200Result* result, double* mean, double* var);
+
 /* ---- host memory helpers (pinned buffers make the D2H of `us` run at PCIe speed) */
 int b200ode_host_register(void* ptr, size_t bytes);
 int b200ode_host_unregister(void* ptr);

@@ -68,7 +68,7 @@ EXPORTS = [
     "b200ode_create", "b200ode_destroy", "b200ode_last_error", "b200ode_version",
     "b200ode_compile", "b200ode_program_destroy", "b200ode_program_info",
     "b200ode_compile_only", "b200ode_free", "b200ode_nslots", "b200ode_solve", "b200ode_solve_device",
-    "b200ode_reduce_sum_device", "b200ode_host_register", "b200ode_host_unregister",
+    "b200ode_reduce_sum_device", "b200ode_timeseries_meanvar_device", "b200ode_solve_meanvar", "b200ode_host_register", "b200ode_host_unregister",
     "b200ode_measure_fma_peak",
 ]
 
@@ -103,6 +103,8 @@ def lib():
     L.b200ode_solve_device.argtypes = [vp, vp, C.POINTER(B200DeviceProblem), C.POINTER(B200Opts),
                                        C.POINTER(B200DeviceResult), vp]
     L.b200ode_reduce_sum_device.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp]
+    L.b200ode_timeseries_meanvar_device.argtypes = [vp, i32, vp, i64, i32, i32, vp, vp, vp]
+    L.b200ode_solve_meanvar.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(B200Result), vp, vp]
     L.b200ode_host_register.argtypes = [vp, C.c_size_t]
     L.b200ode_host_unregister.argtypes = [vp]
     L.b200ode_measure_fma_peak.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]

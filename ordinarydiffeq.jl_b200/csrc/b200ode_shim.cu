@@ -91,7 +91,7 @@ struct b200ode_handle_s {
     DevBuf counter, dt0, saveat, scratch_t;
     std::vector<double> saveat_cached;   // grid currently resident in `saveat` ...
     int saveat_cached_dtype = -1;        // ... in this real type
-    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial;
+    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out;
 };
 
 struct b200ode_program_s {
@@ -303,6 +303,30 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* __restrict__
     }
 }
 
+// column statistics of a row-major [rows][cols] matrix: per-CTA partial sums in fixed order
+template <typename R>
+__global__ void __launch_bounds__(256) k_colsum_partial(const R* __restrict__ x, long long rows, int cols,
+                                                        const double* __restrict__ mean, double* __restrict__ partial) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const double m = mean ? mean[c] : 0.0;
+    double acc = 0.0;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double v = (double)x[r * (long long)cols + c];
+        if (mean) { const double d = v - m; acc = fma(d, d, acc); }
+        else acc += v;
+    }
+    partial[(size_t)blockIdx.x * cols + c] = acc;
+}
+__global__ void __launch_bounds__(256) k_colsum_final(const double* __restrict__ partial, int nparts, int cols, double scale,
+                                                      double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double acc = 0.0;
+    for (int b = 0; b < nparts; ++b) acc += partial[(size_t)b * cols + c];
+    out[c] = acc * scale;
+}
+
 // FMA-pipe peak: 8 independent dependent chains per thread, register resident
 template <typename R>
 __global__ void __launch_bounds__(256) k_fma_peak(R* out, int iters, R a, R b) {
@@ -451,7 +475,7 @@ int b200ode_destroy(b200ode_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->counter, &h->dt0, &h->saveat, &h->scratch_t, &h->in_u0, &h->in_p, &h->out_uf, &h->out_tf,
-                      &h->out_us, &h->out_i32, &h->red_partial})
+                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out})
         b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -569,7 +593,22 @@ int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200Devic
     return launch_solve<double>(h, prog, dp, o, dr, s);
 }
 
+static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,
+                           double* mean, double* var, bool stats_only);
+
 int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res) {
+    return solve_host_impl(h, prog, hp, o, res, nullptr, nullptr, false);
+}
+
+int b200ode_solve_meanvar(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,
+                          double* mean, double* var) {
+    if (!mean) return fail(B200ODE_EINVAL, "mean is NULL");
+    if (!o || !o->saveat || o->nsaveat <= 0) return fail(B200ODE_EINVAL, "timeseries statistics need a saveat grid");
+    return solve_host_impl(h, prog, hp, o, res, mean, var, true);
+}
+
+static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,
+                           double* mean, double* var, bool stats_only) {
     if (!h || !prog || !hp || !o || !res) return fail(B200ODE_EINVAL, "NULL argument");
     if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
     int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, hp->t0, hp->tf, o);
@@ -580,7 +619,7 @@ int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp,
     CUDA_TRY(cudaSetDevice(h->device));
     const int n = prog->n, np = prog->np;
     const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
-    const int nslots = res->us ? b200ode_nslots(hp, o) : 0;
+    const int nslots = (res->us || stats_only) ? b200ode_nslots(hp, o) : 0;
     cudaStream_t s = h->stream;
 
     CUDA_TRY(cudaEventRecord(h->ev0, s));
@@ -606,7 +645,7 @@ int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp,
     // Chunked pipeline: the D2H of the saveat rows of chunk c (copy stream) overlaps the
     // kernels of chunk c+1 (compute stream).  Final-state-only solves are a single chunk.
     long long chunk = N;
-    if (nslots > 0 && N > 131072) {
+    if (nslots > 0 && N > 131072 && !stats_only) {
         chunk = (N + 7) / 8;
         chunk = ((chunk + 1023) / 1024) * 1024;
         if (chunk < 65536) chunk = 65536;
@@ -630,7 +669,7 @@ int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp,
         dr.njacs = i32 + 4 * N + c0; dr.nw = i32 + 5 * N + c0; dr.nsolve = i32 + 6 * N + c0; dr.retcode = i32 + 7 * N + c0;
         rc = b200ode_solve_device(h, prog, &dp, o, &dr, s);
         if (rc) return rc;
-        if (nslots > 0) {
+        if (nslots > 0 && !stats_only) {
             // per-chunk events are created on demand and kept in the handle
             size_t ci = (size_t)(c0 / chunk);
             while (h->chunk_events.size() <= ci) {
@@ -642,6 +681,16 @@ int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* hp,
             CUDA_TRY(cudaMemcpyAsync((char*)res->us + row_bytes * (size_t)c0, (char*)h->out_us.ptr + row_bytes * (size_t)c0,
                                      row_bytes * (size_t)cn, cudaMemcpyDeviceToHost, h->copy_stream));
         }
+    }
+    if (stats_only) {
+        // statistics on the device; only 2 * nslots * n doubles go back
+        CUDA_TRY(h->stat_out.ensure(sizeof(double) * 2 * (size_t)nslots * n));
+        double* dmean = (double*)h->stat_out.ptr;
+        double* dvar = dmean + (size_t)nslots * n;
+        rc = b200ode_timeseries_meanvar_device(h, prog->dtype, h->out_us.ptr, N, nslots, n, dmean, var ? dvar : nullptr, s);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(mean, dmean, sizeof(double) * (size_t)nslots * n, cudaMemcpyDeviceToHost, s));
+        if (var) CUDA_TRY(cudaMemcpyAsync(var, dvar, sizeof(double) * (size_t)nslots * n, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaEventRecord(h->ev2, s));
 
@@ -696,6 +745,31 @@ int b200ode_reduce_sum_device(b200ode_handle h, int dtype, const void* x, int la
     else
         k_reduce_partial<double><<<nblocks, 256, 0, s>>>((const double*)x, ts, cs, count, n, (double*)h->red_partial.ptr);
     k_reduce_final<<<1, 256, 0, s>>>((const double*)h->red_partial.ptr, nblocks, n, out);
+    CUDA_TRY(cudaGetLastError());
+    return B200ODE_OK;
+}
+
+int b200ode_timeseries_meanvar_device(b200ode_handle h, int dtype, const void* us, int64_t count, int nslots, int n,
+                                      double* mean, double* var, void* stream) {
+    if (!h || !us || !mean) return fail(B200ODE_EINVAL, "NULL argument");
+    if (count < 1 || nslots < 1 || n < 1) return fail(B200ODE_EINVAL, "count, nslots and n must be positive");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cols = nslots * n;
+    const int ychunks = (cols + 255) / 256;
+    int nparts = (4 * h->num_sms + ychunks - 1) / ychunks;
+    if ((long long)nparts > count) nparts = (int)count;
+    CUDA_TRY(h->red_partial.ensure(sizeof(double) * (size_t)nparts * cols));
+    double* part = (double*)h->red_partial.ptr;
+    dim3 g(nparts, ychunks);
+    if (dtype == B200ODE_F32) k_colsum_partial<float><<<g, 256, 0, s>>>((const float*)us, count, cols, nullptr, part);
+    else k_colsum_partial<double><<<g, 256, 0, s>>>((const double*)us, count, cols, nullptr, part);
+    k_colsum_final<<<ychunks, 256, 0, s>>>(part, nparts, cols, 1.0 / (double)count, mean);
+    if (var) {
+        if (dtype == B200ODE_F32) k_colsum_partial<float><<<g, 256, 0, s>>>((const float*)us, count, cols, mean, part);
+        else k_colsum_partial<double><<<g, 256, 0, s>>>((const double*)us, count, cols, mean, part);
+        k_colsum_final<<<ychunks, 256, 0, s>>>(part, nparts, cols, count > 1 ? 1.0 / (double)(count - 1) : 0.0, var);
+    }
     CUDA_TRY(cudaGetLastError());
     return B200ODE_OK;
 }

@@ -17,7 +17,7 @@ def _np_real(dtype):
 
 
 def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None,
-               maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None):
+               maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None, _meanvar=None):
     """Host arrays in, host arrays out (b200ode_solve).
 
     u0: (N, n) or (n,) shared; p: (N, np) or (np,) shared or None.
@@ -71,15 +71,29 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     res.u_final = buf("u_final", (N, n), rdt).ctypes.data
     res.t_final = buf("t_final", (N,), np.float64).ctypes.data
     if nslots > 0:
-        res.us = buf("us", (N, nslots, n), rdt).ctypes.data
+        if _meanvar is None:
+            res.us = buf("us", (N, nslots, n), rdt).ctypes.data
         res.ts = buf("ts", (nslots,), np.float64).ctypes.data
     for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         setattr(res, name, buf(name, (N,), np.int32).ctypes.data)
-    _lib.check(L.b200ode_solve(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res)))
+    if _meanvar is not None:
+        mean = buf("mean", (nslots, n), np.float64)
+        var = buf("var", (nslots, n), np.float64) if _meanvar[1] else None
+        _lib.check(L.b200ode_solve_meanvar(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res),
+                                           C.c_void_p(mean.ctypes.data), C.c_void_p(var.ctypes.data) if var is not None else None))
+    else:
+        _lib.check(L.b200ode_solve(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res)))
     out["kernel_ms"] = res.kernel_ms
     out["total_ms"] = res.total_ms
     out["nslots"] = nslots
     return out
+
+
+def solve_host_meanvar(program, u0, p, tspan, saveat, trajectories=None, want_var=True, **kw):
+    """EnsembleAnalysis.timeseries_steps_meanvar without moving the trajectories to the host
+    (b200ode_solve_meanvar): returns dict with ts, mean[nslots][n], var[nslots][n] and the
+    per-trajectory scalars (u_final, retcode, counters)."""
+    return solve_host(program, u0, p, tspan, trajectories=trajectories, saveat=saveat, _meanvar=(True, want_var), **kw)
 
 
 def nslots_for(tspan, saveat, save_start=None, save_end=None):
@@ -143,3 +157,15 @@ def reduce_sum_device(handle, dtype, x, layout, count, n, out, stream=None):
         stream = torch.cuda.current_stream().cuda_stream
     _lib.check(L.b200ode_reduce_sum_device(handle._h, dtype, C.c_void_p(x.data_ptr()), layout, int(count), int(n),
                                            C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
+
+
+def timeseries_meanvar_device(handle, dtype, us, mean, var=None, stream=None):
+    """mean/var (torch float64 [nslots, n], device) over the trajectories of us [N, nslots, n]."""
+    L = _lib.lib()
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    N, nslots, n = us.shape
+    _lib.check(L.b200ode_timeseries_meanvar_device(handle._h, dtype, C.c_void_p(us.data_ptr()), int(N), int(nslots), int(n),
+                                                   C.c_void_p(mean.data_ptr()),
+                                                   C.c_void_p(var.data_ptr()) if var is not None else None, C.c_void_p(stream)))

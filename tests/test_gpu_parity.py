@@ -294,3 +294,33 @@ def test_high_level_solve_api(pkg, oracle):
     s5 = P.solve(ep5, P.Rodas5P(), P.EnsembleB200(), trajectories=64, save_everystep=False, reltol=1e-6, abstol=1e-8)
     assert all(s5[i].retcode == "Success" for i in range(64))
     assert abs(float(s5[3].u[-1].sum()) - 1.0) < 1e-9
+
+
+def test_timeseries_meanvar_on_device(pkg, progs, oracle):
+    """EnsembleAnalysis.timeseries_steps_meanvar evaluated on the device
+    (reference: lib/DiffEqBase/test/downstream/ensemble_analysis.jl:12-33, m ≈ m2, v ≈ v4)."""
+    import torch
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    for f32 in (False, True):
+        N = 5000
+        p = pl.lorenz_params(N, f32=f32)
+        prog = progs(pkg.ALG_TSIT5, f32, "lorenz")
+        full = ll.solve_host(prog, U0, p, (0.0, 10.0), saveat=GRID)
+        st = ll.solve_host_meanvar(prog, U0, p, (0.0, 10.0), GRID)
+        us = full["us"].astype(np.float64)
+        assert "us" not in st and st["mean"].shape == (101, 3)
+        assert np.allclose(st["mean"], us.mean(axis=0), rtol=1e-12, atol=1e-13)
+        assert np.allclose(st["var"], us.var(axis=0, ddof=1), rtol=1e-10, atol=1e-12)
+        assert np.array_equal(st["naccept"], full["naccept"]) and np.array_equal(bits(st["u_final"]), bits(full["u_final"]))
+        # the oracle's trajectories give the same statistics
+        o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(f32), U0, p, (0.0, 10.0), 3, 3, f32=f32, saveat=GRID)
+        assert np.allclose(st["mean"], o["us"].astype(np.float64).mean(axis=0), rtol=1e-12, atol=1e-13)
+        # device-resident entry point, deterministic (two calls, same bits)
+        d_us = torch.from_numpy(full["us"]).cuda()
+        m1 = torch.zeros((101, 3), dtype=torch.float64, device="cuda"); v1 = torch.zeros_like(m1)
+        m2 = torch.zeros_like(m1); v2 = torch.zeros_like(m1)
+        ll.timeseries_meanvar_device(prog.handle, prog.dtype, d_us, m1, v1)
+        ll.timeseries_meanvar_device(prog.handle, prog.dtype, d_us, m2, v2)
+        torch.cuda.synchronize()
+        assert torch.equal(m1, m2) and torch.equal(v1, v2)
+        assert np.array_equal(m1.cpu().numpy(), st["mean"])
