@@ -10,7 +10,7 @@
 #define AOT_STR(x) AOT_STR2(x)
 #include AOT_STR(AOT_PROBLEM_INC)
 
-#define B200_RHS(du, u, p, t) AOT_RHS_NAME((du), (u), (p), (t))
+#define B200_USER_RHS(du, u, p, t) AOT_RHS_NAME((du), (u), (p), (t))
 #ifdef AOT_JAC_NAME
 #define B200_JAC(J, u, p, t) AOT_JAC_NAME((J), (u), (p), (t))
 #define B200_TGRAD(dT, u, p, t) AOT_TGRAD_NAME((dT), (u), (p), (t))

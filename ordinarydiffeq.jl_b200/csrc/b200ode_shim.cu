@@ -100,6 +100,8 @@ struct b200ode_program_s {
     std::vector<char> cubin;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t k_integrate = nullptr, k_initdt = nullptr;
+    int sliced_g = 0;            // > 0: component-sliced kernel with this many warps per 32 trajectories
+    size_t dyn_smem = 0;
     B200ProgramInfo info{};
 };
 
@@ -153,7 +155,7 @@ int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src
 // Assemble the translation unit and run NVRTC.
 int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                 const char* jac_src, const char* jac_name, const char* tgrad_src, const char* tgrad_name,
-                const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms) {
+                const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms, int* sliced_g = nullptr) {
     int rc = validate_compile_args(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name);
     if (rc) return rc;
     bool stiff = (alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_RODAS5P);
@@ -194,7 +196,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         }
     }
     tu += "// ---- steppers ----\n";
-    tu += std::string("#define B200_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
+    tu += std::string("#define B200_USER_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
     if (stiff) {
         tu += std::string("#define B200_JAC(J,u,p,t) ") + jac_name + "((J),(u),(p),(t))\n";
         if (tgrad_src) tu += std::string("#define B200_TGRAD(dT,u,p,t) ") + tgrad_name + "((dT),(u),(p),(t))\n";
@@ -228,6 +230,22 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         }
     }
     int words = n * (dtype == B200ODE_F32 ? 1 : 2);
+    // Component-sliced kernel (device/b200_sliced.cuh, G warps per 32 trajectories): opt-in with
+    // -DB200_SLICED=1.  Measured on Pleiades/Vern7 (r1): bit-exact but 510-930 ms vs 180-220 ms — the
+    // G warps of a CTA run G different slices of the straight-line RHS, so the instruction stream per
+    // SM is G times wider and the 43 KB RHS thrashes the 32 KB instruction cache
+    // (ncu: stall_no_instruction 12 per issue).  It pays only for RHS code that fits the cache.
+    bool sliced = false;
+    if (extra_options && strstr(extra_options, "-DB200_SLICED=0")) sliced = false;
+    if (extra_options && strstr(extra_options, "-DB200_SLICED=1")) sliced = (alg == B200ODE_ALG_VERN7);
+    if (sliced) {
+        if (!(extra_options && strstr(extra_options, "-DB200_SLICED="))) opts.push_back("-DB200_SLICED=1");
+        if (!(extra_options && strstr(extra_options, "-DB200_G="))) {
+            int g = (n + 3) / 4;
+            if (g > 16) g = 16;
+            opts.push_back("-DB200_G=" + std::to_string(g));
+        }
+    }
     if (!has_block) opts.push_back("-DB200_BLOCK=128");
     if (!has_minb) {
         // registers available per thread at k CTAs of 128 threads: 65536/(128k)
@@ -236,6 +254,15 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         else if (alg == B200ODE_ALG_VERN7) minb = (words <= 6) ? 3 : 1;
         else minb = (words <= 8) ? 4 : (words <= 16 ? 2 : 1);
         opts.push_back("-DB200_MINBLOCKS=" + std::to_string(minb));
+    }
+    if (sliced_g) {
+        *sliced_g = 0;
+        bool on = false; int g = 0;
+        for (auto& o : opts) {
+            if (o == "-DB200_SLICED=1") on = true;
+            if (o.rfind("-DB200_G=", 0) == 0) g = atoi(o.c_str() + 9);
+        }
+        if (on && g > 0) *sliced_g = g;
     }
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -404,13 +431,16 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         CUDA_TRY(cudaLaunchKernel((const void*)prog->k_initdt, dim3(g), dim3(256), args, 0, stream));
     }
     unsigned grid;
-    if (o->flags & B200ODE_FLAG_STATIC_SCHEDULE) grid = (unsigned)((N + prog->info.block - 1) / prog->info.block);
+    if (prog->sliced_g > 0) {
+        long long nbatch = (N + 31) / 32;
+        grid = (unsigned)std::min<long long>(prog->info.grid, nbatch);
+    } else if (o->flags & B200ODE_FLAG_STATIC_SCHEDULE) grid = (unsigned)((N + prog->info.block - 1) / prog->info.block);
     else {
         grid = (unsigned)prog->info.grid;
         long long need = (N + prog->info.block - 1) / prog->info.block;
         if ((long long)grid > need) grid = (unsigned)(need > 0 ? need : 1);
     }
-    CUDA_TRY(cudaLaunchKernel((const void*)prog->k_integrate, dim3(grid), dim3(prog->info.block), args, 0, stream));
+    CUDA_TRY(cudaLaunchKernel((const void*)prog->k_integrate, dim3(grid), dim3(prog->info.block), args, prog->dyn_smem, stream));
     return B200ODE_OK;
 }
 
@@ -517,8 +547,10 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     prog->h = h; prog->alg = alg; prog->dtype = dtype; prog->n = n; prog->np = np;
     std::string log; double ms = 0;
     int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
-                         extra_options, prog->cubin, log, &ms);
+                         extra_options, prog->cubin, log, &ms, &prog->sliced_g);
     if (rc) { delete prog; return rc; }
+    if (prog->sliced_g > 0)
+        prog->dyn_smem = (size_t)(3 * n * 32 + prog->sliced_g * 32) * (dtype == B200ODE_F32 ? 4 : 8);
     cudaError_t e = cudaLibraryLoadData(&prog->lib, prog->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
@@ -540,8 +572,13 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
         prog->info.regs_initdt = fb.numRegs;
         prog->info.local_bytes_initdt = (int)fb.localSizeBytes;
     }
+    if (prog->dyn_smem > 48 * 1024) {
+        e = cudaFuncSetAttribute((const void*)prog->k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prog->dyn_smem);
+        if (e != cudaSuccess) { cudaLibraryUnload(prog->lib); delete prog; return fail(B200ODE_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+    }
+    prog->info.smem_bytes_integrate += (int)prog->dyn_smem;
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)prog->k_integrate, prog->info.block, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)prog->k_integrate, prog->info.block, prog->dyn_smem);
     if (e != cudaSuccess || nb < 1) nb = 1;
     prog->info.blocks_per_sm = nb;
     prog->info.grid = nb * h->num_sms;

@@ -32,13 +32,22 @@
 #define B200_ALG_ROS23 3
 #define B200_ALG_RODAS5P 4
 
-#if B200_ALG == B200_ALG_TSIT5
+#ifndef B200_SLICED
+#define B200_SLICED 0
+#endif
+
+#if B200_SLICED
+// defined below, after B200Params (b200_sliced.cuh)
+#elif B200_ALG == B200_ALG_TSIT5
+#define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_tsit5.cuh"
 typedef B200Tsit5 B200Stepper;
 #elif B200_ALG == B200_ALG_VERN7
+#define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_vern7.cuh"
 typedef B200Vern7 B200Stepper;
 #elif B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_rosenbrock.cuh"
 #if B200_ALG == B200_ALG_ROS23
 typedef B200Ros23 B200Stepper;
@@ -83,6 +92,18 @@ struct B200Params {
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
 
+#ifndef B200_BLOCK
+#define B200_BLOCK 128
+#endif
+#ifndef B200_MINBLOCKS
+#define B200_MINBLOCKS 1
+#endif
+
+#if B200_SLICED
+#include "b200_sliced.cuh"
+typedef B200SlicedStepper B200Stepper;
+#endif
+
 // ---------------------------------------------------------------------------
 // ODE_DEFAULT_NORM for a static vector: sqrt(sum(abs2,u)/n), left fold, no fusion
 // (lib/DiffEqBase/src/common_defaults.jl:102-107).
@@ -104,7 +125,7 @@ B200_D real b200_initdt_one(const real* u0, const real* p, real t, real dtmax_td
 #pragma unroll
     for (int i = 0; i < B200_N; ++i) tmp[i] = u0[i] / sk[i];
     real d0 = b200_rms(tmp);
-    B200_RHS(f0, u0, p, t);
+    B200_USER_RHS(f0, u0, p, t);
     bool anynan = false;
 #pragma unroll
     for (int i = 0; i < B200_N; ++i) anynan = anynan || b200_isnan(f0[i]);
@@ -122,7 +143,7 @@ B200_D real b200_initdt_one(const real* u0, const real* p, real t, real dtmax_td
     real u1[B200_N], f1[B200_N];
 #pragma unroll
     for (int i = 0; i < B200_N; ++i) u1[i] = b200_fma(dt0, f0[i], u0[i]);
-    B200_RHS(f1, u1, p, t + dt0);
+    B200_USER_RHS(f1, u1, p, t + dt0);
     bool alleq = true;
 #pragma unroll
     for (int i = 0; i < B200_N; ++i) alleq = alleq && (f0[i] == f1[i]);
@@ -157,6 +178,7 @@ extern "C" __global__ void __launch_bounds__(256) b200_initdt(B200Params P) {
     P.dt0[i] = b200_initdt_one(u0, p, P.t0, dtmax, P.abstol, P.reltol, P.dtmin, B200Stepper::order());
 }
 
+#if !B200_SLICED
 // ---------------------------------------------------------------------------
 struct B200Traj {
     real u[B200_N], uprev[B200_N];
@@ -184,10 +206,6 @@ B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, const rea
     T.nsaved += 1;
 }
 
-// min/max against an operand that is known not to be NaN (c): a NaN in x propagates,
-// exactly like Base.min/max, at the cost of one compare.
-B200_D real b200_min_c(real c, real x) { return (c < x) ? c : x; }
-B200_D real b200_max_c(real c, real x) { return (c > x) ? c : x; }
 
 // modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch, tstops={tf}.
 // tol100 = 100*eps(max(|t|,|tf|)) and dist = |tf - t| depend only on t.
@@ -489,3 +507,4 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
         }
     }
 }
+#endif  // !B200_SLICED

@@ -12,6 +12,21 @@
 #include "b200_base.cuh"
 #include "b200_tableaus_gen.cuh"
 
+// B200_VLEN: components held by one thread.  One-trajectory-per-thread kernels hold the whole
+// state (B200_N); the sliced kernel (b200_sliced.cuh) holds ceil(n/G) components per thread.
+#ifndef B200_VLEN
+#define B200_VLEN B200_N
+#endif
+#ifndef B200_NORM
+#define B200_NORM(res, u) b200_norm_local(res)
+B200_D real b200_norm_local(const real* res) {
+    real acc = res[0] * res[0];
+#pragma unroll
+    for (int i = 1; i < B200_VLEN; ++i) acc = acc + res[i] * res[i];
+    return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
+}
+#endif
+
 struct B200Vern7Coeffs {
 #define B200_X(name, val) real name;
     B200_VERN7_TABLEAU(B200_X)
@@ -46,19 +61,22 @@ __constant__ B200Vern7Coeffs B200_VERN7_C = {
 // Component loops are fully unrolled by default; -DB200_STAGE_UNROLL=k rolls them (smaller code,
 // but stage vectors are then indexed dynamically and live in local memory).
 #ifndef B200_STAGE_UNROLL
-#define B200_STAGE_UNROLL B200_N      // measured best also for n = 28 (see b200ode_shim.cu)
+#define B200_STAGE_UNROLL B200_VLEN   // full unroll: measured best also for n = 28 (see b200ode_shim.cu)
 #endif
 #define B200_PRAGMA_(x) _Pragma(#x)
 #define B200_PRAGMA(x) B200_PRAGMA_(x)
 #define B200_UNROLL_STAGE B200_PRAGMA(unroll B200_STAGE_UNROLL)
 #define B200_V7_STAGE(dst, expr)                                                  \
-    B200_UNROLL_STAGE for (int i = 0; i < B200_N; ++i) dst[i] = b200_fma(dt, (expr), uprev[i]);
+    B200_UNROLL_STAGE for (int i = 0; i < B200_VLEN; ++i) dst[i] = b200_fma(dt, (expr), uprev[i]);
 
 struct B200Vern7 {
-    real k1[B200_N], k2[B200_N], k3[B200_N], k4[B200_N], k5[B200_N], k6[B200_N], k7[B200_N], k8[B200_N],
-        k9[B200_N], k10[B200_N];
-    real k11[B200_N], k12[B200_N], k13[B200_N], k14[B200_N], k15[B200_N], k16[B200_N];   // lazy extra stages
+    real k1[B200_VLEN], k2[B200_VLEN], k3[B200_VLEN], k4[B200_VLEN], k5[B200_VLEN], k6[B200_VLEN], k7[B200_VLEN], k8[B200_VLEN],
+        k9[B200_VLEN], k10[B200_VLEN];
+    real k11[B200_VLEN], k12[B200_VLEN], k13[B200_VLEN], k14[B200_VLEN], k15[B200_VLEN], k16[B200_VLEN];   // lazy extra stages
 
+#ifdef B200_STEPPER_EXTRA_MEMBERS
+    B200_STEPPER_EXTRA_MEMBERS
+#endif
     static B200_D int order() { return 7; }
     static B200_D real qsteady_min() { return (real)1; }
     static B200_D real qsteady_max() { return (real)1; }
@@ -69,11 +87,11 @@ struct B200Vern7 {
     B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt, real reltol, real abstol,
                         int& nf) {
         const B200Vern7Coeffs& C = B200_VERN7_C;
-        real tmp[B200_N];
+        real tmp[B200_VLEN];
         B200_RHS(k1, uprev, p, t);
         const real a = dt * C.a021;
         B200_UNROLL_STAGE
-        for (int i = 0; i < B200_N; ++i) tmp[i] = b200_fma(a, k1[i], uprev[i]);
+        for (int i = 0; i < B200_VLEN; ++i) tmp[i] = b200_fma(a, k1[i], uprev[i]);
         B200_RHS(k2, tmp, p, b200_fma(C.c2, dt, t));
         B200_V7_STAGE(tmp, B200_V7_2(a031, k1, a032, k2))
         B200_RHS(k3, tmp, p, b200_fma(C.c3, dt, t));
@@ -93,16 +111,14 @@ struct B200Vern7 {
         B200_RHS(k10, tmp, p, t + dt);
         nf += 10;
         B200_V7_STAGE(u, B200_V7_7(b1, k1, b4, k4, b5, k5, b6, k6, b7, k7, b8, k8, b9, k9))
-        real acc = (real)0;
+        real res[B200_VLEN];
         B200_UNROLL_STAGE
-        for (int i = 0; i < B200_N; ++i) {
+        for (int i = 0; i < B200_VLEN; ++i) {
             real ut = dt * B200_V7_8(btilde1, k1, btilde4, k4, btilde5, k5, btilde6, k6, btilde7, k7, btilde8, k8,
                                      btilde9, k9, btilde10, k10);
-            real r = ut / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
-            real r2 = r * r;
-            acc = (i == 0) ? r2 : (acc + r2);
+            res[i] = ut / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
         }
-        return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
+        return B200_NORM(res, u);
     }
 
     B200_D void accept() {}
@@ -110,7 +126,7 @@ struct B200Vern7 {
     // _ode_addsteps! extra stages k11..k16 at (tprev, uprev) with the step's dt; not counted in nf
     B200_D void dense_prepare(const real* uprev, const real* /*u*/, const real* p, real t, real dt) {
         const B200Vern7Coeffs& C = B200_VERN7_C;
-        real tmp[B200_N];
+        real tmp[B200_VLEN];
         B200_V7_STAGE(tmp, B200_V7_7(a1101, k1, a1104, k4, a1105, k5, a1106, k6, a1107, k7, a1108, k8, a1109, k9))
         B200_RHS(k11, tmp, p, b200_fma(C.c11, dt, t));
         B200_V7_STAGE(tmp, B200_V7_8(a1201, k1, a1204, k4, a1205, k5, a1206, k6, a1207, k7, a1208, k8, a1209, k9,
@@ -150,7 +166,7 @@ struct B200Vern7 {
         const real b16 = th2 * B200_P6(r162, r163, r164, r165, r166, r167);
 #undef B200_P6
         B200_UNROLL_STAGE
-        for (int i = 0; i < B200_N; ++i) {
+        for (int i = 0; i < B200_VLEN; ++i) {
             real s = k1[i] * b1;
             s = b200_fma(k4[i], b4, s);
             s = b200_fma(k5[i], b5, s);

@@ -52,8 +52,31 @@ def robertson_sources(f32=False):
     return (rhs, "rober_rhs"), (jac, "rober_jac"), (tgrad, "rober_tgrad")
 
 
-def pleiades_source(f32=False, name="pleiades_rhs"):
-    """Straight-line code (all indices static so the state stays in registers)."""
+def pleiades_source(f32=False, name="pleiades_rhs", loops=False):
+    """Pleiades right-hand side.  loops=True mirrors the reference's Julia loops
+    (`for i in 1:7, j in 1:7; i != j`) — a small loop body that stays in the instruction cache;
+    loops=False emits the same arithmetic as straight-line code (42 unrolled pairs).  Both forms
+    perform identical operations in identical order."""
+    if loops:
+        T = _ty(f32)
+        sq = "sqrtf" if f32 else "sqrt"
+        suf = "f" if f32 else ""
+        return ("void %s(%s* du, const %s* u, const %s* p, const %s t) {\n"
+                "  for (int i = 0; i < 7; ++i) { du[i] = u[14 + i]; du[7 + i] = u[21 + i]; }\n"
+                "  #pragma unroll 1\n"
+                "  for (int i = 0; i < 7; ++i) {\n"
+                "    %s ax = 0.0%s, ay = 0.0%s;\n"
+                "    #pragma unroll 1\n"
+                "    for (int j = 0; j < 7; ++j) {\n"
+                "      if (j == i) continue;\n"
+                "      %s dx = u[j] - u[i]; %s dy = u[7 + j] - u[7 + i];\n"
+                "      %s r = %s(dx * dx + dy * dy); %s r3 = r * r * r;\n"
+                "      %s m = (%s)(j + 1);\n"
+                "      ax = ax + m * dx / r3; ay = ay + m * dy / r3;\n"
+                "    }\n"
+                "    du[14 + i] = ax; du[21 + i] = ay;\n"
+                "  }\n"
+                "}\n" % (name, T, T, T, T, T, suf, suf, T, T, T, sq, T, T, T)), name
     T = _ty(f32)
     sq = "sqrtf" if f32 else "sqrt"
     suf = "f" if f32 else ""

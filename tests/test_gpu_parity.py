@@ -324,3 +324,25 @@ def test_timeseries_meanvar_on_device(pkg, progs, oracle):
         torch.cuda.synchronize()
         assert torch.equal(m1, m2) and torch.equal(v1, v2)
         assert np.array_equal(m1.cpu().numpy(), st["mean"])
+
+
+def test_sliced_kernel_variant_is_bit_exact(pkg, handle, oracle):
+    """The opt-in component-sliced Vern7 kernel (G warps per 32 trajectories, stage vectors exchanged
+    through shared memory) reproduces the oracle bit for bit, with and without lazy interpolation."""
+    pl = pkg.problems_library
+    N = 300
+    src, name = pl.pleiades_source(False)
+    prog = handle.compile(pkg.ALG_VERN7, pkg.F64, 28, 0, src, name, extra_options="-DB200_SLICED=1")
+    assert prog.info["block"] == 7 * 32
+    u0 = pl.pleiades_u0(N)
+    for extra in ({}, {"saveat": [0.4, 1.1, 1.15, 2.9]}):
+        kw = dict(reltol=1e-6, abstol=1e-8, **extra)
+        g = pkg.lowlevel.solve_host(prog, u0, None, (0.0, 3.0), **kw)
+        o = oracle.solve(oracle.ALG_VERN7, (src, name), u0, None, (0.0, 3.0), 28, 0, **kw)
+        assert_same_result(g, o)
+    s3, n3 = pl.lorenz_source(False)
+    prog3 = handle.compile(pkg.ALG_VERN7, pkg.F64, 3, 3, s3, n3, extra_options="-DB200_SLICED=1 -DB200_G=2")
+    p = pl.lorenz_params(100)
+    g = pkg.lowlevel.solve_host(prog3, U0, p, (0.0, 5.0), saveat=[1.0, 2.5], maxiters=60)
+    o = oracle.solve(oracle.ALG_VERN7, (s3, n3), U0, p, (0.0, 5.0), 3, 3, saveat=[1.0, 2.5], maxiters=60)
+    assert_same_result(g, o)
