@@ -55,7 +55,9 @@ def sources(pl, w):
         r, j, tg = pl.robertson_sources(f32)
         return r, j, tg, 3, 3
     if w["problem"] == "pleiades":
-        return pl.pleiades_source(f32), None, None, 28, 0
+        # loop-form source + partially rolled stage loops: same speed as the fully unrolled form,
+        # 20x shorter NVRTC compile
+        return pl.pleiades_source(f32, loops=True), None, None, 28, 0
     raise ValueError(w["problem"])
 
 
@@ -284,7 +286,8 @@ def main():
     alg_id = {"tsit5": pkg.ALG_TSIT5, "vern7": pkg.ALG_VERN7, "ros23": pkg.ALG_ROSENBROCK23, "rodas5p": pkg.ALG_RODAS5P}[w["alg"]]
     dtype = pkg.F32 if w["f32"] else pkg.F64
     prog = h.compile(alg_id, dtype, n, np_, rhs[0], rhs[1], jac[0] if jac else None, jac[1] if jac else None,
-                     tg[0] if tg else None, tg[1] if tg else None)
+                     tg[0] if tg else None, tg[1] if tg else None,
+                     extra_options="-DB200_STAGE_UNROLL=4" if w["problem"] == "pleiades" else None)
     N = w["N"]
     grid = pkg.ranges.saveat_grid(w["saveat"], w["tspan"]) if w["saveat"] is not None else None
     nslots = ll.nslots_for(w["tspan"], grid) if grid else 0

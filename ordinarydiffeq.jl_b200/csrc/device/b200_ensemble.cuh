@@ -192,16 +192,17 @@ struct B200Traj {
     int save_idx, nsaved;
     int retcode;
     bool accept, tstop_flag;
+    real* row;                  // next row of us[idx][.][:] (running pointer: no 64-bit index arithmetic per row)
 #if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
     int njacs, nw, nsolve;
 #endif
 };
 
 B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, const real* v) {
-    if (P.nslots > 0 && T.nsaved < P.nslots) {
-        real* dst = P.us + ((size_t)idx * (size_t)P.nslots + (size_t)T.nsaved) * B200_N;
+    if (T.nsaved < P.nslots) {              // nslots == 0: no time series requested
 #pragma unroll
-        for (int c = 0; c < B200_N; ++c) dst[c] = v[c];
+        for (int c = 0; c < B200_N; ++c) T.row[c] = v[c];
+        T.row += B200_N;
     }
     T.nsaved += 1;
 }
@@ -230,6 +231,7 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     T.njacs = 0; T.nw = 0; T.nsolve = 0;
 #endif
     T.nsaved = 0; T.save_idx = 0;
+    T.row = P.us + (size_t)idx * (size_t)P.nslots * B200_N;
     if (P.save_start) b200_emit(P, idx, T, T.u);      // solve.jl:809-824
     T.st.init(T.u, T.p, T.t, T.nf);                   // initialize!(integrator, cache)
     if (P.dt_user == (real)0) { T.dt = P.dt0[idx]; T.nf += 2; }   // auto_dt_reset!: nf += 2
