@@ -246,6 +246,14 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
             opts.push_back("-DB200_G=" + std::to_string(g));
         }
     }
+    // measured launch shapes (scripts/sweep_dev.py): small explicit systems run best as one 512-thread
+    // CTA per SM at 128 registers (FP64) / three 256-thread CTAs at 80 registers (FP32)
+    const bool small_explicit = !stiff && words <= 8 && alg == B200ODE_ALG_TSIT5;
+    if (small_explicit && !has_block && !has_minb) {
+        if (dtype == B200ODE_F32) { opts.push_back("-DB200_BLOCK=256"); opts.push_back("-DB200_MINBLOCKS=3"); }
+        else { opts.push_back("-DB200_BLOCK=512"); opts.push_back("-DB200_MINBLOCKS=1"); }
+        has_block = has_minb = true;
+    }
     if (!has_block) opts.push_back("-DB200_BLOCK=128");
     if (!has_minb) {
         // registers available per thread at k CTAs of 128 threads: 65536/(128k)

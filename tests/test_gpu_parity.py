@@ -251,6 +251,38 @@ def test_full_size_1M_lorenz_properties(pkg, progs, oracle):
     assert np.array_equal(bits(g["us"][idx]), bits(o["us"]))
 
 
+def test_full_size_robertson_and_pleiades_properties(pkg, progs, oracle):
+    """configs[2] and configs[3] at BASELINE sizes: every trajectory succeeds, the invariants of the
+    problems hold, and the oracle agrees bit for bit on a seeded subsample."""
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    N = 1 << 20
+    k = pl.robertson_params(N)
+    r, j, tg = pl.robertson_sources(False)
+    idx = np.sort(np.random.default_rng(11).choice(N, 1500, replace=False))
+    for alg, oalg in ((pkg.ALG_RODAS5P, oracle.ALG_RODAS5P), (pkg.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK23)):
+        g = ll.solve_host(progs(alg, False, "robertson"), U0, k, (0.0, 1e5), reltol=1e-6, abstol=1e-8)
+        assert (g["retcode"] == 1).all() and (g["t_final"] == 1e5).all()
+        assert np.abs(g["u_final"].sum(axis=1) - 1.0).max() < 1e-9            # mass conservation
+        assert (g["u_final"] > -1e-9).all()
+        o = oracle.solve(oalg, r, U0, k[idx], (0.0, 1e5), 3, 3, jac=j, tgrad=tg, reltol=1e-6, abstol=1e-8)
+        assert np.array_equal(g["naccept"][idx], o["naccept"]) and np.array_equal(g["nreject"][idx], o["nreject"])
+        assert np.array_equal(bits(g["u_final"][idx]), bits(o["u_final"]))
+    Np = 1 << 18
+    u0 = pl.pleiades_u0(Np)
+    g = ll.solve_host(progs(pkg.ALG_VERN7, False, "pleiades"), u0, None, (0.0, 3.0), reltol=1e-6, abstol=1e-8)
+    assert (g["retcode"] == 1).all()
+    assert (g["nf"] == 2 + 10 * (g["naccept"] + g["nreject"])).all()
+    # total linear momentum sum_j m_j v_j is conserved by the pairwise forces (m_j = j)
+    m = np.arange(1, 8, dtype=np.float64)
+    for lo in (14, 21):
+        p0 = (u0[:, lo:lo + 7] * m).sum(axis=1)
+        p1 = (g["u_final"][:, lo:lo + 7] * m).sum(axis=1)
+        assert np.abs(p1 - p0).max() < 1e-4
+    idx = np.sort(np.random.default_rng(12).choice(Np, 96, replace=False))
+    o = oracle.solve(oracle.ALG_VERN7, pl.pleiades_source(), u0[idx], None, (0.0, 3.0), 28, 0, reltol=1e-6, abstol=1e-8)
+    assert np.array_equal(g["naccept"][idx], o["naccept"]) and np.array_equal(bits(g["u_final"][idx]), bits(o["u_final"]))
+
+
 def test_high_level_solve_api(pkg, oracle):
     P = pkg
     pl = P.problems_library
