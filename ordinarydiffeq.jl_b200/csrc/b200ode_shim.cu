@@ -101,6 +101,7 @@ struct b200ode_program_s {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t k_integrate = nullptr, k_initdt = nullptr;
     int sliced_g = 0;            // > 0: component-sliced kernel with this many warps per 32 trajectories
+    int sliced_k = 1;            // groups of 32 trajectories per CTA
     size_t dyn_smem = 0;
     B200ProgramInfo info{};
 };
@@ -265,12 +266,13 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     }
     if (sliced_g) {
         *sliced_g = 0;
-        bool on = false; int g = 0;
+        bool on = false; int g = 0, k = 1;
         for (auto& o : opts) {
             if (o == "-DB200_SLICED=1") on = true;
             if (o.rfind("-DB200_G=", 0) == 0) g = atoi(o.c_str() + 9);
+            if (o.rfind("-DB200_K=", 0) == 0) k = atoi(o.c_str() + 9);
         }
-        if (on && g > 0) *sliced_g = g;
+        if (on && g > 0) *sliced_g = g + 1000 * (k > 0 ? k : 1);      // packed: G + 1000*K
     }
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -440,7 +442,8 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     }
     unsigned grid;
     if (prog->sliced_g > 0) {
-        long long nbatch = (N + 31) / 32;
+        long long per = 32LL * prog->sliced_k;
+        long long nbatch = (N + per - 1) / per;
         grid = (unsigned)std::min<long long>(prog->info.grid, nbatch);
     } else if (o->flags & B200ODE_FLAG_STATIC_SCHEDULE) grid = (unsigned)((N + prog->info.block - 1) / prog->info.block);
     else {
@@ -557,8 +560,12 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
                          extra_options, prog->cubin, log, &ms, &prog->sliced_g);
     if (rc) { delete prog; return rc; }
-    if (prog->sliced_g > 0)
-        prog->dyn_smem = (size_t)(3 * n * 32 + prog->sliced_g * 32) * (dtype == B200ODE_F32 ? 4 : 8);
+    if (prog->sliced_g > 0) {
+        prog->sliced_k = prog->sliced_g / 1000;
+        prog->sliced_g = prog->sliced_g % 1000;
+        prog->dyn_smem = prog->sliced_g > 1
+            ? (size_t)prog->sliced_k * (3 * n * 32 + prog->sliced_g * 32) * (dtype == B200ODE_F32 ? 4 : 8) : 0;
+    }
     cudaError_t e = cudaLibraryLoadData(&prog->lib, prog->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");

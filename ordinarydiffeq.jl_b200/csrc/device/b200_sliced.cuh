@@ -21,18 +21,28 @@
 #error "B200_G (slices per trajectory) must be defined for the sliced kernel"
 #endif
 #define B200_VLEN ((B200_N + B200_G - 1) / B200_G)
+// B200_K groups of G slice-warps per CTA; group k owns trajectories [32k, 32k+32) of the CTA's batch.
+// All warps of the CTA run in lockstep (one barrier per RHS evaluation), so warps that execute the
+// same slice fetch the same instructions together.  G = 1 degenerates to one trajectory per thread
+// with CTA-lockstepped stages ("lockstep" mode).
+#ifndef B200_K
+#define B200_K 1
+#endif
+#define B200_SLICE() ((int)(threadIdx.x >> 5) % B200_G)
+#define B200_GROUP() ((int)(threadIdx.x >> 5) / B200_G)
 
 extern __shared__ double b200_smem_raw[];
 
 struct B200SlicedSmem {
     // U[2][N][32], R[N][32], F[G][32] (as real), I[32] (long long refill indices)
-    B200_D static real* U(int buf) { return (real*)b200_smem_raw + (size_t)buf * B200_N * 32; }
-    B200_D static real* R() { return (real*)b200_smem_raw + (size_t)2 * B200_N * 32; }
-    B200_D static real* F() { return (real*)b200_smem_raw + (size_t)3 * B200_N * 32; }
+    B200_D static real* base() { return (real*)b200_smem_raw + (size_t)B200_GROUP() * (3 * B200_N * 32 + B200_G * 32); }
+    B200_D static real* U(int buf) { return base() + (size_t)buf * B200_N * 32; }
+    B200_D static real* R() { return base() + (size_t)2 * B200_N * 32; }
+    B200_D static real* F() { return base() + (size_t)3 * B200_N * 32; }
 };
-#define B200_SLICED_SMEM_REALS (3 * B200_N * 32 + B200_G * 32)
 
 // ---- one slice of the user's RHS -------------------------------------------------------------
+#if B200_G > 1
 struct B200VRet { real v[B200_VLEN]; };
 
 template <int W>
@@ -67,9 +77,18 @@ __device__ __noinline__ B200VRet b200_eval_slice(int w, const real* Ub, int lane
     return B200EvalDispatch<0>::run(w, Ub, lane, p, t);
 }
 
+#endif  // B200_G > 1
+
 // publish my components of the stage vector, barrier, evaluate my slice
 B200_D void b200_rhs_sliced(real* kout, const real* xin, const real* p, real t, int& sbuf) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#if B200_G == 1
+    __syncthreads();                       // lockstep only: keeps the CTA's warps on the same instructions
+    B200_USER_RHS(kout, xin, p, t);
+    (void)sbuf;
+    return;
+#endif
+#if B200_G > 1
+    const int lane = threadIdx.x & 31, w = B200_SLICE();
     real* Ub = B200SlicedSmem::U(sbuf);
 #pragma unroll
     for (int l = 0; l < B200_VLEN; ++l) {
@@ -81,12 +100,25 @@ B200_D void b200_rhs_sliced(real* kout, const real* xin, const real* p, real t, 
 #pragma unroll
     for (int l = 0; l < B200_VLEN; ++l) kout[l] = r.v[l];
     sbuf ^= 1;
+#endif
 }
 
 // error norm: left fold of the squared residuals of components 0..n-1 (any warp order) + the
 // "u is finite" flag of the new state, both exchanged through shared memory
 B200_D real b200_norm_sliced(const real* res, const real* u, bool& all_finite) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#if B200_G == 1
+    {
+        bool fin1 = true;
+        real acc1 = res[0] * res[0];
+#pragma unroll
+        for (int i = 1; i < B200_N; ++i) acc1 = acc1 + res[i] * res[i];
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) fin1 = fin1 && b200_isfinite(u[i]);
+        all_finite = fin1;
+        return b200_sqrt(b200_div_const(acc1, (real)B200_N, (real)1 / (real)B200_N));
+    }
+#endif
+    const int lane = threadIdx.x & 31, w = B200_SLICE();
     real* R = B200SlicedSmem::R();
     real* F = B200SlicedSmem::F();
     bool fin = true;
@@ -127,7 +159,7 @@ struct B200STraj {
 };
 
 B200_D void b200s_emit(const B200Params& P, long long idx, B200STraj& T, const real* v) {
-    const int w = threadIdx.x >> 5;
+    const int w = B200_SLICE();
     if (P.nslots > 0 && T.nsaved < P.nslots) {
         real* dst = P.us + ((size_t)idx * (size_t)P.nslots + (size_t)T.nsaved) * B200_N;
 #pragma unroll
@@ -147,7 +179,7 @@ B200_D void b200s_modify_dt_for_tstops(B200STraj& T, real dist, real tol100) {
 }
 
 B200_D void b200s_begin(const B200Params& P, long long idx, B200STraj& T, bool live) {
-    const int w = threadIdx.x >> 5;
+    const int w = B200_SLICE();
 #pragma unroll
     for (int l = 0; l < B200_VLEN; ++l) {
         const int c = w + B200_G * l;
@@ -175,7 +207,7 @@ B200_D void b200s_begin(const B200Params& P, long long idx, B200STraj& T, bool l
 }
 
 B200_D void b200s_end(const B200Params& P, long long idx, B200STraj& T) {
-    const int w = threadIdx.x >> 5;
+    const int w = B200_SLICE();
     if (T.retcode == B200_RC_DEFAULT) T.retcode = B200_RC_SUCCESS;
     if (P.save_end) {
         bool emit;
@@ -319,14 +351,14 @@ B200_D bool b200s_iterate(const B200Params& P, long long idx, B200STraj& T, bool
     return finished;
 }
 
-extern "C" __global__ void __launch_bounds__(32 * B200_G, B200_MINBLOCKS) b200_integrate(B200Params P) {
+extern "C" __global__ void __launch_bounds__(32 * B200_G * B200_K, B200_MINBLOCKS) b200_integrate(B200Params P) {
     B200STraj T;
     T.st.sbuf = 0;
     const int lane = threadIdx.x & 31;
-    // batches of 32 trajectories, CTA-strided
-    const long long nbatch = (P.N + 31) / 32;
+    // batches of 32*K trajectories, CTA-strided
+    const long long nbatch = (P.N + 32 * B200_K - 1) / (32 * B200_K);
     for (long long b = blockIdx.x; b < nbatch; b += gridDim.x) {
-        const long long idx = b * 32 + lane;
+        const long long idx = b * (32 * B200_K) + B200_GROUP() * 32 + lane;
         bool live = idx < P.N;
         const long long idx_c = live ? idx : (P.N - 1);      // inactive lanes shadow a valid trajectory, write nothing
         b200s_begin(P, idx_c, T, live);
