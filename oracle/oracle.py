@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 _BUILD = os.path.join(_HERE, "_build")
-_GCC_B = "-B/usr/lib/gcc/x86_64-linux-gnu/13"
+
 
 ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P = 1, 2, 3, 4
 
