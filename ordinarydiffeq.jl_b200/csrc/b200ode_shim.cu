@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,8 @@ struct Params {
     int* njacs; int* nw; int* nsolve;
     unsigned long long* work_counter;
     int flags;
+    int tol_const;
+    R tol100_tf;
 };
 
 struct DevBuf {
@@ -433,6 +436,11 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     CUDA_TRY(h->counter.ensure(sizeof(unsigned long long)));
     P.work_counter = (unsigned long long*)h->counter.ptr;
     P.flags = o->flags;
+    {   // tstop tolerance 100*eps(max(|t|,|tf|)) (integrator_utils.jl:277-286) is constant when |t0| <= |tf|
+        const R at0 = std::fabs(P.t0), atf = std::fabs(P.tf);
+        P.tol_const = !(at0 > atf) ? 1 : 0;
+        P.tol100_tf = (R)100 * (std::nextafter(atf, std::numeric_limits<R>::infinity()) - atf);
+    }
     CUDA_TRY(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned long long), stream));
 
     void* args[] = {&P};

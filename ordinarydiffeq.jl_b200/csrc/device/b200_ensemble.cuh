@@ -88,6 +88,8 @@ struct B200Params {
     int* njacs; int* nw; int* nsolve;
     unsigned long long* work_counter;
     int flags;
+    int tol_const;            // |t0| <= |tf|: the tstop tolerance 100*eps(max(|t|,|tf|)) is the constant below
+    real tol100_tf;           // 100*eps(|tf|)
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
@@ -263,10 +265,9 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     const int iter0 = T.naccept + T.nreject;
     const real dist = b200_abs(P.tf - T.t);
     const real at = b200_abs(T.t), atf = b200_abs(P.tf);
-    real tol100;
-    if (!(b200_abs(P.t0) > atf)) tol100 = (real)100 * b200_eps(atf);   // |t| <= |tf| on all of [t0, tf]: loop invariant
-    else tol100 = (real)100 * b200_eps(at > atf ? at : atf);
-    const real eps_t = b200_eps(T.t);
+    // tstop tolerance 100*eps(max(|t|,|tf|)): a launch constant whenever |t0| <= |tf|
+    const real tol100 = P.tol_const ? P.tol100_tf : (real)100 * b200_eps_finite(at > atf ? at : atf);
+    const real eps_t = b200_eps_finite(T.t);
     const real dtmin_t = eps_t > P.dtmin ? eps_t : P.dtmin;          // timedepentdtmin
     // ---- loopheader! ----
     if (iter0 > 0) {
@@ -286,20 +287,18 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     T.dt = b200_min_c(P.dtmax, T.dt);
     T.dt = b200_max_c(dtmin_t, T.dt);
     b200_modify_dt_for_tstops(T, dist, tol100);
-    // ---- check_error ----
-    int rc = B200_RC_SUCCESS;
-    if (b200_isnan(T.dt)) rc = B200_RC_DTNAN;
-    else if ((long long)iter0 + 1 > P.maxiters) rc = B200_RC_MAXITERS;
-    else if (b200_abs(T.dt) <= b200_abs(P.dtmin) && (!T.accept || T.t + T.dt < P.tf)) rc = B200_RC_DTLESSTHANMIN;
-    else if (!T.accept && b200_abs(T.dt) <= eps_t) rc = B200_RC_UNSTABLE;
-    else if (T.accept) {
-        bool bad = false;
+    // ---- check_error ---- (flat predicates; the else-if order of the reference decides the code)
+    const bool c_nan = b200_isnan(T.dt);
+    const bool c_max = ((long long)iter0 + 1 > P.maxiters);
+    const bool c_min = (b200_abs(T.dt) <= b200_abs(P.dtmin)) & (!T.accept | (T.t + T.dt < P.tf));
+    const bool c_uns = (!T.accept) & (b200_abs(T.dt) <= eps_t);
+    bool bad = false;
 #pragma unroll
-        for (int c = 0; c < B200_N; ++c) bad = bad || !b200_isfinite(T.u[c]);
-        if (bad) rc = B200_RC_UNSTABLE;
-    }
-    const bool ok = (rc == B200_RC_SUCCESS);
-    if (!ok) T.retcode = rc;
+    for (int c = 0; c < B200_N; ++c) bad = bad | !b200_isfinite(T.u[c]);
+    const bool c_inf = T.accept & bad;
+    const bool ok = !(c_nan | c_max | c_min | c_uns | c_inf);
+    if (!ok)
+        T.retcode = c_nan ? B200_RC_DTNAN : (c_max ? B200_RC_MAXITERS : (c_min ? B200_RC_DTLESSTHANMIN : B200_RC_UNSTABLE));
     // ---- perform_step! / handle_tstop_step! ----
     const bool skip = T.tstop_flag && b200_abs(T.dt) < eps_t;   // integrator_utils.jl:326-333 (eps(|t|) == eps(t))
     __syncwarp(amask);
@@ -318,17 +317,17 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     // stepsize_controller!(integrator, ::PIControllerCache, alg)
     const real qmax_eff = (T.naccept == 0) ? (real)10000 : qmax;
     real q;
-    if (T.EEst == (real)0) {
-        q = (real)1 / qmax_eff;
-    } else {
-        real q11 = b200_fastpower(T.EEst, beta1);
+    {
+        const real q11 = b200_fastpower(T.EEst, beta1);
         // q = q11 / fastpower(errold, beta2): the divisor was computed when errold was set, together
         // with RN(1/divisor), so the quotient is the 3-operation exact form (b200_div_const)
         q = b200_div_const(q11, T.fpe, T.rfpe);
-        T.q11 = q11;
         q = b200_div_const(q, gamma, (real)1 / gamma);
         const real lo = (real)1 / qmax_eff, hi = (real)1 / qmin;
         q = q < lo ? lo : (q > hi ? hi : q);       // clamp under @fastmath
+        const bool zero = (T.EEst == (real)0);     // iszero(EEst): q = inv(qmax), q11 untouched
+        q = zero ? lo : q;
+        T.q11 = zero ? T.q11 : q11;
     }
     T.accept = (T.EEst <= (real)1);
     if (T.accept) {
@@ -346,7 +345,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         }
         const real dtnew = T.dt / q;
         // calc_dt_propose!: eps at the NEW t
-        const real eps_n = b200_eps(T.t);
+        const real eps_n = b200_eps_finite(T.t);
         T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
         // handle_callbacks! -> savevalues!
         {

@@ -247,10 +247,8 @@ B200_D bool b200s_iterate(const B200Params& P, long long idx, B200STraj& T, bool
     const int iter0 = T.naccept + T.nreject;
     const real dist = b200_abs(P.tf - T.t);
     const real at = b200_abs(T.t), atf = b200_abs(P.tf);
-    real tol100;
-    if (!(b200_abs(P.t0) > atf)) tol100 = (real)100 * b200_eps(atf);
-    else tol100 = (real)100 * b200_eps(at > atf ? at : atf);
-    const real eps_t = b200_eps(T.t);
+    const real tol100 = P.tol_const ? P.tol100_tf : (real)100 * b200_eps_finite(at > atf ? at : atf);
+    const real eps_t = b200_eps_finite(T.t);
     const real dtmin_t = eps_t > P.dtmin ? eps_t : P.dtmin;
     bool ok = true;
     bool skip = false;
@@ -322,7 +320,7 @@ B200_D bool b200s_iterate(const B200Params& P, long long idx, B200STraj& T, bool
                 T.rfpe = (real)1 / T.fpe;
             }
             const real dtnew = T.dt / q;
-            const real eps_n = b200_eps(T.t);
+            const real eps_n = b200_eps_finite(T.t);
             T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
             want_dense = (T.next_save < T.t);       // an interior saveat point in (tprev, t)
         } else {
