@@ -59,6 +59,9 @@ extern "C" {
 /* opts.flags */
 #define B200ODE_FLAG_STATIC_SCHEDULE 1  /* one thread = one trajectory, no lane refill (A/B baseline) */
 
+/* extra_options of b200ode_compile that select a program variant */
+#define B200ODE_OPT_EVERYSTEP "-DB200_EVERYSTEP=1"  /* save_everystep = true: ragged per-step rows (b200ode_solve_everystep) */
+
 typedef struct b200ode_handle_s* b200ode_handle;     /* one per process per GPU */
 typedef struct b200ode_program_s* b200ode_program;   /* one per (alg, dtype, n, np, RHS source) */
 
@@ -185,6 +188,34 @@ int b200ode_solve(b200ode_handle h, b200ode_program prog, const B200Problem* pro
 /* device buffers in/out, asynchronous on `stream` (a cudaStream_t; NULL = default stream) */
 int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* prob,
                          const B200Opts* opts, B200DeviceResult* result, void* stream);
+
+/* ---- save_everystep = true (the reference's default when saveat is empty, solve.jl:138) -----------------
+ * Every accepted step's (t, u) is a row (_savevalues!, integrators/integrator_utils.jl:385-411), plus the
+ * save_start row, any saveat rows (interpolated, in time order) and the end point
+ * (solution_endpoint_match_cur_integrator!, :540-587).  Row counts differ per trajectory, so the output is
+ * ragged: trajectory i owns rows row_offsets[i] .. row_offsets[i+1]-1 of ts[] / us[][n] — its sol.t and sol.u.
+ * The program must have been compiled with B200ODE_OPT_EVERYSTEP in extra_options.
+ * Two passes over the same deterministic integration: count, exclusive scan, fill (no per-trajectory cap,
+ * no wasted HBM).  Dense `sol(t)` needs no stored k's: Tsit5/Vern7/Rosenbrock stages are recomputable from
+ * consecutive rows. */
+typedef struct {
+    int64_t total_rows;
+    int64_t* row_offsets;  /* [trajectories + 1]; malloc'ed by the call, release with b200ode_free */
+    double* ts;            /* [total_rows];       "  */
+    void* us;              /* real[total_rows][n]; "  */
+} B200Ragged;
+
+/* host buffers in; per-trajectory scalars into caller-allocated `result` (result.us / result.ts are ignored,
+ * result.nsaved[i] = rows of trajectory i); ragged rows into `out` */
+int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Problem* prob, const B200Opts* opts,
+                            B200Result* result, B200Ragged* out);
+
+/* device buffers, asynchronous on `stream`.  row_offsets == NULL: counting pass (result.nsaved only).
+ * Otherwise row_offsets is a device int64[trajectories + 1] exclusive scan of those counts, result.us is
+ * real[total_rows][n] and ts is real[total_rows] (real-typed on device). */
+int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* prob,
+                                   const B200Opts* opts, B200DeviceResult* result, const int64_t* row_offsets,
+                                   void* ts, void* stream);
 
 /* ---- ensemble reductions (the `reduction` of EnsembleProblem, on device) ---
  * out[c] = sum over trajectories of x(i, c) as double, deterministic order

@@ -139,6 +139,7 @@ template <typename R> struct Opts {
     const R* saveat; int nsaveat;
     bool save_start, save_end, save_end_user;
     int linsolve;      // 0: StaticWOperator inverse (n<=3), 1: partial-pivot LU
+    bool save_everystep = false;   // solve.jl:138 (default isempty(saveat)); ragged rows, see Out::row_offsets
 };
 
 // ODE_DEFAULT_NORM(u::StaticArray, t) = sqrt_fast(real(sum(abs2,u)) / max(length(u),1))
@@ -316,6 +317,8 @@ static R ode_initdt(const ProblemFns<R>& P, const R* u0, const R* p, R t, R dtma
 template <typename R> struct Out {
     R* u_final; R* t_final; R* us; int nslots;
     int *nsaved, *naccept, *nreject, *nf, *njacs, *nw, *nsolve, *retcode;
+    // ragged output (save_everystep): trajectory i owns rows row_offsets[i]..row_offsets[i+1]-1 of us/ts_rag
+    const long long* row_offsets = nullptr; R* ts_rag = nullptr;
 };
 
 // One trajectory: __init + solve! + postamble!
@@ -332,7 +335,13 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     int nsaved = 0, save_idx = 0;
     R last_saved_t = t0;
     auto emit = [&](R ts, const R* v) {
-        if (out.us && nsaved < out.nslots) {
+        if (out.row_offsets) {
+            if (out.us && nsaved < (int)(out.row_offsets[idx + 1] - out.row_offsets[idx])) {
+                const size_t row = (size_t)out.row_offsets[idx] + (size_t)nsaved;
+                for (int i = 0; i < n; ++i) out.us[row * n + i] = v[i];
+                out.ts_rag[row] = ts;
+            }
+        } else if (out.us && nsaved < out.nslots) {
             R* dst = out.us + ((size_t)idx * out.nslots + nsaved) * n;
             for (int i = 0; i < n; ++i) dst[i] = v[i];
         }
@@ -453,6 +462,10 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
                     emit(t, u);
                 }
             }
+            // save_everystep branch of _savevalues! (integrator_utils.jl:385-411)
+            if (o.save_everystep &&
+                (nsaved == 0 || ((t != last_saved_t || dt == (R)0) && (o.save_end || t != tf))))
+                emit(t, u);
         } else {
             nreject += 1;
         }
@@ -505,6 +518,8 @@ struct OracleArgs {
     // outputs
     void* u_final; void* t_final; void* us; int nslots;
     int *nsaved, *naccept, *nreject, *nf, *njacs, *nw, *nsolve, *retcode;
+    // save_everystep: row_offsets == NULL is the counting pass
+    int save_everystep; const long long* row_offsets; void* ts_rag;
 };
 
 template <typename R> static int run(const OracleArgs& a) {
@@ -524,7 +539,9 @@ template <typename R> static int run(const OracleArgs& a) {
     o.save_end = a.save_end != 0;
     o.save_end_user = a.save_end > 0;
     o.linsolve = a.linsolve;
+    o.save_everystep = a.save_everystep != 0;
     Out<R> out;
+    out.row_offsets = a.row_offsets; out.ts_rag = (R*)a.ts_rag;
     out.u_final = (R*)a.u_final; out.t_final = (R*)a.t_final; out.us = (R*)a.us; out.nslots = a.nslots;
     out.nsaved = a.nsaved; out.naccept = a.naccept; out.nreject = a.nreject; out.nf = a.nf;
     out.njacs = a.njacs; out.nw = a.nw; out.nsolve = a.nsolve; out.retcode = a.retcode;

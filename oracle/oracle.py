@@ -43,7 +43,8 @@ class OracleArgs(C.Structure):
                 ("linsolve", C.c_int), ("nthreads", C.c_int),
                 ("u_final", C.c_void_p), ("t_final", C.c_void_p), ("us", C.c_void_p), ("nslots", C.c_int),
                 ("nsaved", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p), ("nf", C.c_void_p),
-                ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p)]
+                ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p),
+                ("save_everystep", C.c_int), ("row_offsets", C.c_void_p), ("ts_rag", C.c_void_p)]
 
 
 _lib = None
@@ -117,8 +118,9 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
 
 def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
           abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
-          linsolve=0, nthreads=0):
-    """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host."""
+          linsolve=0, nthreads=0, save_everystep=False):
+    """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host.
+    save_everystep=True returns ragged rows (row_offsets, ts, us[total, n]) like lowlevel.solve_host_everystep."""
     L = lib()
     rdt = np.float32 if f32 else np.float64
     user = compile_user([rhs[0], jac[0] if jac else None, tgrad[0] if tgrad else None])
@@ -159,6 +161,24 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     a.nslots = nslots
     for k in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         setattr(a, k, out[k].ctypes.data)
+    if save_everystep:
+        # counting pass, exclusive scan, fill pass (the same two passes the GPU path makes)
+        a.save_everystep = 1; a.us = None; a.nslots = 0; a.row_offsets = None; a.ts_rag = None
+        rc = L.oracle_solve(C.byref(a))
+        if rc != 0:
+            raise RuntimeError("oracle_solve failed: %d" % rc)
+        offs = np.zeros((N + 1,), dtype=np.int64)
+        np.cumsum(out["nsaved"], out=offs[1:])
+        total = int(offs[-1])
+        us = np.zeros((max(total, 1), n), dtype=rdt)
+        ts = np.zeros((max(total, 1),), dtype=rdt)
+        a.us = us.ctypes.data; a.row_offsets = offs.ctypes.data; a.ts_rag = ts.ctypes.data
+        rc = L.oracle_solve(C.byref(a))
+        if rc != 0:
+            raise RuntimeError("oracle_solve failed: %d" % rc)
+        out["row_offsets"] = offs; out["us"] = us[:total]; out["ts"] = ts[:total].astype(np.float64)
+        out["t_final"] = out["t_final"].astype(np.float64)
+        return out
     rc = L.oracle_solve(C.byref(a))
     if rc != 0:
         raise RuntimeError("oracle_solve failed: %d" % rc)

@@ -63,13 +63,20 @@ class B200ProgramInfo(C.Structure):
                 ("grid", C.c_int32), ("cubin_bytes", C.c_int64), ("compile_ms", C.c_double)]
 
 
+class B200Ragged(C.Structure):
+    _fields_ = [("total_rows", C.c_int64), ("row_offsets", C.c_void_p), ("ts", C.c_void_p), ("us", C.c_void_p)]
+
+
+OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
+
+
 # every symbol include/b200ode.h declares (tests/test_abi.py checks the export list)
 EXPORTS = [
     "b200ode_create", "b200ode_destroy", "b200ode_last_error", "b200ode_version",
     "b200ode_compile", "b200ode_program_destroy", "b200ode_program_info",
     "b200ode_compile_only", "b200ode_free", "b200ode_nslots", "b200ode_solve", "b200ode_solve_device",
     "b200ode_reduce_sum_device", "b200ode_timeseries_meanvar_device", "b200ode_solve_meanvar", "b200ode_host_register", "b200ode_host_unregister",
-    "b200ode_measure_fma_peak",
+    "b200ode_measure_fma_peak", "b200ode_solve_everystep", "b200ode_solve_everystep_device",
 ]
 
 _lib = None
@@ -105,6 +112,10 @@ def lib():
     L.b200ode_reduce_sum_device.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp]
     L.b200ode_timeseries_meanvar_device.argtypes = [vp, i32, vp, i64, i32, i32, vp, vp, vp]
     L.b200ode_solve_meanvar.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(B200Result), vp, vp]
+    L.b200ode_solve_everystep.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(B200Result),
+                                          C.POINTER(B200Ragged)]
+    L.b200ode_solve_everystep_device.argtypes = [vp, vp, C.POINTER(B200DeviceProblem), C.POINTER(B200Opts),
+                                                 C.POINTER(B200DeviceResult), vp, vp, vp]
     L.b200ode_host_register.argtypes = [vp, C.c_size_t]
     L.b200ode_host_unregister.argtypes = [vp]
     L.b200ode_measure_fma_peak.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
@@ -179,6 +190,7 @@ class Program:
                  extra_options):
         self.handle = handle
         self.alg, self.dtype, self.n, self.np = alg, dtype, n, np_
+        self.everystep = bool(extra_options) and OPT_EVERYSTEP in extra_options
         self._p = C.c_void_p()
         check(lib().b200ode_compile(handle._h, C.byref(self._p), alg, dtype, n, np_, _b(rhs_src), _b(rhs_name),
                                     _b(jac_src), _b(jac_name), _b(tgrad_src), _b(tgrad_name), _b(extra_options)))

@@ -64,6 +64,8 @@ struct Params {
     int flags;
     int tol_const;
     R tol100_tf;
+    const long long* row_offsets;
+    R* ts_rag;
 };
 
 struct DevBuf {
@@ -94,7 +96,7 @@ struct b200ode_handle_s {
     DevBuf counter, dt0, saveat, scratch_t;
     std::vector<double> saveat_cached;   // grid currently resident in `saveat` ...
     int saveat_cached_dtype = -1;        // ... in this real type
-    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out;
+    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets;
 };
 
 struct b200ode_program_s {
@@ -105,6 +107,7 @@ struct b200ode_program_s {
     cudaKernel_t k_integrate = nullptr, k_initdt = nullptr;
     int sliced_g = 0;            // > 0: component-sliced kernel with this many warps per 32 trajectories
     int sliced_k = 1;            // groups of 32 trajectories per CTA
+    bool everystep = false;      // compiled with -DB200_EVERYSTEP=1 (ragged save_everystep output)
     size_t dyn_smem = 0;
     B200ProgramInfo info{};
 };
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(256) k_fma_peak(R* out, int iters, R a, R b) {
 
 template <typename R>
 int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
-                 B200DeviceResult* dr, cudaStream_t stream) {
+                 B200DeviceResult* dr, cudaStream_t stream, const long long* row_offsets = nullptr, void* ts_rag = nullptr) {
     const int n = prog->n, np = prog->np;
     const long long N = dp->trajectories;
     Params<R> P{};
@@ -408,7 +411,8 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     P.save_start = (o->save_start != 0) ? 1 : 0;
     P.save_end = (o->save_end < 0) ? 1 : (o->save_end ? 2 : 0);
     B200Problem hp{}; hp.t0 = dp->t0; hp.tf = dp->tf;
-    P.nslots = dr->us ? b200ode_nslots(&hp, o) : 0;
+    P.nslots = (dr->us && !prog->everystep) ? b200ode_nslots(&hp, o) : 0;
+    P.row_offsets = row_offsets; P.ts_rag = (R*)ts_rag;
     P.saveat = nullptr;
     if (P.nsaveat > 0) {
         // the grid travels as real[] in the handle's scratch; re-uploaded only when it changes
@@ -524,7 +528,7 @@ int b200ode_destroy(b200ode_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->counter, &h->dt0, &h->saveat, &h->scratch_t, &h->in_u0, &h->in_p, &h->out_uf, &h->out_tf,
-                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out})
+                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets})
         b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -568,6 +572,8 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
                          extra_options, prog->cubin, log, &ms, &prog->sliced_g);
     if (rc) { delete prog; return rc; }
+    prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
+    if (prog->everystep && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_everystep is not available in the sliced kernel"); }
     if (prog->sliced_g > 0) {
         prog->sliced_k = prog->sliced_g / 1000;
         prog->sliced_g = prog->sliced_g % 1000;
@@ -646,11 +652,132 @@ int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200Devic
     bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
     if (stiff && (!dr->njacs || !dr->nw || !dr->nsolve))
         return fail(B200ODE_EINVAL, "Rosenbrock programs need njacs,nw,nsolve result arrays");
+    if (prog->everystep) return fail(B200ODE_EINVAL, "program was compiled for save_everystep: use b200ode_solve_everystep[_device]");
     if (dp->trajectories == 0) return B200ODE_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream
     if (prog->dtype == B200ODE_F32) return launch_solve<float>(h, prog, dp, o, dr, s);
     return launch_solve<double>(h, prog, dp, o, dr, s);
+}
+
+int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
+                                   B200DeviceResult* dr, const int64_t* row_offsets, void* ts, void* stream) {
+    if (!h || !prog || !dp || !o || !dr) return fail(B200ODE_EINVAL, "NULL argument");
+    if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
+    if (!prog->everystep) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
+    int rc = check_problem(dp->trajectories, dp->u0, dp->p, prog->np, dp->t0, dp->tf, o);
+    if (rc) return rc;
+    if (!dr->u_final || !dr->t_final || !dr->naccept || !dr->nreject || !dr->nf || !dr->retcode || !dr->nsaved)
+        return fail(B200ODE_EINVAL, "device result arrays u_final,t_final,naccept,nreject,nf,retcode,nsaved are required");
+    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    if (stiff && (!dr->njacs || !dr->nw || !dr->nsolve))
+        return fail(B200ODE_EINVAL, "Rosenbrock programs need njacs,nw,nsolve result arrays");
+    if (row_offsets && (!dr->us || !ts)) return fail(B200ODE_EINVAL, "the fill pass needs result.us and ts");
+    if (dp->trajectories == 0) return B200ODE_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    static_assert(sizeof(long long) == sizeof(int64_t), "row offsets are 64-bit");
+    if (prog->dtype == B200ODE_F32) return launch_solve<float>(h, prog, dp, o, dr, s, (const long long*)row_offsets, ts);
+    return launch_solve<double>(h, prog, dp, o, dr, s, (const long long*)row_offsets, ts);
+}
+
+int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,
+                            B200Ragged* out) {
+    if (!h || !prog || !hp || !o || !res || !out) return fail(B200ODE_EINVAL, "NULL argument");
+    if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
+    if (!prog->everystep) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
+    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, hp->t0, hp->tf, o);
+    if (rc) return rc;
+    if (!res->u_final) return fail(B200ODE_EINVAL, "result.u_final is required");
+    out->total_rows = 0; out->row_offsets = nullptr; out->ts = nullptr; out->us = nullptr;
+    const long long N = hp->trajectories;
+    if (N == 0) return B200ODE_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = prog->n, np = prog->np;
+    const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    size_t u0_bytes = rs * n * (hp->u0_shared ? 1 : (size_t)N);
+    size_t p_bytes = rs * np * (hp->p_shared ? 1 : (size_t)N);
+    CUDA_TRY(h->in_u0.ensure(u0_bytes));
+    CUDA_TRY(cudaMemcpyAsync(h->in_u0.ptr, hp->u0, u0_bytes, cudaMemcpyHostToDevice, s));
+    if (np > 0) {
+        CUDA_TRY(h->in_p.ensure(p_bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->in_p.ptr, hp->p, p_bytes, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(h->out_uf.ensure(rs * n * (size_t)N));
+    CUDA_TRY(h->out_tf.ensure(rs * (size_t)N));
+    CUDA_TRY(h->out_i32.ensure(sizeof(int32_t) * 8 * (size_t)N));
+    CUDA_TRY(h->row_offsets.ensure(sizeof(int64_t) * ((size_t)N + 1)));
+    int32_t* i32 = (int32_t*)h->out_i32.ptr;
+    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    if (!stiff) CUDA_TRY(cudaMemsetAsync(i32 + 4 * N, 0, sizeof(int32_t) * 3 * (size_t)N, s));
+    B200DeviceProblem dp{};
+    dp.trajectories = N;
+    dp.u0 = h->in_u0.ptr; dp.u0_shared = hp->u0_shared; dp.u0_layout = B200ODE_LAYOUT_AOS;
+    dp.p = np > 0 ? h->in_p.ptr : nullptr; dp.p_shared = hp->p_shared; dp.p_layout = B200ODE_LAYOUT_AOS;
+    dp.t0 = hp->t0; dp.tf = hp->tf;
+    B200DeviceResult dr{};
+    dr.u_final = h->out_uf.ptr; dr.u_final_layout = B200ODE_LAYOUT_AOS;
+    dr.t_final = (double*)h->out_tf.ptr;
+    dr.nsaved = i32 + 0 * N; dr.naccept = i32 + 1 * N; dr.nreject = i32 + 2 * N; dr.nf = i32 + 3 * N;
+    dr.njacs = i32 + 4 * N; dr.nw = i32 + 5 * N; dr.nsolve = i32 + 6 * N; dr.retcode = i32 + 7 * N;
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    // pass 1: count the rows of every trajectory (the integration is deterministic, so pass 2 repeats it exactly)
+    rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, nullptr, nullptr, s);
+    if (rc) return rc;
+    std::vector<int32_t> counts((size_t)N);
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), i32, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * ((size_t)N + 1));
+    if (!offs) return fail(B200ODE_EINVAL, "out of host memory");
+    int64_t total = 0;
+    for (long long i = 0; i < N; ++i) { offs[i] = total; total += counts[(size_t)i]; }
+    offs[N] = total;
+    double* ts_host = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
+    void* us_host = malloc(rs * (size_t)n * (size_t)std::max<int64_t>(total, 1));
+    if (!ts_host || !us_host) { free(offs); free(ts_host); free(us_host); return fail(B200ODE_EINVAL, "out of host memory"); }
+    auto bail = [&](int code) { free(offs); free(ts_host); free(us_host); return code; };
+#define CUDA_TRY_BAIL(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(B200ODE_ECUDA, std::string(#x ": ") + cudaGetErrorString(e_))); } while (0)
+    CUDA_TRY_BAIL(h->out_us.ensure(rs * (size_t)n * (size_t)std::max<int64_t>(total, 1)));
+    CUDA_TRY_BAIL(h->scratch_t.ensure(rs * (size_t)std::max<int64_t>(total, 1)));
+    CUDA_TRY_BAIL(cudaMemcpyAsync(h->row_offsets.ptr, offs, sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+    // pass 2: fill
+    dr.us = h->out_us.ptr;
+    rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, (const int64_t*)h->row_offsets.ptr, h->scratch_t.ptr, s);
+    if (rc) return bail(rc);
+    CUDA_TRY_BAIL(cudaEventRecord(h->ev2, s));
+    CUDA_TRY_BAIL(cudaMemcpyAsync(us_host, h->out_us.ptr, rs * (size_t)n * (size_t)total, cudaMemcpyDeviceToHost, s));
+    std::vector<char> ts_raw;
+    if (rs == 8) CUDA_TRY_BAIL(cudaMemcpyAsync(ts_host, h->scratch_t.ptr, 8 * (size_t)total, cudaMemcpyDeviceToHost, s));
+    else { ts_raw.resize(4 * (size_t)total); CUDA_TRY_BAIL(cudaMemcpyAsync(ts_raw.data(), h->scratch_t.ptr, 4 * (size_t)total, cudaMemcpyDeviceToHost, s)); }
+    CUDA_TRY_BAIL(cudaMemcpyAsync(res->u_final, h->out_uf.ptr, rs * n * (size_t)N, cudaMemcpyDeviceToHost, s));
+    std::vector<char> tf_host;
+    if (res->t_final) {
+        tf_host.resize(rs * (size_t)N);
+        CUDA_TRY_BAIL(cudaMemcpyAsync(tf_host.data(), h->out_tf.ptr, rs * (size_t)N, cudaMemcpyDeviceToHost, s));
+    }
+    struct { int32_t* dst; int slot; } outs[] = {
+        {res->nsaved, 0}, {res->naccept, 1}, {res->nreject, 2}, {res->nf, 3},
+        {res->njacs, 4}, {res->nw, 5}, {res->nsolve, 6}, {res->retcode, 7}};
+    for (auto& oo : outs)
+        if (oo.dst) CUDA_TRY_BAIL(cudaMemcpyAsync(oo.dst, i32 + (size_t)oo.slot * N, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY_BAIL(cudaEventRecord(h->ev3, s));
+    CUDA_TRY_BAIL(cudaStreamSynchronize(s));
+#undef CUDA_TRY_BAIL
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return bail(fail(B200ODE_ECUDA, std::string("kernel failure: ") + cudaGetErrorString(le)));
+    if (rs == 4) for (int64_t i = 0; i < total; ++i) ts_host[i] = (double)((const float*)ts_raw.data())[i];
+    if (res->t_final) {
+        if (rs == 8) memcpy(res->t_final, tf_host.data(), 8 * (size_t)N);
+        else for (long long i = 0; i < N; ++i) res->t_final[i] = (double)((const float*)tf_host.data())[i];
+    }
+    float kms = 0, tms = 0;
+    cudaEventElapsedTime(&kms, h->ev1, h->ev2);
+    cudaEventElapsedTime(&tms, h->ev0, h->ev3);
+    res->kernel_ms = kms; res->total_ms = tms;
+    out->total_rows = total; out->row_offsets = offs; out->ts = ts_host; out->us = us_host;
+    return B200ODE_OK;
 }
 
 static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,

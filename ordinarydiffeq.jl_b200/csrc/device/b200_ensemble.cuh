@@ -90,9 +90,20 @@ struct B200Params {
     int flags;
     int tol_const;            // |t0| <= |tf|: the tstop tolerance 100*eps(max(|t|,|tf|)) is the constant below
     real tol100_tf;           // 100*eps(|tf|)
+    // save_everystep programs (-DB200_EVERYSTEP=1) only: ragged per-step output.  Trajectory i owns rows
+    // row_offsets[i] .. row_offsets[i+1]-1 of us[.][n] / ts_rag[.]; NULL = counting pass (nsaved[] only).
+    const long long* row_offsets;
+    real* ts_rag;
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
+
+#ifndef B200_EVERYSTEP
+#define B200_EVERYSTEP 0      // 1: save_everystep = true (integrator_utils.jl:385-411), ragged rows
+#endif
+#if B200_EVERYSTEP && B200_SLICED
+#error "save_everystep is not available in the component-sliced kernel"
+#endif
 
 #ifndef B200_BLOCK
 #define B200_BLOCK 128
@@ -195,17 +206,32 @@ struct B200Traj {
     int retcode;
     bool accept, tstop_flag;
     real* row;                  // next row of us[idx][.][:] (running pointer: no 64-bit index arithmetic per row)
+#if B200_EVERYSTEP
+    real* trow;                 // next entry of ts_rag
+    real last_t;                // sol.t[end]
+    int cap;                    // rows this trajectory owns (0 in the counting pass)
+#endif
 #if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
     int njacs, nw, nsolve;
 #endif
 };
 
-B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, const real* v) {
+B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, const real* v) {
+#if B200_EVERYSTEP
+    if (T.nsaved < T.cap) {
+#pragma unroll
+        for (int c = 0; c < B200_N; ++c) T.row[c] = v[c];
+        T.row += B200_N;
+        *T.trow++ = ts;
+    }
+    T.last_t = ts;
+#else
     if (T.nsaved < P.nslots) {              // nslots == 0: no time series requested
 #pragma unroll
         for (int c = 0; c < B200_N; ++c) T.row[c] = v[c];
         T.row += B200_N;
     }
+#endif
     T.nsaved += 1;
 }
 
@@ -233,8 +259,18 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     T.njacs = 0; T.nw = 0; T.nsolve = 0;
 #endif
     T.nsaved = 0; T.save_idx = 0;
+#if B200_EVERYSTEP
+    T.cap = 0; T.row = nullptr; T.trow = nullptr; T.last_t = P.t0;
+    if (P.row_offsets != nullptr) {
+        const long long o = P.row_offsets[idx];
+        T.cap = (int)(P.row_offsets[idx + 1] - o);
+        T.row = P.us + (size_t)o * B200_N;
+        T.trow = P.ts_rag + o;
+    }
+#else
     T.row = P.us + (size_t)idx * (size_t)P.nslots * B200_N;
-    if (P.save_start) b200_emit(P, idx, T, T.u);      // solve.jl:809-824
+#endif
+    if (P.save_start) b200_emit(P, idx, T, T.t, T.u);      // solve.jl:809-824
     T.st.init(T.u, T.p, T.t, T.nf);                   // initialize!(integrator, cache)
     if (P.dt_user == (real)0) { T.dt = P.dt0[idx]; T.nf += 2; }   // auto_dt_reset!: nf += 2
     else T.dt = P.dt_user;
@@ -305,7 +341,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     if (ok && !skip) {
 #if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
         T.EEst = T.st.attempt(T.uprev, T.u, T.p, T.t, T.dt, P.reltol, P.abstol, T.nf, T.njacs, T.nw, T.nsolve,
-                              P.nslots > 0 && P.nsaveat > 0);
+                              (B200_EVERYSTEP || P.nslots > 0) && P.nsaveat > 0);
 #else
         T.EEst = T.st.attempt(T.uprev, T.u, T.p, T.t, T.dt, P.reltol, P.abstol, T.nf);
 #endif
@@ -362,12 +398,17 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                     const real th = (curt - T.tprev) / T.dt;
                     real out[B200_N];
                     T.st.interp(th, T.dt, T.uprev, T.u, out);
-                    b200_emit(P, idx, T, out);
+                    b200_emit(P, idx, T, curt, out);
                 } else {
                     if (curt == P.tf && !P.save_end) continue;   // skip_saveat_at_tspan_end
-                    b200_emit(P, idx, T, T.u);
+                    b200_emit(P, idx, T, T.t, T.u);
                 }
             }
+#if B200_EVERYSTEP
+            // save_everystep && (isempty(sol.t) || (t !== sol.t[end] || iszero(dt)) && (save_end || t !== tspan[2]))
+            if ((T.nsaved == 0 || ((T.t != T.last_t || T.dt == (real)0) && (P.save_end || T.t != P.tf))))
+                b200_emit(P, idx, T, T.t, T.u);
+#endif
         }
     } else {
         T.nreject += 1;
@@ -396,13 +437,19 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
         bool emit;
         if (T.nsaved == 0) emit = true;
         else {
+#if B200_EVERYSTEP
+            const real last_t = T.last_t;
+#else
             const real last_t = (T.save_idx > 0) ? P.saveat[T.save_idx - 1] : P.t0;
+#endif
             emit = (last_t != T.t) && (P.save_end == 2 || T.t == P.tf || P.nsaveat == 0);
         }
-        if (emit) b200_emit(P, idx, T, T.u);
+        if (emit) b200_emit(P, idx, T, T.t, T.u);
     }
+#if !B200_EVERYSTEP
     // a trajectory that failed leaves its remaining rows zero (the host does not pre-clear `us`)
     if (P.nslots > 0 && T.nsaved < P.nslots) b200_zero_rows(P.us, idx, T.nsaved, P.nslots);
+#endif
 #pragma unroll
     for (int c = 0; c < B200_N; ++c) P.u_final[idx * P.uf_ts + c * P.uf_cs] = T.u[c];
     P.t_final[idx] = T.t;

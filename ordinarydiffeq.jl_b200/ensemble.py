@@ -191,7 +191,11 @@ class _LazySolutions:
         r = self.res
         if i < 0:
             i += len(self)
-        if self.has_grid:
+        if "row_offsets" in r:
+            # save_everystep = true: this trajectory's slice of the ragged rows is its sol.t / sol.u
+            a, b = int(r["row_offsets"][i]), int(r["row_offsets"][i + 1])
+            t, u = r["ts"][a:b], r["us"][a:b]
+        elif self.has_grid:
             k = int(r["nsaved"][i])
             t = np.array(r["ts"][:k])
             u = r["us"][i, :k]
@@ -243,13 +247,14 @@ def _handle(device):
     return _handles[device]
 
 
-def get_program(handle, alg, fn, n, np_, f32):
+def get_program(handle, alg, fn, n, np_, f32, everystep=False):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
-    key = (handle.device, alg.alg_id, f32, n, np_, rhs, jac, tg)
+    key = (handle.device, alg.alg_id, f32, n, np_, rhs, jac, tg, everystep)
     if key not in _program_cache:
         _program_cache[key] = handle.compile(alg.alg_id, _lib.F32 if f32 else _lib.F64, n, np_, rhs[0], rhs[1],
                                              jac[0] if jac else None, jac[1] if jac else None,
-                                             tg[0] if tg else None, tg[1] if tg else None)
+                                             tg[0] if tg else None, tg[1] if tg else None,
+                                             extra_options=_lib.OPT_EVERYSTEP if everystep else None)
     return _program_cache[key]
 
 
@@ -292,10 +297,8 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     if "trajectories" not in kw:
         raise TypeError("trajectories is required")
     has_saveat = kw.get("saveat", None) is not None and not (hasattr(kw["saveat"], "__len__") and len(kw["saveat"]) == 0)
-    if kw.get("save_everystep", not has_saveat):
-        # the reference's default is save_everystep = isempty(saveat) (solve.jl:138): ragged per-step output
-        raise NotImplementedError("save_everystep=true (ragged per-step output) is not on this path; "
-                                  "pass saveat=... or save_everystep=False")
+    # the reference's default is save_everystep = isempty(saveat) (solve.jl:138): ragged per-step output
+    everystep = bool(kw.get("save_everystep", not has_saveat))
     if not kw.get("adaptive", True):
         raise NotImplementedError("adaptive=false is not on this path")
     if kw.get("dense", False):
@@ -311,7 +314,16 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     np_ = 0 if prob.p is None else int(np.asarray(prob.p).shape[-1])
     grid = ranges.saveat_grid(kw.get("saveat", None), prob.tspan)
     handle = _handle(ensemblealg.device)
-    program = get_program(handle, alg, prob.f, n, np_, f32)
+    program = get_program(handle, alg, prob.f, n, np_, f32, everystep)
+
+    def run(u0, p, ntraj, flags=0):
+        common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
+                      dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
+                      saveat=grid if grid else None, save_start=kw.get("save_start"), save_end=kw.get("save_end"),
+                      flags=flags)
+        if everystep:
+            return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
+        return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
 
     t_start = time.perf_counter()
     reduction, output_func = eprob.reduction, eprob.output_func
@@ -321,11 +333,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     for b0 in range(0, N, max(batch_size, 1)):
         I = np.arange(b0 + 1, min(b0 + batch_size, N) + 1)
         u0, p = _harvest(eprob, I)
-        res = lowlevel.solve_host(program, u0, p, prob.tspan, trajectories=len(I), reltol=kw.get("reltol"),
-                                  abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"),
-                                  maxiters=kw.get("maxiters"), saveat=grid if grid else None,
-                                  save_start=kw.get("save_start"), save_end=kw.get("save_end"),
-                                  flags=kw.get("flags", 0))
+        res = run(u0, p, len(I), kw.get("flags", 0))
         all_arrays.append(res)
         ss = kw.get("save_start"); se = kw.get("save_end")
         mk = lambda r, u0_: _LazySolutions(r, prob.tspan[0], alg, bool(grid), np.asarray(u0_),
@@ -342,11 +350,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
                     # re-solve this trajectory alone with repeat+1 (the driver's rerun loop)
                     repeat += 1
                     u0r, pr = _harvest(eprob, [int(i)], repeat)
-                    r1 = lowlevel.solve_host(program, u0r, pr, prob.tspan, trajectories=1, reltol=kw.get("reltol"),
-                                             abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
-                                             dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
-                                             saveat=grid if grid else None, save_start=kw.get("save_start"),
-                                             save_end=kw.get("save_end"))
+                    r1 = run(u0r, pr, 1)
                     out, rerun = output_func(mk(r1, u0r)[0], EnsembleContext(int(i), repeat))
                 batch.append(out)
         if reduction is None:

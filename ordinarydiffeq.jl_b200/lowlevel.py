@@ -89,6 +89,70 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     return out
 
 
+def solve_host_everystep(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None,
+                         dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None, flags=0):
+    """save_everystep = true (b200ode_solve_everystep): returns the per-trajectory scalars plus the ragged
+    rows — row_offsets[N+1], ts[total], us[total, n]; trajectory i's sol.t / sol.u are
+    ts[row_offsets[i]:row_offsets[i+1]] and the same slice of us."""
+    L = _lib.lib()
+    if not program.everystep:
+        raise ValueError("program was not compiled with OPT_EVERYSTEP")
+    rdt = _np_real(program.dtype)
+    n, npar = program.n, program.np
+    u0 = np.ascontiguousarray(u0, dtype=rdt)
+    u0_shared = (u0.ndim == 1)
+    p_arr = None if p is None else np.ascontiguousarray(p, dtype=rdt)
+    p_shared = True if p_arr is None else (p_arr.ndim == 1)
+    if trajectories is None:
+        if not u0_shared:
+            trajectories = u0.shape[0]
+        elif p_arr is not None and not p_shared:
+            trajectories = p_arr.shape[0]
+        else:
+            raise ValueError("trajectories must be given when both u0 and p are shared")
+    N = int(trajectories)
+    if u0.shape[-1] != n or (not u0_shared and u0.shape[0] != N):
+        raise ValueError("u0 has shape %s, expected (%d, %d) or (%d,)" % (u0.shape, N, n, n))
+    if npar > 0 and (p_arr is None or p_arr.shape[-1] != npar or (not p_shared and p_arr.shape[0] != N)):
+        raise ValueError("p has wrong shape for np=%d" % npar)
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags)
+    prob = _lib.B200Problem()
+    prob.trajectories = N
+    prob.u0 = u0.ctypes.data; prob.u0_shared = int(u0_shared)
+    prob.p = p_arr.ctypes.data if p_arr is not None else None; prob.p_shared = int(p_shared)
+    prob.t0, prob.tf = float(tspan[0]), float(tspan[1])
+    out = {"u_final": np.empty((N, n), dtype=rdt), "t_final": np.empty((N,), dtype=np.float64)}
+    res = _lib.B200Result()
+    res.u_final = out["u_final"].ctypes.data
+    res.t_final = out["t_final"].ctypes.data
+    for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
+        out[name] = np.empty((N,), dtype=np.int32)
+        setattr(res, name, out[name].ctypes.data)
+    rag = _lib.B200Ragged()
+    _lib.check(L.b200ode_solve_everystep(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res),
+                                         C.byref(rag)))
+    try:
+        total = int(rag.total_rows)
+        if N > 0:
+            out["row_offsets"] = np.ctypeslib.as_array(C.cast(rag.row_offsets, C.POINTER(C.c_int64)), (N + 1,)).copy()
+        else:
+            out["row_offsets"] = np.zeros((1,), dtype=np.int64)
+        if total > 0:
+            out["ts"] = np.ctypeslib.as_array(C.cast(rag.ts, C.POINTER(C.c_double)), (total,)).copy()
+            ct = C.c_float if rdt == np.float32 else C.c_double
+            out["us"] = np.ctypeslib.as_array(C.cast(rag.us, C.POINTER(ct)), (total * n,)).reshape(total, n).copy()
+        else:
+            out["ts"] = np.zeros((0,), dtype=np.float64)
+            out["us"] = np.zeros((0, n), dtype=rdt)
+    finally:
+        for ptr in (rag.row_offsets, rag.ts, rag.us):
+            if ptr:
+                L.b200ode_free(C.c_void_p(ptr))
+    out["kernel_ms"] = res.kernel_ms
+    out["total_ms"] = res.total_ms
+    return out
+
+
 def solve_host_meanvar(program, u0, p, tspan, saveat, trajectories=None, want_var=True, **kw):
     """EnsembleAnalysis.timeseries_steps_meanvar without moving the trajectories to the host
     (b200ode_solve_meanvar): returns dict with ts, mean[nslots][n], var[nslots][n] and the

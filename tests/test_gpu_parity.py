@@ -378,3 +378,97 @@ def test_sliced_kernel_variant_is_bit_exact(pkg, handle, oracle):
     g = pkg.lowlevel.solve_host(prog3, U0, p, (0.0, 5.0), saveat=[1.0, 2.5], maxiters=60)
     o = oracle.solve(oracle.ALG_VERN7, (s3, n3), U0, p, (0.0, 5.0), 3, 3, saveat=[1.0, 2.5], maxiters=60)
     assert_same_result(g, o)
+
+
+# ---- save_everystep = true: ragged per-step rows ---------------------------
+def _everystep_prog(pkg, handle, alg, f32, problem):
+    pl = pkg.problems_library
+    dt = pkg.F32 if f32 else pkg.F64
+    opt = pkg._lib.OPT_EVERYSTEP
+    if problem == "lorenz":
+        s, n = pl.lorenz_source(f32)
+        return handle.compile(alg, dt, 3, 3, s, n, extra_options=opt)
+    if problem == "robertson":
+        r, j, tg = pl.robertson_sources(f32)
+        return handle.compile(alg, dt, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1], extra_options=opt)
+    s, n = pl.pleiades_source(f32)
+    return handle.compile(alg, dt, 28, 0, s, n, extra_options=opt)
+
+
+def _assert_same_ragged(g, o):
+    assert_same_result(g, dict(o, us=None))
+    assert np.array_equal(g["row_offsets"], o["row_offsets"])
+    assert np.array_equal(g["ts"], o["ts"])
+    assert np.array_equal(bits(g["us"]), bits(o["us"]))
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_everystep_lorenz_tsit5(pkg, handle, oracle, f32):
+    N = 3000
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N, f32=f32)
+    prog = _everystep_prog(pkg, handle, pkg.ALG_TSIT5, f32, "lorenz")
+    for kw in ({}, {"save_start": False}, {"save_end": False}, {"saveat": [0.25, 1.0, 2.0], "save_end": False},
+               {"saveat": [0.5, 2.0]}, {"maxiters": 20}):
+        g = pkg.lowlevel.solve_host_everystep(prog, U0, p, (0.0, 2.0), **kw)
+        o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(f32), U0, p, (0.0, 2.0), 3, 3, f32=f32, save_everystep=True, **kw)
+        _assert_same_ragged(g, o)
+        if not kw:
+            # sol.t = [t0, every accepted step]; the last row is the end point
+            assert np.array_equal(g["nsaved"], g["naccept"] + 1)
+            last = g["row_offsets"][1:] - 1
+            assert (g["ts"][last] == 2.0).all() and (g["ts"][g["row_offsets"][:-1]] == 0.0).all()
+            assert np.array_equal(bits(g["us"][last]), bits(g["u_final"]))
+        if "maxiters" in kw:
+            assert (g["retcode"] == 2).all()
+
+
+def test_everystep_stiff_and_vern7(pkg, handle, oracle):
+    pl = pkg.problems_library
+    r, j, tg = pl.robertson_sources()
+    p = pl.robertson_params(1024)
+    for alg, oalg in ((pkg.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK23), (pkg.ALG_RODAS5P, oracle.ALG_RODAS5P)):
+        prog = _everystep_prog(pkg, handle, alg, False, "robertson")
+        for kw in ({}, {"saveat": [1.0, 10.0, 50.0]}):
+            g = pkg.lowlevel.solve_host_everystep(prog, U0, p, (0.0, 100.0), reltol=1e-6, abstol=1e-8, **kw)
+            o = oracle.solve(oalg, r, U0, p, (0.0, 100.0), 3, 3, jac=j, tgrad=tg, reltol=1e-6, abstol=1e-8,
+                             save_everystep=True, **kw)
+            _assert_same_ragged(g, o)
+    u0 = pl.pleiades_u0(256)
+    prog = _everystep_prog(pkg, handle, pkg.ALG_VERN7, False, "pleiades")
+    g = pkg.lowlevel.solve_host_everystep(prog, u0, None, (0.0, 1.0), reltol=1e-6, abstol=1e-8, saveat=[0.3, 0.6])
+    o = oracle.solve(oracle.ALG_VERN7, pl.pleiades_source(), u0, None, (0.0, 1.0), 28, 0, reltol=1e-6, abstol=1e-8,
+                     saveat=[0.3, 0.6], save_everystep=True)
+    _assert_same_ragged(g, o)
+
+
+def test_everystep_program_is_refused_by_rectangular_entry_points(pkg, handle, progs):
+    pl = pkg.problems_library
+    p = pl.lorenz_params(64)
+    prog = _everystep_prog(pkg, handle, pkg.ALG_TSIT5, False, "lorenz")
+    with pytest.raises(pkg.B200Error):
+        pkg.lowlevel.solve_host(prog, U0, p, (0.0, 1.0))
+    with pytest.raises(ValueError):
+        pkg.lowlevel.solve_host_everystep(progs(pkg.ALG_TSIT5, False, "lorenz"), U0, p, (0.0, 1.0))
+
+
+def test_high_level_default_is_save_everystep(pkg, oracle):
+    """solve(EnsembleProblem, Tsit5(), EnsembleB200(); trajectories) with no saveat: the reference's default
+    save_everystep = isempty(saveat) (solve.jl:138) — every trajectory's sol.t / sol.u are its accepted steps."""
+    P = pkg
+    pl = P.problems_library
+    N = 300
+    table = pl.lorenz_params(N)
+    prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (0.0, 2.0), table[0])
+    ep = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table))
+    s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N)
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (0.0, 2.0), 3, 3, save_everystep=True)
+    for i in (0, 123, N - 1):
+        a, b = o["row_offsets"][i], o["row_offsets"][i + 1]
+        assert np.array_equal(s[i].t, o["ts"][a:b]) and s[i].t[0] == 0.0 and s[i].t[-1] == 2.0
+        assert np.array_equal(bits(np.ascontiguousarray(s[i].u)), bits(o["us"][a:b]))
+        assert len(s[i]) == s[i].stats.naccept + 1
+    # output_func sees the per-step solution
+    ep2 = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table), output_func=lambda sol, ctx: (len(sol.t), False))
+    s2 = P.solve(ep2, P.Tsit5(), P.EnsembleB200(), trajectories=N)
+    assert list(s2.u) == list(o["nsaved"])

@@ -66,8 +66,8 @@ def test_solve_keyword_contract(pkg):
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, callback=None)
     with pytest.raises(TypeError):
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), saveat=0.1)        # trajectories missing
-    with pytest.raises(NotImplementedError):                        # default save_everystep=true is ragged
-        P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4)
+    with pytest.raises(NotImplementedError):                        # dense sol(t) objects are not on this path
+        P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, dense=True)
     with pytest.raises(NotImplementedError):
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, adaptive=False)
 

@@ -303,3 +303,41 @@ def _run_pin_case(pl, case):
         return oracle.solve(alg, pl.pleiades_source(f32), pl.pleiades_u0(N, f32=f32), None, (0.0, 3.0), 28, 0, f32=f32,
                             **case["kw"])
     raise ValueError(case["problem"])
+
+
+# ---- save_everystep -----------------------------------------------------
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "ros23", "rodas5p"])
+def test_everystep_rows_and_saveat_symdiff(alg):
+    # test/InterfaceI/ode_saveat_tests.jl:52-59,117-124: with save_everystep = true, adding
+    # saveat = [0.125, 0.6, 0.61, 0.8] inserts exactly those times into sol.t and nothing else changes
+    rhs = linear_source()
+    jac, tg = linear_jac_sources()
+    a = {"tsit5": oracle.ALG_TSIT5, "vern7": oracle.ALG_VERN7, "ros23": oracle.ALG_ROSENBROCK23,
+         "rodas5p": oracle.ALG_RODAS5P}[alg]
+    kw = dict(jac=jac, tgrad=tg) if alg in ("ros23", "rodas5p") else {}
+    base = oracle.solve(a, rhs, np.array([[0.5]]), None, (0.0, 1.0), 1, 0, dt=0.25, save_everystep=True, **kw)
+    grid = [0.125, 0.6, 0.61, 0.8]
+    more = oracle.solve(a, rhs, np.array([[0.5]]), None, (0.0, 1.0), 1, 0, dt=0.25, save_everystep=True, saveat=grid, **kw)
+    assert base["retcode"][0] == 1 and more["retcode"][0] == 1
+    assert sorted(set(base["ts"]) ^ set(more["ts"])) == grid
+    assert list(more["ts"]) == sorted(more["ts"])
+    # sol.t = [t0, accepted steps...]: one row per accepted step plus the start, ending at tf
+    assert base["nsaved"][0] == base["naccept"][0] + 1
+    assert base["ts"][0] == 0.0 and base["ts"][-1] == 1.0
+    assert np.array_equal(base["us"][-1], base["u_final"][0])
+    # the per-step rows do not depend on whether saveat rows are interleaved
+    keep = np.isin(more["ts"], base["ts"])
+    assert np.array_equal(more["us"][keep], base["us"])
+    # ode_saveat_tests.jl:11-14: save_everystep = false keeps only the end points
+    ends = oracle.solve(a, rhs, np.array([[0.5]]), None, (0.0, 1.0), 1, 0, dt=0.25, **kw)
+    assert np.array_equal(ends["u_final"], base["u_final"]) and ends["naccept"][0] == base["naccept"][0]
+
+
+def test_everystep_save_end_false_and_failure():
+    rhs = linear_source()
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([[0.5]]), None, (0.0, 1.0), 1, 0, save_everystep=True, save_end=False)
+    assert o["ts"][-1] < 1.0 and o["nsaved"][0] == o["naccept"][0]          # the row at tspan[2] is skipped
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([[0.5]]), None, (0.0, 1.0), 1, 0, save_everystep=True, save_start=False)
+    assert o["ts"][0] > 0.0 and o["ts"][-1] == 1.0
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([[0.5]]), None, (0.0, 1.0), 1, 0, save_everystep=True, maxiters=3)
+    assert o["retcode"][0] == 2 and o["nsaved"][0] == 1 + o["naccept"][0] and o["ts"][-1] == o["t_final"][0] < 1.0
