@@ -212,10 +212,27 @@ int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Pr
 
 /* device buffers, asynchronous on `stream`.  row_offsets == NULL: counting pass (result.nsaved only).
  * Otherwise row_offsets is a device int64[trajectories + 1] exclusive scan of those counts, result.us is
- * real[total_rows][n] and ts is real[total_rows] (real-typed on device). */
+ * real[total_rows][n], ts and dts are real[total_rows] (real-typed on device); dts[r] is the step size the
+ * stages of the step that ends at row r were computed with (what b200ode_dense_eval_device recomputes from). */
 int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* prob,
                                    const B200Opts* opts, B200DeviceResult* result, const int64_t* row_offsets,
-                                   void* ts, void* stream);
+                                   void* ts, void* dts, void* stream);
+
+/* ---- dense output: sol(tq) for every trajectory, post hoc ----------------------------------------------
+ * Replaces ODESolution's interpolation object — ode_interpolation(tvals, id, idxs, deriv, p)
+ * (lib/OrdinaryDiffEqCore/src/dense/generic_dense.jl:833-867; interval rule ts[i-] < t <= ts[i+], extrapolating
+ * from the first/last interval outside [t0, t_end]) — for idxs = nothing, deriv = Val{0}, continuity = :left.
+ * The reference stores every step's stage derivatives (sol.k, integrator_utils.jl:455-473); this path stores
+ * one extra scalar per row (dts) and recomputes the stages, bit-identically, inside the evaluation kernel.
+ * tq: real[nq] device array, ascending; out: real[trajectories][nq][n] device array. */
+int b200ode_dense_eval_device(b200ode_handle h, b200ode_program prog, int64_t trajectories, const void* p, int32_t p_shared,
+                              int32_t p_layout, const int64_t* row_offsets, const void* ts, const void* dts,
+                              const void* us, const void* tq, int32_t nq, void* out, const B200Opts* opts, void* stream);
+
+/* host buffers: integrate with save_everystep (no saveat), evaluate sol_i(tq[j]) on the device and return only
+ * out = real[trajectories][nq][n] plus the per-trajectory scalars. */
+int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Problem* prob, const B200Opts* opts,
+                        const double* tq, int32_t nq, void* out, B200Result* result);
 
 /* ---- ensemble reductions (the `reduction` of EnsembleProblem, on device) ---
  * out[c] = sum over trajectories of x(i, c) as double, deterministic order

@@ -319,6 +319,13 @@ template <typename R> struct Out {
     int *nsaved, *naccept, *nreject, *nf, *njacs, *nw, *nsolve, *retcode;
     // ragged output (save_everystep): trajectory i owns rows row_offsets[i]..row_offsets[i+1]-1 of us/ts_rag
     const long long* row_offsets = nullptr; R* ts_rag = nullptr;
+    // dense = true: every saved row also keeps the stepper cache (its k array), the way sol.k does
+    // (integrator_utils.jl:455-473); points to a DenseSink<R, Alg> owned by dense_one
+    void* dense_sink = nullptr;
+};
+
+template <typename R, typename Alg> struct DenseSink {
+    std::vector<R> ts; std::vector<R> us; std::vector<Alg> ks;
 };
 
 // One trajectory: __init + solve! + postamble!
@@ -335,6 +342,12 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     int nsaved = 0, save_idx = 0;
     R last_saved_t = t0;
     auto emit = [&](R ts, const R* v) {
+        if (out.dense_sink) {
+            auto* sink = (DenseSink<R, Alg>*)out.dense_sink;
+            sink->ts.push_back(ts);
+            for (int i = 0; i < n; ++i) sink->us.push_back(v[i]);
+            sink->ks.push_back(cache);
+        }
         if (out.row_offsets) {
             if (out.us && nsaved < (int)(out.row_offsets[idx + 1] - out.row_offsets[idx])) {
                 const size_t row = (size_t)out.row_offsets[idx] + (size_t)nsaved;
@@ -418,7 +431,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
         if (next_step_tstop && std::fabs(dt) < jl_eps(std::fabs(t))) {
             accept_step = true;
         } else {
-            EEst = cache.perform_step(uprev, u, p, t, dt, o, stats, o.nsaveat > 0);
+            EEst = cache.perform_step(uprev, u, p, t, dt, o, stats, o.nsaveat > 0 || out.dense_sink != nullptr);   // calck (solve.jl:147-148)
         }
         // ---- loopfooter! (:597-677)
         R ttmp = t + dt;
@@ -488,8 +501,13 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
 }
 
 template <typename R, typename Alg>
+static void dense_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R tf, const Opts<R>& o, long long idx,
+                      const Out<R>& out_in, const R* tq, int M, R* dense_out);
+
+template <typename R, typename Alg>
 static void solve_batch(const ProblemFns<R>& P, long long N, const R* u0, int u0_shared, const R* p, int p_shared, R t0,
-                        R tf, const Opts<R>& o, const Out<R>& out, int nthreads) {
+                        R tf, const Opts<R>& o, const Out<R>& out, int nthreads, const R* tq = nullptr, int M = 0,
+                        R* dense_out = nullptr) {
     // the structural analogue of EnsembleThreads' Threads.@threads over trajectories
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -498,7 +516,39 @@ static void solve_batch(const ProblemFns<R>& P, long long N, const R* u0, int u0
     for (long long i = 0; i < N; ++i) {
         const R* ui = u0_shared ? u0 : u0 + (size_t)i * P.n;
         const R* pi = p_shared ? p : p + (size_t)i * P.np;
-        solve_one<R, Alg>(P, ui, pi, t0, tf, o, i, out);
+        if (dense_out) dense_one<R, Alg>(P, ui, pi, t0, tf, o, i, out, tq, M, dense_out);
+        else solve_one<R, Alg>(P, ui, pi, t0, tf, o, i, out);
+    }
+}
+
+// sol(tq) post hoc — ode_interpolation (dense/generic_dense.jl:833-867) over the stored (ts, us, ks):
+// i+ = min(lastindex, max(previous i+, searchsortedfirst(ts, t))) starting from i+ = 2, i- = i+ - 1,
+// dt = ts[i+] - ts[i-], Θ = (t - ts[i-]) / dt, then _ode_addsteps!(ks[i+], ts[i-], u[i-], u[i+], dt, ...)
+// (lazy stages only: the stored k already holds the step's own stages) and ode_interpolant.
+template <typename R, typename Alg>
+static void dense_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R tf, const Opts<R>& o, long long idx,
+                      const Out<R>& out_in, const R* tq, int M, R* dense_out) {
+    DenseSink<R, Alg> sink;
+    Out<R> out = out_in;
+    out.dense_sink = &sink; out.us = nullptr; out.row_offsets = nullptr;
+    solve_one<R, Alg>(P, u0, p, t0, tf, o, idx, out);
+    const int n = P.n;
+    const int nrows = (int)sink.ts.size();
+    R* dst = dense_out + (size_t)idx * M * n;
+    int hi = 1;
+    for (int j = 0; j < M; ++j) {
+        const R t = tq[j];
+        R* v = dst + (size_t)j * n;
+        if (nrows < 2) { for (int i = 0; i < n; ++i) v[i] = nrows == 1 ? sink.us[i] : (R)0; continue; }
+        while (hi < nrows - 1 && sink.ts[hi] < t) hi += 1;
+        const int ip = hi, im = hi - 1;
+        const R dt = sink.ts[ip] - sink.ts[im];
+        const R Theta = (dt == (R)0) ? (R)1 : (t - sink.ts[im]) / dt;
+        Alg k = sink.ks[ip];
+        const R* um = &sink.us[(size_t)im * n];
+        const R* up = &sink.us[(size_t)ip * n];
+        k.addsteps(um, up, p, sink.ts[im], dt);
+        k.interpolant(Theta, dt, um, up, v);
     }
 }
 
@@ -522,7 +572,7 @@ struct OracleArgs {
     int save_everystep; const long long* row_offsets; void* ts_rag;
 };
 
-template <typename R> static int run(const OracleArgs& a) {
+template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
     ProblemFns<R> P;
     P.f = (typename Fn<R>::rhs_t)a.rhs; P.jac = (typename Fn<R>::rhs_t)a.jac; P.tgrad = (typename Fn<R>::rhs_t)a.tgrad;
     P.n = a.n; P.np = a.np;
@@ -546,14 +596,16 @@ template <typename R> static int run(const OracleArgs& a) {
     out.nsaved = a.nsaved; out.naccept = a.naccept; out.nreject = a.nreject; out.nf = a.nf;
     out.njacs = a.njacs; out.nw = a.nw; out.nsolve = a.nsolve; out.retcode = a.retcode;
     const R* u0 = (const R*)a.u0; const R* p = (const R*)a.p;
+    std::vector<R> tq(M > 0 ? M : 1);
+    for (int j = 0; j < M; ++j) tq[j] = (R)tq64[j];
     switch (a.alg) {
-        case ALG_TSIT5: solve_batch<R, Tsit5<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
+        case ALG_TSIT5: solve_batch<R, Tsit5<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #ifdef ORACLE_HAVE_VERN7
-        case ALG_VERN7: solve_batch<R, Vern7<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
+        case ALG_VERN7: solve_batch<R, Vern7<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #endif
 #ifdef ORACLE_HAVE_ROSENBROCK
-        case ALG_ROS23: solve_batch<R, Rosenbrock23<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
-        case ALG_RODAS5P: solve_batch<R, Rodas5P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads); break;
+        case ALG_ROS23: solve_batch<R, Rosenbrock23<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_RODAS5P: solve_batch<R, Rodas5P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #endif
         default: return -2;
     }
@@ -564,6 +616,12 @@ extern "C" {
 int oracle_solve(const OracleArgs* a) {
     if (!a || a->n < 1 || a->n > ORACLE_MAXN || !a->rhs) return -1;
     return a->dtype == 1 ? run<float>(*a) : run<double>(*a);
+}
+// dense = true: integrate with save_everystep, keep (ts, us, ks) per trajectory, evaluate sol(tq[j]);
+// out is real[N][M][n]
+int oracle_dense_solve(const OracleArgs* a, const double* tq, int M, void* out) {
+    if (!a || a->n < 1 || a->n > ORACLE_MAXN || !a->rhs || !tq || M < 1 || !out) return -1;
+    return a->dtype == 1 ? run<float>(*a, tq, M, out) : run<double>(*a, tq, M, out);
 }
 int oracle_num_threads(void) {
 #ifdef _OPENMP

@@ -56,6 +56,7 @@ def lib():
         build()
         L = C.CDLL(_LIB)
         L.oracle_solve.argtypes = [C.POINTER(OracleArgs)]
+        L.oracle_dense_solve.argtypes = [C.POINTER(OracleArgs), C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_fastpower.restype = C.c_double
         L.oracle_fastpower.argtypes = [C.c_double, C.c_double]
         L.oracle_fastpower_f32.restype = C.c_float
@@ -118,7 +119,7 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
 
 def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
           abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
-          linsolve=0, nthreads=0, save_everystep=False):
+          linsolve=0, nthreads=0, save_everystep=False, dense_tq=None):
     """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host.
     save_everystep=True returns ragged rows (row_offsets, ts, us[total, n]) like lowlevel.solve_host_everystep."""
     L = lib()
@@ -161,6 +162,17 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     a.nslots = nslots
     for k in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         setattr(a, k, out[k].ctypes.data)
+    if dense_tq is not None:
+        # dense = true (default when save_everystep and no saveat): sol_i(tq[j]) from the stored k arrays
+        tq = np.ascontiguousarray(dense_tq, dtype=np.float64)
+        dense = np.zeros((N, len(tq), n), dtype=rdt)
+        a.save_everystep = 1; a.us = None; a.nslots = 0; a.row_offsets = None; a.ts_rag = None
+        rc = L.oracle_dense_solve(C.byref(a), tq.ctypes.data, len(tq), dense.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("oracle_dense_solve failed: %d" % rc)
+        out["dense"] = dense
+        out["t_final"] = out["t_final"].astype(np.float64)
+        return out
     if save_everystep:
         # counting pass, exclusive scan, fill pass (the same two passes the GPU path makes)
         a.save_everystep = 1; a.us = None; a.nslots = 0; a.row_offsets = None; a.ts_rag = None

@@ -77,6 +77,7 @@ EXPORTS = [
     "b200ode_compile_only", "b200ode_free", "b200ode_nslots", "b200ode_solve", "b200ode_solve_device",
     "b200ode_reduce_sum_device", "b200ode_timeseries_meanvar_device", "b200ode_solve_meanvar", "b200ode_host_register", "b200ode_host_unregister",
     "b200ode_measure_fma_peak", "b200ode_solve_everystep", "b200ode_solve_everystep_device",
+    "b200ode_dense_eval_device", "b200ode_solve_dense",
 ]
 
 _lib = None
@@ -115,7 +116,10 @@ def lib():
     L.b200ode_solve_everystep.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(B200Result),
                                           C.POINTER(B200Ragged)]
     L.b200ode_solve_everystep_device.argtypes = [vp, vp, C.POINTER(B200DeviceProblem), C.POINTER(B200Opts),
-                                                 C.POINTER(B200DeviceResult), vp, vp, vp]
+                                                 C.POINTER(B200DeviceResult), vp, vp, vp, vp]
+    L.b200ode_dense_eval_device.argtypes = [vp, vp, i64, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, C.POINTER(B200Opts), vp]
+    L.b200ode_solve_dense.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), vp, i32, vp,
+                                      C.POINTER(B200Result)]
     L.b200ode_host_register.argtypes = [vp, C.c_size_t]
     L.b200ode_host_unregister.argtypes = [vp]
     L.b200ode_measure_fma_peak.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]

@@ -66,6 +66,7 @@ struct Params {
     R tol100_tf;
     const long long* row_offsets;
     R* ts_rag;
+    R* dts_rag;
 };
 
 struct DevBuf {
@@ -96,7 +97,7 @@ struct b200ode_handle_s {
     DevBuf counter, dt0, saveat, scratch_t;
     std::vector<double> saveat_cached;   // grid currently resident in `saveat` ...
     int saveat_cached_dtype = -1;        // ... in this real type
-    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets;
+    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out;
 };
 
 struct b200ode_program_s {
@@ -104,7 +105,7 @@ struct b200ode_program_s {
     int alg = 0, dtype = 0, n = 0, np = 0;
     std::vector<char> cubin;
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t k_integrate = nullptr, k_initdt = nullptr;
+    cudaKernel_t k_integrate = nullptr, k_initdt = nullptr, k_dense = nullptr;
     int sliced_g = 0;            // > 0: component-sliced kernel with this many warps per 32 trajectories
     int sliced_k = 1;            // groups of 32 trajectories per CTA
     bool everystep = false;      // compiled with -DB200_EVERYSTEP=1 (ragged save_everystep output)
@@ -387,7 +388,8 @@ __global__ void __launch_bounds__(256) k_fma_peak(R* out, int iters, R a, R b) {
 
 template <typename R>
 int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
-                 B200DeviceResult* dr, cudaStream_t stream, const long long* row_offsets = nullptr, void* ts_rag = nullptr) {
+                 B200DeviceResult* dr, cudaStream_t stream, const long long* row_offsets = nullptr, void* ts_rag = nullptr,
+                 void* dts_rag = nullptr) {
     const int n = prog->n, np = prog->np;
     const long long N = dp->trajectories;
     Params<R> P{};
@@ -412,7 +414,7 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     P.save_end = (o->save_end < 0) ? 1 : (o->save_end ? 2 : 0);
     B200Problem hp{}; hp.t0 = dp->t0; hp.tf = dp->tf;
     P.nslots = (dr->us && !prog->everystep) ? b200ode_nslots(&hp, o) : 0;
-    P.row_offsets = row_offsets; P.ts_rag = (R*)ts_rag;
+    P.row_offsets = row_offsets; P.ts_rag = (R*)ts_rag; P.dts_rag = (R*)dts_rag;
     P.saveat = nullptr;
     if (P.nsaveat > 0) {
         // the grid travels as real[] in the handle's scratch; re-uploaded only when it changes
@@ -528,7 +530,7 @@ int b200ode_destroy(b200ode_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->counter, &h->dt0, &h->saveat, &h->scratch_t, &h->in_u0, &h->in_p, &h->out_uf, &h->out_tf,
-                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets})
+                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets, &h->rag_dts, &h->dense_tq, &h->dense_out})
         b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -584,6 +586,7 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&prog->k_initdt, prog->lib, "b200_initdt");
+    if (e == cudaSuccess && prog->everystep) e = cudaLibraryGetKernel(&prog->k_dense, prog->lib, "b200_dense_eval");
     if (e != cudaSuccess) {
         cudaLibraryUnload(prog->lib); delete prog;
         return fail(B200ODE_ECUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
@@ -661,7 +664,7 @@ int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200Devic
 }
 
 int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
-                                   B200DeviceResult* dr, const int64_t* row_offsets, void* ts, void* stream) {
+                                   B200DeviceResult* dr, const int64_t* row_offsets, void* ts, void* dts, void* stream) {
     if (!h || !prog || !dp || !o || !dr) return fail(B200ODE_EINVAL, "NULL argument");
     if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
     if (!prog->everystep) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
@@ -672,27 +675,20 @@ int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const
     bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
     if (stiff && (!dr->njacs || !dr->nw || !dr->nsolve))
         return fail(B200ODE_EINVAL, "Rosenbrock programs need njacs,nw,nsolve result arrays");
-    if (row_offsets && (!dr->us || !ts)) return fail(B200ODE_EINVAL, "the fill pass needs result.us and ts");
+    if (row_offsets && (!dr->us || !ts || !dts)) return fail(B200ODE_EINVAL, "the fill pass needs result.us, ts and dts");
     if (dp->trajectories == 0) return B200ODE_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     static_assert(sizeof(long long) == sizeof(int64_t), "row offsets are 64-bit");
-    if (prog->dtype == B200ODE_F32) return launch_solve<float>(h, prog, dp, o, dr, s, (const long long*)row_offsets, ts);
-    return launch_solve<double>(h, prog, dp, o, dr, s, (const long long*)row_offsets, ts);
+    if (prog->dtype == B200ODE_F32) return launch_solve<float>(h, prog, dp, o, dr, s, (const long long*)row_offsets, ts, dts);
+    return launch_solve<double>(h, prog, dp, o, dr, s, (const long long*)row_offsets, ts, dts);
 }
 
-int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,
-                            B200Ragged* out) {
-    if (!h || !prog || !hp || !o || !res || !out) return fail(B200ODE_EINVAL, "NULL argument");
-    if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
-    if (!prog->everystep) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
-    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, hp->t0, hp->tf, o);
-    if (rc) return rc;
-    if (!res->u_final) return fail(B200ODE_EINVAL, "result.u_final is required");
-    out->total_rows = 0; out->row_offsets = nullptr; out->ts = nullptr; out->us = nullptr;
+// H2D, counting pass, host exclusive scan, fill pass.  Leaves the ragged rows in the handle's device
+// buffers (out_us, scratch_t = ts, rag_dts, row_offsets) and the scalars in out_uf/out_tf/out_i32.
+static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o,
+                         std::vector<int64_t>& offs) {
     const long long N = hp->trajectories;
-    if (N == 0) return B200ODE_OK;
-    CUDA_TRY(cudaSetDevice(h->device));
     const int n = prog->n, np = prog->np;
     const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
     cudaStream_t s = h->stream;
@@ -724,50 +720,50 @@ int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Pr
     dr.njacs = i32 + 4 * N; dr.nw = i32 + 5 * N; dr.nsolve = i32 + 6 * N; dr.retcode = i32 + 7 * N;
     CUDA_TRY(cudaEventRecord(h->ev1, s));
     // pass 1: count the rows of every trajectory (the integration is deterministic, so pass 2 repeats it exactly)
-    rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, nullptr, nullptr, s);
+    int rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, nullptr, nullptr, nullptr, s);
     if (rc) return rc;
     std::vector<int32_t> counts((size_t)N);
     CUDA_TRY(cudaMemcpyAsync(counts.data(), i32, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * ((size_t)N + 1));
-    if (!offs) return fail(B200ODE_EINVAL, "out of host memory");
+    offs.resize((size_t)N + 1);
     int64_t total = 0;
-    for (long long i = 0; i < N; ++i) { offs[i] = total; total += counts[(size_t)i]; }
-    offs[N] = total;
-    double* ts_host = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
-    void* us_host = malloc(rs * (size_t)n * (size_t)std::max<int64_t>(total, 1));
-    if (!ts_host || !us_host) { free(offs); free(ts_host); free(us_host); return fail(B200ODE_EINVAL, "out of host memory"); }
-    auto bail = [&](int code) { free(offs); free(ts_host); free(us_host); return code; };
-#define CUDA_TRY_BAIL(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return bail(fail(B200ODE_ECUDA, std::string(#x ": ") + cudaGetErrorString(e_))); } while (0)
-    CUDA_TRY_BAIL(h->out_us.ensure(rs * (size_t)n * (size_t)std::max<int64_t>(total, 1)));
-    CUDA_TRY_BAIL(h->scratch_t.ensure(rs * (size_t)std::max<int64_t>(total, 1)));
-    CUDA_TRY_BAIL(cudaMemcpyAsync(h->row_offsets.ptr, offs, sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
+    for (long long i = 0; i < N; ++i) { offs[(size_t)i] = total; total += counts[(size_t)i]; }
+    offs[(size_t)N] = total;
+    const size_t rows = (size_t)std::max<int64_t>(total, 1);
+    CUDA_TRY(h->out_us.ensure(rs * (size_t)n * rows));
+    CUDA_TRY(h->scratch_t.ensure(rs * rows));
+    CUDA_TRY(h->rag_dts.ensure(rs * rows));
+    CUDA_TRY(cudaMemcpyAsync(h->row_offsets.ptr, offs.data(), sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
     // pass 2: fill
     dr.us = h->out_us.ptr;
-    rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, (const int64_t*)h->row_offsets.ptr, h->scratch_t.ptr, s);
-    if (rc) return bail(rc);
-    CUDA_TRY_BAIL(cudaEventRecord(h->ev2, s));
-    CUDA_TRY_BAIL(cudaMemcpyAsync(us_host, h->out_us.ptr, rs * (size_t)n * (size_t)total, cudaMemcpyDeviceToHost, s));
-    std::vector<char> ts_raw;
-    if (rs == 8) CUDA_TRY_BAIL(cudaMemcpyAsync(ts_host, h->scratch_t.ptr, 8 * (size_t)total, cudaMemcpyDeviceToHost, s));
-    else { ts_raw.resize(4 * (size_t)total); CUDA_TRY_BAIL(cudaMemcpyAsync(ts_raw.data(), h->scratch_t.ptr, 4 * (size_t)total, cudaMemcpyDeviceToHost, s)); }
-    CUDA_TRY_BAIL(cudaMemcpyAsync(res->u_final, h->out_uf.ptr, rs * n * (size_t)N, cudaMemcpyDeviceToHost, s));
+    rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, (const int64_t*)h->row_offsets.ptr, h->scratch_t.ptr,
+                                        h->rag_dts.ptr, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev2, s));
+    return B200ODE_OK;
+}
+
+// D2H of the per-trajectory scalars + timing, shared by the ragged entry points (stream must be idle afterwards)
+static int everystep_finish(b200ode_handle h, b200ode_program prog, long long N, B200Result* res) {
+    const int n = prog->n;
+    const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
+    cudaStream_t s = h->stream;
+    int32_t* i32 = (int32_t*)h->out_i32.ptr;
+    CUDA_TRY(cudaMemcpyAsync(res->u_final, h->out_uf.ptr, rs * n * (size_t)N, cudaMemcpyDeviceToHost, s));
     std::vector<char> tf_host;
     if (res->t_final) {
         tf_host.resize(rs * (size_t)N);
-        CUDA_TRY_BAIL(cudaMemcpyAsync(tf_host.data(), h->out_tf.ptr, rs * (size_t)N, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(tf_host.data(), h->out_tf.ptr, rs * (size_t)N, cudaMemcpyDeviceToHost, s));
     }
     struct { int32_t* dst; int slot; } outs[] = {
         {res->nsaved, 0}, {res->naccept, 1}, {res->nreject, 2}, {res->nf, 3},
         {res->njacs, 4}, {res->nw, 5}, {res->nsolve, 6}, {res->retcode, 7}};
     for (auto& oo : outs)
-        if (oo.dst) CUDA_TRY_BAIL(cudaMemcpyAsync(oo.dst, i32 + (size_t)oo.slot * N, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY_BAIL(cudaEventRecord(h->ev3, s));
-    CUDA_TRY_BAIL(cudaStreamSynchronize(s));
-#undef CUDA_TRY_BAIL
+        if (oo.dst) CUDA_TRY(cudaMemcpyAsync(oo.dst, i32 + (size_t)oo.slot * N, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaEventRecord(h->ev3, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) return bail(fail(B200ODE_ECUDA, std::string("kernel failure: ") + cudaGetErrorString(le)));
-    if (rs == 4) for (int64_t i = 0; i < total; ++i) ts_host[i] = (double)((const float*)ts_raw.data())[i];
+    if (le != cudaSuccess) return fail(B200ODE_ECUDA, std::string("kernel failure: ") + cudaGetErrorString(le));
     if (res->t_final) {
         if (rs == 8) memcpy(res->t_final, tf_host.data(), 8 * (size_t)N);
         else for (long long i = 0; i < N; ++i) res->t_final[i] = (double)((const float*)tf_host.data())[i];
@@ -776,8 +772,131 @@ int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Pr
     cudaEventElapsedTime(&kms, h->ev1, h->ev2);
     cudaEventElapsedTime(&tms, h->ev0, h->ev3);
     res->kernel_ms = kms; res->total_ms = tms;
-    out->total_rows = total; out->row_offsets = offs; out->ts = ts_host; out->us = us_host;
     return B200ODE_OK;
+}
+
+static int everystep_check(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res) {
+    if (!h || !prog || !hp || !o || !res) return fail(B200ODE_EINVAL, "NULL argument");
+    if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
+    if (!prog->everystep) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
+    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, hp->t0, hp->tf, o);
+    if (rc) return rc;
+    if (!res->u_final) return fail(B200ODE_EINVAL, "result.u_final is required");
+    return B200ODE_OK;
+}
+
+int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,
+                            B200Ragged* out) {
+    if (!out) return fail(B200ODE_EINVAL, "NULL argument");
+    int rc = everystep_check(h, prog, hp, o, res);
+    if (rc) return rc;
+    out->total_rows = 0; out->row_offsets = nullptr; out->ts = nullptr; out->us = nullptr;
+    const long long N = hp->trajectories;
+    if (N == 0) return B200ODE_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = prog->n;
+    const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
+    cudaStream_t s = h->stream;
+    std::vector<int64_t> offs;
+    rc = everystep_run(h, prog, hp, o, offs);
+    if (rc) return rc;
+    const int64_t total = offs[(size_t)N];
+    int64_t* offs_host = (int64_t*)malloc(sizeof(int64_t) * ((size_t)N + 1));
+    double* ts_host = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
+    void* us_host = malloc(rs * (size_t)n * (size_t)std::max<int64_t>(total, 1));
+    auto bail = [&](int code) { free(offs_host); free(ts_host); free(us_host); return code; };
+    if (!offs_host || !ts_host || !us_host) return bail(fail(B200ODE_EINVAL, "out of host memory"));
+    memcpy(offs_host, offs.data(), sizeof(int64_t) * ((size_t)N + 1));
+    std::vector<char> ts_raw;
+    cudaError_t e = cudaMemcpyAsync(us_host, h->out_us.ptr, rs * (size_t)n * (size_t)total, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) {
+        if (rs == 8) e = cudaMemcpyAsync(ts_host, h->scratch_t.ptr, 8 * (size_t)total, cudaMemcpyDeviceToHost, s);
+        else { ts_raw.resize(4 * (size_t)std::max<int64_t>(total, 1)); e = cudaMemcpyAsync(ts_raw.data(), h->scratch_t.ptr, 4 * (size_t)total, cudaMemcpyDeviceToHost, s); }
+    }
+    if (e != cudaSuccess) return bail(fail(B200ODE_ECUDA, std::string("ragged D2H: ") + cudaGetErrorString(e)));
+    rc = everystep_finish(h, prog, N, res);
+    if (rc) return bail(rc);
+    if (rs == 4) for (int64_t i = 0; i < total; ++i) ts_host[i] = (double)((const float*)ts_raw.data())[i];
+    out->total_rows = total; out->row_offsets = offs_host; out->ts = ts_host; out->us = us_host;
+    return B200ODE_OK;
+}
+
+extern "C++" {
+template <typename R>
+struct DenseParams {
+    long long N;
+    const R* p; long long p_ts, p_cs;
+    const long long* row_offsets; const R* ts; const R* dts; const R* us;
+    const R* tq; int M;
+    R* out;
+    R reltol, abstol;
+};
+
+template <typename R>
+static int launch_dense(b200ode_handle h, b200ode_program prog, long long N, const void* p, int p_shared, int p_layout,
+                        const int64_t* row_offsets, const void* ts, const void* dts, const void* us, const void* tq, int M,
+                        void* out, const B200Opts* o, cudaStream_t s) {
+    DenseParams<R> D{};
+    D.N = N;
+    D.p = (const R*)p;
+    if (p_shared) { D.p_ts = 0; D.p_cs = 1; }
+    else if (p_layout == B200ODE_LAYOUT_SOA) { D.p_ts = 1; D.p_cs = N; }
+    else { D.p_ts = prog->np; D.p_cs = 1; }
+    D.row_offsets = (const long long*)row_offsets; D.ts = (const R*)ts; D.dts = (const R*)dts; D.us = (const R*)us;
+    D.tq = (const R*)tq; D.M = M; D.out = (R*)out;
+    D.reltol = (R)(o && o->reltol > 0 ? o->reltol : 1e-3);
+    D.abstol = (R)(o && o->abstol > 0 ? o->abstol : 1e-6);
+    void* args[] = {&D};
+    unsigned g = (unsigned)((N + 127) / 128);
+    CUDA_TRY(cudaLaunchKernel((const void*)prog->k_dense, dim3(g), dim3(128), args, 0, s));
+    return B200ODE_OK;
+}
+}  // extern "C++"
+
+int b200ode_dense_eval_device(b200ode_handle h, b200ode_program prog, int64_t trajectories, const void* p, int p_shared,
+                              int p_layout, const int64_t* row_offsets, const void* ts, const void* dts, const void* us,
+                              const void* tq, int nq, void* out, const B200Opts* opts, void* stream) {
+    if (!h || !prog || !row_offsets || !ts || !dts || !us || !tq || !out) return fail(B200ODE_EINVAL, "NULL argument");
+    if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
+    if (!prog->everystep || !prog->k_dense) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
+    if (prog->np > 0 && !p) return fail(B200ODE_EINVAL, "p is NULL but the program has np > 0");
+    if (trajectories <= 0 || nq <= 0) return B200ODE_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (prog->dtype == B200ODE_F32)
+        return launch_dense<float>(h, prog, trajectories, p, p_shared, p_layout, row_offsets, ts, dts, us, tq, nq, out, opts, s);
+    return launch_dense<double>(h, prog, trajectories, p, p_shared, p_layout, row_offsets, ts, dts, us, tq, nq, out, opts, s);
+}
+
+int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, const double* tq,
+                        int nq, void* out, B200Result* res) {
+    if (!tq || !out || nq <= 0) return fail(B200ODE_EINVAL, "tq/out is NULL or nq <= 0");
+    int rc = everystep_check(h, prog, hp, o, res);
+    if (rc) return rc;
+    if (o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "dense output excludes saveat (dense = save_everystep && isempty(saveat), solve.jl:139)");
+    if (o->save_start == 0) return fail(B200ODE_EINVAL, "dense output needs save_start");
+    for (int j = 1; j < nq; ++j) if (!(tq[j] >= tq[j - 1])) return fail(B200ODE_EINVAL, "tq must be ascending");
+    const long long N = hp->trajectories;
+    if (N == 0) return B200ODE_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = prog->n;
+    const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
+    cudaStream_t s = h->stream;
+    std::vector<int64_t> offs;
+    rc = everystep_run(h, prog, hp, o, offs);
+    if (rc) return rc;
+    CUDA_TRY(h->dense_tq.ensure(rs * (size_t)nq));
+    CUDA_TRY(h->dense_out.ensure(rs * (size_t)n * (size_t)nq * (size_t)N));
+    std::vector<char> tq_real(rs * (size_t)nq);
+    for (int j = 0; j < nq; ++j) { if (rs == 8) ((double*)tq_real.data())[j] = tq[j]; else ((float*)tq_real.data())[j] = (float)tq[j]; }
+    CUDA_TRY(cudaMemcpyAsync(h->dense_tq.ptr, tq_real.data(), rs * (size_t)nq, cudaMemcpyHostToDevice, s));
+    rc = b200ode_dense_eval_device(h, prog, N, prog->np > 0 ? h->in_p.ptr : nullptr, hp->p_shared, B200ODE_LAYOUT_AOS,
+                                   (const int64_t*)h->row_offsets.ptr, h->scratch_t.ptr, h->rag_dts.ptr, h->out_us.ptr,
+                                   h->dense_tq.ptr, nq, h->dense_out.ptr, o, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev2, s));
+    CUDA_TRY(cudaMemcpyAsync(out, h->dense_out.ptr, rs * (size_t)n * (size_t)nq * (size_t)N, cudaMemcpyDeviceToHost, s));
+    return everystep_finish(h, prog, N, res);
 }
 
 static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o, B200Result* res,

@@ -94,6 +94,7 @@ struct B200Params {
     // row_offsets[i] .. row_offsets[i+1]-1 of us[.][n] / ts_rag[.]; NULL = counting pass (nsaved[] only).
     const long long* row_offsets;
     real* ts_rag;
+    real* dts_rag;            // step size the stages of the step ending at each row were computed with (0 for other rows)
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
@@ -208,6 +209,7 @@ struct B200Traj {
     real* row;                  // next row of us[idx][.][:] (running pointer: no 64-bit index arithmetic per row)
 #if B200_EVERYSTEP
     real* trow;                 // next entry of ts_rag
+    real* drow;                 // next entry of dts_rag
     real last_t;                // sol.t[end]
     int cap;                    // rows this trajectory owns (0 in the counting pass)
 #endif
@@ -216,13 +218,14 @@ struct B200Traj {
 #endif
 };
 
-B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, const real* v) {
+B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, const real* v, real dt_stages = (real)0) {
 #if B200_EVERYSTEP
     if (T.nsaved < T.cap) {
 #pragma unroll
         for (int c = 0; c < B200_N; ++c) T.row[c] = v[c];
         T.row += B200_N;
         *T.trow++ = ts;
+        *T.drow++ = dt_stages;
     }
     T.last_t = ts;
 #else
@@ -260,12 +263,13 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
 #endif
     T.nsaved = 0; T.save_idx = 0;
 #if B200_EVERYSTEP
-    T.cap = 0; T.row = nullptr; T.trow = nullptr; T.last_t = P.t0;
+    T.cap = 0; T.row = nullptr; T.trow = nullptr; T.drow = nullptr; T.last_t = P.t0;
     if (P.row_offsets != nullptr) {
         const long long o = P.row_offsets[idx];
         T.cap = (int)(P.row_offsets[idx + 1] - o);
         T.row = P.us + (size_t)o * B200_N;
         T.trow = P.ts_rag + o;
+        T.drow = P.dts_rag + o;
     }
 #else
     T.row = P.us + (size_t)idx * (size_t)P.nslots * B200_N;
@@ -369,6 +373,9 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     if (T.accept) {
         T.naccept += 1;
         T.tprev = T.t;
+#if B200_EVERYSTEP
+        const real dt_stages = T.dt;                // what perform_step! ran with (the dense pass recomputes the stages from it)
+#endif
         if (T.tstop_flag) T.dt = T.dtpropose;       // restore un-clipped dt (integrator_utils.jl:629-633)
         T.t = T.tstop_flag ? P.tf : ttmp;           // fixed_t_for_tstop_error!
         T.tstop_flag = false;
@@ -407,7 +414,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #if B200_EVERYSTEP
             // save_everystep && (isempty(sol.t) || (t !== sol.t[end] || iszero(dt)) && (save_end || t !== tspan[2]))
             if ((T.nsaved == 0 || ((T.t != T.last_t || T.dt == (real)0) && (P.save_end || T.t != P.tf))))
-                b200_emit(P, idx, T, T.t, T.u);
+                b200_emit(P, idx, T, T.t, T.u, dt_stages);
 #endif
         }
     } else {
@@ -555,4 +562,73 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
         }
     }
 }
+#if B200_EVERYSTEP
+// ---------------------------------------------------------------------------
+// sol(tq) for every trajectory, post hoc, from the ragged per-step rows — ode_interpolation
+// (dense/generic_dense.jl:833-867: interval search :845-849, dt = ts[i+] - ts[i-], Θ :858-859,
+// evaluate_interpolant :795-825 -> _ode_addsteps! + ode_interpolant).  The reference keeps every
+// step's stage derivatives ks[i] (7-16 vectors per row, integrator_utils.jl:455-473); here they are
+// RECOMPUTED from (u[i-], ts[i-], the step's own dt) — the same deterministic arithmetic, so the
+// values are bit-identical — which costs one perform_step! per visited interval instead of 8-17x
+// the HBM footprint.  Lazy extra stages (Vern7 k11..k16) use dt = ts[i+] - ts[i-] as the reference's
+// post-hoc _ode_addsteps! does.  tq must be ascending (the reference sorts the queries first).
+struct B200DenseParams {
+    long long N;
+    const real* p; long long p_ts, p_cs;
+    const long long* row_offsets; const real* ts; const real* dts; const real* us;
+    const real* tq; int M;
+    real* out;                // [N][M][n]
+    real reltol, abstol;      // only feed the (unused) error estimate of the recomputed step
+};
+
+extern "C" __global__ void __launch_bounds__(128) b200_dense_eval(B200DenseParams D) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D.N) return;
+    real p[B200_NP > 0 ? B200_NP : 1];
+#pragma unroll
+    for (int c = 0; c < B200_NP; ++c) p[c] = D.p[idx * D.p_ts + c * D.p_cs];
+    const long long a = D.row_offsets[idx];
+    const int nrows = (int)(D.row_offsets[idx + 1] - a);
+    const real* ts = D.ts + a;
+    const real* dts = D.dts + a;
+    const real* us = D.us + (size_t)a * B200_N;
+    real* out = D.out + (size_t)idx * (size_t)D.M * B200_N;
+    B200Stepper st;
+    real uprev[B200_N], u[B200_N], scratch[B200_N];
+    int hi = 1, cur = -1, nf = 0;
+#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+    int njacs = 0, nw = 0, nsolve = 0;
+#endif
+    for (int j = 0; j < D.M; ++j) {
+        const real t = D.tq[j];
+        real* o = out + (size_t)j * B200_N;
+        if (nrows < 2) {      // a single row: i- = i+, dt = 0 => the interpolant collapses to that row
+#pragma unroll
+            for (int c = 0; c < B200_N; ++c) o[c] = nrows == 1 ? us[c] : (real)0;
+            continue;
+        }
+        // i+ = min(lastindex, max(previous i+, first i with ts[i] >= t)); i- = i+ - 1
+        while (hi < nrows - 1 && ts[hi] < t) hi += 1;
+        const int ip = hi, im = hi - 1;
+        const real dt = ts[ip] - ts[im];
+        const real th = (dt == (real)0) ? (real)1 : (t - ts[im]) / dt;
+        if (ip != cur) {
+#pragma unroll
+            for (int c = 0; c < B200_N; ++c) { uprev[c] = us[(size_t)im * B200_N + c]; u[c] = us[(size_t)ip * B200_N + c]; }
+            st.init(uprev, p, ts[im], nf);                                   // FSAL k1 = f(u[i-], ts[i-])
+#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+            st.attempt(uprev, scratch, p, ts[im], dts[ip], D.reltol, D.abstol, nf, njacs, nw, nsolve, true);
+#else
+            st.attempt(uprev, scratch, p, ts[im], dts[ip], D.reltol, D.abstol, nf);
+#endif
+            st.dense_prepare(uprev, u, p, ts[im], dt);
+            cur = ip;
+        }
+        real val[B200_N];
+        st.interp(th, dt, uprev, u, val);
+#pragma unroll
+        for (int c = 0; c < B200_N; ++c) o[c] = val[c];
+    }
+}
+#endif  // B200_EVERYSTEP
 #endif  // !B200_SLICED

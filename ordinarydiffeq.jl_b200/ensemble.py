@@ -167,8 +167,24 @@ class DEStats:
 
 
 class ODESolution:
-    def __init__(self, t, u, retcode, stats, prob=None, alg=None):
+    def __init__(self, t, u, retcode, stats, prob=None, alg=None, interp=None):
         self.t, self.u, self.retcode, self.stats, self.prob, self.alg = t, u, retcode, stats, prob, alg
+        self._interp = interp
+        self.dense = interp is not None
+
+    def __call__(self, t):
+        """sol(t): the stepper's own dense output (ode_interpolation, dense/generic_dense.jl:833-867), evaluated
+        on the device from this trajectory's steps.  Available when the solve saved every step and no saveat
+        (the reference's default `dense`, solve.jl:144-145)."""
+        if self._interp is None:
+            raise NotImplementedError("this solution has no dense output (solve with save_everystep and no saveat)")
+        scalar = np.isscalar(t)
+        tq = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        order = np.argsort(tq, kind="stable")
+        vals = self._interp(tq[order])
+        out = np.empty_like(vals)
+        out[order] = vals
+        return out[0] if scalar else out
 
     def __getitem__(self, i):
         return self.u[i]
@@ -180,9 +196,10 @@ class ODESolution:
 class _LazySolutions:
     """Vector{ODESolution} over the flat result arrays (materialised per index on demand)."""
 
-    def __init__(self, res, t0, alg, has_grid, u0=None, save_start=True, save_end=True):
+    def __init__(self, res, t0, alg, has_grid, u0=None, save_start=True, save_end=True, dense=None):
         self.res, self.t0, self.alg, self.has_grid = res, t0, alg, has_grid
         self.u0, self.save_start, self.save_end = u0, save_start, save_end
+        self.dense = dense      # callable (i, tq ascending) -> [len(tq), n], or None
 
     def __len__(self):
         return self.res["u_final"].shape[0]
@@ -213,7 +230,8 @@ class _LazySolutions:
             t = np.array(ts)
             u = np.stack(us) if us else np.zeros((0, r["u_final"].shape[1]), dtype=r["u_final"].dtype)
         st = DEStats(r["nf"][i], r["naccept"][i], r["nreject"][i], r["njacs"][i], r["nw"][i], r["nsolve"][i])
-        return ODESolution(t, u, _lib.RETCODE_NAMES[int(r["retcode"][i])], st, alg=self.alg)
+        interp = None if self.dense is None else (lambda tq, i=i: self.dense(i, tq))
+        return ODESolution(t, u, _lib.RETCODE_NAMES[int(r["retcode"][i])], st, alg=self.alg, interp=interp)
 
     def __iter__(self):
         for i in range(len(self)):
@@ -221,8 +239,16 @@ class _LazySolutions:
 
 
 class EnsembleSolution:
-    def __init__(self, u, elapsed, converged, arrays=None):
+    def __init__(self, u, elapsed, converged, arrays=None, dense_all=None):
         self.u, self.elapsed_time, self.converged, self.arrays = u, elapsed, converged, arrays
+        self._dense_all = dense_all
+
+    def at(self, tq):
+        """[sol(tq) for sol in ensemble] as one array [trajectories, len(tq), n] in a single device pass
+        (b200ode_solve_dense); tq ascending."""
+        if self._dense_all is None:
+            raise NotImplementedError("dense output needs save_everystep, no saveat, and the default reduction")
+        return self._dense_all(np.asarray(tq, dtype=np.float64))
 
     def __getitem__(self, i):
         return self.u[i]
@@ -315,15 +341,31 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     grid = ranges.saveat_grid(kw.get("saveat", None), prob.tspan)
     handle = _handle(ensemblealg.device)
     program = get_program(handle, alg, prob.f, n, np_, f32, everystep)
+    save_start, save_end = ranges.resolve_save_flags(kw.get("saveat", None), prob.tspan, everystep,
+                                                     kw.get("save_start"), kw.get("save_end"))
 
     def run(u0, p, ntraj, flags=0):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
                       dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
-                      saveat=grid if grid else None, save_start=kw.get("save_start"), save_end=kw.get("save_end"),
+                      saveat=grid if grid else None, save_start=save_start, save_end=save_end,
                       flags=flags)
         if everystep:
             return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
         return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
+
+    dense_ok = everystep and not grid and save_start      # dense = save_everystep && isempty(saveat) (solve.jl:144)
+    tol_kw = dict(reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
+                  dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"))
+
+    def dense_of(u0, p):
+        u0 = np.asarray(u0); p_ = None if p is None else np.asarray(p)
+
+        def one(i, tq):
+            ui = u0 if u0.ndim == 1 else u0[i:i + 1]
+            pi = p_ if (p_ is None or p_.ndim == 1) else p_[i:i + 1]
+            return lowlevel.solve_host_dense(program, ui, pi, prob.tspan, tq, trajectories=1, **tol_kw)["dense"][0]
+        return one
+    batches_in = []
 
     t_start = time.perf_counter()
     reduction, output_func = eprob.reduction, eprob.output_func
@@ -335,10 +377,11 @@ def solve(eprob, alg, ensemblealg=None, **kw):
         u0, p = _harvest(eprob, I)
         res = run(u0, p, len(I), kw.get("flags", 0))
         all_arrays.append(res)
-        ss = kw.get("save_start"); se = kw.get("save_end")
-        mk = lambda r, u0_: _LazySolutions(r, prob.tspan[0], alg, bool(grid), np.asarray(u0_),
-                                           True if ss is None else bool(ss), True if se is None else bool(se))
-        sols = mk(res, u0)
+        mk = lambda r, u0_, p_=None: _LazySolutions(r, prob.tspan[0], alg, bool(grid), np.asarray(u0_),
+                                                    save_start, save_end is None or save_end,
+                                                    dense=dense_of(u0_, p_) if dense_ok else None)
+        batches_in.append((u0, p, len(I)))
+        sols = mk(res, u0, p)
         if output_func is None:
             batch = sols
         else:
@@ -351,7 +394,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
                     repeat += 1
                     u0r, pr = _harvest(eprob, [int(i)], repeat)
                     r1 = run(u0r, pr, 1)
-                    out, rerun = output_func(mk(r1, u0r)[0], EnsembleContext(int(i), repeat))
+                    out, rerun = output_func(mk(r1, u0r, pr)[0], EnsembleContext(int(i), repeat))
                 batch.append(out)
         if reduction is None:
             if isinstance(u_acc, list) and not u_acc and output_func is None and b0 + batch_size >= N and b0 == 0:
@@ -363,4 +406,9 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             if converged:
                 break
     elapsed = time.perf_counter() - t_start
-    return EnsembleSolution(u_acc, elapsed, converged, arrays=all_arrays)
+    dense_all = None
+    if dense_ok and reduction is None and output_func is None:
+        def dense_all(tq):
+            return np.concatenate([lowlevel.solve_host_dense(program, u0_, p_, prob.tspan, tq, trajectories=cnt, **tol_kw)["dense"]
+                                   for (u0_, p_, cnt) in batches_in])
+    return EnsembleSolution(u_acc, elapsed, converged, arrays=all_arrays, dense_all=dense_all)

@@ -109,7 +109,12 @@ function __solve(eprob::AbstractEnsembleProblem, alg::Union{Tsit5, Vern7, Rosenb
                 (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring),
                 h, prog, alg_id(alg), T === Float32 ? 1 : 0, n, np, rhs, "diffeqf",
                 jac === nothing ? C_NULL : jac, "diffeqjac", tgr === nothing ? C_NULL : tgr, "diffeqtgrad", C_NULL))
-    ss = get(kw, :save_start, nothing); se = get(kw, :save_end, nothing)
+    # defaults of solve.jl:141-143,596-599 (the C ABI only sees the expanded grid)
+    everystep = get(kw, :save_everystep, isempty(grid))
+    dflt(tend) = everystep || isempty(saveat) || saveat isa Number || tend in saveat
+    ss = something(get(kw, :save_start, nothing), dflt(prob.tspan[1]))
+    se = get(kw, :save_end, nothing)
+    se === nothing && !dflt(prob.tspan[2]) && (se = false)
     opts = B200Opts(get(kw, :reltol, 0.0), get(kw, :abstol, 0.0), something(get(kw, :dt, nothing), 0.0),
                     get(kw, :dtmin, 0.0), get(kw, :dtmax, 0.0), get(kw, :maxiters, 0),
                     isempty(grid) ? Ptr{Float64}(C_NULL) : pointer(grid), length(grid),

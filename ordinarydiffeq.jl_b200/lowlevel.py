@@ -89,12 +89,8 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     return out
 
 
-def solve_host_everystep(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None,
-                         dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None, flags=0):
-    """save_everystep = true (b200ode_solve_everystep): returns the per-trajectory scalars plus the ragged
-    rows — row_offsets[N+1], ts[total], us[total, n]; trajectory i's sol.t / sol.u are
-    ts[row_offsets[i]:row_offsets[i+1]] and the same slice of us."""
-    L = _lib.lib()
+def _marshal_ragged(program, u0, p, tspan, trajectories):
+    """Problem + scalar result structs shared by the save_everystep / dense entry points."""
     if not program.everystep:
         raise ValueError("program was not compiled with OPT_EVERYSTEP")
     rdt = _np_real(program.dtype)
@@ -115,7 +111,6 @@ def solve_host_everystep(program, u0, p, tspan, trajectories=None, reltol=None, 
         raise ValueError("u0 has shape %s, expected (%d, %d) or (%d,)" % (u0.shape, N, n, n))
     if npar > 0 and (p_arr is None or p_arr.shape[-1] != npar or (not p_shared and p_arr.shape[0] != N)):
         raise ValueError("p has wrong shape for np=%d" % npar)
-    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags)
     prob = _lib.B200Problem()
     prob.trajectories = N
     prob.u0 = u0.ctypes.data; prob.u0_shared = int(u0_shared)
@@ -128,6 +123,34 @@ def solve_host_everystep(program, u0, p, tspan, trajectories=None, reltol=None, 
     for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         out[name] = np.empty((N,), dtype=np.int32)
         setattr(res, name, out[name].ctypes.data)
+    return N, n, rdt, prob, res, out, (u0, p_arr)
+
+
+def solve_host_dense(program, u0, p, tspan, tq, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None,
+                     dtmax=None, maxiters=None, flags=0):
+    """sol_i(tq[j]) for every trajectory (b200ode_solve_dense): integrates with save_everystep, evaluates the
+    dense output on the device, returns dict with dense[N, len(tq), n] and the per-trajectory scalars."""
+    L = _lib.lib()
+    N, n, rdt, prob, res, out, keep_in = _marshal_ragged(program, u0, p, tspan, trajectories)
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, None, None, None, flags)
+    tq = np.ascontiguousarray(tq, dtype=np.float64)
+    out["dense"] = np.empty((N, len(tq), n), dtype=rdt)
+    _lib.check(L.b200ode_solve_dense(program.handle._h, program._p, C.byref(prob), C.byref(opts),
+                                     C.c_void_p(tq.ctypes.data), len(tq), C.c_void_p(out["dense"].ctypes.data),
+                                     C.byref(res)))
+    out["kernel_ms"] = res.kernel_ms
+    out["total_ms"] = res.total_ms
+    return out
+
+
+def solve_host_everystep(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None,
+                         dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None, flags=0):
+    """save_everystep = true (b200ode_solve_everystep): returns the per-trajectory scalars plus the ragged
+    rows — row_offsets[N+1], ts[total], us[total, n]; trajectory i's sol.t / sol.u are
+    ts[row_offsets[i]:row_offsets[i+1]] and the same slice of us."""
+    L = _lib.lib()
+    N, n, rdt, prob, res, out, keep_in = _marshal_ragged(program, u0, p, tspan, trajectories)
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags)
     rag = _lib.B200Ragged()
     _lib.check(L.b200ode_solve_everystep(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res),
                                          C.byref(rag)))

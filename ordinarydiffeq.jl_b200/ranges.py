@@ -82,3 +82,25 @@ def saveat_grid(saveat, tspan):
         return julia_range(t0 + h, h, tf)
     vals = [float(t) for t in saveat]
     return [t for t in vals if t0 < t <= tf]
+
+
+def resolve_save_flags(saveat, tspan, save_everystep, save_start=None, save_end=None):
+    """Defaults of save_start / save_end (lib/OrdinaryDiffEqCore/src/solve.jl:141-143,596-599):
+
+        save_start = save_everystep || isempty(saveat) || saveat isa Number || tspan[1] in saveat
+        save_end   = (same rule with tspan[2]) when the caller passed nothing
+
+    Returns (save_start, save_end) as the C ABI encodes them: save_start in {0, 1};
+    save_end in {0, None (default true: save_end_user is not a Bool), 1 (explicit true)}."""
+    t0, tf = float(tspan[0]), float(tspan[1])
+    is_number = isinstance(saveat, (int, float))
+    empty = saveat is None or (not is_number and len(saveat) == 0)
+
+    def default(endpoint):
+        return bool(save_everystep or empty or is_number or any(float(s) == endpoint for s in saveat))
+    ss = default(t0) if save_start is None else bool(save_start)
+    if save_end is None:
+        se = None if default(tf) else False
+    else:
+        se = bool(save_end)
+    return ss, se

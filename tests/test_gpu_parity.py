@@ -472,3 +472,62 @@ def test_high_level_default_is_save_everystep(pkg, oracle):
     ep2 = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table), output_func=lambda sol, ctx: (len(sol.t), False))
     s2 = P.solve(ep2, P.Tsit5(), P.EnsembleB200(), trajectories=N)
     assert list(s2.u) == list(o["nsaved"])
+
+
+# ---- dense output sol(t), post hoc, from recomputed stages -------------------
+@pytest.mark.parametrize("f32", [False, True])
+def test_dense_eval_lorenz(pkg, handle, oracle, f32):
+    N = 2000
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N, f32=f32)
+    tq = np.concatenate([[0.0], np.sort(np.random.default_rng(5).uniform(0.0, 2.0, 60)), [2.0, 2.05]])
+    for alg, oalg in ((pkg.ALG_TSIT5, oracle.ALG_TSIT5), (pkg.ALG_VERN7, oracle.ALG_VERN7)):
+        prog = _everystep_prog(pkg, handle, alg, f32, "lorenz")
+        g = pkg.lowlevel.solve_host_dense(prog, U0, p, (0.0, 2.0), tq)
+        o = oracle.solve(oalg, pl.lorenz_source(f32), U0, p, (0.0, 2.0), 3, 3, f32=f32, dense_tq=tq)
+        # the GPU recomputes each step's stages, the oracle interpolates from the k arrays it stored: same bits
+        assert np.array_equal(bits(g["dense"]), bits(o["dense"]))
+        assert_same_result(g, dict(o, us=None))
+        # sol(tf): the interpolation polynomial at Θ = 1 meets the last row to rounding
+        assert np.allclose(g["dense"][:, -2], g["u_final"], rtol=1e-4 if f32 else 1e-12, atol=1e-4 if f32 else 1e-12)
+        assert (g["dense"][:, 0] == np.asarray(U0, dtype=g["dense"].dtype)).all()
+
+
+def test_dense_eval_stiff_and_accuracy(pkg, handle, oracle):
+    pl = pkg.problems_library
+    r, j, tg = pl.robertson_sources()
+    p = pl.robertson_params(512)
+    tq = np.array([0.0, 1e-3, 0.02, 0.5, 1.0, 7.5, 33.0, 99.0, 100.0])
+    for alg, oalg in ((pkg.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK23), (pkg.ALG_RODAS5P, oracle.ALG_RODAS5P)):
+        prog = _everystep_prog(pkg, handle, alg, False, "robertson")
+        g = pkg.lowlevel.solve_host_dense(prog, U0, p, (0.0, 100.0), tq, reltol=1e-6, abstol=1e-8)
+        o = oracle.solve(oalg, r, U0, p, (0.0, 100.0), 3, 3, jac=j, tgrad=tg, reltol=1e-6, abstol=1e-8, dense_tq=tq)
+        assert np.array_equal(bits(g["dense"]), bits(o["dense"]))
+        assert np.abs(g["dense"].sum(axis=2) - 1.0).max() < 1e-6               # mass conservation along sol(t)
+    # against the closed form u0 exp(1.01 t): test/Regression_I/ode_dense_tests.jl bounds (Tsit5 2e-6 at dt = 1/4)
+    s, n = linear_source()
+    prog = handle.compile(pkg.ALG_TSIT5, pkg.F64, 1, 0, s, n, extra_options=pkg._lib.OPT_EVERYSTEP)
+    tq = np.linspace(0.0, 1.0, 101)
+    g = pkg.lowlevel.solve_host_dense(prog, np.array([[0.5]]), None, (0.0, 1.0), tq, dt=0.25)
+    assert np.abs(g["dense"][0, :, 0] - 0.5 * np.exp(1.01 * tq)).max() < 2e-6
+
+
+def test_high_level_dense_solution_call(pkg, oracle):
+    """sol(t) on the default (save_everystep, no saveat) ensemble solution, and the one-pass ensemble form."""
+    P = pkg
+    pl = P.problems_library
+    N = 200
+    table = pl.lorenz_params(N)
+    prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (0.0, 2.0), table[0])
+    ep = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table))
+    s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N)
+    tq = np.array([0.0, 0.3, 0.77, 1.5, 2.0])
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (0.0, 2.0), 3, 3, dense_tq=tq)
+    allv = s.at(tq)
+    assert np.array_equal(bits(allv), bits(o["dense"]))
+    assert s[7].dense and np.array_equal(bits(s[7](tq)), bits(o["dense"][7]))
+    assert np.array_equal(bits(s[7](0.77)), bits(o["dense"][7, 2]))
+    assert np.array_equal(bits(s[7](tq[::-1].copy())), bits(o["dense"][7, ::-1]))     # unsorted queries
+    s2 = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.5)
+    with pytest.raises(NotImplementedError):
+        s2[0](0.3)

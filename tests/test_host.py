@@ -91,3 +91,19 @@ def test_synthetic_tables_are_deterministic(pkg):
     u0 = pl.pleiades_u0(50)
     assert u0.shape == (50, 28) and np.abs(u0[:, :14] - pl.PLEIADES_U0[:14]).max() <= 0.01
     assert np.array_equal(u0[:, 14:], np.tile(pl.PLEIADES_U0[14:], (50, 1)))
+
+
+def test_save_start_and_save_end_defaults(pkg):
+    # solve.jl:141-143,596-599; exercised by test/InterfaceI/ode_saveat_tests.jl:11-32
+    # (saveat = [1/2] alone gives sol.t == [1/2]; saveat = 1/2 as a Number keeps both end points)
+    f = pkg.ranges.resolve_save_flags
+    span = (0.0, 1.0)
+    assert f(None, span, True) == (True, None)                 # save_everystep: both ends
+    assert f(None, span, False) == (True, None)                # isempty(saveat)
+    assert f(0.5, span, False) == (True, None)                 # saveat isa Number
+    assert f([0.5], span, False) == (False, False)             # neither end point is in the vector
+    assert f([0.0, 0.5, 1.0], span, False) == (True, None)
+    assert f([0.5, 1.0], span, False) == (False, None)
+    assert f([0.5], span, True) == (True, None)
+    assert f([0.5], span, False, save_start=True, save_end=True) == (True, True)
+    assert f(0.5, span, False, save_end=False) == (True, False)
