@@ -61,6 +61,11 @@ extern "C" {
 
 /* extra_options of b200ode_compile that select a program variant */
 #define B200ODE_OPT_EVERYSTEP "-DB200_EVERYSTEP=1"  /* save_everystep = true: ragged per-step rows (b200ode_solve_everystep) */
+/* "-DB200_SAVE_IDXS=i0,i1,..." (0-based, no spaces): the save_idxs keyword (solve.jl; _savevalues!
+ * integrator_utils.jl:368-375).  Every saved row — `us` of b200ode_solve[_device], the ragged rows, the mean/var
+ * statistics — then holds only the listed components, in that order: replace n by the list length in those
+ * shapes.  u_final stays the full state.  Not combinable with dense output. */
+#define B200ODE_OPT_SAVE_IDXS_PREFIX "-DB200_SAVE_IDXS="
 
 typedef struct b200ode_handle_s* b200ode_handle;     /* one per process per GPU */
 typedef struct b200ode_program_s* b200ode_program;   /* one per (alg, dtype, n, np, RHS source) */

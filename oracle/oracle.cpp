@@ -322,6 +322,8 @@ template <typename R> struct Out {
     // dense = true: every saved row also keeps the stepper cache (its k array), the way sol.k does
     // (integrator_utils.jl:455-473); points to a DenseSink<R, Alg> owned by dense_one
     void* dense_sink = nullptr;
+    // save_idxs (0-based): saved rows hold only these components (integrator_utils.jl:368-375); NULL = all
+    const int* save_idxs = nullptr; int nsave = 0;
 };
 
 template <typename R, typename Alg> struct DenseSink {
@@ -348,15 +350,17 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
             for (int i = 0; i < n; ++i) sink->us.push_back(v[i]);
             sink->ks.push_back(cache);
         }
+        const int w = out.save_idxs ? out.nsave : n;       // row width
+        auto comp = [&](int i) { return out.save_idxs ? v[out.save_idxs[i]] : v[i]; };
         if (out.row_offsets) {
             if (out.us && nsaved < (int)(out.row_offsets[idx + 1] - out.row_offsets[idx])) {
                 const size_t row = (size_t)out.row_offsets[idx] + (size_t)nsaved;
-                for (int i = 0; i < n; ++i) out.us[row * n + i] = v[i];
+                for (int i = 0; i < w; ++i) out.us[row * w + i] = comp(i);
                 out.ts_rag[row] = ts;
             }
         } else if (out.us && nsaved < out.nslots) {
-            R* dst = out.us + ((size_t)idx * out.nslots + nsaved) * n;
-            for (int i = 0; i < n; ++i) dst[i] = v[i];
+            R* dst = out.us + ((size_t)idx * out.nslots + nsaved) * w;
+            for (int i = 0; i < w; ++i) dst[i] = comp(i);
         }
         nsaved += 1; last_saved_t = ts;
     };
@@ -570,6 +574,7 @@ struct OracleArgs {
     int *nsaved, *naccept, *nreject, *nf, *njacs, *nw, *nsolve, *retcode;
     // save_everystep: row_offsets == NULL is the counting pass
     int save_everystep; const long long* row_offsets; void* ts_rag;
+    const int* save_idxs; int nsave_idxs;
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -592,6 +597,10 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.save_everystep = a.save_everystep != 0;
     Out<R> out;
     out.row_offsets = a.row_offsets; out.ts_rag = (R*)a.ts_rag;
+    if (a.save_idxs && a.nsave_idxs > 0) {
+        for (int i = 0; i < a.nsave_idxs; ++i) if (a.save_idxs[i] < 0 || a.save_idxs[i] >= a.n) return -3;
+        out.save_idxs = a.save_idxs; out.nsave = a.nsave_idxs;
+    }
     out.u_final = (R*)a.u_final; out.t_final = (R*)a.t_final; out.us = (R*)a.us; out.nslots = a.nslots;
     out.nsaved = a.nsaved; out.naccept = a.naccept; out.nreject = a.nreject; out.nf = a.nf;
     out.njacs = a.njacs; out.nw = a.nw; out.nsolve = a.nsolve; out.retcode = a.retcode;

@@ -44,7 +44,8 @@ class OracleArgs(C.Structure):
                 ("u_final", C.c_void_p), ("t_final", C.c_void_p), ("us", C.c_void_p), ("nslots", C.c_int),
                 ("nsaved", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p), ("nf", C.c_void_p),
                 ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p),
-                ("save_everystep", C.c_int), ("row_offsets", C.c_void_p), ("ts_rag", C.c_void_p)]
+                ("save_everystep", C.c_int), ("row_offsets", C.c_void_p), ("ts_rag", C.c_void_p),
+                ("save_idxs", C.c_void_p), ("nsave_idxs", C.c_int)]
 
 
 _lib = None
@@ -119,7 +120,7 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
 
 def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
           abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
-          linsolve=0, nthreads=0, save_everystep=False, dense_tq=None):
+          linsolve=0, nthreads=0, save_everystep=False, dense_tq=None, save_idxs=None):
     """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host.
     save_everystep=True returns ragged rows (row_offsets, ts, us[total, n]) like lowlevel.solve_host_everystep."""
     L = lib()
@@ -135,9 +136,11 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     t0, tf = float(tspan[0]), float(tspan[1])
     grid = None if saveat is None or len(saveat) == 0 else np.ascontiguousarray(saveat, dtype=np.float64)
     nslots = nslots_for(t0, tf, grid, save_start, save_end)
+    idxs = None if save_idxs is None else np.ascontiguousarray(save_idxs, dtype=np.int32)
+    w = n if idxs is None else len(idxs)          # components per saved row (save_idxs, 0-based)
     out = {
         "u_final": np.zeros((N, n), dtype=rdt), "t_final": np.zeros((N,), dtype=rdt),
-        "us": np.zeros((N, nslots, n), dtype=rdt) if nslots > 0 else None,
+        "us": np.zeros((N, nslots, w), dtype=rdt) if nslots > 0 else None,
     }
     for k in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         out[k] = np.zeros((N,), dtype=np.int32)
@@ -157,6 +160,8 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     a.save_start = -1 if save_start is None else int(bool(save_start))
     a.save_end = -1 if save_end is None else int(bool(save_end))
     a.linsolve = linsolve; a.nthreads = nthreads
+    if idxs is not None:
+        a.save_idxs = idxs.ctypes.data; a.nsave_idxs = len(idxs)
     a.u_final = out["u_final"].ctypes.data; a.t_final = out["t_final"].ctypes.data
     a.us = out["us"].ctypes.data if out["us"] is not None else None
     a.nslots = nslots
@@ -182,7 +187,7 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
         offs = np.zeros((N + 1,), dtype=np.int64)
         np.cumsum(out["nsaved"], out=offs[1:])
         total = int(offs[-1])
-        us = np.zeros((max(total, 1), n), dtype=rdt)
+        us = np.zeros((max(total, 1), w), dtype=rdt)
         ts = np.zeros((max(total, 1),), dtype=rdt)
         a.us = us.ctypes.data; a.row_offsets = offs.ctypes.data; a.ts_rag = ts.ctypes.data
         rc = L.oracle_solve(C.byref(a))

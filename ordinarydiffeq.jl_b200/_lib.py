@@ -70,6 +70,11 @@ class B200Ragged(C.Structure):
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
 
 
+def opt_save_idxs(idxs):
+    """extra_options token selecting the saved components (0-based)."""
+    return "-DB200_SAVE_IDXS=" + ",".join(str(int(i)) for i in idxs)
+
+
 # every symbol include/b200ode.h declares (tests/test_abi.py checks the export list)
 EXPORTS = [
     "b200ode_create", "b200ode_destroy", "b200ode_last_error", "b200ode_version",
@@ -195,6 +200,10 @@ class Program:
         self.handle = handle
         self.alg, self.dtype, self.n, self.np = alg, dtype, n, np_
         self.everystep = bool(extra_options) and OPT_EVERYSTEP in extra_options
+        self.nsave = n               # components per saved row
+        for tok in (extra_options or "").split():
+            if tok.startswith("-DB200_SAVE_IDXS="):
+                self.nsave = len(tok.split("=", 1)[1].split(","))
         self._p = C.c_void_p()
         check(lib().b200ode_compile(handle._h, C.byref(self._p), alg, dtype, n, np_, _b(rhs_src), _b(rhs_name),
                                     _b(jac_src), _b(jac_name), _b(tgrad_src), _b(tgrad_name), _b(extra_options)))

@@ -109,6 +109,7 @@ struct b200ode_program_s {
     int sliced_g = 0;            // > 0: component-sliced kernel with this many warps per 32 trajectories
     int sliced_k = 1;            // groups of 32 trajectories per CTA
     bool everystep = false;      // compiled with -DB200_EVERYSTEP=1 (ragged save_everystep output)
+    int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
     B200ProgramInfo info{};
 };
@@ -140,6 +141,25 @@ bool is_identifier(const char* s) {
     for (const char* c = s; *c; ++c)
         if (!(isalnum((unsigned char)*c) || *c == '_')) return false;
     return true;
+}
+
+// -DB200_SAVE_IDXS=i0,i1,...  -> number of listed components (0: option absent, -1: malformed / out of range)
+int parse_save_idxs(const char* extra_options, int n) {
+    const char* key = "-DB200_SAVE_IDXS=";
+    const char* at = extra_options ? strstr(extra_options, key) : nullptr;
+    if (!at) return 0;
+    at += strlen(key);
+    int count = 0;
+    while (*at && *at != ' ') {
+        if (!isdigit((unsigned char)*at)) return -1;
+        long v = 0;
+        while (isdigit((unsigned char)*at)) { v = v * 10 + (*at - '0'); if (v > 100000) return -1; ++at; }
+        if (v >= n) return -1;
+        ++count;
+        if (*at == ',') { ++at; if (!isdigit((unsigned char)*at)) return -1; }
+        else if (*at && *at != ' ') return -1;
+    }
+    return count > 0 ? count : -1;
 }
 
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
@@ -575,6 +595,10 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
                          extra_options, prog->cubin, log, &ms, &prog->sliced_g);
     if (rc) { delete prog; return rc; }
     prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
+    prog->nsave = parse_save_idxs(extra_options, n);
+    if (prog->nsave < 0) { delete prog; return fail(B200ODE_EINVAL, "-DB200_SAVE_IDXS= must list 0-based component indices below n, comma separated"); }
+    if (prog->nsave == 0) prog->nsave = n;
+    if (prog->nsave != n && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_idxs is not available in the sliced kernel"); }
     if (prog->everystep && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_everystep is not available in the sliced kernel"); }
     if (prog->sliced_g > 0) {
         prog->sliced_k = prog->sliced_g / 1000;
@@ -586,7 +610,8 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&prog->k_initdt, prog->lib, "b200_initdt");
-    if (e == cudaSuccess && prog->everystep) e = cudaLibraryGetKernel(&prog->k_dense, prog->lib, "b200_dense_eval");
+    if (e == cudaSuccess && prog->everystep && prog->nsave == n)
+        e = cudaLibraryGetKernel(&prog->k_dense, prog->lib, "b200_dense_eval");
     if (e != cudaSuccess) {
         cudaLibraryUnload(prog->lib); delete prog;
         return fail(B200ODE_ECUDA, std::string("cudaLibraryGetKernel: ") + cudaGetErrorString(e));
@@ -730,7 +755,7 @@ static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Probl
     for (long long i = 0; i < N; ++i) { offs[(size_t)i] = total; total += counts[(size_t)i]; }
     offs[(size_t)N] = total;
     const size_t rows = (size_t)std::max<int64_t>(total, 1);
-    CUDA_TRY(h->out_us.ensure(rs * (size_t)n * rows));
+    CUDA_TRY(h->out_us.ensure(rs * (size_t)prog->nsave * rows));
     CUDA_TRY(h->scratch_t.ensure(rs * rows));
     CUDA_TRY(h->rag_dts.ensure(rs * rows));
     CUDA_TRY(cudaMemcpyAsync(h->row_offsets.ptr, offs.data(), sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
@@ -794,7 +819,7 @@ int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Pr
     const long long N = hp->trajectories;
     if (N == 0) return B200ODE_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    const int n = prog->n;
+    const int n = prog->nsave;      // row width
     const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
     cudaStream_t s = h->stream;
     std::vector<int64_t> offs;
@@ -875,6 +900,7 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
     if (rc) return rc;
     if (o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "dense output excludes saveat (dense = save_everystep && isempty(saveat), solve.jl:139)");
     if (o->save_start == 0) return fail(B200ODE_EINVAL, "dense output needs save_start");
+    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available together with save_idxs");
     for (int j = 1; j < nq; ++j) if (!(tq[j] >= tq[j - 1])) return fail(B200ODE_EINVAL, "tq must be ascending");
     const long long N = hp->trajectories;
     if (N == 0) return B200ODE_OK;
@@ -940,7 +966,8 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
     CUDA_TRY(h->out_uf.ensure(rs * n * (size_t)N));
     CUDA_TRY(h->out_tf.ensure(rs * (size_t)N));
     CUDA_TRY(h->out_i32.ensure(sizeof(int32_t) * 8 * (size_t)N));
-    size_t us_bytes = rs * (size_t)n * (size_t)nslots * (size_t)N;
+    const int nsave = prog->nsave;
+    size_t us_bytes = rs * (size_t)nsave * (size_t)nslots * (size_t)N;
     if (nslots > 0) CUDA_TRY(h->out_us.ensure(us_bytes));
 
     int32_t* i32 = (int32_t*)h->out_i32.ptr;
@@ -957,7 +984,7 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
         if (chunk < 65536) chunk = 65536;
     }
     CUDA_TRY(cudaEventRecord(h->ev1, s));
-    const size_t row_bytes = rs * (size_t)n * (size_t)nslots;
+    const size_t row_bytes = rs * (size_t)nsave * (size_t)nslots;
     for (long long c0 = 0; c0 < N; c0 += chunk) {
         const long long cn = std::min(chunk, N - c0);
         B200DeviceProblem dp{};
@@ -990,13 +1017,13 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
     }
     if (stats_only) {
         // statistics on the device; only 2 * nslots * n doubles go back
-        CUDA_TRY(h->stat_out.ensure(sizeof(double) * 2 * (size_t)nslots * n));
+        CUDA_TRY(h->stat_out.ensure(sizeof(double) * 2 * (size_t)nslots * nsave));
         double* dmean = (double*)h->stat_out.ptr;
-        double* dvar = dmean + (size_t)nslots * n;
-        rc = b200ode_timeseries_meanvar_device(h, prog->dtype, h->out_us.ptr, N, nslots, n, dmean, var ? dvar : nullptr, s);
+        double* dvar = dmean + (size_t)nslots * nsave;
+        rc = b200ode_timeseries_meanvar_device(h, prog->dtype, h->out_us.ptr, N, nslots, nsave, dmean, var ? dvar : nullptr, s);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(mean, dmean, sizeof(double) * (size_t)nslots * n, cudaMemcpyDeviceToHost, s));
-        if (var) CUDA_TRY(cudaMemcpyAsync(var, dvar, sizeof(double) * (size_t)nslots * n, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(mean, dmean, sizeof(double) * (size_t)nslots * nsave, cudaMemcpyDeviceToHost, s));
+        if (var) CUDA_TRY(cudaMemcpyAsync(var, dvar, sizeof(double) * (size_t)nslots * nsave, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaEventRecord(h->ev2, s));
 

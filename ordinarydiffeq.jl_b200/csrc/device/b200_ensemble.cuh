@@ -99,11 +99,25 @@ struct B200Params {
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
 
+// save_idxs (solve.jl kwarg; _savevalues! integrator_utils.jl:368-375, ode_interpolant(Θ, integrator, idxs, ...)):
+// -DB200_SAVE_IDXS=i0,i1,... (0-based) makes every saved row hold only those components, in that order.
+// A compile-time list keeps the state in registers (no dynamic indexing of u[]).
+#ifdef B200_SAVE_IDXS
+template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...(I); };
+#define B200_SAVE_TAB_DECL constexpr int b200_save_tab[] = {B200_SAVE_IDXS};
+#define B200_NSAVE (B200IdxList<B200_SAVE_IDXS>::n)
+#define B200_SAVE_COMP(c) b200_save_tab[c]
+#else
+#define B200_SAVE_TAB_DECL
+#define B200_NSAVE B200_N
+#define B200_SAVE_COMP(c) (c)
+#endif
+
 #ifndef B200_EVERYSTEP
 #define B200_EVERYSTEP 0      // 1: save_everystep = true (integrator_utils.jl:385-411), ragged rows
 #endif
-#if B200_EVERYSTEP && B200_SLICED
-#error "save_everystep is not available in the component-sliced kernel"
+#if (B200_EVERYSTEP || defined(B200_SAVE_IDXS)) && B200_SLICED
+#error "save_everystep / save_idxs are not available in the component-sliced kernel"
 #endif
 
 #ifndef B200_BLOCK
@@ -219,11 +233,12 @@ struct B200Traj {
 };
 
 B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, const real* v, real dt_stages = (real)0) {
+    B200_SAVE_TAB_DECL
 #if B200_EVERYSTEP
     if (T.nsaved < T.cap) {
 #pragma unroll
-        for (int c = 0; c < B200_N; ++c) T.row[c] = v[c];
-        T.row += B200_N;
+        for (int c = 0; c < B200_NSAVE; ++c) T.row[c] = v[B200_SAVE_COMP(c)];
+        T.row += B200_NSAVE;
         *T.trow++ = ts;
         *T.drow++ = dt_stages;
     }
@@ -231,8 +246,8 @@ B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, 
 #else
     if (T.nsaved < P.nslots) {              // nslots == 0: no time series requested
 #pragma unroll
-        for (int c = 0; c < B200_N; ++c) T.row[c] = v[c];
-        T.row += B200_N;
+        for (int c = 0; c < B200_NSAVE; ++c) T.row[c] = v[B200_SAVE_COMP(c)];
+        T.row += B200_NSAVE;
     }
 #endif
     T.nsaved += 1;
@@ -267,12 +282,12 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     if (P.row_offsets != nullptr) {
         const long long o = P.row_offsets[idx];
         T.cap = (int)(P.row_offsets[idx + 1] - o);
-        T.row = P.us + (size_t)o * B200_N;
+        T.row = P.us + (size_t)o * B200_NSAVE;
         T.trow = P.ts_rag + o;
         T.drow = P.dts_rag + o;
     }
 #else
-    T.row = P.us + (size_t)idx * (size_t)P.nslots * B200_N;
+    T.row = P.us + (size_t)idx * (size_t)P.nslots * B200_NSAVE;
 #endif
     if (P.save_start) b200_emit(P, idx, T, T.t, T.u);      // solve.jl:809-824
     T.st.init(T.u, T.p, T.t, T.nf);                   // initialize!(integrator, cache)
@@ -427,8 +442,8 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 // cold path (failed trajectories only): kept out of line so it costs the hot loop no registers
 __device__ __noinline__ void b200_zero_rows(real* us, long long idx, int from, int nslots) {
     for (int s = from; s < nslots; ++s) {
-        real* dst = us + ((size_t)idx * (size_t)nslots + (size_t)s) * B200_N;
-        for (int c = 0; c < B200_N; ++c) dst[c] = (real)0;
+        real* dst = us + ((size_t)idx * (size_t)nslots + (size_t)s) * B200_NSAVE;
+        for (int c = 0; c < B200_NSAVE; ++c) dst[c] = (real)0;
     }
 }
 
@@ -562,7 +577,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
         }
     }
 }
-#if B200_EVERYSTEP
+#if B200_EVERYSTEP && !defined(B200_SAVE_IDXS)      // (rows restricted by save_idxs cannot restart a step)
 // ---------------------------------------------------------------------------
 // sol(tq) for every trajectory, post hoc, from the ragged per-step rows — ode_interpolation
 // (dense/generic_dense.jl:833-867: interval search :845-849, dt = ts[i+] - ts[i-], Θ :858-859,

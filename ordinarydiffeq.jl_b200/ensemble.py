@@ -196,8 +196,8 @@ class ODESolution:
 class _LazySolutions:
     """Vector{ODESolution} over the flat result arrays (materialised per index on demand)."""
 
-    def __init__(self, res, t0, alg, has_grid, u0=None, save_start=True, save_end=True, dense=None):
-        self.res, self.t0, self.alg, self.has_grid = res, t0, alg, has_grid
+    def __init__(self, res, t0, alg, has_grid, u0=None, save_start=True, save_end=True, dense=None, save_idxs=None):
+        self.res, self.t0, self.alg, self.has_grid, self.save_idxs = res, t0, alg, has_grid, save_idxs
         self.u0, self.save_start, self.save_end = u0, save_start, save_end
         self.dense = dense      # callable (i, tq ascending) -> [len(tq), n], or None
 
@@ -221,12 +221,13 @@ class _LazySolutions:
         else:
             # save_everystep = false and no saveat: sol.t = [t0, t_end] (save_start / save_end)
             ts, us = [], []
+            sel = (lambda v: v) if self.save_idxs is None else (lambda v: np.asarray(v)[self.save_idxs])
             if self.save_start:
                 ts.append(self.t0)
-                us.append(self.u0 if self.u0.ndim == 1 else self.u0[i])
+                us.append(sel(self.u0 if self.u0.ndim == 1 else self.u0[i]))
             if self.save_end:
                 ts.append(r["t_final"][i])
-                us.append(r["u_final"][i])
+                us.append(sel(r["u_final"][i]))
             t = np.array(ts)
             u = np.stack(us) if us else np.zeros((0, r["u_final"].shape[1]), dtype=r["u_final"].dtype)
         st = DEStats(r["nf"][i], r["naccept"][i], r["nreject"][i], r["njacs"][i], r["nw"][i], r["nsolve"][i])
@@ -258,7 +259,7 @@ class EnsembleSolution:
 
 
 # ---- solve ------------------------------------------------------------------------------------
-_ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "reltol",
+_ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "save_idxs", "reltol",
                "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags"}
 _program_cache = {}
 _handles = {}
@@ -273,14 +274,20 @@ def _handle(device):
     return _handles[device]
 
 
-def get_program(handle, alg, fn, n, np_, f32, everystep=False):
+def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
-    key = (handle.device, alg.alg_id, f32, n, np_, rhs, jac, tg, everystep)
+    extra = []
+    if everystep:
+        extra.append(_lib.OPT_EVERYSTEP)
+    if save_idxs is not None:
+        extra.append(_lib.opt_save_idxs(save_idxs))
+    extra = " ".join(extra) or None
+    key = (handle.device, alg.alg_id, f32, n, np_, rhs, jac, tg, extra)
     if key not in _program_cache:
         _program_cache[key] = handle.compile(alg.alg_id, _lib.F32 if f32 else _lib.F64, n, np_, rhs[0], rhs[1],
                                              jac[0] if jac else None, jac[1] if jac else None,
                                              tg[0] if tg else None, tg[1] if tg else None,
-                                             extra_options=_lib.OPT_EVERYSTEP if everystep else None)
+                                             extra_options=extra)
     return _program_cache[key]
 
 
@@ -340,7 +347,13 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     np_ = 0 if prob.p is None else int(np.asarray(prob.p).shape[-1])
     grid = ranges.saveat_grid(kw.get("saveat", None), prob.tspan)
     handle = _handle(ensemblealg.device)
-    program = get_program(handle, alg, prob.f, n, np_, f32, everystep)
+    # save_idxs: component indices of the saved rows, 0-based here (the Julia binding converts from 1-based)
+    save_idxs = kw.get("save_idxs", None)
+    if save_idxs is not None:
+        save_idxs = [int(i) for i in (save_idxs if hasattr(save_idxs, "__len__") else [save_idxs])]
+        if not save_idxs or min(save_idxs) < 0 or max(save_idxs) >= n:
+            raise ValueError("save_idxs out of range for a state of length %d" % n)
+    program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs)
     save_start, save_end = ranges.resolve_save_flags(kw.get("saveat", None), prob.tspan, everystep,
                                                      kw.get("save_start"), kw.get("save_end"))
 
@@ -353,7 +366,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
         return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
 
-    dense_ok = everystep and not grid and save_start      # dense = save_everystep && isempty(saveat) (solve.jl:144)
+    dense_ok = everystep and not grid and save_start and save_idxs is None      # dense = save_everystep && isempty(saveat) (solve.jl:144)
     tol_kw = dict(reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
                   dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"))
 
@@ -379,7 +392,8 @@ def solve(eprob, alg, ensemblealg=None, **kw):
         all_arrays.append(res)
         mk = lambda r, u0_, p_=None: _LazySolutions(r, prob.tspan[0], alg, bool(grid), np.asarray(u0_),
                                                     save_start, save_end is None or save_end,
-                                                    dense=dense_of(u0_, p_) if dense_ok else None)
+                                                    dense=dense_of(u0_, p_) if dense_ok else None,
+                                                    save_idxs=save_idxs)
         batches_in.append((u0, p, len(I)))
         sols = mk(res, u0, p)
         if output_func is None:

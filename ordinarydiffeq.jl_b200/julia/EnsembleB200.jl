@@ -47,6 +47,11 @@ mutable struct B200Result
     kernel_ms::Float64; total_ms::Float64
 end
 
+struct B200Ragged            # save_everystep rows (b200ode_solve_everystep); buffers are released with b200ode_free
+    total_rows::Int64
+    row_offsets::Ptr{Int64}; ts::Ptr{Float64}; us::Ptr{Cvoid}
+end
+
 alg_id(::Tsit5) = 1; alg_id(::Vern7) = 2; alg_id(::Rosenbrock23) = 3; alg_id(::Rodas5P) = 4
 isstiff(alg) = alg isa Union{Rosenbrock23, Rodas5P}
 const RETCODES = (ReturnCode.Default, ReturnCode.Success, ReturnCode.MaxIters, ReturnCode.DtLessThanMin,
@@ -84,7 +89,7 @@ function handle(dev)
     end
 end
 
-const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :reltol, :abstol,
+const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :reltol, :abstol,
                  :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense)
 
 function __solve(eprob::AbstractEnsembleProblem, alg::Union{Tsit5, Vern7, Rosenbrock23, Rodas5P}, ens::EnsembleB200;
@@ -101,16 +106,22 @@ function __solve(eprob::AbstractEnsembleProblem, alg::Union{Tsit5, Vern7, Rosenb
     saveat = get(kw, :saveat, ())
     grid = saveat isa Number ? collect(Float64, (t0 + abs(saveat)):abs(saveat):tf) :
            sort!(Float64[s for s in saveat if t0 < s <= tf])
-    get(kw, :save_everystep, isempty(grid)) && throw(ArgumentError("save_everystep=true is not supported; pass saveat or save_everystep=false"))
+    everystep = get(kw, :save_everystep, isempty(grid))            # solve.jl:138
     n, np, rhs, jac, tgr = c_sources(prob, alg, T)
+    idxs = get(kw, :save_idxs, nothing)
+    idxs isa Integer && (idxs = [idxs])
+    w = idxs === nothing ? n : length(idxs)                        # components per saved row
+    extra = String[]
+    everystep && push!(extra, "-DB200_EVERYSTEP=1")
+    idxs === nothing || push!(extra, "-DB200_SAVE_IDXS=" * join(idxs .- 1, ","))   # the C side is 0-based
+    extra_opt = isempty(extra) ? C_NULL : join(extra, " ")
     h = handle(ens.device)
     prog = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:b200ode_compile, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring),
                 h, prog, alg_id(alg), T === Float32 ? 1 : 0, n, np, rhs, "diffeqf",
-                jac === nothing ? C_NULL : jac, "diffeqjac", tgr === nothing ? C_NULL : tgr, "diffeqtgrad", C_NULL))
+                jac === nothing ? C_NULL : jac, "diffeqjac", tgr === nothing ? C_NULL : tgr, "diffeqtgrad", extra_opt))
     # defaults of solve.jl:141-143,596-599 (the C ABI only sees the expanded grid)
-    everystep = get(kw, :save_everystep, isempty(grid))
     dflt(tend) = everystep || isempty(saveat) || saveat isa Number || tend in saveat
     ss = something(get(kw, :save_start, nothing), dflt(prob.tspan[1]))
     se = get(kw, :save_end, nothing)
@@ -135,24 +146,42 @@ function __solve(eprob::AbstractEnsembleProblem, alg::Union{Tsit5, Vern7, Rosenb
         cprob = B200Problem(N, pointer(U0), 0, pointer(P), 0, t0, tf)
         nslots = ccall((:b200ode_nslots, LIB), Cint, (Ref{B200Problem}, Ref{B200Opts}), cprob, opts)
         uf = Matrix{T}(undef, n, N); tfin = Vector{Float64}(undef, N)
-        us = Array{T, 3}(undef, n, max(nslots, 1), N); ts = Vector{Float64}(undef, max(nslots, 1))
+        us = Array{T, 3}(undef, w, max(nslots, 1), N); ts = Vector{Float64}(undef, max(nslots, 1))
         cnt = [Vector{Int32}(undef, N) for _ in 1:8]
         res = B200Result(pointer(uf), pointer(tfin), nslots > 0 ? pointer(us) : C_NULL, pointer(ts),
                          pointer.(cnt)..., 0.0, 0.0)
+        rag = Ref(B200Ragged(0, C_NULL, C_NULL, C_NULL))
         GC.@preserve U0 P grid uf tfin us ts cnt begin
-            check(ccall((:b200ode_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}),
-                        h, prog[], cprob, opts, res))
+            if everystep     # ragged rows: trajectory k owns rows offs[k]+1 : offs[k+1]
+                check(ccall((:b200ode_solve_everystep, LIB), Cint,
+                            (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}, Ref{B200Ragged}),
+                            h, prog[], cprob, opts, res, rag))
+            else
+                check(ccall((:b200ode_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}),
+                            h, prog[], cprob, opts, res))
+            end
         end
         nsaved, naccept, nreject, nf, njacs, nw, nsolve, rc = cnt
+        offs = everystep ? unsafe_wrap(Array, rag[].row_offsets, N + 1) : Int64[]
+        rts = everystep ? unsafe_wrap(Array, rag[].ts, rag[].total_rows) : Float64[]
+        rus = everystep ? unsafe_wrap(Array, Ptr{T}(rag[].us), (w, Int(rag[].total_rows))) : Matrix{T}(undef, 0, 0)
+        sel(v) = idxs === nothing ? v : v[idxs]
         batch = map(1:N) do k
-            tk = nslots > 0 ? ts[1:nsaved[k]] : [t0, tfin[k]]
-            uk = nslots > 0 ? [SVector{n, T}(us[:, s, k]) for s in 1:nsaved[k]] : [SVector{n, T}(U0[:, k]), SVector{n, T}(uf[:, k])]
+            tk = everystep ? rts[(offs[k] + 1):offs[k + 1]] : nslots > 0 ? ts[1:nsaved[k]] : [t0, tfin[k]]
+            uk = everystep ? [SVector{w, T}(rus[:, r]) for r in (offs[k] + 1):offs[k + 1]] :
+                 nslots > 0 ? [SVector{w, T}(us[:, s, k]) for s in 1:nsaved[k]] :
+                 [SVector{w, T}(sel(U0[:, k])), SVector{w, T}(sel(uf[:, k]))]
             stats = SciMLBase.DEStats(Int(nf[k]), 0, 0, Int(nw[k]), Int(nsolve[k]), Int(njacs[k]), 0, 0, 0, 0,
                                       Int(naccept[k]), Int(nreject[k]), 0.0)
             sol = build_solution(prob, alg, tk, uk; dense = false, stats, retcode = RETCODES[rc[k] + 1])
             out, rerun = eprob.output_func(sol, SciMLBase.EnsembleContext(I[k], 1, nothing))
             rerun && error("rerun is served by re-submitting the trajectory; see ensemble.py for the loop")
             out
+        end
+        if everystep
+            for ptr in (rag[].row_offsets, rag[].ts, rag[].us)
+                ccall((:b200ode_free, LIB), Cvoid, (Ptr{Cvoid},), ptr)
+            end
         end
         u, converged = eprob.reduction(u, batch, I)
         converged && break

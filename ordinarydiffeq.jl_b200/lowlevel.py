@@ -72,13 +72,13 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     res.t_final = buf("t_final", (N,), np.float64).ctypes.data
     if nslots > 0:
         if _meanvar is None:
-            res.us = buf("us", (N, nslots, n), rdt).ctypes.data
+            res.us = buf("us", (N, nslots, program.nsave), rdt).ctypes.data
         res.ts = buf("ts", (nslots,), np.float64).ctypes.data
     for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         setattr(res, name, buf(name, (N,), np.int32).ctypes.data)
     if _meanvar is not None:
-        mean = buf("mean", (nslots, n), np.float64)
-        var = buf("var", (nslots, n), np.float64) if _meanvar[1] else None
+        mean = buf("mean", (nslots, program.nsave), np.float64)
+        var = buf("var", (nslots, program.nsave), np.float64) if _meanvar[1] else None
         _lib.check(L.b200ode_solve_meanvar(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res),
                                            C.c_void_p(mean.ctypes.data), C.c_void_p(var.ctypes.data) if var is not None else None))
     else:
@@ -163,10 +163,11 @@ def solve_host_everystep(program, u0, p, tspan, trajectories=None, reltol=None, 
         if total > 0:
             out["ts"] = np.ctypeslib.as_array(C.cast(rag.ts, C.POINTER(C.c_double)), (total,)).copy()
             ct = C.c_float if rdt == np.float32 else C.c_double
-            out["us"] = np.ctypeslib.as_array(C.cast(rag.us, C.POINTER(ct)), (total * n,)).reshape(total, n).copy()
+            w = program.nsave
+            out["us"] = np.ctypeslib.as_array(C.cast(rag.us, C.POINTER(ct)), (total * w,)).reshape(total, w).copy()
         else:
             out["ts"] = np.zeros((0,), dtype=np.float64)
-            out["us"] = np.zeros((0, n), dtype=rdt)
+            out["us"] = np.zeros((0, program.nsave), dtype=rdt)
     finally:
         for ptr in (rag.row_offsets, rag.ts, rag.us):
             if ptr:
@@ -206,7 +207,7 @@ class DeviceBuffers:
         self.p = torch.empty(shape_p, dtype=rt, device=device)
         self.u_final = torch.empty((N, n) if layout == _lib.LAYOUT_AOS else (n, N), dtype=rt, device=device)
         self.t_final = torch.empty((N,), dtype=rt, device=device)
-        self.us = torch.empty((N, nslots, n), dtype=rt, device=device) if nslots > 0 else None
+        self.us = torch.empty((N, nslots, program.nsave), dtype=rt, device=device) if nslots > 0 else None
         self.i32 = torch.zeros((8, N), dtype=torch.int32, device=device)
         names = ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode")
         for k, name in enumerate(names):

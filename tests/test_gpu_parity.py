@@ -531,3 +531,50 @@ def test_high_level_dense_solution_call(pkg, oracle):
     s2 = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.5)
     with pytest.raises(NotImplementedError):
         s2[0](0.3)
+
+
+# ---- save_idxs ---------------------------------------------------------------
+@pytest.mark.parametrize("f32", [False, True])
+def test_save_idxs_rows(pkg, handle, oracle, f32):
+    N = 3000
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N, f32=f32)
+    dt = pkg.F32 if f32 else pkg.F64
+    s, n = pl.lorenz_source(f32)
+    idxs = [2, 0]
+    prog = handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n, extra_options=pkg._lib.opt_save_idxs(idxs))
+    g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 10.0), saveat=GRID)
+    o = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 10.0), 3, 3, f32=f32, saveat=GRID, save_idxs=idxs)
+    assert g["us"].shape == (N, 101, 2)
+    assert_same_result(g, o)
+    full = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 10.0), 3, 3, f32=f32, saveat=GRID)
+    assert np.array_equal(bits(g["us"]), bits(np.ascontiguousarray(full["us"][:, :, idxs])))
+    # statistics over the selected components only
+    mv = pkg.lowlevel.solve_host_meanvar(prog, U0, p, (0.0, 10.0), GRID)
+    assert mv["mean"].shape == (101, 2)
+    assert np.allclose(mv["mean"], o["us"].astype(np.float64).mean(axis=0), rtol=1e-5 if f32 else 1e-12)
+    # ragged rows
+    prog2 = handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n,
+                           extra_options=pkg._lib.opt_save_idxs([1]) + " " + pkg._lib.OPT_EVERYSTEP)
+    g2 = pkg.lowlevel.solve_host_everystep(prog2, U0, p, (0.0, 2.0))
+    o2 = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 2.0), 3, 3, f32=f32, save_everystep=True, save_idxs=[1])
+    assert g2["us"].shape[1] == 1
+    _assert_same_ragged(g2, o2)
+    with pytest.raises(pkg.B200Error):                    # dense output needs whole rows
+        pkg.lowlevel.solve_host_dense(prog2, U0, p, (0.0, 2.0), [0.5])
+    with pytest.raises(pkg.B200Error):                    # index out of range
+        handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n, extra_options="-DB200_SAVE_IDXS=3")
+
+
+def test_high_level_save_idxs(pkg, oracle):
+    P = pkg
+    pl = P.problems_library
+    N = 100
+    table = pl.lorenz_params(N)
+    prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (0.0, 10.0), table[0])
+    ep = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table))
+    s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.1, save_idxs=[0])
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (0.0, 10.0), 3, 3, saveat=GRID, save_idxs=[0])
+    assert s[5].u.shape == (101, 1) and np.array_equal(bits(np.ascontiguousarray(s[5].u)), bits(o["us"][5]))
+    s2 = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, save_everystep=False, save_idxs=[2, 1])
+    assert s2[5].u.shape == (2, 2) and np.array_equal(s2[5].u[-1], o["u_final"][5][[2, 1]])
