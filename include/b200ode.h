@@ -117,8 +117,8 @@ typedef struct {
     int32_t* nsolve;
     int32_t* retcode;
     double kernel_ms;     /* out: compute-stream time from the first kernel launch to the last kernel's end (CUDA
-                             events).  With a saveat grid the launches are chunked and interleaved with D2H copies;
-                             with pageable (unpinned) host buffers those copies stall the launches and are included. */
+                             events).  With a saveat grid the launches are chunked; the D2H copies of finished chunks
+                             run on a second stream and are not part of this figure. */
     double total_ms;      /* out: device time including H2D/D2H copies */
 } B200Result;
 

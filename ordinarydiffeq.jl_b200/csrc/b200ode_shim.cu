@@ -19,6 +19,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device_sources.inc"   // k_b200_header_names[], k_b200_header_sources[], k_b200_num_headers
@@ -98,6 +99,9 @@ struct b200ode_handle_s {
     std::vector<double> saveat_cached;   // grid currently resident in `saveat` ...
     int saveat_cached_dtype = -1;        // ... in this real type
     DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out;
+    // pinned bounce buffers for large D2H copies into pageable caller memory (d2h_large)
+    void* stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 struct b200ode_program_s {
@@ -556,6 +560,7 @@ int b200ode_destroy(b200ode_handle h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { if (h->stage[i]) cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     delete h;
     return B200ODE_OK;
 }
@@ -709,6 +714,52 @@ int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const
     return launch_solve<double>(h, prog, dp, o, dr, s, (const long long*)row_offsets, ts, dts);
 }
 
+// Large device->host copy on stream `s`.  Pinned / registered destinations get one asynchronous copy.
+// Pageable destinations (plain malloc / numpy memory) would make the driver bounce through its own small
+// staging buffer at 2-5 GB/s; instead the copy is pipelined through two pinned 32 MiB buffers owned by the
+// handle, with the pinned->pageable memcpy of chunk i (4 host threads) overlapping the DMA of chunk i+1.
+// Blocking in the pageable case.
+static const size_t kStageBytes = 32u << 20;
+static void parallel_memcpy(char* dst, const char* src, size_t bytes) {
+    const int T = 4;
+    if (bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    std::thread th[T];
+    size_t per = (bytes + T - 1) / T;
+    for (int i = 0; i < T; ++i) {
+        size_t o = std::min(bytes, per * i), len = std::min(per, bytes - o);
+        th[i] = std::thread([=] { if (len) memcpy(dst + o, src + o, len); });
+    }
+    for (int i = 0; i < T; ++i) th[i].join();
+}
+static int d2h_large(b200ode_handle h, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return B200ODE_OK;
+    cudaPointerAttributes attr{};
+    bool pinned = (cudaPointerGetAttributes(&attr, dst) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();     // an unregistered pointer may leave a sticky-less error on old drivers
+    if (pinned || bytes < (16u << 20)) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        return B200ODE_OK;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (!h->stage[i]) CUDA_TRY(cudaHostAlloc(&h->stage[i], kStageBytes, cudaHostAllocDefault));
+        if (!h->stage_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+    }
+    const size_t nchunks = (bytes + kStageBytes - 1) / kStageBytes;
+    for (size_t c = 0; c <= nchunks; ++c) {
+        if (c < nchunks) {
+            const size_t o = c * kStageBytes, len = std::min(kStageBytes, bytes - o);
+            CUDA_TRY(cudaMemcpyAsync(h->stage[c & 1], (const char*)src + o, len, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaEventRecord(h->stage_ev[c & 1], s));
+        }
+        if (c >= 1) {
+            const size_t o = (c - 1) * kStageBytes, len = std::min(kStageBytes, bytes - o);
+            CUDA_TRY(cudaEventSynchronize(h->stage_ev[(c - 1) & 1]));
+            parallel_memcpy((char*)dst + o, (const char*)h->stage[(c - 1) & 1], len);
+        }
+    }
+    return B200ODE_OK;
+}
+
 // H2D, counting pass, host exclusive scan, fill pass.  Leaves the ragged rows in the handle's device
 // buffers (out_us, scratch_t = ts, rag_dts, row_offsets) and the scalars in out_uf/out_tf/out_i32.
 static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o,
@@ -833,12 +884,11 @@ int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Pr
     if (!offs_host || !ts_host || !us_host) return bail(fail(B200ODE_EINVAL, "out of host memory"));
     memcpy(offs_host, offs.data(), sizeof(int64_t) * ((size_t)N + 1));
     std::vector<char> ts_raw;
-    cudaError_t e = cudaMemcpyAsync(us_host, h->out_us.ptr, rs * (size_t)n * (size_t)total, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) {
-        if (rs == 8) e = cudaMemcpyAsync(ts_host, h->scratch_t.ptr, 8 * (size_t)total, cudaMemcpyDeviceToHost, s);
-        else { ts_raw.resize(4 * (size_t)std::max<int64_t>(total, 1)); e = cudaMemcpyAsync(ts_raw.data(), h->scratch_t.ptr, 4 * (size_t)total, cudaMemcpyDeviceToHost, s); }
-    }
-    if (e != cudaSuccess) return bail(fail(B200ODE_ECUDA, std::string("ragged D2H: ") + cudaGetErrorString(e)));
+    rc = d2h_large(h, us_host, h->out_us.ptr, rs * (size_t)n * (size_t)total, s);
+    if (rc) return bail(rc);
+    if (rs == 8) rc = d2h_large(h, ts_host, h->scratch_t.ptr, 8 * (size_t)total, s);
+    else { ts_raw.resize(4 * (size_t)std::max<int64_t>(total, 1)); rc = d2h_large(h, ts_raw.data(), h->scratch_t.ptr, 4 * (size_t)total, s); }
+    if (rc) return bail(rc);
     rc = everystep_finish(h, prog, N, res);
     if (rc) return bail(rc);
     if (rs == 4) for (int64_t i = 0; i < total; ++i) ts_host[i] = (double)((const float*)ts_raw.data())[i];
@@ -921,7 +971,8 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
                                    h->dense_tq.ptr, nq, h->dense_out.ptr, o, s);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev2, s));
-    CUDA_TRY(cudaMemcpyAsync(out, h->dense_out.ptr, rs * (size_t)n * (size_t)nq * (size_t)N, cudaMemcpyDeviceToHost, s));
+    rc = d2h_large(h, out, h->dense_out.ptr, rs * (size_t)n * (size_t)nq * (size_t)N, s);
+    if (rc) return rc;
     return everystep_finish(h, prog, N, res);
 }
 
@@ -1010,9 +1061,20 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
                 h->chunk_events.push_back(e);
             }
             CUDA_TRY(cudaEventRecord(h->chunk_events[ci], s));
-            CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_events[ci], 0));
-            CUDA_TRY(cudaMemcpyAsync((char*)res->us + row_bytes * (size_t)c0, (char*)h->out_us.ptr + row_bytes * (size_t)c0,
-                                     row_bytes * (size_t)cn, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+    }
+    if (!stats_only) CUDA_TRY(cudaEventRecord(h->ev2, s));     // end of the last kernel
+    if (nslots > 0 && !stats_only) {
+        // All chunks are queued; now drain them on the copy stream, each copy gated on its chunk's event.
+        // Pinned destinations: every copy is asynchronous and overlaps the kernels of later chunks.
+        // Pageable destinations: d2h_large pipelines through the handle's pinned bounce buffers (blocking),
+        // still overlapping the kernels that are already in flight.
+        for (long long c0 = 0; c0 < N; c0 += chunk) {
+            const long long cn = std::min(chunk, N - c0);
+            CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_events[(size_t)(c0 / chunk)], 0));
+            rc = d2h_large(h, (char*)res->us + row_bytes * (size_t)c0, (char*)h->out_us.ptr + row_bytes * (size_t)c0,
+                           row_bytes * (size_t)cn, h->copy_stream);
+            if (rc) return rc;
         }
     }
     if (stats_only) {
@@ -1024,8 +1086,8 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(mean, dmean, sizeof(double) * (size_t)nslots * nsave, cudaMemcpyDeviceToHost, s));
         if (var) CUDA_TRY(cudaMemcpyAsync(var, dvar, sizeof(double) * (size_t)nslots * nsave, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaEventRecord(h->ev2, s));
     }
-    CUDA_TRY(cudaEventRecord(h->ev2, s));
 
     CUDA_TRY(cudaMemcpyAsync(res->u_final, h->out_uf.ptr, rs * n * (size_t)N, cudaMemcpyDeviceToHost, s));
     std::vector<char> tf_host;
