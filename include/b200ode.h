@@ -33,6 +33,8 @@ extern "C" {
 #define B200ODE_ALG_VERN7 2        /* lib/OrdinaryDiffEqVerner/src/verner_rk_perform_step.jl:256-383 */
 #define B200ODE_ALG_ROSENBROCK23 3 /* lib/OrdinaryDiffEqRosenbrock/src/rosenbrock_perform_step.jl:249-332 */
 #define B200ODE_ALG_RODAS5P 4      /* lib/OrdinaryDiffEqRosenbrock/src/rosenbrock_perform_step.jl:431-559 */
+#define B200ODE_ALG_DP5 5          /* lib/OrdinaryDiffEqLowOrderRK/src/low_order_rk_perform_step.jl:667-710 */
+#define B200ODE_ALG_BS3 6          /* lib/OrdinaryDiffEqLowOrderRK/src/low_order_rk_perform_step.jl:13-36 */
 
 #define B200ODE_F64 0
 #define B200ODE_F32 1

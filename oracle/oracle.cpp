@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <type_traits>
 #include <vector>
 
 #ifdef _OPENMP
@@ -130,7 +131,7 @@ template <typename R> struct Fn {
     typedef void (*rhs_t)(R* du, const R* u, const R* p, const R t);
 };
 
-enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4 };
+enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4, ALG_DP5 = 5, ALG_BS3 = 6 };
 enum { RC_DEFAULT = 0, RC_SUCCESS = 1, RC_MAXITERS = 2, RC_DTLESSTHANMIN = 3, RC_UNSTABLE = 4, RC_DTNAN = 5 };
 
 template <typename R> struct Opts {
@@ -259,6 +260,9 @@ template <typename R> struct Tsit5 {
     static bool fsal_init() { return true; }
 };
 
+#if __has_include("oracle_lowrk.inc")
+#include "oracle_lowrk.inc"
+#endif
 #if __has_include("oracle_vern7.inc")
 #include "oracle_vern7.inc"
 #define ORACLE_HAVE_VERN7 1
@@ -330,6 +334,15 @@ template <typename R, typename Alg> struct DenseSink {
     std::vector<R> ts; std::vector<R> us; std::vector<Alg> ks;
 };
 
+template <typename A, typename = void> struct PIBeta {
+    static double b2() { return 2.0 / (5.0 * A::order); }
+    static double b1() { return 7.0 / (10.0 * A::order); }
+};
+template <typename A> struct PIBeta<A, std::void_t<decltype(A::beta2())>> {
+    static double b2() { return A::beta2(); }
+    static double b1() { return A::beta1(); }
+};
+
 // One trajectory: __init + solve! + postamble!
 template <typename R, typename Alg>
 static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R tf, const Opts<R>& o, long long idx,
@@ -377,7 +390,9 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     } else dt = o.dt;
     R dtpropose = dt;
     // PIControllerCache (controllers.jl:793-803) and PIController defaults (alg_utils.jl)
-    const R beta2 = (R)(2.0 / (5.0 * Alg::order)), beta1 = (R)(7.0 / (10.0 * Alg::order));
+    // beta2_default = 2//(5 order), beta1_default = 7//(10 order) (alg_utils.jl:766,788) unless the algorithm
+    // overrides them (DP5); QT(rational) = correctly rounded quotient
+    const R beta2 = (R)PIBeta<Alg>::b2(), beta1 = (R)PIBeta<Alg>::b1();
     const R qmin = (R)0.2, qmax = (R)10, gamma = (R)0.9, qoldinit = (R)1e-4, qmax_first_step = (R)10000;
     const R qsteady_min = (R)1, qsteady_max = Alg::qsteady_max();
     R q11 = (R)1, errold = qoldinit, EEst = (R)1;
@@ -615,6 +630,10 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
 #ifdef ORACLE_HAVE_ROSENBROCK
         case ALG_ROS23: solve_batch<R, Rosenbrock23<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS5P: solve_batch<R, Rodas5P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+#endif
+#ifdef ORACLE_HAVE_LOWRK
+        case ALG_DP5: solve_batch<R, DP5<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_BS3: solve_batch<R, BS3<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #endif
         default: return -2;
     }

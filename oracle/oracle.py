@@ -18,7 +18,7 @@ _LIB = os.path.join(_HERE, "liboracle.so")
 _BUILD = os.path.join(_HERE, "_build")
 
 
-ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P = 1, 2, 3, 4
+ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P, ALG_DP5, ALG_BS3 = 1, 2, 3, 4, 5, 6
 
 
 def build(force=False):

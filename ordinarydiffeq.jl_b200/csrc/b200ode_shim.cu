@@ -169,8 +169,8 @@ int parse_save_idxs(const char* extra_options, int n) {
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                           const char* jac_src, const char* jac_name, const char* tgrad_src,
                           const char* tgrad_name) {
-    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS5P)
-        return fail(B200ODE_EINVAL, "alg must be one of B200ODE_ALG_{TSIT5,VERN7,ROSENBROCK23,RODAS5P}");
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_BS3)
+        return fail(B200ODE_EINVAL, "alg must be one of B200ODE_ALG_{TSIT5,VERN7,ROSENBROCK23,RODAS5P,DP5,BS3}");
     if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
     if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");
     if (np < 0 || np > 256) return fail(B200ODE_EINVAL, "parameter dimension np must be in 0..256");
@@ -280,7 +280,8 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     }
     // measured launch shapes (scripts/sweep_dev.py): small explicit systems run best as one 512-thread
     // CTA per SM at 128 registers (FP64) / three 256-thread CTAs at 80 registers (FP32)
-    const bool small_explicit = !stiff && words <= 8 && alg == B200ODE_ALG_TSIT5;
+    const bool small_explicit = !stiff && words <= 8 &&
+                                (alg == B200ODE_ALG_TSIT5 || alg == B200ODE_ALG_DP5 || alg == B200ODE_ALG_BS3);
     if (small_explicit && !has_block && !has_minb) {
         if (dtype == B200ODE_F32) { opts.push_back("-DB200_BLOCK=256"); opts.push_back("-DB200_MINBLOCKS=3"); }
         else { opts.push_back("-DB200_BLOCK=512"); opts.push_back("-DB200_MINBLOCKS=1"); }

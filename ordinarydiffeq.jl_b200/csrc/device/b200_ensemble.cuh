@@ -20,7 +20,7 @@
 // Compile-time configuration (set by the shim before this file):
 //   B200_N, B200_NP      state / parameter dimension
 //   B200_F32             0: double, 1: float
-//   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P
+//   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -31,6 +31,8 @@
 #define B200_ALG_VERN7 2
 #define B200_ALG_ROS23 3
 #define B200_ALG_RODAS5P 4
+#define B200_ALG_DP5 5
+#define B200_ALG_BS3 6
 
 #ifndef B200_SLICED
 #define B200_SLICED 0
@@ -54,6 +56,25 @@ typedef B200Ros23 B200Stepper;
 #else
 typedef B200Rodas5P B200Stepper;
 #endif
+#elif B200_ALG == B200_ALG_DP5 || B200_ALG == B200_ALG_BS3
+#define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
+#include "b200_lowrk.cuh"
+#if B200_ALG == B200_ALG_DP5
+typedef B200DP5 B200Stepper;
+#else
+typedef B200BS3 B200Stepper;
+#endif
+#endif
+
+// PI controller exponents: beta2_default = 2//(5 order), beta1_default = 7//(10 order)
+// (OrdinaryDiffEqCore alg_utils.jl:766,788), overridden for DP5 (LowOrderRK alg_utils.jl:37-39);
+// QT(rational) is the correctly rounded quotient
+#if B200_ALG == B200_ALG_DP5
+#define B200_BETA2 ((real)(4.0 / 100.0))
+#define B200_BETA1 ((real)(17.0 / 100.0))
+#else
+#define B200_BETA2 ((real)(2.0 / (5.0 * B200Stepper::order())))
+#define B200_BETA1 ((real)(7.0 / (10.0 * B200Stepper::order())))
 #endif
 
 // ReturnCode values exported to the host (include/b200ode.h)
@@ -296,7 +317,7 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     T.dtpropose = T.dt;
     T.q11 = (real)1; T.EEst = (real)1;                            // setup_controller_cache (controllers.jl:793-803)
     {   // errold = qoldinit = 1e-4; only fastpower(errold, beta2) is ever used
-        const real beta2 = (real)(2.0 / (5.0 * B200Stepper::order()));
+        const real beta2 = B200_BETA2;
         T.fpe = b200_fastpower((real)1e-4, beta2);
         T.rfpe = (real)1 / T.fpe;
     }
@@ -312,8 +333,8 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
 // a single rejecting lane makes the warp run perform_step! twice).
 B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, unsigned amask) {
     const real qmin = (real)0.2, qmax = (real)10, gamma = (real)0.9;
-    const real beta1 = (real)(7.0 / (10.0 * B200Stepper::order()));   // QT(7//(10 order)): both are correctly rounded
-    const real beta2 = (real)(2.0 / (5.0 * B200Stepper::order()));
+    const real beta1 = B200_BETA1;
+    const real beta2 = B200_BETA2;
     // quantities of modify_dt_for_tstops! that depend only on t (t is finite here)
     // integrator.iter (before its increment) and integrator.success_iter are not stored:
     // iter = naccept + nreject and success_iter = naccept at every point they are read.

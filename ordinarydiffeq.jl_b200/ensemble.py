@@ -47,6 +47,14 @@ class Rodas5P(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS5P, 5, True
 
 
+class DP5(_Alg):            # lib/OrdinaryDiffEqLowOrderRK
+    alg_id, order = _lib.ALG_DP5, 5
+
+
+class BS3(_Alg):
+    alg_id, order = _lib.ALG_BS3, 3
+
+
 class EnsembleAlgorithm:
     pass
 
@@ -320,7 +328,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     if not isinstance(ensemblealg, EnsembleB200):
         raise NotImplementedError("only EnsembleB200() is provided (no CPU fallback)")
     if not isinstance(alg, _Alg):
-        raise TypeError("alg must be one of Tsit5(), Vern7(), Rosenbrock23(), Rodas5P()")
+        raise TypeError("alg must be one of Tsit5(), Vern7(), DP5(), BS3(), Rosenbrock23(), Rodas5P()")
     prob = eprob.prob
     kw = dict(prob.kwargs, **kw)                      # merge_problem_kwargs: solve's kwargs win
     bad = set(kw) - _ALLOWED_KW

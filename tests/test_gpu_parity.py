@@ -578,3 +578,49 @@ def test_high_level_save_idxs(pkg, oracle):
     assert s[5].u.shape == (101, 1) and np.array_equal(bits(np.ascontiguousarray(s[5].u)), bits(o["us"][5]))
     s2 = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, save_everystep=False, save_idxs=[2, 1])
     assert s2[5].u.shape == (2, 2) and np.array_equal(s2[5].u[-1], o["u_final"][5][[2, 1]])
+
+
+# ---- more steppers on the same skeleton: DP5, BS3 ----------------------------
+@pytest.mark.parametrize("alg_name", ["dp5", "bs3"])
+@pytest.mark.parametrize("f32", [False, True])
+def test_low_order_rk_parity(pkg, handle, oracle, alg_name, f32):
+    N = 3000
+    pl = pkg.problems_library
+    alg, oalg = {"dp5": (pkg.ALG_DP5, oracle.ALG_DP5), "bs3": (pkg.ALG_BS3, oracle.ALG_BS3)}[alg_name]
+    p = pl.lorenz_params(N, f32=f32)
+    s, n = pl.lorenz_source(f32)
+    dt = pkg.F32 if f32 else pkg.F64
+    prog = handle.compile(alg, dt, 3, 3, s, n)
+    tf = 10.0 if alg_name == "dp5" else 3.0
+    grid = [k / 10 for k in range(1, int(tf * 10) + 1)]
+    for kw in ({}, {"saveat": grid}, {"reltol": 1e-6, "abstol": 1e-8} if not f32 else {"reltol": 1e-4, "abstol": 1e-5},
+               {"maxiters": 15}):
+        g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, tf), **kw)
+        o = oracle.solve(oalg, (s, n), U0, p, (0.0, tf), 3, 3, f32=f32, **kw)
+        assert_same_result(g, o)
+    stages = 6 if alg_name == "dp5" else 3
+    assert (g["nf"] == 3 + stages * (g["naccept"] + g["nreject"])).all()        # 1 (FSAL start) + 2 (initdt)
+    # ragged rows and dense output through the same generic paths
+    prog_e = handle.compile(alg, dt, 3, 3, s, n, extra_options=pkg._lib.OPT_EVERYSTEP)
+    ge = pkg.lowlevel.solve_host_everystep(prog_e, U0, p, (0.0, 2.0), saveat=[0.5, 1.5])
+    oe = oracle.solve(oalg, (s, n), U0, p, (0.0, 2.0), 3, 3, f32=f32, save_everystep=True, saveat=[0.5, 1.5])
+    _assert_same_ragged(ge, oe)
+    tq = np.linspace(0.0, 2.0, 41)
+    gd = pkg.lowlevel.solve_host_dense(prog_e, U0, p, (0.0, 2.0), tq)
+    od = oracle.solve(oalg, (s, n), U0, p, (0.0, 2.0), 3, 3, f32=f32, dense_tq=tq)
+    assert np.array_equal(bits(gd["dense"]), bits(od["dense"]))
+
+
+def test_low_order_rk_high_level(pkg, oracle):
+    P = pkg
+    pl = P.problems_library
+    N = 128
+    table = pl.lorenz_params(N)
+    prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (0.0, 5.0), table[0])
+    ep = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table))
+    for alg, oalg in ((P.DP5(), oracle.ALG_DP5), (P.BS3(), oracle.ALG_BS3)):
+        s = P.solve(ep, alg, P.EnsembleB200(), trajectories=N, saveat=0.5)
+        o = oracle.solve(oalg, pl.lorenz_source(), U0, table, (0.0, 5.0), 3, 3, saveat=[k / 2 for k in range(1, 11)])
+        for i in (0, 77):
+            assert np.array_equal(bits(np.ascontiguousarray(s[i].u)), bits(o["us"][i]))
+            assert s[i].stats.naccept == o["naccept"][i]

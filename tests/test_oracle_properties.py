@@ -123,6 +123,8 @@ def _fixed_step_l2_error(alg, h, stiff=False):
     (oracle.ALG_TSIT5, 5, (7, 6, 5, 4, 3), 0.4, False),    # test/Regression_II/ode_unrolled_comparison_tests.jl:70-77
     (oracle.ALG_VERN7, 7, (3, 2, 1), 0.4, False),          # lib/OrdinaryDiffEqVerner/test/ode_verner_tests.jl:61-65 (BigFloat there; larger dts in binary64)
     (oracle.ALG_ROSENBROCK23, 2, (6, 5, 4, 3), 0.2, True),  # lib/OrdinaryDiffEqRosenbrock/test/ode_rosenbrock_tests.jl:15-23
+    (oracle.ALG_BS3, 3, (8, 7, 6, 5, 4), 0.2, False),      # lib/OrdinaryDiffEqLowOrderRK/test/low_order_erk_convergence_tests.jl:32,74-75
+    (oracle.ALG_DP5, 5, (7, 6, 5, 4, 3), 0.4, False),      # DP5 shares Tsit5's dts in test/Regression_II/ode_unrolled_comparison_tests.jl
 ])
 def test_convergence_order(alg, order, exps, tol, stiff):
     errs = [_fixed_step_l2_error(alg, 0.5 ** k, stiff) for k in exps]
@@ -200,7 +202,8 @@ def test_tableau_consistency():
 
 # ---- dense output regression bounds -----------------------------------------------------------
 @pytest.mark.parametrize("alg,bound", [
-    (oracle.ALG_TSIT5, 2e-6), (oracle.ALG_VERN7, 3e-9), (oracle.ALG_ROSENBROCK23, 3e-3), (oracle.ALG_RODAS5P, 2e-5)])
+    (oracle.ALG_TSIT5, 2e-6), (oracle.ALG_VERN7, 3e-9), (oracle.ALG_ROSENBROCK23, 3e-3), (oracle.ALG_RODAS5P, 2e-5),
+    (oracle.ALG_DP5, 5e-6), (oracle.ALG_BS3, 5e-4)])           # ode_dense_tests.jl:355,358
 def test_dense_output_regression_bounds(alg, bound):
     # test/Regression_I/ode_dense_tests.jl:56-75 with the per-algorithm tolerances at
     # :369-370 (Tsit5), :429-433 (Vern7), :452-453 (Rosenbrock23), :479-480 (Rodas5P):
@@ -306,14 +309,14 @@ def _run_pin_case(pl, case):
 
 
 # ---- save_everystep -----------------------------------------------------
-@pytest.mark.parametrize("alg", ["tsit5", "vern7", "ros23", "rodas5p"])
+@pytest.mark.parametrize("alg", ["tsit5", "vern7", "ros23", "rodas5p", "dp5", "bs3"])
 def test_everystep_rows_and_saveat_symdiff(alg):
     # test/InterfaceI/ode_saveat_tests.jl:52-59,117-124: with save_everystep = true, adding
     # saveat = [0.125, 0.6, 0.61, 0.8] inserts exactly those times into sol.t and nothing else changes
     rhs = linear_source()
     jac, tg = linear_jac_sources()
     a = {"tsit5": oracle.ALG_TSIT5, "vern7": oracle.ALG_VERN7, "ros23": oracle.ALG_ROSENBROCK23,
-         "rodas5p": oracle.ALG_RODAS5P}[alg]
+         "rodas5p": oracle.ALG_RODAS5P, "dp5": oracle.ALG_DP5, "bs3": oracle.ALG_BS3}[alg]
     kw = dict(jac=jac, tgrad=tg) if alg in ("ros23", "rodas5p") else {}
     base = oracle.solve(a, rhs, np.array([[0.5]]), None, (0.0, 1.0), 1, 0, dt=0.25, save_everystep=True, **kw)
     grid = [0.125, 0.6, 0.61, 0.8]
