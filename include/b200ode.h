@@ -35,6 +35,13 @@ extern "C" {
 #define B200ODE_ALG_RODAS5P 4      /* lib/OrdinaryDiffEqRosenbrock/src/rosenbrock_perform_step.jl:431-559 */
 #define B200ODE_ALG_DP5 5          /* lib/OrdinaryDiffEqLowOrderRK/src/low_order_rk_perform_step.jl:667-710 */
 #define B200ODE_ALG_BS3 6          /* lib/OrdinaryDiffEqLowOrderRK/src/low_order_rk_perform_step.jl:13-36 */
+/* the RodasTableau family: same stepper as Rodas5P (rosenbrock_perform_step.jl:431-559) over the tableaus of
+ * lib/OrdinaryDiffEqRosenbrockTableaus/src/rosenbrock_tableaus.jl:26-220 */
+#define B200ODE_ALG_RODAS5 7
+#define B200ODE_ALG_RODAS4 8
+#define B200ODE_ALG_RODAS42 9
+#define B200ODE_ALG_RODAS4P 10
+#define B200ODE_ALG_RODAS4P2 11
 
 #define B200ODE_F64 0
 #define B200ODE_F32 1

@@ -147,6 +147,11 @@ bool is_identifier(const char* s) {
     return true;
 }
 
+bool is_stiff_alg(int alg) {      // Rosenbrock-type: need jac + tgrad, report njacs/nw/nsolve
+    return alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_RODAS5P ||
+           (alg >= B200ODE_ALG_RODAS5 && alg <= B200ODE_ALG_RODAS4P2);
+}
+
 // -DB200_SAVE_IDXS=i0,i1,...  -> number of listed components (0: option absent, -1: malformed / out of range)
 int parse_save_idxs(const char* extra_options, int n) {
     const char* key = "-DB200_SAVE_IDXS=";
@@ -169,13 +174,13 @@ int parse_save_idxs(const char* extra_options, int n) {
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                           const char* jac_src, const char* jac_name, const char* tgrad_src,
                           const char* tgrad_name) {
-    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_BS3)
-        return fail(B200ODE_EINVAL, "alg must be one of B200ODE_ALG_{TSIT5,VERN7,ROSENBROCK23,RODAS5P,DP5,BS3}");
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS4P2)
+        return fail(B200ODE_EINVAL, "alg must be one of the B200ODE_ALG_* constants");
     if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
     if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");
     if (np < 0 || np > 256) return fail(B200ODE_EINVAL, "parameter dimension np must be in 0..256");
     if (!rhs_src || !is_identifier(rhs_name)) return fail(B200ODE_EINVAL, "rhs_src and a valid rhs_name are required");
-    bool stiff = (alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_RODAS5P);
+    bool stiff = is_stiff_alg(alg);
     if (stiff) {
         if (!jac_src || !is_identifier(jac_name))
             return fail(B200ODE_EINVAL, "Rosenbrock algorithms need jac_src/jac_name (ODEFunction(f; jac, tgrad))");
@@ -190,7 +195,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
                 const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms, int* sliced_g = nullptr) {
     int rc = validate_compile_args(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name);
     if (rc) return rc;
-    bool stiff = (alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_RODAS5P);
+    bool stiff = is_stiff_alg(alg);
     auto t_begin = std::chrono::steady_clock::now();
 
     std::string tu;
@@ -683,7 +688,7 @@ int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200Devic
     if (rc) return rc;
     if (!dr->u_final || !dr->t_final || !dr->naccept || !dr->nreject || !dr->nf || !dr->retcode || !dr->nsaved)
         return fail(B200ODE_EINVAL, "device result arrays u_final,t_final,naccept,nreject,nf,retcode,nsaved are required");
-    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    bool stiff = is_stiff_alg(prog->alg);
     if (stiff && (!dr->njacs || !dr->nw || !dr->nsolve))
         return fail(B200ODE_EINVAL, "Rosenbrock programs need njacs,nw,nsolve result arrays");
     if (prog->everystep) return fail(B200ODE_EINVAL, "program was compiled for save_everystep: use b200ode_solve_everystep[_device]");
@@ -703,7 +708,7 @@ int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const
     if (rc) return rc;
     if (!dr->u_final || !dr->t_final || !dr->naccept || !dr->nreject || !dr->nf || !dr->retcode || !dr->nsaved)
         return fail(B200ODE_EINVAL, "device result arrays u_final,t_final,naccept,nreject,nf,retcode,nsaved are required");
-    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    bool stiff = is_stiff_alg(prog->alg);
     if (stiff && (!dr->njacs || !dr->nw || !dr->nsolve))
         return fail(B200ODE_EINVAL, "Rosenbrock programs need njacs,nw,nsolve result arrays");
     if (row_offsets && (!dr->us || !ts || !dts)) return fail(B200ODE_EINVAL, "the fill pass needs result.us, ts and dts");
@@ -783,7 +788,7 @@ static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Probl
     CUDA_TRY(h->out_i32.ensure(sizeof(int32_t) * 8 * (size_t)N));
     CUDA_TRY(h->row_offsets.ensure(sizeof(int64_t) * ((size_t)N + 1)));
     int32_t* i32 = (int32_t*)h->out_i32.ptr;
-    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    bool stiff = is_stiff_alg(prog->alg);
     if (!stiff) CUDA_TRY(cudaMemsetAsync(i32 + 4 * N, 0, sizeof(int32_t) * 3 * (size_t)N, s));
     B200DeviceProblem dp{};
     dp.trajectories = N;
@@ -1023,7 +1028,7 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
     if (nslots > 0) CUDA_TRY(h->out_us.ensure(us_bytes));
 
     int32_t* i32 = (int32_t*)h->out_i32.ptr;
-    bool stiff = (prog->alg == B200ODE_ALG_ROSENBROCK23 || prog->alg == B200ODE_ALG_RODAS5P);
+    bool stiff = is_stiff_alg(prog->alg);
     if (!stiff) CUDA_TRY(cudaMemsetAsync(i32 + 4 * N, 0, sizeof(int32_t) * 3 * (size_t)N, s));
     // (rows a failed trajectory does not reach are zero-filled by the kernel itself)
 

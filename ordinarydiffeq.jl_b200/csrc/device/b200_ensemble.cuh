@@ -20,7 +20,8 @@
 // Compile-time configuration (set by the shim before this file):
 //   B200_N, B200_NP      state / parameter dimension
 //   B200_F32             0: double, 1: float
-//   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3
+//   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3,
+//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -33,6 +34,13 @@
 #define B200_ALG_RODAS5P 4
 #define B200_ALG_DP5 5
 #define B200_ALG_BS3 6
+#define B200_ALG_RODAS5 7
+#define B200_ALG_RODAS4 8
+#define B200_ALG_RODAS42 9
+#define B200_ALG_RODAS4P 10
+#define B200_ALG_RODAS4P2 11
+#define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
+#define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_IS_RODAS)
 
 #ifndef B200_SLICED
 #define B200_SLICED 0
@@ -48,7 +56,7 @@ typedef B200Tsit5 B200Stepper;
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_vern7.cuh"
 typedef B200Vern7 B200Stepper;
-#elif B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#elif B200_IS_ROSENBROCK
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_rosenbrock.cuh"
 #if B200_ALG == B200_ALG_ROS23
@@ -248,7 +256,7 @@ struct B200Traj {
     real last_t;                // sol.t[end]
     int cap;                    // rows this trajectory owns (0 in the counting pass)
 #endif
-#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#if B200_IS_ROSENBROCK
     int njacs, nw, nsolve;
 #endif
 };
@@ -294,7 +302,7 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     for (int c = 0; c < B200_NP; ++c) T.p[c] = P.p[idx * P.p_ts + c * P.p_cs];
     T.t = P.t0; T.tprev = P.t0;
     T.nf = 0;
-#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#if B200_IS_ROSENBROCK
     T.njacs = 0; T.nw = 0; T.nsolve = 0;
 #endif
     T.nsaved = 0; T.save_idx = 0;
@@ -379,7 +387,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     const bool skip = T.tstop_flag && b200_abs(T.dt) < eps_t;   // integrator_utils.jl:326-333 (eps(|t|) == eps(t))
     __syncwarp(amask);
     if (ok && !skip) {
-#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#if B200_IS_ROSENBROCK
         T.EEst = T.st.attempt(T.uprev, T.u, T.p, T.t, T.dt, P.reltol, P.abstol, T.nf, T.njacs, T.nw, T.nsolve,
                               (B200_EVERYSTEP || P.nslots > 0) && P.nsaveat > 0);
 #else
@@ -501,7 +509,7 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
     P.nf[idx] = T.nf;
     P.retcode[idx] = T.retcode;
     P.nsaved[idx] = T.nsaved;
-#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#if B200_IS_ROSENBROCK
     P.njacs[idx] = T.njacs; P.nw[idx] = T.nw; P.nsolve[idx] = T.nsolve;
 #endif
 }
@@ -632,7 +640,7 @@ extern "C" __global__ void __launch_bounds__(128) b200_dense_eval(B200DenseParam
     B200Stepper st;
     real uprev[B200_N], u[B200_N], scratch[B200_N];
     int hi = 1, cur = -1, nf = 0;
-#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#if B200_IS_ROSENBROCK
     int njacs = 0, nw = 0, nsolve = 0;
 #endif
     for (int j = 0; j < D.M; ++j) {
@@ -652,7 +660,7 @@ extern "C" __global__ void __launch_bounds__(128) b200_dense_eval(B200DenseParam
 #pragma unroll
             for (int c = 0; c < B200_N; ++c) { uprev[c] = us[(size_t)im * B200_N + c]; u[c] = us[(size_t)ip * B200_N + c]; }
             st.init(uprev, p, ts[im], nf);                                   // FSAL k1 = f(u[i-], ts[i-])
-#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_RODAS5P
+#if B200_IS_ROSENBROCK
             st.attempt(uprev, scratch, p, ts[im], dts[ip], D.reltol, D.abstol, nf, njacs, nw, nsolve, true);
 #else
             st.attempt(uprev, scratch, p, ts[im], dts[ip], D.reltol, D.abstol, nf);

@@ -237,21 +237,45 @@ struct B200Ros23 {
 };
 
 // ---------------------------------------------------------------------------
+// Tableau selection for the generic Rodas-type stepper (RodasTableau family; b = [A[S,1:S-1]; 1],
+// btilde = e_S; rosenbrock_tableaus.jl of OrdinaryDiffEqRosenbrock / OrdinaryDiffEqRosenbrockTableaus).
+#if B200_ALG == B200_ALG_RODAS5
+#define B200_RODAS_NAME(x) B200_RODAS5_##x
+#define B200_RODAS_ORDER 5
+#elif B200_ALG == B200_ALG_RODAS4
+#define B200_RODAS_NAME(x) B200_RODAS4_##x
+#define B200_RODAS_ORDER 4
+#elif B200_ALG == B200_ALG_RODAS42
+#define B200_RODAS_NAME(x) B200_RODAS42_##x
+#define B200_RODAS_ORDER 4
+#elif B200_ALG == B200_ALG_RODAS4P
+#define B200_RODAS_NAME(x) B200_RODAS4P_##x
+#define B200_RODAS_ORDER 4
+#elif B200_ALG == B200_ALG_RODAS4P2
+#define B200_RODAS_NAME(x) B200_RODAS4P2_##x
+#define B200_RODAS_ORDER 4
+#else
+#define B200_RODAS_NAME(x) B200_RODAS5P_##x
+#define B200_RODAS_ORDER 5
+#endif
+#define B200_RODAS_S B200_RODAS_NAME(S)
+#define B200_RODAS_HR B200_RODAS_NAME(HR)
+
 struct B200Rodas5PCoeffs {
-    real A[8][8];
-    real C[8][7];
-    real c[8];
-    real d[8];
-    real H[3][8];
+    real A[B200_RODAS_S][B200_RODAS_S];
+    real C[B200_RODAS_S][B200_RODAS_S - 1];
+    real c[B200_RODAS_S];
+    real d[B200_RODAS_S];
+    real H[B200_RODAS_HR][B200_RODAS_S];
     real gamma;
 };
-__constant__ B200Rodas5PCoeffs B200_RODAS5P_TAB = {B200_RODAS5P_A, B200_RODAS5P_C, B200_RODAS5P_c, B200_RODAS5P_d,
-                                                 B200_RODAS5P_H, B200_RODAS5P_GAMMA};
+__constant__ B200Rodas5PCoeffs B200_RODAS5P_TAB = {B200_RODAS_NAME(A), B200_RODAS_NAME(C), B200_RODAS_NAME(c), B200_RODAS_NAME(d),
+                                                 B200_RODAS_NAME(H), B200_RODAS_NAME(GAMMA)};
 
 struct B200Rodas5P {
-    real dense[3][B200_N];             // integrator.k[1..3] (only filled when saveat is used)
+    real dense[B200_RODAS_HR][B200_N];   // integrator.k[1..size(H,1)] (only filled when rows are interpolated)
 
-    static B200_D int order() { return 5; }
+    static B200_D int order() { return B200_RODAS_ORDER; }
     static B200_D real qsteady_min() { return (real)1; }
     static B200_D real qsteady_max() { return (real)1.2; }
 
@@ -262,7 +286,7 @@ struct B200Rodas5P {
         const B200Rodas5PCoeffs& T = B200_RODAS5P_TAB;
         const real dtgamma = dt * T.gamma;
         real dT[B200_N], du[B200_N], lt[B200_N], us[B200_N];
-        real ks[8][B200_N];
+        real ks[B200_RODAS_S][B200_N];
         B200WFact F;
         b200_build_W(uprev, p, t, dtgamma, dT, F, njacs, nw);
         if (!F.ok) return (real)2;
@@ -277,7 +301,7 @@ struct B200Rodas5P {
         for (int i = 0; i < B200_N; ++i) lt[i] = -b200_fma(dt * T.d[0], dT[i], du[i]);
         F.solve(lt, ks[0]);
 #pragma unroll
-        for (int s = 1; s < 8; ++s) {
+        for (int s = 1; s < B200_RODAS_S; ++s) {
 #pragma unroll
             for (int i = 0; i < B200_N; ++i) us[i] = uprev[i];
 #pragma unroll
@@ -308,25 +332,25 @@ struct B200Rodas5P {
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) u[i] = uprev[i];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const real b = (j < 7) ? T.A[7][j] : (real)1;      // b = [A[8,1:7]; 1]
-            if (j < 7 && T.A[7][j] == (real)0) continue;
+        for (int j = 0; j < B200_RODAS_S; ++j) {
+            const real b = (j < B200_RODAS_S - 1) ? T.A[B200_RODAS_S - 1][j] : (real)1;      // b = [A[S,1:S-1]; 1]
+            if (j < B200_RODAS_S - 1 && T.A[B200_RODAS_S - 1][j] == (real)0) continue;
 #pragma unroll
             for (int i = 0; i < B200_N; ++i) u[i] = b200_fma(b, ks[j][i], u[i]);
         }
-        // btilde = e_8: du = 0 + 1*ks[8]
+        // btilde = e_S: du = 0 + 1*ks[S]
 #pragma unroll
-        for (int i = 0; i < B200_N; ++i) du[i] = b200_fma((real)1, ks[7][i], (real)0);
+        for (int i = 0; i < B200_N; ++i) du[i] = b200_fma((real)1, ks[B200_RODAS_S - 1][i], (real)0);
         const real EEst = b200_err_norm(du, uprev, u, reltol, abstol);
         if (calck) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < B200_RODAS_HR; ++r)
 #pragma unroll
                 for (int i = 0; i < B200_N; ++i) dense[r][i] = (real)0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < B200_RODAS_S; ++j)
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int r = 0; r < B200_RODAS_HR; ++r)
 #pragma unroll
                     for (int i = 0; i < B200_N; ++i) dense[r][i] = b200_fma(T.H[r][j], ks[j][i], dense[r][i]);
         }
@@ -336,13 +360,18 @@ struct B200Rodas5P {
     B200_D void accept() {}
     B200_D void dense_prepare(const real*, const real*, const real*, real, real) {}
 
-    // Θ1*y0 + Θ*(y1 + Θ1*(k1 + Θ*(k2 + Θ*k3)))
+    // interp_order = size(H,1) (rosenbrock_interpolants.jl:172-206):
+    //   3: Θ1*y0 + Θ*(y1 + Θ1*(k1 + Θ*(k2 + Θ*k3)))     2: Θ1*y0 + Θ*(y1 + Θ1*(k1 + Θ*k2))
     B200_D void interp(real th, real /*dt*/, const real* y0, const real* y1, real* out) const {
         const real th1 = (real)1 - th;
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) {
+#if B200_RODAS_HR == 3
             real in = b200_fma(th, dense[2][i], dense[1][i]);
             in = b200_fma(th, in, dense[0][i]);
+#else
+            real in = b200_fma(th, dense[1][i], dense[0][i]);
+#endif
             in = b200_fma(th1, in, y1[i]);
             out[i] = b200_fma(th, in, th1 * y0[i]);
         }

@@ -47,6 +47,26 @@ class Rodas5P(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS5P, 5, True
 
 
+class Rodas5(_Alg):         # RodasTableau family (lib/OrdinaryDiffEqRosenbrockTableaus)
+    alg_id, order, stiff = _lib.ALG_RODAS5, 5, True
+
+
+class Rodas4(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS4, 4, True
+
+
+class Rodas42(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS42, 4, True
+
+
+class Rodas4P(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS4P, 4, True
+
+
+class Rodas4P2(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS4P2, 4, True
+
+
 class DP5(_Alg):            # lib/OrdinaryDiffEqLowOrderRK
     alg_id, order = _lib.ALG_DP5, 5
 
@@ -328,7 +348,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     if not isinstance(ensemblealg, EnsembleB200):
         raise NotImplementedError("only EnsembleB200() is provided (no CPU fallback)")
     if not isinstance(alg, _Alg):
-        raise TypeError("alg must be one of Tsit5(), Vern7(), DP5(), BS3(), Rosenbrock23(), Rodas5P()")
+        raise TypeError("alg must be one of Tsit5(), Vern7(), DP5(), BS3(), Rosenbrock23(), Rodas4/42/4P/4P2/5/5P()")
     prob = eprob.prob
     kw = dict(prob.kwargs, **kw)                      # merge_problem_kwargs: solve's kwargs win
     bad = set(kw) - _ALLOWED_KW

@@ -624,3 +624,33 @@ def test_low_order_rk_high_level(pkg, oracle):
         for i in (0, 77):
             assert np.array_equal(bits(np.ascontiguousarray(s[i].u)), bits(o["us"][i]))
             assert s[i].stats.naccept == o["naccept"][i]
+
+
+@pytest.mark.parametrize("name", ["Rodas5", "Rodas4", "Rodas42", "Rodas4P", "Rodas4P2"])
+def test_rodas_family_parity(pkg, handle, oracle, name):
+    """The generic RodasTableau stepper over the other members of the family, Robertson FP64 (+ FP32 for two)."""
+    pl = pkg.problems_library
+    alg = getattr(pkg, "ALG_" + name.upper())
+    oalg = getattr(oracle, "ALG_" + name.upper())
+    N = 1024
+    for f32 in ((False, True) if name in ("Rodas5", "Rodas4") else (False,)):
+        r, j, tg = pl.robertson_sources(f32)
+        p = pl.robertson_params(N, f32=f32)
+        dt = pkg.F32 if f32 else pkg.F64
+        tf = 1e4 if not f32 else 1e3
+        tol = dict(reltol=1e-6, abstol=1e-8) if not f32 else dict(reltol=1e-3, abstol=1e-5)
+        prog = handle.compile(alg, dt, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1])
+        for extra in ({}, {"saveat": [tf * 1e-3, tf * 1e-2, tf * 0.5]}):
+            kw = dict(tol, **extra)
+            g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, tf), **kw)
+            o = oracle.solve(oalg, r, U0, p, (0.0, tf), 3, 3, f32=f32, jac=j, tgrad=tg, **kw)
+            assert_same_result(g, o)
+            assert (g["retcode"] == 1).all()
+        assert np.abs(g["u_final"].astype(np.float64).sum(axis=1) - 1.0).max() < (1e-7 if not f32 else 1e-3)
+    r, j, tg = pl.robertson_sources()
+    p = pl.robertson_params(N)
+    prog_e = handle.compile(alg, pkg.F64, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1], extra_options=pkg._lib.OPT_EVERYSTEP)
+    tq = np.array([0.0, 0.01, 1.0, 20.0, 100.0])
+    gd = pkg.lowlevel.solve_host_dense(prog_e, U0, p, (0.0, 100.0), tq, reltol=1e-6, abstol=1e-8)
+    od = oracle.solve(oalg, r, U0, p, (0.0, 100.0), 3, 3, jac=j, tgrad=tg, reltol=1e-6, abstol=1e-8, dense_tq=tq)
+    assert np.array_equal(bits(gd["dense"]), bits(od["dense"]))
