@@ -132,7 +132,8 @@ template <typename R> struct Fn {
 };
 
 enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4, ALG_DP5 = 5, ALG_BS3 = 6,
-       ALG_RODAS5 = 7, ALG_RODAS4 = 8, ALG_RODAS42 = 9, ALG_RODAS4P = 10, ALG_RODAS4P2 = 11 };
+       ALG_RODAS5 = 7, ALG_RODAS4 = 8, ALG_RODAS42 = 9, ALG_RODAS4P = 10, ALG_RODAS4P2 = 11,
+       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_VERN7_GENERATED = 102 };
 enum { RC_DEFAULT = 0, RC_SUCCESS = 1, RC_MAXITERS = 2, RC_DTLESSTHANMIN = 3, RC_UNSTABLE = 4, RC_DTNAN = 5 };
 
 template <typename R> struct Opts {
@@ -261,6 +262,9 @@ template <typename R> struct Tsit5 {
     static bool fsal_init() { return true; }
 };
 
+#if __has_include("oracle_verner_gen.inc")
+#include "oracle_verner_gen.inc"
+#endif
 #if __has_include("oracle_lowrk.inc")
 #include "oracle_lowrk.inc"
 #endif
@@ -636,6 +640,12 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         case ALG_RODAS42: solve_batch<R, Rodas42<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P: solve_batch<R, Rodas4P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P2: solve_batch<R, Rodas4P2<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+#endif
+#ifdef ORACLE_HAVE_VERNER_GEN
+        case ALG_VERN6: solve_batch<R, Vern6<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_VERN8: solve_batch<R, Vern8<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_VERN9: solve_batch<R, Vern9<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_VERN7_GENERATED: solve_batch<R, Vern7Gen<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #endif
 #ifdef ORACLE_HAVE_LOWRK
         case ALG_DP5: solve_batch<R, DP5<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;

@@ -174,7 +174,7 @@ int parse_save_idxs(const char* extra_options, int n) {
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                           const char* jac_src, const char* jac_name, const char* tgrad_src,
                           const char* tgrad_name) {
-    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS4P2)
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_VERN9)
         return fail(B200ODE_EINVAL, "alg must be one of the B200ODE_ALG_* constants");
     if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
     if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");
@@ -297,7 +297,8 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         // registers available per thread at k CTAs of 128 threads: 65536/(128k)
         int minb = 4;
         if (stiff) minb = (words <= 8) ? (alg == B200ODE_ALG_ROSENBROCK23 ? 5 : 4) : 1;   // measured (scripts/sweep_rober.py)
-        else if (alg == B200ODE_ALG_VERN7) minb = (words <= 6) ? 3 : 1;
+        else if (alg == B200ODE_ALG_VERN7 || alg == B200ODE_ALG_VERN6 || alg == B200ODE_ALG_VERN8 || alg == B200ODE_ALG_VERN9)
+            minb = (words <= 6) ? (alg == B200ODE_ALG_VERN9 ? 2 : 3) : 1;
         else minb = (words <= 8) ? 4 : (words <= 16 ? 2 : 1);
         opts.push_back("-DB200_MINBLOCKS=" + std::to_string(minb));
     }

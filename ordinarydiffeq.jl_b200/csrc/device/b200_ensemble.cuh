@@ -21,7 +21,7 @@
 //   B200_N, B200_NP      state / parameter dimension
 //   B200_F32             0: double, 1: float
 //   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3,
-//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2
+//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -39,6 +39,9 @@
 #define B200_ALG_RODAS42 9
 #define B200_ALG_RODAS4P 10
 #define B200_ALG_RODAS4P2 11
+#define B200_ALG_VERN6 12
+#define B200_ALG_VERN8 13
+#define B200_ALG_VERN9 14
 #define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
 #define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_IS_RODAS)
 
@@ -63,6 +66,16 @@ typedef B200Vern7 B200Stepper;
 typedef B200Ros23 B200Stepper;
 #else
 typedef B200Rodas5P B200Stepper;
+#endif
+#elif B200_ALG == B200_ALG_VERN6 || B200_ALG == B200_ALG_VERN8 || B200_ALG == B200_ALG_VERN9
+#define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
+#include "b200_verner_gen.cuh"
+#if B200_ALG == B200_ALG_VERN6
+typedef B200Vern6 B200Stepper;
+#elif B200_ALG == B200_ALG_VERN8
+typedef B200Vern8 B200Stepper;
+#else
+typedef B200Vern9 B200Stepper;
 #endif
 #elif B200_ALG == B200_ALG_DP5 || B200_ALG == B200_ALG_BS3
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)

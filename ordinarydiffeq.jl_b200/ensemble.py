@@ -47,6 +47,18 @@ class Rodas5P(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS5P, 5, True
 
 
+class Vern6(_Alg):
+    alg_id, order = _lib.ALG_VERN6, 6
+
+
+class Vern8(_Alg):
+    alg_id, order = _lib.ALG_VERN8, 8
+
+
+class Vern9(_Alg):
+    alg_id, order = _lib.ALG_VERN9, 9
+
+
 class Rodas5(_Alg):         # RodasTableau family (lib/OrdinaryDiffEqRosenbrockTableaus)
     alg_id, order, stiff = _lib.ALG_RODAS5, 5, True
 

@@ -654,3 +654,46 @@ def test_rodas_family_parity(pkg, handle, oracle, name):
     gd = pkg.lowlevel.solve_host_dense(prog_e, U0, p, (0.0, 100.0), tq, reltol=1e-6, abstol=1e-8)
     od = oracle.solve(oalg, r, U0, p, (0.0, 100.0), 3, 3, jac=j, tgrad=tg, reltol=1e-6, abstol=1e-8, dense_tq=tq)
     assert np.array_equal(bits(gd["dense"]), bits(od["dense"]))
+
+
+@pytest.mark.parametrize("name", ["Vern6", "Vern8", "Vern9"])
+@pytest.mark.parametrize("f32", [False, True])
+def test_generated_verner_parity(pkg, handle, oracle, name, f32):
+    """Vern6/8/9 (scripts/gen_verner.py): final states, stats, lazily interpolated saveat rows, ragged rows, dense."""
+    pl = pkg.problems_library
+    alg = getattr(pkg, "ALG_" + name.upper())
+    oalg = getattr(oracle, "ALG_" + name.upper())
+    N = 2000
+    p = pl.lorenz_params(N, f32=f32)
+    s, n = pl.lorenz_source(f32)
+    prog = handle.compile(alg, pkg.F32 if f32 else pkg.F64, 3, 3, s, n)
+    grid = [k / 4 for k in range(1, 21)]
+    tol = dict(reltol=1e-8, abstol=1e-10) if not f32 else dict(reltol=1e-4, abstol=1e-5)
+    for kw in ({}, {"saveat": grid}, dict(tol, saveat=grid), {"maxiters": 9}):
+        g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 5.0), **kw)
+        o = oracle.solve(oalg, (s, n), U0, p, (0.0, 5.0), 3, 3, f32=f32, **kw)
+        assert_same_result(g, o)
+    prog_e = handle.compile(alg, pkg.F32 if f32 else pkg.F64, 3, 3, s, n, extra_options=pkg._lib.OPT_EVERYSTEP)
+    ge = pkg.lowlevel.solve_host_everystep(prog_e, U0, p, (0.0, 2.0), saveat=[0.7])
+    oe = oracle.solve(oalg, (s, n), U0, p, (0.0, 2.0), 3, 3, f32=f32, save_everystep=True, saveat=[0.7])
+    _assert_same_ragged(ge, oe)
+    tq = np.linspace(0.0, 2.0, 33)
+    gd = pkg.lowlevel.solve_host_dense(prog_e, U0, p, (0.0, 2.0), tq)
+    od = oracle.solve(oalg, (s, n), U0, p, (0.0, 2.0), 3, 3, f32=f32, dense_tq=tq)
+    assert np.array_equal(bits(gd["dense"]), bits(od["dense"]))
+
+
+def test_vern9_wider_state(pkg, handle, oracle):
+    """n = 8 (prob_ode_2Dlinear flattened).  Pleiades (n = 28, 43 KB straight-line RHS) is not paired with Vern9 here:
+    26 inlined copies of that RHS take NVRTC/ptxas more than 15 minutes to compile."""
+    from helpers import linear2d_source
+    s, n = linear2d_source(8)
+    rng = np.random.default_rng(3)
+    u0 = rng.uniform(0.1, 1.0, size=(300, 8))
+    prog = handle.compile(pkg.ALG_VERN9, pkg.F64, 8, 0, s, n)
+    kw = dict(reltol=1e-8, abstol=1e-10, saveat=[0.25, 0.5, 1.0])
+    g = pkg.lowlevel.solve_host(prog, u0, None, (0.0, 1.0), **kw)
+    o = oracle.solve(oracle.ALG_VERN9, (s, n), u0, None, (0.0, 1.0), 8, 0, **kw)
+    assert_same_result(g, o)
+    assert (g["retcode"] == 1).all()
+    assert np.allclose(g["u_final"], u0 * np.exp(1.01), rtol=1e-8)

@@ -132,6 +132,14 @@ def test_convergence_order(alg, order, exps, tol, stiff):
     assert abs(np.mean(rates) - order) < tol, (errs, rates)
 
 
+def test_vern6_is_at_least_sixth_order():
+    # lib/OrdinaryDiffEqVerner/test/ode_verner_tests.jl:42-43 (BigFloat there; binary64 needs large dts, where the
+    # linear problem shows a rate above 6)
+    errs = [_fixed_step_l2_error(oracle.ALG_VERN6, 0.5 ** k, False) for k in (3, 2, 1)]
+    rates = [math.log2(errs[i + 1] / errs[i]) for i in range(len(errs) - 1)]
+    assert 5.6 < np.mean(rates) < 7.2, (errs, rates)
+
+
 def test_rodas5p_is_at_least_fifth_order():
     errs = [_fixed_step_l2_error(oracle.ALG_RODAS5P, 0.5 ** k, True) for k in (4, 3, 2)]
     rates = [math.log2(errs[i + 1] / errs[i]) for i in range(len(errs) - 1)]
@@ -205,13 +213,14 @@ def test_tableau_consistency():
     (oracle.ALG_TSIT5, 2e-6), (oracle.ALG_VERN7, 3e-9), (oracle.ALG_ROSENBROCK23, 3e-3), (oracle.ALG_RODAS5P, 2e-5),
     (oracle.ALG_DP5, 5e-6), (oracle.ALG_BS3, 5e-4),            # ode_dense_tests.jl:355,358
     (oracle.ALG_RODAS4, 8.5e-6), (oracle.ALG_RODAS42, 3e-5), (oracle.ALG_RODAS4P, 4e-5), (oracle.ALG_RODAS4P2, 2e-5),
-    (oracle.ALG_RODAS5, 2e-6)])                                # ode_dense_tests.jl:465-477
+    (oracle.ALG_RODAS5, 2e-6),                                 # ode_dense_tests.jl:465-477
+    (oracle.ALG_VERN6, 7e-8), (oracle.ALG_VERN8, 3e-8), (oracle.ALG_VERN9, 1e-9)])   # ode_dense_tests.jl:406,437,444
 def test_dense_output_regression_bounds(alg, bound):
     # test/Regression_I/ode_dense_tests.jl:56-75 with the per-algorithm tolerances at
     # :369-370 (Tsit5), :429-433 (Vern7), :452-453 (Rosenbrock23), :479-480 (Rodas5P):
     # interpolant of the adaptive dt0 = 1/4 solve vs the fixed dt = 1/16 solve, at k/16.
     jac, tg = linear_jac_sources()
-    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_RODAS5P) or alg >= oracle.ALG_RODAS5
+    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_RODAS5P) or oracle.ALG_RODAS5 <= alg <= oracle.ALG_RODAS4P2
     kw = dict(jac=jac, tgrad=tg) if stiff else {}
     pts = [k / 16 for k in range(1, 17)]
     a = oracle.solve(alg, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, dt=0.25,
@@ -364,3 +373,32 @@ def test_rodas_family_order_and_step_count(alg, order):
     S = 8 if alg == oracle.ALG_RODAS5 else 6
     iters = o["naccept"][0] + o["nreject"][0]
     assert o["nf"][0] == 2 + S * iters and o["nsolve"][0] == (S - 1) * iters and o["njacs"][0] == 2 * iters
+
+
+# ---- generated Verner steppers (scripts/gen_verner.py) ----------------------------------------
+def test_generated_vern7_equals_handwritten_vern7(pkg):
+    """The generator that writes Vern6/8/9 also emits a Vern7; it must reproduce the hand-written Vern7
+    (oracle_vern7.inc) bit for bit — steps, stats, final state and lazily interpolated rows."""
+    pl = pkg.problems_library
+    p = pl.lorenz_params(256)
+    grid = [k / 8 for k in range(1, 25)]
+    for kw in (dict(reltol=1e-8, abstol=1e-10), {}):
+        a = oracle.solve(oracle.ALG_VERN7, pl.lorenz_source(), np.array([1.0, 0, 0]), p, (0.0, 3.0), 3, 3, saveat=grid, **kw)
+        b = oracle.solve(oracle.ALG_VERN7_GENERATED, pl.lorenz_source(), np.array([1.0, 0, 0]), p, (0.0, 3.0), 3, 3,
+                         saveat=grid, **kw)
+        for key in ("naccept", "nreject", "nf", "retcode", "nsaved"):
+            assert np.array_equal(a[key], b[key])
+        assert np.array_equal(a["u_final"].view(np.uint64), b["u_final"].view(np.uint64))
+        assert np.array_equal(a["us"].view(np.uint64), b["us"].view(np.uint64))
+
+
+@pytest.mark.parametrize("alg,stages,fsal", [(oracle.ALG_VERN6, 8, True), (oracle.ALG_VERN8, 13, False),
+                                             (oracle.ALG_VERN9, 16, False)])
+def test_verner_nf_accounting(pkg, alg, stages, fsal):
+    # increment_nf!(stats, 8 / 13 / 16) per step (verner_rk_perform_step.jl:41,635,1096); Vern6 is FSAL (+1 at start);
+    # lazy interpolation stages are not counted
+    pl = pkg.problems_library
+    p = pl.lorenz_params(32)
+    o = oracle.solve(alg, pl.lorenz_source(), np.array([1.0, 0, 0]), p, (0.0, 2.0), 3, 3, saveat=[0.5, 1.0, 1.7])
+    assert (o["retcode"] == 1).all()
+    assert np.array_equal(o["nf"], 2 + (1 if fsal else 0) + stages * (o["naccept"] + o["nreject"]))
