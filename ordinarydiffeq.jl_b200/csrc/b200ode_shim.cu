@@ -210,7 +210,21 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     // on Pleiades/Vern7 (n = 28): the out-of-line / rolled variants are slower (230-310 ms vs
     // 177-220 ms for 2^18 trajectories) although the fully inlined loop body (470 KB) misses the
     // instruction cache — dynamic indexing forces every stage vector through local memory.
-    bool rhs_inline = true;
+    // Default: inline unless the inlined copies would add up to more source than ptxas digests in reasonable time
+    // (Vern9 x Pleiades, 28 call sites x 6.5 KB: > 15 min inlined, 22 s out of line).
+    int call_sites = 2;     // b200_initdt
+    switch (alg) {
+        case B200ODE_ALG_TSIT5: case B200ODE_ALG_DP5: call_sites += 7; break;
+        case B200ODE_ALG_BS3: call_sites += 4; break;
+        case B200ODE_ALG_VERN6: call_sites += 12; break;
+        case B200ODE_ALG_VERN7: call_sites += 16; break;
+        case B200ODE_ALG_VERN8: call_sites += 21; break;
+        case B200ODE_ALG_VERN9: call_sites += 26; break;
+        case B200ODE_ALG_ROSENBROCK23: call_sites += 3; break;
+        case B200ODE_ALG_RODAS5P: case B200ODE_ALG_RODAS5: call_sites += 8; break;
+        default: call_sites += 6; break;
+    }
+    bool rhs_inline = strlen(rhs_src) * (size_t)call_sites <= 120000;
     if (extra_options && strstr(extra_options, "-DB200_RHS_INLINE=1")) rhs_inline = true;
     if (extra_options && strstr(extra_options, "-DB200_RHS_INLINE=0")) rhs_inline = false;
     tu += std::string(rhs_inline ? "__device__ __forceinline__ void " : "__device__ __noinline__ void ") + rhs_name +

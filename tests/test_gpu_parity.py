@@ -684,8 +684,7 @@ def test_generated_verner_parity(pkg, handle, oracle, name, f32):
 
 
 def test_vern9_wider_state(pkg, handle, oracle):
-    """n = 8 (prob_ode_2Dlinear flattened).  Pleiades (n = 28, 43 KB straight-line RHS) is not paired with Vern9 here:
-    26 inlined copies of that RHS take NVRTC/ptxas more than 15 minutes to compile."""
+    """n = 8 (prob_ode_2Dlinear flattened)."""
     from helpers import linear2d_source
     s, n = linear2d_source(8)
     rng = np.random.default_rng(3)
@@ -697,3 +696,18 @@ def test_vern9_wider_state(pkg, handle, oracle):
     assert_same_result(g, o)
     assert (g["retcode"] == 1).all()
     assert np.allclose(g["u_final"], u0 * np.exp(1.01), rtol=1e-8)
+
+
+def test_vern9_pleiades_out_of_line_rhs(pkg, handle, oracle):
+    """28 inlined copies of the 6.5 KB Pleiades RHS would take ptxas > 15 minutes; the shim keeps the RHS out of line
+    when (source size x call sites) is large (b200ode_shim.cu: rhs_inline).  Same bits either way."""
+    pl = pkg.problems_library
+    u0 = pl.pleiades_u0(96)
+    s, n = pl.pleiades_source()
+    prog = handle.compile(pkg.ALG_VERN9, pkg.F64, 28, 0, s, n)
+    assert prog.info["compile_ms"] < 120e3
+    kw = dict(reltol=1e-8, abstol=1e-10, saveat=[1.0, 2.0, 3.0])
+    g = pkg.lowlevel.solve_host(prog, u0, None, (0.0, 3.0), **kw)
+    o = oracle.solve(oracle.ALG_VERN9, (s, n), u0, None, (0.0, 3.0), 28, 0, **kw)
+    assert_same_result(g, o)
+    assert (g["retcode"] == 1).all()
