@@ -52,8 +52,14 @@ struct B200Ragged            # save_everystep rows (b200ode_solve_everystep); bu
     row_offsets::Ptr{Int64}; ts::Ptr{Float64}; us::Ptr{Cvoid}
 end
 
+# B200ODE_ALG_* of include/b200ode.h
 alg_id(::Tsit5) = 1; alg_id(::Vern7) = 2; alg_id(::Rosenbrock23) = 3; alg_id(::Rodas5P) = 4
-isstiff(alg) = alg isa Union{Rosenbrock23, Rodas5P}
+alg_id(::DP5) = 5; alg_id(::BS3) = 6
+alg_id(::Rodas5) = 7; alg_id(::Rodas4) = 8; alg_id(::Rodas42) = 9; alg_id(::Rodas4P) = 10; alg_id(::Rodas4P2) = 11
+alg_id(::Vern6) = 12; alg_id(::Vern8) = 13; alg_id(::Vern9) = 14
+const StiffAlgs = Union{Rosenbrock23, Rodas5P, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2}
+const B200Algs = Union{Tsit5, Vern6, Vern7, Vern8, Vern9, DP5, BS3, StiffAlgs}
+isstiff(alg) = alg isa StiffAlgs
 const RETCODES = (ReturnCode.Default, ReturnCode.Success, ReturnCode.MaxIters, ReturnCode.DtLessThanMin,
                   ReturnCode.Unstable, ReturnCode.DtNaN)
 
@@ -92,7 +98,7 @@ end
 const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :reltol, :abstol,
                  :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense)
 
-function __solve(eprob::AbstractEnsembleProblem, alg::Union{Tsit5, Vern7, Rosenbrock23, Rodas5P}, ens::EnsembleB200;
+function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB200;
                  trajectories, batch_size = trajectories, kwargs...)
     prob = eprob.prob
     kw = merge(NamedTuple(prob.kwargs), NamedTuple(kwargs))          # merge_problem_kwargs
