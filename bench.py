@@ -370,6 +370,9 @@ def main():
             pass
         roofline = {"bound": "fp64_fma" if not w["f32"] else "fp32_fma", "achieved": achieved, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "bound_note": "compute-bound on the scalar FP64 (FP32) FMA pipe: the path has no contraction, so "
+                                  "neither the tensor-core nor the HBM roofline applies; the HBM side of the same "
+                                  "launch is reported under roofline.hbm",
                     "peak_source": "measured live: b200ode_measure_fma_peak (register-resident FMA chains); "
                                    "MEASURED_PEAKS.json has no FP64 figure",
                     "algorithmic_flops_per_launch": flops_per_launch,
