@@ -98,7 +98,7 @@ struct b200ode_handle_s {
     DevBuf counter, dt0, saveat, scratch_t;
     std::vector<double> saveat_cached;   // grid currently resident in `saveat` ...
     int saveat_cached_dtype = -1;        // ... in this real type
-    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out;
+    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out, scan_tiles;
     // pinned bounce buffers for large D2H copies into pageable caller memory (d2h_large)
     void* stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -417,6 +417,78 @@ __global__ void __launch_bounds__(256) k_colsum_final(const double* __restrict__
 }
 
 // FMA-pipe peak: 8 independent dependent chains per thread, register resident
+// ---- exclusive scan of the per-trajectory row counts (save_everystep): int32[N] -> int64[N+1] -------------
+// Three small launches: per-tile sums (1024 counts per CTA), a single-CTA scan of the tile sums, and the
+// per-tile exclusive scan offset by its tile base.  HBM-bound and tiny next to the integration passes; it only
+// exists so that the counts never travel to the host (8 bytes do: the total).
+#define B200_SCAN_TILE 1024
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const int* __restrict__ counts, long long N, long long* __restrict__ tile_sums) {
+    __shared__ long long sm[256];
+    const long long base = (long long)blockIdx.x * B200_SCAN_TILE;
+    long long acc = 0;
+    for (int k = 0; k < 4; ++k) {
+        long long i = base + threadIdx.x * 4 + k;
+        if (i < N) acc += counts[i];
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = sm[0];
+}
+__global__ void __launch_bounds__(1024) k_scan_tiles(long long* __restrict__ tile_sums, int ntiles, long long* __restrict__ total) {
+    // single CTA, sequential over chunks of 1024 tiles (ntiles is N/1024: a few thousand at most)
+    __shared__ long long sm[1024];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < ntiles; c0 += 1024) {
+        const int i = c0 + (int)threadIdx.x;
+        const long long v = (i < ntiles) ? tile_sums[i] : 0;
+        sm[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan
+            long long add = ((int)threadIdx.x >= off) ? sm[threadIdx.x - off] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < ntiles) tile_sums[i] = carry + sm[threadIdx.x] - v;    // exclusive
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sm[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(const int* __restrict__ counts, long long N, const long long* __restrict__ tile_base,
+                                                    const long long* __restrict__ total, long long* __restrict__ offsets) {
+    __shared__ long long sm[256];
+    const long long base = (long long)blockIdx.x * B200_SCAN_TILE;
+    long long v[4], acc = 0;
+    for (int k = 0; k < 4; ++k) {
+        long long i = base + threadIdx.x * 4 + k;
+        v[k] = (i < N) ? counts[i] : 0;
+        acc += v[k];
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        long long add = ((int)threadIdx.x >= off) ? sm[threadIdx.x - off] : 0;
+        __syncthreads();
+        sm[threadIdx.x] += add;
+        __syncthreads();
+    }
+    long long run = tile_base[blockIdx.x] + sm[threadIdx.x] - acc;
+    for (int k = 0; k < 4; ++k) {
+        long long i = base + threadIdx.x * 4 + k;
+        if (i < N) offsets[i] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[N] = *total;
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256) k_fma_peak(R* out, int iters, R a, R b) {
     R x0 = (R)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -575,7 +647,7 @@ int b200ode_destroy(b200ode_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->counter, &h->dt0, &h->saveat, &h->scratch_t, &h->in_u0, &h->in_p, &h->out_uf, &h->out_tf,
-                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets, &h->rag_dts, &h->dense_tq, &h->dense_out})
+                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets, &h->rag_dts, &h->dense_tq, &h->dense_out, &h->scan_tiles})
         b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -784,7 +856,7 @@ static int d2h_large(b200ode_handle h, void* dst, const void* src, size_t bytes,
 // H2D, counting pass, host exclusive scan, fill pass.  Leaves the ragged rows in the handle's device
 // buffers (out_us, scratch_t = ts, rag_dts, row_offsets) and the scalars in out_uf/out_tf/out_i32.
 static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o,
-                         std::vector<int64_t>& offs) {
+                         long long& total_out) {
     const long long N = hp->trajectories;
     const int n = prog->n, np = prog->np;
     const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
@@ -819,18 +891,22 @@ static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Probl
     // pass 1: count the rows of every trajectory (the integration is deterministic, so pass 2 repeats it exactly)
     int rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, nullptr, nullptr, nullptr, s);
     if (rc) return rc;
-    std::vector<int32_t> counts((size_t)N);
-    CUDA_TRY(cudaMemcpyAsync(counts.data(), i32, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, s));
+    // exclusive scan on the device; only the total comes back (the host needs it to size the buffers)
+    const int ntiles = (int)((N + B200_SCAN_TILE - 1) / B200_SCAN_TILE);
+    CUDA_TRY(h->scan_tiles.ensure(sizeof(long long) * ((size_t)ntiles + 1)));
+    long long* tiles = (long long*)h->scan_tiles.ptr;
+    long long* dtotal = tiles + ntiles;
+    k_scan_tile_sums<<<ntiles, 256, 0, s>>>(i32, N, tiles);
+    k_scan_tiles<<<1, 1024, 0, s>>>(tiles, ntiles, dtotal);
+    k_scan_apply<<<ntiles, 256, 0, s>>>(i32, N, tiles, dtotal, (long long*)h->row_offsets.ptr);
+    long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, dtotal, sizeof(long long), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    offs.resize((size_t)N + 1);
-    int64_t total = 0;
-    for (long long i = 0; i < N; ++i) { offs[(size_t)i] = total; total += counts[(size_t)i]; }
-    offs[(size_t)N] = total;
-    const size_t rows = (size_t)std::max<int64_t>(total, 1);
+    total_out = total;
+    const size_t rows = (size_t)std::max<long long>(total, 1);
     CUDA_TRY(h->out_us.ensure(rs * (size_t)prog->nsave * rows));
     CUDA_TRY(h->scratch_t.ensure(rs * rows));
     CUDA_TRY(h->rag_dts.ensure(rs * rows));
-    CUDA_TRY(cudaMemcpyAsync(h->row_offsets.ptr, offs.data(), sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyHostToDevice, s));
     // pass 2: fill
     dr.us = h->out_us.ptr;
     rc = b200ode_solve_everystep_device(h, prog, &dp, o, &dr, (const int64_t*)h->row_offsets.ptr, h->scratch_t.ptr,
@@ -894,16 +970,19 @@ int b200ode_solve_everystep(b200ode_handle h, b200ode_program prog, const B200Pr
     const int n = prog->nsave;      // row width
     const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
     cudaStream_t s = h->stream;
-    std::vector<int64_t> offs;
-    rc = everystep_run(h, prog, hp, o, offs);
+    long long total_ll = 0;
+    rc = everystep_run(h, prog, hp, o, total_ll);
     if (rc) return rc;
-    const int64_t total = offs[(size_t)N];
+    const int64_t total = (int64_t)total_ll;
     int64_t* offs_host = (int64_t*)malloc(sizeof(int64_t) * ((size_t)N + 1));
     double* ts_host = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
     void* us_host = malloc(rs * (size_t)n * (size_t)std::max<int64_t>(total, 1));
     auto bail = [&](int code) { free(offs_host); free(ts_host); free(us_host); return code; };
     if (!offs_host || !ts_host || !us_host) return bail(fail(B200ODE_EINVAL, "out of host memory"));
-    memcpy(offs_host, offs.data(), sizeof(int64_t) * ((size_t)N + 1));
+    {
+        cudaError_t e0 = cudaMemcpyAsync(offs_host, h->row_offsets.ptr, sizeof(int64_t) * ((size_t)N + 1), cudaMemcpyDeviceToHost, s);
+        if (e0 != cudaSuccess) return bail(fail(B200ODE_ECUDA, std::string("row_offsets D2H: ") + cudaGetErrorString(e0)));
+    }
     std::vector<char> ts_raw;
     rc = d2h_large(h, us_host, h->out_us.ptr, rs * (size_t)n * (size_t)total, s);
     if (rc) return bail(rc);
@@ -979,8 +1058,8 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
     const int n = prog->n;
     const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
     cudaStream_t s = h->stream;
-    std::vector<int64_t> offs;
-    rc = everystep_run(h, prog, hp, o, offs);
+    long long total_ll = 0;
+    rc = everystep_run(h, prog, hp, o, total_ll);
     if (rc) return rc;
     CUDA_TRY(h->dense_tq.ensure(rs * (size_t)nq));
     CUDA_TRY(h->dense_out.ensure(rs * (size_t)n * (size_t)nq * (size_t)N));
