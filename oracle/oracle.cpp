@@ -143,6 +143,8 @@ template <typename R> struct Opts {
     bool save_start, save_end, save_end_user;
     int linsolve;      // 0: StaticWOperator inverse (n<=3), 1: partial-pivot LU
     bool save_everystep = false;   // solve.jl:138 (default isempty(saveat)); ragged rows, see Out::row_offsets
+    // opts.tstops as initialize_tstops builds it (solve.jl:1021-1040): ascending, inside (t0, tf), tf last; NULL: {tf}
+    const R* tstops = nullptr; int ntstops = 0;
 };
 
 // ODE_DEFAULT_NORM(u::StaticArray, t) = sqrt_fast(real(sum(abs2,u)) / max(length(u),1))
@@ -382,6 +384,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
         }
         nsaved += 1; last_saved_t = ts;
     };
+    int tstop_idx = 0;
+    R cur_tstop = (o.ntstops > 0) ? o.tstops[0] : tf;                   // first(opts.tstops)
     // save_start (solve.jl:809-824)
     if (o.save_start) emit(t, u);
     // initialize!(integrator, cache) (solve.jl:831)
@@ -389,7 +393,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     // handle_dt! (solve.jl:968-985): automatic dt when dt == 0 and adaptive
     R dt;
     if (o.dt == (R)0) {
-        R dtmax_init = jl_min(std::fabs(dtmax), std::fabs(tf - t));     // _determine_initdt
+        R dtmax_init = jl_min(std::fabs(dtmax), std::fabs(cur_tstop - t));     // _determine_initdt: first_tstop
         dt = ode_initdt(P, u, p, t, dtmax_init, o.abstol, o.reltol, opts_dtmin, Alg::order);
         stats.nf += 2;
     } else dt = o.dt;
@@ -403,12 +407,12 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     R q11 = (R)1, errold = qoldinit, EEst = (R)1;
     long long iter = 0; int success_iter = 0, naccept = 0, nreject = 0;
     bool accept_step = false, next_step_tstop = false;
-    R tstop_target = tf;
+    R tstop_target = cur_tstop;
     int retcode = RC_DEFAULT;
 
     // modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch
     auto modify_dt_for_tstops = [&]() {
-        R tdir_t = t, tdir_tstop = tf;
+        R tdir_t = t, tdir_tstop = cur_tstop;                           // first_tstop(integrator)
         R distance_to_tstop = std::fabs(tdir_tstop - tdir_t);
         R tstop_tol = (R)100 * jl_eps(jl_max(std::fabs(t), std::fabs(tdir_tstop)));
         R original_dt = std::fabs(dt);
@@ -418,7 +422,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
         dt = jl_min(original_dt, distance_to_tstop);
     };
 
-    // solve! (solve.jl:904-946); tstops = {tf}
+    // solve! (solve.jl:904-946): `while !isempty(tstops); while t < first(tstops) ... end; handle_tstop! end`.
+    // tf is the last stop, so the two loops collapse into this one plus the pop at the end of an accepted step.
     while (t < tf) {
         // ---- loopheader! (integrator_utils.jl:84-127)
         if (iter > 0) {
@@ -444,7 +449,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
             int code = RC_SUCCESS;
             if (std::isnan(dt)) code = RC_DTNAN;
             else if (iter > o.maxiters) code = RC_MAXITERS;
-            else if (std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < tf)) code = RC_DTLESSTHANMIN;
+            else if (std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < cur_tstop)) code = RC_DTLESSTHANMIN;
             else if (!accept_step && std::fabs(dt) <= std::fabs(jl_eps(t))) code = RC_UNSTABLE;
             else if (accept_step) {
                 for (int i = 0; i < n; ++i) if (!Bits<R>::finite(u[i])) code = RC_UNSTABLE;
@@ -503,6 +508,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
             if (o.save_everystep &&
                 (nsaved == 0 || ((t != last_saved_t || dt == (R)0) && (o.save_end || t != tf))))
                 emit(t, u);
+            // handle_tstop! (integrator_utils.jl:1290-1314): pop every copy of a stop that was reached
+            while (o.ntstops > 0 && t == cur_tstop && tstop_idx + 1 < o.ntstops) cur_tstop = o.tstops[++tstop_idx];
         } else {
             nreject += 1;
         }
@@ -595,6 +602,7 @@ struct OracleArgs {
     // save_everystep: row_offsets == NULL is the counting pass
     int save_everystep; const long long* row_offsets; void* ts_rag;
     const int* save_idxs; int nsave_idxs;
+    const double* tstops; int ntstops;      // the tstops keyword, unfiltered
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -615,6 +623,16 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.save_end_user = a.save_end > 0;
     o.linsolve = a.linsolve;
     o.save_everystep = a.save_everystep != 0;
+    std::vector<R> stops;
+    if (a.tstops && a.ntstops > 0) {
+        for (int i = 0; i < a.ntstops; ++i) {
+            R v = (R)a.tstops[i];
+            if (v > (R)a.t0 && v < (R)a.tf) stops.push_back(v);
+        }
+        std::sort(stops.begin(), stops.end());
+        stops.push_back((R)a.tf);
+        o.tstops = stops.data(); o.ntstops = (int)stops.size();
+    }
     Out<R> out;
     out.row_offsets = a.row_offsets; out.ts_rag = (R*)a.ts_rag;
     if (a.save_idxs && a.nsave_idxs > 0) {

@@ -35,7 +35,8 @@ class B200Opts(C.Structure):
     _fields_ = [("reltol", C.c_double), ("abstol", C.c_double), ("dt", C.c_double), ("dtmin", C.c_double),
                 ("dtmax", C.c_double), ("maxiters", C.c_int64), ("saveat", C.POINTER(C.c_double)),
                 ("nsaveat", C.c_int32), ("save_start", C.c_int32), ("save_end", C.c_int32),
-                ("flags", C.c_int32), ("reserved", C.c_int32)]
+                ("flags", C.c_int32), ("reserved", C.c_int32),
+                ("tstops", C.POINTER(C.c_double)), ("ntstops", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class B200Result(C.Structure):
@@ -70,6 +71,7 @@ class B200Ragged(C.Structure):
 
 
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
+OPT_TSTOPS = "-DB200_TSTOPS=1"
 
 
 def opt_save_idxs(idxs):
@@ -226,7 +228,7 @@ class Program:
 
 
 def make_opts(reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None,
-              save_start=None, save_end=None, flags=0):
+              save_start=None, save_end=None, flags=0, tstops=None):
     """Returns (B200Opts, keepalive)."""
     import numpy as np
     o = B200Opts()
@@ -247,4 +249,12 @@ def make_opts(reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiter
     o.save_start = -1 if save_start is None else int(bool(save_start))
     o.save_end = -1 if save_end is None else int(bool(save_end))
     o.flags = int(flags)
+    if tstops is not None and len(tstops) > 0:
+        keep_t = np.ascontiguousarray(tstops, dtype=np.float64)
+        o.tstops = keep_t.ctypes.data_as(C.POINTER(C.c_double))
+        o.ntstops = int(keep_t.shape[0])
+        keep = (keep, keep_t)
+    else:
+        o.tstops = None
+        o.ntstops = 0
     return o, keep

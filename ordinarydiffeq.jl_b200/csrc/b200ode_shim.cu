@@ -68,6 +68,8 @@ struct Params {
     const long long* row_offsets;
     R* ts_rag;
     R* dts_rag;
+    const R* tstops;
+    int ntstops;
 };
 
 struct DevBuf {
@@ -98,7 +100,9 @@ struct b200ode_handle_s {
     DevBuf counter, dt0, saveat, scratch_t;
     std::vector<double> saveat_cached;   // grid currently resident in `saveat` ...
     int saveat_cached_dtype = -1;        // ... in this real type
-    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out, scan_tiles;
+    std::vector<double> tstops_cached;   // same for the tstops list
+    int tstops_cached_dtype = -1;
+    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out, scan_tiles, tstops;
     // pinned bounce buffers for large D2H copies into pageable caller memory (d2h_large)
     void* stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -113,6 +117,7 @@ struct b200ode_program_s {
     int sliced_g = 0;            // > 0: component-sliced kernel with this many warps per 32 trajectories
     int sliced_k = 1;            // groups of 32 trajectories per CTA
     bool everystep = false;      // compiled with -DB200_EVERYSTEP=1 (ragged save_everystep output)
+    bool tstops = false;         // compiled with -DB200_TSTOPS=1
     int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
     B200ProgramInfo info{};
@@ -532,6 +537,27 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     B200Problem hp{}; hp.t0 = dp->t0; hp.tf = dp->tf;
     P.nslots = (dr->us && !prog->everystep) ? b200ode_nslots(&hp, o) : 0;
     P.row_offsets = row_offsets; P.ts_rag = (R*)ts_rag; P.dts_rag = (R*)dts_rag;
+    P.tstops = nullptr; P.ntstops = 0;
+    const bool want_tstops = o->tstops && o->ntstops > 0;
+    if (want_tstops && !prog->tstops) return fail(B200ODE_EINVAL, "opts.tstops needs a program compiled with -DB200_TSTOPS=1");
+    if (prog->tstops) {
+        // initialize_tstops: stops strictly inside (t0, tf), ascending, duplicates kept, tf last — in the real type
+        std::vector<R> stops;
+        for (int i = 0; want_tstops && i < o->ntstops; ++i) {
+            const R v = (R)o->tstops[i];
+            if (v > (R)dp->t0 && v < (R)dp->tf) stops.push_back(v);
+        }
+        std::sort(stops.begin(), stops.end());
+        stops.push_back((R)dp->tf);
+        std::vector<double> key(stops.begin(), stops.end());
+        if (h->tstops_cached_dtype != (int)sizeof(R) || key != h->tstops_cached) {      // re-uploaded only when it changes
+            CUDA_TRY(cudaDeviceSynchronize());      // no launch may still be reading the old list
+            CUDA_TRY(h->tstops.ensure(sizeof(R) * stops.size()));
+            CUDA_TRY(cudaMemcpy(h->tstops.ptr, stops.data(), sizeof(R) * stops.size(), cudaMemcpyHostToDevice));
+            h->tstops_cached = key; h->tstops_cached_dtype = (int)sizeof(R);
+        }
+        P.tstops = (const R*)h->tstops.ptr; P.ntstops = (int)stops.size();
+    }
     P.saveat = nullptr;
     if (P.nsaveat > 0) {
         // the grid travels as real[] in the handle's scratch; re-uploaded only when it changes
@@ -602,6 +628,9 @@ int check_problem(int64_t N, const void* u0, const void* p, int np, double t0, d
             prev = s;
         }
     }
+    if (o->ntstops < 0 || (o->ntstops > 0 && !o->tstops)) return fail(B200ODE_EINVAL, "bad tstops");
+    for (int i = 0; i < o->ntstops; ++i)
+        if (!std::isfinite(o->tstops[i])) return fail(B200ODE_EINVAL, "tstops must be finite");
     if (o->dt < 0) return fail(B200ODE_EINVAL, "dt must be >= 0 (0 = automatic)");
     if (o->dtmin < 0) return fail(B200ODE_EINVAL, "dtmin must be >= 0");
     return B200ODE_OK;
@@ -647,7 +676,7 @@ int b200ode_destroy(b200ode_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->counter, &h->dt0, &h->saveat, &h->scratch_t, &h->in_u0, &h->in_p, &h->out_uf, &h->out_tf,
-                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets, &h->rag_dts, &h->dense_tq, &h->dense_out, &h->scan_tiles})
+                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets, &h->rag_dts, &h->dense_tq, &h->dense_out, &h->scan_tiles, &h->tstops})
         b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -693,6 +722,8 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
                          extra_options, prog->cubin, log, &ms, &prog->sliced_g);
     if (rc) { delete prog; return rc; }
     prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
+    prog->tstops = extra_options && strstr(extra_options, "-DB200_TSTOPS=1");
+    if (prog->tstops && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "tstops are not available in the sliced kernel"); }
     prog->nsave = parse_save_idxs(extra_options, n);
     if (prog->nsave < 0) { delete prog; return fail(B200ODE_EINVAL, "-DB200_SAVE_IDXS= must list 0-based component indices below n, comma separated"); }
     if (prog->nsave == 0) prog->nsave = n;

@@ -137,6 +137,10 @@ struct B200Params {
     const long long* row_offsets;
     real* ts_rag;
     real* dts_rag;            // step size the stages of the step ending at each row were computed with (0 for other rows)
+    // tstops programs (-DB200_TSTOPS=1) only: opts.tstops as initialize_tstops builds it (solve.jl:1021-1040):
+    // ascending, strictly inside (t0, tf), duplicates kept, tf appended last
+    const real* tstops;
+    int ntstops;
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
@@ -153,6 +157,13 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #define B200_SAVE_TAB_DECL
 #define B200_NSAVE B200_N
 #define B200_SAVE_COMP(c) (c)
+#endif
+
+#ifndef B200_TSTOPS
+#define B200_TSTOPS 0         // 1: the tstops keyword (several stop times); 0: tstops = {tf}
+#endif
+#if B200_TSTOPS && B200_SLICED
+#error "tstops are not available in the component-sliced kernel"
 #endif
 
 #ifndef B200_EVERYSTEP
@@ -244,7 +255,12 @@ extern "C" __global__ void __launch_bounds__(256) b200_initdt(B200Params P) {
 #pragma unroll
     for (int c = 0; c < B200_NP; ++c) p[c] = P.p[i * P.p_ts + c * P.p_cs];
     // _determine_initdt: dtmax = min(|opts.dtmax|, |first_tstop - t|)
+    // _determine_initdt: dtmax = min(|opts.dtmax|, |first_tstop - t|) (integrator_interface.jl:643-647)
+#if B200_TSTOPS
+    real dtmax = b200_min(b200_abs(P.dtmax), b200_abs(P.tstops[0] - P.t0));
+#else
     real dtmax = b200_min(b200_abs(P.dtmax), b200_abs(P.tf - P.t0));
+#endif
     P.dt0[i] = b200_initdt_one(u0, p, P.t0, dtmax, P.abstol, P.reltol, P.dtmin, B200Stepper::order());
 }
 
@@ -263,6 +279,10 @@ struct B200Traj {
     int retcode;
     bool accept, tstop_flag;
     real* row;                  // next row of us[idx][.][:] (running pointer: no 64-bit index arithmetic per row)
+#if B200_TSTOPS
+    real tstop;                 // first(opts.tstops)
+    int tstop_idx;
+#endif
 #if B200_EVERYSTEP
     real* trow;                 // next entry of ts_rag
     real* drow;                 // next entry of dts_rag
@@ -343,6 +363,9 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
         T.rfpe = (real)1 / T.fpe;
     }
     T.next_save = (P.nsaveat > 0) ? P.saveat[0] : b200_inf();
+#if B200_TSTOPS
+    T.tstop_idx = 0; T.tstop = P.tstops[0];
+#endif
     T.naccept = 0; T.nreject = 0;
     T.accept = false; T.tstop_flag = false;
     T.retcode = B200_RC_DEFAULT;
@@ -360,10 +383,18 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     // integrator.iter (before its increment) and integrator.success_iter are not stored:
     // iter = naccept + nreject and success_iter = naccept at every point they are read.
     const int iter0 = T.naccept + T.nreject;
+#if B200_TSTOPS
+    const real tstop = T.tstop;
+    const real dist = b200_abs(tstop - T.t);
+    const real at = b200_abs(T.t), atf = b200_abs(tstop);
+    const real tol100 = (real)100 * b200_eps_finite(at > atf ? at : atf);
+#else
+    const real tstop = P.tf;
     const real dist = b200_abs(P.tf - T.t);
     const real at = b200_abs(T.t), atf = b200_abs(P.tf);
     // tstop tolerance 100*eps(max(|t|,|tf|)): a launch constant whenever |t0| <= |tf|
     const real tol100 = P.tol_const ? P.tol100_tf : (real)100 * b200_eps_finite(at > atf ? at : atf);
+#endif
     const real eps_t = b200_eps_finite(T.t);
     const real dtmin_t = eps_t > P.dtmin ? eps_t : P.dtmin;          // timedepentdtmin
     // ---- loopheader! ----
@@ -387,7 +418,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     // ---- check_error ---- (flat predicates; the else-if order of the reference decides the code)
     const bool c_nan = b200_isnan(T.dt);
     const bool c_max = ((long long)iter0 + 1 > P.maxiters);
-    const bool c_min = (b200_abs(T.dt) <= b200_abs(P.dtmin)) & (!T.accept | (T.t + T.dt < P.tf));
+    const bool c_min = (b200_abs(T.dt) <= b200_abs(P.dtmin)) & (!T.accept | (T.t + T.dt < tstop));   // first(opts.tstops) (check_error.jl:93-99)
     const bool c_uns = (!T.accept) & (b200_abs(T.dt) <= eps_t);
     bool bad = false;
 #pragma unroll
@@ -434,7 +465,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         const real dt_stages = T.dt;                // what perform_step! ran with (the dense pass recomputes the stages from it)
 #endif
         if (T.tstop_flag) T.dt = T.dtpropose;       // restore un-clipped dt (integrator_utils.jl:629-633)
-        T.t = T.tstop_flag ? P.tf : ttmp;           // fixed_t_for_tstop_error!
+        T.t = T.tstop_flag ? tstop : ttmp;          // fixed_t_for_tstop_error! (tstop_target)
         T.tstop_flag = false;
         // step_accept_controller!
         if (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) q = (real)1;
@@ -474,6 +505,14 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                 b200_emit(P, idx, T, T.t, T.u, dt_stages);
 #endif
         }
+#if B200_TSTOPS
+        // handle_tstop! (integrator_utils.jl:1290-1314): pop every copy of a stop time that was reached;
+        // the list ends with tf, whose pop ends the solve (the return below)
+        while (T.t == T.tstop && T.tstop_idx + 1 < P.ntstops) {
+            T.tstop_idx += 1;
+            T.tstop = P.tstops[T.tstop_idx];
+        }
+#endif
     } else {
         T.nreject += 1;
     }

@@ -299,7 +299,7 @@ class EnsembleSolution:
 
 
 # ---- solve ------------------------------------------------------------------------------------
-_ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "save_idxs", "reltol",
+_ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "save_idxs", "tstops", "reltol",
                "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags"}
 _program_cache = {}
 _handles = {}
@@ -314,11 +314,13 @@ def _handle(device):
     return _handles[device]
 
 
-def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None):
+def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
     extra = []
     if everystep:
         extra.append(_lib.OPT_EVERYSTEP)
+    if tstops:
+        extra.append(_lib.OPT_TSTOPS)
     if save_idxs is not None:
         extra.append(_lib.opt_save_idxs(save_idxs))
     extra = " ".join(extra) or None
@@ -393,7 +395,9 @@ def solve(eprob, alg, ensemblealg=None, **kw):
         save_idxs = [int(i) for i in (save_idxs if hasattr(save_idxs, "__len__") else [save_idxs])]
         if not save_idxs or min(save_idxs) < 0 or max(save_idxs) >= n:
             raise ValueError("save_idxs out of range for a state of length %d" % n)
-    program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs)
+    tstops = kw.get("tstops", None)
+    tstops = None if tstops is None or len(tstops) == 0 else [float(x) for x in tstops]
+    program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs, tstops is not None)
     save_start, save_end = ranges.resolve_save_flags(kw.get("saveat", None), prob.tspan, everystep,
                                                      kw.get("save_start"), kw.get("save_end"))
 
@@ -401,12 +405,12 @@ def solve(eprob, alg, ensemblealg=None, **kw):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
                       dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
                       saveat=grid if grid else None, save_start=save_start, save_end=save_end,
-                      flags=flags)
+                      flags=flags, tstops=tstops)
         if everystep:
             return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
         return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
 
-    dense_ok = everystep and not grid and save_start and save_idxs is None      # dense = save_everystep && isempty(saveat) (solve.jl:144)
+    dense_ok = everystep and not grid and save_start and save_idxs is None and tstops is None      # dense = save_everystep && isempty(saveat) (solve.jl:144)
     tol_kw = dict(reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
                   dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"))
 

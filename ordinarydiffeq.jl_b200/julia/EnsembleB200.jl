@@ -39,6 +39,7 @@ struct B200Opts
     maxiters::Int64
     saveat::Ptr{Float64}; nsaveat::Int32
     save_start::Int32; save_end::Int32; flags::Int32; reserved::Int32
+    tstops::Ptr{Float64}; ntstops::Int32; reserved2::Int32
 end
 mutable struct B200Result
     u_final::Ptr{Cvoid}; t_final::Ptr{Float64}; us::Ptr{Cvoid}; ts::Ptr{Float64}
@@ -95,7 +96,7 @@ function handle(dev)
     end
 end
 
-const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :reltol, :abstol,
+const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :tstops, :reltol, :abstol,
                  :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense)
 
 function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB200;
@@ -120,6 +121,8 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     extra = String[]
     everystep && push!(extra, "-DB200_EVERYSTEP=1")
     idxs === nothing || push!(extra, "-DB200_SAVE_IDXS=" * join(idxs .- 1, ","))   # the C side is 0-based
+    tstops = collect(Float64, get(kw, :tstops, ()))
+    isempty(tstops) || push!(extra, "-DB200_TSTOPS=1")
     extra_opt = isempty(extra) ? C_NULL : join(extra, " ")
     h = handle(ens.device)
     prog = Ref{Ptr{Cvoid}}(C_NULL)
@@ -135,7 +138,8 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     opts = B200Opts(get(kw, :reltol, 0.0), get(kw, :abstol, 0.0), something(get(kw, :dt, nothing), 0.0),
                     get(kw, :dtmin, 0.0), get(kw, :dtmax, 0.0), get(kw, :maxiters, 0),
                     isempty(grid) ? Ptr{Float64}(C_NULL) : pointer(grid), length(grid),
-                    ss === nothing ? -1 : Int32(ss), se === nothing ? -1 : Int32(se), 0, 0)
+                    ss === nothing ? -1 : Int32(ss), se === nothing ? -1 : Int32(se), 0, 0,
+                    isempty(tstops) ? Ptr{Float64}(C_NULL) : pointer(tstops), length(tstops), 0)
     tstart = time()
     u = eprob.u_init === nothing ? [] : eprob.u_init
     converged = false
@@ -157,7 +161,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
         res = B200Result(pointer(uf), pointer(tfin), nslots > 0 ? pointer(us) : C_NULL, pointer(ts),
                          pointer.(cnt)..., 0.0, 0.0)
         rag = Ref(B200Ragged(0, C_NULL, C_NULL, C_NULL))
-        GC.@preserve U0 P grid uf tfin us ts cnt begin
+        GC.@preserve U0 P grid tstops uf tfin us ts cnt begin
             if everystep     # ragged rows: trajectory k owns rows offs[k]+1 : offs[k+1]
                 check(ccall((:b200ode_solve_everystep, LIB), Cint,
                             (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}, Ref{B200Ragged}),

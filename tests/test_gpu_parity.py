@@ -711,3 +711,40 @@ def test_vern9_pleiades_out_of_line_rhs(pkg, handle, oracle):
     o = oracle.solve(oracle.ALG_VERN9, (s, n), u0, None, (0.0, 3.0), 28, 0, **kw)
     assert_same_result(g, o)
     assert (g["retcode"] == 1).all()
+
+
+# ---- tstops ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("f32", [False, True])
+def test_tstops_parity(pkg, handle, oracle, f32):
+    N = 2000
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N, f32=f32)
+    s, n = pl.lorenz_source(f32)
+    dt = pkg.F32 if f32 else pkg.F64
+    stops = [0.37, 1.0, 1.0, 2.5, 7.0, -3.0]
+    prog = handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n, extra_options=pkg._lib.OPT_TSTOPS)
+    for kw in ({}, {"saveat": [0.37, 0.5, 1.0, 3.0]}, {"maxiters": 12}):
+        g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 3.0), tstops=stops, **kw)
+        o = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 3.0), 3, 3, f32=f32, tstops=stops, **kw)
+        assert_same_result(g, o)
+    base = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 3.0), 3, 3, f32=f32)
+    assert not np.array_equal(o["naccept"], base["naccept"])
+    prog_e = handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n, extra_options=pkg._lib.OPT_TSTOPS + " " + pkg._lib.OPT_EVERYSTEP)
+    ge = pkg.lowlevel.solve_host_everystep(prog_e, U0, p, (0.0, 3.0), tstops=stops)
+    oe = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 3.0), 3, 3, f32=f32, tstops=stops, save_everystep=True)
+    _assert_same_ragged(ge, oe)
+    rdt = np.float32 if f32 else np.float64
+    for i in (0, N - 1):
+        row = ge["ts"][ge["row_offsets"][i]:ge["row_offsets"][i + 1]]
+        for st in (0.37, 1.0, 2.5):
+            assert float(rdt(st)) in row                       # every stop is a step end point
+    # a program without the option refuses tstops; stiff steppers take them too
+    with pytest.raises(pkg.B200Error):
+        pkg.lowlevel.solve_host(handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n), U0, p, (0.0, 3.0), tstops=stops)
+    if not f32:
+        r, j, tg = pl.robertson_sources()
+        k = pl.robertson_params(512)
+        progr = handle.compile(pkg.ALG_RODAS5P, pkg.F64, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1], extra_options=pkg._lib.OPT_TSTOPS)
+        g = pkg.lowlevel.solve_host(progr, U0, k, (0.0, 100.0), tstops=[1.0, 10.0], reltol=1e-6, abstol=1e-8)
+        o = oracle.solve(oracle.ALG_RODAS5P, r, U0, k, (0.0, 100.0), 3, 3, jac=j, tgrad=tg, tstops=[1.0, 10.0], reltol=1e-6, abstol=1e-8)
+        assert_same_result(g, o)

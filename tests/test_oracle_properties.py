@@ -404,3 +404,25 @@ def test_verner_nf_accounting(pkg, alg, stages, fsal):
     o = oracle.solve(alg, pl.lorenz_source(), np.array([1.0, 0, 0]), p, (0.0, 2.0), 3, 3, saveat=[0.5, 1.0, 1.7])
     assert (o["retcode"] == 1).all()
     assert np.array_equal(o["nf"], 2 + (1 if fsal else 0) + stages * (o["naccept"] + o["nreject"]))
+
+
+# ---- tstops -------------------------------------------------------------------------------------
+def test_tstops_are_hit_exactly_and_saved():
+    # test/InterfaceI/ode_saveat_tests.jl:27-36: saveat = [1/2] with tstops = [1/2] gives sol.t == [1/2]; the stop
+    # time is a step end point (no interpolation); stops outside (t0, tf) are dropped, duplicates are harmless
+    s = linear_source()
+    u0 = np.array([[0.5]])
+    o = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.25, saveat=[0.5], tstops=[0.5],
+                     save_start=False, save_end=False)
+    assert list(o["ts"]) == [0.5] and o["nsaved"][0] == 1
+    e = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.25, save_everystep=True,
+                     tstops=[0.5, 0.3, 0.3, 2.0, -1.0, 1.0])
+    assert 0.3 in e["ts"] and 0.5 in e["ts"] and e["ts"][-1] == 1.0 and list(e["ts"]) == sorted(set(e["ts"]))
+    plain = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.25, save_everystep=True)
+    assert 0.3 not in plain["ts"]
+    # the row saved at a stop time is the step's own end state: it equals the final state of a solve that ends there
+    half = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 0.3), 1, 0, dt=0.25)
+    assert e["us"][list(e["ts"]).index(0.3), 0] == half["u_final"][0, 0]
+    # an empty / out-of-range list changes nothing
+    same = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.25, save_everystep=True, tstops=[5.0])
+    assert np.array_equal(same["ts"], plain["ts"]) and np.array_equal(same["us"], plain["us"])
