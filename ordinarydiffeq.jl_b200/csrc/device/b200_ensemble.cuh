@@ -601,10 +601,13 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
     long long pool_next = 0, pool_end = 0;     // warp-uniform
     long long idx = -1;
     bool active = false;
-    bool exhausted = false;                    // warp-uniform: global counter ran past N
+    // "exhausted" (the global counter ran past N) is not stored: it is pool_next >= N.  A pool that ends exactly
+    // at N was the last chunk the counter handed out, so nothing is left in that case either.  (A separate flag
+    // was spilled to local memory and re-loaded at the top of every iteration.)
+#define B200_EXHAUSTED (pool_next >= P.N)
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !active);
-        if (need != 0u && !exhausted) {
+        if (need != 0u && !B200_EXHAUSTED) {
             const int want = __popc(need);
             if (pool_end - pool_next < want) {
                 // refill the warp pool: guided chunk (large while plenty of work remains,
@@ -632,7 +635,6 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
                 }
                 pool_next = base + (want - old_left);
                 pool_end = got_end;
-                if (base >= P.N) exhausted = true;
                 if (pool_end > P.N) pool_end = P.N > pool_next ? P.N : pool_next;
             } else {
                 if (!active) {
@@ -647,7 +649,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
         }
         const unsigned am = __ballot_sync(0xffffffffu, active);
         if (am == 0u) {
-            if (exhausted || need == 0u) break;
+            if (B200_EXHAUSTED || need == 0u) break;
             continue;
         }
         if (active) {
