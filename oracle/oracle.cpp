@@ -145,6 +145,7 @@ template <typename R> struct Opts {
     bool save_everystep = false;   // solve.jl:138 (default isempty(saveat)); ragged rows, see Out::row_offsets
     // opts.tstops as initialize_tstops builds it (solve.jl:1021-1040): ascending, inside (t0, tf), tf last; NULL: {tf}
     const R* tstops = nullptr; int ntstops = 0;
+    bool adaptive = true;          // false: fixed dt = opts.dt (dtcache), every step accepted
 };
 
 // ODE_DEFAULT_NORM(u::StaticArray, t) = sqrt_fast(real(sum(abs2,u)) / max(length(u),1))
@@ -392,7 +393,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     if (Alg::fsal_init()) cache.initialize(uprev, p, t, stats);
     // handle_dt! (solve.jl:968-985): automatic dt when dt == 0 and adaptive
     R dt;
-    if (o.dt == (R)0) {
+    const R dtcache = o.dt;                                            // solve.jl:699
+    if (o.dt == (R)0 && o.adaptive) {
         R dtmax_init = jl_min(std::fabs(dtmax), std::fabs(cur_tstop - t));     // _determine_initdt: first_tstop
         dt = ode_initdt(P, u, p, t, dtmax_init, o.abstol, o.reltol, opts_dtmin, Alg::order);
         stats.nf += 2;
@@ -415,11 +417,20 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
         R tdir_t = t, tdir_tstop = cur_tstop;                           // first_tstop(integrator)
         R distance_to_tstop = std::fabs(tdir_tstop - tdir_t);
         R tstop_tol = (R)100 * jl_eps(jl_max(std::fabs(t), std::fabs(tdir_tstop)));
-        R original_dt = std::fabs(dt);
-        dtpropose = original_dt;
-        if (original_dt + tstop_tol < distance_to_tstop) next_step_tstop = false;
-        else { next_step_tstop = true; tstop_target = tdir_tstop; }
-        dt = jl_min(original_dt, distance_to_tstop);
+        if (o.adaptive) {
+            R original_dt = std::fabs(dt);
+            dtpropose = original_dt;
+            if (original_dt + tstop_tol < distance_to_tstop) next_step_tstop = false;
+            else { next_step_tstop = true; tstop_target = tdir_tstop; }
+            dt = jl_min(original_dt, distance_to_tstop);
+        } else if (dtcache == (R)0) {                                   // (:300-304) step from stop to stop
+            dt = distance_to_tstop;
+            next_step_tstop = true; tstop_target = tdir_tstop;
+        } else {                                                        // (:305-316) dtchangeable, !force_stepfail
+            if (std::fabs(dtcache) + tstop_tol < distance_to_tstop) next_step_tstop = false;
+            else { next_step_tstop = true; tstop_target = tdir_tstop; }
+            dt = jl_min(std::fabs(dtcache), distance_to_tstop);
+        }
     };
 
     // solve! (solve.jl:904-946): `while !isempty(tstops); while t < first(tstops) ... end; handle_tstop! end`.
@@ -427,7 +438,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     while (t < tf) {
         // ---- loopheader! (integrator_utils.jl:84-127)
         if (iter > 0) {
-            if (accept_step) {
+            if (accept_step || !o.adaptive) {                          // (:98-110)
                 success_iter += 1;
                 // apply_step! (:175-203)
                 for (int i = 0; i < n; ++i) uprev[i] = u[i];
@@ -449,8 +460,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
             int code = RC_SUCCESS;
             if (std::isnan(dt)) code = RC_DTNAN;
             else if (iter > o.maxiters) code = RC_MAXITERS;
-            else if (std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < cur_tstop)) code = RC_DTLESSTHANMIN;
-            else if (!accept_step && std::fabs(dt) <= std::fabs(jl_eps(t))) code = RC_UNSTABLE;
+            else if (o.adaptive && std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < cur_tstop)) code = RC_DTLESSTHANMIN;
+            else if (o.adaptive && !accept_step && std::fabs(dt) <= std::fabs(jl_eps(t))) code = RC_UNSTABLE;
             else if (accept_step) {
                 for (int i = 0; i < n; ++i) if (!Bits<R>::finite(u[i])) code = RC_UNSTABLE;
             }
@@ -464,31 +475,39 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
         }
         // ---- loopfooter! (:597-677)
         R ttmp = t + dt;
-        // stepsize_controller!(integrator, ::PIControllerCache, alg) (controllers.jl:805-821)
-        R qmax_cur = (success_iter == 0) ? qmax_first_step : qmax;      // get_current_qmax (:288-293)
-        R q;
-        if (EEst == (R)0) q = (R)1 / qmax_cur;
-        else {
-            R q11_new = fastpower(EEst, beta1);
-            q = q11_new / fastpower(errold, beta2);
-            q11 = q11_new;
-            q = q / gamma;
-            R lo = (R)1 / qmax_cur, hi = (R)1 / qmin;
-            q = q < lo ? lo : (q > hi ? hi : q);
+        R q = (R)1;
+        if (o.adaptive) {
+            // stepsize_controller!(integrator, ::PIControllerCache, alg) (controllers.jl:805-821)
+            R qmax_cur = (success_iter == 0) ? qmax_first_step : qmax;      // get_current_qmax (:288-293)
+            if (EEst == (R)0) q = (R)1 / qmax_cur;
+            else {
+                R q11_new = fastpower(EEst, beta1);
+                q = q11_new / fastpower(errold, beta2);
+                q11 = q11_new;
+                q = q / gamma;
+                R lo = (R)1 / qmax_cur, hi = (R)1 / qmin;
+                q = q < lo ? lo : (q > hi ? hi : q);
+            }
+            accept_step = (EEst <= (R)1);                                  // accept_step_controller (:245-250)
+        } else {
+            accept_step = true;                                            // not adaptive (:650-659)
         }
-        accept_step = (EEst <= (R)1);                                  // accept_step_controller (:245-250)
         if (accept_step) {
             naccept += 1;
             tprev = t;
-            if (next_step_tstop) dt = dtpropose;                       // (:629-633)
+            if (o.adaptive && next_step_tstop) dt = dtpropose;         // (:629-633)
             if (next_step_tstop) { next_step_tstop = false; t = tstop_target; } else t = ttmp;   // fixed_t_for_tstop_error!
-            // step_accept_controller! (controllers.jl:823-836)
-            if (qsteady_min <= q && q <= qsteady_max) q = (R)1;
-            errold = jl_max(EEst, qoldinit);
-            R dtnew = dt / q;
-            // calc_dt_propose! (:1199-1210)
-            dtpropose = jl_min(std::fabs(dtmax), std::fabs(dtnew));
-            dtpropose = jl_max(std::fabs(dtpropose), jl_max(jl_eps(t), opts_dtmin));
+            if (o.adaptive) {
+                // step_accept_controller! (controllers.jl:823-836)
+                if (qsteady_min <= q && q <= qsteady_max) q = (R)1;
+                errold = jl_max(EEst, qoldinit);
+                R dtnew = dt / q;
+                // calc_dt_propose! (:1199-1210)
+                dtpropose = jl_min(std::fabs(dtmax), std::fabs(dtnew));
+                dtpropose = jl_max(std::fabs(dtpropose), jl_max(jl_eps(t), opts_dtmin));
+            } else {
+                dtpropose = dt;
+            }
             // handle_callbacks! -> savevalues! (:340-414)
             bool added = false;
             while (save_idx < o.nsaveat && o.saveat[save_idx] <= t) {
@@ -603,6 +622,7 @@ struct OracleArgs {
     int save_everystep; const long long* row_offsets; void* ts_rag;
     const int* save_idxs; int nsave_idxs;
     const double* tstops; int ntstops;      // the tstops keyword, unfiltered
+    int fixed_dt;                           // 1: adaptive = false
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -623,6 +643,8 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.save_end_user = a.save_end > 0;
     o.linsolve = a.linsolve;
     o.save_everystep = a.save_everystep != 0;
+    o.adaptive = a.fixed_dt == 0;
+    if (!o.adaptive && a.dt == 0.0 && !(a.tstops && a.ntstops > 0)) return -4;     // solve.jl:277-280
     std::vector<R> stops;
     if (a.tstops && a.ntstops > 0) {
         for (int i = 0; i < a.ntstops; ++i) {

@@ -48,7 +48,7 @@ class OracleArgs(C.Structure):
                 ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p),
                 ("save_everystep", C.c_int), ("row_offsets", C.c_void_p), ("ts_rag", C.c_void_p),
                 ("save_idxs", C.c_void_p), ("nsave_idxs", C.c_int),
-                ("tstops", C.c_void_p), ("ntstops", C.c_int)]
+                ("tstops", C.c_void_p), ("ntstops", C.c_int), ("fixed_dt", C.c_int)]
 
 
 _lib = None
@@ -123,7 +123,7 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
 
 def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
           abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
-          linsolve=0, nthreads=0, save_everystep=False, dense_tq=None, save_idxs=None, tstops=None):
+          linsolve=0, nthreads=0, save_everystep=False, dense_tq=None, save_idxs=None, tstops=None, adaptive=True):
     """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host.
     save_everystep=True returns ragged rows (row_offsets, ts, us[total, n]) like lowlevel.solve_host_everystep."""
     L = lib()
@@ -165,6 +165,7 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     a.linsolve = linsolve; a.nthreads = nthreads
     if idxs is not None:
         a.save_idxs = idxs.ctypes.data; a.nsave_idxs = len(idxs)
+    a.fixed_dt = 0 if adaptive else 1
     stops = None
     if tstops is not None and len(tstops) > 0:
         stops = np.ascontiguousarray(tstops, dtype=np.float64)

@@ -72,6 +72,7 @@ class B200Ragged(C.Structure):
 
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
 OPT_TSTOPS = "-DB200_TSTOPS=1"
+OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
 
 
 def opt_save_idxs(idxs):

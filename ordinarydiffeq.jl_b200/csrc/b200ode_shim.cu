@@ -118,6 +118,7 @@ struct b200ode_program_s {
     int sliced_k = 1;            // groups of 32 trajectories per CTA
     bool everystep = false;      // compiled with -DB200_EVERYSTEP=1 (ragged save_everystep output)
     bool tstops = false;         // compiled with -DB200_TSTOPS=1
+    bool adaptive = true;        // false: compiled with -DB200_ADAPTIVE=0 (fixed dt)
     int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
     B200ProgramInfo info{};
@@ -592,8 +593,10 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     }
     CUDA_TRY(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned long long), stream));
 
+    if (!prog->adaptive && o->dt == 0.0 && !want_tstops)
+        return fail(B200ODE_EINVAL, "Fixed timestep methods require a choice of dt or choosing the tstops");   // solve.jl:277-280
     void* args[] = {&P};
-    if (o->dt == 0.0) {
+    if (o->dt == 0.0 && prog->adaptive) {
         unsigned g = (unsigned)((N + 255) / 256);
         CUDA_TRY(cudaLaunchKernel((const void*)prog->k_initdt, dim3(g), dim3(256), args, 0, stream));
     }
@@ -723,6 +726,8 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     if (rc) { delete prog; return rc; }
     prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
     prog->tstops = extra_options && strstr(extra_options, "-DB200_TSTOPS=1");
+    prog->adaptive = !(extra_options && strstr(extra_options, "-DB200_ADAPTIVE=0"));
+    if (!prog->adaptive && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "adaptive=false is not available in the sliced kernel"); }
     if (prog->tstops && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "tstops are not available in the sliced kernel"); }
     prog->nsave = parse_save_idxs(extra_options, n);
     if (prog->nsave < 0) { delete prog; return fail(B200ODE_EINVAL, "-DB200_SAVE_IDXS= must list 0-based component indices below n, comma separated"); }

@@ -159,6 +159,13 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #define B200_SAVE_COMP(c) (c)
 #endif
 
+#ifndef B200_ADAPTIVE
+#define B200_ADAPTIVE 1       // 0: adaptive = false — fixed dt = opts.dt (dtcache), every step accepted, no controller
+#endif
+#if !B200_ADAPTIVE && B200_SLICED
+#error "adaptive=false is not available in the component-sliced kernel"
+#endif
+
 #ifndef B200_TSTOPS
 #define B200_TSTOPS 0         // 1: the tstops keyword (several stop times); 0: tstops = {tf}
 #endif
@@ -318,12 +325,23 @@ B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, 
 
 // modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch, tstops={tf}.
 // tol100 = 100*eps(max(|t|,|tf|)) and dist = |tf - t| depend only on t.
-B200_D void b200_modify_dt_for_tstops(B200Traj& T, real dist, real tol100) {
+#if B200_ADAPTIVE
+B200_D void b200_modify_dt_for_tstops(const B200Params&, B200Traj& T, real dist, real tol100) {
     real orig = b200_abs(T.dt);
     T.dtpropose = orig;
     T.tstop_flag = !(orig + tol100 < dist);
     T.dt = b200_min_c(dist, orig);
 }
+#else
+// non-adaptive branches (integrator_utils.jl:300-316; dtchangeable): always step with dtcache = opts.dt,
+// shortened to the next stop; dtcache == 0 steps from stop to stop
+B200_D void b200_modify_dt_for_tstops(const B200Params& P, B200Traj& T, real dist, real tol100) {
+    const real dtcache = b200_abs(P.dt_user);
+    if (dtcache == (real)0) { T.dt = dist; T.tstop_flag = true; return; }
+    T.tstop_flag = !(dtcache + tol100 < dist);
+    T.dt = b200_min_c(dist, dtcache);
+}
+#endif
 
 B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
 #pragma unroll
@@ -353,8 +371,12 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
 #endif
     if (P.save_start) b200_emit(P, idx, T, T.t, T.u);      // solve.jl:809-824
     T.st.init(T.u, T.p, T.t, T.nf);                   // initialize!(integrator, cache)
+#if B200_ADAPTIVE
     if (P.dt_user == (real)0) { T.dt = P.dt0[idx]; T.nf += 2; }   // auto_dt_reset!: nf += 2
     else T.dt = P.dt_user;
+#else
+    T.dt = P.dt_user;          // handle_dt!: the automatic initial dt is adaptive-only (solve.jl:968-985)
+#endif
     T.dtpropose = T.dt;
     T.q11 = (real)1; T.EEst = (real)1;                            // setup_controller_cache (controllers.jl:793-803)
     {   // errold = qoldinit = 1e-4; only fastpower(errold, beta2) is ever used
@@ -405,7 +427,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
             for (int c = 0; c < B200_N; ++c) T.uprev[c] = T.u[c];
             T.dt = T.dtpropose;
             T.st.accept();
-            b200_modify_dt_for_tstops(T, dist, tol100);
+            b200_modify_dt_for_tstops(P, T, dist, tol100);
         } else {
             // step_reject_controller!: dt /= min(inv(qmin), q11/gamma)
             T.dt = T.dt / b200_min_c((real)1 / qmin, b200_div_const(T.q11, gamma, (real)1 / gamma));
@@ -414,12 +436,20 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     // fix_dt_at_bounds!
     T.dt = b200_min_c(P.dtmax, T.dt);
     T.dt = b200_max_c(dtmin_t, T.dt);
-    b200_modify_dt_for_tstops(T, dist, tol100);
+    b200_modify_dt_for_tstops(P, T, dist, tol100);
     // ---- check_error ---- (flat predicates; the else-if order of the reference decides the code)
     const bool c_nan = b200_isnan(T.dt);
     const bool c_max = ((long long)iter0 + 1 > P.maxiters);
+#if B200_ADAPTIVE
     const bool c_min = (b200_abs(T.dt) <= b200_abs(P.dtmin)) & (!T.accept | (T.t + T.dt < tstop));   // first(opts.tstops) (check_error.jl:93-99)
+#else
+    const bool c_min = false;
+#endif
+#if B200_ADAPTIVE
     const bool c_uns = (!T.accept) & (b200_abs(T.dt) <= eps_t);
+#else
+    const bool c_uns = false;           // the dtmin / eps(t) checks are adaptive-only (check_error.jl:91)
+#endif
     bool bad = false;
 #pragma unroll
     for (int c = 0; c < B200_N; ++c) bad = bad | !b200_isfinite(T.u[c]);
@@ -442,6 +472,11 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     if (!ok) return true;
     // ---- loopfooter! ----
     const real ttmp = T.t + T.dt;
+#if !B200_ADAPTIVE
+    // not adaptive (integrator_utils.jl:650-659): every step is accepted, dtpropose = dt, no controller
+    T.accept = true;
+    real q = (real)1;
+#else
     // stepsize_controller!(integrator, ::PIControllerCache, alg)
     const real qmax_eff = (T.naccept == 0) ? (real)10000 : qmax;
     real q;
@@ -458,15 +493,22 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         T.q11 = zero ? T.q11 : q11;
     }
     T.accept = (T.EEst <= (real)1);
+#endif
     if (T.accept) {
         T.naccept += 1;
         T.tprev = T.t;
 #if B200_EVERYSTEP
         const real dt_stages = T.dt;                // what perform_step! ran with (the dense pass recomputes the stages from it)
 #endif
+#if B200_ADAPTIVE
         if (T.tstop_flag) T.dt = T.dtpropose;       // restore un-clipped dt (integrator_utils.jl:629-633)
+#endif
         T.t = T.tstop_flag ? tstop : ttmp;          // fixed_t_for_tstop_error! (tstop_target)
         T.tstop_flag = false;
+#if !B200_ADAPTIVE
+        T.dtpropose = T.dt;
+        (void)q; (void)beta1; (void)beta2; (void)qmin; (void)qmax; (void)gamma;
+#else
         // step_accept_controller!
         if (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) q = (real)1;
         {   // errold = max(EEst, qoldinit); its fastpower is all later steps need
@@ -478,6 +520,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         // calc_dt_propose!: eps at the NEW t
         const real eps_n = b200_eps_finite(T.t);
         T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
+#endif
         // handle_callbacks! -> savevalues!
         {
             bool dense_ready = false;

@@ -314,13 +314,15 @@ def _handle(device):
     return _handles[device]
 
 
-def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False):
+def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
     extra = []
     if everystep:
         extra.append(_lib.OPT_EVERYSTEP)
     if tstops:
         extra.append(_lib.OPT_TSTOPS)
+    if not adaptive:
+        extra.append(_lib.OPT_FIXED_DT)
     if save_idxs is not None:
         extra.append(_lib.opt_save_idxs(save_idxs))
     extra = " ".join(extra) or None
@@ -374,8 +376,10 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     has_saveat = kw.get("saveat", None) is not None and not (hasattr(kw["saveat"], "__len__") and len(kw["saveat"]) == 0)
     # the reference's default is save_everystep = isempty(saveat) (solve.jl:138): ragged per-step output
     everystep = bool(kw.get("save_everystep", not has_saveat))
-    if not kw.get("adaptive", True):
-        raise NotImplementedError("adaptive=false is not on this path")
+    adaptive = bool(kw.get("adaptive", True))
+    if not adaptive and kw.get("dt") is None and not kw.get("tstops"):
+        # solve.jl:277-280
+        raise ValueError("Fixed timestep methods require a choice of dt or choosing the tstops")
     if kw.get("dense", False):
         raise NotImplementedError("dense=true is not on this path")
     N = int(kw["trajectories"])
@@ -397,7 +401,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             raise ValueError("save_idxs out of range for a state of length %d" % n)
     tstops = kw.get("tstops", None)
     tstops = None if tstops is None or len(tstops) == 0 else [float(x) for x in tstops]
-    program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs, tstops is not None)
+    program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs, tstops is not None, adaptive)
     save_start, save_end = ranges.resolve_save_flags(kw.get("saveat", None), prob.tspan, everystep,
                                                      kw.get("save_start"), kw.get("save_end"))
 

@@ -123,6 +123,10 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     idxs === nothing || push!(extra, "-DB200_SAVE_IDXS=" * join(idxs .- 1, ","))   # the C side is 0-based
     tstops = collect(Float64, get(kw, :tstops, ()))
     isempty(tstops) || push!(extra, "-DB200_TSTOPS=1")
+    adaptive = get(kw, :adaptive, true)
+    adaptive || push!(extra, "-DB200_ADAPTIVE=0")
+    adaptive || get(kw, :dt, nothing) !== nothing || !isempty(tstops) ||
+        throw(ArgumentError("Fixed timestep methods require a choice of dt or choosing the tstops"))
     extra_opt = isempty(extra) ? C_NULL : join(extra, " ")
     h = handle(ens.device)
     prog = Ref{Ptr{Cvoid}}(C_NULL)

@@ -748,3 +748,38 @@ def test_tstops_parity(pkg, handle, oracle, f32):
         g = pkg.lowlevel.solve_host(progr, U0, k, (0.0, 100.0), tstops=[1.0, 10.0], reltol=1e-6, abstol=1e-8)
         o = oracle.solve(oracle.ALG_RODAS5P, r, U0, k, (0.0, 100.0), 3, 3, jac=j, tgrad=tg, tstops=[1.0, 10.0], reltol=1e-6, abstol=1e-8)
         assert_same_result(g, o)
+
+
+# ---- adaptive = false -----------------------------------------------------------------------------
+@pytest.mark.parametrize("f32", [False, True])
+def test_fixed_step_parity(pkg, handle, oracle, f32):
+    N = 1500
+    pl = pkg.problems_library
+    p = pl.lorenz_params(N, f32=f32)
+    s, n = pl.lorenz_source(f32)
+    dt = pkg.F32 if f32 else pkg.F64
+    L = pkg._lib
+    prog = handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n, extra_options=L.OPT_FIXED_DT)
+    for kw in ({"dt": 0.01}, {"dt": 0.03, "saveat": [0.5, 1.0, 1.5]}, {"dt": 0.01, "maxiters": 50}):
+        g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 2.0), **kw)
+        o = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 2.0), 3, 3, f32=f32, adaptive=False, **kw)
+        assert_same_result(g, o)
+    assert (g["retcode"] == 2).all()
+    with pytest.raises(pkg.B200Error):                                  # neither dt nor tstops
+        pkg.lowlevel.solve_host(prog, U0, p, (0.0, 2.0))
+    prog2 = handle.compile(pkg.ALG_TSIT5, dt, 3, 3, s, n,
+                           extra_options=" ".join([L.OPT_FIXED_DT, L.OPT_TSTOPS, L.OPT_EVERYSTEP]))
+    # (dt = 0.3 would be beyond Lorenz's stability limit: those trajectories end Unstable on both sides with the
+    # same counters, but the NaN payloads of x86 and the GPU differ, so states are compared on a stable step only)
+    ge = pkg.lowlevel.solve_host_everystep(prog2, U0, p, (0.0, 2.0), dt=0.03, tstops=[0.5, 1.25])
+    oe = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 2.0), 3, 3, f32=f32, adaptive=False, dt=0.03,
+                      tstops=[0.5, 1.25], save_everystep=True)
+    _assert_same_ragged(ge, oe)
+    assert (ge["retcode"] == 1).all() and (ge["nsaved"] == ge["nsaved"][0]).all()    # one step grid for every trajectory
+    if not f32:
+        r, j, tg = pl.robertson_sources()
+        k = pl.robertson_params(256)
+        pr = handle.compile(pkg.ALG_RODAS5P, pkg.F64, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1], extra_options=L.OPT_FIXED_DT)
+        g = pkg.lowlevel.solve_host(pr, U0, k, (0.0, 1.0), dt=0.01)
+        o = oracle.solve(oracle.ALG_RODAS5P, r, U0, k, (0.0, 1.0), 3, 3, jac=j, tgrad=tg, adaptive=False, dt=0.01)
+        assert_same_result(g, o)

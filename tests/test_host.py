@@ -68,7 +68,7 @@ def test_solve_keyword_contract(pkg):
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), saveat=0.1)        # trajectories missing
     with pytest.raises(NotImplementedError):                        # dense sol(t) objects are not on this path
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, dense=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                                 # solve.jl:277-280: fixed step needs dt (or tstops)
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, adaptive=False)
 
 

@@ -426,3 +426,30 @@ def test_tstops_are_hit_exactly_and_saved():
     # an empty / out-of-range list changes nothing
     same = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.25, save_everystep=True, tstops=[5.0])
     assert np.array_equal(same["ts"], plain["ts"]) and np.array_equal(same["us"], plain["us"])
+
+
+# ---- adaptive = false ----------------------------------------------------------------------------
+def test_fixed_step_mode():
+    s = linear_source()
+    u0 = np.array([[0.5]])
+    # test/InterfaceI/ode_saveat_tests.jl:44-50 (RK4 there): fixed dt = 1/4 with save_everystep; adding saveat
+    # inserts exactly those times
+    a = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.25, adaptive=False, save_everystep=True)
+    assert list(a["ts"]) == [0.0, 0.25, 0.5, 0.75, 1.0] and a["naccept"][0] == 4 and a["nreject"][0] == 0
+    b = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.25, adaptive=False, save_everystep=True,
+                     saveat=[0.125, 0.6, 0.61, 0.8])
+    assert sorted(set(a["ts"]) ^ set(b["ts"])) == [0.125, 0.6, 0.61, 0.8]
+    assert a["nf"][0] == 1 + 6 * 4                                    # no automatic initial dt (handle_dt! is adaptive-only)
+    # the tolerance-free emulation the convergence tests use (huge tolerances, dtmax = dt) takes the same steps
+    e = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=1 / 16, dtmax=1 / 16, reltol=1e12, abstol=1e12,
+                     save_everystep=True)
+    f = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=1 / 16, adaptive=False, save_everystep=True)
+    assert np.array_equal(e["us"], f["us"]) and np.array_equal(e["ts"], f["ts"])
+    # a dt that does not divide the span: the last step is shortened to land on tf; stops are honoured
+    g = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, dt=0.3, adaptive=False, save_everystep=True, tstops=[0.5])
+    assert np.allclose(g["ts"], [0.0, 0.3, 0.5, 0.8, 1.0], atol=1e-15) and g["ts"][2] == 0.5 and g["ts"][-1] == 1.0
+    # dt = 0: step from stop to stop
+    h = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, adaptive=False, save_everystep=True, tstops=[0.25, 0.5])
+    assert list(h["ts"]) == [0.0, 0.25, 0.5, 1.0]
+    with pytest.raises(RuntimeError):
+        oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, adaptive=False)
