@@ -300,7 +300,10 @@ class EnsembleSolution:
 
 # ---- solve ------------------------------------------------------------------------------------
 _ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "save_idxs", "tstops", "reltol",
-               "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags"}
+               "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags", "save_on"}
+# accepted and ignored: they do not change the numbers (logging / progress / error-statistics switches of solve.jl:166-181)
+_IGNORED_KW = {"verbose", "progress", "progress_steps", "progress_name", "progress_message", "progress_id",
+               "timeseries_errors", "dense_errors", "alias", "userdata"}
 _program_cache = {}
 _handles = {}
 
@@ -367,6 +370,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
         raise TypeError("alg must be one of Tsit5(), Vern7(), DP5(), BS3(), Rosenbrock23(), Rodas4/42/4P/4P2/5/5P()")
     prob = eprob.prob
     kw = dict(prob.kwargs, **kw)                      # merge_problem_kwargs: solve's kwargs win
+    kw = {k: v for k, v in kw.items() if k not in _IGNORED_KW}
     bad = set(kw) - _ALLOWED_KW
     if bad:
         # the reference throws for unrecognised keywords (lib/DiffEqBase/src/solve.jl:79-93)
@@ -392,6 +396,13 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     n = int(prob.u0.shape[-1])
     np_ = 0 if prob.p is None else int(np.asarray(prob.p).shape[-1])
     grid = ranges.saveat_grid(kw.get("saveat", None), prob.tspan)
+    # save_start / save_end defaults depend on the keywords as given (solve.jl:141-143,596-599) ...
+    save_start, save_end = ranges.resolve_save_flags(kw.get("saveat", None), prob.tspan, everystep,
+                                                     kw.get("save_start"), kw.get("save_end"))
+    if not kw.get("save_on", True):
+        # ... while save_on = false only silences _savevalues! (integrator_utils.jl:342): no saveat / per-step rows,
+        # the start row and the end point are still stored
+        grid, everystep = [], False
     handle = _handle(ensemblealg.device)
     # save_idxs: component indices of the saved rows, 0-based here (the Julia binding converts from 1-based)
     save_idxs = kw.get("save_idxs", None)
@@ -402,8 +413,6 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     tstops = kw.get("tstops", None)
     tstops = None if tstops is None or len(tstops) == 0 else [float(x) for x in tstops]
     program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs, tstops is not None, adaptive)
-    save_start, save_end = ranges.resolve_save_flags(kw.get("saveat", None), prob.tspan, everystep,
-                                                     kw.get("save_start"), kw.get("save_end"))
 
     def run(u0, p, ntraj, flags=0):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),

@@ -66,6 +66,8 @@ def test_solve_keyword_contract(pkg):
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, callback=None)
     with pytest.raises(TypeError):
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), saveat=0.1)        # trajectories missing
+    with pytest.raises(TypeError):                                  # logging switches are accepted (and ignored) ...
+        P.solve(ep, P.Tsit5(), P.EnsembleB200(), saveat=0.1, verbose=False, progress=True)    # ... trajectories still missing
     with pytest.raises(NotImplementedError):                        # dense sol(t) objects are not on this path
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, dense=True)
     with pytest.raises(ValueError):                                 # solve.jl:277-280: fixed step needs dt (or tstops)
