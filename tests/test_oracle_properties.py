@@ -453,3 +453,74 @@ def test_fixed_step_mode():
     assert list(h["ts"]) == [0.0, 0.25, 0.5, 1.0]
     with pytest.raises(RuntimeError):
         oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, adaptive=False)
+
+
+# ---- exact time grids from the reference's own tstops / saveat tests ---------------------------
+def test_reference_tstops_known_answers():
+    """test/InterfaceI/ode_tstops_tests.jl:9-45,278-289 — the step grid is algorithm independent for fixed steps, so
+    the RK4/Euler expectations hold verbatim for Tsit5."""
+    s = linear_source()
+    u0 = np.array([[0.5]])
+
+    def ts(**kw):
+        return list(oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, save_everystep=True, **kw)["ts"])
+    # :12-13  sol = solve(prob, Tsit5(), dt = 1//2^6, tstops = [1/2]);  1//2 in sol.t
+    assert 0.5 in ts(dt=1 / 64, tstops=[0.5])
+    # :15-16  dt = 1//3, tstops = [1/2], adaptive = false  =>  sol.t == [0, 1/3, 1/2, 1/3 + 1/2, 1]
+    assert ts(dt=1 / 3, tstops=[0.5], adaptive=False) == [0, 1 / 3, 1 / 2, 1 / 3 + 1 / 2, 1]
+    # :30-31  no dt: the stops themselves are the steps
+    stops = [1 / 5, 1 / 4, 1 / 3, 1 / 2, 3 / 4]
+    assert ts(tstops=stops, adaptive=False) == [0] + stops + [1]
+    # :33-37  stops at both ends are dropped by initialize_tstops
+    assert ts(tstops=[0] + stops + [1], adaptive=False) == [0] + stops + [1]
+    # :39-40  tstops = 0:1//16:1
+    grid = [k / 16 for k in range(17)]
+    assert ts(tstops=grid, adaptive=False) == grid
+    # :42-43  tstops = range(0, stop = 1, length = 100)
+    rng = [float(x) for x in np.linspace(0.0, 1.0, 100)]
+    got = ts(tstops=rng, adaptive=False)
+    assert len(got) == 100 and got[0] == 0.0 and got[-1] == 1.0 and np.allclose(got, rng, rtol=0, atol=1e-15)
+    # :278-289  fixed dt = 0.1 on (0, 1): accumulated drift must not produce a spurious 12th step
+    got = ts(dt=0.1, adaptive=False)
+    assert len(got) == 11 and got[-1] == 1.0
+
+
+def test_reference_saveat_bookkeeping_known_answers():
+    # test/InterfaceI/ode_saveat_tests.jl:214-220: save_everystep = false keeps [t0, tf]; with maxiters = 3 the failed
+    # solve still has two entries (start + the point it reached)
+    s = ("void g(double* du, const double* u, const double* p, const double t) { du[0] = u[0]; }\n", "g")
+    u0 = np.array([[1.0]])
+    o = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0)
+    assert o["nsaved"][0] == 2 and o["retcode"][0] == 1
+    o = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, maxiters=3)
+    assert o["nsaved"][0] == 2 and o["retcode"][0] == 2 and o["t_final"][0] < 1.0
+
+
+def test_reference_saveat_defaults_known_answers(pkg):
+    """test/InterfaceI/ode_saveat_tests.jl:11-41 replayed through the host layer's keyword resolution
+    (ranges.saveat_grid + ranges.resolve_save_flags) and the oracle, with DP5 and dt = 1/4 as in the reference."""
+    s = linear_source()
+    u0 = np.array([[0.5]])
+    span = (0.0, 1.0)
+
+    def sol_t(saveat=None, tstops=None, save_everystep=None):
+        has = saveat is not None and not (hasattr(saveat, "__len__") and len(saveat) == 0)
+        every = (not has) if save_everystep is None else save_everystep
+        grid = pkg.ranges.saveat_grid(saveat, span)
+        ss, se = pkg.ranges.resolve_save_flags(saveat, span, every)
+        o = oracle.solve(oracle.ALG_DP5, s, u0, None, span, 1, 0, dt=0.25, saveat=grid or None, tstops=tstops,
+                         save_start=ss, save_end=se, save_everystep=every)
+        if every:
+            return list(o["ts"])
+        if not grid:                                    # no saveat: the final-only path reports [t0, t_end]
+            return ([0.0] if ss else []) + ([float(o["t_final"][0])] if se is None or se else [])
+        return list(o["ts"][:o["nsaved"][0]])
+    base = sol_t(save_everystep=False)
+    assert base == [0.0, 1.0]
+    assert sorted(set(base) ^ set(sol_t(saveat=[0.5], save_everystep=False))) == [0.0, 0.5, 1.0]      # :12-14
+    assert sorted(set(base) ^ set(sol_t(saveat=[0.0, 0.5, 1.0], save_everystep=False))) == [0.5]      # :16-21
+    assert sorted(set(base) ^ set(sol_t(saveat=0.5, save_everystep=False))) == [0.5]                  # :23-25
+    assert sol_t(saveat=[0.5], tstops=[0.5], save_everystep=False) == [0.5]                           # :27-32
+    assert sol_t(saveat=[0.0, 0.5, 1.0], tstops=[0.5]) == [0.0, 0.5, 1.0]                             # :34-36
+    # :38-41  saveat = 1/10, tstops = [1/2]  =>  sol3.t == collect(0.0:0.1:1.0) (exactly the range's values)
+    assert sol_t(saveat=0.1, tstops=[0.5]) == pkg.ranges.julia_range(0.0, 0.1, 1.0)
