@@ -524,3 +524,27 @@ def test_reference_saveat_defaults_known_answers(pkg):
     assert sol_t(saveat=[0.0, 0.5, 1.0], tstops=[0.5]) == [0.0, 0.5, 1.0]                             # :34-36
     # :38-41  saveat = 1/10, tstops = [1/2]  =>  sol3.t == collect(0.0:0.1:1.0) (exactly the range's values)
     assert sol_t(saveat=0.1, tstops=[0.5]) == pkg.ranges.julia_range(0.0, 0.1, 1.0)
+
+
+@pytest.mark.parametrize("alg", ["ros23", "rodas4", "rodas4p", "rodas5", "rodas5p", "rodas42", "rodas4p2"])
+def test_reference_possibly_singular_problem_succeeds(alg):
+    # test/Regression_I/ode_adaptive_tests.jl:93-110: a problem whose W matrix is nearly singular must still end
+    # with ReturnCode.Success for Rosenbrock23, Rodas4, Rodas4P, Rodas5, Rodas5P (Float32 literals promoted to Float64
+    # exactly as in the reference; the Jacobian is analytic here, ForwardDiff there)
+    a = {"ros23": oracle.ALG_ROSENBROCK23, "rodas4": oracle.ALG_RODAS4, "rodas4p": oracle.ALG_RODAS4P,
+         "rodas5": oracle.ALG_RODAS5, "rodas5p": oracle.ALG_RODAS5P, "rodas42": oracle.ALG_RODAS42,
+         "rodas4p2": oracle.ALG_RODAS4P2}[alg]
+    rhs = ("static double rr(double x1, double x2) { return x1 * ((double)-2.1474936f * (x2 + x1)); }\n"
+           "void ps_rhs(double* du, const double* u, const double* p, const double t) {\n"
+           "  du[0] = -rr(u[0], u[1]); du[1] = rr(u[0], u[1]);\n}\n", "ps_rhs")
+    jac = ("void ps_jac(double* J, const double* u, const double* p, const double t) {\n"
+           "  const double c = (double)-2.1474936f;\n"
+           "  double d1 = c * (u[1] + u[0]) + u[0] * c, d2 = u[0] * c;\n"
+           "  J[0] = -d1; J[1] = d1; J[2] = -d2; J[3] = d2;\n}\n", "ps_jac")
+    tg = ("void ps_tgrad(double* dT, const double* u, const double* p, const double t) { dT[0] = 0.0; dT[1] = 0.0; }\n",
+          "ps_tgrad")
+    t0, tf = float(np.float32(1.6078221)), 2.0
+    u0 = np.array([[float(np.float32(2.1349438e6)), float(np.float32(-2.1349438e6))]])
+    for linsolve in (0, 1):       # StaticWOperator inverse (SVector form) and LU (Vector form, what the test uses)
+        o = oracle.solve(a, rhs, u0, None, (t0, tf), 2, 0, jac=jac, tgrad=tg, linsolve=linsolve)
+        assert o["retcode"][0] == 1, (alg, linsolve, o["retcode"], o["naccept"], o["nreject"])
