@@ -548,3 +548,42 @@ def test_reference_possibly_singular_problem_succeeds(alg):
     for linsolve in (0, 1):       # StaticWOperator inverse (SVector form) and LU (Vector form, what the test uses)
         o = oracle.solve(a, rhs, u0, None, (t0, tf), 2, 0, jac=jac, tgrad=tg, linsolve=linsolve)
         assert o["retcode"][0] == 1, (alg, linsolve, o["retcode"], o["naccept"], o["nreject"])
+
+
+def test_reference_save_start_save_end_behavior(pkg):
+    """test/InterfaceI/ode_saveat_tests.jl:240-269 ("Proper save_start and save_end behavior"), Tsit5 on
+    du = -cos(u) u, u0 = 10, tspan (0, 0.4), replayed through the host layer's keyword resolution."""
+    s = ("#include <math.h>\nvoid f2(double* du, const double* u, const double* p, const double t) { du[0] = -cos(u[0]) * u[0]; }\n",
+         "f2")
+    u0 = np.array([[10.0]])
+    span = (0.0, 0.4)
+    rng = pkg.ranges.julia_range(0.0, 0.1, 0.4)
+
+    def sol_t(saveat=None, save_start=None, save_end=None):
+        has = saveat is not None
+        every = not has
+        grid = pkg.ranges.saveat_grid(saveat, span)
+        ss, se = pkg.ranges.resolve_save_flags(saveat, span, every, save_start, save_end)
+        o = oracle.solve(oracle.ALG_TSIT5, s, u0, None, span, 1, 0, saveat=grid or None, save_start=ss, save_end=se,
+                         save_everystep=every)
+        return list(o["ts"]) if every else list(o["ts"][:o["nsaved"][0]])
+    assert sol_t(saveat=rng) == rng          # == [0.0; 0.1; 0.2; 0.3; 0.4] up to the range's own rounding of 0.3
+    assert sol_t(saveat=rng, save_start=True, save_end=True) == rng
+    assert sol_t(saveat=rng, save_start=False, save_end=False) == rng[1:-1]
+    ts = sol_t()
+    assert 0.0 in ts and 0.4 in ts
+    ts = sol_t(save_start=True, save_end=True)
+    assert 0.0 in ts and 0.4 in ts
+    ts = sol_t(save_start=False, save_end=False)
+    assert 0.0 not in ts and 0.4 not in ts and len(ts) > 0
+    assert sol_t(saveat=[0.2]) == [0.2]
+    assert sol_t(saveat=[0.2], save_start=True, save_end=True) == [0.0, 0.2, 0.4]
+    assert sol_t(saveat=[0.2], save_start=False, save_end=False) == [0.2]
+
+
+def test_reference_initdt_tiny_timespan_succeeds():
+    # test/InterfaceI/ode_initdt_tests.jl:68-70: "dtmin is set based on timespan" — u' = 1e20 sin(1e20 t) on (0, 1e-19)
+    s = ("#include <math.h>\nvoid g(double* du, const double* u, const double* p, const double t) { du[0] = 1.0e20 * sin(1.0e20 * t); }\n",
+         "g")
+    o = oracle.solve(oracle.ALG_TSIT5, s, np.array([[0.1]]), None, (0.0, 1.0e-19), 1, 0)
+    assert o["retcode"][0] == 1 and o["t_final"][0] == 1.0e-19
