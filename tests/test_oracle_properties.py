@@ -567,7 +567,8 @@ def test_reference_save_start_save_end_behavior(pkg):
         o = oracle.solve(oracle.ALG_TSIT5, s, u0, None, span, 1, 0, saveat=grid or None, save_start=ss, save_end=se,
                          save_everystep=every)
         return list(o["ts"]) if every else list(o["ts"][:o["nsaved"][0]])
-    assert sol_t(saveat=rng) == rng          # == [0.0; 0.1; 0.2; 0.3; 0.4] up to the range's own rounding of 0.3
+    assert rng == [0.0, 0.1, 0.2, 0.3, 0.4]      # Julia's TwicePrecision range hits 0.3 exactly
+    assert sol_t(saveat=rng) == [0.0, 0.1, 0.2, 0.3, 0.4]
     assert sol_t(saveat=rng, save_start=True, save_end=True) == rng
     assert sol_t(saveat=rng, save_start=False, save_end=False) == rng[1:-1]
     ts = sol_t()
