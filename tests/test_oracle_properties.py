@@ -588,3 +588,61 @@ def test_reference_initdt_tiny_timespan_succeeds():
          "g")
     o = oracle.solve(oracle.ALG_TSIT5, s, np.array([[0.1]]), None, (0.0, 1.0e-19), 1, 0)
     assert o["retcode"][0] == 1 and o["t_final"][0] == 1.0e-19
+
+
+@pytest.mark.parametrize("name,S", [("Vern6", 9), ("Vern7Gen", 10), ("Vern8", 13), ("Vern9", 16)])
+def test_generated_verner_code_satisfies_tableau_identities(name, S):
+    """Independent of how scripts/gen_verner.py assembled them: the emitted stage lines must satisfy the identities
+    every Runge-Kutta pair with a continuous extension has — row sums equal the abscissae (main and lazy stages),
+    Σ b = 1, Σ b̃ = 0, and the interpolant at Θ = 1 reproduces the solution weights (b_j(1) = b_j, 0 for lazy stages)."""
+    import re
+    text = open(os.path.join(HERE, "..", "oracle", "oracle_verner_gen.inc")).read()
+    m = re.search(r"template <typename R> struct %s \{(.*?)\n\};" % name, text, re.S)
+    body = m.group(1)
+    consts = {k: float(v) for k, v in re.findall(r"const R (\w+) = \(R\)([-+0-9.eE]+);", body)}
+
+    def chain_terms(expr):
+        return [(consts[a], int(k)) for a, k in re.findall(r"\b([a-z]+\d+)\b[ ,*]+k\[(\d+)\]\[i\]", expr)]
+    stages = re.findall(r"tmp\[i\] = jl_fma\(dt, (.*?), uprev\[i\]\);\s*P->f\(k\[(\d+)\], tmp, p, (.*?)\);", body)
+    assert len(stages) >= S - 3
+    seen = set()
+    for chain, kidx, tm in stages:
+        cm = re.fullmatch(r"jl_fma\((\w+), dt, t\)", tm)
+        c = consts[cm.group(1)] if cm else 1.0
+        terms = chain_terms(chain)
+        assert terms and all(k < int(kidx) for _, k in terms)          # explicit method: only earlier stages
+        scale = sum(abs(a) for a, _ in terms)
+        assert abs(math.fsum(a for a, _ in terms) - c) < 4e-15 * max(scale, 1.0), (name, kidx, scale, c)
+        seen.add(int(kidx))
+    assert max(seen) + 1 > S                                           # the lazy stages were checked as well
+    u_chain = re.search(r"u\[i\] = jl_fma\(dt, (.*?), uprev\[i\]\);", body).group(1)
+    b = {k: a for a, k in chain_terms(u_chain)}
+    assert abs(math.fsum(b.values()) - 1.0) < 4e-15 * sum(abs(v) for v in b.values())
+    e_chain = re.search(r"R utilde = dt \* \((.*?)\);", body).group(1)
+    et = [a for a, _ in chain_terms(e_chain)]
+    assert abs(math.fsum(et)) < 4e-15 * max(sum(abs(a) for a in et), 1.0)
+    # interpolant polynomials: const R bJ = th|th2 * Horner(...)
+    for j, poly in re.findall(r"const R b(\d+) = th2? \* (.*?);", body):
+        rs = [consts[r] for r in re.findall(r"\b(r\d+)\b", poly)]
+        want = b.get(int(j) - 1, 0.0)
+        assert abs(math.fsum(rs) - want) < 1e-14 * max(sum(abs(r) for r in rs), 1.0), (name, j, math.fsum(rs), want)
+
+
+def test_low_order_rk_tableau_identities():
+    """DP5 and BS3 as transcribed into oracle_lowrk.inc: row sums equal the abscissae, the embedded error weights sum
+    to zero, the solution weights to one (low_order_rk_tableaus.jl:1096-1151, 27-44)."""
+    import re
+    text = open(os.path.join(HERE, "..", "oracle", "oracle_lowrk.inc")).read()
+    dp = re.search(r"template <typename R> struct DP5 \{(.*?)\n\};", text, re.S).group(1)
+    v = {k: float(x) for k, x in re.findall(r"\b(\w+) = \(R\)([-+0-9.eE]+)", dp)}
+    rows = {"c1": ["a21"], "c2": ["a31", "a32"], "c3": ["a41", "a42", "a43"], "c4": ["a51", "a52", "a53", "a54"]}
+    for c, names in rows.items():
+        assert abs(math.fsum(v[n] for n in names) - v[c]) < 1e-14, c
+    assert abs(math.fsum(v[n] for n in ["a61", "a62", "a63", "a64", "a65"]) - 1.0) < 1e-14
+    assert abs(math.fsum(v[n] for n in ["a71", "a73", "a74", "a75", "a76"]) - 1.0) < 1e-15
+    assert abs(math.fsum(v["btilde%d" % i] for i in (1, 3, 4, 5, 6, 7))) < 1e-16
+    bs = re.search(r"template <typename R> struct BS3 \{(.*?)\n\};", text, re.S).group(1)
+    w = {k: float(x) for k, x in re.findall(r"\b(\w+) = \(R\)([-+0-9.eE]+)", bs)}
+    assert w["a21"] == w["c1"] and w["a32"] == w["c2"]
+    assert abs(w["a41"] + w["a42"] + w["a43"] - 1.0) < 1e-15
+    assert abs(math.fsum(w["btilde%d" % i] for i in (1, 2, 3, 4))) < 1e-16
