@@ -21,7 +21,7 @@
 //   B200_N, B200_NP      state / parameter dimension
 //   B200_F32             0: double, 1: float
 //   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3,
-//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9
+//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9, 15 Rosenbrock32
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -42,8 +42,9 @@
 #define B200_ALG_VERN6 12
 #define B200_ALG_VERN8 13
 #define B200_ALG_VERN9 14
+#define B200_ALG_ROS32 15
 #define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
-#define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_IS_RODAS)
+#define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32 || B200_IS_RODAS)
 
 #ifndef B200_SLICED
 #define B200_SLICED 0
@@ -62,7 +63,7 @@ typedef B200Vern7 B200Stepper;
 #elif B200_IS_ROSENBROCK
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_rosenbrock.cuh"
-#if B200_ALG == B200_ALG_ROS23
+#if B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32
 typedef B200Ros23 B200Stepper;
 #else
 typedef B200Rodas5P B200Stepper;
@@ -703,7 +704,9 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
         }
     }
 }
-#if B200_EVERYSTEP && !defined(B200_SAVE_IDXS)      // (rows restricted by save_idxs cannot restart a step)
+// (rows restricted by save_idxs cannot restart a step; Rosenbrock32's fsalfirst is f(uprev + dt k2) of the previous
+// step, not f of the saved row, so its stages are not recomputable from (row, dt) either)
+#if B200_EVERYSTEP && !defined(B200_SAVE_IDXS) && B200_ALG != B200_ALG_ROS32
 // ---------------------------------------------------------------------------
 // sol(tq) for every trajectory, post hoc, from the ragged per-step rows — ode_interpolation
 // (dense/generic_dense.jl:833-867: interval search :845-849, dt = ts[i+] - ts[i-], Θ :858-859,

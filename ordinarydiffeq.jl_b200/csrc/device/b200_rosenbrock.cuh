@@ -162,11 +162,15 @@ B200_D real b200_err_norm(const real* ut, const real* uprev, const real* u, real
 }
 
 // ---------------------------------------------------------------------------
+// Rosenbrock23 and Rosenbrock32 share the three stages (rosenbrock_perform_step.jl:249-332 / :333-417).
+// Rosenbrock32 (B200_ROS_THIRD) advances with the third-order combination u = uprev + dt/6 (k1 + 4 k2 + k3), keeps
+// f(uprev + dt k2) as fsallast, and forms k1 as (W \ -(fsalfirst + dtγ dT)) / dtγ.
+#define B200_ROS_THIRD (B200_ALG == B200_ALG_ROS32)
 struct B200Ros23 {
     real k1[B200_N], k2[B200_N];       // dense output rows (integrator.k[1], k[2])
     real f0[B200_N], f2[B200_N];       // fsalfirst, fsallast
 
-    static B200_D int order() { return 2; }
+    static B200_D int order() { return B200_ROS_THIRD ? 3 : 2; }
     static B200_D real qsteady_min() { return (real)1; }
     static B200_D real qsteady_max() { return (real)1.2; }     // 6//5 for implicit methods (alg_utils.jl:857)
 
@@ -187,11 +191,19 @@ struct B200Ros23 {
         B200WFact F;
         b200_build_W(uprev, p, t, dtg, dT, F, njacs, nw);
         if (!F.ok) return (real)2;
+#if B200_ROS_THIRD
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) rhs[i] = -b200_fma(dtg, dT[i], f0[i]);
+        F.solve(rhs, k1);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) k1[i] = k1[i] / dtg;
+#else
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) rhs[i] = b200_fma(dtg, dT[i], f0[i]);
         F.solve(rhs, k1);
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) k1[i] = k1[i] * ninv;
+#endif
         nsolve += 1;
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) tmp[i] = b200_fma(dto2, k1[i], uprev[i]);
@@ -215,6 +227,11 @@ struct B200Ros23 {
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) k3[i] = k3[i] * ninv;
         nsolve += 1;
+#if B200_ROS_THIRD
+        // (u held uprev + dt k2 for fsallast) u = uprev + dto6*(k1 + 4k2 + k3) = muladd(dto6, muladd(4, k2, k1 + k3), uprev)
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) u[i] = b200_fma(dto6, b200_fma((real)4, k2[i], k1[i] + k3[i]), uprev[i]);
+#endif
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) tmp[i] = dto6 * (b200_fma((real)-2, k2[i], k1[i]) + k3[i]);
         return b200_err_norm(tmp, uprev, u, reltol, abstol);

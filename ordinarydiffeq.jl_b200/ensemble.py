@@ -43,6 +43,10 @@ class Rosenbrock23(_Alg):   # lib/OrdinaryDiffEqRosenbrock
     alg_id, order, stiff = _lib.ALG_ROSENBROCK23, 2, True
 
 
+class Rosenbrock32(_Alg):
+    alg_id, order, stiff = _lib.ALG_ROSENBROCK32, 3, True
+
+
 class Rodas5P(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS5P, 5, True
 
@@ -423,7 +427,8 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
         return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
 
-    dense_ok = everystep and not grid and save_start and save_idxs is None and tstops is None      # dense = save_everystep && isempty(saveat) (solve.jl:144)
+    dense_ok = (everystep and not grid and save_start and save_idxs is None and tstops is None
+                and alg.alg_id != _lib.ALG_ROSENBROCK32)      # dense = save_everystep && isempty(saveat) (solve.jl:144)
     tol_kw = dict(reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
                   dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"))
 

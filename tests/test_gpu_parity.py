@@ -783,3 +783,40 @@ def test_fixed_step_parity(pkg, handle, oracle, f32):
         g = pkg.lowlevel.solve_host(pr, U0, k, (0.0, 1.0), dt=0.01)
         o = oracle.solve(oracle.ALG_RODAS5P, r, U0, k, (0.0, 1.0), 3, 3, jac=j, tgrad=tg, adaptive=False, dt=0.01)
         assert_same_result(g, o)
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_rosenbrock32_parity(pkg, handle, oracle, f32):
+    """Rosenbrock32 is only A-stable and re-uses f(uprev + dt k2) as the next fsalfirst (both as in the reference), so on
+    Robertson it needs ~3000 steps to t = 10 and runs into maxiters long before 1e4; FP32 trajectories partly end
+    Unstable.  Parity covers all of that: same counters, same retcodes, same states."""
+    pl = pkg.problems_library
+    r, j, tg = pl.robertson_sources(f32)
+    p = pl.robertson_params(1024, f32=f32)
+    dt = pkg.F32 if f32 else pkg.F64
+    tf = 10.0
+    tol = dict(reltol=1e-6, abstol=1e-8) if not f32 else dict(reltol=1e-3, abstol=1e-5)
+    prog = handle.compile(pkg.ALG_ROSENBROCK32, dt, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1])
+    for extra in ({}, {"saveat": [0.01, 0.1, 5.0]}, {"maxiters": 500}):
+        kw = dict(tol, **extra)
+        g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, tf), **kw)
+        o = oracle.solve(oracle.ALG_ROSENBROCK32, r, U0, p, (0.0, tf), 3, 3, f32=f32, jac=j, tgrad=tg, **kw)
+        ok = o["retcode"] == 1
+        assert_same_result(g, o, keys=("naccept", "nreject", "nf", "retcode", "nsaved", "njacs", "nw", "nsolve")) if ok.all() \
+            else None
+        for k in ("naccept", "nreject", "nf", "retcode", "nsaved", "njacs", "nw", "nsolve"):
+            assert np.array_equal(g[k], o[k]), k
+        assert np.array_equal(bits(g["u_final"][ok]), bits(o["u_final"][ok]))       # failed ones may hold NaNs
+        if "saveat" in extra:
+            assert np.array_equal(bits(g["us"][ok]), bits(o["us"][ok]))
+    if not f32:
+        assert ok.sum() == 0                    # maxiters = 500 stops every trajectory
+        prog_e = handle.compile(pkg.ALG_ROSENBROCK32, dt, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1],
+                                extra_options=pkg._lib.OPT_EVERYSTEP)
+        ge = pkg.lowlevel.solve_host_everystep(prog_e, U0, p, (0.0, 1.0), **tol)
+        oe = oracle.solve(oracle.ALG_ROSENBROCK32, r, U0, p, (0.0, 1.0), 3, 3, jac=j, tgrad=tg, save_everystep=True, **tol)
+        _assert_same_ragged(ge, oe)
+        # post-hoc dense output recomputes a step's stages from its saved start row; Rosenbrock32's fsalfirst is
+        # f(uprev + dt k2) of the previous step, which no saved row holds, so the path declines instead of guessing
+        with pytest.raises(pkg.B200Error):
+            pkg.lowlevel.solve_host_dense(prog_e, U0, p, (0.0, 1.0), np.array([0.0, 0.3]), **tol)

@@ -123,6 +123,7 @@ def _fixed_step_l2_error(alg, h, stiff=False):
     (oracle.ALG_TSIT5, 5, (7, 6, 5, 4, 3), 0.4, False),    # test/Regression_II/ode_unrolled_comparison_tests.jl:70-77
     (oracle.ALG_VERN7, 7, (3, 2, 1), 0.4, False),          # lib/OrdinaryDiffEqVerner/test/ode_verner_tests.jl:61-65 (BigFloat there; larger dts in binary64)
     (oracle.ALG_ROSENBROCK23, 2, (6, 5, 4, 3), 0.2, True),  # lib/OrdinaryDiffEqRosenbrock/test/ode_rosenbrock_tests.jl:15-23
+    (oracle.ALG_ROSENBROCK32, 3, (6, 5, 4, 3), 0.2, True),  # same file, Rosenbrock32 block (𝒪est[:final] ≈ 3)
     (oracle.ALG_BS3, 3, (8, 7, 6, 5, 4), 0.2, False),      # lib/OrdinaryDiffEqLowOrderRK/test/low_order_erk_convergence_tests.jl:32,74-75
     (oracle.ALG_DP5, 5, (7, 6, 5, 4, 3), 0.4, False),      # DP5 shares Tsit5's dts in test/Regression_II/ode_unrolled_comparison_tests.jl
 ])
@@ -214,13 +215,15 @@ def test_tableau_consistency():
     (oracle.ALG_DP5, 5e-6), (oracle.ALG_BS3, 5e-4),            # ode_dense_tests.jl:355,358
     (oracle.ALG_RODAS4, 8.5e-6), (oracle.ALG_RODAS42, 3e-5), (oracle.ALG_RODAS4P, 4e-5), (oracle.ALG_RODAS4P2, 2e-5),
     (oracle.ALG_RODAS5, 2e-6),                                 # ode_dense_tests.jl:465-477
+    (oracle.ALG_ROSENBROCK32, 6e-4),                           # ode_dense_tests.jl:456
     (oracle.ALG_VERN6, 7e-8), (oracle.ALG_VERN8, 3e-8), (oracle.ALG_VERN9, 1e-9)])   # ode_dense_tests.jl:406,437,444
 def test_dense_output_regression_bounds(alg, bound):
     # test/Regression_I/ode_dense_tests.jl:56-75 with the per-algorithm tolerances at
     # :369-370 (Tsit5), :429-433 (Vern7), :452-453 (Rosenbrock23), :479-480 (Rodas5P):
     # interpolant of the adaptive dt0 = 1/4 solve vs the fixed dt = 1/16 solve, at k/16.
     jac, tg = linear_jac_sources()
-    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_RODAS5P) or oracle.ALG_RODAS5 <= alg <= oracle.ALG_RODAS4P2
+    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK32, oracle.ALG_RODAS5P) or \
+        oracle.ALG_RODAS5 <= alg <= oracle.ALG_RODAS4P2
     kw = dict(jac=jac, tgrad=tg) if stiff else {}
     pts = [k / 16 for k in range(1, 17)]
     a = oracle.solve(alg, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, dt=0.25,
@@ -526,12 +529,13 @@ def test_reference_saveat_defaults_known_answers(pkg):
     assert sol_t(saveat=0.1, tstops=[0.5]) == pkg.ranges.julia_range(0.0, 0.1, 1.0)
 
 
-@pytest.mark.parametrize("alg", ["ros23", "rodas4", "rodas4p", "rodas5", "rodas5p", "rodas42", "rodas4p2"])
+@pytest.mark.parametrize("alg", ["ros23", "ros32", "rodas4", "rodas4p", "rodas5", "rodas5p", "rodas42", "rodas4p2"])
 def test_reference_possibly_singular_problem_succeeds(alg):
     # test/Regression_I/ode_adaptive_tests.jl:93-110: a problem whose W matrix is nearly singular must still end
     # with ReturnCode.Success for Rosenbrock23, Rodas4, Rodas4P, Rodas5, Rodas5P (Float32 literals promoted to Float64
     # exactly as in the reference; the Jacobian is analytic here, ForwardDiff there)
-    a = {"ros23": oracle.ALG_ROSENBROCK23, "rodas4": oracle.ALG_RODAS4, "rodas4p": oracle.ALG_RODAS4P,
+    a = {"ros23": oracle.ALG_ROSENBROCK23, "ros32": oracle.ALG_ROSENBROCK32, "rodas4": oracle.ALG_RODAS4,
+         "rodas4p": oracle.ALG_RODAS4P,
          "rodas5": oracle.ALG_RODAS5, "rodas5p": oracle.ALG_RODAS5P, "rodas42": oracle.ALG_RODAS42,
          "rodas4p2": oracle.ALG_RODAS4P2}[alg]
     rhs = ("static double rr(double x1, double x2) { return x1 * ((double)-2.1474936f * (x2 + x1)); }\n"
