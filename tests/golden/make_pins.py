@@ -28,6 +28,8 @@ cases = [
 for a in ("dp5", "bs3", "vern6", "vern8", "vern9"):
     cases.append(dict(name="lorenz %s" % a, problem="lorenz", alg=a, f32=False, N=8, kw=dict()))
 cases.append(dict(name="lorenz dp5 f32", problem="lorenz", alg="dp5", f32=True, N=8, kw=dict()))
+cases.append(dict(name="robertson ros32 (mildly stiff span)", problem="robertson", alg="ros32", f32=False, N=4, tf=10.0,
+                  kw=dict(reltol=1e-6, abstol=1e-8)))
 for a in ("rodas5", "rodas4", "rodas42", "rodas4p", "rodas4p2"):
     cases.append(dict(name="robertson %s" % a, problem="robertson", alg=a, f32=False, N=4, tf=1e4,
                       kw=dict(reltol=1e-6, abstol=1e-8)))

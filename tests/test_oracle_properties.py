@@ -306,7 +306,8 @@ def test_golden_regression_pins(pkg):
 
 def _run_pin_case(pl, case):
     alg = {"tsit5": oracle.ALG_TSIT5, "vern7": oracle.ALG_VERN7, "ros23": oracle.ALG_ROSENBROCK23,
-           "rodas5p": oracle.ALG_RODAS5P, "dp5": oracle.ALG_DP5, "bs3": oracle.ALG_BS3, "vern6": oracle.ALG_VERN6,
+           "rodas5p": oracle.ALG_RODAS5P, "ros32": oracle.ALG_ROSENBROCK32, "dp5": oracle.ALG_DP5, "bs3": oracle.ALG_BS3,
+           "vern6": oracle.ALG_VERN6,
            "vern8": oracle.ALG_VERN8, "vern9": oracle.ALG_VERN9, "rodas5": oracle.ALG_RODAS5, "rodas4": oracle.ALG_RODAS4,
            "rodas42": oracle.ALG_RODAS42, "rodas4p": oracle.ALG_RODAS4P, "rodas4p2": oracle.ALG_RODAS4P2}[case["alg"]]
     f32 = case["f32"]
