@@ -133,7 +133,7 @@ template <typename R> struct Fn {
 
 enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4, ALG_DP5 = 5, ALG_BS3 = 6,
        ALG_RODAS5 = 7, ALG_RODAS4 = 8, ALG_RODAS42 = 9, ALG_RODAS4P = 10, ALG_RODAS4P2 = 11,
-       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_VERN7_GENERATED = 102 };
+       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_RODAS5PE = 16, ALG_VERN7_GENERATED = 102 };
 enum { RC_DEFAULT = 0, RC_SUCCESS = 1, RC_MAXITERS = 2, RC_DTLESSTHANMIN = 3, RC_UNSTABLE = 4, RC_DTNAN = 5 };
 
 template <typename R> struct Opts {
@@ -676,6 +676,7 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         case ALG_ROS23: solve_batch<R, Rosenbrock23<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_ROS32: solve_batch<R, Rosenbrock32<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS5P: solve_batch<R, Rodas5P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_RODAS5PE: solve_batch<R, Rodas5Pe<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS5: solve_batch<R, Rodas5<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4: solve_batch<R, Rodas4<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS42: solve_batch<R, Rodas42<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;

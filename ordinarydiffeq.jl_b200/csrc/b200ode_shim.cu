@@ -155,6 +155,7 @@ bool is_identifier(const char* s) {
 
 bool is_stiff_alg(int alg) {      // Rosenbrock-type: need jac + tgrad, report njacs/nw/nsolve
     return alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_ROSENBROCK32 || alg == B200ODE_ALG_RODAS5P ||
+           alg == B200ODE_ALG_RODAS5PE ||
            (alg >= B200ODE_ALG_RODAS5 && alg <= B200ODE_ALG_RODAS4P2);
 }
 
@@ -180,7 +181,7 @@ int parse_save_idxs(const char* extra_options, int n) {
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                           const char* jac_src, const char* jac_name, const char* tgrad_src,
                           const char* tgrad_name) {
-    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_ROSENBROCK32)
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS5PE)
         return fail(B200ODE_EINVAL, "alg must be one of the B200ODE_ALG_* constants");
     if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
     if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");
@@ -227,7 +228,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         case B200ODE_ALG_VERN8: call_sites += 21; break;
         case B200ODE_ALG_VERN9: call_sites += 26; break;
         case B200ODE_ALG_ROSENBROCK23: case B200ODE_ALG_ROSENBROCK32: call_sites += 3; break;
-        case B200ODE_ALG_RODAS5P: case B200ODE_ALG_RODAS5: call_sites += 8; break;
+        case B200ODE_ALG_RODAS5P: case B200ODE_ALG_RODAS5PE: case B200ODE_ALG_RODAS5: call_sites += 8; break;
         default: call_sites += 6; break;
     }
     bool rhs_inline = strlen(rhs_src) * (size_t)call_sites <= 120000;

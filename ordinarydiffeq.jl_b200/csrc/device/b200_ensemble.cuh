@@ -21,7 +21,7 @@
 //   B200_N, B200_NP      state / parameter dimension
 //   B200_F32             0: double, 1: float
 //   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3,
-//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9, 15 Rosenbrock32
+//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9, 15 Rosenbrock32, 16 Rodas5Pe
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -43,7 +43,8 @@
 #define B200_ALG_VERN8 13
 #define B200_ALG_VERN9 14
 #define B200_ALG_ROS32 15
-#define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
+#define B200_ALG_RODAS5PE 16
+#define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || B200_ALG == B200_ALG_RODAS5PE || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
 #define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32 || B200_IS_RODAS)
 
 #ifndef B200_SLICED

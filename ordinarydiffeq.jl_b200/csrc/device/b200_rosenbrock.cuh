@@ -271,7 +271,7 @@ struct B200Ros23 {
 #elif B200_ALG == B200_ALG_RODAS4P2
 #define B200_RODAS_NAME(x) B200_RODAS4P2_##x
 #define B200_RODAS_ORDER 4
-#else
+#else      // Rodas5P and Rodas5Pe (same tableau; Rodas5Pe brings a full vector of embedded error weights)
 #define B200_RODAS_NAME(x) B200_RODAS5P_##x
 #define B200_RODAS_ORDER 5
 #endif
@@ -285,9 +285,16 @@ struct B200Rodas5PCoeffs {
     real d[B200_RODAS_S];
     real H[B200_RODAS_HR][B200_RODAS_S];
     real gamma;
+#if B200_ALG == B200_ALG_RODAS5PE
+    real btilde[B200_RODAS_S];
+#endif
 };
 __constant__ B200Rodas5PCoeffs B200_RODAS5P_TAB = {B200_RODAS_NAME(A), B200_RODAS_NAME(C), B200_RODAS_NAME(c), B200_RODAS_NAME(d),
-                                                 B200_RODAS_NAME(H), B200_RODAS_NAME(GAMMA)};
+                                                 B200_RODAS_NAME(H), B200_RODAS_NAME(GAMMA)
+#if B200_ALG == B200_ALG_RODAS5PE
+                                                 , B200_RODAS5PE_BTILDE
+#endif
+};
 
 struct B200Rodas5P {
     real dense[B200_RODAS_HR][B200_N];   // integrator.k[1..size(H,1)] (only filled when rows are interpolated)
@@ -355,9 +362,19 @@ struct B200Rodas5P {
 #pragma unroll
             for (int i = 0; i < B200_N; ++i) u[i] = b200_fma(b, ks[j][i], u[i]);
         }
+#if B200_ALG == B200_ALG_RODAS5PE
+        // du = zero(uprev); for i: du = du + btilde[i]*ks[i] (no entry of Rodas5Pe's btilde is zero)
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) du[i] = (real)0;
+#pragma unroll
+        for (int j = 0; j < B200_RODAS_S; ++j)
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) du[i] = b200_fma(T.btilde[j], ks[j][i], du[i]);
+#else
         // btilde = e_S: du = 0 + 1*ks[S]
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) du[i] = b200_fma((real)1, ks[B200_RODAS_S - 1][i], (real)0);
+#endif
         const real EEst = b200_err_norm(du, uprev, u, reltol, abstol);
         if (calck) {
 #pragma unroll

@@ -43,6 +43,10 @@ class Rosenbrock23(_Alg):   # lib/OrdinaryDiffEqRosenbrock
     alg_id, order, stiff = _lib.ALG_ROSENBROCK23, 2, True
 
 
+class Rodas5Pe(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS5PE, 5, True
+
+
 class Rosenbrock32(_Alg):
     alg_id, order, stiff = _lib.ALG_ROSENBROCK32, 3, True
 

@@ -57,8 +57,8 @@ end
 alg_id(::Tsit5) = 1; alg_id(::Vern7) = 2; alg_id(::Rosenbrock23) = 3; alg_id(::Rodas5P) = 4
 alg_id(::DP5) = 5; alg_id(::BS3) = 6
 alg_id(::Rodas5) = 7; alg_id(::Rodas4) = 8; alg_id(::Rodas42) = 9; alg_id(::Rodas4P) = 10; alg_id(::Rodas4P2) = 11
-alg_id(::Vern6) = 12; alg_id(::Vern8) = 13; alg_id(::Vern9) = 14; alg_id(::Rosenbrock32) = 15
-const StiffAlgs = Union{Rosenbrock23, Rosenbrock32, Rodas5P, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2}
+alg_id(::Vern6) = 12; alg_id(::Vern8) = 13; alg_id(::Vern9) = 14; alg_id(::Rosenbrock32) = 15; alg_id(::Rodas5Pe) = 16
+const StiffAlgs = Union{Rosenbrock23, Rosenbrock32, Rodas5P, Rodas5Pe, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2}
 const B200Algs = Union{Tsit5, Vern6, Vern7, Vern8, Vern9, DP5, BS3, StiffAlgs}
 isstiff(alg) = alg isa StiffAlgs
 const RETCODES = (ReturnCode.Default, ReturnCode.Success, ReturnCode.MaxIters, ReturnCode.DtLessThanMin,

@@ -626,7 +626,7 @@ def test_low_order_rk_high_level(pkg, oracle):
             assert s[i].stats.naccept == o["naccept"][i]
 
 
-@pytest.mark.parametrize("name", ["Rodas5", "Rodas4", "Rodas42", "Rodas4P", "Rodas4P2"])
+@pytest.mark.parametrize("name", ["Rodas5", "Rodas4", "Rodas42", "Rodas4P", "Rodas4P2", "Rodas5Pe"])
 def test_rodas_family_parity(pkg, handle, oracle, name):
     """The generic RodasTableau stepper over the other members of the family, Robertson FP64 (+ FP32 for two)."""
     pl = pkg.problems_library

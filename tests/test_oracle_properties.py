@@ -216,13 +216,14 @@ def test_tableau_consistency():
     (oracle.ALG_RODAS4, 8.5e-6), (oracle.ALG_RODAS42, 3e-5), (oracle.ALG_RODAS4P, 4e-5), (oracle.ALG_RODAS4P2, 2e-5),
     (oracle.ALG_RODAS5, 2e-6),                                 # ode_dense_tests.jl:465-477
     (oracle.ALG_ROSENBROCK32, 6e-4),                           # ode_dense_tests.jl:456
+    (oracle.ALG_RODAS5PE, 2e-5),                               # ode_dense_tests.jl:483
     (oracle.ALG_VERN6, 7e-8), (oracle.ALG_VERN8, 3e-8), (oracle.ALG_VERN9, 1e-9)])   # ode_dense_tests.jl:406,437,444
 def test_dense_output_regression_bounds(alg, bound):
     # test/Regression_I/ode_dense_tests.jl:56-75 with the per-algorithm tolerances at
     # :369-370 (Tsit5), :429-433 (Vern7), :452-453 (Rosenbrock23), :479-480 (Rodas5P):
     # interpolant of the adaptive dt0 = 1/4 solve vs the fixed dt = 1/16 solve, at k/16.
     jac, tg = linear_jac_sources()
-    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK32, oracle.ALG_RODAS5P) or \
+    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK32, oracle.ALG_RODAS5P, oracle.ALG_RODAS5PE) or \
         oracle.ALG_RODAS5 <= alg <= oracle.ALG_RODAS4P2
     kw = dict(jac=jac, tgrad=tg) if stiff else {}
     pts = [k / 16 for k in range(1, 17)]
@@ -530,13 +531,13 @@ def test_reference_saveat_defaults_known_answers(pkg):
     assert sol_t(saveat=0.1, tstops=[0.5]) == pkg.ranges.julia_range(0.0, 0.1, 1.0)
 
 
-@pytest.mark.parametrize("alg", ["ros23", "ros32", "rodas4", "rodas4p", "rodas5", "rodas5p", "rodas42", "rodas4p2"])
+@pytest.mark.parametrize("alg", ["ros23", "ros32", "rodas4", "rodas4p", "rodas5", "rodas5p", "rodas5pe", "rodas42", "rodas4p2"])
 def test_reference_possibly_singular_problem_succeeds(alg):
     # test/Regression_I/ode_adaptive_tests.jl:93-110: a problem whose W matrix is nearly singular must still end
     # with ReturnCode.Success for Rosenbrock23, Rodas4, Rodas4P, Rodas5, Rodas5P (Float32 literals promoted to Float64
     # exactly as in the reference; the Jacobian is analytic here, ForwardDiff there)
     a = {"ros23": oracle.ALG_ROSENBROCK23, "ros32": oracle.ALG_ROSENBROCK32, "rodas4": oracle.ALG_RODAS4,
-         "rodas4p": oracle.ALG_RODAS4P,
+         "rodas4p": oracle.ALG_RODAS4P, "rodas5pe": oracle.ALG_RODAS5PE,
          "rodas5": oracle.ALG_RODAS5, "rodas5p": oracle.ALG_RODAS5P, "rodas42": oracle.ALG_RODAS42,
          "rodas4p2": oracle.ALG_RODAS4P2}[alg]
     rhs = ("static double rr(double x1, double x2) { return x1 * ((double)-2.1474936f * (x2 + x1)); }\n"
