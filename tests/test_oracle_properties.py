@@ -652,3 +652,55 @@ def test_low_order_rk_tableau_identities():
     assert w["a21"] == w["c1"] and w["a32"] == w["c2"]
     assert abs(w["a41"] + w["a42"] + w["a43"] - 1.0) < 1e-15
     assert abs(math.fsum(w["btilde%d" % i] for i in (1, 2, 3, 4))) < 1e-16
+
+
+def _generic_rk_final(A, b, h, nsteps, lam=1.01, u=0.5):
+    """Plain explicit RK on u' = lam u with a Butcher tableau given as rows {j: a_sj} and weights {j: b_j} (0-based)."""
+    S = max(max(A), max(b)) + 1
+    for _ in range(nsteps):
+        k = [0.0] * S
+        for s in range(S):
+            us = u + h * math.fsum(a * k[j] for j, a in A.get(s, {}).items())
+            k[s] = lam * us
+        u = u + h * math.fsum(w * k[j] for j, w in b.items())
+    return u
+
+
+@pytest.mark.parametrize("name", ["DP5", "BS3", "Vern6", "Vern8", "Vern9"])
+def test_unrolled_steppers_agree_with_generic_tableau_rk(name):
+    # test/Regression_II/ode_unrolled_comparison_tests.jl:79-96 and lib/OrdinaryDiffEqVerner/test/ode_verner_tests.jl:45-52:
+    # the unrolled stepper and a generic tableau RK with the same coefficients agree to 1e-10 at fixed dt
+    import re
+    if name in ("DP5", "BS3"):
+        text = open(os.path.join(HERE, "..", "oracle", "oracle_lowrk.inc")).read()
+        body = re.search(r"template <typename R> struct %s \{(.*?)\n\};" % name, text, re.S).group(1)
+        v = {k: float(x) for k, x in re.findall(r"\b(\w+) = \(R\)([-+0-9.eE]+)", body)}
+        A = {}
+        for k, x in v.items():
+            m = re.fullmatch(r"a(\d)(\d)", k)
+            if m:
+                A.setdefault(int(m.group(1)) - 1, {})[int(m.group(2)) - 1] = x
+        if name == "DP5":
+            b = A.pop(6)                       # row 7 of DP5 is the solution row (FSAL)
+        else:
+            b = A.pop(3)                       # row 4 of BS3
+        alg = oracle.ALG_DP5 if name == "DP5" else oracle.ALG_BS3
+    else:
+        text = open(os.path.join(HERE, "..", "oracle", "oracle_verner_gen.inc")).read()
+        body = re.search(r"template <typename R> struct %s \{(.*?)\n\};" % name, text, re.S).group(1)
+        consts = {k: float(x) for k, x in re.findall(r"const R (\w+) = \(R\)([-+0-9.eE]+);", body)}
+        A = {}
+        for chain, kidx, _tm in re.findall(r"tmp\[i\] = jl_fma\(dt, (.*?), uprev\[i\]\);\s*P->f\(k\[(\d+)\], tmp, p, (.*?)\);",
+                                           body.split("void addsteps")[0]):
+            A[int(kidx)] = {int(k): consts[a] for a, k in re.findall(r"\b([a-z]+\d+)\b[ ,*]+k\[(\d+)\]\[i\]", chain)}
+        first = re.search(r"const R a = dt \* (\w+);", body).group(1)
+        A[1] = {0: consts[first]}
+        u_chain = re.search(r"u\[i\] = jl_fma\(dt, (.*?), uprev\[i\]\);", body).group(1)
+        b = {int(k): consts[a] for a, k in re.findall(r"\b([a-z]+\d+)\b[ ,*]+k\[(\d+)\]\[i\]", u_chain)}
+        alg = getattr(oracle, "ALG_" + name.upper())
+    h, nsteps = 1 / 16, 16
+    want = _generic_rk_final(A, b, h, nsteps)
+    o = oracle.solve(alg, linear_source(), np.array([[0.5]]), None, (0.0, 1.0), 1, 0, dt=h, adaptive=False)
+    assert o["naccept"][0] == nsteps
+    assert abs(o["u_final"][0, 0] - want) < 1e-10
+    assert abs(want - 0.5 * math.exp(1.01)) < (1e-4 if name == "BS3" else 1e-8)
