@@ -392,8 +392,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     if not adaptive and kw.get("dt") is None and not kw.get("tstops"):
         # solve.jl:277-280
         raise ValueError("Fixed timestep methods require a choice of dt or choosing the tstops")
-    if kw.get("dense", False):
-        raise NotImplementedError("dense=true is not on this path")
+    dense_kw = kw.get("dense", None)     # default: save_everystep && isempty(saveat) (solve.jl:144-145)
     N = int(kw["trajectories"])
     batch_size = int(kw.get("batch_size", N)) if N > 0 else 1
     f32 = kw.get("dtype", None)
@@ -411,7 +410,6 @@ def solve(eprob, alg, ensemblealg=None, **kw):
         # ... while save_on = false only silences _savevalues! (integrator_utils.jl:342): no saveat / per-step rows,
         # the start row and the end point are still stored
         grid, everystep = [], False
-    handle = _handle(ensemblealg.device)
     # save_idxs: component indices of the saved rows, 0-based here (the Julia binding converts from 1-based)
     save_idxs = kw.get("save_idxs", None)
     if save_idxs is not None:
@@ -420,6 +418,12 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             raise ValueError("save_idxs out of range for a state of length %d" % n)
     tstops = kw.get("tstops", None)
     tstops = None if tstops is None or len(tstops) == 0 else [float(x) for x in tstops]
+    dense_ok = (everystep and not grid and save_start and save_idxs is None and tstops is None
+                and alg.alg_id != _lib.ALG_ROSENBROCK32 and dense_kw is not False)      # dense = save_everystep && isempty(saveat) (solve.jl:144)
+    if dense_kw and not dense_ok:
+        raise NotImplementedError("dense=true is served for save_everystep solves without saveat / save_idxs / tstops "
+                                  "(the stages are recomputed from the saved steps); not for Rosenbrock32")
+    handle = _handle(ensemblealg.device)
     program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs, tstops is not None, adaptive)
 
     def run(u0, p, ntraj, flags=0):
@@ -431,8 +435,6 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
         return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
 
-    dense_ok = (everystep and not grid and save_start and save_idxs is None and tstops is None
-                and alg.alg_id != _lib.ALG_ROSENBROCK32)      # dense = save_everystep && isempty(saveat) (solve.jl:144)
     tol_kw = dict(reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
                   dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"))
 

@@ -531,6 +531,12 @@ def test_high_level_dense_solution_call(pkg, oracle):
     s2 = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.5)
     with pytest.raises(NotImplementedError):
         s2[0](0.3)
+    s3 = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, dense=True)          # explicit dense = true
+    assert np.array_equal(bits(s3[7](tq)), bits(o["dense"][7]))
+    s4 = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, dense=False)
+    assert not s4[7].dense
+    with pytest.raises(NotImplementedError):
+        P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.5, dense=True)
 
 
 # ---- save_idxs ---------------------------------------------------------------
