@@ -3,6 +3,7 @@ arguments, compiles through NVRTC without a GPU, and fails loudly when no device
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -100,3 +101,29 @@ def test_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".jl")):
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_nslots_agrees_with_rows_the_oracle_actually_saves(pkg):
+    """b200ode_nslots (pure host arithmetic, no GPU needed) must equal the number of rows a successful trajectory
+    saves, for every combination of the save flags and random grids — checked against the oracle's nsaved."""
+    import itertools
+    from oracle import oracle
+    from helpers import linear_source
+    ll = pkg.lowlevel
+    rng = np.random.default_rng(11)
+    s = linear_source()
+    u0 = np.array([[0.5]])
+    for trial in range(12):
+        k = int(rng.integers(1, 6))
+        grid = sorted(float(x) for x in rng.uniform(0.05, 1.0, k))
+        if trial % 3 == 0:
+            grid[-1] = 1.0                                   # grid ends at tf
+        if trial % 4 == 1 and k > 1:
+            grid[1] = grid[0]                                # duplicate point
+        for ss, se in itertools.product((None, True, False), repeat=2):
+            n = ll.nslots_for((0.0, 1.0), grid, save_start=ss, save_end=se)
+            o = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, saveat=grid, save_start=ss, save_end=se)
+            assert o["retcode"][0] == 1
+            assert n == o["nslots"] == o["nsaved"][0], (grid, ss, se, n, o["nsaved"][0])
+            if n > 0:
+                assert len(o["ts"]) == n and list(o["ts"]) == sorted(o["ts"])
