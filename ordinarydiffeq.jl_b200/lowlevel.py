@@ -257,3 +257,48 @@ def timeseries_meanvar_device(handle, dtype, us, mean, var=None, stream=None):
     _lib.check(L.b200ode_timeseries_meanvar_device(handle._h, dtype, C.c_void_p(us.data_ptr()), int(N), int(nslots), int(n),
                                                    C.c_void_p(mean.data_ptr()),
                                                    C.c_void_p(var.data_ptr()) if var is not None else None, C.c_void_p(stream)))
+
+
+def solve_everystep_device(program, bufs, tspan, row_offsets=None, ts=None, dts=None, us=None, reltol=None, abstol=None,
+                           dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
+                           flags=0, stream=None, tstops=None):
+    """Device-resident save_everystep (b200ode_solve_everystep_device); asynchronous.
+
+    Counting pass: row_offsets=None — fills bufs.nsaved.  Fill pass: row_offsets = int64[N+1] exclusive scan of those
+    counts (e.g. torch.cumsum on the device), ts/dts = real[total], us = real[total, nsave], all device tensors."""
+    L = _lib.lib()
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops)
+    dp = _lib.B200DeviceProblem()
+    dp.trajectories = bufs.N
+    dp.u0 = bufs.u0.data_ptr(); dp.u0_shared = int(bufs.u0_shared); dp.u0_layout = bufs.layout
+    dp.p = bufs.p.data_ptr(); dp.p_shared = int(bufs.p_shared); dp.p_layout = bufs.layout
+    dp.t0, dp.tf = float(tspan[0]), float(tspan[1])
+    dr = _lib.B200DeviceResult()
+    dr.u_final = bufs.u_final.data_ptr(); dr.u_final_layout = bufs.layout
+    dr.t_final = bufs.t_final.data_ptr()
+    dr.us = us.data_ptr() if us is not None else None
+    for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
+        setattr(dr, name, getattr(bufs, name).data_ptr())
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.b200ode_solve_everystep_device(
+        program.handle._h, program._p, C.byref(dp), C.byref(opts), C.byref(dr),
+        C.c_void_p(row_offsets.data_ptr()) if row_offsets is not None else None,
+        C.c_void_p(ts.data_ptr()) if ts is not None else None,
+        C.c_void_p(dts.data_ptr()) if dts is not None else None, C.c_void_p(stream)))
+
+
+def dense_eval_device(program, N, p, row_offsets, ts, dts, us, tq, out, p_shared=False, layout=_lib.LAYOUT_AOS,
+                      reltol=None, abstol=None, stream=None):
+    """sol_i(tq[j]) from device-resident ragged rows (b200ode_dense_eval_device); tq ascending, out = real[N, len(tq), n]."""
+    L = _lib.lib()
+    opts, keep = _lib.make_opts(reltol, abstol)
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.b200ode_dense_eval_device(
+        program.handle._h, program._p, int(N), C.c_void_p(p.data_ptr()) if p is not None else None, int(p_shared),
+        int(layout), C.c_void_p(row_offsets.data_ptr()), C.c_void_p(ts.data_ptr()), C.c_void_p(dts.data_ptr()),
+        C.c_void_p(us.data_ptr()), C.c_void_p(tq.data_ptr()), int(tq.numel()), C.c_void_p(out.data_ptr()),
+        C.byref(opts), C.c_void_p(stream)))

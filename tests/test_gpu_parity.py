@@ -826,3 +826,37 @@ def test_rosenbrock32_parity(pkg, handle, oracle, f32):
         # f(uprev + dt k2) of the previous step, which no saved row holds, so the path declines instead of guessing
         with pytest.raises(pkg.B200Error):
             pkg.lowlevel.solve_host_dense(prog_e, U0, p, (0.0, 1.0), np.array([0.0, 0.3]), **tol)
+
+
+def test_device_resident_ragged_and_dense_api(pkg, handle, oracle):
+    """The torch-tensor form of save_everystep / dense output: count pass, scan on the device (torch.cumsum), fill pass,
+    dense evaluation — nothing but the total row count visits the host."""
+    import torch
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    N = 4096
+    s, n = pl.lorenz_source()
+    p = pl.lorenz_params(N)
+    prog = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, s, n, extra_options=pkg._lib.OPT_EVERYSTEP)
+    b = ll.DeviceBuffers(prog, N, 0, "cuda:0", u0_shared=True)
+    b.u0.copy_(torch.tensor([1.0, 0, 0], dtype=torch.float64)); b.p.copy_(torch.from_numpy(p))
+    ll.solve_everystep_device(prog, b, (0.0, 2.0))
+    offs = torch.zeros(N + 1, dtype=torch.int64, device="cuda:0")
+    offs[1:] = torch.cumsum(b.nsaved.to(torch.int64), 0)
+    total = int(offs[-1].item())
+    ts = torch.empty(total, dtype=torch.float64, device="cuda:0")
+    dts = torch.empty_like(ts)
+    us = torch.empty((total, 3), dtype=torch.float64, device="cuda:0")
+    ll.solve_everystep_device(prog, b, (0.0, 2.0), row_offsets=offs, ts=ts, dts=dts, us=us)
+    o = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 2.0), 3, 3, save_everystep=True)
+    assert np.array_equal(offs.cpu().numpy(), o["row_offsets"])
+    assert np.array_equal(ts.cpu().numpy(), o["ts"]) and np.array_equal(bits(us.cpu().numpy()), bits(o["us"]))
+    # dts: the step that ended at each row; the start row carries 0; consecutive rows differ by it up to rounding
+    d = dts.cpu().numpy(); t = ts.cpu().numpy(); first = o["row_offsets"][:-1]
+    assert (d[first] == 0).all()
+    inner = np.ones(total, dtype=bool); inner[first] = False
+    assert np.allclose(t[inner] - t[np.nonzero(inner)[0] - 1], d[inner], rtol=1e-12, atol=1e-15)
+    tq = torch.linspace(0.0, 2.0, 17, dtype=torch.float64, device="cuda:0")
+    out = torch.empty((N, 17, 3), dtype=torch.float64, device="cuda:0")
+    ll.dense_eval_device(prog, N, b.p, offs, ts, dts, us, tq, out)
+    od = oracle.solve(oracle.ALG_TSIT5, (s, n), U0, p, (0.0, 2.0), 3, 3, dense_tq=tq.cpu().numpy())
+    assert np.array_equal(bits(out.cpu().numpy()), bits(od["dense"]))
