@@ -704,3 +704,25 @@ def test_unrolled_steppers_agree_with_generic_tableau_rk(name):
     assert o["naccept"][0] == nsteps
     assert abs(o["u_final"][0, 0] - want) < 1e-10
     assert abs(want - 0.5 * math.exp(1.01)) < (1e-4 if name == "BS3" else 1e-8)
+
+
+def test_reference_tstops_with_adaptive_steppers(pkg):
+    s_late = ("void rhs(double* du, const double* u, const double* p, const double t) { du[0] = u[0] * p[0] + t; }\n", "rhs")
+    # test/InterfaceI/ode_tstops_tests.jl:96-106 ("Late binding tstops"): tstops = tspan[1]:p:tspan[2]; the whole range ⊆ sol.t
+    for pval in (0.1, 0.07):
+        stops = pkg.ranges.julia_range(0.0, pval, 1.0)
+        o = oracle.solve(oracle.ALG_TSIT5, s_late, np.array([[1.0]]), np.array([[pval]]), (0.0, 1.0), 1, 1,
+                         tstops=stops, save_everystep=True)
+        assert o["retcode"][0] == 1 and set(stops) <= set(o["ts"]), pval
+    # :110-151 ("StaticArrays vs Arrays with extreme precision", issue #2752: tstop overshoot): Vern9, reltol 1e-12,
+    # abstol 1e-15, tstops = [0.5, 1.0, 1.5] — Success and every stop is in sol.t
+    s_prec = ("#include <math.h>\nvoid pd(double* du, const double* u, const double* p, const double t) {\n"
+              "  double f = 1.0e-6 * sin(100 * t);\n"
+              "  du[0] = u[2]; du[1] = u[3]; du[2] = -0.01 * u[0] + f * 1; du[3] = -0.01 * u[1] + f * 1;\n}\n", "pd")
+    u0 = np.array([[1.0, -0.5, 0.01, 0.01]])
+    o = oracle.solve(oracle.ALG_VERN9, s_prec, u0, None, (0.0, 2.0), 4, 0, reltol=1e-12, abstol=1e-15,
+                     tstops=[0.5, 1.0, 1.5], save_everystep=True)
+    assert o["retcode"][0] == 1 and {0.5, 1.0, 1.5} <= set(o["ts"]) and o["ts"][-1] == 2.0
+    # the harmonic part has the closed form x(t) = x0 cos(0.1 t) + v0 sin(0.1 t)/0.1 up to the 1e-6 forcing
+    x = 1.0 * math.cos(0.2) + 0.01 * math.sin(0.2) / 0.1
+    assert abs(o["u_final"][0, 0] - x) < 1e-6
