@@ -149,3 +149,64 @@ def pleiades_u0(N, offset=0, f32=False):
         # U(i,j) is defined for j < 4 by the 4 i + j packing; use a disjoint stream per j
         u0[:, j] += 0.01 * (2.0 * splitmix64_uniform(idx * np.uint64(4) + np.uint64(j // 4), j % 4) - 1.0)
     return u0.astype(np.float32) if f32 else u0
+
+
+# ---- stiff systems with n != 3: the LU branch of the Rosenbrock linear solve -----------------------
+# Van der Pol   /root/reference/benchmark/benchmarks.jl:110-123   (n = 2, p = [mu])
+# HIRES n = 5   /root/reference/test/InterfaceI/static_array_tests.jl:125-143  (SVector form, StaticWOperator inv path)
+# HIRES n = 8   /root/reference/test/InterfaceI/static_array_tests.jl:145-167  (n > 7: StaticWOperator keeps lu(W))
+# The reference solves these with AD Jacobians; here jac/tgrad are derived symbolically (codegen.py), the
+# ODEFunction(f; jac, tgrad) branch of calc_J / calc_tderivative.  Rate constants are parameters so that
+# prob_func can randomise them.
+def _vdp(u, p, t):
+    x, y = u
+    return [y, p[0] * ((1 - x * x) * y - x)]
+
+
+def _hires5(u, p, t):
+    y1, y2, y3, y4, y5 = u
+    return [-p[0] * y1 + 0.43 * y2 + 8.32 * y3 + 0.0007,
+            p[0] * y1 - 8.75 * y2,
+            -10.03 * y3 + 0.43 * y4 + 0.035 * y5,
+            8.32 * y2 + p[0] * y3 - 1.12 * y4,
+            -1.745 * y5 + 0.43 * y2 + 0.43 * y4]
+
+
+def _hires8(u, p, t):
+    y1, y2, y3, y4, y5, y6, y7, y8 = u
+    return [-p[0] * y1 + 0.43 * y2 + 8.32 * y3 + 0.0007,
+            p[0] * y1 - 8.75 * y2,
+            -10.03 * y3 + 0.43 * y4 + 0.035 * y5,
+            8.32 * y2 + p[0] * y3 - 1.12 * y4,
+            -1.745 * y5 + 0.43 * y6 + 0.43 * y7,
+            -p[1] * y6 * y8 + 0.69 * y4 + p[0] * y5 - 0.43 * y6 + 0.69 * y7,
+            p[1] * y6 * y8 - 1.81 * y7,
+            -p[1] * y6 * y8 + 1.81 * y7]
+
+
+STIFF_PROBLEMS = {
+    # name: (f, n, np, u0, tspan, nominal p)
+    "vdp": (_vdp, 2, 1, [1.0, 1.0], (0.0, 6.3), [1.0e3]),
+    "hires5": (_hires5, 5, 1, [1.0, 0.0, 0.0, 0.0, 0.0057], (0.0, 321.8122), [1.71]),
+    "hires8": (_hires8, 8, 2, [1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0057], (0.0, 321.8122), [1.71, 280.0]),
+}
+
+
+def stiff_sources(name, f32=False):
+    """(rhs, jac, tgrad) C sources (each (text, function name)), n, np, u0, tspan for a STIFF_PROBLEMS entry."""
+    from . import codegen
+    f, n, np_, u0, tspan, _ = STIFF_PROBLEMS[name]
+    rhs = codegen.build_function_c(f, n, np_, fname=name + "_rhs", f32=f32)
+    jac = codegen.build_jacobian_c(f, n, np_, fname=name + "_jac", f32=f32)
+    tg = codegen.build_tgrad_c(f, n, np_, fname=name + "_tgrad", f32=f32)
+    return rhs, jac, tg, n, np_, np.asarray(u0, dtype=np.float32 if f32 else np.float64), tspan
+
+
+def stiff_params(name, N, offset=0, f32=False):
+    """p[i][j] = nominal_j (0.5 + U(i, j))."""
+    nominal = STIFF_PROBLEMS[name][5]
+    idx = np.arange(offset, offset + N, dtype=np.uint64)
+    p = np.empty((N, len(nominal)), dtype=np.float64)
+    for j, v in enumerate(nominal):
+        p[:, j] = v * (0.5 + splitmix64_uniform(idx, j))
+    return p.astype(np.float32) if f32 else p

@@ -1,0 +1,84 @@
+"""Multi-GPU parity (-m gpu; skipped on a single-GPU box): the interleaved shards of the rho sweep, integrated by one
+process per GPU and gathered back over NCCL, must equal the single-GPU run bit for bit and in trajectory order;
+the all-reduced ensemble mean must equal the single-GPU mean to 1e-12 (different summation tree)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_main(rank, world, port, N, q):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import torch
+    import torch.distributed as dist
+    import b200_import
+    pkg = b200_import.load()
+    d = importlib.import_module("ordinarydiffeq_jl_b200.distributed")
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    h = pkg.Handle(rank)
+    rhs = pl.lorenz_source(False)
+    prog = h.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1])
+    idx = d.shard_indices(N, world, rank)
+    m = int(idx.shape[0])
+    p = pl.lorenz_params(N, sweep_total=N)[idx]
+    bufs = ll.DeviceBuffers(prog, m, 0, dev, u0_shared=True)
+    bufs.u0.copy_(torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64))
+    bufs.p.copy_(torch.from_numpy(np.ascontiguousarray(p)))
+    ll.solve_device(prog, bufs, (0.0, 10.0))
+    part = torch.zeros(3, dtype=torch.float64, device=dev)
+    ll.reduce_sum_device(h, pkg.F64, bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
+    full = d.gather_in_order(bufs.u_final, N)
+    steps = d.gather_in_order((bufs.naccept + bufs.nreject).to(torch.int32), N)
+    mean = d.allreduce_mean(part, N)
+    torch.cuda.synchronize()
+    if rank == 0:
+        q.put((full.cpu().numpy(), steps.cpu().numpy(), mean.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+    prog.close()
+    h.close()
+
+
+@pytest.mark.parametrize("N", [8192, 5000])      # a multiple of world*1024 (strided un-interleave) and a ragged count
+def test_two_rank_nccl_sweep_equals_single_gpu(pkg, handle, N):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    rhs = pl.lorenz_source(False)
+    prog = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1])
+    one = ll.solve_host(prog, np.array([1.0, 0.0, 0.0]), pl.lorenz_params(N, sweep_total=N), (0.0, 10.0))
+    prog.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, N, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full, steps, mean = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert np.array_equal(full.view(np.uint64), one["u_final"].view(np.uint64))
+    assert np.array_equal(steps, one["naccept"] + one["nreject"])
+    assert np.allclose(mean, one["u_final"].mean(axis=0), rtol=1e-12, atol=0)

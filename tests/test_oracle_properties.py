@@ -726,3 +726,24 @@ def test_reference_tstops_with_adaptive_steppers(pkg):
     # the harmonic part has the closed form x(t) = x0 cos(0.1 t) + v0 sin(0.1 t)/0.1 up to the 1e-6 forcing
     x = 1.0 * math.cos(0.2) + 0.01 * math.sin(0.2) / 0.1
     assert abs(o["u_final"][0, 0] - x) < 1e-6
+
+
+# ---- SVector stiff systems of the reference's static-array tests (the StaticWOperator path with n != 3) ----
+@pytest.mark.parametrize("problem", ["vdp", "hires5", "hires8"])
+def test_reference_static_array_stiff_systems_succeed(pkg, problem):
+    """test/InterfaceI/static_array_tests.jl:106-167 (`@test_nowarn solve(prob, Rosenbrock23/Rodas5(...))` at the default
+    tolerances) and benchmark/benchmarks.jl:110-123: the solves succeed; HIRES keeps its invariant-free state finite and
+    Rosenbrock23 / Rodas5P agree to the tolerance."""
+    from oracle import oracle
+    pl = pkg.problems_library
+    r, j, tg, n, np_, u0, tspan = pl.stiff_sources(problem)
+    p = np.asarray([pl.STIFF_PROBLEMS[problem][5]], dtype=np.float64)
+    sols = []
+    for alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_RODAS5, oracle.ALG_RODAS5P):
+        o = oracle.solve(alg, r, u0, p, tspan, n, np_, jac=j, tgrad=tg)
+        assert o["retcode"][0] == 1 and o["t_final"][0] == tspan[1]
+        assert o["njacs"][0] == 2 * (o["naccept"][0] + o["nreject"][0])
+        sols.append(o["u_final"][0])
+    tight = oracle.solve(oracle.ALG_RODAS5P, r, u0, p, tspan, n, np_, jac=j, tgrad=tg, reltol=1e-10, abstol=1e-12)["u_final"][0]
+    for s in sols:
+        assert np.abs(s - tight).max() <= 5e-2 * max(1.0, np.abs(tight).max())
