@@ -6,7 +6,7 @@ The directory name contains a dot, so it is imported through `b200_import.load()
 """
 from . import _lib, codegen, lowlevel, problems_library  # noqa: F401
 from ._lib import (ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P, ALG_DP5, ALG_BS3, ALG_RODAS5, ALG_RODAS4,
-                   ALG_RODAS42, ALG_RODAS4P, ALG_RODAS4P2, ALG_VERN6, ALG_VERN8, ALG_VERN9, ALG_ROSENBROCK32, ALG_RODAS5PE, F32, F64, B200Error, Handle,  # noqa: F401
+                   ALG_RODAS42, ALG_RODAS4P, ALG_RODAS4P2, ALG_VERN6, ALG_VERN8, ALG_VERN9, ALG_ROSENBROCK32, ALG_RODAS5PE, F32, F64, B200Error, Handle, MultiHandle,  # noqa: F401
                    compile_only)
 from .ensemble import (CSource, DEStats, EnsembleAlgorithm, EnsembleB200, EnsembleContext, EnsembleDistributed,  # noqa: F401
                        EnsembleProblem, EnsembleSerial, EnsembleSolution, EnsembleThreads, ODEFunction, ODEProblem,

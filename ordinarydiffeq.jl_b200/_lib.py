@@ -73,6 +73,7 @@ class B200Ragged(C.Structure):
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
 OPT_TSTOPS = "-DB200_TSTOPS=1"
 OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
+OPT_COMPONENT_RHS = "-DB200_COOP=1"
 
 
 def opt_save_idxs(idxs):
@@ -87,7 +88,9 @@ EXPORTS = [
     "b200ode_compile_only", "b200ode_free", "b200ode_nslots", "b200ode_solve", "b200ode_solve_device",
     "b200ode_reduce_sum_device", "b200ode_timeseries_meanvar_device", "b200ode_solve_meanvar", "b200ode_host_register", "b200ode_host_unregister",
     "b200ode_measure_fma_peak", "b200ode_solve_everystep", "b200ode_solve_everystep_device",
-    "b200ode_dense_eval_device", "b200ode_solve_dense",
+    "b200ode_dense_eval_device", "b200ode_solve_dense", "b200ode_selftest_fastmath",
+    "b200ode_multi_create", "b200ode_multi_destroy", "b200ode_multi_device_count", "b200ode_multi_compile",
+    "b200ode_multi_program_destroy", "b200ode_multi_solve", "b200ode_multi_reduce_mean",
 ]
 
 _lib = None
@@ -133,6 +136,15 @@ def lib():
     L.b200ode_host_register.argtypes = [vp, C.c_size_t]
     L.b200ode_host_unregister.argtypes = [vp]
     L.b200ode_measure_fma_peak.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl)]
+    L.b200ode_selftest_fastmath.argtypes = [vp, i64, C.c_uint64, C.POINTER(i64), C.POINTER(i64)]
+    L.b200ode_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), i32]
+    L.b200ode_multi_destroy.argtypes = [vp]
+    L.b200ode_multi_device_count.argtypes = [vp]
+    L.b200ode_multi_compile.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, cp, cp, cp, cp, cp, cp, cp]
+    L.b200ode_multi_program_destroy.argtypes = [vp]
+    L.b200ode_multi_solve.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(B200Result)]
+    L.b200ode_multi_reduce_mean.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(dbl),
+                                            C.POINTER(B200Result)]
     _lib = L
     return L
 
@@ -198,6 +210,12 @@ class Handle:
         check(lib().b200ode_measure_fma_peak(self._h, dtype, C.byref(tf), C.byref(mhz)))
         return tf.value, mhz.value
 
+    def selftest_fastmath(self, samples=1 << 24, seed=1):
+        """(mismatches, flagged) of the branch-free division / square-root sequences vs the IEEE operators."""
+        bad, fl = (C.c_int64 * 6)(), C.c_int64()
+        check(lib().b200ode_selftest_fastmath(self._h, int(samples), int(seed), bad, C.byref(fl)))
+        return list(bad), fl.value
+
 
 class Program:
     def __init__(self, handle, alg, dtype, n, np_, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
@@ -219,6 +237,64 @@ class Program:
     def close(self):
         if self._p:
             lib().b200ode_program_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiHandle:
+    """Several GPUs driven from this process (b200ode_multi_create).  devices: list of device ids, or None = all."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices is None:
+            check(lib().b200ode_multi_create(C.byref(self._h), None, 0))
+        else:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            check(lib().b200ode_multi_create(C.byref(self._h), ids, len(devices)))
+        self.ndev = lib().b200ode_multi_device_count(self._h)
+
+    def compile(self, alg, dtype, n, np_, rhs_src, rhs_name, jac_src=None, jac_name=None, tgrad_src=None,
+                tgrad_name=None, extra_options=None):
+        return MultiProgram(self, alg, dtype, n, np_, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
+                            extra_options)
+
+    def close(self):
+        if self._h:
+            lib().b200ode_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiProgram:
+    """One program per device of a MultiHandle; accepted by lowlevel.solve_host / solve_host_mean."""
+    multi = True
+
+    def __init__(self, handle, alg, dtype, n, np_, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
+                 extra_options):
+        self.handle = handle
+        self.alg, self.dtype, self.n, self.np = alg, dtype, n, np_
+        self.everystep = bool(extra_options) and OPT_EVERYSTEP in extra_options
+        self.nsave = n
+        for tok in (extra_options or "").split():
+            if tok.startswith("-DB200_SAVE_IDXS="):
+                self.nsave = len(tok.split("=", 1)[1].split(","))
+        self._p = C.c_void_p()
+        check(lib().b200ode_multi_compile(handle._h, C.byref(self._p), alg, dtype, n, np_, _b(rhs_src), _b(rhs_name),
+                                          _b(jac_src), _b(jac_name), _b(tgrad_src), _b(tgrad_name), _b(extra_options)))
+
+    def close(self):
+        if self._p:
+            lib().b200ode_multi_program_destroy(self._p)
             self._p = C.c_void_p()
 
     def __del__(self):

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "device_sources.inc"   // k_b200_header_names[], k_b200_header_sources[], k_b200_num_headers
+#include "device/b200_base.cuh"  // the flagged fast division / square root, for b200ode_selftest_fastmath
 
 namespace {
 
@@ -114,8 +115,7 @@ struct b200ode_program_s {
     std::vector<char> cubin;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t k_integrate = nullptr, k_initdt = nullptr, k_dense = nullptr;
-    int sliced_g = 0;            // > 0: component-sliced kernel with this many warps per 32 trajectories
-    int sliced_k = 1;            // groups of 32 trajectories per CTA
+    int coop_l = 0;              // > 0: lane-group kernel (device/b200_coop.cuh) with this many lanes per trajectory
     bool everystep = false;      // compiled with -DB200_EVERYSTEP=1 (ragged save_everystep output)
     bool tstops = false;         // compiled with -DB200_TSTOPS=1
     bool adaptive = true;        // false: compiled with -DB200_ADAPTIVE=0 (fixed dt)
@@ -199,7 +199,7 @@ int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src
 // Assemble the translation unit and run NVRTC.
 int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                 const char* jac_src, const char* jac_name, const char* tgrad_src, const char* tgrad_name,
-                const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms, int* sliced_g = nullptr) {
+                const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms, int* coop_l = nullptr) {
     int rc = validate_compile_args(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name);
     if (rc) return rc;
     bool stiff = is_stiff_alg(alg);
@@ -234,6 +234,12 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     bool rhs_inline = strlen(rhs_src) * (size_t)call_sites <= 120000;
     if (extra_options && strstr(extra_options, "-DB200_RHS_INLINE=1")) rhs_inline = true;
     if (extra_options && strstr(extra_options, "-DB200_RHS_INLINE=0")) rhs_inline = false;
+    // Lane-group kernel (device/b200_coop.cuh): opt-in with -DB200_COOP=1; the RHS is then in component form
+    //     real NAME(int i, const real* u, const real* p, const real t)   returning du_i
+    const bool coop = extra_options && strstr(extra_options, "-DB200_COOP=1");
+    if (coop && alg != B200ODE_ALG_VERN7)
+        return fail(B200ODE_EUNSUPPORTED, "the lane-group kernel (B200ODE_OPT_COMPONENT_RHS) is available for Vern7");
+    if (!coop)
     tu += std::string(rhs_inline ? "__device__ __forceinline__ void " : "__device__ __noinline__ void ") + rhs_name +
           "(real* du, const real* u, const real* p, const real t);\n";
     if (stiff) {
@@ -244,6 +250,24 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
                   "(real* dT, const real* u, const real* p, const real t);\n";
     }
     tu += "// ---- user source (RHS) ----\n";
+    if (coop) {
+        // Component form: the user's text is compiled twice as a member function of two wrapper structs.
+        //  B200UserFast:  sqrt()/sqrtf() and the optional B200_DIV(a, b) hint expand to the flagged branch-free
+        //                 sequences of b200_base.cuh (bit-identical to the IEEE operators unless they raise the flag),
+        //                 so the independent terms of a sum interleave instead of queueing behind one another's
+        //                 slow-path branches;
+        //  B200UserExact: the plain operators; evaluated only when the fast evaluation raised its flag.
+        const std::string body = strip_includes(rhs_src);
+        tu += "struct B200UserFast {\n  bool b200_bad;\n"
+              "#define B200_DIV(a, b) b200_div_fast((a), (b), b200_bad)\n"
+              "#define sqrt(x) b200_sqrt_fast((x), b200_bad)\n#define sqrtf(x) b200_sqrt_fast((x), b200_bad)\n";
+        tu += body;
+        tu += "\n#undef B200_DIV\n#undef sqrt\n#undef sqrtf\n};\n";
+        tu += "struct B200UserExact {\n#define B200_DIV(a, b) ((a) / (b))\n";
+        tu += body;
+        tu += "\n#undef B200_DIV\n};\n";
+        tu += std::string("#define B200_USER_COMP_NAME ") + rhs_name + "\n";
+    } else
     tu += strip_includes(rhs_src);
     if (stiff) {
         tu += "// ---- user source (Jacobian) ----\n";
@@ -254,7 +278,8 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         }
     }
     tu += "// ---- steppers ----\n";
-    tu += std::string("#define B200_USER_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
+    if (coop) tu += "#define B200_USER_RHS_COMP(i,u,p,t) (B200UserExact().B200_USER_COMP_NAME((i),(u),(p),(t)))\n";
+    else tu += std::string("#define B200_USER_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
     if (stiff) {
         tu += std::string("#define B200_JAC(J,u,p,t) ") + jac_name + "((J),(u),(p),(t))\n";
         if (tgrad_src) tu += std::string("#define B200_TGRAD(dT,u,p,t) ") + tgrad_name + "((dT),(u),(p),(t))\n";
@@ -288,22 +313,20 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         }
     }
     int words = n * (dtype == B200ODE_F32 ? 1 : 2);
-    // Component-sliced kernel (device/b200_sliced.cuh, G warps per 32 trajectories): opt-in with
-    // -DB200_SLICED=1.  Measured on Pleiades/Vern7 (r1): bit-exact but 510-930 ms vs 180-220 ms — the
-    // G warps of a CTA run G different slices of the straight-line RHS, so the instruction stream per
-    // SM is G times wider and the 43 KB RHS thrashes the 32 KB instruction cache
-    // (ncu: stall_no_instruction 12 per issue).  It pays only for RHS code that fits the cache.
-    bool sliced = false;
-    if (extra_options && strstr(extra_options, "-DB200_SLICED=0")) sliced = false;
-    if (extra_options && strstr(extra_options, "-DB200_SLICED=1")) sliced = (alg == B200ODE_ALG_VERN7);
-    if (sliced) {
-        if (!(extra_options && strstr(extra_options, "-DB200_SLICED="))) opts.push_back("-DB200_SLICED=1");
-        if (!(extra_options && strstr(extra_options, "-DB200_G="))) {
-            int g = (n + 3) / 4;
-            if (g > 16) g = 16;
-            opts.push_back("-DB200_G=" + std::to_string(g));
+    int coop_lanes = 0;
+    if (coop) {
+        // lanes per trajectory: the smallest power of two that leaves at most 2 components per lane (n = 28 -> 16)
+        const char* at = extra_options ? strstr(extra_options, "-DB200_L=") : nullptr;
+        if (at) coop_lanes = atoi(at + 9);
+        else {
+            coop_lanes = 2;
+            while (coop_lanes < 32 && (n + coop_lanes - 1) / coop_lanes > 2) coop_lanes *= 2;
+            opts.push_back("-DB200_L=" + std::to_string(coop_lanes));
         }
+        if (coop_lanes < 2 || coop_lanes > 32 || (coop_lanes & (coop_lanes - 1)))
+            return fail(B200ODE_EINVAL, "-DB200_L= must be a power of two in 2..32");
     }
+    if (coop_l) *coop_l = coop_lanes;
     // measured launch shapes (scripts/sweep_dev.py): small explicit systems run best as one 512-thread
     // CTA per SM at 128 registers (FP64) / three 256-thread CTAs at 80 registers (FP32)
     const bool small_explicit = !stiff && words <= 8 &&
@@ -313,6 +336,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         else { opts.push_back("-DB200_BLOCK=512"); opts.push_back("-DB200_MINBLOCKS=1"); }
         has_block = has_minb = true;
     }
+    if (coop && !has_minb) { opts.push_back("-DB200_MINBLOCKS=4"); has_minb = true; }
     if (!has_block) opts.push_back("-DB200_BLOCK=128");
     if (!has_minb) {
         // registers available per thread at k CTAs of 128 threads: 65536/(128k)
@@ -322,16 +346,6 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
             minb = (words <= 6) ? (alg == B200ODE_ALG_VERN9 ? 2 : 3) : 1;
         else minb = (words <= 8) ? 4 : (words <= 16 ? 2 : 1);
         opts.push_back("-DB200_MINBLOCKS=" + std::to_string(minb));
-    }
-    if (sliced_g) {
-        *sliced_g = 0;
-        bool on = false; int g = 0, k = 1;
-        for (auto& o : opts) {
-            if (o == "-DB200_SLICED=1") on = true;
-            if (o.rfind("-DB200_G=", 0) == 0) g = atoi(o.c_str() + 9);
-            if (o.rfind("-DB200_K=", 0) == 0) k = atoi(o.c_str() + 9);
-        }
-        if (on && g > 0) *sliced_g = g + 1000 * (k > 0 ? k : 1);      // packed: G + 1000*K
     }
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
@@ -496,6 +510,78 @@ __global__ void __launch_bounds__(256) k_scan_apply(const int* __restrict__ coun
     if (blockIdx.x == 0 && threadIdx.x == 0) offsets[N] = *total;
 }
 
+// ---- self-test of the flagged fast division / square root (device/b200_base.cuh) against the plain operators ----
+__device__ __forceinline__ unsigned long long st_mix(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// operand generator: class 0 = arbitrary bit patterns (every exponent, subnormals, Inf, NaN), 1 = moderate exponents
+// (what an ODE step sees), 2 = mantissas near all-ones / all-zeros (the hard cases of Markstein-type corrections)
+__device__ __forceinline__ double st_f64(unsigned long long r, int cls) {
+    if (cls == 0) return __longlong_as_double((long long)r);
+    unsigned long long mant = r & 0xFFFFFFFFFFFFFull, sign = r & 0x8000000000000000ull;
+    unsigned long long e = 1023ull - 40ull + ((r >> 52) % 81ull);
+    if (cls == 2) { const unsigned k = (unsigned)((r >> 40) & 31u); mant = ((r >> 47) & 1ull) ? (0xFFFFFFFFFFFFFull >> k << k) : (mant >> (k + 20)); }
+    return __longlong_as_double((long long)(sign | (e << 52) | mant));
+}
+__device__ __forceinline__ float st_f32(unsigned long long r, int cls) {
+    const unsigned u = (unsigned)(r >> 17);
+    if (cls == 0) return __uint_as_float(u);
+    unsigned mant = u & 0x7FFFFFu, sign = u & 0x80000000u, e = 127u - 30u + ((unsigned)(r >> 50) % 61u);
+    if (cls == 2) { const unsigned k = (unsigned)((r >> 8) & 15u); mant = ((r >> 7) & 1ull) ? (0x7FFFFFu >> k << k) : (mant >> (k + 6)); }
+    return __uint_as_float(sign | (e << 23) | mant);
+}
+__global__ void __launch_bounds__(256) k_selftest_fastmath(long long samples, unsigned long long seed,
+                                                           unsigned long long* counters) {
+    // counters: [0] div64 [1] div_const64 [2] sqrt64 [3] div32 [4] sqrt32 [5] unguarded div32 (mismatches); [6] flagged
+    unsigned long long bad[6] = {0, 0, 0, 0, 0, 0}, flag_count = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < samples; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long r0 = st_mix(seed + 3ull * (unsigned long long)i), r1 = st_mix(r0), r2 = st_mix(r1);
+        const int cls = (int)(r2 % 3ull);
+        {   // binary64 division
+            const double a = st_f64(r0, cls), b = st_f64(r1, cls);
+            bool f = false;
+            const double q = b200_div_fast(a, b, f), e = a / b;
+            flag_count += f;
+            if (!f && __double_as_longlong(q) != __double_as_longlong(e) && !(q != q && e != e)) bad[0]++;
+            // a / c with rc = RN(1/c) (b200_div_const_fast) for the divisor classes the kernels use: gamma = 0.9, the
+            // state dimension n = 1..64, and binary32-valued divisors (fastpower results).  (For arbitrary divisors
+            // the 3-operation form is NOT always the IEEE quotient — Markstein's exceptions — so it is never used there.)
+            const unsigned sel = (unsigned)(r2 >> 60) % 3u;
+            const double c = sel == 0 ? 0.9 : (sel == 1 ? (double)(1 + (int)((r2 >> 20) & 63ull))
+                                                        : (double)(0.001f + 999.0f * (float)((r1 >> 11) & 0xFFFFFFu) * (1.0f / 16777216.0f)));
+            bool g = false;
+            const double qc = b200_div_const_fast(a, c, 1.0 / c, g);
+            if (!g && __double_as_longlong(qc) != __double_as_longlong(a / c)) bad[1]++;
+        }
+        {   // binary64 square root
+            const double x = fabs(st_f64(r2, cls));
+            bool f = false;
+            const double s = b200_sqrt_fast(x, f), e = sqrt(x);
+            flag_count += f;
+            if (!f && __double_as_longlong(s) != __double_as_longlong(e) && !(s != s && e != e)) bad[2]++;
+        }
+        {   // binary32 division and square root
+            const float a = st_f32(r0, cls), b = st_f32(r1, cls), x = fabsf(st_f32(r2, cls));
+            bool f = false;
+            const float q = b200_div_fast(a, b, f), e = a / b;
+            if (!f && __float_as_uint(q) != __float_as_uint(e) && !(q != q && e != e)) bad[3]++;
+            bool g = false;
+            const float s = b200_sqrt_fast(x, g), es = sqrtf(x);
+            flag_count += f + g;
+            if (!g && __float_as_uint(s) != __float_as_uint(es) && !(s != s && es != es)) bad[4]++;
+            // the unguarded division of fastlog2: den in [1.27, 2.03), |num| < 1.3
+            const float den = 1.27f + 0.76f * (float)((r1 >> 11) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+            const float num = -0.55f + 1.85f * (float)((r0 >> 11) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+            if (__float_as_uint(b200_div_fast_nocheck(num, den)) != __float_as_uint(num / den)) bad[5]++;
+        }
+    }
+    for (int k = 0; k < 6; ++k) if (bad[k]) atomicAdd(counters + k, bad[k]);
+    if (flag_count) atomicAdd(counters + 6, flag_count);
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256) k_fma_peak(R* out, int iters, R a, R b) {
     R x0 = (R)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -602,10 +688,10 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         CUDA_TRY(cudaLaunchKernel((const void*)prog->k_initdt, dim3(g), dim3(256), args, 0, stream));
     }
     unsigned grid;
-    if (prog->sliced_g > 0) {
-        long long per = 32LL * prog->sliced_k;
-        long long nbatch = (N + per - 1) / per;
-        grid = (unsigned)std::min<long long>(prog->info.grid, nbatch);
+    if (prog->coop_l > 0) {
+        const long long per_cta = (long long)(prog->info.block / prog->coop_l);      // trajectories in flight per CTA
+        const long long need = (N + per_cta - 1) / per_cta;
+        grid = (unsigned)std::min<long long>(prog->info.grid, need > 0 ? need : 1);
     } else if (o->flags & B200ODE_FLAG_STATIC_SCHEDULE) grid = (unsigned)((N + prog->info.block - 1) / prog->info.block);
     else {
         grid = (unsigned)prog->info.grid;
@@ -723,24 +809,18 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     prog->h = h; prog->alg = alg; prog->dtype = dtype; prog->n = n; prog->np = np;
     std::string log; double ms = 0;
     int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
-                         extra_options, prog->cubin, log, &ms, &prog->sliced_g);
+                         extra_options, prog->cubin, log, &ms, &prog->coop_l);
     if (rc) { delete prog; return rc; }
     prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
     prog->tstops = extra_options && strstr(extra_options, "-DB200_TSTOPS=1");
     prog->adaptive = !(extra_options && strstr(extra_options, "-DB200_ADAPTIVE=0"));
-    if (!prog->adaptive && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "adaptive=false is not available in the sliced kernel"); }
-    if (prog->tstops && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "tstops are not available in the sliced kernel"); }
+    if ((!prog->adaptive || prog->tstops || prog->everystep) && prog->coop_l > 0) {
+        delete prog; return fail(B200ODE_EUNSUPPORTED, "adaptive=false, tstops and save_everystep are not available in the lane-group kernel");
+    }
     prog->nsave = parse_save_idxs(extra_options, n);
     if (prog->nsave < 0) { delete prog; return fail(B200ODE_EINVAL, "-DB200_SAVE_IDXS= must list 0-based component indices below n, comma separated"); }
     if (prog->nsave == 0) prog->nsave = n;
-    if (prog->nsave != n && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_idxs is not available in the sliced kernel"); }
-    if (prog->everystep && prog->sliced_g > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_everystep is not available in the sliced kernel"); }
-    if (prog->sliced_g > 0) {
-        prog->sliced_k = prog->sliced_g / 1000;
-        prog->sliced_g = prog->sliced_g % 1000;
-        prog->dyn_smem = prog->sliced_g > 1
-            ? (size_t)prog->sliced_k * (3 * n * 32 + prog->sliced_g * 32) * (dtype == B200ODE_F32 ? 4 : 8) : 0;
-    }
+    if (prog->nsave != n && prog->coop_l > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_idxs is not available in the lane-group kernel"); }
     cudaError_t e = cudaLibraryLoadData(&prog->lib, prog->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
@@ -1317,6 +1397,23 @@ int b200ode_host_unregister(void* ptr) {
     return B200ODE_OK;
 }
 
+int b200ode_selftest_fastmath(b200ode_handle h, int64_t samples, uint64_t seed, int64_t* mismatches, int64_t* flagged) {
+    if (!h || !mismatches) return fail(B200ODE_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), h->stream));
+    k_selftest_fastmath<<<h->num_sms * 8, 256, 0, h->stream>>>((long long)samples, (unsigned long long)seed, d);
+    unsigned long long out[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(out, d, sizeof(out), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(B200ODE_ECUDA, std::string("selftest: ") + cudaGetErrorString(e));
+    for (int k = 0; k < 6; ++k) mismatches[k] = (int64_t)out[k];
+    if (flagged) *flagged = (int64_t)out[6];
+    return B200ODE_OK;
+}
+
 int b200ode_measure_fma_peak(b200ode_handle h, int dtype, double* tflops, double* sm_clock_mhz) {
     if (!h || !tflops) return fail(B200ODE_EINVAL, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -1342,6 +1439,189 @@ int b200ode_measure_fma_peak(b200ode_handle h, int dtype, double* tflops, double
         *sm_clock_mhz = khz / 1000.0;
     }
     return B200ODE_OK;
+}
+
+}  // extern "C"
+
+// ===========================================================================
+// Multi-GPU from ONE process (the reference analogue is EnsembleDistributed's pmap over workers,
+// lib/DiffEqBase/test/downstream/distributed_ensemble.jl:43-51): trajectories are independent, so the ensemble is cut
+// into contiguous chunks that are dealt round-robin to the devices (chunk c -> device c % ndev; several chunks per
+// device so that a parameter sweep whose cost varies with the index is balanced), one host thread per device runs its
+// chunks through the single-device entry points, and every chunk's outputs land directly in the caller's arrays at
+// the chunk's offset — the "ordered gather" costs no extra copy.  No NCCL is needed: there is no exchange step in
+// the integration; the ensemble mean is combined from per-chunk partial sums in chunk order (deterministic).
+struct b200ode_multi_s {
+    std::vector<b200ode_handle> dev;
+};
+struct b200ode_multi_program_s {
+    b200ode_multi m = nullptr;
+    std::vector<b200ode_program> prog;     // one per device
+};
+
+namespace {
+const int kChunksPerDevice = 8;
+struct ChunkPlan { long long c0, cn; int dev; };
+std::vector<ChunkPlan> plan_chunks(long long N, int ndev) {
+    std::vector<ChunkPlan> plan;
+    if (N <= 0) return plan;
+    long long nchunks = (long long)ndev * kChunksPerDevice;
+    long long per = (N + nchunks - 1) / nchunks;
+    per = ((per + 1023) / 1024) * 1024;                 // whole blocks of 1024 trajectories
+    int c = 0;
+    for (long long c0 = 0; c0 < N; c0 += per, ++c) plan.push_back({c0, std::min(per, N - c0), c % ndev});
+    return plan;
+}
+size_t real_size(int dtype) { return dtype == B200ODE_F32 ? 4 : 8; }
+}  // namespace
+
+extern "C" {
+
+int b200ode_multi_create(b200ode_multi* out, const int* device_ids, int ndev) {
+    if (!out) return fail(B200ODE_EINVAL, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(B200ODE_ECUDA, "no CUDA device available; this library has no CPU fallback");
+    if (ndev <= 0) ndev = count;                         // all visible devices
+    if (ndev > count && !device_ids) return fail(B200ODE_EINVAL, "ndev exceeds the number of visible devices");
+    b200ode_multi m = new b200ode_multi_s();
+    for (int i = 0; i < ndev; ++i) {
+        b200ode_handle h = nullptr;
+        int rc = b200ode_create(&h, device_ids ? device_ids[i] : i);
+        if (rc) { for (auto d : m->dev) b200ode_destroy(d); delete m; return rc; }
+        m->dev.push_back(h);
+    }
+    *out = m;
+    return B200ODE_OK;
+}
+
+int b200ode_multi_destroy(b200ode_multi m) {
+    if (!m) return B200ODE_OK;
+    for (auto d : m->dev) b200ode_destroy(d);
+    delete m;
+    return B200ODE_OK;
+}
+
+int b200ode_multi_device_count(b200ode_multi m) { return m ? (int)m->dev.size() : 0; }
+
+int b200ode_multi_compile(b200ode_multi m, b200ode_multi_program* out, int alg, int dtype, int n, int np,
+                          const char* rhs_src, const char* rhs_name, const char* jac_src, const char* jac_name,
+                          const char* tgrad_src, const char* tgrad_name, const char* extra_options) {
+    if (!m || !out) return fail(B200ODE_EINVAL, "multi handle/out is NULL");
+    *out = nullptr;
+    b200ode_multi_program mp = new b200ode_multi_program_s();
+    mp->m = m;
+    for (auto h : m->dev) {
+        b200ode_program p = nullptr;
+        int rc = b200ode_compile(h, &p, alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name, extra_options);
+        if (rc) { for (auto q : mp->prog) b200ode_program_destroy(q); delete mp; return rc; }
+        mp->prog.push_back(p);
+    }
+    *out = mp;
+    return B200ODE_OK;
+}
+
+int b200ode_multi_program_destroy(b200ode_multi_program mp) {
+    if (!mp) return B200ODE_OK;
+    for (auto q : mp->prog) b200ode_program_destroy(q);
+    delete mp;
+    return B200ODE_OK;
+}
+
+// shared driver of b200ode_multi_solve / b200ode_multi_reduce_mean
+static int multi_run(b200ode_multi m, b200ode_multi_program mp, const B200Problem* hp, const B200Opts* o, B200Result* res,
+                     double* mean) {
+    if (!m || !mp || !hp || !o) return fail(B200ODE_EINVAL, "NULL argument");
+    if (mp->m != m) return fail(B200ODE_EINVAL, "program was compiled for a different multi handle");
+    const int ndev = (int)m->dev.size();
+    const long long N = hp->trajectories;
+    const b200ode_program p0 = mp->prog[0];
+    const int n = p0->n, np = p0->np, nsave = p0->nsave;
+    const size_t rs = real_size(p0->dtype);
+    int rc = check_problem(N, hp->u0, hp->p, np, hp->t0, hp->tf, o);
+    if (rc) return rc;
+    if (!mean && (!res || !res->u_final)) return fail(B200ODE_EINVAL, "result.u_final is required");
+    const int nslots = b200ode_nslots(hp, o);
+    const std::vector<ChunkPlan> plan = plan_chunks(N, ndev);
+    std::vector<std::vector<double>> partial(plan.size());          // per-chunk sums for the ensemble mean
+    std::vector<int> status(ndev, 0);
+    std::vector<std::string> message(ndev);
+    std::vector<double> kms(ndev, 0.0), tms(ndev, 0.0);
+    auto worker = [&](int d) {
+        b200ode_handle h = m->dev[d];
+        b200ode_program prog = mp->prog[d];
+        std::vector<double> ts_scratch((size_t)std::max(nslots, 1));
+        std::vector<char> uf_scratch;
+        for (size_t ci = 0; ci < plan.size(); ++ci) {
+            if (plan[ci].dev != d) continue;
+            const long long c0 = plan[ci].c0, cn = plan[ci].cn;
+            B200Problem sub = *hp;
+            sub.trajectories = cn;
+            sub.u0 = hp->u0_shared ? hp->u0 : (const char*)hp->u0 + rs * n * (size_t)c0;
+            sub.p = (np > 0 && !hp->p_shared) ? (const void*)((const char*)hp->p + rs * np * (size_t)c0) : hp->p;
+            B200Result r{};
+            if (res) {
+                r = *res;
+                auto off = [&](void* base, size_t stride) -> void* { return base ? (char*)base + stride * (size_t)c0 : nullptr; };
+                r.u_final = off(res->u_final, rs * n);
+                r.t_final = (double*)off(res->t_final, sizeof(double));
+                r.us = off(res->us, rs * (size_t)nsave * (size_t)nslots);
+                r.ts = (ci == 0) ? res->ts : (res->ts ? ts_scratch.data() : nullptr);   // one writer for the shared grid
+                r.nsaved = (int32_t*)off(res->nsaved, 4); r.naccept = (int32_t*)off(res->naccept, 4);
+                r.nreject = (int32_t*)off(res->nreject, 4); r.nf = (int32_t*)off(res->nf, 4);
+                r.njacs = (int32_t*)off(res->njacs, 4); r.nw = (int32_t*)off(res->nw, 4);
+                r.nsolve = (int32_t*)off(res->nsolve, 4); r.retcode = (int32_t*)off(res->retcode, 4);
+            }
+            if (!r.u_final) { uf_scratch.resize(rs * n * (size_t)cn); r.u_final = uf_scratch.data(); }
+            int st = b200ode_solve(h, prog, &sub, o, &r);
+            if (st) { status[d] = st; message[d] = g_last_error; return; }
+            kms[d] += r.kernel_ms; tms[d] += r.total_ms;
+            if (mean) {
+                // the chunk's final states are still resident in the handle's device buffer: reduce them there
+                partial[ci].assign(n, 0.0);
+                cudaSetDevice(h->device);
+                if (h->stat_out.ensure(sizeof(double) * n) != cudaSuccess) { status[d] = B200ODE_ECUDA; message[d] = "out of memory"; return; }
+                st = b200ode_reduce_sum_device(h, prog->dtype, h->out_uf.ptr, B200ODE_LAYOUT_AOS, cn, n, (double*)h->stat_out.ptr, h->stream);
+                if (st == 0 && cudaMemcpyAsync(partial[ci].data(), h->stat_out.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) st = B200ODE_ECUDA;
+                if (st == 0 && cudaStreamSynchronize(h->stream) != cudaSuccess) st = B200ODE_ECUDA;
+                if (st) { status[d] = st; message[d] = g_last_error; return; }
+            }
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int d = 1; d < ndev; ++d) threads.emplace_back(worker, d);
+    worker(0);
+    for (auto& t : threads) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (status[d]) return fail(status[d], "device " + std::to_string(m->dev[d]->device) + ": " + message[d]);
+    if (res) {
+        res->kernel_ms = *std::max_element(kms.begin(), kms.end());
+        res->total_ms = *std::max_element(tms.begin(), tms.end());
+    }
+    if (mean) {
+        for (int c = 0; c < n; ++c) {
+            double acc = 0.0;
+            for (size_t ci = 0; ci < plan.size(); ++ci) acc += partial[ci][c];      // chunk order: deterministic
+            mean[c] = N > 0 ? acc / (double)N : 0.0;
+        }
+    }
+    return B200ODE_OK;
+}
+
+int b200ode_multi_solve(b200ode_multi m, b200ode_multi_program mp, const B200Problem* hp, const B200Opts* o, B200Result* res) {
+    if (mp && !mp->prog.empty() && mp->prog[0]->everystep)
+        return fail(B200ODE_EUNSUPPORTED, "save_everystep programs are single-device (ragged output)");
+    return multi_run(m, mp, hp, o, res, nullptr);
+}
+
+int b200ode_multi_reduce_mean(b200ode_multi m, b200ode_multi_program mp, const B200Problem* hp, const B200Opts* o,
+                              double* mean, B200Result* res) {
+    if (!mean) return fail(B200ODE_EINVAL, "mean is NULL");
+    if (mp && !mp->prog.empty() && mp->prog[0]->everystep)
+        return fail(B200ODE_EUNSUPPORTED, "save_everystep programs are single-device (ragged output)");
+    if (o && o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "b200ode_multi_reduce_mean reduces final states: no saveat grid");
+    return multi_run(m, mp, hp, o, res, mean);
 }
 
 }  // extern "C"

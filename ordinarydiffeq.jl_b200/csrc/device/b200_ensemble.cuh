@@ -47,12 +47,14 @@
 #define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || B200_ALG == B200_ALG_RODAS5PE || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
 #define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32 || B200_IS_RODAS)
 
-#ifndef B200_SLICED
-#define B200_SLICED 0
+#ifndef B200_COOP
+#define B200_COOP 0           // 1: lane-group kernel (b200_coop.cuh): B200_L lanes per trajectory, component-form RHS
 #endif
 
-#if B200_SLICED
-// defined below, after B200Params (b200_sliced.cuh)
+#if B200_COOP
+// defined below, after B200Params (b200_coop.cuh)
+// the one-thread-per-trajectory initial-dt kernel evaluates the component form in a loop
+#define B200_USER_RHS(du, u, p, t) do { for (int b200_i = 0; b200_i < B200_N; ++b200_i) (du)[b200_i] = B200_USER_RHS_COMP(b200_i, (u), (p), (t)); } while (0)
 #elif B200_ALG == B200_ALG_TSIT5
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_tsit5.cuh"
@@ -164,22 +166,22 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #ifndef B200_ADAPTIVE
 #define B200_ADAPTIVE 1       // 0: adaptive = false — fixed dt = opts.dt (dtcache), every step accepted, no controller
 #endif
-#if !B200_ADAPTIVE && B200_SLICED
-#error "adaptive=false is not available in the component-sliced kernel"
+#if !B200_ADAPTIVE && B200_COOP
+#error "adaptive=false is not available in the lane-group kernel"
 #endif
 
 #ifndef B200_TSTOPS
 #define B200_TSTOPS 0         // 1: the tstops keyword (several stop times); 0: tstops = {tf}
 #endif
-#if B200_TSTOPS && B200_SLICED
-#error "tstops are not available in the component-sliced kernel"
+#if B200_TSTOPS && B200_COOP
+#error "tstops are not available in the lane-group kernel"
 #endif
 
 #ifndef B200_EVERYSTEP
 #define B200_EVERYSTEP 0      // 1: save_everystep = true (integrator_utils.jl:385-411), ragged rows
 #endif
-#if (B200_EVERYSTEP || defined(B200_SAVE_IDXS)) && B200_SLICED
-#error "save_everystep / save_idxs are not available in the component-sliced kernel"
+#if (B200_EVERYSTEP || defined(B200_SAVE_IDXS)) && B200_COOP
+#error "save_everystep / save_idxs are not available in the lane-group kernel"
 #endif
 
 #ifndef B200_BLOCK
@@ -189,9 +191,12 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #define B200_MINBLOCKS 1
 #endif
 
-#if B200_SLICED
-#include "b200_sliced.cuh"
-typedef B200SlicedStepper B200Stepper;
+#if B200_COOP
+#if B200_ALG != B200_ALG_VERN7
+#error "the lane-group kernel is available for Vern7"
+#endif
+struct B200CoopStepperTag { static B200_D int order() { return 7; } static B200_D real qsteady_min() { return (real)1; } static B200_D real qsteady_max() { return (real)1; } };
+typedef B200CoopStepperTag B200Stepper;       // order / qsteady for the controller helpers (the stepper itself follows)
 #endif
 
 // ---------------------------------------------------------------------------
@@ -273,7 +278,61 @@ extern "C" __global__ void __launch_bounds__(256) b200_initdt(B200Params P) {
     P.dt0[i] = b200_initdt_one(u0, p, P.t0, dtmax, P.abstol, P.reltol, P.dtmin, B200Stepper::order());
 }
 
-#if !B200_SLICED
+#if B200_ADAPTIVE
+// ---- stepsize_controller! / step_accept_controller! / step_reject_controller! of the PI controller -------------
+// (lib/OrdinaryDiffEqCore/src/integrators/controllers.jl:805-843), all scalar work of one loopfooter! in one
+// straight-line block:
+//   q11 = fastpower(EEst, beta1); q = q11 / fastpower(errold, beta2) / gamma, clamped to [1/qmax, 1/qmin]
+//   accept:  (qsteady) q = 1;  errold = max(EEst, 1e-4);  dtnew = dt / q
+//   reject:  dt = dt / min(1/qmin, q11/gamma)            (the reference does this in the next loopheader!)
+// Accepted and rejected steps need ONE true division (numerator/denominator selected first), and the two
+// fastpower calls share fastlog2(Float32(EEst)) whenever errold == EEst.  FAST = flagged branch-free math
+// (b200_base.cuh); the caller repeats the block with FAST = false if the flag comes back set.
+struct B200Ctl { real q11, fpe, rfpe, dtdiv, num; bool accept; };
+template <bool FAST>
+B200_D B200Ctl b200_controller_t(real EEst, real q11_old, real fpe, real rfpe, real dt, real dtpropose, bool tstop_flag,
+                                 bool first, bool& bad) {
+    const real qmin = (real)0.2, qmax = (real)10, gamma = (real)0.9;
+    const real beta1 = B200_BETA1, beta2 = B200_BETA2;
+    B200Ctl c;
+    const real qmax_eff = first ? (real)10000 : qmax;
+    // fastpower(EEst, beta1) and fastpower(max(EEst, 1e-4), beta2) from one logarithm
+#if B200_F32
+    const float ef = EEst;
+#else
+    const float ef = (float)EEst;
+#endif
+    const float lg = b200_fastlog2(ef);
+    const bool small = ((real)1e-4 > EEst);            // errold = max_c(1e-4, EEst) picks the constant
+    const float lg_old = small ? b200_fastlog2((float)(real)1e-4) : lg;
+    real q11 = (real)b200_exp2_fast((float)beta1 * lg);
+    q11 = (EEst == (real)0) ? (real)0 : q11;           // fastpower(0, y) = 0
+    c.fpe = (real)b200_exp2_fast((float)beta2 * lg_old);
+    c.rfpe = B200Math<FAST>::div((real)1, c.fpe, bad);
+    real q = B200Math<FAST>::divc(q11, fpe, rfpe, bad);
+    q = B200Math<FAST>::divc(q, gamma, (real)1 / gamma, bad);
+    const real lo = (real)1 / qmax_eff, hi = (real)1 / qmin;
+    q = q < lo ? lo : (q > hi ? hi : q);               // clamp under @fastmath
+    const bool zero = (EEst == (real)0);               // iszero(EEst): q = inv(qmax), q11 untouched
+    q = zero ? lo : q;
+    c.q11 = zero ? q11_old : q11;
+    c.accept = (EEst <= (real)1);
+    // step_accept_controller!: qsteady window
+    const real qa = (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) ? (real)1 : q;
+    // step_reject_controller!: dt /= min(inv(qmin), q11/gamma)
+    const real qr = b200_min_c((real)1 / qmin, B200Math<FAST>::divc(c.q11, gamma, (real)1 / gamma, bad));
+    // accepted steps divide the un-clipped dt (integrator_utils.jl:629-633 restores it first)
+    c.num = (c.accept && tstop_flag) ? dtpropose : dt;
+    c.dtdiv = B200Math<FAST>::div(c.num, c.accept ? qa : qr, bad);
+    return c;
+}
+#endif
+
+#if B200_COOP
+#include "b200_coop.cuh"
+#endif
+
+#if !B200_COOP
 // ---------------------------------------------------------------------------
 struct B200Traj {
     real u[B200_N], uprev[B200_N];
@@ -430,10 +489,9 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
             T.dt = T.dtpropose;
             T.st.accept();
             b200_modify_dt_for_tstops(P, T, dist, tol100);
-        } else {
-            // step_reject_controller!: dt /= min(inv(qmin), q11/gamma)
-            T.dt = T.dt / b200_min_c((real)1 / qmin, b200_div_const(T.q11, gamma, (real)1 / gamma));
         }
+        // (rejected step: step_reject_controller!'s dt /= min(inv(qmin), q11/gamma) was applied by the loopfooter
+        //  that rejected it — one shared division, see b200_controller_t)
     }
     // fix_dt_at_bounds!
     T.dt = b200_min_c(P.dtmax, T.dt);
@@ -479,22 +537,19 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     T.accept = true;
     real q = (real)1;
 #else
-    // stepsize_controller!(integrator, ::PIControllerCache, alg)
-    const real qmax_eff = (T.naccept == 0) ? (real)10000 : qmax;
-    real q;
+    // stepsize_controller! + step_accept/reject_controller! (one straight-line block, see b200_controller_t)
+    real q = (real)1;
+    B200Ctl ctl;
     {
-        const real q11 = b200_fastpower(T.EEst, beta1);
-        // q = q11 / fastpower(errold, beta2): the divisor was computed when errold was set, together
-        // with RN(1/divisor), so the quotient is the 3-operation exact form (b200_div_const)
-        q = b200_div_const(q11, T.fpe, T.rfpe);
-        q = b200_div_const(q, gamma, (real)1 / gamma);
-        const real lo = (real)1 / qmax_eff, hi = (real)1 / qmin;
-        q = q < lo ? lo : (q > hi ? hi : q);       // clamp under @fastmath
-        const bool zero = (T.EEst == (real)0);     // iszero(EEst): q = inv(qmax), q11 untouched
-        q = zero ? lo : q;
-        T.q11 = zero ? T.q11 : q11;
+        bool bad = false;
+        ctl = b200_controller_t<true>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, bad);
+        if (bad) {      // cold, inline
+            bool unused = false;
+            ctl = b200_controller_t<false>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, unused);
+        }
     }
-    T.accept = (T.EEst <= (real)1);
+    T.q11 = ctl.q11;
+    T.accept = ctl.accept;
 #endif
     if (T.accept) {
         T.naccept += 1;
@@ -503,7 +558,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         const real dt_stages = T.dt;                // what perform_step! ran with (the dense pass recomputes the stages from it)
 #endif
 #if B200_ADAPTIVE
-        if (T.tstop_flag) T.dt = T.dtpropose;       // restore un-clipped dt (integrator_utils.jl:629-633)
+        T.dt = ctl.num;                             // tstop_flag: the un-clipped dt is restored (integrator_utils.jl:629-633)
 #endif
         T.t = T.tstop_flag ? tstop : ttmp;          // fixed_t_for_tstop_error! (tstop_target)
         T.tstop_flag = false;
@@ -511,14 +566,10 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         T.dtpropose = T.dt;
         (void)q; (void)beta1; (void)beta2; (void)qmin; (void)qmax; (void)gamma;
 #else
-        // step_accept_controller!
-        if (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) q = (real)1;
-        {   // errold = max(EEst, qoldinit); its fastpower is all later steps need
-            const real errold = b200_max_c((real)1e-4, T.EEst);
-            T.fpe = b200_fastpower(errold, beta2);
-            T.rfpe = (real)1 / T.fpe;
-        }
-        const real dtnew = T.dt / q;
+        // step_accept_controller!: errold = max(EEst, qoldinit) — only fastpower(errold, beta2) and its reciprocal are kept
+        T.fpe = ctl.fpe;
+        T.rfpe = ctl.rfpe;
+        const real dtnew = ctl.dtdiv;
         // calc_dt_propose!: eps at the NEW t
         const real eps_n = b200_eps_finite(T.t);
         T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
@@ -535,7 +586,12 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                         T.st.dense_prepare(T.uprev, T.u, T.p, T.tprev, T.dt);
                         dense_ready = true;
                     }
-                    const real th = (curt - T.tprev) / T.dt;
+                    real th;
+                    {   // Θ = (curt - tprev) / dt: flagged fast division, plain operator in the (cold) flagged case
+                        bool bad = false;
+                        th = b200_div_fast(curt - T.tprev, T.dt, bad);
+                        if (bad) th = (curt - T.tprev) / T.dt;
+                    }
                     real out[B200_N];
                     T.st.interp(th, T.dt, T.uprev, T.u, out);
                     b200_emit(P, idx, T, curt, out);
@@ -560,6 +616,9 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #endif
     } else {
         T.nreject += 1;
+#if B200_ADAPTIVE
+        T.dt = ctl.dtdiv;                           // step_reject_controller!
+#endif
     }
     // while tdir*t < first_tstop
     return !(T.t < P.tf);
@@ -776,4 +835,4 @@ extern "C" __global__ void __launch_bounds__(128) b200_dense_eval(B200DenseParam
     }
 }
 #endif  // B200_EVERYSTEP
-#endif  // !B200_SLICED
+#endif  // !B200_COOP

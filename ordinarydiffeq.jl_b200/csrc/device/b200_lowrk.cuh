@@ -96,17 +96,13 @@ struct B200DP5 {
         }
         B200_RHS(k7, u, p, t + dt);
         nf += 6;
-        real acc = (real)0;
+        real ut[B200_N];
 #pragma unroll
-        for (int i = 0; i < B200_N; ++i) {
-            real ut = dt * b200_fma(bt7, k7[i],
+        for (int i = 0; i < B200_N; ++i)
+            ut[i] = dt * b200_fma(bt7, k7[i],
                                     b200_fma(bt6, k6[i],
                                              b200_fma(bt5, k5[i], b200_fma(bt4, k4[i], b200_fma(bt3, k3[i], bt1 * k1[i])))));
-            real r = ut / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
-            real r2 = r * r;
-            acc = (i == 0) ? r2 : (acc + r2);
-        }
-        return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
+        return b200_residual_norm(ut, uprev, u, reltol, abstol);
     }
 
     B200_D void accept() {
@@ -176,15 +172,11 @@ struct B200BS3 {
             u[i] = b200_fma(dt, b200_fma(a43, k3[i], b200_fma(a42, k2[i], a41 * k1[i])), uprev[i]);
         B200_RHS(k4, u, p, t + dt);
         nf += 3;
-        real acc = (real)0;
+        real ut[B200_N];
 #pragma unroll
-        for (int i = 0; i < B200_N; ++i) {
-            real ut = dt * b200_fma(bt4, k4[i], b200_fma(bt3, k3[i], b200_fma(bt2, k2[i], bt1 * k1[i])));
-            real r = ut / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
-            real r2 = r * r;
-            acc = (i == 0) ? r2 : (acc + r2);
-        }
-        return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
+        for (int i = 0; i < B200_N; ++i)
+            ut[i] = dt * b200_fma(bt4, k4[i], b200_fma(bt3, k3[i], b200_fma(bt2, k2[i], bt1 * k1[i])));
+        return b200_residual_norm(ut, uprev, u, reltol, abstol);
     }
 
     B200_D void accept() {

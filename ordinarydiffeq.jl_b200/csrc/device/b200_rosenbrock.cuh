@@ -151,14 +151,7 @@ B200_D void b200_build_W(const real* uprev, const real* p, real t, real dtgamma,
 }
 
 B200_D real b200_err_norm(const real* ut, const real* uprev, const real* u, real reltol, real abstol) {
-    real acc = (real)0;
-#pragma unroll
-    for (int i = 0; i < B200_N; ++i) {
-        real r = ut[i] / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
-        real r2 = r * r;
-        acc = (i == 0) ? r2 : (acc + r2);
-    }
-    return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
+    return b200_residual_norm(ut, uprev, u, reltol, abstol);
 }
 
 // ---------------------------------------------------------------------------

@@ -23,7 +23,10 @@ B200_D real b200_norm_local(const real* res) {
     real acc = res[0] * res[0];
 #pragma unroll
     for (int i = 1; i < B200_VLEN; ++i) acc = acc + res[i] * res[i];
-    return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));
+    bool bad = false;
+    real e = b200_sqrt_fast(b200_div_const_fast(acc, (real)B200_N, (real)1 / (real)B200_N, bad), bad);
+    if (bad) e = b200_sqrt(acc / (real)B200_N);
+    return e;
 }
 #endif
 
@@ -111,12 +114,19 @@ struct B200Vern7 {
         B200_RHS(k10, tmp, p, t + dt);
         nf += 10;
         B200_V7_STAGE(u, B200_V7_7(b1, k1, b4, k4, b5, k5, b6, k6, b7, k7, b8, k8, b9, k9))
-        real res[B200_VLEN];
+        // calculate_residuals: flagged fast divisions (they interleave), plain operator in the flagged case
+        real res[B200_VLEN], ut[B200_VLEN], den[B200_VLEN];
+        bool bad = false;
         B200_UNROLL_STAGE
         for (int i = 0; i < B200_VLEN; ++i) {
-            real ut = dt * B200_V7_8(btilde1, k1, btilde4, k4, btilde5, k5, btilde6, k6, btilde7, k7, btilde8, k8,
-                                     btilde9, k9, btilde10, k10);
-            res[i] = ut / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
+            ut[i] = dt * B200_V7_8(btilde1, k1, btilde4, k4, btilde5, k5, btilde6, k6, btilde7, k7, btilde8, k8,
+                                   btilde9, k9, btilde10, k10);
+            den[i] = b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
+            res[i] = b200_div_fast(ut[i], den[i], bad);
+        }
+        if (bad) {
+            B200_UNROLL_STAGE
+            for (int i = 0; i < B200_VLEN; ++i) res[i] = ut[i] / den[i];
         }
         return B200_NORM(res, u);
     }

@@ -17,8 +17,8 @@ def _np_real(dtype):
 
 
 def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None,
-               maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None, _meanvar=None, tstops=None):
-    """Host arrays in, host arrays out (b200ode_solve).
+               maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None, _meanvar=None, tstops=None, _mean=None):
+    """Host arrays in, host arrays out (b200ode_solve; b200ode_multi_solve for a MultiProgram).
 
     u0: (N, n) or (n,) shared; p: (N, np) or (np,) shared or None.
     saveat: explicit ascending grid in (t0, tf] or None.
@@ -81,6 +81,12 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
         var = buf("var", (nslots, program.nsave), np.float64) if _meanvar[1] else None
         _lib.check(L.b200ode_solve_meanvar(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res),
                                            C.c_void_p(mean.ctypes.data), C.c_void_p(var.ctypes.data) if var is not None else None))
+    elif _mean is not None:
+        mean = buf("mean", (n,), np.float64)
+        _lib.check(L.b200ode_multi_reduce_mean(program.handle._h, program._p, C.byref(prob), C.byref(opts),
+                                               mean.ctypes.data_as(C.POINTER(C.c_double)), C.byref(res)))
+    elif getattr(program, "multi", False):
+        _lib.check(L.b200ode_multi_solve(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res)))
     else:
         _lib.check(L.b200ode_solve(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res)))
     out["kernel_ms"] = res.kernel_ms
@@ -182,6 +188,14 @@ def solve_host_meanvar(program, u0, p, tspan, saveat, trajectories=None, want_va
     (b200ode_solve_meanvar): returns dict with ts, mean[nslots][n], var[nslots][n] and the
     per-trajectory scalars (u_final, retcode, counters)."""
     return solve_host(program, u0, p, tspan, trajectories=trajectories, saveat=saveat, _meanvar=(True, want_var), **kw)
+
+
+def solve_host_mean(program, u0, p, tspan, trajectories=None, **kw):
+    """Ensemble mean of u(tf) over all trajectories, sharded over the devices of a MultiProgram
+    (b200ode_multi_reduce_mean); the per-trajectory results are returned as well."""
+    if not getattr(program, "multi", False):
+        raise ValueError("solve_host_mean needs a MultiProgram (MultiHandle.compile)")
+    return solve_host(program, u0, p, tspan, trajectories=trajectories, _mean=True, **kw)
 
 
 def nslots_for(tspan, saveat, save_start=None, save_end=None):

@@ -99,6 +99,36 @@ def pleiades_source(f32=False, name="pleiades_rhs", loops=False):
     return "\n".join(L) + "\n", name
 
 
+def pleiades_component_source(f32=False, name="pleiades_rhs_i"):
+    """Pleiades in COMPONENT FORM for the lane-group kernel (B200ODE_OPT_COMPONENT_RHS): du_i as a function of the
+    run-time index i.  Components 0..13 copy the velocities; components 14..27 are the accelerations of body
+    b = (i - 14) % 7 along x (i < 21) or y, accumulated over j = 0..6, j != b, in the reference's loop order with
+    the reference's operations (dx, dy, r = sqrt(dx dx + dy dy), r3 = r r r, m dq / r3), so every du_i has the same
+    bits as pleiades_source's.  The j == b term is computed on dummy operands and dropped by a select instead of a
+    `continue`, which keeps the seven terms in one basic block (they then overlap on the FP64 pipe)."""
+    T = _ty(f32)
+    sq = "sqrtf" if f32 else "sqrt"
+    suf = "f" if f32 else ""
+    return ("#ifndef B200_DIV\n#define B200_DIV(a, b) ((a) / (b))\n#endif\n"
+            "%(T)s %(name)s(int i, const %(T)s* u, const %(T)s* p, const %(T)s t) {\n"
+            "  if (i < 14) return u[14 + i];\n"
+            "  const int yaxis = (i >= 21);\n"
+            "  const int b = i - (yaxis ? 21 : 14);\n"
+            "  %(T)s acc = 0.0%(s)s;\n"
+            "  for (int j = 0; j < 7; ++j) {\n"
+            "    const int self = (j == b);\n"
+            "    const %(T)s dx = u[j] - u[b], dy = u[7 + j] - u[7 + b];\n"
+            "    const %(T)s r2 = self ? 1.0%(s)s : dx * dx + dy * dy;\n"
+            "    const %(T)s r = %(sq)s(r2); const %(T)s r3 = r * r * r;\n"
+            "    const %(T)s m = (%(T)s)(j + 1);\n"
+            "    const %(T)s num = self ? 1.0%(s)s : m * (yaxis ? dy : dx);\n"
+            "    const %(T)s term = B200_DIV(num, r3);\n"
+            "    acc = self ? acc : acc + term;\n"
+            "  }\n"
+            "  return acc;\n"
+            "}\n" % dict(T=T, name=name, s=suf, sq=sq)), name
+
+
 PLEIADES_U0 = np.array([3.0, 3.0, -1.0, -3.0, 2.0, -2.0, 2.0, 3.0, -3.0, 2.0, 0, 0, -4.0, 4.0,
                         0, 0, 0, 0, 0, 1.75, -1.5, 0, 0, 0, -1.25, 1, 0, 0], dtype=np.float64)
 

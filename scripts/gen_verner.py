@@ -247,14 +247,9 @@ def emit(M, flavor):
         L.append("        " + rhs("k[%d]" % (S - 1), "u", "t + dt"))
     L.append("        %s += %d;" % ("nf" if dev else "st.nf", st["nf"]))
     if dev:
-        L.append("        real acc = (real)0;")
-        L.append("        " + loop + "{")
-        L.append("            const real ut = dt * (%s);" % chain(st["err"]))
-        L.append("            const real r = ut / b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);")
-        L.append("            const real r2 = r * r;")
-        L.append("            acc = (i == 0) ? r2 : (acc + r2);")
-        L.append("        }")
-        L.append("        return b200_sqrt(b200_div_const(acc, (real)B200_N, (real)1 / (real)B200_N));")
+        L.append("        real ut[B200_N];")
+        L.append("        " + loop + "ut[i] = dt * (%s);" % chain(st["err"]))
+        L.append("        return b200_residual_norm(ut, uprev, u, reltol, abstol);")
         L.append("    }")
         if st["fsal_first"]:
             L.append("    B200_D void accept() {\n#pragma unroll\n        for (int i = 0; i < B200_N; ++i) k[0][i] = k[%d][i];\n    }" % (S - 1))

@@ -82,3 +82,42 @@ def test_two_rank_nccl_sweep_equals_single_gpu(pkg, handle, N):
     assert np.array_equal(full.view(np.uint64), one["u_final"].view(np.uint64))
     assert np.array_equal(steps, one["naccept"] + one["nreject"])
     assert np.allclose(mean, one["u_final"].mean(axis=0), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_multi_device_c_abi_equals_single_device(pkg, handle, ndev):
+    """b200ode_multi_solve / b200ode_multi_reduce_mean (several GPUs from one process): results in global trajectory
+    order equal the single-device solve bit for bit — with saveat rows and final-state only — and the mean equals the
+    mean of those final states to 1e-12 (chunk-wise summation tree)."""
+    import torch
+    if torch.cuda.device_count() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    pl, ll = pkg.problems_library, pkg.lowlevel
+    rhs = pl.lorenz_source(False)
+    N = 40000 + 37                      # several chunks per device, ragged tail
+    p = pl.lorenz_params(N, sweep_total=N)
+    u0 = np.array([1.0, 0.0, 0.0])
+    prog1 = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1])
+    mh = pkg.MultiHandle(list(range(ndev)))
+    assert mh.ndev == ndev
+    progm = mh.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1])
+    try:
+        grid = [1.0, 2.5, 4.0]
+        for kw in ({}, {"saveat": grid}, {"saveat": grid, "save_start": False, "save_end": False}):
+            a = ll.solve_host(prog1, u0, p, (0.0, 4.0), **kw)
+            b = ll.solve_host(progm, u0, p, (0.0, 4.0), **kw)
+            for k in ("naccept", "nreject", "nf", "retcode", "nsaved"):
+                assert np.array_equal(a[k], b[k]), k
+            assert np.array_equal(a["u_final"].view(np.uint64), b["u_final"].view(np.uint64))
+            assert np.array_equal(a["t_final"], b["t_final"])
+            if "saveat" in kw:
+                assert np.array_equal(a["us"].view(np.uint64), b["us"].view(np.uint64))
+                assert np.array_equal(a["ts"], b["ts"])
+        a = ll.solve_host(prog1, u0, p, (0.0, 4.0))
+        m = ll.solve_host_mean(progm, u0, p, (0.0, 4.0))
+        assert np.array_equal(a["u_final"].view(np.uint64), m["u_final"].view(np.uint64))
+        assert np.allclose(m["mean"], a["u_final"].mean(axis=0), rtol=1e-12, atol=0)
+    finally:
+        progm.close()
+        mh.close()
+        prog1.close()

@@ -358,28 +358,6 @@ def test_timeseries_meanvar_on_device(pkg, progs, oracle):
         assert np.array_equal(m1.cpu().numpy(), st["mean"])
 
 
-def test_sliced_kernel_variant_is_bit_exact(pkg, handle, oracle):
-    """The opt-in component-sliced Vern7 kernel (G warps per 32 trajectories, stage vectors exchanged
-    through shared memory) reproduces the oracle bit for bit, with and without lazy interpolation."""
-    pl = pkg.problems_library
-    N = 300
-    src, name = pl.pleiades_source(False)
-    prog = handle.compile(pkg.ALG_VERN7, pkg.F64, 28, 0, src, name, extra_options="-DB200_SLICED=1")
-    assert prog.info["block"] == 7 * 32
-    u0 = pl.pleiades_u0(N)
-    for extra in ({}, {"saveat": [0.4, 1.1, 1.15, 2.9]}):
-        kw = dict(reltol=1e-6, abstol=1e-8, **extra)
-        g = pkg.lowlevel.solve_host(prog, u0, None, (0.0, 3.0), **kw)
-        o = oracle.solve(oracle.ALG_VERN7, (src, name), u0, None, (0.0, 3.0), 28, 0, **kw)
-        assert_same_result(g, o)
-    s3, n3 = pl.lorenz_source(False)
-    prog3 = handle.compile(pkg.ALG_VERN7, pkg.F64, 3, 3, s3, n3, extra_options="-DB200_SLICED=1 -DB200_G=2")
-    p = pl.lorenz_params(100)
-    g = pkg.lowlevel.solve_host(prog3, U0, p, (0.0, 5.0), saveat=[1.0, 2.5], maxiters=60)
-    o = oracle.solve(oracle.ALG_VERN7, (s3, n3), U0, p, (0.0, 5.0), 3, 3, saveat=[1.0, 2.5], maxiters=60)
-    assert_same_result(g, o)
-
-
 # ---- save_everystep = true: ragged per-step rows (SURVEY §8(f) row 2) ---------------------------
 def _everystep_prog(pkg, handle, alg, f32, problem):
     pl = pkg.problems_library
@@ -911,3 +889,70 @@ def test_singular_w_is_rejected_like_the_reference(pkg, handle, oracle):
             assert (g["u_final"][:, 1] == 2.0).all()
         finally:
             prog.close()
+
+
+def test_fast_math_matches_ieee(handle):
+    """The branch-free division / square-root sequences of the kernels (b200_base.cuh) give the bits of the plain IEEE
+    operators on 2^27 operand sets (arbitrary bit patterns, ODE-scale exponents, near-all-ones mantissas) wherever
+    they do not raise their flag; the flag is rare on ODE-scale operands."""
+    bad, flagged = handle.selftest_fastmath(1 << 27, seed=20261017)
+    assert bad == [0] * 6, bad   # [div64, div_const64, sqrt64, div32, sqrt32, unguarded div32]
+    assert flagged > 0          # the arbitrary-bit-pattern class must exercise the flag
+    bad2, _ = handle.selftest_fastmath(1 << 22, seed=7)
+    assert bad2 == [0] * 6, bad2
+
+
+# ---- lane-group kernel (device/b200_coop.cuh): 16 lanes per trajectory, component-form RHS ---------------------------
+def test_lane_group_kernel_pleiades_vern7(pkg, handle, oracle):
+    """BASELINE config 4 through the lane-group kernel: bit-exact against the oracle run on the ordinary (full-vector)
+    Pleiades source — final states, step counts, nf and the lazily interpolated saveat rows."""
+    pl = pkg.problems_library
+    N = 777                      # not a multiple of the trajectories per warp / CTA
+    u0 = pl.pleiades_u0(N)
+    src, name = pl.pleiades_component_source()
+    prog = handle.compile(pkg.ALG_VERN7, pkg.F64, 28, 0, src, name, extra_options=pkg._lib.OPT_COMPONENT_RHS)
+    try:
+        assert prog.info["local_bytes_integrate"] == 0 or prog.info["local_bytes_integrate"] < 512
+        kw = dict(reltol=1e-6, abstol=1e-8)
+        for extra in ({}, {"saveat": [0.5, 1.0, 1.5, 2.0, 2.5, 3.0]}, {"saveat": [0.01, 2.999], "save_start": False}):
+            g = pkg.lowlevel.solve_host(prog, u0, None, (0.0, 3.0), **dict(kw, **extra))
+            o = oracle.solve(oracle.ALG_VERN7, pl.pleiades_source(), u0, None, (0.0, 3.0), 28, 0, **dict(kw, **extra))
+            assert_same_result(g, o)
+            assert (g["nf"] == 2 + 10 * (g["naccept"] + g["nreject"])).all()
+        # failure retcodes reach the host and do not stall the other group of the warp
+        g = pkg.lowlevel.solve_host(prog, u0[:33], None, (0.0, 3.0), maxiters=7, **kw)
+        o = oracle.solve(oracle.ALG_VERN7, pl.pleiades_source(), u0[:33], None, (0.0, 3.0), 28, 0, maxiters=7, **kw)
+        assert_same_result(g, o)
+        assert (g["retcode"] == pkg._lib.RC_MAXITERS).all()
+    finally:
+        prog.close()
+
+
+def test_lane_group_kernel_other_shapes(pkg, handle, oracle):
+    """The same kernel at other group shapes: Lorenz (n = 3) as 2 and 4 lanes per trajectory, FP32 Pleiades."""
+    pl = pkg.problems_library
+    lor = ("double lorenz_i(int i, const double* u, const double* p, const double t) {\n"
+           "  if (i == 0) return p[0] * (u[1] - u[0]);\n"
+           "  if (i == 1) return u[0] * (p[1] - u[2]) - u[1];\n"
+           "  return u[0] * u[1] - p[2] * u[2];\n}\n", "lorenz_i")
+    N = 500
+    p = pl.lorenz_params(N)
+    grid = [k / 2 for k in range(1, 21)]
+    o = oracle.solve(oracle.ALG_VERN7, pl.lorenz_source(), U0, p, (0.0, 10.0), 3, 3, saveat=grid)
+    for L in (2, 4):
+        prog = handle.compile(pkg.ALG_VERN7, pkg.F64, 3, 3, lor[0], lor[1], extra_options="-DB200_COOP=1 -DB200_L=%d" % L)
+        try:
+            g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 10.0), saveat=grid)
+            assert_same_result(g, o)
+        finally:
+            prog.close()
+    u0 = pl.pleiades_u0(256, f32=True)
+    src, name = pl.pleiades_component_source(f32=True)
+    prog = handle.compile(pkg.ALG_VERN7, pkg.F32, 28, 0, src, name, extra_options=pkg._lib.OPT_COMPONENT_RHS)
+    try:
+        kw = dict(reltol=1e-4, abstol=1e-5)
+        g = pkg.lowlevel.solve_host(prog, u0, None, (0.0, 3.0), **kw)
+        o32 = oracle.solve(oracle.ALG_VERN7, pl.pleiades_source(True), u0, None, (0.0, 3.0), 28, 0, f32=True, **kw)
+        assert_same_result(g, o32)
+    finally:
+        prog.close()
