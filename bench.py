@@ -6,17 +6,24 @@
 One "step" = one pass of the hot path over one batch: solve a 2^20-trajectory Lorenz/Tsit5 FP64
 ensemble with saveat = 0.1 (BASELINE.json configs[1], the configuration `metric` is quoted on).
 Prints ONE JSON line (rank 0):
-  value      trajectories/s, whole job, inputs resident in HBM, CUDA-event time, max over ranks
-  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H timed
+  value      trajectories/s, whole job (weak scaling: every rank its own 2^20 trajectories), inputs resident in HBM,
+             CUDA-event time, max over ranks
+  e2e        same metric through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H timed; with the
+             cudaMemcpy-only D2H time of the same bytes beside it (the PCIe ceiling) and labelled variants
+             (FP32, save_idxs, mean/var on the device)
   roofline   FP64-FMA roofline of b200_integrate (algorithmic flops / CUDA-event time vs the FMA
              peak measured live on this GPU) + the HBM side of the saveat stream
   cpu_baseline  the CPU oracle (port of the reference algorithm) on this box's host cores, bounded sample
+  configs    the other BASELINE.json configurations (FP32, final-state only, Robertson Rodas5P / Rosenbrock23,
+             Pleiades Vern7), each with value, roofline and cpu_baseline (short runs; N = 1 only)
+  strong_1m  ONE 2^20-trajectory saveat ensemble sharded over the N ranks (interleaved blocks), per-rank kernel ms
+  sweep_64m  BASELINE configs[4]: the 64 Mi-trajectory rho sweep sharded over the N ranks with the ordered gather of
+             the final states and the ensemble mean inside the timed step, NCCL time separated
 `--impl reference` times the CPU oracle alone (the reference is Julia and cannot run here).
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -26,9 +33,23 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-F_STEP_TSIT5_LORENZ = 247.0     # algorithmic FP64 flops per attempted step
-F_INTERP = 85.0                 # per interpolated saveat row
-F_INIT = 60.0                   # initdt: 2 RHS + 3 norms
+# Algorithmic FP64/FP32 flops per unit of work (FMA = 2; add/mul/div/sqrt = 1; abs/max/compare/select = 0; the
+# scalar controller is excluded) — SURVEY §8(d), derivations in DESIGN.md §4:
+#   Tsit5/Lorenz      3*61 stage/solution/error combinations + 6*8 RHS + 9 residuals + 7 norm          = 247 / attempt
+#   Tsit5 interpolant Theta 2 + Theta^2 1 + b1 7 + b2..b7 30 + 3*15                                     = 85 / row
+#   Rosenbrock23/ROBER (n = 3: RHS 13, J 10, W 4, 3x3 inverse 38, mat-vec solve 15, norm 16)
+#       4 + 52 + stage1 24 + stage2 44 + u,RHS 20 + stage3 42 + error 28                                = 214 / attempt
+#   Rodas5P/ROBER     1 + 52 + 1 + 13 + 7 + 15 + sum_{s=1..7}(13 s + 40) + 48 + 6 + 16                   = 803 / attempt
+#   Vern7/Pleiades    28*111 + 10*588 + 84 + 57                                                          = 9129 / attempt
+F_INIT = 60.0                   # initdt: 2 RHS + 3 norms (Lorenz); negligible elsewhere
+FLOPS = {("lorenz", "tsit5"): dict(step=247.0, row=85.0), ("lorenz_sweep", "tsit5"): dict(step=247.0, row=85.0),
+         ("robertson", "ros23"): dict(step=214.0, row=0.0), ("robertson", "rodas5p"): dict(step=803.0, row=0.0),
+         ("pleiades", "vern7"): dict(step=9129.0, row=0.0)}
+FLOPS_NOTE = {("lorenz", "tsit5"): "247/attempted step + 85/interpolated row + 60/trajectory",
+              ("lorenz_sweep", "tsit5"): "247/attempted step + 60/trajectory",
+              ("robertson", "ros23"): "214/attempted step (RHS 13, J 10, W 4, 3x3 inverse 38, 3 mat-vec solves 15, norm 16)",
+              ("robertson", "rodas5p"): "803/attempted step (8 stages: sum(13 s + 40), 8 mat-vec solves)",
+              ("pleiades", "vern7"): "9129/attempted step (28*111 + 10*588 + 84 + 57)"}
 
 WORKLOADS = {
     # name: (problem, alg, f32, N per GPU, saveat h or None, tspan, tolerances)
@@ -45,29 +66,49 @@ WORKLOADS = {
     "pleiades_vern7_256k": dict(problem="pleiades", alg="vern7", f32=False, N=1 << 18, saveat=None, tspan=(0.0, 3.0),
                                 tol=dict(reltol=1e-6, abstol=1e-8)),
 }
+OTHER_CONFIGS = ["lorenz_tsit5_saveat_1m_f32", "lorenz_tsit5_final_1m", "robertson_rodas5p_1m", "robertson_rosenbrock23_1m",
+                 "pleiades_vern7_256k"]
+ALG_NAMES = {"tsit5": "ALG_TSIT5", "vern7": "ALG_VERN7", "ros23": "ALG_ROSENBROCK23", "rodas5p": "ALG_RODAS5P"}
 
 
-def sources(pl, w):
+def sources(pl, w, device=False):
+    """(rhs, jac, tgrad, n, np, extra compile options).  device=True: the form the GPU program is compiled from
+    (Pleiades: component form for the lane-group kernel); otherwise the full-vector form the CPU oracle compiles."""
     f32 = w["f32"]
     if w["problem"] in ("lorenz", "lorenz_sweep"):
-        return pl.lorenz_source(f32), None, None, 3, 3
+        return pl.lorenz_source(f32), None, None, 3, 3, None
     if w["problem"] == "robertson":
         r, j, tg = pl.robertson_sources(f32)
-        return r, j, tg, 3, 3
+        return r, j, tg, 3, 3, None
     if w["problem"] == "pleiades":
-        # loop-form source + partially rolled stage loops: same speed as the fully unrolled form,
-        # 20x shorter NVRTC compile
-        return pl.pleiades_source(f32, loops=True), None, None, 28, 0
+        if device:
+            return pl.pleiades_component_source(f32), None, None, 28, 0, "-DB200_COOP=1"
+        return pl.pleiades_source(f32, loops=True), None, None, 28, 0, None
     raise ValueError(w["problem"])
 
 
-def inputs(pl, w, N, offset):
+def inputs(pl, w, N, offset=0, idx=None, total=None):
+    """u0 (shared or per trajectory) and p for trajectories offset..offset+N-1, or for the global indices `idx`."""
     f32 = w["f32"]
-    if w["problem"] == "lorenz":
-        return np.array([1.0, 0.0, 0.0]), pl.lorenz_params(N, offset=offset, f32=f32)
+    if idx is None:
+        idx = np.arange(offset, offset + N, dtype=np.uint64)
+    idx = np.asarray(idx, dtype=np.uint64)
+    if w["problem"] in ("lorenz", "lorenz_sweep"):
+        p = np.empty((idx.shape[0], 3), dtype=np.float64)
+        p[:, 0] = 10.0
+        p[:, 2] = 8.0 / 3.0
+        if w["problem"] == "lorenz_sweep":
+            p[:, 1] = 14.0 + 28.0 * idx.astype(np.float64) / float(total)
+        else:
+            p[:, 1] = 28.0 * (0.5 + pl.splitmix64_uniform(idx, 0))
+        return np.array([1.0, 0.0, 0.0]), (p.astype(np.float32) if f32 else p)
     if w["problem"] == "robertson":
-        return np.array([1.0, 0.0, 0.0]), pl.robertson_params(N, offset=offset, f32=f32)
-    return pl.pleiades_u0(N, offset=offset, f32=f32), None
+        base = np.array([0.04, 3.0e7, 1.0e4])
+        p = np.empty((idx.shape[0], 3), dtype=np.float64)
+        for j in range(3):
+            p[:, j] = base[j] * (0.5 + pl.splitmix64_uniform(idx, j))
+        return np.array([1.0, 0.0, 0.0]), (p.astype(np.float32) if f32 else p)
+    return pl.pleiades_u0(idx.shape[0], offset=int(idx[0]), f32=f32), None
 
 
 class ClockSampler(threading.Thread):
@@ -103,6 +144,11 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.002)
 
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        return self.summary()
+
     def summary(self):
         nv = self.nv
         if not self.samples:
@@ -124,9 +170,8 @@ def cpu_oracle_rate(pl, w, seconds, nthreads=0):
     """Time the CPU oracle on a bounded sample of the workload (same inputs, same options).
     Returns (traj_per_s, sample, threads, steps_per_traj)."""
     from oracle import oracle
-    rhs, jac, tg, n, np_ = sources(pl, w)
-    alg = {"tsit5": oracle.ALG_TSIT5, "vern7": oracle.ALG_VERN7, "ros23": oracle.ALG_ROSENBROCK23,
-           "rodas5p": oracle.ALG_RODAS5P}[w["alg"]]
+    rhs, jac, tg, n, np_, _ = sources(pl, w)
+    alg = getattr(oracle, ALG_NAMES[w["alg"]])
     import b200_import
     pkg = b200_import.load()
     grid = pkg.ranges.saveat_grid(w["saveat"], w["tspan"]) if w["saveat"] is not None else None
@@ -137,9 +182,10 @@ def cpu_oracle_rate(pl, w, seconds, nthreads=0):
         except Exception:
             nthreads = os.cpu_count() or 1
     threads = nthreads
+    total = w["N"]
 
     def run(N):
-        u0, p = inputs(pl, w, N, 0)
+        u0, p = inputs(pl, w, N, 0, total=total)
         t = time.perf_counter()
         o = oracle.solve(alg, rhs, u0, p, w["tspan"], n, np_, f32=w["f32"], jac=jac, tgrad=tg, saveat=grid,
                          nthreads=nthreads, **w["tol"])
@@ -153,72 +199,309 @@ def cpu_oracle_rate(pl, w, seconds, nthreads=0):
     return sample / dt, sample, threads, float((o["naccept"] + o["nreject"]).mean())
 
 
-def sweep_main(args, w, pkg, rank, world, local_rank, metric, config):
-    """configs[4]: 64 Mi-trajectory rho sweep, interleaved shards, gather + mean over NCCL."""
-    import importlib
-    import torch
-    import torch.distributed as dist
-    d = importlib.import_module("ordinarydiffeq_jl_b200.distributed")
-    pl, ll = pkg.problems_library, pkg.lowlevel
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+def cpu_baseline_entry(pl, w, seconds):
+    v, sample, threads, spt = cpu_oracle_rate(pl, w, seconds)
+    return {"value": v, "unit": "trajectories/s", "cores": threads, "kind": "port",
+            "sample": "%d of the %d trajectories (same inputs/options), CPU oracle with OpenMP schedule(dynamic,64)" % (sample, w["N"]),
+            "steps_per_trajectory": spt}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class DeviceRun:
+    """One workload resident on one GPU: program + device buffers, timed with CUDA events on torch's current stream
+    (the stream b200ode_solve_device is launched on)."""
+
+    def __init__(self, pkg, h, w, N, dev, idx=None, offset=0, total=None, extra_options=None):
+        import torch
+        self.pkg, self.h, self.w, self.N, self.dev, self.torch = pkg, h, w, N, dev, torch
+        pl, ll = pkg.problems_library, pkg.lowlevel
+        rhs, jac, tg, self.n, self.np_, extra = sources(pl, w, device=True)
+        self.dtype = pkg.F32 if w["f32"] else pkg.F64
+        if extra_options:
+            extra = (extra + " " + extra_options) if extra else extra_options
+        self.prog = h.compile(getattr(pkg, ALG_NAMES[w["alg"]]), self.dtype, self.n, self.np_, rhs[0], rhs[1],
+                              jac[0] if jac else None, jac[1] if jac else None, tg[0] if tg else None, tg[1] if tg else None,
+                              extra_options=extra)
+        self.grid = pkg.ranges.saveat_grid(w["saveat"], w["tspan"]) if w["saveat"] is not None else None
+        self.nslots = ll.nslots_for(w["tspan"], self.grid) if self.grid else 0
+        self.u0, self.p = inputs(pl, w, N, offset=offset, idx=idx, total=total)
+        self.rs = 4 if w["f32"] else 8
+        self.bufs = ll.DeviceBuffers(self.prog, N, self.nslots, dev, u0_shared=(self.u0.ndim == 1), p_shared=(self.p is None))
+        self.bufs.u0.copy_(torch.from_numpy(np.ascontiguousarray(self.u0, dtype=np.float32 if w["f32"] else np.float64)))
+        if self.p is not None:
+            self.bufs.p.copy_(torch.from_numpy(np.ascontiguousarray(self.p)))
+        self.kw = dict(saveat=self.grid, **w["tol"])
+
+    def step(self):
+        self.pkg.lowlevel.solve_device(self.prog, self.bufs, self.w["tspan"], **self.kw)
+
+    def timed(self, steps, warmup, barrier):
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_wall = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            ev[i][0].record()
+            self.step()
+            ev[i][1].record()
+        e1.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        return e0.elapsed_time(e1), [a.elapsed_time(b) for a, b in ev], t_wall
+
+    def attempts(self):
+        b = self.bufs
+        assert bool((b.retcode == 1).all()), "bench: some trajectories did not reach tf"
+        return int((b.naccept.to(self.torch.int64).sum() + b.nreject.to(self.torch.int64).sum()).item())
+
+    def roofline(self, kern_ms, attempts, traffic=None):
+        w, N = self.w, self.N
+        key = (w["problem"], w["alg"])
+        f = FLOPS[key]
+        n_interp = N * (len(self.grid) - 1) if self.grid else 0      # the row at tf is a copy, not an interpolation
+        flops = f["step"] * attempts + f["row"] * n_interp + F_INIT * N
+        peak_tf, _ = self.h.measure_fma_peak(self.dtype)
+        achieved = flops / (kern_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        n, rs = self.n, self.rs
+        out_bytes = N * self.nslots * n * rs + N * (n * rs + rs + 4 * 8)
+        in_bytes = N * self.np_ * rs + N * rs + (0 if self.u0.ndim == 1 else N * n * rs)
+        return {"bound": "fp32_fma" if w["f32"] else "fp64_fma", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf,
+                "bound_note": "compute-bound on the scalar FP64 (FP32) FMA pipe: the path has no contraction, so neither the "
+                              "tensor-core nor the HBM roofline applies; the HBM side of the same launch is under roofline.hbm",
+                "peak_source": "measured live: b200ode_measure_fma_peak (register-resident FMA chains); "
+                               "MEASURED_PEAKS.json has no FP64/FP32 FMA figure",
+                "algorithmic_flops_per_launch": flops, "flops_model": FLOPS_NOTE[key] + " (DESIGN.md §4)",
+                "kernel_ms": kern_ms, "traffic": traffic,
+                "traffic_source": None if traffic is None else "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                  "(profiles/r2_ncu_traffic.json: a static capture, not re-measured in this run)",
+                "hbm": {"algorithmic_bytes_per_launch": out_bytes + in_bytes,
+                        "achieved": (out_bytes + in_bytes) / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                        "unit": "GB/s", "frac": (out_bytes + in_bytes) / (kern_ms * 1e-3) / 1e9 / hbm_peak}}
+
+    def close(self):
+        self.bufs = None
+        self.prog.close()
+
+
+def ncu_traffic(workload):
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+            t = prof.get(workload, {}).get("dram_bytes_per_launch")
+            if t is not None:
+                return t
+        except Exception:
+            pass
+    return None
+
+
+def pinned(torch, shape, dt):
+    return torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+
+
+def e2e_host(pkg, torch, run, steps, warmup, barrier, world, dev, dist, extra_kw=None, meanvar=False):
+    """The same workload through b200ode_solve with HOST (pinned) buffers: H2D, kernels and D2H inside the timed region."""
+    ll = pkg.lowlevel
+    w, N, n = run.w, run.N, run.n
+    prog = run.prog
+    rdt = torch.float32 if w["f32"] else torch.float64
+    nsave = prog.nsave
+    out = {"u_final": pinned(torch, (N, n), rdt), "t_final": pinned(torch, (N,), torch.float64)}
+    if run.nslots > 0:
+        if not meanvar:
+            out["us"] = pinned(torch, (N, run.nslots, nsave), rdt)
+        out["ts"] = np.empty((run.nslots,), dtype=np.float64)
+    for k in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
+        out[k] = pinned(torch, (N,), torch.int32)
+    u0_h = np.ascontiguousarray(run.u0, dtype=np.float32 if w["f32"] else np.float64)
+    p_pin = None
+    if run.p is not None:
+        p_pin = pinned(torch, run.p.shape, rdt)
+        p_pin[...] = run.p
+    kw = dict(run.kw, **(extra_kw or {}))
+    if meanvar:
+        kw["_meanvar"] = (True, True)
+
+    def step_host():
+        return ll.solve_host(prog, u0_h, p_pin, w["tspan"], trajectories=N, out=out, **kw)
+    for _ in range(max(1, min(warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = step_host()
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    N = w["N"]
-    h = pkg.Handle(local_rank)
-    rhs = pl.lorenz_source(False)
-    prog = h.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1])
-    idx = d.shard_indices(N, world, rank)
-    m = int(idx.shape[0])
-    p = np.empty((m, 3), dtype=np.float64)
-    p[:, 0] = 10.0
-    p[:, 1] = 14.0 + 28.0 * idx.astype(np.float64) / float(N)
-    p[:, 2] = 8.0 / 3.0
-    bufs = ll.DeviceBuffers(prog, m, 0, dev, u0_shared=True)
-    bufs.u0.copy_(torch.tensor([1.0, 0.0, 0.0], dtype=torch.float64))
-    bufs.p.copy_(torch.from_numpy(p))
-    part = torch.zeros(3, dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    h2d = u0_h.nbytes + (p_pin.nbytes if p_pin is not None else 0) + (len(run.grid) * run.rs if run.grid else 0)
+    d2h = sum(v.nbytes for k, v in out.items() if isinstance(v, np.ndarray) and k != "ts")
+    return {"value": world * N * steps / float(tt.item()), "unit": "trajectories/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "device_ms_per_step": r["total_ms"],
+            "kernel_ms_per_step": r["kernel_ms"]}, out
 
-    def step():
-        ll.solve_device(prog, bufs, w["tspan"])
-        ll.reduce_sum_device(h, pkg.F64, bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
-        if world > 1:
-            full = d.gather_in_order(bufs.u_final, N)
-            mean = d.allreduce_mean(part, N)
-        else:
-            full, mean = bufs.u_final, part / float(N)
-        return full, mean
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        step()
+def d2h_ceiling(torch, run, out, barrier, world, dev, dist, reps=3):
+    """cudaMemcpyAsync-only baseline: the D2H of the step's result bytes (device buffers -> the same pinned host
+    buffers), all ranks at once — what the host side of PCIe allows for this many GPUs, with no kernels involved."""
+    pairs = []
+    b = run.bufs
+    if run.nslots > 0 and "us" in out:
+        pairs.append((torch.from_numpy(out["us"]), b.us))
+    pairs.append((torch.from_numpy(out["u_final"]), b.u_final))
+    for k in ("nsaved", "naccept", "nreject", "nf", "retcode"):
+        pairs.append((torch.from_numpy(out[k]), getattr(b, k)))
+    nbytes = sum(d.numel() * d.element_size() for d, _ in pairs)
+    for d, s in pairs:
+        d.copy_(s.reshape(d.shape), non_blocking=True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        full, mean = step()
+    for _ in range(reps):
+        for d, s in pairs:
+            d.copy_(s.reshape(d.shape), non_blocking=True)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tt = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    assert full.shape[0] == N and bool((bufs.retcode == 1).all())
-    if rank == 0:
-        print(json.dumps({"metric": metric, "value": N * args.steps / (ms * 1e-3), "unit": "trajectories/s", "n_gpus": world,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": dict(config, trajectories_total=N, trajectories_per_gpu=m,
-                                         partition="interleaved blocks of 1024 trajectories; NCCL all-gather of final states + all-reduce mean"),
-                          "ensemble_mean_u_tf": [float(x) for x in mean.cpu()], "gpu_launches": 4 * args.steps}))
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    return {"d2h_only_ms_per_step": ms, "d2h_only_gb_s_per_gpu": nbytes / (ms * 1e-3) / 1e9,
+            "d2h_only_gb_s_total": world * nbytes / (ms * 1e-3) / 1e9,
+            "note": "cudaMemcpyAsync of the step's result bytes into the same pinned buffers on all ranks at once, no kernels: "
+                    "the host-side PCIe ceiling of e2e at this GPU count"}
+
+
+def gather_stats(torch, dist, world, dev, values):
+    """min / max / all of one float per rank."""
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=dev)
+    if world == 1:
+        return [t.tolist()]
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
+
+
+def strong_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barrier):
+    """ONE 2^20-trajectory Lorenz/Tsit5 saveat ensemble sharded over the ranks in interleaved blocks of 1024."""
+    import importlib
+    d = importlib.import_module("ordinarydiffeq_jl_b200.distributed")
+    w = WORKLOADS["lorenz_tsit5_saveat_1m"]
+    Ntot = w["N"]
+    idx = d.shard_indices(Ntot, world, rank)
+    run = DeviceRun(pkg, h, w, int(idx.shape[0]), dev, idx=idx)
+    steps = max(3, min(args.steps, 10))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total, step_ms, _ = run.timed(steps, max(3, min(args.warmup, 3)), barrier)
+    clocks = sampler.finish()
+    per_rank = gather_stats(torch, dist, world, dev, [np.mean(step_ms), run.attempts()])
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    kms = [x[0] for x in per_rank]
+    out = {"metric": "trajectories/sec", "value": Ntot * steps / (ms * 1e-3), "unit": "trajectories/s", "scaling": "strong",
+           "trajectories_total": Ntot, "trajectories_per_gpu": int(idx.shape[0]), "steps": steps, "ms_per_step": ms / steps,
+           "partition": "interleaved blocks of 1024 trajectories (block b -> rank b % N); outputs stay sharded in HBM, no collective",
+           "kernel_ms_per_rank": {"min": min(kms), "max": max(kms), "all": kms},
+           "attempted_steps_per_rank": [int(x[1]) for x in per_rank],
+           "load_imbalance": (max(kms) - min(kms)) / max(kms) if max(kms) > 0 else 0.0, "clocks": clocks}
+    run.close()
+    return out
+
+
+def sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barrier, N=None):
+    """configs[4]: 64 Mi-trajectory rho sweep, interleaved shards; ordered gather of the final states (copy-free: one
+    all_gather per round, written in place) + ensemble mean (device partial sums, all-reduce) inside the timed step."""
+    import importlib
+    d = importlib.import_module("ordinarydiffeq_jl_b200.distributed")
+    ll = pkg.lowlevel
+    w = WORKLOADS["lorenz_sweep_64m"]
+    N = N or w["N"]
+    block = d.sweep_block(N, world)
+    idx = d.shard_indices(N, world, rank, block=block)
+    m = int(idx.shape[0])
+    run = DeviceRun(pkg, h, w, m, dev, idx=idx, total=N)
+    part = torch.zeros(3, dtype=torch.float64, device=dev)
+    full = torch.empty((N, 3), dtype=torch.float64, device=dev) if world > 1 else None
+    in_place = world > 1 and (N % (world * block) == 0)
+    steps = max(2, min(args.steps, 4))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    mean = None
+
+    def step(i=None):
+        nonlocal mean
+        if i is not None:
+            ev[i][0].record()
+        run.step()
+        ll.reduce_sum_device(h, pkg.F64, run.bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
+        if i is not None:
+            ev[i][1].record()
+        if world > 1:
+            if in_place:
+                d.gather_in_place(run.bufs.u_final, N, block, out=full)
+            else:
+                full.copy_(d.gather_in_order(run.bufs.u_final, N, block=block))
+            mean = d.allreduce_mean(part, N)
+        else:
+            mean = part / float(N)
+        if i is not None:
+            ev[i][2].record()
+    for _ in range(3):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    kern = float(np.mean([a[0].elapsed_time(a[1]) for a in ev]))
+    coll = float(np.mean([a[1].elapsed_time(a[2]) for a in ev]))
+    per_rank = gather_stats(torch, dist, world, dev, [kern, coll])
+    tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    attempts = run.attempts()
+    if world > 1:
+        # the gathered array is in global trajectory order: this rank's block 0 sits at global block `rank`
+        assert torch.equal(full[rank * block:(rank + 1) * block], run.bufs.u_final[:block])
+    kms = [x[0] for x in per_rank]
+    cms = [x[1] for x in per_rank]
+    out = {"metric": "trajectories/sec", "value": N * steps / (ms * 1e-3), "unit": "trajectories/s", "scaling": "strong",
+           "trajectories_total": N, "trajectories_per_gpu": m, "steps": steps, "ms_per_step": ms / steps,
+           "partition": "interleaved blocks of %d trajectories (block b -> rank b %% N)" % block,
+           "collectives": "none (single GPU)" if world == 1 else
+                          "%d x ncclAllGather of the final states written in place (no un-interleave copy) + ncclAllReduce of the "
+                          "partial sums, over NVLink" % (N // (world * block) if in_place else 1),
+           "kernel_ms_per_rank": {"min": min(kms), "max": max(kms), "all": kms},
+           "collective_ms_per_rank": {"min": min(cms), "max": max(cms), "all": cms},
+           "collective_share": (max(cms) / (ms / steps)) if ms > 0 else None,
+           "gathered_bytes": N * 24, "load_imbalance": (max(kms) - min(kms)) / max(kms) if max(kms) > 0 else 0.0,
+           "ensemble_mean_u_tf": [float(x) for x in mean.cpu()], "attempted_steps_this_rank": attempts, "clocks": clocks,
+           "roofline": run.roofline(kern, attempts)}
+    run.close()
+    return out
 
 
 def main():
@@ -231,6 +514,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations")
+    ap.add_argument("--no-scaling-sections", action="store_true", help="skip strong_1m / sweep_64m")
+    ap.add_argument("--sweep-n", type=int, default=0, help="trajectories of the sweep section (default 2^26)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -269,41 +555,16 @@ def main():
         print(json.dumps(line))
         return 0
 
-    if w["problem"] == "lorenz_sweep":
-        return sweep_main(args, w, pkg, rank, world, local_rank, metric, config)
-
     # ------------------------------------------------------------------ B200 arm
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU oracle")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ll = pkg.lowlevel
-    h = pkg.Handle(local_rank)
-    rhs, jac, tg, n, np_ = sources(pl, w)
-    alg_id = {"tsit5": pkg.ALG_TSIT5, "vern7": pkg.ALG_VERN7, "ros23": pkg.ALG_ROSENBROCK23, "rodas5p": pkg.ALG_RODAS5P}[w["alg"]]
-    dtype = pkg.F32 if w["f32"] else pkg.F64
-    prog = h.compile(alg_id, dtype, n, np_, rhs[0], rhs[1], jac[0] if jac else None, jac[1] if jac else None,
-                     tg[0] if tg else None, tg[1] if tg else None,
-                     extra_options="-DB200_STAGE_UNROLL=4" if w["problem"] == "pleiades" else None)
-    N = w["N"]
-    grid = pkg.ranges.saveat_grid(w["saveat"], w["tspan"]) if w["saveat"] is not None else None
-    nslots = ll.nslots_for(w["tspan"], grid) if grid else 0
-    u0, p = inputs(pl, w, N, rank * N)        # weak scaling: every rank integrates its own N trajectories
-    rs = 4 if w["f32"] else 8
     dev = torch.device("cuda", local_rank)
-
-    # device-resident buffers (value)
-    bufs = ll.DeviceBuffers(prog, N, nslots, dev, u0_shared=(u0.ndim == 1), p_shared=(p is None))
-    bufs.u0.copy_(torch.from_numpy(np.ascontiguousarray(u0, dtype=np.float32 if w["f32"] else np.float64)))
-    if p is not None:
-        bufs.p.copy_(torch.from_numpy(np.ascontiguousarray(p)))
-    kw = dict(saveat=grid, **w["tol"])
-
-    def step_device():
-        ll.solve_device(prog, bufs, w["tspan"], **kw)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h = pkg.Handle(local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -311,154 +572,122 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if w["problem"] == "lorenz_sweep":
+        sec = sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barrier, N=args.sweep_n or None)
+        if rank == 0:
+            line = dict(sec, n_gpus=world, warmup=3, higher_is_better=True, vs_baseline=None, dtype="f64", data="synthetic",
+                        config=dict(config, trajectories_total=sec["trajectories_total"]), gpu_launches=4 * sec["steps"])
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    N = w["N"]
+    run = DeviceRun(pkg, h, w, N, dev, offset=rank * N)       # weak scaling: every rank integrates its own N trajectories
     for _ in range(args.warmup):
-        step_device()
+        run.step()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall = time.perf_counter()
-    e_all0.record()
-    for i in range(args.steps):
-        ev[i][0].record()
-        step_device()
-        ev[i][1].record()
-    e_all1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    dev_ms_total = e_all0.elapsed_time(e_all1)
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    # statistics of the run (for the algorithmic flop count) and a sanity check that it solved
-    naccept = bufs.naccept.cpu().numpy().astype(np.int64)
-    nreject = bufs.nreject.cpu().numpy().astype(np.int64)
-    retcode = bufs.retcode.cpu().numpy()
-    assert (retcode == 1).all(), "bench: some trajectories did not reach tf"
-    attempts = int(naccept.sum() + nreject.sum())
+    dev_ms_total, step_ms, t_wall = run.timed(args.steps, 0, barrier)
+    clocks = sampler.finish()
+    attempts = run.attempts()
     t = torch.tensor([dev_ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * N * args.steps / (ms_total * 1e-3)
-
-    # ---- kernel-only duration of b200_integrate for the roofline: one extra pass with events around the solve call
-    # (initdt + integrate; initdt is <2% of the time, see profiles/)
     kern_ms = float(np.mean(step_ms))
-    flops_per_launch = None
-    roofline = None
-    if w["problem"] == "lorenz" and w["alg"] == "tsit5":
-        n_interp = N * (len(grid) - 1) if grid else 0            # the row at tf is a copy, not an interpolation
-        flops_per_launch = F_STEP_TSIT5_LORENZ * attempts + F_INTERP * n_interp + F_INIT * N
-        peak_tf, _ = h.measure_fma_peak(dtype)
-        achieved = flops_per_launch / (kern_ms * 1e-3) / 1e12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        out_bytes = N * nslots * n * rs + N * (n * rs + rs + 4 * 8)
-        in_bytes = N * np_ * rs + N * rs
-        traffic = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-            traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        roofline = {"bound": "fp64_fma" if not w["f32"] else "fp32_fma", "achieved": achieved, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "bound_note": "compute-bound on the scalar FP64 (FP32) FMA pipe: the path has no contraction, so "
-                                  "neither the tensor-core nor the HBM roofline applies; the HBM side of the same "
-                                  "launch is reported under roofline.hbm",
-                    "peak_source": "measured live: b200ode_measure_fma_peak (register-resident FMA chains); "
-                                   "MEASURED_PEAKS.json has no FP64 figure",
-                    "algorithmic_flops_per_launch": flops_per_launch,
-                    "flops_model": "247/attempted step + 85/interpolated row + 60/trajectory (DESIGN.md)",
-                    "kernel_ms": kern_ms, "traffic": traffic,
-                    "hbm": {"algorithmic_bytes_per_launch": out_bytes + in_bytes,
-                            "achieved": (out_bytes + in_bytes) / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                            "unit": "GB/s", "frac": (out_bytes + in_bytes) / (kern_ms * 1e-3) / 1e9 / hbm_peak}}
+    per_rank = gather_stats(torch, dist, world, dev, [kern_ms])
+    roofline = run.roofline(kern_ms, attempts, traffic=ncu_traffic(args.workload)) if (w["problem"], w["alg"]) in FLOPS else None
 
     # ---- e2e: host (pinned) buffers through b200ode_solve, H2D and D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        def pinned(shape, dt):
-            tt = torch.empty(shape, dtype=dt, pin_memory=True)
-            return tt.numpy()
-        rdt = torch.float32 if w["f32"] else torch.float64
-        out = {"u_final": pinned((N, n), rdt), "t_final": pinned((N,), torch.float64)}
-        if nslots > 0:
-            out["us"] = pinned((N, nslots, n), rdt)
-            out["ts"] = np.empty((nslots,), dtype=np.float64)
-        for k in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
-            out[k] = pinned((N,), torch.int32)
-        u0_h = np.ascontiguousarray(u0, dtype=np.float32 if w["f32"] else np.float64)
-        if p is not None:
-            p_pin = pinned(p.shape, rdt)
-            p_pin[...] = p
-        else:
-            p_pin = None
-
-        def step_host():
-            return ll.solve_host(prog, u0_h, p_pin, w["tspan"], trajectories=N, out=out, **kw)
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_host()
-        barrier()
         k_e2e = max(2, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            r = step_host()
-        barrier()
-        dt_e2e = time.perf_counter() - t0
-        tt = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        h2d = u0_h.nbytes + (p_pin.nbytes if p_pin is not None else 0) + (len(grid) * rs if grid else 0)
-        d2h = sum(v.nbytes for k, v in out.items() if isinstance(v, np.ndarray) and k != "ts")
-        e2e = {"value": world * N * k_e2e / float(tt.item()), "unit": "trajectories/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": k_e2e, "api": "b200ode_solve (C ABI, pinned host buffers)",
-               "device_ms_per_step": r["total_ms"], "kernel_ms_per_step": r["kernel_ms"]}
-
-        # informational: the same ensemble when only EnsembleAnalysis statistics are wanted
-        # (b200ode_solve_meanvar: rows stay in HBM, mean/var per saved row come back)
-        if nslots > 0:
-            out2 = {k: v for k, v in out.items() if k not in ("us",)}
-            ll.solve_host(prog, u0_h, p_pin, w["tspan"], trajectories=N, out=out2, _meanvar=(True, True), **kw)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(k_e2e):
-                ll.solve_host(prog, u0_h, p_pin, w["tspan"], trajectories=N, out=out2, _meanvar=(True, True), **kw)
-            barrier()
-            e2e["stats_only"] = {"value": world * N * k_e2e / (time.perf_counter() - t0), "unit": "trajectories/s",
-                                 "api": "b200ode_solve_meanvar (timeseries mean/var reduced on the device)",
-                                 "d2h_bytes_per_step": int(sum(v.nbytes for k, v in out2.items() if isinstance(v, np.ndarray) and k != "ts"))}
+        e2e, out = e2e_host(pkg, torch, run, k_e2e, args.warmup, barrier, world, dev, dist)
+        e2e["api"] = "b200ode_solve (C ABI, pinned host buffers)"
+        e2e["copy_ceiling"] = d2h_ceiling(torch, run, out, barrier, world, dev, dist)
+        ceil_ms = e2e["copy_ceiling"]["d2h_only_ms_per_step"]
+        e2e["fraction_of_copy_ceiling"] = (ceil_ms / e2e["device_ms_per_step"]) if e2e["device_ms_per_step"] else None
+        del out
+        variants = {}
+        if run.nslots > 0:
+            # only EnsembleAnalysis statistics wanted: rows stay in HBM (b200ode_solve_meanvar)
+            v, _ = e2e_host(pkg, torch, run, k_e2e, 1, barrier, world, dev, dist, meanvar=True)
+            v["api"] = "b200ode_solve_meanvar (timeseries mean/var reduced on the device)"
+            variants["meanvar_on_device"] = v
+        e2e["variants"] = variants
+        e2e["stats_only"] = variants.get("meanvar_on_device")
 
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sample, threads, spt = cpu_oracle_rate(pl, w, args.cpu_seconds)
-        cpu = {"value": v, "unit": "trajectories/s", "cores": threads, "kind": "port",
-               "sample": "%d of the %d trajectories (same inputs/options), CPU oracle with OpenMP schedule(dynamic,64)" % (sample, N),
-               "steps_per_trajectory": spt}
+        cpu = cpu_baseline_entry(pl, w, args.cpu_seconds)
+    prog_info = run.prog.info
+    run.close()
+
+    # ---- the other BASELINE configurations, short runs (N = 1 only: they are single-GPU configurations)
+    configs = []
+    if world == 1 and not args.no_configs and args.workload == "lorenz_tsit5_saveat_1m":
+        for name in OTHER_CONFIGS:
+            wc = WORKLOADS[name]
+            r = DeviceRun(pkg, h, wc, wc["N"], dev)
+            smp = ClockSampler(local_rank)
+            smp.start()
+            tot, sms, _ = r.timed(3, 3, barrier)
+            ck = smp.finish()
+            att = r.attempts()
+            entry = {"workload": name, "problem": wc["problem"], "alg": wc["alg"], "dtype": "f32" if wc["f32"] else "f64",
+                     "trajectories": wc["N"], "saveat": wc["saveat"], "tolerances": wc["tol"] or "defaults",
+                     "value": wc["N"] * 3 / (tot * 1e-3), "unit": "trajectories/s", "ms_per_step": tot / 3, "steps": 3, "warmup": 3,
+                     "attempted_steps_per_launch": att, "clocks": ck, "program": r.prog.info,
+                     "roofline": r.roofline(float(np.mean(sms)), att, traffic=ncu_traffic(name))}
+            if name == "lorenz_tsit5_saveat_1m_f32" and not args.no_e2e:
+                v, _ = e2e_host(pkg, torch, r, 3, 1, barrier, world, dev, dist)
+                v["api"] = "b200ode_solve (C ABI, pinned host buffers), FP32"
+                entry["e2e"] = v
+            if not args.no_cpu_baseline:
+                entry["cpu_baseline"] = cpu_baseline_entry(pl, wc, 3.0)
+            r.close()
+            configs.append(entry)
+        if not args.no_e2e:
+            # save_idxs variant of the headline workload: one component per saved row (a third of the row bytes)
+            r = DeviceRun(pkg, h, w, N, dev, extra_options=pkg._lib.opt_save_idxs([0]))
+            v, _ = e2e_host(pkg, torch, r, 3, 1, barrier, world, dev, dist)
+            v["api"] = "b200ode_solve (C ABI, pinned host buffers), save_idxs = [1]"
+            e2e["variants"]["save_idxs_first_component"] = v
+            r.close()
+
+    strong = sweep = None
+    if not args.no_scaling_sections and args.workload == "lorenz_tsit5_saveat_1m":
+        strong = strong_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barrier)
+        sweep = sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barrier, N=args.sweep_n or None)
 
     if rank == 0:
+        launches = 2 * args.steps
         line = {"metric": metric, "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if w["f32"] else "f64", "data": "synthetic", "config": config,
-                "clocks": sampler.summary(), "gpu_launches": 2 * args.steps,
-                "gpu_launches_note": "b200_initdt + b200_integrate per step (NVRTC-compiled, loaded by libb200ode.so)",
+                "clocks": clocks, "gpu_launches": launches,
+                "gpu_launches_note": "b200_initdt + b200_integrate per step of the timed headline region (NVRTC-compiled, "
+                                     "loaded by libb200ode.so); the other sections launch the same two kernels per step",
                 "attempted_steps_per_launch": attempts, "wall_s_timed_region": t_wall,
-                "program": prog.info}
+                "kernel_ms_per_rank": {"min": min(x[0] for x in per_rank), "max": max(x[0] for x in per_rank)},
+                "program": prog_info}
         if e2e:
             line["e2e"] = e2e
         if roofline:
             line["roofline"] = roofline
         if cpu:
             line["cpu_baseline"] = cpu
+        if configs:
+            line["configs"] = configs
+        if strong:
+            line["strong_1m"] = strong
+        if sweep:
+            line["sweep_64m"] = sweep
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -48,7 +48,15 @@ __shared__ real b200_coop_smem[(B200_BLOCK / 32) * B200_GPW * B200_COOP_WORDS];
 // acceleration of one body) are computed once and independent terms overlap; the plain operators (B200UserExact) redo
 // the lane only if a flag was raised.
 struct B200VRet { real v[B200_VLEN]; };
-__device__ __noinline__ B200VRet b200_rhs_lane(int g, const real* Ub, const real* p, real t) {
+#ifndef B200_COOP_INLINE
+#define B200_COOP_INLINE 0      // 1: inline the lane evaluator at every stage (measured: see DESIGN.md §4)
+#endif
+#if B200_COOP_INLINE
+__device__ __forceinline__ B200VRet b200_rhs_lane(int g, const real* Ub, const real* p, real t);
+#else
+__device__ __noinline__ B200VRet b200_rhs_lane(int g, const real* Ub, const real* p, real t);
+#endif
+B200VRet b200_rhs_lane(int g, const real* Ub, const real* p, real t) {
     B200VRet r;
 #pragma unroll
     for (int l = 0; l < B200_VLEN; ++l) r.v[l] = (real)0;

@@ -58,6 +58,33 @@ def gather_in_order(local, N, block=BLOCK, group=None):
     return full
 
 
+def sweep_block(N, world, chunks_per_rank=32, base=BLOCK):
+    """Interleave granularity for large ensembles: ~chunks_per_rank blocks per rank (whole multiples of `base`),
+    coarse enough that the ordered gather is a handful of collectives, fine enough that a parameter sweep whose cost
+    varies smoothly with the index is balanced to within a block."""
+    b = max(base, N // max(1, world * chunks_per_rank))
+    return max(base, (b // base) * base)
+
+
+def gather_in_place(local, N, block, out=None, group=None):
+    """Ordered all-gather WITHOUT an un-interleave copy: with blocks dealt round-robin (block b -> rank b % world),
+    round k of the gather (every rank's k-th block) is exactly the contiguous slice [k*world*block, (k+1)*world*block)
+    of the result in rank order — one all_gather_into_tensor per round, written straight into its final place.
+    Needs N % (world*block) == 0 (callers pick `block` with sweep_block; otherwise use gather_in_order)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert N % (world * block) == 0, "gather_in_place needs whole rounds"
+    tail = tuple(local.shape[1:])
+    rounds = N // (world * block)
+    if out is None:
+        out = torch.empty((N,) + tail, dtype=local.dtype, device=local.device)
+    loc = local.contiguous()
+    for k in range(rounds):
+        dist.all_gather_into_tensor(out[k * world * block:(k + 1) * world * block], loc[k * block:(k + 1) * block], group=group)
+    return out
+
+
 def allreduce_mean(local_sum, N, group=None):
     """local_sum: float64 tensor [n] = sum of this rank's trajectories (b200ode_reduce_sum_device).
     Returns the ensemble mean [n] on every rank."""

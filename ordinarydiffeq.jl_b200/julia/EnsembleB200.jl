@@ -7,25 +7,36 @@
 # emits the RHS / Jacobian as C with Symbolics `build_function(...; target = CTarget())`, and
 # `ccall`s libb200ode.so.  Nothing below constructs an ODEIntegrator.
 #
-# NOTE: this file could not be executed in the build environment (no Julia toolchain there);
-# the same ABI is exercised end-to-end by the Python host mirror (ordinarydiffeq.jl_b200/ensemble.py),
-# whose structs mirror the ones below field by field.
+# STATUS: EXPERIMENTAL — this file has never been executed: no Julia toolchain exists in the build
+# container or on the GPU boxes (`which julia` is empty on both).  The same ABI is exercised end to end
+# by the Python host mirror (ordinarydiffeq.jl_b200/ensemble.py), whose structs mirror the ones below
+# field by field, and by tests/test_abi.py.  Every name used here is imported explicitly below.
 module EnsembleB200Mod
 
 using SciMLBase, Symbolics, StaticArrays
-import SciMLBase: __solve, AbstractEnsembleProblem, EnsembleAlgorithm, EnsembleSolution, build_solution
+import SciMLBase: __solve, AbstractEnsembleProblem, EnsembleAlgorithm, EnsembleSolution, build_solution, ReturnCode
 using OrdinaryDiffEqTsit5: Tsit5
-using OrdinaryDiffEqVerner: Vern7
-using OrdinaryDiffEqRosenbrock: Rosenbrock23, Rodas5P
+using OrdinaryDiffEqVerner: Vern6, Vern7, Vern8, Vern9
+using OrdinaryDiffEqLowOrderRK: DP5, BS3
+using OrdinaryDiffEqRosenbrock: Rosenbrock23, Rosenbrock32, Rodas5P, Rodas5Pe, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2
 
 export EnsembleB200
 
 const LIB = get(ENV, "B200ODE_LIB", "libb200ode.so")
 
+"""
+    EnsembleB200()                 # device 0
+    EnsembleB200(2)                # device 2
+    EnsembleB200([0, 1, 2, 3])     # several GPUs from this one process (b200ode_multi_*; chunks dealt round-robin)
+    EnsembleB200(:all)             # every visible GPU
+"""
 struct EnsembleB200 <: EnsembleAlgorithm
-    device::Int
+    devices::Vector{Int}           # empty = all visible devices
 end
-EnsembleB200() = EnsembleB200(0)
+EnsembleB200() = EnsembleB200([0])
+EnsembleB200(dev::Integer) = EnsembleB200([Int(dev)])
+EnsembleB200(s::Symbol) = s === :all ? EnsembleB200(Int[]) : throw(ArgumentError("EnsembleB200(:all) or a device list"))
+ismulti(e::EnsembleB200) = length(e.devices) != 1
 
 # ---- C structs (include/b200ode.h) ----------------------------------------------------------
 struct B200Problem
@@ -47,7 +58,6 @@ mutable struct B200Result
     njacs::Ptr{Int32}; nw::Ptr{Int32}; nsolve::Ptr{Int32}; retcode::Ptr{Int32}
     kernel_ms::Float64; total_ms::Float64
 end
-
 struct B200Ragged            # save_everystep rows (b200ode_solve_everystep); buffers are released with b200ode_free
     total_rows::Int64
     row_offsets::Ptr{Int64}; ts::Ptr{Float64}; us::Ptr{Cvoid}
@@ -72,7 +82,7 @@ end
 
 # ---- code generation: Symbolics traces f(u,p,t) and emits C ------------------------------------
 function c_sources(prob, alg, ::Type{T}) where {T}
-    n, np = length(prob.u0), prob.p === nothing ? 0 : length(prob.p)
+    n, np = length(prob.u0), (prob.p === nothing || prob.p isa SciMLBase.NullParameters) ? 0 : length(prob.p)
     @variables u[1:n] p[1:max(np, 1)] t
     us, ps = collect(u), collect(p)
     du = SciMLBase.isinplace(prob) ? (d = similar(us, Num); prob.f.f(d, us, ps, t); d) : collect(prob.f.f(us, ps, t))
@@ -80,24 +90,161 @@ function c_sources(prob, alg, ::Type{T}) where {T}
     rhs = fix(build_function(du, us, ps, t; target = Symbolics.CTarget(), fname = :diffeqf))
     jac = tgr = nothing
     if isstiff(alg)
-        J = Symbolics.jacobian(du, us)
+        # ODEFunction(f; jac, tgrad) given by the user: trace those; otherwise differentiate symbolically
+        J = prob.f.jac === nothing ? Symbolics.jacobian(du, us) :
+            (SciMLBase.isinplace(prob) ? (M = Matrix{Num}(undef, n, n); prob.f.jac(M, us, ps, t); M) : collect(prob.f.jac(us, ps, t)))
+        dT = prob.f.tgrad === nothing ? Symbolics.derivative.(du, t) :
+             (SciMLBase.isinplace(prob) ? (v = similar(us, Num); prob.f.tgrad(v, us, ps, t); v) : collect(prob.f.tgrad(us, ps, t)))
         jac = fix(build_function(vec(J), us, ps, t; target = Symbolics.CTarget(), fname = :diffeqjac))  # column major
-        tgr = fix(build_function(Symbolics.derivative.(du, t), us, ps, t; target = Symbolics.CTarget(), fname = :diffeqtgrad))
+        tgr = fix(build_function(dT, us, ps, t; target = Symbolics.CTarget(), fname = :diffeqtgrad))
     end
     return n, np, rhs, jac, tgr
 end
 
-const HANDLES = Dict{Int, Ptr{Cvoid}}()
-function handle(dev)
-    get!(HANDLES, dev) do
-        h = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:b200ode_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), h, dev))
-        h[]
+# ---- handles and the program cache ----------------------------------------------------------------
+# One handle per device list for the life of the process; one compiled program per
+# (devices, alg, T, n, np, hash of the generated sources, variant options).  Programs are destroyed
+# (b200ode_[multi_]program_destroy) when the cache is emptied or at exit — never leaked per solve.
+const HANDLES = Dict{Vector{Int}, Ptr{Cvoid}}()
+const PROGRAMS = Dict{Any, Tuple{Ptr{Cvoid}, Bool}}()
+const CACHE_LOCK = ReentrantLock()
+
+function handle(ens::EnsembleB200)
+    lock(CACHE_LOCK) do
+        get!(HANDLES, ens.devices) do
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            if ismulti(ens)
+                ids = Cint.(ens.devices)
+                check(ccall((:b200ode_multi_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Ptr{Cint}, Cint),
+                            h, isempty(ids) ? C_NULL : pointer(ids), length(ids)))
+            else
+                check(ccall((:b200ode_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Cint), h, ens.devices[1]))
+            end
+            h[]
+        end
+    end
+end
+
+function program(ens::EnsembleB200, h, alg, ::Type{T}, n, np, rhs, jac, tgr, extra::String) where {T}
+    key = (ens.devices, alg_id(alg), T, n, np, hash(rhs), hash(jac), hash(tgr), extra)
+    lock(CACHE_LOCK) do
+        get!(PROGRAMS, key) do
+            prog = Ref{Ptr{Cvoid}}(C_NULL)
+            args = (h, prog, alg_id(alg), T === Float32 ? 1 : 0, n, np, rhs, "diffeqf",
+                    jac === nothing ? C_NULL : jac, "diffeqjac", tgr === nothing ? C_NULL : tgr, "diffeqtgrad",
+                    isempty(extra) ? C_NULL : extra)
+            if ismulti(ens)
+                check(ccall((:b200ode_multi_compile, LIB), Cint,
+                            (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring),
+                            args...))
+            else
+                check(ccall((:b200ode_compile, LIB), Cint,
+                            (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring),
+                            args...))
+            end
+            (prog[], ismulti(ens))
+        end
+    end
+end
+
+"Destroy every cached program and handle (also registered with atexit)."
+function release!()
+    lock(CACHE_LOCK) do
+        for (prog, multi) in values(PROGRAMS)
+            multi ? ccall((:b200ode_multi_program_destroy, LIB), Cint, (Ptr{Cvoid},), prog) :
+                    ccall((:b200ode_program_destroy, LIB), Cint, (Ptr{Cvoid},), prog)
+        end
+        empty!(PROGRAMS)
+        for (devs, h) in HANDLES
+            length(devs) != 1 ? ccall((:b200ode_multi_destroy, LIB), Cint, (Ptr{Cvoid},), h) :
+                                ccall((:b200ode_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+        end
+        empty!(HANDLES)
+    end
+end
+__init__() = atexit(release!)
+
+# page-lock an output array for the duration of a call (D2H then runs at PCIe speed, profiles/r1_time_pageable_vs_pinned.json)
+function with_pinned(f, arrays...)
+    pinned = Any[]
+    try
+        for a in arrays
+            (a === nothing || sizeof(a) < (1 << 20)) && continue
+            ccall((:b200ode_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), pointer(a), sizeof(a)) == 0 && push!(pinned, a)
+        end
+        return f()
+    finally
+        for a in pinned
+            ccall((:b200ode_host_unregister, LIB), Cint, (Ptr{Cvoid},), pointer(a))
+        end
     end
 end
 
 const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :tstops, :reltol, :abstol,
-                 :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense)
+                 :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense, :verbose, :progress)
+
+# One batch of trajectories I (global sim ids) with repeat counters `rep`: harvest prob_func, solve, wrap.
+function solve_ids(eprob, prob, alg, ens, h, prog, multi, opts, grid, tstops, everystep, idxs, w, n, np, T, t0, tf, I, rep)
+    N = length(I)
+    U0 = Matrix{T}(undef, n, N); P = Matrix{T}(undef, max(np, 1), N)
+    for (k, i) in enumerate(I)
+        q = eprob.prob_func(prob, SciMLBase.EnsembleContext(i, rep[k], nothing))
+        q.tspan == prob.tspan || throw(ArgumentError("EnsembleB200: prob_func must keep tspan (all trajectories share it)"))
+        U0[:, k] .= q.u0
+        np > 0 && (P[:, k] .= q.p)
+    end
+    cprob = B200Problem(N, pointer(U0), 0, pointer(P), 0, t0, tf)
+    nslots = ccall((:b200ode_nslots, LIB), Cint, (Ref{B200Problem}, Ref{B200Opts}), cprob, opts)
+    uf = Matrix{T}(undef, n, N); tfin = Vector{Float64}(undef, N)
+    us = Array{T, 3}(undef, w, max(nslots, 1), N); ts = Vector{Float64}(undef, max(nslots, 1))
+    cnt = [zeros(Int32, N) for _ in 1:8]
+    res = B200Result(pointer(uf), pointer(tfin), nslots > 0 ? pointer(us) : C_NULL, pointer(ts),
+                     pointer.(cnt)..., 0.0, 0.0)
+    rag = Ref(B200Ragged(0, C_NULL, C_NULL, C_NULL))
+    GC.@preserve U0 P grid tstops uf tfin us ts cnt begin
+        with_pinned(us, uf) do
+            if everystep     # ragged rows: trajectory k owns rows offs[k]+1 : offs[k+1]  (single device)
+                check(ccall((:b200ode_solve_everystep, LIB), Cint,
+                            (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}, Ref{B200Ragged}),
+                            h, prog, cprob, opts, res, rag))
+            elseif multi
+                check(ccall((:b200ode_multi_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}),
+                            h, prog, cprob, opts, res))
+            else
+                check(ccall((:b200ode_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}),
+                            h, prog, cprob, opts, res))
+            end
+        end
+    end
+    nsaved, naccept, nreject, nf, njacs, nw, nsolve, rc = cnt
+    offs = everystep ? copy(unsafe_wrap(Array, rag[].row_offsets, N + 1)) : Int64[]
+    rts = everystep ? copy(unsafe_wrap(Array, rag[].ts, rag[].total_rows)) : Float64[]
+    rus = everystep ? copy(unsafe_wrap(Array, Ptr{T}(rag[].us), (w, Int(rag[].total_rows)))) : Matrix{T}(undef, 0, 0)
+    if everystep
+        for ptr in (rag[].row_offsets, rag[].ts, rag[].us)
+            ccall((:b200ode_free, LIB), Cvoid, (Ptr{Cvoid},), ptr)
+        end
+    end
+    sel(v) = idxs === nothing ? v : v[idxs]
+    ss = opts.save_start != 0
+    se = opts.save_end != 0
+    sols = map(1:N) do k
+        if everystep
+            r = (offs[k] + 1):offs[k + 1]
+            tk = rts[r]; uk = [SVector{w, T}(@view rus[:, j]) for j in r]
+        elseif nslots > 0
+            tk = ts[1:nsaved[k]]; uk = [SVector{w, T}(@view us[:, s, k]) for s in 1:nsaved[k]]
+        else    # no saveat grid, save_everystep = false: the start and/or end point, as save_start / save_end say
+            tk = Float64[]; uk = SVector{w, T}[]
+            ss && (push!(tk, t0); push!(uk, SVector{w, T}(sel(@view U0[:, k]))))
+            se && (push!(tk, tfin[k]); push!(uk, SVector{w, T}(sel(@view uf[:, k]))))
+        end
+        stats = SciMLBase.DEStats(Int(nf[k]), 0, 0, Int(nw[k]), Int(nsolve[k]), Int(njacs[k]), 0, 0, 0, 0,
+                                  Int(naccept[k]), Int(nreject[k]), 0.0)
+        build_solution(prob, alg, tk, uk; dense = false, stats, retcode = RETCODES[rc[k] + 1])
+    end
+    return sols
+end
 
 function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB200;
                  trajectories, batch_size = trajectories, kwargs...)
@@ -114,6 +261,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     grid = saveat isa Number ? collect(Float64, (t0 + abs(saveat)):abs(saveat):tf) :
            sort!(Float64[s for s in saveat if t0 < s <= tf])
     everystep = get(kw, :save_everystep, isempty(grid))            # solve.jl:138
+    everystep && ismulti(ens) && throw(ArgumentError("EnsembleB200: save_everystep output is ragged and single-device; pass one device"))
     n, np, rhs, jac, tgr = c_sources(prob, alg, T)
     idxs = get(kw, :save_idxs, nothing)
     idxs isa Integer && (idxs = [idxs])
@@ -127,13 +275,8 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     adaptive || push!(extra, "-DB200_ADAPTIVE=0")
     adaptive || get(kw, :dt, nothing) !== nothing || !isempty(tstops) ||
         throw(ArgumentError("Fixed timestep methods require a choice of dt or choosing the tstops"))
-    extra_opt = isempty(extra) ? C_NULL : join(extra, " ")
-    h = handle(ens.device)
-    prog = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:b200ode_compile, LIB), Cint,
-                (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring),
-                h, prog, alg_id(alg), T === Float32 ? 1 : 0, n, np, rhs, "diffeqf",
-                jac === nothing ? C_NULL : jac, "diffeqjac", tgr === nothing ? C_NULL : tgr, "diffeqtgrad", extra_opt))
+    h = handle(ens)
+    prog, multi = program(ens, h, alg, T, n, np, rhs, jac, tgr, join(extra, " "))
     # defaults of solve.jl:141-143,596-599 (the C ABI only sees the expanded grid)
     dflt(tend) = everystep || isempty(saveat) || saveat isa Number || tend in saveat
     ss = something(get(kw, :save_start, nothing), dflt(prob.tspan[1]))
@@ -142,60 +285,32 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     opts = B200Opts(get(kw, :reltol, 0.0), get(kw, :abstol, 0.0), something(get(kw, :dt, nothing), 0.0),
                     get(kw, :dtmin, 0.0), get(kw, :dtmax, 0.0), get(kw, :maxiters, 0),
                     isempty(grid) ? Ptr{Float64}(C_NULL) : pointer(grid), length(grid),
-                    ss === nothing ? -1 : Int32(ss), se === nothing ? -1 : Int32(se), 0, 0,
+                    Int32(ss), se === nothing ? Int32(-1) : Int32(se), 0, 0,
                     isempty(tstops) ? Ptr{Float64}(C_NULL) : pointer(tstops), length(tstops), 0)
     tstart = time()
     u = eprob.u_init === nothing ? [] : eprob.u_init
     converged = false
     for b0 in 1:batch_size:trajectories
-        I = b0:min(b0 + batch_size - 1, trajectories)
-        N = length(I)
-        # harvest prob_func on the host: flat AoS tables (Vector{SVector{n,T}} is already this layout)
-        U0 = Matrix{T}(undef, n, N); P = Matrix{T}(undef, max(np, 1), N)
-        for (k, i) in enumerate(I)
-            q = eprob.prob_func(prob, SciMLBase.EnsembleContext(i, 1, nothing))
-            U0[:, k] .= q.u0
-            np > 0 && (P[:, k] .= q.p)
-        end
-        cprob = B200Problem(N, pointer(U0), 0, pointer(P), 0, t0, tf)
-        nslots = ccall((:b200ode_nslots, LIB), Cint, (Ref{B200Problem}, Ref{B200Opts}), cprob, opts)
-        uf = Matrix{T}(undef, n, N); tfin = Vector{Float64}(undef, N)
-        us = Array{T, 3}(undef, w, max(nslots, 1), N); ts = Vector{Float64}(undef, max(nslots, 1))
-        cnt = [Vector{Int32}(undef, N) for _ in 1:8]
-        res = B200Result(pointer(uf), pointer(tfin), nslots > 0 ? pointer(us) : C_NULL, pointer(ts),
-                         pointer.(cnt)..., 0.0, 0.0)
-        rag = Ref(B200Ragged(0, C_NULL, C_NULL, C_NULL))
-        GC.@preserve U0 P grid tstops uf tfin us ts cnt begin
-            if everystep     # ragged rows: trajectory k owns rows offs[k]+1 : offs[k+1]
-                check(ccall((:b200ode_solve_everystep, LIB), Cint,
-                            (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}, Ref{B200Ragged}),
-                            h, prog[], cprob, opts, res, rag))
-            else
-                check(ccall((:b200ode_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{B200Problem}, Ref{B200Opts}, Ref{B200Result}),
-                            h, prog[], cprob, opts, res))
+        I = collect(b0:min(b0 + batch_size - 1, trajectories))
+        batch = Vector{Any}(undef, length(I))
+        pending = collect(1:length(I))           # positions of the batch still to be (re)solved
+        rep = ones(Int, length(I))               # ctx.repeat of each position
+        # output_func's rerun flag (SciMLBase solve_batch: `while rerun; prob_func(prob, ctx(repeat += 1)); solve; end`),
+        # served batch-wise: everything flagged is re-submitted to the GPU together until nothing is flagged
+        while !isempty(pending)
+            sols = solve_ids(eprob, prob, alg, ens, h, prog, multi, opts, grid, tstops, everystep, idxs, w, n, np, T, t0, tf,
+                             I[pending], rep[pending])
+            again = Int[]
+            for (j, pos) in enumerate(pending)
+                out, rerun = eprob.output_func(sols[j], SciMLBase.EnsembleContext(I[pos], rep[pos], nothing))
+                if rerun
+                    rep[pos] += 1
+                    push!(again, pos)
+                else
+                    batch[pos] = out
+                end
             end
-        end
-        nsaved, naccept, nreject, nf, njacs, nw, nsolve, rc = cnt
-        offs = everystep ? unsafe_wrap(Array, rag[].row_offsets, N + 1) : Int64[]
-        rts = everystep ? unsafe_wrap(Array, rag[].ts, rag[].total_rows) : Float64[]
-        rus = everystep ? unsafe_wrap(Array, Ptr{T}(rag[].us), (w, Int(rag[].total_rows))) : Matrix{T}(undef, 0, 0)
-        sel(v) = idxs === nothing ? v : v[idxs]
-        batch = map(1:N) do k
-            tk = everystep ? rts[(offs[k] + 1):offs[k + 1]] : nslots > 0 ? ts[1:nsaved[k]] : [t0, tfin[k]]
-            uk = everystep ? [SVector{w, T}(rus[:, r]) for r in (offs[k] + 1):offs[k + 1]] :
-                 nslots > 0 ? [SVector{w, T}(us[:, s, k]) for s in 1:nsaved[k]] :
-                 [SVector{w, T}(sel(U0[:, k])), SVector{w, T}(sel(uf[:, k]))]
-            stats = SciMLBase.DEStats(Int(nf[k]), 0, 0, Int(nw[k]), Int(nsolve[k]), Int(njacs[k]), 0, 0, 0, 0,
-                                      Int(naccept[k]), Int(nreject[k]), 0.0)
-            sol = build_solution(prob, alg, tk, uk; dense = false, stats, retcode = RETCODES[rc[k] + 1])
-            out, rerun = eprob.output_func(sol, SciMLBase.EnsembleContext(I[k], 1, nothing))
-            rerun && error("rerun is served by re-submitting the trajectory; see ensemble.py for the loop")
-            out
-        end
-        if everystep
-            for ptr in (rag[].row_offsets, rag[].ts, rag[].us)
-                ccall((:b200ode_free, LIB), Cvoid, (Ptr{Cvoid},), ptr)
-            end
+            pending = again
         end
         u, converged = eprob.reduction(u, batch, I)
         converged && break

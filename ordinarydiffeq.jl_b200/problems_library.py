@@ -102,10 +102,11 @@ def pleiades_source(f32=False, name="pleiades_rhs", loops=False):
 def pleiades_component_source(f32=False, name="pleiades_rhs_i"):
     """Pleiades in COMPONENT FORM for the lane-group kernel (B200ODE_OPT_COMPONENT_RHS): du_i as a function of the
     run-time index i.  Components 0..13 copy the velocities; components 14..27 are the accelerations of body
-    b = (i - 14) % 7 along x (i < 21) or y, accumulated over j = 0..6, j != b, in the reference's loop order with
-    the reference's operations (dx, dy, r = sqrt(dx dx + dy dy), r3 = r r r, m dq / r3), so every du_i has the same
-    bits as pleiades_source's.  The j == b term is computed on dummy operands and dropped by a select instead of a
-    `continue`, which keeps the seven terms in one basic block (they then overlap on the FP64 pipe)."""
+    b = (i - 14) % 7 along x (i < 21) or y, accumulated over the six other bodies j in ascending order with the
+    reference's operations (dx, dy, r = sqrt(dx dx + dy dy), r3 = r r r, m dq / r3), so every du_i has the same bits
+    as pleiades_source's.  The loop runs over k = 0..5 with j = k + (k >= b) — the reference's `j != i` skip without a
+    branch — so the six terms sit in one basic block and overlap on the FP64 pipe; the mass m = j + 1 is formed by an
+    exact floating-point increment instead of an int->double conversion per term."""
     T = _ty(f32)
     sq = "sqrtf" if f32 else "sqrt"
     suf = "f" if f32 else ""
@@ -114,16 +115,15 @@ def pleiades_component_source(f32=False, name="pleiades_rhs_i"):
             "  if (i < 14) return u[14 + i];\n"
             "  const int yaxis = (i >= 21);\n"
             "  const int b = i - (yaxis ? 21 : 14);\n"
+            "  const %(T)s xb = u[b], yb = u[7 + b];\n"
             "  %(T)s acc = 0.0%(s)s;\n"
-            "  for (int j = 0; j < 7; ++j) {\n"
-            "    const int self = (j == b);\n"
-            "    const %(T)s dx = u[j] - u[b], dy = u[7 + j] - u[7 + b];\n"
-            "    const %(T)s r2 = self ? 1.0%(s)s : dx * dx + dy * dy;\n"
-            "    const %(T)s r = %(sq)s(r2); const %(T)s r3 = r * r * r;\n"
-            "    const %(T)s m = (%(T)s)(j + 1);\n"
-            "    const %(T)s num = self ? 1.0%(s)s : m * (yaxis ? dy : dx);\n"
-            "    const %(T)s term = B200_DIV(num, r3);\n"
-            "    acc = self ? acc : acc + term;\n"
+            "  for (int k = 0; k < 6; ++k) {\n"
+            "    const int skip = (k >= b);\n"
+            "    const int j = k + skip;\n"
+            "    const %(T)s dx = u[j] - xb, dy = u[7 + j] - yb;\n"
+            "    const %(T)s r = %(sq)s(dx * dx + dy * dy); const %(T)s r3 = r * r * r;\n"
+            "    const %(T)s m = (%(T)s)(k + 1) + (skip ? 1.0%(s)s : 0.0%(s)s);\n"
+            "    acc = acc + B200_DIV(m * (yaxis ? dy : dx), r3);\n"
             "  }\n"
             "  return acc;\n"
             "}\n" % dict(T=T, name=name, s=suf, sq=sq)), name
