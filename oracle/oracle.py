@@ -112,11 +112,11 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
         return 0
     ss = 1 if (save_start is None or save_start) else 0
     se = 1 if (save_end is None or save_end) else 0
-    has_tf = (saveat[-1] == tf)
+    at_tf = sum(1 for s in saveat if s == tf)        # every copy of tf is skipped when save_end = false
     slots = ss + len(saveat)
-    if has_tf and not se:
-        slots -= 1
-    if not has_tf and se:
+    if at_tf and not se:
+        slots -= at_tf
+    if not at_tf and se:
         slots += 1
     return slots
 

@@ -85,7 +85,7 @@ def opt_save_idxs(idxs):
 EXPORTS = [
     "b200ode_create", "b200ode_destroy", "b200ode_last_error", "b200ode_version",
     "b200ode_compile", "b200ode_program_destroy", "b200ode_program_info",
-    "b200ode_compile_only", "b200ode_free", "b200ode_nslots", "b200ode_solve", "b200ode_solve_device",
+    "b200ode_compile_only", "b200ode_free", "b200ode_nslots", "b200ode_nslots_program", "b200ode_solve", "b200ode_solve_device",
     "b200ode_reduce_sum_device", "b200ode_timeseries_meanvar_device", "b200ode_solve_meanvar", "b200ode_host_register", "b200ode_host_unregister",
     "b200ode_measure_fma_peak", "b200ode_solve_everystep", "b200ode_solve_everystep_device",
     "b200ode_dense_eval_device", "b200ode_solve_dense", "b200ode_selftest_fastmath",
@@ -120,6 +120,7 @@ def lib():
     L.b200ode_free.argtypes = [vp]
     L.b200ode_free.restype = None
     L.b200ode_nslots.argtypes = [C.POINTER(B200Problem), C.POINTER(B200Opts)]
+    L.b200ode_nslots_program.argtypes = [vp, C.POINTER(B200Problem), C.POINTER(B200Opts)]
     L.b200ode_solve.argtypes = [vp, vp, C.POINTER(B200Problem), C.POINTER(B200Opts), C.POINTER(B200Result)]
     L.b200ode_solve_device.argtypes = [vp, vp, C.POINTER(B200DeviceProblem), C.POINTER(B200Opts),
                                        C.POINTER(B200DeviceResult), vp]

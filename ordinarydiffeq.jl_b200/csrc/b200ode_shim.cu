@@ -12,6 +12,7 @@
 #include <nvrtc.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -33,6 +34,8 @@ int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
+
+int nslots_typed(const B200Problem* prob, const B200Opts* o, int dtype);
 
 #define CUDA_TRY(expr)                                                                              \
     do {                                                                                            \
@@ -90,8 +93,10 @@ struct DevBuf {
 
 }  // namespace
 
+static const unsigned kCounterRing = 256;
 struct b200ode_handle_s {
     int device = 0;
+    std::atomic<unsigned> launch_seq{0};
     int num_sms = 0;
     cudaStream_t stream = nullptr;       // compute + H2D
     cudaStream_t copy_stream = nullptr;  // D2H of finished chunks
@@ -623,7 +628,7 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     P.save_start = (o->save_start != 0) ? 1 : 0;
     P.save_end = (o->save_end < 0) ? 1 : (o->save_end ? 2 : 0);
     B200Problem hp{}; hp.t0 = dp->t0; hp.tf = dp->tf;
-    P.nslots = (dr->us && !prog->everystep) ? b200ode_nslots(&hp, o) : 0;
+    P.nslots = (dr->us && !prog->everystep) ? nslots_typed(&hp, o, prog->dtype) : 0;
     P.row_offsets = row_offsets; P.ts_rag = (R*)ts_rag; P.dts_rag = (R*)dts_rag;
     P.tstops = nullptr; P.ntstops = 0;
     const bool want_tstops = o->tstops && o->ntstops > 0;
@@ -662,23 +667,27 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         }
         P.saveat = (const R*)h->saveat.ptr;
     }
-    CUDA_TRY(h->dt0.ensure(sizeof(R) * (size_t)N));
-    P.dt0 = (R*)h->dt0.ptr;
+    // Initial step sizes: b200_initdt writes them into the caller's t_final[] (each trajectory reads its own slot when it
+    // starts and overwrites it with t_final when it ends), so the launch owns no handle-level scratch and launches on
+    // different streams cannot disturb each other.
+    P.dt0 = (R*)dr->t_final;
     P.u_final = (R*)dr->u_final;
     if (dr->u_final_layout == B200ODE_LAYOUT_SOA) { P.uf_ts = 1; P.uf_cs = N; } else { P.uf_ts = n; P.uf_cs = 1; }
     P.t_final = (R*)dr->t_final;
     P.us = (R*)dr->us;
     P.naccept = dr->naccept; P.nreject = dr->nreject; P.nf = dr->nf; P.retcode = dr->retcode; P.nsaved = dr->nsaved;
     P.njacs = dr->njacs; P.nw = dr->nw; P.nsolve = dr->nsolve;
-    CUDA_TRY(h->counter.ensure(sizeof(unsigned long long)));
-    P.work_counter = (unsigned long long*)h->counter.ptr;
+    // work counter: one of a ring of kCounterRing counters per launch (zeroed on the launch's own stream), so up to
+    // kCounterRing launches may be in flight on one handle
+    CUDA_TRY(h->counter.ensure(sizeof(unsigned long long) * kCounterRing));
+    P.work_counter = (unsigned long long*)h->counter.ptr + (h->launch_seq.fetch_add(1) % kCounterRing);
     P.flags = o->flags;
     {   // tstop tolerance 100*eps(max(|t|,|tf|)) (integrator_utils.jl:277-286) is constant when |t0| <= |tf|
         const R at0 = std::fabs(P.t0), atf = std::fabs(P.tf);
         P.tol_const = !(at0 > atf) ? 1 : 0;
         P.tol100_tf = (R)100 * (std::nextafter(atf, std::numeric_limits<R>::infinity()) - atf);
     }
-    CUDA_TRY(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned long long), stream));
+    CUDA_TRY(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long), stream));
 
     if (!prog->adaptive && o->dt == 0.0 && !want_tstops)
         return fail(B200ODE_EINVAL, "Fixed timestep methods require a choice of dt or choosing the tstops");   // solve.jl:277-280
@@ -873,15 +882,26 @@ int b200ode_program_info(b200ode_program prog, B200ProgramInfo* info) {
     return B200ODE_OK;
 }
 
-int b200ode_nslots(const B200Problem* prob, const B200Opts* o) {
+// rows per trajectory as the KERNEL counts them: grid values and tf compared in the program's real type (a grid point
+// that rounds to (float)tf is the end point for an F32 program), and with save_end = false EVERY grid entry equal to tf
+// is skipped (skip_saveat_at_tspan_end), not just one
+}  // extern "C"
+namespace { int nslots_typed(const B200Problem* prob, const B200Opts* o, int dtype) {
     if (!prob || !o || !o->saveat || o->nsaveat <= 0) return 0;
-    int save_start = (o->save_start != 0) ? 1 : 0;
-    int save_end = (o->save_end != 0) ? 1 : 0;
-    bool grid_has_tf = (o->saveat[o->nsaveat - 1] == prob->tf);
+    const int save_start = (o->save_start != 0) ? 1 : 0;
+    const int save_end = (o->save_end != 0) ? 1 : 0;
+    auto is_tf = [&](double v) { return dtype == B200ODE_F32 ? ((float)v == (float)prob->tf) : (v == prob->tf); };
+    int at_tf = 0;
+    for (int i = 0; i < o->nsaveat; ++i) at_tf += is_tf(o->saveat[i]) ? 1 : 0;
     int slots = save_start + o->nsaveat;
-    if (grid_has_tf && !save_end) slots -= 1;          // skip_saveat_at_tspan_end
-    if (!grid_has_tf && save_end) slots += 1;          // solution_endpoint_match_cur_integrator!
+    if (at_tf > 0 && !save_end) slots -= at_tf;        // skip_saveat_at_tspan_end
+    if (at_tf == 0 && save_end) slots += 1;            // solution_endpoint_match_cur_integrator!
     return slots;
+} }  // namespace
+extern "C" {
+int b200ode_nslots(const B200Problem* prob, const B200Opts* o) { return nslots_typed(prob, o, B200ODE_F64); }
+int b200ode_nslots_program(b200ode_program prog, const B200Problem* prob, const B200Opts* o) {
+    return nslots_typed(prob, o, prog ? prog->dtype : B200ODE_F64);
 }
 
 int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
@@ -1219,7 +1239,7 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
     CUDA_TRY(cudaSetDevice(h->device));
     const int n = prog->n, np = prog->np;
     const size_t rs = prog->dtype == B200ODE_F32 ? 4 : 8;
-    const int nslots = (res->us || stats_only) ? b200ode_nslots(hp, o) : 0;
+    const int nslots = (res->us || stats_only) ? nslots_typed(hp, o, prog->dtype) : 0;
     cudaStream_t s = h->stream;
 
     CUDA_TRY(cudaEventRecord(h->ev0, s));
@@ -1330,7 +1350,8 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
         int k = 0;
         if (o->save_start != 0) res->ts[k++] = hp->t0;
         for (int i = 0; i < o->nsaveat && k < nslots; ++i) {
-            if (o->saveat[i] == hp->tf && o->save_end == 0) continue;
+            const bool at_tf = (rs == 8) ? (o->saveat[i] == hp->tf) : ((float)o->saveat[i] == (float)hp->tf);
+            if (at_tf && o->save_end == 0) continue;
             // the grid is stored in the program's real type
             res->ts[k++] = (rs == 8) ? o->saveat[i] : (double)(float)o->saveat[i];
         }
@@ -1542,7 +1563,7 @@ static int multi_run(b200ode_multi m, b200ode_multi_program mp, const B200Proble
     int rc = check_problem(N, hp->u0, hp->p, np, hp->t0, hp->tf, o);
     if (rc) return rc;
     if (!mean && (!res || !res->u_final)) return fail(B200ODE_EINVAL, "result.u_final is required");
-    const int nslots = b200ode_nslots(hp, o);
+    const int nslots = nslots_typed(hp, o, p0->dtype);
     const std::vector<ChunkPlan> plan = plan_chunks(N, ndev);
     std::vector<std::vector<double>> partial(plan.size());          // per-chunk sums for the ensemble mean
     std::vector<int> status(ndev, 0);

@@ -56,7 +56,12 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     prob.p = p_arr.ctypes.data if p_arr is not None else None
     prob.p_shared = int(p_shared)
     prob.t0, prob.tf = t0, tf
-    nslots = L.b200ode_nslots(C.byref(prob), C.byref(opts))
+    if getattr(program, "multi", False):
+        # (a MultiProgram holds one program per device; the F64 rule differs from the F32 one only for grid points
+        # within a float ulp of tf)
+        nslots = L.b200ode_nslots(C.byref(prob), C.byref(opts))
+    else:
+        nslots = L.b200ode_nslots_program(program._p, C.byref(prob), C.byref(opts))
     out = {} if out is None else out
 
     def buf(name, shape, dtype):

@@ -120,6 +120,8 @@ def test_nslots_agrees_with_rows_the_oracle_actually_saves(pkg):
             grid[-1] = 1.0                                   # grid ends at tf
         if trial % 4 == 1 and k > 1:
             grid[1] = grid[0]                                # duplicate point
+        if trial % 6 == 3 and k > 1:
+            grid[-2] = grid[-1] = 1.0                        # tf twice: save_end = false skips both copies
         for ss, se in itertools.product((None, True, False), repeat=2):
             n = ll.nslots_for((0.0, 1.0), grid, save_start=ss, save_end=se)
             o = oracle.solve(oracle.ALG_TSIT5, s, u0, None, (0.0, 1.0), 1, 0, saveat=grid, save_start=ss, save_end=se)
