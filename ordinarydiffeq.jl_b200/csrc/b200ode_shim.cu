@@ -74,6 +74,7 @@ struct Params {
     R* dts_rag;
     const R* tstops;
     int ntstops;
+    R fpe0, rfpe0;
 };
 
 struct DevBuf {
@@ -162,6 +163,20 @@ bool is_stiff_alg(int alg) {      // Rosenbrock-type: need jac + tgrad, report n
     return alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_ROSENBROCK32 || alg == B200ODE_ALG_RODAS5P ||
            alg == B200ODE_ALG_RODAS5PE ||
            (alg >= B200ODE_ALG_RODAS5 && alg <= B200ODE_ALG_RODAS4P2);
+}
+
+// alg_order of the reference (alg_utils.jl of each solver package)
+int alg_order(int alg) {
+    switch (alg) {
+        case B200ODE_ALG_TSIT5: case B200ODE_ALG_DP5: case B200ODE_ALG_RODAS5P: case B200ODE_ALG_RODAS5PE: case B200ODE_ALG_RODAS5: return 5;
+        case B200ODE_ALG_VERN6: return 6;
+        case B200ODE_ALG_VERN7: return 7;
+        case B200ODE_ALG_VERN8: return 8;
+        case B200ODE_ALG_VERN9: return 9;
+        case B200ODE_ALG_ROSENBROCK23: return 2;
+        case B200ODE_ALG_BS3: case B200ODE_ALG_ROSENBROCK32: return 3;
+        default: return 4;      // Rodas4, Rodas42, Rodas4P, Rodas4P2
+    }
 }
 
 // -DB200_SAVE_IDXS=i0,i1,...  -> number of listed components (0: option absent, -1: malformed / out of range)
@@ -686,6 +701,11 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         const R at0 = std::fabs(P.t0), atf = std::fabs(P.tf);
         P.tol_const = !(at0 > atf) ? 1 : 0;
         P.tol100_tf = (R)100 * (std::nextafter(atf, std::numeric_limits<R>::infinity()) - atf);
+    }
+    {   // controller start state: fastpower(qoldinit, beta2), beta2 = 2//(5 order) (4//100 for DP5) rounded to the real type
+        const R beta2 = (R)(prog->alg == B200ODE_ALG_DP5 ? 4.0 / 100.0 : 2.0 / (5.0 * alg_order(prog->alg)));
+        P.fpe0 = b200_fastpower((R)1e-4, beta2);
+        P.rfpe0 = (R)1 / P.fpe0;
     }
     CUDA_TRY(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned long long), stream));
 

@@ -171,8 +171,7 @@ B200_D void b200c_begin(const B200Params& P, long long idx, B200CTraj& T, int g)
     if (P.dt_user == (real)0) { T.dt = P.dt0[idx]; T.nf += 2; } else T.dt = P.dt_user;
     T.dtpropose = T.dt;
     T.q11 = (real)1; T.EEst = (real)1;
-    T.fpe = b200_fastpower((real)1e-4, B200_BETA2);
-    T.rfpe = (real)1 / T.fpe;
+    T.fpe = P.fpe0; T.rfpe = P.rfpe0;
     T.next_save = (P.nsaveat > 0) ? P.saveat[0] : b200_inf();
     T.naccept = 0; T.nreject = 0;
     T.accept = false; T.tstop_flag = false;

@@ -145,6 +145,9 @@ struct B200Params {
     // ascending, strictly inside (t0, tf), duplicates kept, tf appended last
     const real* tstops;
     int ntstops;
+    // fastpower(qoldinit = 1e-4, beta2) and its correctly rounded reciprocal: the controller state every trajectory
+    // starts from (setup_controller_cache, controllers.jl:793-803), computed once by the host
+    real fpe0, rfpe0;
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
@@ -440,11 +443,7 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
 #endif
     T.dtpropose = T.dt;
     T.q11 = (real)1; T.EEst = (real)1;                            // setup_controller_cache (controllers.jl:793-803)
-    {   // errold = qoldinit = 1e-4; only fastpower(errold, beta2) is ever used
-        const real beta2 = B200_BETA2;
-        T.fpe = b200_fastpower((real)1e-4, beta2);
-        T.rfpe = (real)1 / T.fpe;
-    }
+    T.fpe = P.fpe0; T.rfpe = P.rfpe0;       // errold = qoldinit = 1e-4; only fastpower(errold, beta2) is ever used
     T.next_save = (P.nsaveat > 0) ? P.saveat[0] : b200_inf();
 #if B200_TSTOPS
     T.tstop_idx = 0; T.tstop = P.tstops[0];
@@ -577,6 +576,8 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         // handle_callbacks! -> savevalues!
         {
             bool dense_ready = false;
+            real rdt = (real)0;         // refined 1/dt, shared by the rows of this step
+            if (T.next_save <= T.t) rdt = b200_rcp_refine(T.dt);
             while (T.next_save <= T.t) {
                 const real curt = T.next_save;
                 T.save_idx += 1;
@@ -587,10 +588,11 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                         dense_ready = true;
                     }
                     real th;
-                    {   // Θ = (curt - tprev) / dt: flagged fast division, plain operator in the (cold) flagged case
+                    {   // Θ = (curt - tprev) / dt: flagged fast division (divisor part hoisted), the plain IEEE
+                        // operation in the (cold, non-speculable) flagged case
                         bool bad = false;
-                        th = b200_div_fast(curt - T.tprev, T.dt, bad);
-                        if (bad) th = (curt - T.tprev) / T.dt;
+                        th = b200_div_rcp(curt - T.tprev, T.dt, rdt, bad);
+                        if (bad) th = b200_div_cold(curt - T.tprev, T.dt);
                     }
                     real out[B200_N];
                     T.st.interp(th, T.dt, T.uprev, T.u, out);
