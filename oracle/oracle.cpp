@@ -133,7 +133,8 @@ template <typename R> struct Fn {
 
 enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4, ALG_DP5 = 5, ALG_BS3 = 6,
        ALG_RODAS5 = 7, ALG_RODAS4 = 8, ALG_RODAS42 = 9, ALG_RODAS4P = 10, ALG_RODAS4P2 = 11,
-       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_RODAS5PE = 16, ALG_VERN7_GENERATED = 102 };
+       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_RODAS5PE = 16, ALG_AUTOTSIT5_ROS23 = 17,
+       ALG_VERN7_GENERATED = 102 };
 enum { RC_DEFAULT = 0, RC_SUCCESS = 1, RC_MAXITERS = 2, RC_DTLESSTHANMIN = 3, RC_UNSTABLE = 4, RC_DTNAN = 5 };
 
 template <typename R> struct Opts {
@@ -177,6 +178,7 @@ template <typename R> struct Tsit5 {
     static constexpr int order = 5;
     static constexpr bool is_rosenbrock = false;
     R k[7][ORACLE_MAXN];
+    R g6[ORACLE_MAXN];                // stage state of k6 (read by the composite algorithm's stiffness estimate)
     const ProblemFns<R>* P;
 
     void initialize(const R* uprev, const R* p, R t, Stats<R>& st) {
@@ -198,7 +200,7 @@ template <typename R> struct Tsit5 {
                 btilde5 = (R)0.5823571654525552, btilde6 = (R)-0.45808210592918697,
                 btilde7 = (R)0.015151515151515152;
         R *k1 = k[0], *k2 = k[1], *k3 = k[2], *k4 = k[3], *k5 = k[4], *k6 = k[5], *k7 = k[6];
-        R tmp[ORACLE_MAXN], g6[ORACLE_MAXN];
+        R tmp[ORACLE_MAXN];
         R a = dt * a21;
         // k2 = f(uprev + a*k1, p, t + c1*dt)
         for (int i = 0; i < n; ++i) tmp[i] = jl_fma(a, k1[i], uprev[i]);
@@ -278,6 +280,10 @@ template <typename R> struct Tsit5 {
 #if __has_include("oracle_rosenbrock.inc")
 #include "oracle_rosenbrock.inc"
 #define ORACLE_HAVE_ROSENBROCK 1
+#if __has_include("oracle_composite.inc")
+#include "oracle_composite.inc"
+#define ORACLE_HAVE_COMPOSITE 1
+#endif
 #endif
 
 // ---------------------------------------------------------------------------
@@ -351,6 +357,12 @@ template <typename A> struct PIBeta<A, std::void_t<decltype(A::beta2())>> {
     static double b1() { return A::beta1(); }
 };
 
+// CompositeAlgorithm (AutoTsit5(Rosenbrock23()), oracle_composite.inc): one PI controller cache per branch
+// (CompositeController, controllers.jl:1254-1338), choose_algorithm! in loopheader! (integrator_utils.jl:121),
+// do_error_check (composite_algs.jl:37-42, solve.jl:909)
+template <typename A, typename = void> struct IsComposite { static constexpr bool value = false; };
+template <typename A> struct IsComposite<A, std::void_t<decltype(A::is_composite)>> { static constexpr bool value = A::is_composite; };
+
 // One trajectory: __init + solve! + postamble!
 template <typename R, typename Alg>
 static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R tf, const Opts<R>& o, long long idx,
@@ -403,10 +415,27 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     // PIControllerCache (controllers.jl:793-803) and PIController defaults (alg_utils.jl)
     // beta2_default = 2//(5 order), beta1_default = 7//(10 order) (alg_utils.jl:766,788) unless the algorithm
     // overrides them (DP5); QT(rational) = correctly rounded quotient
-    const R beta2 = (R)PIBeta<Alg>::b2(), beta1 = (R)PIBeta<Alg>::b1();
+    constexpr bool composite = IsComposite<Alg>::value;
+    R beta2 = (R)0, beta1 = (R)0;
     const R qmin = (R)0.2, qmax = (R)10, gamma = (R)0.9, qoldinit = (R)1e-4, qmax_first_step = (R)10000;
-    const R qsteady_min = (R)1, qsteady_max = Alg::qsteady_max();
-    R q11 = (R)1, errold = qoldinit, EEst = (R)1;
+    const R qsteady_min = (R)1;
+    R qsteady_max = (R)1;
+    // PIControllerCache state, one per branch of a composite algorithm (q11 = 1, errold = qoldinit)
+    R q11_b[2] = {(R)1, (R)1}, errold_b[2] = {qoldinit, qoldinit};
+    R EEst = (R)1;
+    int br = 0;                       // branch whose controller cache is active (cache.current - 1)
+    bool do_error_check = true;
+    auto select_branch = [&]() {      // controller parameters of the active branch
+        if constexpr (composite) {
+            br = cache.current - 1;
+            beta2 = (R)cache.beta2_cur(); beta1 = (R)cache.beta1_cur(); qsteady_max = cache.qsteady_max_cur();
+        } else {
+            beta2 = (R)PIBeta<Alg>::b2(); beta1 = (R)PIBeta<Alg>::b1(); qsteady_max = Alg::qsteady_max();
+        }
+    };
+    select_branch();
+#define q11 q11_b[br]
+#define errold errold_b[br]
     long long iter = 0; int success_iter = 0, naccept = 0, nreject = 0;
     bool accept_step = false, next_step_tstop = false;
     R tstop_target = cur_tstop;
@@ -451,12 +480,16 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
             }
         }
         iter += 1;
+        if constexpr (composite) {      // choose_algorithm!(integrator, integrator.cache) (:121)
+            cache.choose_algorithm(dt, uprev, p, t, stats, do_error_check);
+            select_branch();
+        }
         // fix_dt_at_bounds! (:1243-1256); timedepentdtmin = max(eps(t), dtmin)
         dt = jl_min(dtmax, dt);
         dt = jl_max(dt, jl_max(jl_eps(t), opts_dtmin));
         modify_dt_for_tstops();
-        // ---- check_error (lib/DiffEqBase/src/check_error.jl:70-118)
-        {
+        // ---- check_error (lib/DiffEqBase/src/check_error.jl:70-118); `integrator.do_error_check &&` (solve.jl:909)
+        if (do_error_check) {
             int code = RC_SUCCESS;
             if (std::isnan(dt)) code = RC_DTNAN;
             else if (iter > o.maxiters) code = RC_MAXITERS;
@@ -474,6 +507,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
             EEst = cache.perform_step(uprev, u, p, t, dt, o, stats, o.nsaveat > 0 || out.dense_sink != nullptr);   // calck (solve.jl:147-148)
         }
         // ---- loopfooter! (:597-677)
+        do_error_check = true;
         R ttmp = t + dt;
         R q = (R)1;
         if (o.adaptive) {
@@ -548,6 +582,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     if (out.nw) out.nw[idx] = stats.nw;
     if (out.nsolve) out.nsolve[idx] = stats.nsolve;
     if (out.retcode) out.retcode[idx] = retcode;
+#undef q11
+#undef errold
 }
 
 template <typename R, typename Alg>
@@ -682,6 +718,9 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         case ALG_RODAS42: solve_batch<R, Rodas42<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P: solve_batch<R, Rodas4P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P2: solve_batch<R, Rodas4P2<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+#endif
+#ifdef ORACLE_HAVE_COMPOSITE
+        case ALG_AUTOTSIT5_ROS23: solve_batch<R, AutoTsit5Ros23<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #endif
 #ifdef ORACLE_HAVE_VERNER_GEN
         case ALG_VERN6: solve_batch<R, Vern6<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;

@@ -161,7 +161,7 @@ bool is_identifier(const char* s) {
 
 bool is_stiff_alg(int alg) {      // Rosenbrock-type: need jac + tgrad, report njacs/nw/nsolve
     return alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_ROSENBROCK32 || alg == B200ODE_ALG_RODAS5P ||
-           alg == B200ODE_ALG_RODAS5PE ||
+           alg == B200ODE_ALG_RODAS5PE || alg == B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 ||
            (alg >= B200ODE_ALG_RODAS5 && alg <= B200ODE_ALG_RODAS4P2);
 }
 
@@ -169,6 +169,7 @@ bool is_stiff_alg(int alg) {      // Rosenbrock-type: need jac + tgrad, report n
 int alg_order(int alg) {
     switch (alg) {
         case B200ODE_ALG_TSIT5: case B200ODE_ALG_DP5: case B200ODE_ALG_RODAS5P: case B200ODE_ALG_RODAS5PE: case B200ODE_ALG_RODAS5: return 5;
+        case B200ODE_ALG_AUTOTSIT5_ROSENBROCK23: return 5;      // the branch a trajectory starts in (Tsit5)
         case B200ODE_ALG_VERN6: return 6;
         case B200ODE_ALG_VERN7: return 7;
         case B200ODE_ALG_VERN8: return 8;
@@ -201,7 +202,7 @@ int parse_save_idxs(const char* extra_options, int n) {
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                           const char* jac_src, const char* jac_name, const char* tgrad_src,
                           const char* tgrad_name) {
-    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS5PE)
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_AUTOTSIT5_ROSENBROCK23)
         return fail(B200ODE_EINVAL, "alg must be one of the B200ODE_ALG_* constants");
     if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
     if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");
@@ -248,6 +249,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         case B200ODE_ALG_VERN8: call_sites += 21; break;
         case B200ODE_ALG_VERN9: call_sites += 26; break;
         case B200ODE_ALG_ROSENBROCK23: case B200ODE_ALG_ROSENBROCK32: call_sites += 3; break;
+        case B200ODE_ALG_AUTOTSIT5_ROSENBROCK23: call_sites += 12; break;
         case B200ODE_ALG_RODAS5P: case B200ODE_ALG_RODAS5PE: case B200ODE_ALG_RODAS5: call_sites += 8; break;
         default: call_sites += 6; break;
     }
@@ -361,7 +363,8 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     if (!has_minb) {
         // registers available per thread at k CTAs of 128 threads: 65536/(128k)
         int minb = 4;
-        if (stiff) minb = (words <= 8) ? ((alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_ROSENBROCK32) ? 5 : 4) : 1;   // measured (scripts/sweep_rober.py)
+        if (alg == B200ODE_ALG_AUTOTSIT5_ROSENBROCK23) minb = (words <= 8) ? 3 : 1;
+        else if (stiff) minb = (words <= 8) ? ((alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_ROSENBROCK32) ? 5 : 4) : 1;   // measured (scripts/sweep_rober.py)
         else if (alg == B200ODE_ALG_VERN7 || alg == B200ODE_ALG_VERN6 || alg == B200ODE_ALG_VERN8 || alg == B200ODE_ALG_VERN9)
             minb = (words <= 6) ? (alg == B200ODE_ALG_VERN9 ? 2 : 3) : 1;
         else minb = (words <= 8) ? 4 : (words <= 16 ? 2 : 1);
@@ -854,7 +857,8 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&prog->k_initdt, prog->lib, "b200_initdt");
-    if (e == cudaSuccess && prog->everystep && prog->nsave == n && alg != B200ODE_ALG_ROSENBROCK32)
+    if (e == cudaSuccess && prog->everystep && prog->nsave == n && alg != B200ODE_ALG_ROSENBROCK32 &&
+        alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23)
         e = cudaLibraryGetKernel(&prog->k_dense, prog->lib, "b200_dense_eval");
     if (e != cudaSuccess) {
         cudaLibraryUnload(prog->lib); delete prog;
@@ -1207,7 +1211,7 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
     if (rc) return rc;
     if (o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "dense output excludes saveat (dense = save_everystep && isempty(saveat), solve.jl:139)");
     if (o->save_start == 0) return fail(B200ODE_EINVAL, "dense output needs save_start");
-    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs or for Rosenbrock32 (its stages are not recomputable from the saved rows)");
+    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows) or for the composite algorithm");
     for (int j = 1; j < nq; ++j) if (!(tq[j] >= tq[j - 1])) return fail(B200ODE_EINVAL, "tq must be ascending");
     const long long N = hp->trajectories;
     if (N == 0) return B200ODE_OK;

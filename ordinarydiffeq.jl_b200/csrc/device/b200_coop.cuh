@@ -264,10 +264,10 @@ B200_D bool b200c_iterate(const B200Params& P, long long idx, B200CTraj& T, bool
         B200Ctl ctl;
         {
             bool bad = false;
-            ctl = b200_controller_t<true>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, bad);
+            ctl = b200_controller_t<true>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, bad, b200_ctl_cfg_static());
             if (bad) {
                 bool unused = false;
-                ctl = b200_controller_t<false>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, unused);
+                ctl = b200_controller_t<false>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, unused, b200_ctl_cfg_static());
             }
         }
         T.q11 = ctl.q11;

@@ -21,7 +21,8 @@
 //   B200_N, B200_NP      state / parameter dimension
 //   B200_F32             0: double, 1: float
 //   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3,
-//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9, 15 Rosenbrock32, 16 Rodas5Pe
+//                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9, 15 Rosenbrock32, 16 Rodas5Pe,
+//                        17 AutoTsit5(Rosenbrock23())
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -44,8 +45,11 @@
 #define B200_ALG_VERN9 14
 #define B200_ALG_ROS32 15
 #define B200_ALG_RODAS5PE 16
+#define B200_ALG_AUTOTSIT5_ROS23 17
+#define B200_COMPOSITE (B200_ALG == B200_ALG_AUTOTSIT5_ROS23)
 #define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || B200_ALG == B200_ALG_RODAS5PE || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
-#define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32 || B200_IS_RODAS)
+// (the composite algorithm counts as Rosenbrock-type here: it needs jac/tgrad and reports njacs / nw / nsolve)
+#define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32 || B200_IS_RODAS || B200_COMPOSITE)
 
 #ifndef B200_COOP
 #define B200_COOP 0           // 1: lane-group kernel (b200_coop.cuh): B200_L lanes per trajectory, component-form RHS
@@ -63,6 +67,10 @@ typedef B200Tsit5 B200Stepper;
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_vern7.cuh"
 typedef B200Vern7 B200Stepper;
+#elif B200_COMPOSITE
+#define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
+#include "b200_composite.cuh"
+typedef B200AutoTsit5Ros23 B200Stepper;
 #elif B200_IS_ROSENBROCK
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_rosenbrock.cuh"
@@ -292,11 +300,19 @@ extern "C" __global__ void __launch_bounds__(256) b200_initdt(B200Params P) {
 // fastpower calls share fastlog2(Float32(EEst)) whenever errold == EEst.  FAST = flagged branch-free math
 // (b200_base.cuh); the caller repeats the block with FAST = false if the flag comes back set.
 struct B200Ctl { real q11, fpe, rfpe, dtdiv, num; bool accept; };
+// PI parameters that depend on the algorithm (compile-time constants except for a composite algorithm, whose
+// branches bring their own: CompositeController, controllers.jl:1254-1338)
+struct B200CtlCfg { real beta1, beta2, qsteady_min, qsteady_max; };
+B200_D B200CtlCfg b200_ctl_cfg_static() {
+    B200CtlCfg c; c.beta1 = B200_BETA1; c.beta2 = B200_BETA2;
+    c.qsteady_min = B200Stepper::qsteady_min(); c.qsteady_max = B200Stepper::qsteady_max();
+    return c;
+}
 template <bool FAST>
 B200_D B200Ctl b200_controller_t(real EEst, real q11_old, real fpe, real rfpe, real dt, real dtpropose, bool tstop_flag,
-                                 bool first, bool& bad) {
+                                 bool first, bool& bad, const B200CtlCfg cfg) {
     const real qmin = (real)0.2, qmax = (real)10, gamma = (real)0.9;
-    const real beta1 = B200_BETA1, beta2 = B200_BETA2;
+    const real beta1 = cfg.beta1, beta2 = cfg.beta2;
     B200Ctl c;
     const real qmax_eff = first ? (real)10000 : qmax;
     // fastpower(EEst, beta1) and fastpower(max(EEst, 1e-4), beta2) from one logarithm
@@ -321,7 +337,7 @@ B200_D B200Ctl b200_controller_t(real EEst, real q11_old, real fpe, real rfpe, r
     c.q11 = zero ? q11_old : q11;
     c.accept = (EEst <= (real)1);
     // step_accept_controller!: qsteady window
-    const real qa = (B200Stepper::qsteady_min() <= q && q <= B200Stepper::qsteady_max()) ? (real)1 : q;
+    const real qa = (cfg.qsteady_min <= q && q <= cfg.qsteady_max) ? (real)1 : q;
     // step_reject_controller!: dt /= min(inv(qmin), q11/gamma)
     const real qr = b200_min_c((real)1 / qmin, B200Math<FAST>::divc(c.q11, gamma, (real)1 / gamma, bad));
     // accepted steps divide the un-clipped dt (integrator_utils.jl:629-633 restores it first)
@@ -344,6 +360,9 @@ struct B200Traj {
     real t, tprev, dt, dtpropose;
     real q11, EEst;
     real fpe, rfpe;             // fastpower(errold, beta2) and its correctly rounded reciprocal (see iterate)
+#if B200_COMPOSITE
+    real q11_o, fpe_o, rfpe_o;  // the PI cache of the branch that is not running (swapped in when the algorithm switches)
+#endif
     real next_save;             // saveat[save_idx] (or +Inf when the grid is exhausted)
     int naccept, nreject, nf;      // iter = naccept+nreject(+1), success_iter = naccept (see iterate)
     int save_idx, nsaved;
@@ -444,6 +463,12 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     T.dtpropose = T.dt;
     T.q11 = (real)1; T.EEst = (real)1;                            // setup_controller_cache (controllers.jl:793-803)
     T.fpe = P.fpe0; T.rfpe = P.rfpe0;       // errold = qoldinit = 1e-4; only fastpower(errold, beta2) is ever used
+#if B200_COMPOSITE
+    // the stiff branch's own PIControllerCache (q11 = 1, errold = qoldinit, beta2 = 2//(5*2))
+    T.q11_o = (real)1;
+    T.fpe_o = b200_fastpower((real)1e-4, (real)(2.0 / 10.0));
+    T.rfpe_o = (real)1 / T.fpe_o;
+#endif
     T.next_save = (P.nsaveat > 0) ? P.saveat[0] : b200_inf();
 #if B200_TSTOPS
     T.tstop_idx = 0; T.tstop = P.tstops[0];
@@ -492,6 +517,15 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         // (rejected step: step_reject_controller!'s dt /= min(inv(qmin), q11/gamma) was applied by the loopfooter
         //  that rejected it — one shared division, see b200_controller_t)
     }
+#if B200_COMPOSITE
+    // choose_algorithm!(integrator, integrator.cache) (integrator_utils.jl:121): after iter += 1, before the dt bounds
+    if (T.st.choose(T.dt, T.uprev, T.p, T.t, T.nf)) {
+        real x;
+        x = T.q11; T.q11 = T.q11_o; T.q11_o = x;
+        x = T.fpe; T.fpe = T.fpe_o; T.fpe_o = x;
+        x = T.rfpe; T.rfpe = T.rfpe_o; T.rfpe_o = x;
+    }
+#endif
     // fix_dt_at_bounds!
     T.dt = b200_min_c(P.dtmax, T.dt);
     T.dt = b200_max_c(dtmin_t, T.dt);
@@ -513,7 +547,12 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #pragma unroll
     for (int c = 0; c < B200_N; ++c) bad = bad | !b200_isfinite(T.u[c]);
     const bool c_inf = T.accept & bad;
+#if B200_COMPOSITE
+    // `integrator.do_error_check && check_error!(integrator)` (solve.jl:909); loopfooter! sets the flag again
+    const bool ok = !(T.st.do_error_check & (c_nan | c_max | c_min | c_uns | c_inf));
+#else
     const bool ok = !(c_nan | c_max | c_min | c_uns | c_inf);
+#endif
     if (!ok)
         T.retcode = c_nan ? B200_RC_DTNAN : (c_max ? B200_RC_MAXITERS : (c_min ? B200_RC_DTLESSTHANMIN : B200_RC_UNSTABLE));
     // ---- perform_step! / handle_tstop_step! ----
@@ -540,11 +579,18 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     real q = (real)1;
     B200Ctl ctl;
     {
+#if B200_COMPOSITE
+        B200CtlCfg cfg;
+        cfg.beta1 = T.st.beta1(); cfg.beta2 = T.st.beta2(); cfg.qsteady_min = (real)1; cfg.qsteady_max = T.st.qsteady_max_cur();
+        T.st.do_error_check = true;                 // loopfooter! (integrator_utils.jl:599)
+#else
+        const B200CtlCfg cfg = b200_ctl_cfg_static();
+#endif
         bool bad = false;
-        ctl = b200_controller_t<true>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, bad);
+        ctl = b200_controller_t<true>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, bad, cfg);
         if (bad) {      // cold, inline
             bool unused = false;
-            ctl = b200_controller_t<false>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, unused);
+            ctl = b200_controller_t<false>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, unused, cfg);
         }
     }
     T.q11 = ctl.q11;
@@ -768,7 +814,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
 }
 // (rows restricted by save_idxs cannot restart a step; Rosenbrock32's fsalfirst is f(uprev + dt k2) of the previous
 // step, not f of the saved row, so its stages are not recomputable from (row, dt) either)
-#if B200_EVERYSTEP && !defined(B200_SAVE_IDXS) && B200_ALG != B200_ALG_ROS32
+#if B200_EVERYSTEP && !defined(B200_SAVE_IDXS) && B200_ALG != B200_ALG_ROS32 && !B200_COMPOSITE
 // ---------------------------------------------------------------------------
 // sol(tq) for every trajectory, post hoc, from the ragged per-step rows — ode_interpolation
 // (dense/generic_dense.jl:833-867: interval search :845-849, dt = ts[i+] - ts[i-], Θ :858-859,

@@ -57,8 +57,9 @@ struct B200Tsit5 {
     }
 
     // one attempted step; returns EEst
+    // g6out (optional): receives the stage state of k6, which the composite algorithm's stiffness estimate reads
     B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt,
-                        real reltol, real abstol, int& nf) {
+                        real reltol, real abstol, int& nf, real* g6out = nullptr) {
         const real c1 = B200_TSIT5_C.c1, c2 = B200_TSIT5_C.c2, c3 = B200_TSIT5_C.c3, c4 = B200_TSIT5_C.c4;
 #define B200_T5(name) const real name = B200_TSIT5_C.name
         B200_T5(a21); B200_T5(a31); B200_T5(a32); B200_T5(a41); B200_T5(a42); B200_T5(a43);
@@ -92,6 +93,10 @@ struct B200Tsit5 {
                                        b200_fma(a64, k4[i], b200_fma(a63, k3[i], b200_fma(a62, k2[i], a61 * k1[i])))),
                               uprev[i]);
         B200_RHS(k6, tmp, p, t + dt);
+        if (g6out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) g6out[i] = tmp[i];
+        }
 #pragma unroll
         for (int i = 0; i < B200_N; ++i)
             u[i] = b200_fma(dt,

@@ -95,6 +95,21 @@ class BS3(_Alg):
     alg_id, order = _lib.ALG_BS3, 3
 
 
+def AutoTsit5(stiff_alg):
+    """AutoTsit5(Rosenbrock23()) = AutoAlgSwitch(Tsit5(), stiff_alg) with the default AutoSwitch parameters
+    (lib/OrdinaryDiffEqTsit5/src/algorithms.jl:27-33, lib/OrdinaryDiffEqCore/src/composite_algs.jl:4-15)."""
+    if not isinstance(stiff_alg, Rosenbrock23):
+        raise NotImplementedError("AutoTsit5 is available with Rosenbrock23() as the stiff algorithm")
+    return _AutoTsit5Rosenbrock23()
+
+
+class _AutoTsit5Rosenbrock23(_Alg):
+    alg_id, order, stiff = _lib.ALG_AUTOTSIT5_ROSENBROCK23, 5, True
+
+    def __repr__(self):
+        return "AutoTsit5(Rosenbrock23())"
+
+
 class EnsembleAlgorithm:
     pass
 

@@ -956,3 +956,66 @@ def test_lane_group_kernel_other_shapes(pkg, handle, oracle):
         assert_same_result(g, o32)
     finally:
         prog.close()
+
+
+# ---- AutoTsit5(Rosenbrock23()): per-trajectory switching between Tsit5 and Rosenbrock23 ------------------------------
+def _vdp_mixed_params(pl, N, f32):
+    """Van der Pol with mu spread over [0.5, 500]: the ensemble holds trajectories that never leave Tsit5, trajectories
+    that switch to Rosenbrock23 for good and trajectories that switch back and forth."""
+    mu = 0.5 * (1000.0 ** pl.splitmix64_uniform(np.arange(N, dtype=np.uint64), 0))
+    return mu.reshape(N, 1).astype(np.float32 if f32 else np.float64)
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_autotsit5_rosenbrock23_parity(pkg, handle, oracle, f32):
+    pl = pkg.problems_library
+    r, j, tg, n, np_, u0, _ = pl.stiff_sources("vdp", f32)
+    N = 512
+    p = _vdp_mixed_params(pl, N, f32)
+    tspan = (0.0, 20.0)
+    prog = handle.compile(pkg.ALG_AUTOTSIT5_ROSENBROCK23, pkg.F32 if f32 else pkg.F64, n, np_, r[0], r[1], j[0], j[1],
+                          tg[0], tg[1])
+    try:
+        for kw in ({}, {"saveat": [0.5 * k for k in range(1, 41)]}, {"reltol": 1e-6, "abstol": 1e-8}):
+            if f32 and "reltol" in kw:
+                continue
+            g = pkg.lowlevel.solve_host(prog, u0, p, tspan, **kw)
+            o = oracle.solve(oracle.ALG_AUTOTSIT5_ROSENBROCK23, r, u0, p, tspan, n, np_, f32=f32, jac=j, tgrad=tg,
+                             linsolve=1, **kw)
+            assert_same_result(g, o)
+            assert (g["retcode"] == 1).all()
+            # the ensemble really is mixed: some trajectories never build a W, some do
+            assert (g["njacs"] == 0).any() and (g["njacs"] > 0).any()
+        # a non-stiff ensemble never switches: identical to plain Tsit5 except for nothing at all
+        pn = np.full((64, 1), 0.5, dtype=p.dtype)
+        g = pkg.lowlevel.solve_host(prog, u0, pn, (0.0, 5.0))
+        t5 = oracle.solve(oracle.ALG_TSIT5, r, u0, pn, (0.0, 5.0), n, np_, f32=f32)
+        assert (g["njacs"] == 0).all()
+        assert np.array_equal(bits(g["u_final"]), bits(t5["u_final"])) and np.array_equal(g["nf"], t5["nf"])
+    finally:
+        prog.close()
+
+
+def test_autotsit5_robertson_and_everystep(pkg, handle, oracle):
+    pl = pkg.problems_library
+    r, j, tg = pl.robertson_sources()
+    p = pl.robertson_params(512)
+    prog = handle.compile(pkg.ALG_AUTOTSIT5_ROSENBROCK23, pkg.F64, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1])
+    try:
+        g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 1e5), reltol=1e-6, abstol=1e-8, saveat=[1.0, 100.0, 1e4])
+        o = oracle.solve(oracle.ALG_AUTOTSIT5_ROSENBROCK23, r, U0, p, (0.0, 1e5), 3, 3, jac=j, tgrad=tg, reltol=1e-6,
+                         abstol=1e-8, saveat=[1.0, 100.0, 1e4])
+        assert_same_result(g, o)
+        assert (g["retcode"] == 1).all() and (g["njacs"] > 0).all()
+    finally:
+        prog.close()
+    prog = _everystep_prog(pkg, handle, pkg.ALG_AUTOTSIT5_ROSENBROCK23, False, "robertson")
+    try:
+        g = pkg.lowlevel.solve_host_everystep(prog, U0, p, (0.0, 100.0), reltol=1e-6, abstol=1e-8, saveat=[1.0, 50.0])
+        o = oracle.solve(oracle.ALG_AUTOTSIT5_ROSENBROCK23, r, U0, p, (0.0, 100.0), 3, 3, jac=j, tgrad=tg, reltol=1e-6,
+                         abstol=1e-8, saveat=[1.0, 50.0], save_everystep=True)
+        _assert_same_ragged(g, o)
+        with pytest.raises(pkg.B200Error):      # no dense output for the composite algorithm
+            pkg.lowlevel.solve_host_dense(prog, U0, p, (0.0, 100.0), [1.0, 2.0])
+    finally:
+        prog.close()

@@ -747,3 +747,54 @@ def test_reference_static_array_stiff_systems_succeed(pkg, problem):
     tight = oracle.solve(oracle.ALG_RODAS5P, r, u0, p, tspan, n, np_, jac=j, tgrad=tg, reltol=1e-10, abstol=1e-12)["u_final"][0]
     for s in sols:
         assert np.abs(s - tight).max() <= 5e-2 * max(1.0, np.abs(tight).max())
+
+
+# ---- AutoTsit5(Rosenbrock23()) ----------------------------------------------------------------------------------------
+def _vdp_sources():
+    import b200_import
+    pl = b200_import.load().problems_library
+    return pl.stiff_sources("vdp")
+
+
+def test_autotsit5_switches_back_and_forth_on_van_der_pol():
+    # test/InterfaceI/stiffness_detection_test.jl:18-43: Van der Pol, u0 = [2, 0], tspan (0, 6), mu = inv(0.003),
+    # solve(prob, AutoTsit5(Rosenbrock23()), maxiters = 1000) must use BOTH algorithms more than 5 times
+    # (is_switching_fb) and, therefore, finish within the 1000 iterations.  nw counts the Rosenbrock23 attempts.
+    r, j, tg, n, np_, _, _ = _vdp_sources()
+    u0 = np.array([2.0, 0.0])
+    p = np.array([[1.0 / 0.003]])
+    o = oracle.solve(oracle.ALG_AUTOTSIT5_ROSENBROCK23, r, u0, p, (0.0, 6.0), n, np_, jac=j, tgrad=tg, maxiters=1000)
+    attempts = int(o["naccept"][0] + o["nreject"][0])
+    stiff_attempts = int(o["nw"][0])
+    assert o["retcode"][0] == 1 and attempts <= 1000
+    assert stiff_attempts > 5 and attempts - stiff_attempts > 5
+    # accuracy against a tight Rodas5P solve
+    ref = oracle.solve(oracle.ALG_RODAS5P, r, u0, p, (0.0, 6.0), n, np_, jac=j, tgrad=tg, reltol=1e-10, abstol=1e-12)
+    tight = oracle.solve(oracle.ALG_AUTOTSIT5_ROSENBROCK23, r, u0, p, (0.0, 6.0), n, np_, jac=j, tgrad=tg, reltol=1e-7, abstol=1e-9)
+    assert np.abs(tight["u_final"] - ref["u_final"]).max() < 1e-3
+
+
+def test_autotsit5_is_tsit5_while_nothing_is_stiff_and_rosenbrock23_like_on_robertson():
+    import b200_import
+    pl = b200_import.load().problems_library
+    r, j, tg, n, np_, u0, _ = _vdp_sources()
+    p = np.array([[0.5], [1.0]])
+    a = oracle.solve(oracle.ALG_AUTOTSIT5_ROSENBROCK23, r, u0, p, (0.0, 5.0), n, np_, jac=j, tgrad=tg, saveat=[1.0, 2.5])
+    b = oracle.solve(oracle.ALG_TSIT5, r, u0, p, (0.0, 5.0), n, np_, saveat=[1.0, 2.5])
+    for k in ("naccept", "nreject", "nf"):
+        assert np.array_equal(a[k], b[k])
+    assert np.array_equal(a["us"], b["us"]) and (a["njacs"] == 0).all()
+    # Robertson: the stiff branch takes over after a few steps; step counts stay in Rosenbrock23's range
+    rr, jj, tt = pl.robertson_sources()
+    pr = pl.robertson_params(4)
+    u0r = np.array([1.0, 0.0, 0.0])
+    c = oracle.solve(oracle.ALG_AUTOTSIT5_ROSENBROCK23, rr, u0r, pr, (0.0, 1e5), 3, 3, jac=jj, tgrad=tt, reltol=1e-6, abstol=1e-8)
+    d = oracle.solve(oracle.ALG_ROSENBROCK23, rr, u0r, pr, (0.0, 1e5), 3, 3, jac=jj, tgrad=tt, reltol=1e-6, abstol=1e-8)
+    assert (c["retcode"] == 1).all()
+    assert (np.abs(c["naccept"] - d["naccept"]) < 0.1 * d["naccept"]).all()
+    assert np.abs(c["u_final"] - d["u_final"]).max() < 1e-5
+    # nf: 1 (pre-start) + 2 (initdt) + 6 per Tsit5 attempt + 2 per Rosenbrock23 attempt + 1 per switch
+    att = c["naccept"] + c["nreject"]
+    ros = c["nw"]
+    switches = c["nf"] - (3 + 6 * (att - ros) + 2 * ros)
+    assert (switches >= 1).all() and (switches <= 3).all()
