@@ -36,6 +36,7 @@
 #endif
 
 #define ORACLE_MAXN 64
+#define ORACLE_MAXNP 256
 
 // ---------------------------------------------------------------------------
 // Julia Base scalar helpers
@@ -133,9 +134,76 @@ template <typename R> struct Fn {
 
 enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4, ALG_DP5 = 5, ALG_BS3 = 6,
        ALG_RODAS5 = 7, ALG_RODAS4 = 8, ALG_RODAS42 = 9, ALG_RODAS4P = 10, ALG_RODAS4P2 = 11,
-       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_RODAS5PE = 16, ALG_AUTOTSIT5_ROS23 = 17,
+       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_RODAS5PE = 16, ALG_AUTOTSIT5_ROS23 = 17, ALG_RODAS3P = 18,
        ALG_VERN7_GENERATED = 102 };
 enum { RC_DEFAULT = 0, RC_SUCCESS = 1, RC_MAXITERS = 2, RC_DTLESSTHANMIN = 3, RC_UNSTABLE = 4, RC_DTNAN = 5 };
+
+// One callback of the CallbackSet.  condition: R f(const R* u, const R* p, R t); affect: void f(R* u, R* p, R t, int* terminate)
+// (the C rendering of condition(u, t, integrator) / affect!(integrator); *terminate = 1 is terminate!(integrator)).
+struct OracleCallback {
+    int kind;                 // 0 DiscreteCallback, 1 ContinuousCallback
+    void* condition;
+    void* affect;             // NULL: nothing
+    void* affect_neg;         // continuous only; NULL: nothing
+    int rootfind;             // 0 NoRootFind, 1 LeftRootFind (default), 2 RightRootFind
+    int interp_points;        // default 10
+    double abstol;            // default 10eps(Float64)
+    double repeat_nudge;      // default 1//100
+    int save_before, save_after;   // save_positions
+};
+enum { RC_TERMINATED = 6 };
+
+// Element i (1-based) of range(start, stop = stop, length = len) for IEEE floats — Base._linspace + the twice-precision
+// getindex (Julia Base twiceprecision.jl, EXT).  The rational shortcut Base.range takes for "simple" end points is not
+// reproduced; the sample points only bracket sign changes, so a last-bit difference cannot move an event unless its
+// root lies within an ulp of a sample point.
+template <typename R> struct JlLinspace {
+    R ref_hi, ref_lo, step_hi, step_lo; long long offset, len;
+    static void add12(R x, R y, R& hi, R& lo) {
+        if (std::fabs(y) > std::fabs(x)) std::swap(x, y);
+        hi = x + y; lo = (x - hi) + y;
+    }
+    static R truncbits(R x, int nb) {
+        typename Bits<R>::U m = ~(typename Bits<R>::U)0;
+        return Bits<R>::from(Bits<R>::to(x) & (m << nb));
+    }
+    JlLinspace(R start, R stop, long long len_) : len(len_) {
+        R delta = stop - start;                                   // (finite end points, no overflow handling)
+        R tmin = -(start / delta);
+        // imin = round(Int, tmin*(len-1)+1) (ties to even); clamp before the conversion
+        R timin = std::nearbyint(tmin * (R)(len - 1) + (R)1);
+        long long imin = timin <= (R)1 ? 1 : (timin >= (R)len ? len : (long long)timin);
+        R ref, step;
+        if (1 < imin && imin < len) {
+            double t = (double)(imin - 1) / (double)(len - 1);
+            ref = (R)((1 - t) * (double)start + t * (double)stop);
+            step = (imin - 1 < len - imin) ? (ref - start) / (R)(imin - 1) : (stop - ref) / (R)(len - imin);
+        } else if (imin <= 1) { imin = 1; ref = start; step = delta / (R)(len - 1); }
+        else { imin = len; ref = stop; step = delta / (R)(len - 1); }
+        const R m = std::nextafter(std::numeric_limits<R>::max(), (R)0);
+        const R k = (R)std::max(imin - 1, len - imin);
+        const R lo = std::max(-(m + ref) / k, (-m + ref) / k), hi = std::min((m - ref) / k, (m + ref) / k);
+        R step_pre = step < lo ? lo : (step > hi ? hi : step);
+        const int prec_half = std::is_same<R, float>::value ? 12 : 27;         // cld(precision(T), 2)
+        long long mx = std::max(imin - 1, len - imin);
+        int nbl = len < 2 ? 0 : (int)std::ceil(std::log2((double)mx)) + 1;
+        const int nb = std::min(prec_half, nbl);
+        step_hi = truncbits(step_pre, nb);
+        R x1h, x1l, x2h, x2l;
+        add12((R)(1 - imin) * step_hi, ref, x1h, x1l);
+        add12((R)(len - imin) * step_hi, ref, x2h, x2l);
+        R a = (start - x1h) - x1l, b = (stop - x2h) - x2l;
+        step_lo = (b - a) / (R)(len - 1);
+        ref_hi = ref; ref_lo = a - (R)(1 - imin) * step_lo;
+        offset = imin;
+    }
+    R operator[](long long i) const {
+        const R u = (R)(i - offset);
+        const R sh = u * step_hi, sl = u * step_lo;
+        R xh, xl; add12(ref_hi, sh, xh, xl);
+        return xh + (xl + (sl + ref_lo));
+    }
+};
 
 template <typename R> struct Opts {
     R reltol, abstol, dt, dtmin, dtmax;
@@ -147,6 +215,8 @@ template <typename R> struct Opts {
     // opts.tstops as initialize_tstops builds it (solve.jl:1021-1040): ascending, inside (t0, tf), tf last; NULL: {tf}
     const R* tstops = nullptr; int ntstops = 0;
     bool adaptive = true;          // false: fixed dt = opts.dt (dtcache), every step accepted
+    // callbacks (CallbackSet: continuous callbacks first, then discrete ones, each group in the order given)
+    const struct OracleCallback* cbs = nullptr; int ncb = 0;
 };
 
 // ODE_DEFAULT_NORM(u::StaticArray, t) = sqrt_fast(real(sum(abs2,u)) / max(length(u),1))
@@ -238,6 +308,41 @@ template <typename R> struct Tsit5 {
     }
     void update_fsal() { memcpy(k[0], k[6], sizeof(R) * P->n); }   // fsalfirst = fsallast
     void addsteps(const R*, const R*, const R*, R, R) {}            // length(k) >= 7: nothing to add
+    static constexpr bool supports_callbacks = true;
+    // reset_fsal! (integrator_utils.jl:1325-1343): fsalfirst = f(u, p, t), nf += 1
+    void reset_fsal(const R* u, const R* p, R t, Stats<R>& st) { P->f(k[0], u, p, t); st.nf += 1; }
+    // _ode_addsteps!(k, t, uprev, u, dt, f, p, ::Tsit5ConstantCache, always_calc_begin = true)
+    // (lib/OrdinaryDiffEqTsit5/src/tsit_perform_step.jl:40-82): all seven stages again from uprev with the (shortened)
+    // dt — note `uprev + dt*(a21*k1)`, not perform_step!'s `a = dt*a21; uprev + a*k1`; stats are not touched
+    void addsteps_always(const R* uprev, const R* p, R t, R dt) {
+        const int n = P->n;
+        const R c1 = (R)0.161, c2 = (R)0.327, c3 = (R)0.9, c4 = (R)0.9800255409045097;
+        const R a21 = (R)0.161, a31 = (R)-0.008480655492356989, a32 = (R)0.335480655492357,
+                a41 = (R)2.8971530571054935, a42 = (R)-6.359448489975075, a43 = (R)4.3622954328695815,
+                a51 = (R)5.325864828439257, a52 = (R)-11.748883564062828, a53 = (R)7.4955393428898365,
+                a54 = (R)-0.09249506636175525, a61 = (R)5.86145544294642, a62 = (R)-12.92096931784711,
+                a63 = (R)8.159367898576159, a64 = (R)-0.071584973281401, a65 = (R)-0.028269050394068383,
+                a71 = (R)0.09646076681806523, a72 = (R)0.01, a73 = (R)0.4798896504144996,
+                a74 = (R)1.379008574103742, a75 = (R)-3.290069515436081, a76 = (R)2.324710524099774;
+        R *k1 = k[0], *k2 = k[1], *k3 = k[2], *k4 = k[3], *k5 = k[4], *k6 = k[5], *k7 = k[6];
+        R tmp[ORACLE_MAXN];
+        P->f(k1, uprev, p, t);
+        for (int i = 0; i < n; ++i) tmp[i] = jl_fma(dt, a21 * k1[i], uprev[i]);
+        P->f(k2, tmp, p, jl_fma(c1, dt, t));
+        for (int i = 0; i < n; ++i) tmp[i] = jl_fma(dt, jl_fma(a32, k2[i], a31 * k1[i]), uprev[i]);
+        P->f(k3, tmp, p, jl_fma(c2, dt, t));
+        for (int i = 0; i < n; ++i) tmp[i] = jl_fma(dt, jl_fma(a43, k3[i], jl_fma(a42, k2[i], a41 * k1[i])), uprev[i]);
+        P->f(k4, tmp, p, jl_fma(c3, dt, t));
+        for (int i = 0; i < n; ++i)
+            tmp[i] = jl_fma(dt, jl_fma(a54, k4[i], jl_fma(a53, k3[i], jl_fma(a52, k2[i], a51 * k1[i]))), uprev[i]);
+        P->f(k5, tmp, p, jl_fma(c4, dt, t));
+        for (int i = 0; i < n; ++i)
+            tmp[i] = jl_fma(dt, jl_fma(a65, k5[i], jl_fma(a64, k4[i], jl_fma(a63, k3[i], jl_fma(a62, k2[i], a61 * k1[i])))), uprev[i]);
+        P->f(k6, tmp, p, t + dt);
+        for (int i = 0; i < n; ++i)
+            tmp[i] = jl_fma(dt, jl_fma(a76, k6[i], jl_fma(a75, k5[i], jl_fma(a74, k4[i], jl_fma(a73, k3[i], jl_fma(a72, k2[i], a71 * k1[i]))))), uprev[i]);
+        P->f(k7, tmp, p, t + dt);
+    }
     void interpolant(R Theta, R dt, const R* y0, const R*, R* out) const {
         const int n = P->n;
         const R r11 = (R)1.0, r12 = (R)-2.763706197274826, r13 = (R)2.9132554618219126, r14 = (R)-1.0530884977290216,
@@ -360,18 +465,24 @@ template <typename A> struct PIBeta<A, std::void_t<decltype(A::beta2())>> {
 // CompositeAlgorithm (AutoTsit5(Rosenbrock23()), oracle_composite.inc): one PI controller cache per branch
 // (CompositeController, controllers.jl:1254-1338), choose_algorithm! in loopheader! (integrator_utils.jl:121),
 // do_error_check (composite_algs.jl:37-42, solve.jl:909)
+template <typename A, typename = void> struct SupportsCallbacks { static constexpr bool value = false; };
+template <typename A> struct SupportsCallbacks<A, std::void_t<decltype(A::supports_callbacks)>> { static constexpr bool value = A::supports_callbacks; };
 template <typename A, typename = void> struct IsComposite { static constexpr bool value = false; };
 template <typename A> struct IsComposite<A, std::void_t<decltype(A::is_composite)>> { static constexpr bool value = A::is_composite; };
 
 // One trajectory: __init + solve! + postamble!
 template <typename R, typename Alg>
-static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R tf, const Opts<R>& o, long long idx,
+static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, R tf, const Opts<R>& o, long long idx,
                       const Out<R>& out) {
     const int n = P.n;
     Alg cache; cache.P = &P;
     Stats<R> stats;
     R u[ORACLE_MAXN], uprev[ORACLE_MAXN];
     for (int i = 0; i < n; ++i) { u[i] = u0[i]; uprev[i] = u0[i]; }
+    // affect! may change the parameters of its own trajectory: work on a private copy when there are callbacks
+    R p_local[ORACLE_MAXNP];
+    if (o.ncb > 0 && p_in != nullptr) { for (int i = 0; i < P.np; ++i) p_local[i] = p_in[i]; }
+    const R* p = (o.ncb > 0 && p_in != nullptr) ? p_local : p_in;
     R t = t0, tprev = t0;
     const R dtmax = o.dtmax, opts_dtmin = o.dtmin;
     int nsaved = 0, save_idx = 0;
@@ -462,6 +573,172 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
         }
     };
 
+    // ---- savevalues! / _savevalues! (integrator_utils.jl:336-414); returns savedexactly
+    auto savevalues = [&](bool force_save) -> bool {
+        bool savedexactly = false, added = false;
+        while (save_idx < o.nsaveat && o.saveat[save_idx] <= t) {
+            R curt = o.saveat[save_idx++];
+            if (curt != t) {
+                R Theta = (curt - tprev) / dt;
+                if (!added) { cache.addsteps(uprev, u, p, tprev, dt); added = true; }
+                R val[ORACLE_MAXN];
+                cache.interpolant(Theta, dt, uprev, u, val);
+                emit(curt, val);
+            } else {
+                if (curt == tf && !o.save_end) continue;           // skip_saveat_at_tspan_end
+                savedexactly = true;
+                emit(t, u);
+            }
+        }
+        // force_save || save_everystep branch (:385-411)
+        if (force_save || (o.save_everystep &&
+                           (nsaved == 0 || ((t != last_saved_t || dt == (R)0) && (o.save_end || t != tf))))) {
+            savedexactly = true;
+            emit(t, u);
+        }
+        return savedexactly;
+    };
+
+    // ---- callbacks (lib/DiffEqBase/src/callbacks.jl) --------------------------------------------------------------
+    bool reeval_fsal = false, terminated = false;
+    int event_last_time = 0;                 // 1-based index of the continuous callback whose event ended the last step
+    R last_event_error = (R)0;
+    typedef R (*cond_t)(const R*, const R*, R);
+    typedef void (*affect_t)(R*, R*, R, int*);
+    auto jl_sign = [](R x) -> R { return x > (R)0 ? (R)1 : (x < (R)0 ? (R)-1 : x); };      // sign(±0) = ±0, sign(NaN) = NaN
+    // get_condition (callbacks.jl:91-137): u at t, uprev at tprev, the interpolant in between
+    auto get_condition = [&](const OracleCallback& cb, R abst) -> R {
+        cond_t f = (cond_t)cb.condition;
+        if (abst == t) return f(u, p, abst);
+        if (abst == tprev) return f(uprev, p, abst);
+        R val[ORACLE_MAXN];
+        R Theta = (abst - tprev) / dt;                                 // current_interpolant
+        cache.addsteps(uprev, u, p, tprev, dt);
+        cache.interpolant(Theta, dt, uprev, u, val);
+        return f(val, p, abst);
+    };
+    // is_event_occurrence (callbacks.jl:523-528)
+    auto is_event = [&](const OracleCallback& cb, R prev_sign, R next_sign) -> bool {
+        return ((prev_sign < (R)0 && cb.affect != nullptr) || (prev_sign > (R)0 && cb.affect_neg != nullptr)) &&
+               prev_sign * next_sign <= (R)0;
+    };
+    // find_callback_time(integrator, callback::ContinuousCallback, callback_idx) (callbacks.jl:361-403)
+    auto find_callback_time = [&](const OracleCallback& cb, int callback_idx, R& callback_t, R& bottom_sign, R& residual) -> bool {
+        R bottom_t = tprev;
+        R bottom_condition = get_condition(cb, bottom_t);
+        if (event_last_time == callback_idx) {
+            // nudge_tprev (:413-422): still within abstol of the last root => look just right of tprev
+            if (std::fabs(bottom_condition - last_event_error) <= (R)cb.abstol) bottom_t = tprev + dt * (R)cb.repeat_nudge;
+            else bottom_t = tprev;
+            bottom_condition = get_condition(cb, bottom_t);
+        }
+        bottom_sign = jl_sign(bottom_condition);
+        // check_event_occurrence (:427-446)
+        R top_t = t;
+        R top_sign = jl_sign(get_condition(cb, top_t));
+        bool occurred = is_event(cb, bottom_sign, top_sign);
+        if (cb.interp_points != 0 && !occurred) {
+            JlLinspace<R> ts(tprev, t, cb.interp_points);              // range(tprev, stop = t, length = interp_points)
+            for (int i = 2; i <= cb.interp_points; ++i) {
+                top_t = (i == cb.interp_points) ? t : ts[i];           // the last element is `stop` exactly
+                top_sign = jl_sign(get_condition(cb, top_t));
+                occurred = is_event(cb, bottom_sign, top_sign);
+                if (occurred) break;
+            }
+        }
+        if (!occurred) { callback_t = t; residual = (R)0; }
+        else if (cb.rootfind == 0 || top_sign == (R)0) { callback_t = top_t; residual = (R)0; }
+        else {
+            // find_root (:478-491): IntervalNonlinearProblem solved with ModAB(), abstol = reltol = 0 — EXT
+            // (BracketingNonlinearSolve).  With zero tolerances every bracketing method ends on the pair of adjacent
+            // floats around the sign change, so plain bisection is used; an exact zero counts as the far side.
+            R left = bottom_t, right = top_t;
+            for (;;) {
+                R mid = left + (right - left) / (R)2;
+                if (!(left < mid && mid < right)) break;
+                R sm = jl_sign(get_condition(cb, mid));
+                if (sm == bottom_sign) left = mid; else right = mid;
+            }
+            callback_t = (cb.rootfind == 1) ? left : right;
+            residual = get_condition(cb, callback_t);
+        }
+        return occurred;
+    };
+    // reeval_internals_due_to_modification! (integrator_interface.jl:54-80)
+    auto reeval_internals = [&](bool continuous_modification) {
+        if constexpr (SupportsCallbacks<Alg>::value) {
+            if (continuous_modification) cache.addsteps_always(uprev, p, tprev, dt);    // opts.calck is true with callbacks
+        }
+        reeval_fsal = true;
+    };
+    auto run_affect = [&](void* fn) {
+        int term = 0;
+        ((affect_t)fn)(u, p_local, t, &term);
+        if (term) { terminated = true; retcode = RC_TERMINATED; }      // terminate!(integrator)
+    };
+    // apply_callback! (callbacks.jl:557-637)
+    auto apply_callback = [&](const OracleCallback& cb, R cb_time, R prev_sign, bool& saved_in_cb) -> bool {
+        if (o.adaptive) dtpropose = jl_max(jl_nextfloat(opts_dtmin), dt);      // set_proposed_dt!(max(nextfloat(dtmin), dtrelax*dt)), dtrelax = 1
+        // change_t_via_interpolation! (integrator_interface.jl:5-39)
+        if (cb_time != t) {
+            R val[ORACLE_MAXN];
+            R Theta = (cb_time - tprev) / dt;
+            cache.addsteps(uprev, u, p, tprev, dt);
+            cache.interpolant(Theta, dt, uprev, u, val);
+            for (int i = 0; i < n; ++i) u[i] = val[i];
+            t = cb_time;
+            dt = t - tprev;
+            reeval_internals(true);
+        }
+        bool savedexactly = savevalues(false);
+        saved_in_cb = true;
+        if (cb.save_before && !savedexactly) savevalues(true);
+        void* fn = prev_sign < (R)0 ? cb.affect : (prev_sign > (R)0 ? cb.affect_neg : nullptr);
+        if (fn == nullptr) return false;                            // derivative_discontinuity = false
+        run_affect(fn);
+        reeval_internals(true);
+        if (cb.save_after) { savevalues(true); saved_in_cb = true; }
+        return true;
+    };
+    auto handle_callbacks = [&]() {
+        bool saved_in_cb = false;
+        int ncont = 0;
+        for (int k = 0; k < o.ncb; ++k) if (o.cbs[k].kind == 1) ncont += 1;
+        if (ncont > 0) {
+            // find_first_continuous_callback (:140-226): the earliest event wins, ties keep the first callback
+            bool event_occurred = false; R tmin = t, upcrossing = (R)0, residual = (R)0; int identified = 0, ci = 0, evc = 0;
+            for (int k = 0; k < o.ncb; ++k) {
+                if (o.cbs[k].kind != 1) continue;
+                ci += 1;
+                R t2, s2, r2;
+                bool occ2 = find_callback_time(o.cbs[k], ci, t2, s2, r2);
+                if (ci == 1) { tmin = t2; upcrossing = s2; residual = r2; event_occurred = occ2; identified = k; }
+                else if (occ2 && (!event_occurred || t2 < tmin)) {
+                    tmin = t2; upcrossing = s2; residual = r2; event_occurred = true; identified = k;
+                }
+                if (event_occurred && identified == k) evc = ci;
+            }
+            if (event_occurred) {
+                last_event_error = residual;
+                event_last_time = evc;
+                apply_callback(o.cbs[identified], tmin, upcrossing, saved_in_cb);
+            } else event_last_time = 0;
+        }
+        // apply_discrete_callback! (:649-690), in order
+        for (int k = 0; k < o.ncb; ++k) {
+            const OracleCallback& cb = o.cbs[k];
+            if (cb.kind != 0) continue;
+            if (((cond_t)cb.condition)(u, p, t) != (R)0) {
+                bool savedexactly = savevalues(false);
+                saved_in_cb = true;
+                if (cb.save_before && !savedexactly) savevalues(true);
+                if (cb.affect) { run_affect(cb.affect); reeval_internals(false); }
+                if (cb.save_after) { savevalues(true); saved_in_cb = true; }
+            }
+        }
+        if (!saved_in_cb) savevalues(false);
+    };
+
     // solve! (solve.jl:904-946): `while !isempty(tstops); while t < first(tstops) ... end; handle_tstop! end`.
     // tf is the last stop, so the two loops collapse into this one plus the pop at the end of an accepted step.
     while (t < tf) {
@@ -472,7 +749,10 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
                 // apply_step! (:175-203)
                 for (int i = 0; i < n; ++i) uprev[i] = u[i];
                 dt = dtpropose;
-                cache.update_fsal();
+                // update_fsal! (:215-239): reeval_fsal / derivative_discontinuity => reset_fsal!
+                if constexpr (SupportsCallbacks<Alg>::value) {
+                    if (reeval_fsal) cache.reset_fsal(u, p, t, stats); else cache.update_fsal();
+                } else cache.update_fsal();
                 modify_dt_for_tstops();
             } else {
                 // handle_step_rejection! -> step_reject_controller! (controllers.jl:838-843)
@@ -508,6 +788,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
         }
         // ---- loopfooter! (:597-677)
         do_error_check = true;
+        reeval_fsal = false;                                            // loopfooter_reset!
         R ttmp = t + dt;
         R q = (R)1;
         if (o.adaptive) {
@@ -542,25 +823,11 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
             } else {
                 dtpropose = dt;
             }
-            // handle_callbacks! -> savevalues! (:340-414)
-            bool added = false;
-            while (save_idx < o.nsaveat && o.saveat[save_idx] <= t) {
-                R curt = o.saveat[save_idx++];
-                if (curt != t) {
-                    R Theta = (curt - tprev) / dt;
-                    if (!added) { cache.addsteps(uprev, u, p, tprev, dt); added = true; }
-                    R val[ORACLE_MAXN];
-                    cache.interpolant(Theta, dt, uprev, u, val);
-                    emit(curt, val);
-                } else {
-                    if (curt == tf && !o.save_end) continue;           // skip_saveat_at_tspan_end
-                    emit(t, u);
-                }
-            }
-            // save_everystep branch of _savevalues! (integrator_utils.jl:385-411)
-            if (o.save_everystep &&
-                (nsaved == 0 || ((t != last_saved_t || dt == (R)0) && (o.save_end || t != tf))))
-                emit(t, u);
+            // handle_callbacks! (integrator_utils.jl:1081-1132) -> savevalues! (:340-414)
+            if constexpr (SupportsCallbacks<Alg>::value) {
+                if (o.ncb > 0) handle_callbacks(); else savevalues(false);
+            } else savevalues(false);
+            if (terminated) break;                                      // terminate!: the tstops heap was emptied
             // handle_tstop! (integrator_utils.jl:1290-1314): pop every copy of a stop that was reached
             while (o.ntstops > 0 && t == cur_tstop && tstop_idx + 1 < o.ntstops) cur_tstop = o.tstops[++tstop_idx];
         } else {
@@ -659,6 +926,7 @@ struct OracleArgs {
     const int* save_idxs; int nsave_idxs;
     const double* tstops; int ntstops;      // the tstops keyword, unfiltered
     int fixed_dt;                           // 1: adaptive = false
+    const OracleCallback* cbs; int ncb;     // the CallbackSet (Tsit5 only)
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -678,8 +946,12 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.save_end = a.save_end != 0;
     o.save_end_user = a.save_end > 0;
     o.linsolve = a.linsolve;
-    o.save_everystep = a.save_everystep != 0;
+    o.save_everystep = a.save_everystep == 1;      // 2: ragged rows without the per-step rows (callbacks + saveat)
     o.adaptive = a.fixed_dt == 0;
+    if (a.ncb > 0) {
+        if (a.alg != ALG_TSIT5 || !a.cbs) return -5;                // callbacks: Tsit5 only (first slice of SURVEY §8(f) row 4)
+        o.cbs = a.cbs; o.ncb = a.ncb;
+    }
     if (!o.adaptive && a.dt == 0.0 && !(a.tstops && a.ntstops > 0)) return -4;     // solve.jl:277-280
     std::vector<R> stops;
     if (a.tstops && a.ntstops > 0) {
@@ -717,6 +989,7 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         case ALG_RODAS4: solve_batch<R, Rodas4<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS42: solve_batch<R, Rodas42<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P: solve_batch<R, Rodas4P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_RODAS3P: solve_batch<R, Rodas3P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P2: solve_batch<R, Rodas4P2<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #endif
 #ifdef ORACLE_HAVE_COMPOSITE

@@ -21,7 +21,7 @@ _BUILD = os.path.join(_HERE, "_build")
 ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P, ALG_DP5, ALG_BS3 = 1, 2, 3, 4, 5, 6
 ALG_RODAS5, ALG_RODAS4, ALG_RODAS42, ALG_RODAS4P, ALG_RODAS4P2 = 7, 8, 9, 10, 11
 ALG_VERN6, ALG_VERN8, ALG_VERN9, ALG_ROSENBROCK32, ALG_RODAS5PE, ALG_VERN7_GENERATED = 12, 13, 14, 15, 16, 102
-ALG_AUTOTSIT5_ROSENBROCK23 = 17
+ALG_AUTOTSIT5_ROSENBROCK23, ALG_RODAS3P = 17, 18
 
 
 def build(force=False):
@@ -49,7 +49,50 @@ class OracleArgs(C.Structure):
                 ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p),
                 ("save_everystep", C.c_int), ("row_offsets", C.c_void_p), ("ts_rag", C.c_void_p),
                 ("save_idxs", C.c_void_p), ("nsave_idxs", C.c_int),
-                ("tstops", C.c_void_p), ("ntstops", C.c_int), ("fixed_dt", C.c_int)]
+                ("tstops", C.c_void_p), ("ntstops", C.c_int), ("fixed_dt", C.c_int),
+                ("cbs", C.c_void_p), ("ncb", C.c_int)]
+
+
+class OracleCallback(C.Structure):
+    _fields_ = [("kind", C.c_int), ("condition", C.c_void_p), ("affect", C.c_void_p), ("affect_neg", C.c_void_p),
+                ("rootfind", C.c_int), ("interp_points", C.c_int), ("abstol", C.c_double), ("repeat_nudge", C.c_double),
+                ("save_before", C.c_int), ("save_after", C.c_int)]
+
+
+RC_TERMINATED = 6
+
+
+def _callback_sources(callbacks):
+    out = []
+    for cb in callbacks or []:
+        for key in ("condition", "affect", "affect_neg"):
+            v = cb.get(key)
+            if v is not None:
+                out.append(v[0])
+    return out
+
+
+def _callback_array(user, callbacks):
+    """callbacks: list of dicts — kind ("discrete" | "continuous"), condition (src, name), affect (src, name) or None,
+    affect_neg (continuous: defaults to affect; pass False for `nothing`), rootfind ("left" | "right" | "none"),
+    interp_points, abstol, repeat_nudge, save_positions.  Continuous callbacks must come first (CallbackSet order)."""
+    arr = (OracleCallback * len(callbacks))()
+    for i, cb in enumerate(callbacks):
+        c = arr[i]
+        cont = cb["kind"] == "continuous"
+        c.kind = 1 if cont else 0
+        c.condition = fn_ptr(user, cb["condition"][1])
+        aff = cb.get("affect")
+        c.affect = fn_ptr(user, aff[1]) if aff else None
+        neg = cb.get("affect_neg", aff if cont else None)
+        c.affect_neg = fn_ptr(user, neg[1]) if (cont and neg) else None
+        c.rootfind = {"none": 0, "left": 1, "right": 2}[cb.get("rootfind", "left")]
+        c.interp_points = cb.get("interp_points", 10)
+        c.abstol = cb.get("abstol", 10 * 2.0 ** -52)
+        c.repeat_nudge = cb.get("repeat_nudge", 0.01)
+        sp = cb.get("save_positions", (True, True))
+        c.save_before, c.save_after = int(bool(sp[0])), int(bool(sp[1]))
+    return arr
 
 
 _lib = None
@@ -124,12 +167,13 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
 
 def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
           abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
-          linsolve=0, nthreads=0, save_everystep=False, dense_tq=None, save_idxs=None, tstops=None, adaptive=True):
+          linsolve=0, nthreads=0, save_everystep=False, dense_tq=None, save_idxs=None, tstops=None, adaptive=True,
+          callbacks=None, ragged_saveat=False):
     """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host.
     save_everystep=True returns ragged rows (row_offsets, ts, us[total, n]) like lowlevel.solve_host_everystep."""
     L = lib()
     rdt = np.float32 if f32 else np.float64
-    user = compile_user([rhs[0], jac[0] if jac else None, tgrad[0] if tgrad else None])
+    user = compile_user([rhs[0], jac[0] if jac else None, tgrad[0] if tgrad else None] + _callback_sources(callbacks))
     u0 = np.ascontiguousarray(u0, dtype=rdt)
     u0_shared = u0.ndim == 1
     p_arr = None if p is None else np.ascontiguousarray(p, dtype=rdt)
@@ -167,6 +211,10 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     if idxs is not None:
         a.save_idxs = idxs.ctypes.data; a.nsave_idxs = len(idxs)
     a.fixed_dt = 0 if adaptive else 1
+    cb_arr = None
+    if callbacks:
+        cb_arr = _callback_array(user, callbacks)
+        a.cbs = C.cast(cb_arr, C.c_void_p).value; a.ncb = len(callbacks)
     stops = None
     if tstops is not None and len(tstops) > 0:
         stops = np.ascontiguousarray(tstops, dtype=np.float64)
@@ -187,9 +235,10 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
         out["dense"] = dense
         out["t_final"] = out["t_final"].astype(np.float64)
         return out
-    if save_everystep:
-        # counting pass, exclusive scan, fill pass (the same two passes the GPU path makes)
-        a.save_everystep = 1; a.us = None; a.nslots = 0; a.row_offsets = None; a.ts_rag = None
+    if save_everystep or ragged_saveat:
+        # counting pass, exclusive scan, fill pass (the same two passes the GPU path makes).  ragged_saveat: ragged rows
+        # (saveat + the rows callbacks force) without the per-step rows, i.e. save_everystep = false with callbacks
+        a.save_everystep = 1 if save_everystep else 2; a.us = None; a.nslots = 0; a.row_offsets = None; a.ts_rag = None
         rc = L.oracle_solve(C.byref(a))
         if rc != 0:
             raise RuntimeError("oracle_solve failed: %d" % rc)

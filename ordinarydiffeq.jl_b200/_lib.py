@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200ode.so")
 ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P, ALG_DP5, ALG_BS3 = 1, 2, 3, 4, 5, 6
 ALG_RODAS5, ALG_RODAS4, ALG_RODAS42, ALG_RODAS4P, ALG_RODAS4P2 = 7, 8, 9, 10, 11
 ALG_VERN6, ALG_VERN8, ALG_VERN9, ALG_ROSENBROCK32, ALG_RODAS5PE = 12, 13, 14, 15, 16
-ALG_AUTOTSIT5_ROSENBROCK23 = 17
+ALG_AUTOTSIT5_ROSENBROCK23, ALG_RODAS3P = 17, 18
 F64, F32 = 0, 1
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 FLAG_STATIC_SCHEDULE = 1

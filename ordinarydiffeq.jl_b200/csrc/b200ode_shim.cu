@@ -161,7 +161,7 @@ bool is_identifier(const char* s) {
 
 bool is_stiff_alg(int alg) {      // Rosenbrock-type: need jac + tgrad, report njacs/nw/nsolve
     return alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_ROSENBROCK32 || alg == B200ODE_ALG_RODAS5P ||
-           alg == B200ODE_ALG_RODAS5PE || alg == B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 ||
+           alg == B200ODE_ALG_RODAS5PE || alg == B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 || alg == B200ODE_ALG_RODAS3P ||
            (alg >= B200ODE_ALG_RODAS5 && alg <= B200ODE_ALG_RODAS4P2);
 }
 
@@ -175,7 +175,7 @@ int alg_order(int alg) {
         case B200ODE_ALG_VERN8: return 8;
         case B200ODE_ALG_VERN9: return 9;
         case B200ODE_ALG_ROSENBROCK23: return 2;
-        case B200ODE_ALG_BS3: case B200ODE_ALG_ROSENBROCK32: return 3;
+        case B200ODE_ALG_BS3: case B200ODE_ALG_ROSENBROCK32: case B200ODE_ALG_RODAS3P: return 3;
         default: return 4;      // Rodas4, Rodas42, Rodas4P, Rodas4P2
     }
 }
@@ -202,7 +202,7 @@ int parse_save_idxs(const char* extra_options, int n) {
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                           const char* jac_src, const char* jac_name, const char* tgrad_src,
                           const char* tgrad_name) {
-    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_AUTOTSIT5_ROSENBROCK23)
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS3P)
         return fail(B200ODE_EINVAL, "alg must be one of the B200ODE_ALG_* constants");
     if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
     if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");

@@ -22,7 +22,7 @@
 //   B200_F32             0: double, 1: float
 //   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3,
 //                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9, 15 Rosenbrock32, 16 Rodas5Pe,
-//                        17 AutoTsit5(Rosenbrock23())
+//                        17 AutoTsit5(Rosenbrock23()), 18 Rodas3P
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -46,8 +46,9 @@
 #define B200_ALG_ROS32 15
 #define B200_ALG_RODAS5PE 16
 #define B200_ALG_AUTOTSIT5_ROS23 17
+#define B200_ALG_RODAS3P 18
 #define B200_COMPOSITE (B200_ALG == B200_ALG_AUTOTSIT5_ROS23)
-#define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || B200_ALG == B200_ALG_RODAS5PE || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
+#define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || B200_ALG == B200_ALG_RODAS5PE || B200_ALG == B200_ALG_RODAS3P || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
 // (the composite algorithm counts as Rosenbrock-type here: it needs jac/tgrad and reports njacs / nw / nsolve)
 #define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32 || B200_IS_RODAS || B200_COMPOSITE)
 

@@ -249,7 +249,28 @@ struct B200Ros23 {
 // ---------------------------------------------------------------------------
 // Tableau selection for the generic Rodas-type stepper (RodasTableau family; b = [A[S,1:S-1]; 1],
 // btilde = e_S; rosenbrock_tableaus.jl of OrdinaryDiffEqRosenbrock / OrdinaryDiffEqRosenbrockTableaus).
-#if B200_ALG == B200_ALG_RODAS5
+// Rodas3P (lib/OrdinaryDiffEqRosenbrockTableaus/src/rosenbrock_tableaus.jl:386-445), written as the reference writes it
+// (4.0 / 3.0 etc. are Float64 quotients, then convert(T, .)): 5 stages, explicit b / btilde, stage 5 repeats stage 4's
+// (c, A row) so its f evaluation is skipped (rosenbrock_perform_step.jl:474-481), three rows of H of which the
+// interpolant uses two (interp_order = 2, rosenbrock_caches.jl:487-488).
+#define B200_RODAS3P_S 5
+#define B200_RODAS3P_HR 3
+#define B200_RODAS3P_GAMMA (1.0 / 3.0)
+#define B200_RODAS3P_A { {0, 0, 0, 0, 0}, {4.0 / 3.0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {2.90625, 3.375, 0.40625, 0, 0}, {2.90625, 3.375, 0.40625, 0, 0} }
+#define B200_RODAS3P_C { {0, 0, 0, 0}, {-4.0, 0, 0, 0}, {8.25, 6.75, 0, 0}, {1.21875, -5.0625, -1.96875, 0}, {4.03125, -15.1875, -4.03125, 6.0} }
+#define B200_RODAS3P_c {0, 4.0 / 9.0, 0, 1, 1}
+#define B200_RODAS3P_d {1.0 / 3.0, -(1.0 / 9.0), 1.0, 0, 0}
+#define B200_RODAS3P_H { {1.78125, 6.75, 0.15625, -6.0, -1.0}, {4.21875, -15.1875, -3.09375, 9.0, 0}, {4.21875, -2.025, -1.63125, -1.7, -0.1} }
+#define B200_RODAS3P_B {2.90625, 3.375, 0.40625, 0, 1}
+#define B200_RODAS3P_BTILDE {0, 0, 0, -1, 1}
+
+#if B200_ALG == B200_ALG_RODAS3P
+#define B200_RODAS_NAME(x) B200_RODAS3P_##x
+#define B200_RODAS_ORDER 3
+#define B200_RODAS_EXPLICIT_B 1         // b and btilde are stored vectors (zero entries skipped like the reference)
+#define B200_RODAS_INTERP 2             // interp_order
+#define B200_RODAS_FSKIP 4              // 0-based stage that reuses the previous stage's f (asserted on the host side too)
+#elif B200_ALG == B200_ALG_RODAS5
 #define B200_RODAS_NAME(x) B200_RODAS5_##x
 #define B200_RODAS_ORDER 5
 #elif B200_ALG == B200_ALG_RODAS4
@@ -270,6 +291,15 @@ struct B200Ros23 {
 #endif
 #define B200_RODAS_S B200_RODAS_NAME(S)
 #define B200_RODAS_HR B200_RODAS_NAME(HR)
+#ifndef B200_RODAS_EXPLICIT_B
+#define B200_RODAS_EXPLICIT_B 0
+#endif
+#ifndef B200_RODAS_INTERP
+#define B200_RODAS_INTERP B200_RODAS_HR
+#endif
+#ifndef B200_RODAS_FSKIP
+#define B200_RODAS_FSKIP (-1)
+#endif
 
 struct B200Rodas5PCoeffs {
     real A[B200_RODAS_S][B200_RODAS_S];
@@ -281,11 +311,18 @@ struct B200Rodas5PCoeffs {
 #if B200_ALG == B200_ALG_RODAS5PE
     real btilde[B200_RODAS_S];
 #endif
+#if B200_RODAS_EXPLICIT_B
+    real b[B200_RODAS_S];
+    real btilde[B200_RODAS_S];
+#endif
 };
 __constant__ B200Rodas5PCoeffs B200_RODAS5P_TAB = {B200_RODAS_NAME(A), B200_RODAS_NAME(C), B200_RODAS_NAME(c), B200_RODAS_NAME(d),
                                                  B200_RODAS_NAME(H), B200_RODAS_NAME(GAMMA)
 #if B200_ALG == B200_ALG_RODAS5PE
                                                  , B200_RODAS5PE_BTILDE
+#endif
+#if B200_RODAS_EXPLICIT_B
+                                                 , B200_RODAS_NAME(B), B200_RODAS_NAME(BTILDE)
 #endif
 };
 
@@ -325,8 +362,10 @@ struct B200Rodas5P {
             for (int j = 0; j < s; ++j)
 #pragma unroll
                 for (int i = 0; i < B200_N; ++i) us[i] = b200_fma(T.A[s][j], ks[j][i], us[i]);
-            B200_RHS(du, us, p, b200_fma(T.c[s], dt, t));
-            nf += 1;
+            if (s != B200_RODAS_FSKIP) {        // a stage that repeats the previous (c, A row) keeps du (:474-481)
+                B200_RHS(du, us, p, b200_fma(T.c[s], dt, t));
+                nf += 1;
+            }
 #pragma unroll
             for (int i = 0; i < B200_N; ++i) lt[i] = (real)0;
 #pragma unroll
@@ -350,12 +389,27 @@ struct B200Rodas5P {
         for (int i = 0; i < B200_N; ++i) u[i] = uprev[i];
 #pragma unroll
         for (int j = 0; j < B200_RODAS_S; ++j) {
+#if B200_RODAS_EXPLICIT_B
+            const real b = T.b[j];
+            if (b == (real)0) continue;
+#else
             const real b = (j < B200_RODAS_S - 1) ? T.A[B200_RODAS_S - 1][j] : (real)1;      // b = [A[S,1:S-1]; 1]
             if (j < B200_RODAS_S - 1 && T.A[B200_RODAS_S - 1][j] == (real)0) continue;
+#endif
 #pragma unroll
             for (int i = 0; i < B200_N; ++i) u[i] = b200_fma(b, ks[j][i], u[i]);
         }
-#if B200_ALG == B200_ALG_RODAS5PE
+#if B200_RODAS_EXPLICIT_B
+        // du = zero(uprev); for i: if !iszero(btilde[i]) du = du + btilde[i]*ks[i]
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) du[i] = (real)0;
+#pragma unroll
+        for (int j = 0; j < B200_RODAS_S; ++j) {
+            if (T.btilde[j] == (real)0) continue;
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) du[i] = b200_fma(T.btilde[j], ks[j][i], du[i]);
+        }
+#elif B200_ALG == B200_ALG_RODAS5PE
         // du = zero(uprev); for i: du = du + btilde[i]*ks[i] (no entry of Rodas5Pe's btilde is zero)
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) du[i] = (real)0;
@@ -393,7 +447,7 @@ struct B200Rodas5P {
         const real th1 = (real)1 - th;
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) {
-#if B200_RODAS_HR == 3
+#if B200_RODAS_INTERP == 3
             real in = b200_fma(th, dense[2][i], dense[1][i]);
             in = b200_fma(th, in, dense[0][i]);
 #else

@@ -83,6 +83,10 @@ class Rodas4P(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS4P, 4, True
 
 
+class Rodas3P(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS3P, 3, True
+
+
 class Rodas4P2(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS4P2, 4, True
 

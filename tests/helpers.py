@@ -50,3 +50,24 @@ def assert_same_result(g, o, keys=("naccept", "nreject", "nf", "retcode", "nsave
     if o.get("us") is not None:
         assert np.array_equal(bits(g["us"]), bits(o["us"])), "saveat rows differ"
         assert np.array_equal(g["ts"], o["ts"]), "ts differ"
+
+
+# ---- callbacks written as C source (condition: real f(u, p, t); affect: void f(u, p, t, int* terminate)) ----------
+def ball_sources(f32=False):
+    """Bouncing ball of test/Integrators_I/ode_event_tests.jl:105-126: y'' = -g (g = p[0]), event y = 0."""
+    T = "float" if f32 else "double"
+    rhs = ("void ball_rhs(%s* du, const %s* u, const %s* p, const %s t) { du[0] = u[1]; du[1] = -p[0]; }\n" % (T, T, T, T), "ball_rhs")
+    cond = ("%s ball_cond(const %s* u, const %s* p, const %s t) { return u[0]; }\n" % (T, T, T, T), "ball_cond")
+    bounce = ("void ball_bounce(%s* u, %s* p, const %s t, int* terminate) { u[1] = -p[1] * u[1]; }\n" % (T, T, T), "ball_bounce")
+    stop = ("void ball_stop(%s* u, %s* p, const %s t, int* terminate) { *terminate = 1; }\n" % (T, T, T), "ball_stop")
+    return rhs, cond, bounce, stop
+
+
+def always_true_source(f32=False, name="cb_true"):
+    T = "float" if f32 else "double"
+    return ("%s %s(const %s* u, const %s* p, const %s t) { return 1; }\n" % (T, name, T, T, T), name)
+
+
+def noop_affect_source(f32=False, name="cb_noop"):
+    T = "float" if f32 else "double"
+    return ("void %s(%s* u, %s* p, const %s t, int* terminate) { }\n" % (name, T, T, T), name)

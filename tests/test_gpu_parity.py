@@ -610,14 +610,14 @@ def test_low_order_rk_high_level(pkg, oracle):
             assert s[i].stats.naccept == o["naccept"][i]
 
 
-@pytest.mark.parametrize("name", ["Rodas5", "Rodas4", "Rodas42", "Rodas4P", "Rodas4P2", "Rodas5Pe"])
+@pytest.mark.parametrize("name", ["Rodas5", "Rodas4", "Rodas42", "Rodas4P", "Rodas4P2", "Rodas5Pe", "Rodas3P"])
 def test_rodas_family_parity(pkg, handle, oracle, name):
     """The generic RodasTableau stepper over the other members of the family, Robertson FP64 (+ FP32 for two)."""
     pl = pkg.problems_library
     alg = getattr(pkg, "ALG_" + name.upper())
     oalg = getattr(oracle, "ALG_" + name.upper())
     N = 1024
-    for f32 in ((False, True) if name in ("Rodas5", "Rodas4") else (False,)):
+    for f32 in ((False, True) if name in ("Rodas5", "Rodas4", "Rodas3P") else (False,)):
         r, j, tg = pl.robertson_sources(f32)
         p = pl.robertson_params(N, f32=f32)
         dt = pkg.F32 if f32 else pkg.F64

@@ -217,13 +217,14 @@ def test_tableau_consistency():
     (oracle.ALG_RODAS5, 2e-6),                                 # ode_dense_tests.jl:465-477
     (oracle.ALG_ROSENBROCK32, 6e-4),                           # ode_dense_tests.jl:456
     (oracle.ALG_RODAS5PE, 2e-5),                               # ode_dense_tests.jl:483
+    (oracle.ALG_RODAS3P, 2e-4),                                # ode_dense_tests.jl:462
     (oracle.ALG_VERN6, 7e-8), (oracle.ALG_VERN8, 3e-8), (oracle.ALG_VERN9, 1e-9)])   # ode_dense_tests.jl:406,437,444
 def test_dense_output_regression_bounds(alg, bound):
     # test/Regression_I/ode_dense_tests.jl:56-75 with the per-algorithm tolerances at
     # :369-370 (Tsit5), :429-433 (Vern7), :452-453 (Rosenbrock23), :479-480 (Rodas5P):
     # interpolant of the adaptive dt0 = 1/4 solve vs the fixed dt = 1/16 solve, at k/16.
     jac, tg = linear_jac_sources()
-    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK32, oracle.ALG_RODAS5P, oracle.ALG_RODAS5PE) or \
+    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK32, oracle.ALG_RODAS5P, oracle.ALG_RODAS5PE, oracle.ALG_RODAS3P) or \
         oracle.ALG_RODAS5 <= alg <= oracle.ALG_RODAS4P2
     kw = dict(jac=jac, tgrad=tg) if stiff else {}
     pts = [k / 16 for k in range(1, 17)]
@@ -380,6 +381,20 @@ def test_rodas_family_order_and_step_count(alg, order):
     S = 8 if alg == oracle.ALG_RODAS5 else 6
     iters = o["naccept"][0] + o["nreject"][0]
     assert o["nf"][0] == 2 + S * iters and o["nsolve"][0] == (S - 1) * iters and o["njacs"][0] == 2 * iters
+
+
+def test_rodas3p_order_step_count_and_f_skip():
+    # Rodas3P: third order (alg_utils.jl:3); stage 5 repeats stage 4's (c, A row), so every attempt evaluates f four
+    # times (at uprev and for stages 2-4) although it has five stages (rosenbrock_perform_step.jl:474-481)
+    errs = [_fixed_step_l2_error(oracle.ALG_RODAS3P, 0.5 ** k, True) for k in (6, 5, 4, 3)]
+    rates = [math.log2(errs[i + 1] / errs[i]) for i in range(len(errs) - 1)]
+    assert abs(np.mean(rates) - 3) < 0.2, (errs, rates)
+    jac, tg = linear_jac_sources()
+    o = oracle.solve(oracle.ALG_RODAS3P, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, jac=jac,
+                     tgrad=tg, save_everystep=True)
+    assert o["retcode"][0] == 1 and o["nsaved"][0] < 20
+    iters = o["naccept"][0] + o["nreject"][0]
+    assert o["nf"][0] == 2 + 4 * iters and o["nsolve"][0] == 4 * iters and o["njacs"][0] == 2 * iters
 
 
 # ---- generated Verner steppers (scripts/gen_verner.py) ----------------------------------------
@@ -798,3 +813,58 @@ def test_autotsit5_is_tsit5_while_nothing_is_stiff_and_rosenbrock23_like_on_robe
     ros = c["nw"]
     switches = c["nf"] - (3 + 6 * (att - ros) + 2 * ros)
     assert (switches >= 1).all() and (switches <= 3).all()
+
+
+# ---- callbacks (first slice: Tsit5) -----------------------------------------------------------------
+def test_bouncing_ball_terminates_like_the_reference():
+    # test/Integrators_I/ode_event_tests.jl:262-311: u0 = [50, 0], g = 9.81, ContinuousCallback(u[1], terminate!):
+    # retcode Terminated, sol.u[end][1] < 3e-12, sol.t[end] ≈ sqrt(50*2/9.81).  (tspan (0, Inf) there; a far tf here.)
+    from helpers import ball_sources
+    rhs, cond, bounce, stop = ball_sources()
+    cbs = [dict(kind="continuous", condition=cond, affect=stop)]
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([50.0, 0.0]), np.array([[9.81, 1.0]]), (0.0, 1e3), 2, 2,
+                     callbacks=cbs, save_everystep=True)
+    assert o["retcode"][0] == oracle.RC_TERMINATED
+    assert o["us"][-1][0] < 3e-12 and o["us"][-1][0] >= 0.0          # LeftRootFind: still on the positive side
+    assert o["ts"][-1] == pytest.approx(math.sqrt(50 * 2 / 9.81), rel=1e-12)
+    assert o["t_final"][0] == o["ts"][-1]
+
+
+def test_event_time_rows_with_saveat_like_the_reference():
+    # ode_event_tests.jl:160-170: with save_everystep = false the rows are [t0, event (before), event (after), tf];
+    # saveat = t (the event time) or t - eps(t) both leave exactly two rows at t
+    from helpers import ball_sources
+    rhs, cond, bounce, stop = ball_sources()
+    cbs = [dict(kind="continuous", condition=cond, affect=None, affect_neg=bounce, interp_points=100)]
+    u0, p = np.array([50.0, 0.0]), np.array([[9.81, 1.0]])
+    # "save_everystep = false": ragged rows without the per-step rows = saveat at tf only
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, (0.0, 15.0), 2, 2, callbacks=cbs, save_everystep=True)
+    ts = o["ts"]
+    ev = [ts[i] for i in range(1, len(ts)) if ts[i] == ts[i - 1]]
+    assert len(ev) >= 2
+    t = ev[0]
+    assert t == pytest.approx(math.sqrt(50 * 2 / 9.81), rel=1e-12)
+    for grid in ([t], [float(np.nextafter(t, 0.0))]):                  # t and t - eps(t)
+        q = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, (0.0, 15.0), 2, 2, callbacks=cbs, saveat=grid, ragged_saveat=True)
+        assert int(np.sum(q["ts"] == t)) == 2
+        rows = q["us"][q["ts"] == t]
+        assert rows[0][1] < 0 < rows[1][1]                             # velocity flips across the discontinuity
+
+
+def test_saving_callbacks_double_the_rows_like_the_reference():
+    # ode_event_tests.jl:232-252: DiscreteCallback(true, noop; save_positions = (true, false)) leaves sol.t alone (the
+    # per-step row already is that save), two of them force one extra row per step: length == 2 length(sol4.t) - 1
+    from helpers import ball_sources, always_true_source, noop_affect_source
+    rhs = ball_sources()[0]
+    u0, p = np.array([50.0, 0.0]), np.array([[9.81, 1.0]])
+    one = [dict(kind="discrete", condition=always_true_source(), affect=noop_affect_source(), save_positions=(True, False))]
+    two = one + [dict(kind="discrete", condition=always_true_source(name="cb_true2"),
+                      affect=noop_affect_source(name="cb_noop2"), save_positions=(True, False))]
+    plain = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, (0.0, 3.0), 2, 2, save_everystep=True)
+    a = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, (0.0, 3.0), 2, 2, callbacks=one, save_everystep=True)
+    b = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, (0.0, 3.0), 2, 2, callbacks=two, save_everystep=True)
+    assert np.array_equal(a["ts"], plain["ts"])
+    assert len(b["ts"]) == 2 * len(a["ts"]) - 1
+    # every affect! counts as a modification: the FSAL derivative is re-evaluated once per accepted step
+    # (reset_fsal! in the next loopheader!, so not after the last one)
+    assert a["naccept"][0] == plain["naccept"][0] and a["nf"][0] == plain["nf"][0] + a["naccept"][0] - 1
