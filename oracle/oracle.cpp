@@ -628,7 +628,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
         R bottom_condition = get_condition(cb, bottom_t);
         if (event_last_time == callback_idx) {
             // nudge_tprev (:413-422): still within abstol of the last root => look just right of tprev
-            if (std::fabs(bottom_condition - last_event_error) <= (R)cb.abstol) bottom_t = tprev + dt * (R)cb.repeat_nudge;
+            if ((double)std::fabs(bottom_condition - last_event_error) <= cb.abstol) bottom_t = tprev + dt * (R)cb.repeat_nudge;
             else bottom_t = tprev;
             bottom_condition = get_condition(cb, bottom_t);
         }
@@ -637,7 +637,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
         R top_t = t;
         R top_sign = jl_sign(get_condition(cb, top_t));
         bool occurred = is_event(cb, bottom_sign, top_sign);
-        if (cb.interp_points != 0 && !occurred) {
+        if (cb.interp_points >= 2 && !occurred) {
             JlLinspace<R> ts(tprev, t, cb.interp_points);              // range(tprev, stop = t, length = interp_points)
             for (int i = 2; i <= cb.interp_points; ++i) {
                 top_t = (i == cb.interp_points) ? t : ts[i];           // the last element is `stop` exactly

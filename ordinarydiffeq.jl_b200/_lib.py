@@ -16,8 +16,10 @@ ALG_AUTOTSIT5_ROSENBROCK23, ALG_RODAS3P = 17, 18
 F64, F32 = 0, 1
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 FLAG_STATIC_SCHEDULE = 1
-RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN = range(6)
-RETCODE_NAMES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "DtLessThanMin", 4: "Unstable", 5: "DtNaN"}
+FLAG_NO_STEP_ROWS = 2
+RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN, RC_TERMINATED = range(7)
+RETCODE_NAMES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "DtLessThanMin", 4: "Unstable", 5: "DtNaN", 6: "Terminated"}
+CB_DISCRETE, CB_CONTINUOUS = 0, 1
 OK, EINVAL, ECOMPILE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
 
 
@@ -71,6 +73,40 @@ class B200Ragged(C.Structure):
     _fields_ = [("total_rows", C.c_int64), ("row_offsets", C.c_void_p), ("ts", C.c_void_p), ("us", C.c_void_p)]
 
 
+class B200CallbackSrc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("rootfind", C.c_int32),
+                ("condition_src", C.c_char_p), ("condition_name", C.c_char_p),
+                ("affect_src", C.c_char_p), ("affect_name", C.c_char_p),
+                ("affect_neg_src", C.c_char_p), ("affect_neg_name", C.c_char_p),
+                ("interp_points", C.c_int32), ("save_before", C.c_int32), ("save_after", C.c_int32), ("reserved", C.c_int32),
+                ("abstol", C.c_double), ("repeat_nudge", C.c_double)]
+
+
+def callback_array(callbacks):
+    """List of callback dicts -> (B200CallbackSrc array, n).  Keys: kind ("discrete" | "continuous"), condition (src, name),
+    affect (src, name) or None, affect_neg (continuous: defaults to affect; False/None-with-key = nothing),
+    rootfind ("left" | "right" | "none"), interp_points, abstol, repeat_nudge, save_positions."""
+    arr = (B200CallbackSrc * len(callbacks))()
+    for i, cb in enumerate(callbacks):
+        c = arr[i]
+        cont = cb["kind"] == "continuous"
+        c.kind = CB_CONTINUOUS if cont else CB_DISCRETE
+        c.condition_src, c.condition_name = _b(cb["condition"][0]), _b(cb["condition"][1])
+        aff = cb.get("affect")
+        if aff:
+            c.affect_src, c.affect_name = _b(aff[0]), _b(aff[1])
+        neg = cb.get("affect_neg", aff if cont else None)
+        if cont and neg:
+            c.affect_neg_src, c.affect_neg_name = _b(neg[0]), _b(neg[1])
+        c.rootfind = {"none": 0, "left": 1, "right": 2}[cb.get("rootfind", "left")]
+        c.interp_points = int(cb.get("interp_points", -1))
+        c.abstol = float(cb.get("abstol", -1.0))
+        c.repeat_nudge = float(cb.get("repeat_nudge", -1.0))
+        sp = cb.get("save_positions", (True, True))
+        c.save_before, c.save_after = int(bool(sp[0])), int(bool(sp[1]))
+    return arr, len(callbacks)
+
+
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
 OPT_TSTOPS = "-DB200_TSTOPS=1"
 OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
@@ -92,6 +128,7 @@ EXPORTS = [
     "b200ode_dense_eval_device", "b200ode_solve_dense", "b200ode_selftest_fastmath",
     "b200ode_multi_create", "b200ode_multi_destroy", "b200ode_multi_device_count", "b200ode_multi_compile",
     "b200ode_multi_program_destroy", "b200ode_multi_solve", "b200ode_multi_reduce_mean",
+    "b200ode_compile_callbacks", "b200ode_compile_only_callbacks",
 ]
 
 _lib = None
@@ -114,6 +151,9 @@ def lib():
     L.b200ode_last_error.restype = cp
     L.b200ode_version.restype = cp
     L.b200ode_compile.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, cp, cp, cp, cp, cp, cp, cp]
+    L.b200ode_compile_callbacks.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, cp, cp, cp, cp, cp, cp, vp, i32, cp]
+    L.b200ode_compile_only_callbacks.argtypes = [i32, i32, i32, i32, cp, cp, vp, i32, cp,
+                                                 C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
     L.b200ode_program_destroy.argtypes = [vp]
     L.b200ode_program_info.argtypes = [vp, C.POINTER(B200ProgramInfo)]
     L.b200ode_compile_only.argtypes = [i32, i32, i32, i32, cp, cp, cp, cp, cp, cp, cp,
@@ -162,15 +202,20 @@ def _b(s):
 
 
 def compile_only(alg, dtype, n, np_, rhs_src, rhs_name, jac_src=None, jac_name=None, tgrad_src=None,
-                 tgrad_name=None, extra_options=None):
+                 tgrad_name=None, extra_options=None, callbacks=None):
     """NVRTC-compile without a GPU; returns (cubin_bytes, log)."""
     L = lib()
     cubin = C.c_void_p()
     size = C.c_size_t()
     log = C.c_void_p()
-    rc = L.b200ode_compile_only(alg, dtype, n, np_, _b(rhs_src), _b(rhs_name), _b(jac_src), _b(jac_name),
-                                _b(tgrad_src), _b(tgrad_name), _b(extra_options),
-                                C.byref(cubin), C.byref(size), C.byref(log))
+    if callbacks:
+        arr, ncb = callback_array(callbacks)
+        rc = L.b200ode_compile_only_callbacks(alg, dtype, n, np_, _b(rhs_src), _b(rhs_name), C.cast(arr, C.c_void_p), ncb,
+                                              _b(extra_options), C.byref(cubin), C.byref(size), C.byref(log))
+    else:
+        rc = L.b200ode_compile_only(alg, dtype, n, np_, _b(rhs_src), _b(rhs_name), _b(jac_src), _b(jac_name),
+                                    _b(tgrad_src), _b(tgrad_name), _b(extra_options),
+                                    C.byref(cubin), C.byref(size), C.byref(log))
     log_s = C.string_at(log.value).decode("utf-8", "replace") if log.value else ""
     if log.value:
         L.b200ode_free(log)
@@ -203,9 +248,9 @@ class Handle:
             pass
 
     def compile(self, alg, dtype, n, np_, rhs_src, rhs_name, jac_src=None, jac_name=None, tgrad_src=None,
-                tgrad_name=None, extra_options=None):
+                tgrad_name=None, extra_options=None, callbacks=None):
         return Program(self, alg, dtype, n, np_, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
-                       extra_options)
+                       extra_options, callbacks)
 
     def measure_fma_peak(self, dtype=F64):
         tf, mhz = C.c_double(), C.c_double()
@@ -221,7 +266,7 @@ class Handle:
 
 class Program:
     def __init__(self, handle, alg, dtype, n, np_, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
-                 extra_options):
+                 extra_options, callbacks=None):
         self.handle = handle
         self.alg, self.dtype, self.n, self.np = alg, dtype, n, np_
         self.everystep = bool(extra_options) and OPT_EVERYSTEP in extra_options
@@ -230,8 +275,15 @@ class Program:
             if tok.startswith("-DB200_SAVE_IDXS="):
                 self.nsave = len(tok.split("=", 1)[1].split(","))
         self._p = C.c_void_p()
-        check(lib().b200ode_compile(handle._h, C.byref(self._p), alg, dtype, n, np_, _b(rhs_src), _b(rhs_name),
-                                    _b(jac_src), _b(jac_name), _b(tgrad_src), _b(tgrad_name), _b(extra_options)))
+        self.callbacks = bool(callbacks)
+        if callbacks:
+            arr, ncb = callback_array(callbacks)
+            check(lib().b200ode_compile_callbacks(handle._h, C.byref(self._p), alg, dtype, n, np_, _b(rhs_src), _b(rhs_name),
+                                                  _b(jac_src), _b(jac_name), _b(tgrad_src), _b(tgrad_name),
+                                                  C.cast(arr, C.c_void_p), ncb, _b(extra_options)))
+        else:
+            check(lib().b200ode_compile(handle._h, C.byref(self._p), alg, dtype, n, np_, _b(rhs_src), _b(rhs_name),
+                                        _b(jac_src), _b(jac_name), _b(tgrad_src), _b(tgrad_name), _b(extra_options)))
         info = B200ProgramInfo()
         check(lib().b200ode_program_info(self._p, C.byref(info)))
         self.info = {k: getattr(info, k) for k, _ in B200ProgramInfo._fields_}

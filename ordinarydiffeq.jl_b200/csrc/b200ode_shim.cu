@@ -125,6 +125,7 @@ struct b200ode_program_s {
     bool everystep = false;      // compiled with -DB200_EVERYSTEP=1 (ragged save_everystep output)
     bool tstops = false;         // compiled with -DB200_TSTOPS=1
     bool adaptive = true;        // false: compiled with -DB200_ADAPTIVE=0 (fixed dt)
+    bool callbacks = false;      // compiled with a CallbackSet (b200ode_compile_callbacks)
     int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
     B200ProgramInfo info{};
@@ -217,12 +218,87 @@ int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src
     return B200ODE_OK;
 }
 
+// The CallbackSet of a program: forward declarations + the user's condition / affect sources, the parameter table
+// B200_CB_TABLE and the two dispatchers device/b200_callbacks.cuh calls.  Continuous callbacks come first, then the
+// discrete ones, each group in the caller's order (CallbackSet(continuous..., discrete...)).
+int callbacks_source(int alg, int dtype, const B200CallbackSrc* cbs, int ncb, bool everystep, bool coop, std::string& out) {
+    if (!cbs || ncb < 1 || ncb > 16) return fail(B200ODE_EINVAL, "callbacks: between 1 and 16 callbacks");
+    if (alg != B200ODE_ALG_TSIT5 || coop) return fail(B200ODE_EUNSUPPORTED, "callbacks are available for Tsit5 (one trajectory per thread)");
+    std::vector<int> order;
+    for (int pass = 1; pass >= 0; --pass)
+        for (int i = 0; i < ncb; ++i) {
+            if (cbs[i].kind != B200ODE_CB_DISCRETE && cbs[i].kind != B200ODE_CB_CONTINUOUS)
+                return fail(B200ODE_EINVAL, "callbacks: kind must be B200ODE_CB_DISCRETE or B200ODE_CB_CONTINUOUS");
+            if (cbs[i].kind == pass) order.push_back(i);
+        }
+    int ncc = 0;
+    for (int i = 0; i < ncb; ++i) ncc += (cbs[i].kind == B200ODE_CB_CONTINUOUS);
+    std::vector<std::string> emitted;
+    auto add_fn = [&](const char* src, const char* name, bool is_condition) -> int {
+        if (!is_identifier(name)) return fail(B200ODE_EINVAL, "callbacks: a function name is not an identifier");
+        for (auto& e : emitted) if (e == name) return B200ODE_OK;          // one definition may serve several callbacks
+        if (!src) return fail(B200ODE_EINVAL, std::string("callbacks: no source for ") + name);
+        emitted.push_back(name);
+        if (is_condition) out += std::string("__device__ __forceinline__ real ") + name + "(const real* u, const real* p, const real t);\n";
+        else out += std::string("__device__ __forceinline__ void ") + name + "(real* u, real* p, const real t, int* terminate);\n";
+        out += strip_includes(src);
+        out += "\n";
+        return B200ODE_OK;
+    };
+    out += "// ---- user source (callbacks) ----\n";
+    char buf[512];
+    std::string table = "#define B200_CB_TABLE { ", cond = "", aff = "";
+    for (size_t k = 0; k < order.size(); ++k) {
+        const B200CallbackSrc& c = cbs[order[k]];
+        const bool cont = c.kind == B200ODE_CB_CONTINUOUS;
+        int rc = add_fn(c.condition_src, c.condition_name, true);
+        if (rc) return rc;
+        const bool has_aff = c.affect_name != nullptr, has_neg = cont && c.affect_neg_name != nullptr;
+        if (has_aff && (rc = add_fn(c.affect_src, c.affect_name, false))) return rc;
+        if (has_neg && (rc = add_fn(c.affect_neg_src, c.affect_neg_name, false))) return rc;
+        if (!everystep && (c.save_before || c.save_after))
+            return fail(B200ODE_EUNSUPPORTED, "callbacks with save_positions need the ragged output: compile with B200ODE_OPT_EVERYSTEP "
+                                              "(and pass B200ODE_FLAG_NO_STEP_ROWS for save_everystep = false), or use save_positions = (false, false)");
+        if (c.rootfind < -1 || c.rootfind > 2) return fail(B200ODE_EINVAL, "callbacks: rootfind must be -1 (default), 0, 1 or 2");
+        const int rootfind = c.rootfind < 0 ? 1 : c.rootfind;
+        const int ip = c.interp_points < 0 ? 10 : c.interp_points;
+        const double eps = dtype == B200ODE_F32 ? 1.1920928955078125e-07 : 2.220446049250313e-16;
+        // abstol = 10eps (of Float64 in SciMLBase's constructor; converted to the real type when it is compared)
+        const double abstol = c.abstol < 0 ? 10.0 * 2.220446049250313e-16 : c.abstol;
+        (void)eps;
+        const double nudge = c.repeat_nudge < 0 ? 0.01 : c.repeat_nudge;
+        snprintf(buf, sizeof buf, "{%d, %d, %d, %d, %d, %d, %d, %.17g, (real)%.17g}, ", cont ? 1 : 0, has_aff ? 1 : 0,
+                 has_neg ? 1 : 0, rootfind, ip, c.save_before ? 1 : 0, c.save_after ? 1 : 0, abstol, nudge);
+        table += buf;
+        cond += "        case " + std::to_string(k) + ": return " + c.condition_name + "(u, p, t);\n";
+        aff += "        case " + std::to_string(k) + ": ";
+        if (has_neg) aff += std::string("if (neg) { ") + c.affect_neg_name + "(u, p, t, terminate); break; } ";
+        if (has_aff) aff += std::string("if (!neg) { ") + c.affect_name + "(u, p, t, terminate); } ";
+        aff += "break;\n";
+    }
+    table += "}\n";
+    out += "#define B200_CALLBACKS 1\n#define B200_NCB " + std::to_string(ncb) + "\n#define B200_NCC " + std::to_string(ncc) + "\n";
+    out += table;
+    out += "__device__ __forceinline__ real b200_cb_condition(int k, const real* u, const real* p, real t) {\n    switch (k) {\n" + cond +
+           "    }\n    return (real)0;\n}\n";
+    out += "__device__ __forceinline__ void b200_cb_affect(int k, bool neg, real* u, real* p, real t, int* terminate) {\n    switch (k) {\n" + aff +
+           "    }\n}\n";
+    return B200ODE_OK;
+}
+
 // Assemble the translation unit and run NVRTC.
 int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                 const char* jac_src, const char* jac_name, const char* tgrad_src, const char* tgrad_name,
-                const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms, int* coop_l = nullptr) {
+                const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms, int* coop_l = nullptr,
+                const B200CallbackSrc* cbs = nullptr, int ncb = 0) {
     int rc = validate_compile_args(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name);
     if (rc) return rc;
+    std::string cb_text;
+    if (ncb > 0) {
+        const bool everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
+        rc = callbacks_source(alg, dtype, cbs, ncb, everystep, extra_options && strstr(extra_options, "-DB200_COOP=1"), cb_text);
+        if (rc) return rc;
+    }
     bool stiff = is_stiff_alg(alg);
     auto t_begin = std::chrono::steady_clock::now();
 
@@ -299,6 +375,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
             tu += strip_includes(tgrad_src);
         }
     }
+    tu += cb_text;
     tu += "// ---- steppers ----\n";
     if (coop) tu += "#define B200_USER_RHS_COMP(i,u,p,t) (B200UserExact().B200_USER_COMP_NAME((i),(u),(p),(t)))\n";
     else tu += std::string("#define B200_USER_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
@@ -353,6 +430,10 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     // CTA per SM at 128 registers (FP64) / three 256-thread CTAs at 80 registers (FP32)
     const bool small_explicit = !stiff && words <= 8 &&
                                 (alg == B200ODE_ALG_TSIT5 || alg == B200ODE_ALG_DP5 || alg == B200ODE_ALG_BS3);
+    if (ncb > 0 && !has_block && !has_minb) {       // event handling needs registers beyond the step loop's
+        opts.push_back("-DB200_BLOCK=128"); opts.push_back("-DB200_MINBLOCKS=3");
+        has_block = has_minb = true;
+    }
     if (small_explicit && !has_block && !has_minb) {
         if (dtype == B200ODE_F32) { opts.push_back("-DB200_BLOCK=256"); opts.push_back("-DB200_MINBLOCKS=3"); }
         else { opts.push_back("-DB200_BLOCK=512"); opts.push_back("-DB200_MINBLOCKS=1"); }
@@ -831,9 +912,47 @@ int b200ode_compile_only(int alg, int dtype, int n, int np, const char* rhs_src,
     return B200ODE_OK;
 }
 
+static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dtype, int n, int np,
+                        const char* rhs_src, const char* rhs_name, const char* jac_src, const char* jac_name,
+                        const char* tgrad_src, const char* tgrad_name, const char* extra_options,
+                        const B200CallbackSrc* cbs, int ncb);
 int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, int n, int np,
                     const char* rhs_src, const char* rhs_name, const char* jac_src, const char* jac_name,
                     const char* tgrad_src, const char* tgrad_name, const char* extra_options) {
+    return compile_impl(h, out, alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name, extra_options,
+                        nullptr, 0);
+}
+int b200ode_compile_callbacks(b200ode_handle h, b200ode_program* out, int alg, int dtype, int n, int np,
+                              const char* rhs_src, const char* rhs_name, const char* jac_src, const char* jac_name,
+                              const char* tgrad_src, const char* tgrad_name, const B200CallbackSrc* callbacks, int ncallbacks,
+                              const char* extra_options) {
+    if (ncallbacks < 0 || (ncallbacks > 0 && !callbacks)) return fail(B200ODE_EINVAL, "callbacks is NULL");
+    return compile_impl(h, out, alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name, extra_options,
+                        callbacks, ncallbacks);
+}
+int b200ode_compile_only_callbacks(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
+                                   const B200CallbackSrc* callbacks, int ncallbacks, const char* extra_options,
+                                   void** cubin, size_t* cubin_bytes, char** log) {
+    std::vector<char> cb; std::string lg;
+    if (cubin) *cubin = nullptr;
+    if (cubin_bytes) *cubin_bytes = 0;
+    if (log) *log = nullptr;
+    int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, nullptr, nullptr, nullptr, nullptr, extra_options, cb, lg, nullptr,
+                         nullptr, callbacks, ncallbacks);
+    if (log) {
+        const std::string& src = (rc != B200ODE_OK) ? g_last_error : lg;
+        *log = (char*)malloc(src.size() + 1);
+        memcpy(*log, src.c_str(), src.size() + 1);
+    }
+    if (rc) return rc;
+    if (cubin) { *cubin = malloc(cb.size()); memcpy(*cubin, cb.data(), cb.size()); }
+    if (cubin_bytes) *cubin_bytes = cb.size();
+    return B200ODE_OK;
+}
+static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dtype, int n, int np,
+                        const char* rhs_src, const char* rhs_name, const char* jac_src, const char* jac_name,
+                        const char* tgrad_src, const char* tgrad_name, const char* extra_options,
+                        const B200CallbackSrc* cbs, int ncb) {
     if (!h || !out) return fail(B200ODE_EINVAL, "handle/out is NULL");
     *out = nullptr;
     CUDA_TRY(cudaSetDevice(h->device));
@@ -841,8 +960,9 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     prog->h = h; prog->alg = alg; prog->dtype = dtype; prog->n = n; prog->np = np;
     std::string log; double ms = 0;
     int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
-                         extra_options, prog->cubin, log, &ms, &prog->coop_l);
+                         extra_options, prog->cubin, log, &ms, &prog->coop_l, cbs, ncb);
     if (rc) { delete prog; return rc; }
+    prog->callbacks = ncb > 0;
     prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
     prog->tstops = extra_options && strstr(extra_options, "-DB200_TSTOPS=1");
     prog->adaptive = !(extra_options && strstr(extra_options, "-DB200_ADAPTIVE=0"));
@@ -858,7 +978,7 @@ int b200ode_compile(b200ode_handle h, b200ode_program* out, int alg, int dtype, 
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&prog->k_initdt, prog->lib, "b200_initdt");
     if (e == cudaSuccess && prog->everystep && prog->nsave == n && alg != B200ODE_ALG_ROSENBROCK32 &&
-        alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23)
+        alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 && !prog->callbacks)
         e = cudaLibraryGetKernel(&prog->k_dense, prog->lib, "b200_dense_eval");
     if (e != cudaSuccess) {
         cudaLibraryUnload(prog->lib); delete prog;
@@ -1211,7 +1331,7 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
     if (rc) return rc;
     if (o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "dense output excludes saveat (dense = save_everystep && isempty(saveat), solve.jl:139)");
     if (o->save_start == 0) return fail(B200ODE_EINVAL, "dense output needs save_start");
-    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows) or for the composite algorithm");
+    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows), for the composite algorithm or with callbacks");
     for (int j = 1; j < nq; ++j) if (!(tq[j] >= tq[j - 1])) return fail(B200ODE_EINVAL, "tq must be ascending");
     const long long N = hp->trajectories;
     if (N == 0) return B200ODE_OK;

@@ -118,6 +118,7 @@ typedef B200BS3 B200Stepper;
 #define B200_RC_DTLESSTHANMIN 3
 #define B200_RC_UNSTABLE 4
 #define B200_RC_DTNAN 5
+#define B200_RC_TERMINATED 6      // terminate!(integrator) from a callback
 
 struct B200Params {
     long long N;              // trajectories handled by this launch
@@ -160,6 +161,7 @@ struct B200Params {
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
+#define B200_FLAG_NO_STEP_ROWS 2      // save_everystep programs: ragged rows without the per-step rows (saveat + callback rows)
 
 // save_idxs (solve.jl kwarg; _savevalues! integrator_utils.jl:368-375, ode_interpolant(Θ, integrator, idxs, ...)):
 // -DB200_SAVE_IDXS=i0,i1,... (0-based) makes every saved row hold only those components, in that order.
@@ -191,6 +193,12 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 
 #ifndef B200_EVERYSTEP
 #define B200_EVERYSTEP 0      // 1: save_everystep = true (integrator_utils.jl:385-411), ragged rows
+#endif
+#ifndef B200_CALLBACKS
+#define B200_CALLBACKS 0      // 1: the program carries a CallbackSet (device/b200_callbacks.cuh; Tsit5)
+#endif
+#if B200_CALLBACKS && (B200_COOP || B200_ALG != B200_ALG_TSIT5)
+#error "callbacks are available for Tsit5"
 #endif
 #if (B200_EVERYSTEP || defined(B200_SAVE_IDXS)) && B200_COOP
 #error "save_everystep / save_idxs are not available in the lane-group kernel"
@@ -383,6 +391,11 @@ struct B200Traj {
 #if B200_IS_ROSENBROCK
     int njacs, nw, nsolve;
 #endif
+#if B200_CALLBACKS
+    int event_last;             // integrator.event_last_time: 1-based index of the continuous callback that ended the last step
+    real last_event_error;      // integrator.last_event_error
+    bool reeval_fsal, terminated;
+#endif
 };
 
 B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, const real* v, real dt_stages = (real)0) {
@@ -477,7 +490,14 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     T.naccept = 0; T.nreject = 0;
     T.accept = false; T.tstop_flag = false;
     T.retcode = B200_RC_DEFAULT;
+#if B200_CALLBACKS
+    T.event_last = 0; T.last_event_error = (real)0; T.reeval_fsal = false; T.terminated = false;
+#endif
 }
+
+#if B200_CALLBACKS
+#include "b200_callbacks.cuh"
+#endif
 
 // One pass of the while-loop body of solve!.  Returns true when the trajectory is finished.
 // `amask` = the lanes of this warp that execute this call; the short accept/reject
@@ -512,7 +532,12 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #pragma unroll
             for (int c = 0; c < B200_N; ++c) T.uprev[c] = T.u[c];
             T.dt = T.dtpropose;
+#if B200_CALLBACKS
+            // update_fsal! (integrator_utils.jl:215-239): reeval_fsal => reset_fsal!
+            if (T.reeval_fsal) T.st.reset_fsal(T.u, T.p, T.t, T.nf); else T.st.accept();
+#else
             T.st.accept();
+#endif
             b200_modify_dt_for_tstops(P, T, dist, tol100);
         }
         // (rejected step: step_reject_controller!'s dt /= min(inv(qmin), q11/gamma) was applied by the loopfooter
@@ -570,6 +595,9 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     __syncwarp(amask);
     if (!ok) return true;
     // ---- loopfooter! ----
+#if B200_CALLBACKS
+    T.reeval_fsal = false;                              // loopfooter_reset!
+#endif
     const real ttmp = T.t + T.dt;
 #if !B200_ADAPTIVE
     // not adaptive (integrator_utils.jl:650-659): every step is accepted, dtpropose = dt, no controller
@@ -621,6 +649,10 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
 #endif
         // handle_callbacks! -> savevalues!
+#if B200_CALLBACKS
+        b200_handle_callbacks(P, idx, T);
+        if (T.terminated) return true;                  // terminate! emptied the tstops
+#else
         {
             bool dense_ready = false;
             real rdt = (real)0;         // refined 1/dt, shared by the rows of this step
@@ -655,6 +687,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                 b200_emit(P, idx, T, T.t, T.u, dt_stages);
 #endif
         }
+#endif  // !B200_CALLBACKS
 #if B200_TSTOPS
         // handle_tstop! (integrator_utils.jl:1290-1314): pop every copy of a stop time that was reached;
         // the list ends with tf, whose pop ends the solve (the return below)
@@ -815,7 +848,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
 }
 // (rows restricted by save_idxs cannot restart a step; Rosenbrock32's fsalfirst is f(uprev + dt k2) of the previous
 // step, not f of the saved row, so its stages are not recomputable from (row, dt) either)
-#if B200_EVERYSTEP && !defined(B200_SAVE_IDXS) && B200_ALG != B200_ALG_ROS32 && !B200_COMPOSITE
+#if B200_EVERYSTEP && !defined(B200_SAVE_IDXS) && B200_ALG != B200_ALG_ROS32 && !B200_COMPOSITE && !B200_CALLBACKS
 // ---------------------------------------------------------------------------
 // sol(tq) for every trajectory, post hoc, from the ragged per-step rows — ode_interpolation
 // (dense/generic_dense.jl:833-867: interval search :845-849, dt = ts[i+] - ts[i-], Θ :858-859,

@@ -126,6 +126,49 @@ struct B200Tsit5 {
         for (int i = 0; i < B200_N; ++i) k1[i] = k7[i];
     }
 
+    // reset_fsal! (integrator_utils.jl:1325-1343): fsalfirst = f(u, p, t); nf += 1 (after a callback modified u)
+    B200_D void reset_fsal(const real* u, const real* p, real t, int& nf) {
+        B200_RHS(k1, u, p, t);
+        nf += 1;
+    }
+
+    // _ode_addsteps!(k, t, uprev, u, dt, f, p, ::Tsit5ConstantCache, always_calc_begin = true) (tsit_perform_step.jl:40-82):
+    // all seven stages again from uprev with the (shortened) dt, after change_t_via_interpolation! moved t to an event.
+    // Note `uprev + dt*(a21*k1)` here against perform_step!'s `a = dt*a21; uprev + a*k1`; stats are not touched.
+    B200_D void addsteps_always(const real* uprev, const real* p, real t, real dt) {
+        const real c1 = B200_TSIT5_C.c1, c2 = B200_TSIT5_C.c2, c3 = B200_TSIT5_C.c3, c4 = B200_TSIT5_C.c4;
+#define B200_T5(name) const real name = B200_TSIT5_C.name
+        B200_T5(a21); B200_T5(a31); B200_T5(a32); B200_T5(a41); B200_T5(a42); B200_T5(a43);
+        B200_T5(a51); B200_T5(a52); B200_T5(a53); B200_T5(a54);
+        B200_T5(a61); B200_T5(a62); B200_T5(a63); B200_T5(a64); B200_T5(a65);
+        B200_T5(a71); B200_T5(a72); B200_T5(a73); B200_T5(a74); B200_T5(a75); B200_T5(a76);
+#undef B200_T5
+        real tmp[B200_N];
+        B200_RHS(k1, uprev, p, t);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) tmp[i] = b200_fma(dt, a21 * k1[i], uprev[i]);
+        B200_RHS(k2, tmp, p, b200_fma(c1, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) tmp[i] = b200_fma(dt, b200_fma(a32, k2[i], a31 * k1[i]), uprev[i]);
+        B200_RHS(k3, tmp, p, b200_fma(c2, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt, b200_fma(a43, k3[i], b200_fma(a42, k2[i], a41 * k1[i])), uprev[i]);
+        B200_RHS(k4, tmp, p, b200_fma(c3, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt, b200_fma(a54, k4[i], b200_fma(a53, k3[i], b200_fma(a52, k2[i], a51 * k1[i]))), uprev[i]);
+        B200_RHS(k5, tmp, p, b200_fma(c4, dt, t));
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt, b200_fma(a65, k5[i], b200_fma(a64, k4[i], b200_fma(a63, k3[i], b200_fma(a62, k2[i], a61 * k1[i])))), uprev[i]);
+        B200_RHS(k6, tmp, p, t + dt);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i)
+            tmp[i] = b200_fma(dt, b200_fma(a76, k6[i], b200_fma(a75, k5[i], b200_fma(a74, k4[i], b200_fma(a73, k3[i], b200_fma(a72, k2[i], a71 * k1[i]))))), uprev[i]);
+        B200_RHS(k7, tmp, p, t + dt);
+    }
+
     // nothing to prepare: all 7 stages are kept (ode_addsteps! is a no-op once length(k) >= 7)
     B200_D void dense_prepare(const real*, const real*, const real*, real, real) {}
 

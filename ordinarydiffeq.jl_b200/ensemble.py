@@ -152,6 +152,60 @@ class CSource:
         self.source, self.name = source, name
 
 
+# ---- callbacks (lib/DiffEqBase/src/callbacks.jl; constructors are SciMLBase's, EXT) --------------------------------------
+class ContinuousCallback:
+    """ContinuousCallback(condition, affect!, affect_neg! = affect!; rootfind = LeftRootFind, save_positions = (true, true),
+    interp_points = 10, abstol = 10eps(), repeat_nudge = 1//100).  condition / affect! are CSource objects:
+        condition:  real NAME(const real* u, const real* p, const real t)
+        affect!:    void NAME(real* u, real* p, const real t, int* terminate)      (*terminate = 1 is terminate!(integrator))
+    Pass affect=None or affect_neg=None for `nothing` (events of that direction are ignored)."""
+    _same = object()
+
+    def __init__(self, condition, affect, affect_neg=_same, rootfind="left", save_positions=(True, True),
+                 interp_points=10, abstol=None, repeat_nudge=None):
+        self.condition, self.affect = condition, affect
+        self.affect_neg = affect if affect_neg is ContinuousCallback._same else affect_neg
+        self.rootfind, self.save_positions, self.interp_points = rootfind, tuple(save_positions), interp_points
+        self.abstol, self.repeat_nudge = abstol, repeat_nudge
+
+    def spec(self):
+        d = dict(kind="continuous", condition=(self.condition.source, self.condition.name),
+                 affect=None if self.affect is None else (self.affect.source, self.affect.name),
+                 affect_neg=None if self.affect_neg is None else (self.affect_neg.source, self.affect_neg.name),
+                 rootfind=self.rootfind, save_positions=self.save_positions, interp_points=self.interp_points)
+        if self.abstol is not None:
+            d["abstol"] = self.abstol
+        if self.repeat_nudge is not None:
+            d["repeat_nudge"] = self.repeat_nudge
+        return d
+
+
+class DiscreteCallback:
+    """DiscreteCallback(condition, affect!; save_positions = (true, true)); the condition holds when its C function
+    returns a non-zero value."""
+
+    def __init__(self, condition, affect, save_positions=(True, True)):
+        self.condition, self.affect, self.save_positions = condition, affect, tuple(save_positions)
+
+    def spec(self):
+        return dict(kind="discrete", condition=(self.condition.source, self.condition.name),
+                    affect=None if self.affect is None else (self.affect.source, self.affect.name),
+                    save_positions=self.save_positions)
+
+
+class CallbackSet:
+    """CallbackSet(cb...): continuous callbacks are handled before the discrete ones, each group in the given order."""
+
+    def __init__(self, *cbs):
+        flat = []
+        for c in cbs:
+            flat.extend(c.callbacks if isinstance(c, CallbackSet) else [c])
+        self.callbacks = ([c for c in flat if isinstance(c, ContinuousCallback)] +
+                          [c for c in flat if isinstance(c, DiscreteCallback)])
+        if len(self.callbacks) != len(flat):
+            raise TypeError("CallbackSet takes ContinuousCallback / DiscreteCallback objects")
+
+
 class ODEFunction:
     """ODEFunction(f; jac, tgrad).  `f` is either a Python callable f(u, p, t) -> [exprs] traced with
     sympy (stand-in for Symbolics tracing) or a CSource; jac/tgrad likewise, or None to have them
@@ -327,7 +381,7 @@ class EnsembleSolution:
 
 # ---- solve ------------------------------------------------------------------------------------
 _ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "save_idxs", "tstops", "reltol",
-               "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags", "save_on"}
+               "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags", "save_on", "callback"}
 # accepted and ignored: they do not change the numbers (logging / progress / error-statistics switches of solve.jl:166-181)
 _IGNORED_KW = {"verbose", "progress", "progress_steps", "progress_name", "progress_message", "progress_id",
                "timeseries_errors", "dense_errors", "alias", "userdata"}
@@ -344,7 +398,7 @@ def _handle(device):
     return _handles[device]
 
 
-def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True):
+def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True, callbacks=None):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
     extra = []
     if everystep:
@@ -356,12 +410,12 @@ def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, t
     if save_idxs is not None:
         extra.append(_lib.opt_save_idxs(save_idxs))
     extra = " ".join(extra) or None
-    key = (handle.device, alg.alg_id, f32, n, np_, rhs, jac, tg, extra)
+    key = (handle.device, alg.alg_id, f32, n, np_, rhs, jac, tg, extra, repr(callbacks))
     if key not in _program_cache:
         _program_cache[key] = handle.compile(alg.alg_id, _lib.F32 if f32 else _lib.F64, n, np_, rhs[0], rhs[1],
                                              jac[0] if jac else None, jac[1] if jac else None,
                                              tg[0] if tg else None, tg[1] if tg else None,
-                                             extra_options=extra)
+                                             extra_options=extra, callbacks=callbacks)
     return _program_cache[key]
 
 
@@ -442,15 +496,29 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     if dense_kw and not dense_ok:
         raise NotImplementedError("dense=true is served for save_everystep solves without saveat / save_idxs / tstops "
                                   "(the stages are recomputed from the saved steps); not for Rosenbrock32")
+    # callback = ContinuousCallback / DiscreteCallback / CallbackSet: events on the device (Tsit5).  Rows forced by
+    # save_positions make the output ragged even when save_everystep = false.
+    cb_specs, cb_flags, ragged = None, 0, everystep
+    if kw.get("callback") is not None:
+        cbset = kw["callback"] if isinstance(kw["callback"], CallbackSet) else CallbackSet(kw["callback"])
+        if cbset.callbacks:
+            if not isinstance(alg, Tsit5):
+                raise NotImplementedError("callbacks are available with Tsit5()")
+            cb_specs = [c.spec() for c in cbset.callbacks]
+            if any(any(c.save_positions) for c in cbset.callbacks) and not everystep:
+                ragged, cb_flags = True, _lib.FLAG_NO_STEP_ROWS
+            dense_ok = False
+            if dense_kw:
+                raise NotImplementedError("dense=true is not available with callbacks")
     handle = _handle(ensemblealg.device)
-    program = get_program(handle, alg, prob.f, n, np_, f32, everystep, save_idxs, tstops is not None, adaptive)
+    program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None, adaptive, cb_specs)
 
     def run(u0, p, ntraj, flags=0):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
                       dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
                       saveat=grid if grid else None, save_start=save_start, save_end=save_end,
-                      flags=flags, tstops=tstops)
-        if everystep:
+                      flags=flags | cb_flags, tstops=tstops)
+        if ragged:
             return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
         return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
 

@@ -1019,3 +1019,111 @@ def test_autotsit5_robertson_and_everystep(pkg, handle, oracle):
             pkg.lowlevel.solve_host_dense(prog, U0, p, (0.0, 100.0), [1.0, 2.0])
     finally:
         prog.close()
+
+
+# ---- callbacks (Tsit5): ContinuousCallback / DiscreteCallback against the oracle -------------------------------------------
+def _ball_ensemble(pkg, N, f32):
+    """Bouncing balls with their own gravity and restitution: p[i] = (g_i, e_i)."""
+    U = pkg.problems_library.splitmix64_uniform
+    idx = np.arange(N, dtype=np.uint64)
+    p = np.stack([9.81 * (0.5 + U(idx, 0)), 0.8 + 0.2 * U(idx, 1)], axis=1)
+    return p.astype(np.float32 if f32 else np.float64)
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_callbacks_bouncing_ball_parity(pkg, handle, oracle, f32):
+    from helpers import ball_sources, always_true_source, noop_affect_source
+    rhs, cond, bounce, stop = ball_sources(f32)
+    N = 777
+    p = _ball_ensemble(pkg, N, f32)
+    u0 = np.array([50.0, 0.0])
+    dt = pkg.F32 if f32 else pkg.F64
+    bounce_cb = dict(kind="continuous", condition=cond, affect=None, affect_neg=bounce)
+    cases = [
+        ([bounce_cb], {}, 0),
+        ([dict(bounce_cb, interp_points=0, rootfind="right")], {"saveat": [1.0, 2.5, 7.0]}, 0),
+        ([dict(bounce_cb, save_positions=(True, False))], {"saveat": [0.5 * k for k in range(1, 30)]}, pkg._lib.FLAG_NO_STEP_ROWS),
+        ([dict(kind="continuous", condition=cond, affect=stop)], {}, 0),                     # terminate! at the first hit
+        ([bounce_cb, dict(kind="discrete", condition=always_true_source(f32), affect=noop_affect_source(f32),
+                          save_positions=(False, True))], {}, 0),
+    ]
+    for cbs, kw, flags in cases:
+        prog = handle.compile(pkg.ALG_TSIT5, dt, 2, 2, rhs[0], rhs[1], extra_options=pkg._lib.OPT_EVERYSTEP, callbacks=cbs)
+        try:
+            g = pkg.lowlevel.solve_host_everystep(prog, u0, p, (0.0, 15.0), flags=flags, **kw)
+            o = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, (0.0, 15.0), 2, 2, f32=f32, callbacks=cbs,
+                             save_everystep=(flags == 0), ragged_saveat=(flags != 0), **kw)
+            _assert_same_ragged(g, o)
+            if cbs[0].get("affect") is stop:
+                assert (g["retcode"] == pkg._lib.RC_TERMINATED).all() and (g["t_final"] < 15.0).all()
+            else:
+                assert (g["retcode"] == 1).all()
+        finally:
+            prog.close()
+    # rectangular saveat output: save_positions = (false, false)
+    cbs = [dict(bounce_cb, save_positions=(False, False))]
+    prog = handle.compile(pkg.ALG_TSIT5, dt, 2, 2, rhs[0], rhs[1], callbacks=cbs)
+    try:
+        grid = [0.25 * k for k in range(1, 61)]
+        g = pkg.lowlevel.solve_host(prog, u0, p, (0.0, 15.0), saveat=grid)
+        o = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, (0.0, 15.0), 2, 2, f32=f32, callbacks=cbs, saveat=grid)
+        assert_same_result(g, o)
+        assert (g["us"][:, :, 0] > -1e-3).all()            # the balls stay above the floor
+    finally:
+        prog.close()
+    with pytest.raises(pkg.B200Error):                      # save_positions need the ragged output
+        handle.compile(pkg.ALG_TSIT5, dt, 2, 2, rhs[0], rhs[1], callbacks=[bounce_cb])
+
+
+def test_callbacks_parameter_change_and_lorenz_events(pkg, handle, oracle):
+    """A discrete callback that changes the trajectory's own parameter, and sign-change events of a chaotic state:
+    Lorenz with a section at x = 0 (both directions) that flips nothing but saves, plus a one-shot rho kick."""
+    pl = pkg.problems_library
+    rhs = pl.lorenz_source(False)
+    T = "double"
+    cond = ("%s lz_sec(const %s* u, const %s* p, const %s t) { return u[0]; }\n" % (T, T, T, T), "lz_sec")
+    mark = ("void lz_mark(%s* u, %s* p, const %s t, int* terminate) { u[2] = u[2] + 0.0; }\n" % (T, T, T), "lz_mark")
+    dcond = ("%s lz_kick_c(const %s* u, const %s* p, const %s t) { return (t >= 5.0 && p[1] < 100.0) ? 1.0 : 0.0; }\n" % (T, T, T, T), "lz_kick_c")
+    kick = ("void lz_kick(%s* u, %s* p, const %s t, int* terminate) { p[1] = p[1] + 100.0; }\n" % (T, T, T), "lz_kick")
+    cbs = [dict(kind="continuous", condition=cond, affect=mark),
+           dict(kind="discrete", condition=dcond, affect=kick, save_positions=(False, False))]
+    N = 500
+    p = pl.lorenz_params(N)
+    prog = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1], extra_options=pkg._lib.OPT_EVERYSTEP, callbacks=cbs)
+    try:
+        g = pkg.lowlevel.solve_host_everystep(prog, U0, p, (0.0, 10.0))
+        o = oracle.solve(oracle.ALG_TSIT5, rhs, U0, p, (0.0, 10.0), 3, 3, callbacks=cbs, save_everystep=True)
+        _assert_same_ragged(g, o)
+        assert (g["retcode"] == 1).all()
+    finally:
+        prog.close()
+
+
+def test_high_level_callbacks(pkg, oracle):
+    """solve(EnsembleProblem, Tsit5(), EnsembleB200(); callback = CallbackSet(...)) — the reference's keyword, served on the
+    device: default save_positions add the two event rows to sol.t; terminate! gives retcode Terminated."""
+    from helpers import ball_sources
+    rhs, cond, bounce, stop = ball_sources()
+    CS = pkg.CSource
+    N = 64
+    p = _ball_ensemble(pkg, N, False)
+    prob = pkg.ODEProblem(pkg.ODEFunction(CS(*rhs)), np.array([50.0, 0.0]), (0.0, 15.0), p[0])
+    eprob = pkg.EnsembleProblem(prob, prob_func=pkg.TableProbFunc(p=p))
+    cb = pkg.ContinuousCallback(CS(*cond), None, CS(*bounce))
+    sim = pkg.solve(eprob, pkg.Tsit5(), pkg.EnsembleB200(), trajectories=N, callback=cb, saveat=1.0)
+    spec = [cb.spec()]
+    grid = [float(k) for k in range(1, 16)]
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([50.0, 0.0]), p, (0.0, 15.0), 2, 2, callbacks=spec, saveat=grid,
+                     ragged_saveat=True)
+    for i in (0, 7, N - 1):
+        a, b = int(o["row_offsets"][i]), int(o["row_offsets"][i + 1])
+        sol = sim[i]
+        assert np.array_equal(sol.t, o["ts"][a:b]) and np.array_equal(bits(sol.u), bits(o["us"][a:b]))
+        assert len(sol.t) > 16 and sol.retcode == "Success"          # 16 grid rows + two rows per bounce
+    term = pkg.ContinuousCallback(CS(*cond), CS(*stop))
+    sim = pkg.solve(eprob, pkg.Tsit5(), pkg.EnsembleB200(), trajectories=N, callback=pkg.CallbackSet(term))
+    assert all(sim[i].retcode == "Terminated" for i in range(N))
+    t_hit = np.sqrt(2 * 50.0 / p[:, 0])
+    assert np.allclose([sim[i].t[-1] for i in range(N)], t_hit, rtol=1e-9)
+    with pytest.raises(NotImplementedError):
+        pkg.solve(eprob, pkg.Vern7(), pkg.EnsembleB200(), trajectories=N, callback=cb)
