@@ -63,7 +63,7 @@ def test_solve_keyword_contract(pkg):
     with pytest.raises(NotImplementedError):
         P.solve(ep, P.Tsit5(), None, trajectories=4, saveat=0.1)
     with pytest.raises(TypeError):                                  # unknown keyword => error, like the reference
-        P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, callback=None)
+        P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=4, saveat=0.1, internalnorm=None)
     with pytest.raises(TypeError):
         P.solve(ep, P.Tsit5(), P.EnsembleB200(), saveat=0.1)        # trajectories missing
     with pytest.raises(TypeError):                                  # logging switches are accepted (and ignored) ...
