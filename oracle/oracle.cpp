@@ -134,14 +134,14 @@ template <typename R> struct Fn {
 
 enum { ALG_TSIT5 = 1, ALG_VERN7 = 2, ALG_ROS23 = 3, ALG_RODAS5P = 4, ALG_DP5 = 5, ALG_BS3 = 6,
        ALG_RODAS5 = 7, ALG_RODAS4 = 8, ALG_RODAS42 = 9, ALG_RODAS4P = 10, ALG_RODAS4P2 = 11,
-       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_RODAS5PE = 16, ALG_AUTOTSIT5_ROS23 = 17, ALG_RODAS3P = 18,
+       ALG_VERN6 = 12, ALG_VERN8 = 13, ALG_VERN9 = 14, ALG_ROS32 = 15, ALG_RODAS5PE = 16, ALG_AUTOTSIT5_ROS23 = 17, ALG_RODAS3P = 18, ALG_RODAS23W = 19,
        ALG_VERN7_GENERATED = 102 };
 enum { RC_DEFAULT = 0, RC_SUCCESS = 1, RC_MAXITERS = 2, RC_DTLESSTHANMIN = 3, RC_UNSTABLE = 4, RC_DTNAN = 5 };
 
 // One callback of the CallbackSet.  condition: R f(const R* u, const R* p, R t); affect: void f(R* u, R* p, R t, int* terminate)
 // (the C rendering of condition(u, t, integrator) / affect!(integrator); *terminate = 1 is terminate!(integrator)).
 struct OracleCallback {
-    int kind;                 // 0 DiscreteCallback, 1 ContinuousCallback
+    int kind;                 // 0 DiscreteCallback, 1 ContinuousCallback, 2 the isoutofdomain function (condition only)
     void* condition;
     void* affect;             // NULL: nothing
     void* affect_neg;         // continuous only; NULL: nothing
@@ -207,6 +207,10 @@ template <typename R> struct JlLinspace {
 
 template <typename R> struct Opts {
     R reltol, abstol, dt, dtmin, dtmax;
+    // per-component tolerances (abstol / reltol given as vectors, solve.jl:377-399); NULL: the scalars above
+    const R* abstol_v = nullptr; const R* reltol_v = nullptr;
+    R atol(int i) const { return abstol_v ? abstol_v[i] : abstol; }
+    R rtol(int i) const { return reltol_v ? reltol_v[i] : reltol; }
     long long maxiters;
     const R* saveat; int nsaveat;
     bool save_start, save_end, save_end_user;
@@ -217,6 +221,8 @@ template <typename R> struct Opts {
     bool adaptive = true;          // false: fixed dt = opts.dt (dtcache), every step accepted
     // callbacks (CallbackSet: continuous callbacks first, then discrete ones, each group in the order given)
     const struct OracleCallback* cbs = nullptr; int ncb = 0;
+    // isoutofdomain(u, p, t) (solve.jl:166): R f(const R* u, const R* p, R t), non-zero = outside; NULL: never
+    void* isout = nullptr;
 };
 
 // ODE_DEFAULT_NORM(u::StaticArray, t) = sqrt_fast(real(sum(abs2,u)) / max(length(u),1))
@@ -302,7 +308,7 @@ template <typename R> struct Tsit5 {
                                           jl_fma(btilde5, k5[i],
                                                  jl_fma(btilde4, k4[i],
                                                         jl_fma(btilde3, k3[i], jl_fma(btilde2, k2[i], btilde1 * k1[i]))))));
-            atmp[i] = residual(utilde, uprev[i], u[i], o.abstol, o.reltol);
+            atmp[i] = residual(utilde, uprev[i], u[i], o.atol(i), o.rtol(i));
         }
         return rms(atmp, n);
     }
@@ -395,13 +401,14 @@ template <typename R> struct Tsit5 {
 // _ode_initdt_oop — lib/OrdinaryDiffEqCore/src/initdt.jl:346-459 (g === nothing, tdir = +1)
 template <typename R>
 static R ode_initdt(const ProblemFns<R>& P, const R* u0, const R* p, R t, R dtmax, R abstol, R reltol, R opts_dtmin,
-                    int order) {
+                    int order, const R* abstol_v = nullptr, const R* reltol_v = nullptr) {
     const int n = P.n;
     R dtmax_tdir = dtmax;
     R dtmin = jl_nextfloat(jl_max(opts_dtmin, jl_eps(t)));
     R smalldt = jl_max(dtmin, (R)1e-6);                 // convert(_tType, 1//10^6)
     R sk[ORACLE_MAXN], tmp[ORACLE_MAXN], f0[ORACLE_MAXN], f1[ORACLE_MAXN], u1[ORACLE_MAXN];
-    for (int i = 0; i < n; ++i) sk[i] = jl_fma(std::fabs(u0[i]), reltol, abstol);     // abstol + |u0|*reltol (@muladd)
+    for (int i = 0; i < n; ++i)      // abstol + |u0|*reltol (@muladd), element-wise for vector tolerances
+        sk[i] = jl_fma(std::fabs(u0[i]), reltol_v ? reltol_v[i] : reltol, abstol_v ? abstol_v[i] : abstol);
     for (int i = 0; i < n; ++i) tmp[i] = u0[i] / sk[i];
     R d0 = rms(tmp, n);
     P.f(f0, u0, p, t);
@@ -519,7 +526,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
     const R dtcache = o.dt;                                            // solve.jl:699
     if (o.dt == (R)0 && o.adaptive) {
         R dtmax_init = jl_min(std::fabs(dtmax), std::fabs(cur_tstop - t));     // _determine_initdt: first_tstop
-        dt = ode_initdt(P, u, p, t, dtmax_init, o.abstol, o.reltol, opts_dtmin, Alg::order);
+        dt = ode_initdt(P, u, p, t, dtmax_init, o.abstol, o.reltol, opts_dtmin, Alg::order, o.abstol_v, o.reltol_v);
         stats.nf += 2;
     } else dt = o.dt;
     R dtpropose = dt;
@@ -548,7 +555,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
 #define q11 q11_b[br]
 #define errold errold_b[br]
     long long iter = 0; int success_iter = 0, naccept = 0, nreject = 0;
-    bool accept_step = false, next_step_tstop = false;
+    bool accept_step = false, next_step_tstop = false, isout = false;
     R tstop_target = cur_tstop;
     int retcode = RC_DEFAULT;
 
@@ -755,8 +762,9 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 } else cache.update_fsal();
                 modify_dt_for_tstops();
             } else {
-                // handle_step_rejection! -> step_reject_controller! (controllers.jl:838-843)
-                dt = dt / jl_min((R)1 / qmin, q11 / gamma);
+                // handle_step_rejection! (:129-139): isout => dt * qmin, else step_reject_controller! (controllers.jl:838-843)
+                if (isout) dt = dt * qmin;
+                else dt = dt / jl_min((R)1 / qmin, q11 / gamma);
             }
         }
         iter += 1;
@@ -803,7 +811,9 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 R lo = (R)1 / qmax_cur, hi = (R)1 / qmin;
                 q = q < lo ? lo : (q > hi ? hi : q);
             }
-            accept_step = (EEst <= (R)1);                                  // accept_step_controller (:245-250)
+            // isout = opts.isoutofdomain(u, p, ttmp); accept_step = !isout && accept_step_controller (:612-618, :245-250)
+            isout = o.isout ? (((R (*)(const R*, const R*, R))o.isout)(u, p, ttmp) != (R)0) : false;
+            accept_step = !isout && (EEst <= (R)1);
         } else {
             accept_step = true;                                            // not adaptive (:650-659)
         }
@@ -927,6 +937,7 @@ struct OracleArgs {
     const double* tstops; int ntstops;      // the tstops keyword, unfiltered
     int fixed_dt;                           // 1: adaptive = false
     const OracleCallback* cbs; int ncb;     // the CallbackSet (Tsit5 only)
+    const double* abstol_v; const double* reltol_v;    // per-component tolerances (n entries each) or NULL
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -941,6 +952,9 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.dt = (R)a.dt; o.dtmin = (R)a.dtmin;
     o.dtmax = (R)(a.dtmax > 0 ? a.dtmax : (a.tf - a.t0));
     o.maxiters = a.maxiters > 0 ? a.maxiters : 1000000;
+    std::vector<R> atv, rtv;
+    if (a.abstol_v) { atv.assign(a.abstol_v, a.abstol_v + a.n); o.abstol_v = atv.data(); }
+    if (a.reltol_v) { rtv.assign(a.reltol_v, a.reltol_v + a.n); o.reltol_v = rtv.data(); }
     o.saveat = grid.data(); o.nsaveat = a.nsaveat;
     o.save_start = a.save_start != 0;
     o.save_end = a.save_end != 0;
@@ -948,9 +962,16 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.linsolve = a.linsolve;
     o.save_everystep = a.save_everystep == 1;      // 2: ragged rows without the per-step rows (callbacks + saveat)
     o.adaptive = a.fixed_dt == 0;
+    std::vector<OracleCallback> real_cbs;
     if (a.ncb > 0) {
-        if (a.alg != ALG_TSIT5 || !a.cbs) return -5;                // callbacks: Tsit5 only (first slice of SURVEY §8(f) row 4)
-        o.cbs = a.cbs; o.ncb = a.ncb;
+        if (!a.cbs) return -5;
+        for (int i = 0; i < a.ncb; ++i) {
+            if (a.cbs[i].kind == 2) o.isout = a.cbs[i].condition; else real_cbs.push_back(a.cbs[i]);
+        }
+        if (!real_cbs.empty()) {
+            if (a.alg != ALG_TSIT5) return -5;                      // callbacks: Tsit5 only (first slice of SURVEY §8(f) row 4)
+            o.cbs = real_cbs.data(); o.ncb = (int)real_cbs.size();
+        }
     }
     if (!o.adaptive && a.dt == 0.0 && !(a.tstops && a.ntstops > 0)) return -4;     // solve.jl:277-280
     std::vector<R> stops;
@@ -989,6 +1010,7 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         case ALG_RODAS4: solve_batch<R, Rodas4<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS42: solve_batch<R, Rodas42<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P: solve_batch<R, Rodas4P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
+        case ALG_RODAS23W: solve_batch<R, Rodas23W<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS3P: solve_batch<R, Rodas3P<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
         case ALG_RODAS4P2: solve_batch<R, Rodas4P2<R>>(P, a.N, u0, a.u0_shared, p, a.p_shared, (R)a.t0, (R)a.tf, o, out, a.nthreads, tq.data(), M, (R*)dense_out); break;
 #endif

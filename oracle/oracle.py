@@ -21,7 +21,7 @@ _BUILD = os.path.join(_HERE, "_build")
 ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P, ALG_DP5, ALG_BS3 = 1, 2, 3, 4, 5, 6
 ALG_RODAS5, ALG_RODAS4, ALG_RODAS42, ALG_RODAS4P, ALG_RODAS4P2 = 7, 8, 9, 10, 11
 ALG_VERN6, ALG_VERN8, ALG_VERN9, ALG_ROSENBROCK32, ALG_RODAS5PE, ALG_VERN7_GENERATED = 12, 13, 14, 15, 16, 102
-ALG_AUTOTSIT5_ROSENBROCK23, ALG_RODAS3P = 17, 18
+ALG_AUTOTSIT5_ROSENBROCK23, ALG_RODAS3P, ALG_RODAS23W = 17, 18, 19
 
 
 def build(force=False):
@@ -50,7 +50,7 @@ class OracleArgs(C.Structure):
                 ("save_everystep", C.c_int), ("row_offsets", C.c_void_p), ("ts_rag", C.c_void_p),
                 ("save_idxs", C.c_void_p), ("nsave_idxs", C.c_int),
                 ("tstops", C.c_void_p), ("ntstops", C.c_int), ("fixed_dt", C.c_int),
-                ("cbs", C.c_void_p), ("ncb", C.c_int)]
+                ("cbs", C.c_void_p), ("ncb", C.c_int), ("abstol_v", C.c_void_p), ("reltol_v", C.c_void_p)]
 
 
 class OracleCallback(C.Structure):
@@ -80,7 +80,7 @@ def _callback_array(user, callbacks):
     for i, cb in enumerate(callbacks):
         c = arr[i]
         cont = cb["kind"] == "continuous"
-        c.kind = 1 if cont else 0
+        c.kind = {"continuous": 1, "discrete": 0, "isoutofdomain": 2}[cb["kind"]]
         c.condition = fn_ptr(user, cb["condition"][1])
         aff = cb.get("affect")
         c.affect = fn_ptr(user, aff[1]) if aff else None
@@ -201,7 +201,16 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     a.u0 = u0.ctypes.data; a.u0_shared = int(u0_shared)
     a.p = p_arr.ctypes.data if p_arr is not None else None; a.p_shared = int(p_shared)
     a.t0, a.tf = t0, tf
-    a.reltol = reltol or 0.0; a.abstol = abstol or 0.0; a.dt = dt or 0.0; a.dtmin = dtmin or 0.0
+    # abstol / reltol may be vectors (one entry per component)
+    tolv = {}
+    for key, val in (("abstol", abstol), ("reltol", reltol)):
+        if val is not None and np.ndim(val) > 0:
+            tolv[key] = np.ascontiguousarray(val, dtype=np.float64)
+            assert tolv[key].shape == (n,)
+            setattr(a, key + "_v", tolv[key].ctypes.data)
+    a.reltol = 0.0 if (reltol is None or "reltol" in tolv) else reltol
+    a.abstol = 0.0 if (abstol is None or "abstol" in tolv) else abstol
+    a.dt = dt or 0.0; a.dtmin = dtmin or 0.0
     a.dtmax = dtmax or 0.0; a.maxiters = maxiters or 0
     a.saveat = grid.ctypes.data if grid is not None else None
     a.nsaveat = 0 if grid is None else len(grid)

@@ -12,14 +12,14 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb200ode.so")
 ALG_TSIT5, ALG_VERN7, ALG_ROSENBROCK23, ALG_RODAS5P, ALG_DP5, ALG_BS3 = 1, 2, 3, 4, 5, 6
 ALG_RODAS5, ALG_RODAS4, ALG_RODAS42, ALG_RODAS4P, ALG_RODAS4P2 = 7, 8, 9, 10, 11
 ALG_VERN6, ALG_VERN8, ALG_VERN9, ALG_ROSENBROCK32, ALG_RODAS5PE = 12, 13, 14, 15, 16
-ALG_AUTOTSIT5_ROSENBROCK23, ALG_RODAS3P = 17, 18
+ALG_AUTOTSIT5_ROSENBROCK23, ALG_RODAS3P, ALG_RODAS23W = 17, 18, 19
 F64, F32 = 0, 1
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 FLAG_STATIC_SCHEDULE = 1
 FLAG_NO_STEP_ROWS = 2
 RC_DEFAULT, RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN, RC_TERMINATED = range(7)
 RETCODE_NAMES = {0: "Default", 1: "Success", 2: "MaxIters", 3: "DtLessThanMin", 4: "Unstable", 5: "DtNaN", 6: "Terminated"}
-CB_DISCRETE, CB_CONTINUOUS = 0, 1
+CB_DISCRETE, CB_CONTINUOUS, CB_ISOUTOFDOMAIN = 0, 1, 2
 OK, EINVAL, ECOMPILE, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4
 
 
@@ -39,7 +39,8 @@ class B200Opts(C.Structure):
                 ("dtmax", C.c_double), ("maxiters", C.c_int64), ("saveat", C.POINTER(C.c_double)),
                 ("nsaveat", C.c_int32), ("save_start", C.c_int32), ("save_end", C.c_int32),
                 ("flags", C.c_int32), ("reserved", C.c_int32),
-                ("tstops", C.POINTER(C.c_double)), ("ntstops", C.c_int32), ("reserved2", C.c_int32)]
+                ("tstops", C.POINTER(C.c_double)), ("ntstops", C.c_int32), ("reserved2", C.c_int32),
+                ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double))]
 
 
 class B200Result(C.Structure):
@@ -90,7 +91,7 @@ def callback_array(callbacks):
     for i, cb in enumerate(callbacks):
         c = arr[i]
         cont = cb["kind"] == "continuous"
-        c.kind = CB_CONTINUOUS if cont else CB_DISCRETE
+        c.kind = {"continuous": CB_CONTINUOUS, "discrete": CB_DISCRETE, "isoutofdomain": CB_ISOUTOFDOMAIN}[cb["kind"]]
         c.condition_src, c.condition_name = _b(cb["condition"][0]), _b(cb["condition"][1])
         aff = cb.get("affect")
         if aff:
@@ -109,6 +110,7 @@ def callback_array(callbacks):
 
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
 OPT_TSTOPS = "-DB200_TSTOPS=1"
+OPT_VECTOR_TOL = "-DB200_VECTOR_TOL=1"
 OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
 OPT_COMPONENT_RHS = "-DB200_COOP=1"
 
@@ -363,8 +365,15 @@ def make_opts(reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiter
     """Returns (B200Opts, keepalive)."""
     import numpy as np
     o = B200Opts()
-    o.reltol = float(reltol) if reltol is not None else 0.0
-    o.abstol = float(abstol) if abstol is not None else 0.0
+    keep_tol = []
+    for name, val in (("reltol", reltol), ("abstol", abstol)):
+        if val is not None and np.ndim(val) > 0:        # a vector: one tolerance per component
+            arr = np.ascontiguousarray(val, dtype=np.float64)
+            keep_tol.append(arr)
+            setattr(o, name + "_vec", arr.ctypes.data_as(C.POINTER(C.c_double)))
+            setattr(o, name, 0.0)
+        else:
+            setattr(o, name, float(val) if val is not None else 0.0)
     o.dt = float(dt) if dt is not None else 0.0
     o.dtmin = float(dtmin) if dtmin is not None else 0.0
     o.dtmax = float(dtmax) if dtmax is not None else 0.0
@@ -388,4 +397,4 @@ def make_opts(reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiter
     else:
         o.tstops = None
         o.ntstops = 0
-    return o, keep
+    return o, (keep, keep_tol)

@@ -126,6 +126,8 @@ struct b200ode_program_s {
     bool tstops = false;         // compiled with -DB200_TSTOPS=1
     bool adaptive = true;        // false: compiled with -DB200_ADAPTIVE=0 (fixed dt)
     bool callbacks = false;      // compiled with a CallbackSet (b200ode_compile_callbacks)
+    bool vector_tol = false;     // compiled with -DB200_VECTOR_TOL=1 (per-component abstol / reltol)
+    std::vector<double> tolv_cached;   // the 2n tolerances currently resident in the module's B200_TOLV
     int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
     B200ProgramInfo info{};
@@ -162,7 +164,7 @@ bool is_identifier(const char* s) {
 
 bool is_stiff_alg(int alg) {      // Rosenbrock-type: need jac + tgrad, report njacs/nw/nsolve
     return alg == B200ODE_ALG_ROSENBROCK23 || alg == B200ODE_ALG_ROSENBROCK32 || alg == B200ODE_ALG_RODAS5P ||
-           alg == B200ODE_ALG_RODAS5PE || alg == B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 || alg == B200ODE_ALG_RODAS3P ||
+           alg == B200ODE_ALG_RODAS5PE || alg == B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 || alg == B200ODE_ALG_RODAS3P || alg == B200ODE_ALG_RODAS23W ||
            (alg >= B200ODE_ALG_RODAS5 && alg <= B200ODE_ALG_RODAS4P2);
 }
 
@@ -176,7 +178,7 @@ int alg_order(int alg) {
         case B200ODE_ALG_VERN8: return 8;
         case B200ODE_ALG_VERN9: return 9;
         case B200ODE_ALG_ROSENBROCK23: return 2;
-        case B200ODE_ALG_BS3: case B200ODE_ALG_ROSENBROCK32: case B200ODE_ALG_RODAS3P: return 3;
+        case B200ODE_ALG_BS3: case B200ODE_ALG_ROSENBROCK32: case B200ODE_ALG_RODAS3P: case B200ODE_ALG_RODAS23W: return 3;
         default: return 4;      // Rodas4, Rodas42, Rodas4P, Rodas4P2
     }
 }
@@ -203,7 +205,7 @@ int parse_save_idxs(const char* extra_options, int n) {
 int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                           const char* jac_src, const char* jac_name, const char* tgrad_src,
                           const char* tgrad_name) {
-    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS3P)
+    if (alg < B200ODE_ALG_TSIT5 || alg > B200ODE_ALG_RODAS23W)
         return fail(B200ODE_EINVAL, "alg must be one of the B200ODE_ALG_* constants");
     if (dtype != B200ODE_F64 && dtype != B200ODE_F32) return fail(B200ODE_EINVAL, "dtype must be B200ODE_F64 or B200ODE_F32");
     if (n < 1 || n > 64) return fail(B200ODE_EINVAL, "state dimension n must be in 1..64 (one trajectory per thread)");
@@ -223,16 +225,23 @@ int validate_compile_args(int alg, int dtype, int n, int np, const char* rhs_src
 // discrete ones, each group in the caller's order (CallbackSet(continuous..., discrete...)).
 int callbacks_source(int alg, int dtype, const B200CallbackSrc* cbs, int ncb, bool everystep, bool coop, std::string& out) {
     if (!cbs || ncb < 1 || ncb > 16) return fail(B200ODE_EINVAL, "callbacks: between 1 and 16 callbacks");
-    if (alg != B200ODE_ALG_TSIT5 || coop) return fail(B200ODE_EUNSUPPORTED, "callbacks are available for Tsit5 (one trajectory per thread)");
+    if (coop) return fail(B200ODE_EUNSUPPORTED, "callbacks / isoutofdomain are not available in the lane-group kernel");
     std::vector<int> order;
+    int isout_at = -1;
     for (int pass = 1; pass >= 0; --pass)
         for (int i = 0; i < ncb; ++i) {
-            if (cbs[i].kind != B200ODE_CB_DISCRETE && cbs[i].kind != B200ODE_CB_CONTINUOUS)
-                return fail(B200ODE_EINVAL, "callbacks: kind must be B200ODE_CB_DISCRETE or B200ODE_CB_CONTINUOUS");
+            if (cbs[i].kind != B200ODE_CB_DISCRETE && cbs[i].kind != B200ODE_CB_CONTINUOUS && cbs[i].kind != B200ODE_CB_ISOUTOFDOMAIN)
+                return fail(B200ODE_EINVAL, "callbacks: kind must be one of the B200ODE_CB_* constants");
             if (cbs[i].kind == pass) order.push_back(i);
+            if (cbs[i].kind == B200ODE_CB_ISOUTOFDOMAIN && pass == 0) {
+                if (isout_at >= 0) return fail(B200ODE_EINVAL, "callbacks: at most one isoutofdomain function");
+                isout_at = i;
+            }
         }
     int ncc = 0;
     for (int i = 0; i < ncb; ++i) ncc += (cbs[i].kind == B200ODE_CB_CONTINUOUS);
+    if (!order.empty() && alg != B200ODE_ALG_TSIT5)
+        return fail(B200ODE_EUNSUPPORTED, "callbacks are available for Tsit5 (one trajectory per thread)");
     std::vector<std::string> emitted;
     auto add_fn = [&](const char* src, const char* name, bool is_condition) -> int {
         if (!is_identifier(name)) return fail(B200ODE_EINVAL, "callbacks: a function name is not an identifier");
@@ -246,6 +255,13 @@ int callbacks_source(int alg, int dtype, const B200CallbackSrc* cbs, int ncb, bo
         return B200ODE_OK;
     };
     out += "// ---- user source (callbacks) ----\n";
+    if (isout_at >= 0) {        // the isoutofdomain keyword (solve.jl:166; integrator_utils.jl:612): any algorithm
+        int rc = add_fn(cbs[isout_at].condition_src, cbs[isout_at].condition_name, true);
+        if (rc) return rc;
+        out += std::string("#define B200_ISOUT(u, p, t) ") + cbs[isout_at].condition_name + "((u), (p), (t))\n";
+    }
+    if (order.empty()) return B200ODE_OK;
+    ncb = (int)order.size();
     char buf[512];
     std::string table = "#define B200_CB_TABLE { ", cond = "", aff = "";
     for (size_t k = 0; k < order.size(); ++k) {
@@ -430,7 +446,9 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     // CTA per SM at 128 registers (FP64) / three 256-thread CTAs at 80 registers (FP32)
     const bool small_explicit = !stiff && words <= 8 &&
                                 (alg == B200ODE_ALG_TSIT5 || alg == B200ODE_ALG_DP5 || alg == B200ODE_ALG_BS3);
-    if (ncb > 0 && !has_block && !has_minb) {       // event handling needs registers beyond the step loop's
+    int real_cbs = 0;
+    for (int i = 0; i < ncb; ++i) real_cbs += (cbs[i].kind != B200ODE_CB_ISOUTOFDOMAIN);
+    if (real_cbs > 0 && !has_block && !has_minb) {       // event handling needs registers beyond the step loop's
         opts.push_back("-DB200_BLOCK=128"); opts.push_back("-DB200_MINBLOCKS=3");
         has_block = has_minb = true;
     }
@@ -719,6 +737,26 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     P.t0 = (R)dp->t0; P.tf = (R)dp->tf;
     P.reltol = (R)(o->reltol > 0 ? o->reltol : 1e-3);
     P.abstol = (R)(o->abstol > 0 ? o->abstol : 1e-6);
+    if ((o->abstol_vec || o->reltol_vec) && !prog->vector_tol)
+        return fail(B200ODE_EINVAL, "opts.abstol_vec / reltol_vec need a program compiled with B200ODE_OPT_VECTOR_TOL");
+    if (prog->vector_tol) {
+        // reltol[0..n) then abstol[0..n) in the real type; a missing vector is the scalar broadcast.  Module-level constant
+        // memory: re-uploaded (after a device synchronisation) only when the values change.
+        std::vector<double> key(2 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            key[i] = o->reltol_vec ? o->reltol_vec[i] : (o->reltol > 0 ? o->reltol : 1e-3);
+            key[n + i] = o->abstol_vec ? o->abstol_vec[i] : (o->abstol > 0 ? o->abstol : 1e-6);
+        }
+        if (key != prog->tolv_cached) {
+            std::vector<R> vals(key.begin(), key.end());
+            void* sym = nullptr; size_t bytes = 0;
+            CUDA_TRY(cudaLibraryGetGlobal(&sym, &bytes, prog->lib, "B200_TOLV"));
+            if (bytes != sizeof(R) * vals.size()) return fail(B200ODE_ECUDA, "B200_TOLV has an unexpected size");
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemcpy(sym, vals.data(), bytes, cudaMemcpyHostToDevice));
+            prog->tolv_cached = key;
+        }
+    }
     P.dt_user = (R)o->dt;
     P.dtmin = (R)o->dtmin;
     P.dtmax = (R)(o->dtmax > 0 ? o->dtmax : (dp->tf - dp->t0));
@@ -962,7 +1000,10 @@ static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dty
     int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
                          extra_options, prog->cubin, log, &ms, &prog->coop_l, cbs, ncb);
     if (rc) { delete prog; return rc; }
-    prog->callbacks = ncb > 0;
+    prog->callbacks = false;
+    for (int i = 0; i < ncb; ++i) prog->callbacks = prog->callbacks || (cbs[i].kind != B200ODE_CB_ISOUTOFDOMAIN);
+    prog->vector_tol = extra_options && strstr(extra_options, "-DB200_VECTOR_TOL=1");
+    if (prog->vector_tol && prog->coop_l > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "per-component tolerances are not available in the lane-group kernel"); }
     prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
     prog->tstops = extra_options && strstr(extra_options, "-DB200_TSTOPS=1");
     prog->adaptive = !(extra_options && strstr(extra_options, "-DB200_ADAPTIVE=0"));

@@ -9,8 +9,7 @@
 //   alg_stability_size(Tsit5) = 3.5068                         lib/OrdinaryDiffEqTsit5/src/alg_utils.jl:3
 //   one PI controller cache per branch (CompositeController)   lib/OrdinaryDiffEqCore/src/integrators/controllers.jl:1254-1338
 //   "CompositeAlgorithm always recomputes" J and W             lib/OrdinaryDiffEqDifferentiation/src/derivative_utils.jl:107-111
-// The Rosenbrock steppers of this reference version leave integrator.eigen_est alone: while the stiff branch runs, the
-// estimate is the last Tsit5 step's and only dt moves the stiffness ratio.
+//   eigen_est of a Rosenbrock23 step = opnorm(J, Inf)           lib/OrdinaryDiffEqDifferentiation/src/derivative_utils.jl:996-999 (calc_W)
 //
 // Lanes of a warp may sit in different branches; the warp then runs both step bodies one after the other (the same
 // divergence the reference's per-trajectory `if cache.current == 1` has, paid per warp instead of per thread).
@@ -54,7 +53,8 @@ struct B200AutoTsit5Ros23 {
             for (int i = 1; i < B200_N; ++i) m = b200_max(m, b200_abs((ns.k7[i] - ns.k6[i]) / (u[i] - g6[i])));
             eigen_est = b200_abs(m);
         } else {
-            EEst = stf.attempt(uprev, u, p, t, dt, reltol, abstol, nf, njacs, nw, nsolve, calck);
+            // calc_W of a CompositeAlgorithm: integrator.eigen_est = opnorm(J, Inf) (derivative_utils.jl:996-999)
+            EEst = stf.attempt(uprev, u, p, t, dt, reltol, abstol, nf, njacs, nw, nsolve, calck, &eigen_est);
         }
         return EEst;
     }

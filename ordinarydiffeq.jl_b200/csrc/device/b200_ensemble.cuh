@@ -22,7 +22,7 @@
 //   B200_F32             0: double, 1: float
 //   B200_ALG             1 Tsit5, 2 Vern7, 3 Rosenbrock23, 4 Rodas5P, 5 DP5, 6 BS3,
 //                        7 Rodas5, 8 Rodas4, 9 Rodas42, 10 Rodas4P, 11 Rodas4P2, 12 Vern6, 13 Vern8, 14 Vern9, 15 Rosenbrock32, 16 Rodas5Pe,
-//                        17 AutoTsit5(Rosenbrock23()), 18 Rodas3P
+//                        17 AutoTsit5(Rosenbrock23()), 18 Rodas3P, 19 Rodas23W
 //   B200_RHS(du,u,p,t)   user right-hand side (plus B200_JAC / B200_TGRAD for stiff)
 //   B200_BLOCK, B200_MINBLOCKS   launch bounds
 #pragma once
@@ -47,8 +47,9 @@
 #define B200_ALG_RODAS5PE 16
 #define B200_ALG_AUTOTSIT5_ROS23 17
 #define B200_ALG_RODAS3P 18
+#define B200_ALG_RODAS23W 19
 #define B200_COMPOSITE (B200_ALG == B200_ALG_AUTOTSIT5_ROS23)
-#define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || B200_ALG == B200_ALG_RODAS5PE || B200_ALG == B200_ALG_RODAS3P || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
+#define B200_IS_RODAS (B200_ALG == B200_ALG_RODAS5P || B200_ALG == B200_ALG_RODAS5PE || B200_ALG == B200_ALG_RODAS3P || B200_ALG == B200_ALG_RODAS23W || (B200_ALG >= B200_ALG_RODAS5 && B200_ALG <= B200_ALG_RODAS4P2))
 // (the composite algorithm counts as Rosenbrock-type here: it needs jac/tgrad and reports njacs / nw / nsolve)
 #define B200_IS_ROSENBROCK (B200_ALG == B200_ALG_ROS23 || B200_ALG == B200_ALG_ROS32 || B200_IS_RODAS || B200_COMPOSITE)
 
@@ -197,6 +198,12 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #ifndef B200_CALLBACKS
 #define B200_CALLBACKS 0      // 1: the program carries a CallbackSet (device/b200_callbacks.cuh; Tsit5)
 #endif
+#if defined(B200_ISOUT) && B200_COOP
+#error "isoutofdomain is not available in the lane-group kernel"
+#endif
+#if B200_VECTOR_TOL && B200_COOP
+#error "per-component tolerances are not available in the lane-group kernel"
+#endif
 #if B200_CALLBACKS && (B200_COOP || B200_ALG != B200_ALG_TSIT5)
 #error "callbacks are available for Tsit5"
 #endif
@@ -236,7 +243,7 @@ B200_D real b200_initdt_one(const real* u0, const real* p, real t, real dtmax_td
     real smalldt = b200_max(dtmin, (real)1e-6);
     real sk[B200_N], f0[B200_N], tmp[B200_N];
 #pragma unroll
-    for (int i = 0; i < B200_N; ++i) sk[i] = b200_fma(b200_abs(u0[i]), reltol, abstol);
+    for (int i = 0; i < B200_N; ++i) sk[i] = b200_fma(b200_abs(u0[i]), B200_RTOL_AT(i, reltol), B200_ATOL_AT(i, abstol));
 #pragma unroll
     for (int i = 0; i < B200_N; ++i) tmp[i] = u0[i] / sk[i];
     real d0 = b200_rms(tmp);
@@ -319,7 +326,7 @@ B200_D B200CtlCfg b200_ctl_cfg_static() {
 }
 template <bool FAST>
 B200_D B200Ctl b200_controller_t(real EEst, real q11_old, real fpe, real rfpe, real dt, real dtpropose, bool tstop_flag,
-                                 bool first, bool& bad, const B200CtlCfg cfg) {
+                                 bool first, bool& bad, const B200CtlCfg cfg, bool isout = false) {
     const real qmin = (real)0.2, qmax = (real)10, gamma = (real)0.9;
     const real beta1 = cfg.beta1, beta2 = cfg.beta2;
     B200Ctl c;
@@ -344,7 +351,8 @@ B200_D B200Ctl b200_controller_t(real EEst, real q11_old, real fpe, real rfpe, r
     const bool zero = (EEst == (real)0);               // iszero(EEst): q = inv(qmax), q11 untouched
     q = zero ? lo : q;
     c.q11 = zero ? q11_old : q11;
-    c.accept = (EEst <= (real)1);
+    // accept_step = !isout && accept_step_controller (integrator_utils.jl:612-618); isout = isoutofdomain(u, p, t + dt)
+    c.accept = (EEst <= (real)1) & !isout;
     // step_accept_controller!: qsteady window
     const real qa = (cfg.qsteady_min <= q && q <= cfg.qsteady_max) ? (real)1 : q;
     // step_reject_controller!: dt /= min(inv(qmin), q11/gamma)
@@ -352,6 +360,8 @@ B200_D B200Ctl b200_controller_t(real EEst, real q11_old, real fpe, real rfpe, r
     // accepted steps divide the un-clipped dt (integrator_utils.jl:629-633 restores it first)
     c.num = (c.accept && tstop_flag) ? dtpropose : dt;
     c.dtdiv = B200Math<FAST>::div(c.num, c.accept ? qa : qr, bad);
+    // handle_step_rejection! (integrator_utils.jl:135-136): a step rejected by isoutofdomain shrinks dt by qmin
+    c.dtdiv = isout ? dt * qmin : c.dtdiv;
     return c;
 }
 #endif
@@ -615,11 +625,16 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #else
         const B200CtlCfg cfg = b200_ctl_cfg_static();
 #endif
+#ifdef B200_ISOUT
+        const bool isout = B200_ISOUT(T.u, T.p, ttmp) != (real)0;      // opts.isoutofdomain(u, p, ttmp)
+#else
+        const bool isout = false;
+#endif
         bool bad = false;
-        ctl = b200_controller_t<true>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, bad, cfg);
+        ctl = b200_controller_t<true>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, bad, cfg, isout);
         if (bad) {      // cold, inline
             bool unused = false;
-            ctl = b200_controller_t<false>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, unused, cfg);
+            ctl = b200_controller_t<false>(T.EEst, T.q11, T.fpe, T.rfpe, T.dt, T.dtpropose, T.tstop_flag, T.naccept == 0, unused, cfg, isout);
         }
     }
     T.q11 = ctl.q11;

@@ -132,10 +132,23 @@ struct B200WFact {
 };
 
 // J, dT at (uprev, t); W = J - I * inv(dtgamma)
+// opnorm_out (composite algorithms only): receives opnorm(J, Inf) = the largest row sum of |J| (rows summed left to right),
+// which calc_W stores in integrator.eigen_est when the algorithm is a CompositeAlgorithm (derivative_utils.jl:996-999)
 B200_D void b200_build_W(const real* uprev, const real* p, real t, real dtgamma, real* dT, B200WFact& F,
-                         int& njacs, int& nw) {
+                         int& njacs, int& nw, real* opnorm_out = nullptr) {
     real J[B200_N * B200_N];
     B200_JAC(J, uprev, p, t);
+    if (opnorm_out != nullptr) {
+        real nrm = (real)0;
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) {
+            real row = b200_abs(J[i]);
+#pragma unroll
+            for (int j = 1; j < B200_N; ++j) row = row + b200_abs(J[i + B200_N * j]);
+            nrm = (i == 0) ? row : b200_max(nrm, row);
+        }
+        *opnorm_out = nrm;
+    }
 #ifdef B200_TGRAD
     B200_TGRAD(dT, uprev, p, t);
 #else
@@ -173,7 +186,7 @@ struct B200Ros23 {
     }
 
     B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt, real reltol, real abstol,
-                        int& nf, int& njacs, int& nw, int& nsolve, bool /*calck*/) {
+                        int& nf, int& njacs, int& nw, int& nsolve, bool /*calck*/, real* opnorm_out = nullptr) {
         const real d = (real)0.2928932188134525;       // convert(T, 1/(2+sqrt(2)))
         const real c32 = (real)7.414213562373095;      // convert(T, 6+sqrt(2))
         const real dtg = dt * d;
@@ -182,7 +195,7 @@ struct B200Ros23 {
         const real dto6 = dt / (real)6;
         real dT[B200_N], rhs[B200_N], tmp[B200_N], f1[B200_N], k3[B200_N];
         B200WFact F;
-        b200_build_W(uprev, p, t, dtg, dT, F, njacs, nw);
+        b200_build_W(uprev, p, t, dtg, dT, F, njacs, nw, opnorm_out);
         if (!F.ok) return (real)2;
 #if B200_ROS_THIRD
 #pragma unroll
@@ -264,7 +277,27 @@ struct B200Ros23 {
 #define B200_RODAS3P_B {2.90625, 3.375, 0.40625, 0, 1}
 #define B200_RODAS3P_BTILDE {0, 0, 0, -1, 1}
 
-#if B200_ALG == B200_ALG_RODAS3P
+// Rodas23W (lib/OrdinaryDiffEqRosenbrock/src/rosenbrock_tableaus.jl:179-236): Rodas3P's stages, the weights of the
+// second-order solution, H rows (h2, 0, h2).  A W-method whose Jacobian reuse never engages for SVector states
+// (`cache.W isa AbstractSciMLOperator` holds for a StaticWOperator: _rosenbrock_jac_reuse_decision returns (true, true)).
+#define B200_RODAS23W_S 5
+#define B200_RODAS23W_HR 3
+#define B200_RODAS23W_GAMMA B200_RODAS3P_GAMMA
+#define B200_RODAS23W_A B200_RODAS3P_A
+#define B200_RODAS23W_C B200_RODAS3P_C
+#define B200_RODAS23W_c B200_RODAS3P_c
+#define B200_RODAS23W_d B200_RODAS3P_d
+#define B200_RODAS23W_H { {4.21875, -2.025, -1.63125, -1.7, -0.1}, {0, 0, 0, 0, 0}, {4.21875, -2.025, -1.63125, -1.7, -0.1} }
+#define B200_RODAS23W_B {2.90625, 3.375, 0.40625, 1, 0}
+#define B200_RODAS23W_BTILDE {0, 0, 0, 1, -1}
+
+#if B200_ALG == B200_ALG_RODAS23W
+#define B200_RODAS_NAME(x) B200_RODAS23W_##x
+#define B200_RODAS_ORDER 3
+#define B200_RODAS_EXPLICIT_B 1
+#define B200_RODAS_INTERP 2
+#define B200_RODAS_FSKIP 4
+#elif B200_ALG == B200_ALG_RODAS3P
 #define B200_RODAS_NAME(x) B200_RODAS3P_##x
 #define B200_RODAS_ORDER 3
 #define B200_RODAS_EXPLICIT_B 1         // b and btilde are stored vectors (zero entries skipped like the reference)

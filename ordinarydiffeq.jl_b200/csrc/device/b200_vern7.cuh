@@ -121,7 +121,7 @@ struct B200Vern7 {
         for (int i = 0; i < B200_VLEN; ++i) {
             ut[i] = dt * B200_V7_8(btilde1, k1, btilde4, k4, btilde5, k5, btilde6, k6, btilde7, k7, btilde8, k8,
                                    btilde9, k9, btilde10, k10);
-            den[i] = b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), reltol, abstol);
+            den[i] = b200_fma(b200_max_fast(b200_abs(uprev[i]), b200_abs(u[i])), B200_RTOL_AT(i, reltol), B200_ATOL_AT(i, abstol));
             res[i] = b200_div_fast(ut[i], den[i], bad);
         }
         if (bad) {

@@ -83,6 +83,10 @@ class Rodas4P(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS4P, 4, True
 
 
+class Rodas23W(_Alg):
+    alg_id, order, stiff = _lib.ALG_RODAS23W, 3, True
+
+
 class Rodas3P(_Alg):
     alg_id, order, stiff = _lib.ALG_RODAS3P, 3, True
 
@@ -398,7 +402,8 @@ def _handle(device):
     return _handles[device]
 
 
-def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True, callbacks=None):
+def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True, callbacks=None,
+                vector_tol=False):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
     extra = []
     if everystep:
@@ -407,6 +412,8 @@ def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, t
         extra.append(_lib.OPT_TSTOPS)
     if not adaptive:
         extra.append(_lib.OPT_FIXED_DT)
+    if vector_tol:
+        extra.append(_lib.OPT_VECTOR_TOL)
     if save_idxs is not None:
         extra.append(_lib.opt_save_idxs(save_idxs))
     extra = " ".join(extra) or None
@@ -511,7 +518,13 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             if dense_kw:
                 raise NotImplementedError("dense=true is not available with callbacks")
     handle = _handle(ensemblealg.device)
-    program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None, adaptive, cb_specs)
+    # abstol / reltol given as vectors: one tolerance per component (solve.jl:377-399)
+    vector_tol = np.ndim(kw.get("reltol")) > 0 or np.ndim(kw.get("abstol")) > 0
+    for name in ("reltol", "abstol"):
+        if np.ndim(kw.get(name)) > 0 and len(kw[name]) != n:
+            raise ValueError("%s must be a number or a vector with one entry per component" % name)
+    program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None, adaptive, cb_specs,
+                          vector_tol)
 
     def run(u0, p, ntraj, flags=0):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),

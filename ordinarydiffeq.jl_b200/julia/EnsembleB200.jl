@@ -18,9 +18,11 @@ import SciMLBase: __solve, AbstractEnsembleProblem, EnsembleAlgorithm, EnsembleS
 using OrdinaryDiffEqTsit5: Tsit5
 using OrdinaryDiffEqVerner: Vern6, Vern7, Vern8, Vern9
 using OrdinaryDiffEqLowOrderRK: DP5, BS3
-using OrdinaryDiffEqRosenbrock: Rosenbrock23, Rosenbrock32, Rodas5P, Rodas5Pe, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2
+using OrdinaryDiffEqRosenbrock: Rosenbrock23, Rosenbrock32, Rodas5P, Rodas5Pe, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2,
+                                Rodas3P, Rodas23W
+using OrdinaryDiffEqCore: CompositeAlgorithm, AutoSwitch
 
-export EnsembleB200
+export EnsembleB200, B200ContinuousCallback, B200DiscreteCallback
 
 const LIB = get(ENV, "B200ODE_LIB", "libb200ode.so")
 
@@ -51,7 +53,42 @@ struct B200Opts
     saveat::Ptr{Float64}; nsaveat::Int32
     save_start::Int32; save_end::Int32; flags::Int32; reserved::Int32
     tstops::Ptr{Float64}; ntstops::Int32; reserved2::Int32
+    abstol_vec::Ptr{Float64}; reltol_vec::Ptr{Float64}      # per-component tolerances or C_NULL
 end
+struct B200CallbackSrc       # include/b200ode.h
+    kind::Int32; rootfind::Int32
+    condition_src::Cstring; condition_name::Cstring
+    affect_src::Cstring; affect_name::Cstring
+    affect_neg_src::Cstring; affect_neg_name::Cstring
+    interp_points::Int32; save_before::Int32; save_after::Int32; reserved::Int32
+    abstol::Float64; repeat_nudge::Float64
+end
+
+"""
+Callbacks cross the boundary as C source (the closures of a SciMLBase callback cannot be traced into `affect!` code in
+general): `condition` is `real NAME(const real* u, const real* p, const real t)`, `affect` / `affect_neg` are
+`void NAME(real* u, real* p, const real t, int* terminate)`, each given as a `(source, name)` pair or `nothing`.
+`solve(...; callback = B200ContinuousCallback(...))` or a tuple of them.  Tsit5 only.
+"""
+struct B200ContinuousCallback
+    condition::Tuple{String, String}
+    affect::Union{Nothing, Tuple{String, String}}
+    affect_neg::Union{Nothing, Tuple{String, String}}
+    rootfind::Int                 # 0 NoRootFind, 1 LeftRootFind, 2 RightRootFind
+    interp_points::Int
+    save_positions::Tuple{Bool, Bool}
+    abstol::Float64
+    repeat_nudge::Float64
+end
+B200ContinuousCallback(condition, affect, affect_neg = affect; rootfind = 1, interp_points = 10,
+                       save_positions = (true, true), abstol = 10eps(), repeat_nudge = 1 / 100) =
+    B200ContinuousCallback(condition, affect, affect_neg, rootfind, interp_points, save_positions, abstol, repeat_nudge)
+struct B200DiscreteCallback
+    condition::Tuple{String, String}
+    affect::Union{Nothing, Tuple{String, String}}
+    save_positions::Tuple{Bool, Bool}
+end
+B200DiscreteCallback(condition, affect; save_positions = (true, true)) = B200DiscreteCallback(condition, affect, save_positions)
 mutable struct B200Result
     u_final::Ptr{Cvoid}; t_final::Ptr{Float64}; us::Ptr{Cvoid}; ts::Ptr{Float64}
     nsaved::Ptr{Int32}; naccept::Ptr{Int32}; nreject::Ptr{Int32}; nf::Ptr{Int32}
@@ -68,11 +105,21 @@ alg_id(::Tsit5) = 1; alg_id(::Vern7) = 2; alg_id(::Rosenbrock23) = 3; alg_id(::R
 alg_id(::DP5) = 5; alg_id(::BS3) = 6
 alg_id(::Rodas5) = 7; alg_id(::Rodas4) = 8; alg_id(::Rodas42) = 9; alg_id(::Rodas4P) = 10; alg_id(::Rodas4P2) = 11
 alg_id(::Vern6) = 12; alg_id(::Vern8) = 13; alg_id(::Vern9) = 14; alg_id(::Rosenbrock32) = 15; alg_id(::Rodas5Pe) = 16
-const StiffAlgs = Union{Rosenbrock23, Rosenbrock32, Rodas5P, Rodas5Pe, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2}
+alg_id(::Rodas3P) = 18; alg_id(::Rodas23W) = 19
+# AutoTsit5(Rosenbrock23()) = CompositeAlgorithm((Tsit5(), Rosenbrock23()), AutoSwitch(...)) with the default switch parameters
+const AutoTsit5Ros23 = CompositeAlgorithm{<:Any, <:Tuple{Tsit5, Rosenbrock23}, <:AutoSwitch}
+function alg_id(alg::AutoTsit5Ros23)
+    c = alg.choice_function
+    (c.maxstiffstep == 10 && c.maxnonstiffstep == 3 && c.nonstifftol == 9 // 10 && c.stifftol == 9 // 10 && c.dtfac == 2 &&
+     !c.stiffalgfirst && c.switch_max == 5) || throw(ArgumentError("EnsembleB200 serves AutoTsit5(Rosenbrock23()) with the default AutoSwitch parameters"))
+    return 17
+end
+const StiffAlgs = Union{Rosenbrock23, Rosenbrock32, Rodas5P, Rodas5Pe, Rodas5, Rodas4, Rodas42, Rodas4P, Rodas4P2, Rodas3P, Rodas23W,
+                        AutoTsit5Ros23}
 const B200Algs = Union{Tsit5, Vern6, Vern7, Vern8, Vern9, DP5, BS3, StiffAlgs}
 isstiff(alg) = alg isa StiffAlgs
 const RETCODES = (ReturnCode.Default, ReturnCode.Success, ReturnCode.MaxIters, ReturnCode.DtLessThanMin,
-                  ReturnCode.Unstable, ReturnCode.DtNaN)
+                  ReturnCode.Unstable, ReturnCode.DtNaN, ReturnCode.Terminated)
 
 function check(rc)
     rc == 0 && return
@@ -125,15 +172,44 @@ function handle(ens::EnsembleB200)
     end
 end
 
-function program(ens::EnsembleB200, h, alg, ::Type{T}, n, np, rhs, jac, tgr, extra::String) where {T}
-    key = (ens.devices, alg_id(alg), T, n, np, hash(rhs), hash(jac), hash(tgr), extra)
+cb_list(::Nothing) = ()
+cb_list(cb::Union{B200ContinuousCallback, B200DiscreteCallback}) = (cb,)
+cb_list(cbs::Tuple) = cbs
+cb_list(cb) = throw(ArgumentError("EnsembleB200: pass callbacks as B200ContinuousCallback / B200DiscreteCallback (C source), got $(typeof(cb))"))
+
+# b200ode_compile_callbacks (single device).  The Cstring fields point into `keep`, which outlives the ccall.
+function compile_with_callbacks(h, prog, alg, ::Type{T}, n, np, rhs, jac, tgr, extra, cbs) where {T}
+    keep = String[]
+    cs(x) = x === nothing ? Cstring(C_NULL) : (push!(keep, x); Base.unsafe_convert(Cstring, keep[end]))
+    pair(x) = x === nothing ? (nothing, nothing) : x
+    arr = map(cbs) do cb
+        cont = cb isa B200ContinuousCallback
+        a, an = pair(cb.affect); ng, ngn = cont ? pair(cb.affect_neg) : (nothing, nothing)
+        B200CallbackSrc(cont ? 1 : 0, cont ? cb.rootfind : 1, cs(cb.condition[1]), cs(cb.condition[2]), cs(a), cs(an),
+                        cs(ng), cs(ngn), cont ? cb.interp_points : 0, cb.save_positions[1], cb.save_positions[2], 0,
+                        cont ? cb.abstol : -1.0, cont ? cb.repeat_nudge : -1.0)
+    end |> collect
+    GC.@preserve keep arr begin
+        check(ccall((:b200ode_compile_callbacks, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring,
+                     Ptr{B200CallbackSrc}, Cint, Cstring),
+                    h, prog, alg_id(alg), T === Float32 ? 1 : 0, n, np, rhs, "diffeqf", jac === nothing ? C_NULL : jac, "diffeqjac",
+                    tgr === nothing ? C_NULL : tgr, "diffeqtgrad", pointer(arr), length(arr), isempty(extra) ? C_NULL : extra))
+    end
+end
+
+function program(ens::EnsembleB200, h, alg, ::Type{T}, n, np, rhs, jac, tgr, extra::String, cbs = ()) where {T}
+    key = (ens.devices, alg_id(alg), T, n, np, hash(rhs), hash(jac), hash(tgr), extra, hash(cbs))
     lock(CACHE_LOCK) do
         get!(PROGRAMS, key) do
             prog = Ref{Ptr{Cvoid}}(C_NULL)
             args = (h, prog, alg_id(alg), T === Float32 ? 1 : 0, n, np, rhs, "diffeqf",
                     jac === nothing ? C_NULL : jac, "diffeqjac", tgr === nothing ? C_NULL : tgr, "diffeqtgrad",
                     isempty(extra) ? C_NULL : extra)
-            if ismulti(ens)
+            if !isempty(cbs)
+                ismulti(ens) && throw(ArgumentError("EnsembleB200: callbacks are single-device"))
+                compile_with_callbacks(h, prog, alg, T, n, np, rhs, jac, tgr, extra, cbs)
+            elseif ismulti(ens)
                 check(ccall((:b200ode_multi_compile, LIB), Cint,
                             (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cint, Cint, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring, Cstring),
                             args...))
@@ -181,7 +257,7 @@ function with_pinned(f, arrays...)
 end
 
 const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :tstops, :reltol, :abstol,
-                 :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense, :verbose, :progress)
+                 :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense, :verbose, :progress, :callback)
 
 # One batch of trajectories I (global sim ids) with repeat counters `rep`: harvest prob_func, solve, wrap.
 function solve_ids(eprob, prob, alg, ens, h, prog, multi, opts, grid, tstops, everystep, idxs, w, n, np, T, t0, tf, I, rep)
@@ -275,19 +351,36 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     adaptive || push!(extra, "-DB200_ADAPTIVE=0")
     adaptive || get(kw, :dt, nothing) !== nothing || !isempty(tstops) ||
         throw(ArgumentError("Fixed timestep methods require a choice of dt or choosing the tstops"))
+    # callbacks: rows forced by save_positions make the output ragged even with save_everystep = false
+    cbs = cb_list(get(kw, :callback, nothing))
+    flags = Int32(0)
+    if !isempty(cbs)
+        alg isa Tsit5 || throw(ArgumentError("EnsembleB200: callbacks are available with Tsit5()"))
+        if any(any(cb.save_positions) for cb in cbs) && !everystep
+            push!(extra, "-DB200_EVERYSTEP=1"); flags = Int32(2)         # B200ODE_FLAG_NO_STEP_ROWS
+            everystep = true
+        end
+    end
+    # abstol / reltol as vectors: one tolerance per component (solve.jl:377-399)
+    rtol, atol = get(kw, :reltol, 0.0), get(kw, :abstol, 0.0)
+    rtv = rtol isa AbstractVector ? collect(Float64, rtol) : Float64[]
+    atv = atol isa AbstractVector ? collect(Float64, atol) : Float64[]
+    (isempty(rtv) && isempty(atv)) || push!(extra, "-DB200_VECTOR_TOL=1")
     h = handle(ens)
-    prog, multi = program(ens, h, alg, T, n, np, rhs, jac, tgr, join(extra, " "))
+    prog, multi = program(ens, h, alg, T, n, np, rhs, jac, tgr, join(extra, " "), cbs)
     # defaults of solve.jl:141-143,596-599 (the C ABI only sees the expanded grid)
     dflt(tend) = everystep || isempty(saveat) || saveat isa Number || tend in saveat
     ss = something(get(kw, :save_start, nothing), dflt(prob.tspan[1]))
     se = get(kw, :save_end, nothing)
     se === nothing && !dflt(prob.tspan[2]) && (se = false)
-    opts = B200Opts(get(kw, :reltol, 0.0), get(kw, :abstol, 0.0), something(get(kw, :dt, nothing), 0.0),
+    opts = B200Opts(isempty(rtv) ? Float64(rtol) : 0.0, isempty(atv) ? Float64(atol) : 0.0, something(get(kw, :dt, nothing), 0.0),
                     get(kw, :dtmin, 0.0), get(kw, :dtmax, 0.0), get(kw, :maxiters, 0),
                     isempty(grid) ? Ptr{Float64}(C_NULL) : pointer(grid), length(grid),
-                    Int32(ss), se === nothing ? Int32(-1) : Int32(se), 0, 0,
-                    isempty(tstops) ? Ptr{Float64}(C_NULL) : pointer(tstops), length(tstops), 0)
+                    Int32(ss), se === nothing ? Int32(-1) : Int32(se), flags, 0,
+                    isempty(tstops) ? Ptr{Float64}(C_NULL) : pointer(tstops), length(tstops), 0,
+                    isempty(atv) ? Ptr{Float64}(C_NULL) : pointer(atv), isempty(rtv) ? Ptr{Float64}(C_NULL) : pointer(rtv))
     tstart = time()
+    tol_keep = (atv, rtv)          # opts points into these: keep them reachable until the last batch returns
     u = eprob.u_init === nothing ? [] : eprob.u_init
     converged = false
     for b0 in 1:batch_size:trajectories
@@ -315,6 +408,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
         u, converged = eprob.reduction(u, batch, I)
         converged && break
     end
+    GC.@preserve tol_keep nothing
     return EnsembleSolution(u, time() - tstart, converged)
 end
 

@@ -261,7 +261,7 @@ def emit(M, flavor):
         L.append("        R atmp[ORACLE_MAXN];")
         L.append("        for (int i = 0; i < n; ++i) {")
         L.append("            R utilde = dt * (%s);" % chain(st["err"]))
-        L.append("            atmp[i] = residual(utilde, uprev[i], u[i], o.abstol, o.reltol);")
+        L.append("            atmp[i] = residual(utilde, uprev[i], u[i], o.atol(i), o.rtol(i));")
         L.append("        }")
         L.append("        return rms(atmp, n);")
         L.append("    }")

@@ -610,7 +610,7 @@ def test_low_order_rk_high_level(pkg, oracle):
             assert s[i].stats.naccept == o["naccept"][i]
 
 
-@pytest.mark.parametrize("name", ["Rodas5", "Rodas4", "Rodas42", "Rodas4P", "Rodas4P2", "Rodas5Pe", "Rodas3P"])
+@pytest.mark.parametrize("name", ["Rodas5", "Rodas4", "Rodas42", "Rodas4P", "Rodas4P2", "Rodas5Pe", "Rodas3P", "Rodas23W"])
 def test_rodas_family_parity(pkg, handle, oracle, name):
     """The generic RodasTableau stepper over the other members of the family, Robertson FP64 (+ FP32 for two)."""
     pl = pkg.problems_library
@@ -1127,3 +1127,81 @@ def test_high_level_callbacks(pkg, oracle):
     assert np.allclose([sim[i].t[-1] for i in range(N)], t_hit, rtol=1e-9)
     with pytest.raises(NotImplementedError):
         pkg.solve(eprob, pkg.Vern7(), pkg.EnsembleB200(), trajectories=N, callback=cb)
+
+
+# ---- per-component tolerances (abstol / reltol vectors, solve.jl:377-399) ----------------------------------------------
+@pytest.mark.parametrize("f32", [False, True])
+def test_vector_tolerances_parity(pkg, handle, oracle, f32):
+    pl = pkg.problems_library
+    dt = pkg.F32 if f32 else pkg.F64
+    N = 1500
+    rt, at = [1e-5, 1e-3, 1e-4], [1e-7, 1e-4, 1e-6]
+    # explicit (Tsit5, Vern7) and stiff (Rodas5P) steppers; a scalar abstol next to a vector reltol
+    p = pl.lorenz_params(N, f32=f32)
+    for alg, oalg in ((pkg.ALG_TSIT5, oracle.ALG_TSIT5), (pkg.ALG_VERN7, oracle.ALG_VERN7)):
+        s, nm = pl.lorenz_source(f32)
+        prog = handle.compile(alg, dt, 3, 3, s, nm, extra_options=pkg._lib.OPT_VECTOR_TOL)
+        try:
+            for kw in (dict(reltol=rt, abstol=at), dict(reltol=rt), dict(reltol=rt, abstol=at, saveat=[0.5, 1.0, 2.5])):
+                g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 3.0), **kw)
+                o = oracle.solve(oalg, (s, nm), U0, p, (0.0, 3.0), 3, 3, f32=f32, **kw)
+                assert_same_result(g, o)
+            # uniform vectors reproduce the scalar solve
+            g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 3.0), reltol=[1e-4] * 3, abstol=[1e-6] * 3)
+            o = oracle.solve(oalg, (s, nm), U0, p, (0.0, 3.0), 3, 3, f32=f32, reltol=1e-4, abstol=1e-6)
+            assert_same_result(g, o)
+        finally:
+            prog.close()
+        plain = handle.compile(alg, dt, 3, 3, s, nm)
+        try:
+            with pytest.raises(pkg.B200Error):
+                pkg.lowlevel.solve_host(plain, U0, p, (0.0, 3.0), reltol=rt)
+        finally:
+            plain.close()
+    r, j, tg = pl.robertson_sources(f32)
+    pr = pl.robertson_params(512, f32=f32)
+    prog = handle.compile(pkg.ALG_RODAS5P, dt, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1], extra_options=pkg._lib.OPT_VECTOR_TOL)
+    try:
+        kw = dict(reltol=[1e-4, 1e-3, 1e-4], abstol=[1e-6, 1e-9, 1e-6])
+        g = pkg.lowlevel.solve_host(prog, U0, pr, (0.0, 1e3), **kw)
+        o = oracle.solve(oracle.ALG_RODAS5P, r, U0, pr, (0.0, 1e3), 3, 3, f32=f32, jac=j, tgrad=tg, **kw)
+        assert_same_result(g, o)
+    finally:
+        prog.close()
+
+
+# ---- isoutofdomain (solve.jl:166; integrator_utils.jl:135-136,612-618) ----------------------------------------------------
+def test_isoutofdomain_parity(pkg, handle, oracle):
+    """Robertson concentrations must stay non-negative: isoutofdomain = any(u < 0) rejects such steps and retries them with
+    dt * qmin.  Explicit (Tsit5 on Lorenz with an artificial half-space) and stiff (Rodas5P, Rosenbrock23) steppers."""
+    pl = pkg.problems_library
+    T = "double"
+    pos = ("%s rober_out(const %s* u, const %s* p, const %s t) { return (u[0] < 0.0 || u[1] < 0.0 || u[2] < 0.0) ? 1.0 : 0.0; }\n" % (T, T, T, T), "rober_out")
+    r, j, tg = pl.robertson_sources()
+    pr = pl.robertson_params(700)
+    cbs = [dict(kind="isoutofdomain", condition=pos)]
+    for alg, oalg in ((pkg.ALG_RODAS5P, oracle.ALG_RODAS5P), (pkg.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK23)):
+        prog = handle.compile(alg, pkg.F64, 3, 3, r[0], r[1], j[0], j[1], tg[0], tg[1], callbacks=cbs)
+        try:
+            kw = dict(reltol=1e-2, abstol=1e-4, saveat=[1.0, 100.0])       # loose tolerances overshoot into u2 < 0
+            g = pkg.lowlevel.solve_host(prog, U0, pr, (0.0, 1e4), **kw)
+            o = oracle.solve(oalg, r, U0, pr, (0.0, 1e4), 3, 3, jac=j, tgrad=tg, callbacks=cbs, **kw)
+            free = oracle.solve(oalg, r, U0, pr, (0.0, 1e4), 3, 3, jac=j, tgrad=tg, **kw)
+            assert_same_result(g, o)
+            assert (g["u_final"] >= 0).all() and (g["us"] >= 0).all()
+            if alg == pkg.ALG_RODAS5P:       # (Rosenbrock23 never leaves the domain at these tolerances)
+                assert (g["nreject"] != free["nreject"]).any()              # the domain check really rejected steps
+        finally:
+            prog.close()
+    half = ("%s lz_out(const %s* u, const %s* p, const %s t) { return u[2] > 45.0 ? 1.0 : 0.0; }\n" % (T, T, T, T), "lz_out")
+    s, nm = pl.lorenz_source()
+    p = pl.lorenz_params(900)
+    cbs = [dict(kind="isoutofdomain", condition=half)]
+    prog = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, s, nm, callbacks=cbs)
+    try:
+        g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 3.0), maxiters=2000)
+        o = oracle.solve(oracle.ALG_TSIT5, (s, nm), U0, p, (0.0, 3.0), 3, 3, callbacks=cbs, maxiters=2000)
+        assert_same_result(g, o)
+        assert (g["retcode"] != 1).any() and (g["retcode"] == 1).any()      # trajectories that must leave the half-space stall
+    finally:
+        prog.close()

@@ -218,13 +218,14 @@ def test_tableau_consistency():
     (oracle.ALG_ROSENBROCK32, 6e-4),                           # ode_dense_tests.jl:456
     (oracle.ALG_RODAS5PE, 2e-5),                               # ode_dense_tests.jl:483
     (oracle.ALG_RODAS3P, 2e-4),                                # ode_dense_tests.jl:462
+    (oracle.ALG_RODAS23W, 2e-3),                               # ode_dense_tests.jl:459
     (oracle.ALG_VERN6, 7e-8), (oracle.ALG_VERN8, 3e-8), (oracle.ALG_VERN9, 1e-9)])   # ode_dense_tests.jl:406,437,444
 def test_dense_output_regression_bounds(alg, bound):
     # test/Regression_I/ode_dense_tests.jl:56-75 with the per-algorithm tolerances at
     # :369-370 (Tsit5), :429-433 (Vern7), :452-453 (Rosenbrock23), :479-480 (Rodas5P):
     # interpolant of the adaptive dt0 = 1/4 solve vs the fixed dt = 1/16 solve, at k/16.
     jac, tg = linear_jac_sources()
-    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK32, oracle.ALG_RODAS5P, oracle.ALG_RODAS5PE, oracle.ALG_RODAS3P) or \
+    stiff = alg in (oracle.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK32, oracle.ALG_RODAS5P, oracle.ALG_RODAS5PE, oracle.ALG_RODAS3P, oracle.ALG_RODAS23W) or \
         oracle.ALG_RODAS5 <= alg <= oracle.ALG_RODAS4P2
     kw = dict(jac=jac, tgrad=tg) if stiff else {}
     pts = [k / 16 for k in range(1, 17)]
@@ -395,6 +396,18 @@ def test_rodas3p_order_step_count_and_f_skip():
     assert o["retcode"][0] == 1 and o["nsaved"][0] < 20
     iters = o["naccept"][0] + o["nreject"][0]
     assert o["nf"][0] == 2 + 4 * iters and o["nsolve"][0] == 4 * iters and o["njacs"][0] == 2 * iters
+
+
+def test_rodas23w_is_second_order_like_the_reference():
+    # lib/OrdinaryDiffEqRosenbrock/test/ode_rosenbrock_tests.jl:111-123: dts = (1/2)^(6:-1:3), O_est[:final] ≈ 2 (atol 0.2),
+    # length(sol.t) < 20 on prob_ode_linear
+    errs = [_fixed_step_l2_error(oracle.ALG_RODAS23W, 0.5 ** k, True) for k in (6, 5, 4, 3)]
+    rates = [math.log2(errs[i + 1] / errs[i]) for i in range(len(errs) - 1)]
+    assert abs(np.mean(rates) - 2) < 0.2, (errs, rates)
+    jac, tg = linear_jac_sources()
+    o = oracle.solve(oracle.ALG_RODAS23W, linear_source(), np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, jac=jac,
+                     tgrad=tg, save_everystep=True)
+    assert o["retcode"][0] == 1 and o["nsaved"][0] < 20
 
 
 # ---- generated Verner steppers (scripts/gen_verner.py) ----------------------------------------
