@@ -100,3 +100,48 @@ def build_tgrad_c(f, n, np_, fname="diffeqtgrad", f32=False, iip=False):
     """∂f/∂t."""
     exprs, u, p, t = trace(f, n, np_, iip)
     return _emit(fname, "dT", [sp.diff(e, t) for e in exprs], u, p, t, f32), fname
+
+
+# ---- component form (the lane-group kernels, B200ODE_OPT_COMPONENT_RHS) -------------------------------------------------
+# The same expressions, printed by the same printer, behind an index: lane g of a trajectory's lane group evaluates only
+# ITS component (row).  A generated function can only be a switch over the index; lanes of one group then take different
+# cases (serialised), while the groups of a warp run the same case together.  Hand-written component functions with loops
+# over a regular structure (problems_library.pleiades_component_source) avoid that.
+def _emit_switch(name, index_args, cases, u, p, t, f32):
+    pr = _B200CPrinter(f32)
+    ty = "float" if f32 else "double"
+    zero = "0.0f" if f32 else "0.0"
+    sub = {s: sp.Symbol("RHS1[%d]" % i) for i, s in enumerate(u)}
+    sub.update({s: sp.Symbol("RHS2[%d]" % i) for i, s in enumerate(p)})
+    lines = ["#include <math.h>",
+             "%s %s(%s, const %s* RHS1, const %s* RHS2, const %s RHS3) {" % (ty, name, index_args[0], ty, ty, ty),
+             "  switch (%s) {" % index_args[1]]
+    for key, e in cases:
+        e = sp.sympify(e)
+        if e == 0:
+            continue                      # falls through to the default
+        lines.append("    case %d: return %s;" % (key, pr.doprint(e.xreplace(sub))))
+    lines += ["    default: return %s;" % zero, "  }", "}"]
+    return "\n".join(lines) + "\n"
+
+
+def build_function_component_c(f, n, np_, fname="diffeqf_i", f32=False, iip=False):
+    """real NAME(int i, u, p, t) -> du_i."""
+    exprs, u, p, t = trace(f, n, np_, iip)
+    return _emit_switch(fname, ("int i", "i"), list(enumerate(exprs)), u, p, t, f32), fname
+
+
+def build_jacobian_entry_c(f, n, np_, fname="diffeqjac_ij", f32=False, iip=False):
+    """real NAME(int i, int j, u, p, t) -> (∂f/∂u)[i][j]; structural zeros share the default case."""
+    exprs, u, p, t = trace(f, n, np_, iip)
+    cases = [(i * n + j, sp.diff(exprs[i], u[j])) for i in range(n) for j in range(n)]
+    return _emit_switch(fname, ("int i, int j", "i * %d + j" % n), cases, u, p, t, f32), fname
+
+
+def build_tgrad_component_c(f, n, np_, fname="diffeqtgrad_i", f32=False, iip=False):
+    """real NAME(int i, u, p, t) -> (∂f/∂t)_i, or None when the system is autonomous."""
+    exprs, u, p, t = trace(f, n, np_, iip)
+    cases = [(i, sp.diff(e, t)) for i, e in enumerate(exprs)]
+    if all(sp.sympify(e) == 0 for _, e in cases):
+        return None
+    return _emit_switch(fname, ("int i", "i"), cases, u, p, t, f32), fname

@@ -351,12 +351,15 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     // Lane-group kernel (device/b200_coop.cuh): opt-in with -DB200_COOP=1; the RHS is then in component form
     //     real NAME(int i, const real* u, const real* p, const real t)   returning du_i
     const bool coop = extra_options && strstr(extra_options, "-DB200_COOP=1");
-    if (coop && alg != B200ODE_ALG_VERN7)
-        return fail(B200ODE_EUNSUPPORTED, "the lane-group kernel (B200ODE_OPT_COMPONENT_RHS) is available for Vern7");
+    if (coop && alg != B200ODE_ALG_VERN7 && alg != B200ODE_ALG_ROSENBROCK23)
+        return fail(B200ODE_EUNSUPPORTED, "the lane-group kernel (B200ODE_OPT_COMPONENT_RHS) is available for Vern7 and Rosenbrock23");
+    if (coop && alg == B200ODE_ALG_ROSENBROCK23 && (n < 2 || n > 16 || n == 3))
+        return fail(B200ODE_EUNSUPPORTED, "the lane-group Rosenbrock23 (warp-shuffle LU) serves n = 2 and 4..16; n = 3 uses the in-register "
+                                          "inverse of the one-thread kernel");
     if (!coop)
     tu += std::string(rhs_inline ? "__device__ __forceinline__ void " : "__device__ __noinline__ void ") + rhs_name +
           "(real* du, const real* u, const real* p, const real t);\n";
-    if (stiff) {
+    if (stiff && !coop) {
         tu += std::string("__device__ __forceinline__ void ") + jac_name +
               "(real* J, const real* u, const real* p, const real t);\n";
         if (tgrad_src)
@@ -371,7 +374,12 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         //                 so the independent terms of a sum interleave instead of queueing behind one another's
         //                 slow-path branches;
         //  B200UserExact: the plain operators; evaluated only when the fast evaluation raised its flag.
-        const std::string body = strip_includes(rhs_src);
+        // (Rosenbrock23: the Jacobian entry function and the optional time-gradient component function ride along)
+        std::string body = strip_includes(rhs_src);
+        if (stiff) {
+            body += strip_includes(jac_src);
+            if (tgrad_src) body += strip_includes(tgrad_src);
+        }
         tu += "struct B200UserFast {\n  bool b200_bad;\n"
               "#define B200_DIV(a, b) b200_div_fast((a), (b), b200_bad)\n"
               "#define sqrt(x) b200_sqrt_fast((x), b200_bad)\n#define sqrtf(x) b200_sqrt_fast((x), b200_bad)\n";
@@ -381,9 +389,13 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         tu += body;
         tu += "\n#undef B200_DIV\n};\n";
         tu += std::string("#define B200_USER_COMP_NAME ") + rhs_name + "\n";
+        if (stiff) {
+            tu += std::string("#define B200_USER_JAC_NAME ") + jac_name + "\n";
+            if (tgrad_src) tu += std::string("#define B200_USER_TGRAD_NAME ") + tgrad_name + "\n";
+        }
     } else
     tu += strip_includes(rhs_src);
-    if (stiff) {
+    if (stiff && !coop) {
         tu += "// ---- user source (Jacobian) ----\n";
         tu += strip_includes(jac_src);
         if (tgrad_src) {
@@ -395,7 +407,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     tu += "// ---- steppers ----\n";
     if (coop) tu += "#define B200_USER_RHS_COMP(i,u,p,t) (B200UserExact().B200_USER_COMP_NAME((i),(u),(p),(t)))\n";
     else tu += std::string("#define B200_USER_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
-    if (stiff) {
+    if (stiff && !coop) {
         tu += std::string("#define B200_JAC(J,u,p,t) ") + jac_name + "((J),(u),(p),(t))\n";
         if (tgrad_src) tu += std::string("#define B200_TGRAD(dT,u,p,t) ") + tgrad_name + "((dT),(u),(p),(t))\n";
     }
@@ -435,7 +447,8 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         if (at) coop_lanes = atoi(at + 9);
         else {
             coop_lanes = 2;
-            while (coop_lanes < 32 && (n + coop_lanes - 1) / coop_lanes > 2) coop_lanes *= 2;
+            const int per_lane = stiff ? 1 : 2;       // the shuffle LU keeps one row per lane
+            while (coop_lanes < 32 && (n + coop_lanes - 1) / coop_lanes > per_lane) coop_lanes *= 2;
             opts.push_back("-DB200_L=" + std::to_string(coop_lanes));
         }
         if (coop_lanes < 2 || coop_lanes > 32 || (coop_lanes & (coop_lanes - 1)))

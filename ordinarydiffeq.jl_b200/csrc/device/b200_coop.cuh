@@ -24,8 +24,8 @@
 //     compute on stale state and discard the result), finished groups pull the next trajectory from the global
 //     counter.
 // Same reference semantics as b200_ensemble.cuh (citations there).  Limitations of this variant: adaptive stepping,
-// tstops = {tf}, rectangular saveat output (no save_everystep / save_idxs / dense), explicit steppers with the
-// B200_VLEN hooks (Vern7).
+// tstops = {tf}, rectangular saveat output (no save_everystep / save_idxs / dense); steppers: Vern7 (B200_VLEN hooks of
+// b200_vern7.cuh) and Rosenbrock23 with a warp-shuffle LU (b200_ros23_coop.cuh).
 #pragma once
 
 #ifndef B200_L
@@ -122,8 +122,13 @@ B200_D real b200_norm_coop(const real* res, const real* u, bool& all_finite, rea
 #define B200_STEPPER_EXTRA_MEMBERS int sbuf; bool all_finite; real* sm; int g; unsigned gmask;
 #define B200_RHS(du, u, p, t) b200_rhs_coop((du), (u), (p), (t), sbuf, sm, g)
 #define B200_NORM(res, u) b200_norm_coop((res), (u), all_finite, sm, g, gmask)
+#if B200_ALG == B200_ALG_ROS23
+#include "b200_ros23_coop.cuh"
+typedef B200Ros23Coop B200CoopStepper;
+#else
 #include "b200_vern7.cuh"
 typedef B200Vern7 B200CoopStepper;
+#endif
 
 struct B200CTraj {
     real u[B200_VLEN], uprev[B200_VLEN];
@@ -135,6 +140,9 @@ struct B200CTraj {
     int save_idx, nsaved;
     int retcode;
     bool accept, tstop_flag;
+#if B200_IS_ROSENBROCK
+    int njacs, nw, nsolve;
+#endif
 };
 
 B200_D void b200c_emit(const B200Params& P, long long idx, B200CTraj& T, const real* v, int g) {
@@ -177,6 +185,10 @@ B200_D void b200c_begin(const B200Params& P, long long idx, B200CTraj& T, int g)
     T.accept = false; T.tstop_flag = false;
     T.retcode = B200_RC_DEFAULT;
     T.st.all_finite = true;
+#if B200_IS_ROSENBROCK
+    T.njacs = 0; T.nw = 0; T.nsolve = 0;
+#endif
+    T.st.init(T.u, T.p, T.t, T.nf);         // (a stepper with a first-same-as-last stage defers the evaluation to its first attempt)
 }
 
 B200_D void b200c_end(const B200Params& P, long long idx, B200CTraj& T, int g) {
@@ -206,6 +218,9 @@ B200_D void b200c_end(const B200Params& P, long long idx, B200CTraj& T, int g) {
         P.t_final[idx] = T.t;
         P.naccept[idx] = T.naccept; P.nreject[idx] = T.nreject; P.nf[idx] = T.nf;
         P.retcode[idx] = T.retcode; P.nsaved[idx] = T.nsaved;
+#if B200_IS_ROSENBROCK
+        P.njacs[idx] = T.njacs; P.nw[idx] = T.nw; P.nsolve[idx] = T.nsolve;
+#endif
     }
 }
 
@@ -226,6 +241,7 @@ B200_D bool b200c_iterate(const B200Params& P, long long idx, B200CTraj& T, bool
 #pragma unroll
             for (int l = 0; l < B200_VLEN; ++l) T.uprev[l] = T.u[l];
             T.dt = T.dtpropose;
+            T.st.accept();                      // update_fsal!
             b200c_modify_dt_for_tstops(T, dist, tol100);
         }
         T.dt = b200_min_c(P.dtmax, T.dt);
@@ -248,7 +264,13 @@ B200_D bool b200c_iterate(const B200Params& P, long long idx, B200CTraj& T, bool
     real unew[B200_VLEN];
     int nf_dummy = 0;
     const bool fin_before = T.st.all_finite;
+#if B200_IS_ROSENBROCK
+    int nj_dummy = 0, nw_dummy = 0, ns_dummy = 0;
+    const real e = T.st.attempt(T.uprev, unew, T.p, T.t, T.dt, P.reltol, P.abstol, do_step ? T.nf : nf_dummy,
+                                do_step ? T.njacs : nj_dummy, do_step ? T.nw : nw_dummy, do_step ? T.nsolve : ns_dummy, do_step);
+#else
     const real e = T.st.attempt(T.uprev, unew, T.p, T.t, T.dt, P.reltol, P.abstol, do_step ? T.nf : nf_dummy);
+#endif
     if (do_step) {
         T.EEst = e;
 #pragma unroll
@@ -321,6 +343,10 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
     T.st.gmask = gmask;
     T.st.sm = b200_coop_smem + ((size_t)(threadIdx.x >> 5) * B200_GPW + grp) * B200_COOP_WORDS;
     T.st.all_finite = true;
+#if B200_ALG == B200_ALG_ROS23
+    T.st.need_f0 = false;
+    T.st.f0[0] = (real)0; T.st.f2[0] = (real)0; T.st.k1[0] = (real)0; T.st.k2[0] = (real)0;
+#endif
 #pragma unroll
     for (int l = 0; l < B200_VLEN; ++l) { T.u[l] = (real)0; T.uprev[l] = (real)0; }
 #pragma unroll

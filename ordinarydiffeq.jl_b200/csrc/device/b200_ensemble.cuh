@@ -219,10 +219,14 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #endif
 
 #if B200_COOP
-#if B200_ALG != B200_ALG_VERN7
-#error "the lane-group kernel is available for Vern7"
+#if B200_ALG != B200_ALG_VERN7 && B200_ALG != B200_ALG_ROS23
+#error "the lane-group kernel is available for Vern7 and Rosenbrock23"
 #endif
+#if B200_ALG == B200_ALG_ROS23
+struct B200CoopStepperTag { static B200_D int order() { return 2; } static B200_D real qsteady_min() { return (real)1; } static B200_D real qsteady_max() { return (real)1.2; } };
+#else
 struct B200CoopStepperTag { static B200_D int order() { return 7; } static B200_D real qsteady_min() { return (real)1; } static B200_D real qsteady_max() { return (real)1; } };
+#endif
 typedef B200CoopStepperTag B200Stepper;       // order / qsteady for the controller helpers (the stepper itself follows)
 #endif
 

@@ -214,10 +214,24 @@ def _hires8(u, p, t):
             -p[1] * y6 * y8 + 1.81 * y7]
 
 
+def _chain16(u, p, t):
+    """Stiff reaction-diffusion chain, n = 16: u_i' = D (u_{i-1} - 2 u_i + u_{i+1}) - k u_i^3 + s_i with fixed ends
+    (D = p[0], k = p[1]); a tridiagonal Jacobian with eigenvalues down to about -4 D."""
+    n = 16
+    out = []
+    for i in range(n):
+        left = u[i - 1] if i > 0 else 0
+        right = u[i + 1] if i < n - 1 else 0
+        src = 1.0 if i == 0 else 0
+        out.append(p[0] * (left - 2 * u[i] + right) - p[1] * u[i] * u[i] * u[i] + src)
+    return out
+
+
 STIFF_PROBLEMS = {
     # name: (f, n, np, u0, tspan, nominal p)
     "vdp": (_vdp, 2, 1, [1.0, 1.0], (0.0, 6.3), [1.0e3]),
     "hires5": (_hires5, 5, 1, [1.0, 0.0, 0.0, 0.0, 0.0057], (0.0, 321.8122), [1.71]),
+    "chain16": (_chain16, 16, 2, [0.0] * 16, (0.0, 10.0), [400.0, 1.0]),
     "hires8": (_hires8, 8, 2, [1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0057], (0.0, 321.8122), [1.71, 280.0]),
 }
 
@@ -240,3 +254,14 @@ def stiff_params(name, N, offset=0, f32=False):
     for j, v in enumerate(nominal):
         p[:, j] = v * (0.5 + splitmix64_uniform(idx, j))
     return p.astype(np.float32) if f32 else p
+
+
+def stiff_component_sources(name, f32=False):
+    """Component-form sources of a STIFF_PROBLEMS entry for the lane-group Rosenbrock23 (B200ODE_OPT_COMPONENT_RHS):
+    (rhs_i, jac_ij, tgrad_i or None), n, np, u0, tspan — the same expressions as stiff_sources, behind an index."""
+    from . import codegen
+    f, n, np_, u0, tspan, _ = STIFF_PROBLEMS[name]
+    rhs = codegen.build_function_component_c(f, n, np_, fname=name + "_rhs_i", f32=f32)
+    jac = codegen.build_jacobian_entry_c(f, n, np_, fname=name + "_jac_ij", f32=f32)
+    tg = codegen.build_tgrad_component_c(f, n, np_, fname=name + "_tgrad_i", f32=f32)
+    return rhs, jac, tg, n, np_, np.asarray(u0, dtype=np.float32 if f32 else np.float64), tspan

@@ -1205,3 +1205,35 @@ def test_isoutofdomain_parity(pkg, handle, oracle):
         assert (g["retcode"] != 1).any() and (g["retcode"] == 1).any()      # trajectories that must leave the half-space stall
     finally:
         prog.close()
+
+
+# ---- lane-group Rosenbrock23: rows of W across the lanes of a warp, LU and solves on shuffles ---------------------------------
+@pytest.mark.parametrize("problem", ["vdp", "hires5", "hires8", "chain16"])
+@pytest.mark.parametrize("f32", [False, True])
+def test_lane_group_rosenbrock23_shuffle_lu(pkg, handle, oracle, problem, f32):
+    """Same bits as the oracle's sequential partial-pivot LU path (and therefore as the one-thread kernel): final states,
+    saveat rows, step counts, nf / njacs / nw / nsolve."""
+    pl = pkg.problems_library
+    rc, jc, tc, n, np_, u0, tspan = pl.stiff_component_sources(problem, f32)
+    r, j, tg = pl.stiff_sources(problem, f32)[:3]
+    N = 1000 if problem != "vdp" else 250
+    p = pl.stiff_params(problem, N, f32=f32)
+    tol = dict(reltol=1e-6, abstol=1e-8) if not f32 else dict(reltol=1e-3, abstol=1e-5)
+    prog = handle.compile(pkg.ALG_ROSENBROCK23, pkg.F32 if f32 else pkg.F64, n, np_, rc[0], rc[1], jc[0], jc[1],
+                          tc[0] if tc else None, tc[1] if tc else None, extra_options=pkg._lib.OPT_COMPONENT_RHS)
+    try:
+        assert prog.info["local_bytes_integrate"] <= 256
+        mid = [tspan[1] * 0.01, tspan[1] * 0.5]
+        for extra in ({}, {"saveat": mid}):
+            kw = dict(tol, **extra)
+            g = pkg.lowlevel.solve_host(prog, u0, p, tspan, **kw)
+            o = oracle.solve(oracle.ALG_ROSENBROCK23, r, u0, p, tspan, n, np_, f32=f32, jac=j, tgrad=tg, **kw)
+            assert_same_result(g, o)
+            assert (g["retcode"] == 1).all()
+    finally:
+        prog.close()
+    if problem == "hires8" and not f32:
+        with pytest.raises(pkg.B200Error):          # n = 3 stays with the in-register inverse of the one-thread kernel
+            rr, jj, tt = pl.robertson_sources()
+            handle.compile(pkg.ALG_ROSENBROCK23, pkg.F64, 3, 3, rr[0], rr[1], jj[0], jj[1], tt[0], tt[1],
+                           extra_options=pkg._lib.OPT_COMPONENT_RHS)
