@@ -780,6 +780,9 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
 #ifndef B200_CHUNK_MAX
 #define B200_CHUNK_MAX 64
 #endif
+#ifndef B200_REFILL_MIN
+#define B200_REFILL_MIN 1
+#endif
 
 extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_integrate(B200Params P) {
     B200Traj T;
@@ -812,7 +815,9 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
 #define B200_EXHAUSTED (pool_next >= P.N)
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !active);
-        if (need != 0u && !B200_EXHAUSTED) {
+        // B200_REFILL_MIN idle lanes are collected before the (single-lane, divergent) begin path runs: fewer passes
+        // through it against lanes that wait a few steps (measured)
+        if (need != 0u && !B200_EXHAUSTED && (__popc(need) >= B200_REFILL_MIN || need == 0xffffffffu || (P.N - pool_next) < 64)) {
             const int want = __popc(need);
             if (pool_end - pool_next < want) {
                 // refill the warp pool: guided chunk (large while plenty of work remains,

@@ -126,7 +126,8 @@ let
     f = ODEFunction{false}(rober; jac = rober_jac, tgrad = rober_tgrad)
     prob = ODEProblem(f, SVector(1.0, 0.0, 0.0), (0.0, 1.0e5), P[1])
     for (nm, alg) in (("rodas5p", Rodas5P()), ("rosenbrock23", Rosenbrock23()), ("rodas5", Rodas5()), ("rodas4", Rodas4()),
-                      ("rodas42", Rodas42()), ("rodas4p", Rodas4P()), ("rodas4p2", Rodas4P2()), ("rodas5pe", Rodas5Pe()))
+                      ("rodas42", Rodas42()), ("rodas4p", Rodas4P()), ("rodas4p2", Rodas4P2()), ("rodas5pe", Rodas5Pe()),
+                      ("rodas3p", Rodas3P()), ("rodas23w", Rodas23W()), ("autotsit5_rosenbrock23", AutoTsit5(Rosenbrock23())))
         run_case("cfg3_robertson_$(nm)", prob, P, nothing, alg; reltol = 1e-6, abstol = 1e-8, save_everystep = false)
     end
     run_case("cfg3_robertson_rodas5p_saveat", prob, P, nothing, Rodas5P(); reltol = 1e-6, abstol = 1e-8,
@@ -144,4 +145,18 @@ let
     end
     prob = ODEProblem{false}(pleiades, U0[1], (0.0, 3.0))
     run_case("cfg4_pleiades_vern7", prob, nothing, U0, Vern7(); reltol = 1e-6, abstol = 1e-8, save_everystep = false)
+end
+
+# callbacks (Tsit5): the bouncing balls of tests/test_gpu_parity.py::test_callbacks_bouncing_ball_parity
+# (p = (g, e): y'' = -g, v -> -e v at y = 0, downcrossings only; default save_positions, saveat = 0.5)
+let
+    ball(u, p, t) = SVector(u[2], -p[1])
+    P = [SVector(9.81 * (0.5 + U(i - 1, 0)), 0.8 + 0.2 * U(i - 1, 1)) for i in 1:NTRAJ]
+    prob = ODEProblem{false}(ball, SVector(50.0, 0.0), (0.0, 15.0), P[1])
+    condition(u, t, integrator) = u[1]
+    bounce!(integrator) = (integrator.u = SVector(integrator.u[1], -integrator.p[2] * integrator.u[2]))
+    cb = ContinuousCallback(condition, nothing, bounce!)
+    run_case("callbacks_bouncing_ball_tsit5", prob, P, nothing, Tsit5(); callback = cb, saveat = 0.5)
+    term = ContinuousCallback(condition, terminate!)
+    run_case("callbacks_bouncing_ball_terminate_tsit5", prob, P, nothing, Tsit5(); callback = term)
 end

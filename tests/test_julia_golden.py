@@ -35,6 +35,9 @@ CASES = {
     "cfg3_robertson_rodas4p": ("ALG_RODAS4P", "robertson", False, dict(reltol=1e-6, abstol=1e-8)),
     "cfg3_robertson_rodas4p2": ("ALG_RODAS4P2", "robertson", False, dict(reltol=1e-6, abstol=1e-8)),
     "cfg3_robertson_rodas5pe": ("ALG_RODAS5PE", "robertson", False, dict(reltol=1e-6, abstol=1e-8)),
+    "cfg3_robertson_rodas3p": ("ALG_RODAS3P", "robertson", False, dict(reltol=1e-6, abstol=1e-8)),
+    "cfg3_robertson_rodas23w": ("ALG_RODAS23W", "robertson", False, dict(reltol=1e-6, abstol=1e-8)),
+    "cfg3_robertson_autotsit5_rosenbrock23": ("ALG_AUTOTSIT5_ROSENBROCK23", "robertson", False, dict(reltol=1e-6, abstol=1e-8)),
     "cfg3_robertson_rodas5p_saveat": ("ALG_RODAS5P", "robertson", False,
                                       dict(reltol=1e-6, abstol=1e-8, saveat=[100.0, 1000.0, 5.0e4])),
     "cfg4_pleiades_vern7": ("ALG_VERN7", "pleiades", False, dict(reltol=1e-6, abstol=1e-8)),
