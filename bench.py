@@ -65,10 +65,16 @@ WORKLOADS = {
     "lorenz_sweep_64m": dict(problem="lorenz_sweep", alg="tsit5", f32=False, N=1 << 26, saveat=None, tspan=(0.0, 10.0), tol={}),
     "pleiades_vern7_256k": dict(problem="pleiades", alg="vern7", f32=False, N=1 << 18, saveat=None, tspan=(0.0, 3.0),
                                 tol=dict(reltol=1e-6, abstol=1e-8)),
+    # not a BASELINE configuration: a mixed stiff / non-stiff ensemble for the switching algorithm —
+    # Van der Pol with mu log-uniform in [0.5, 500]: lanes that stay in Tsit5, lanes that move to Rosenbrock23 for good and
+    # lanes that switch back and forth share warps
+    "vdp_autotsit5_mixed_256k": dict(problem="vdp_mixed", alg="autotsit5", f32=False, N=1 << 18, saveat=None, tspan=(0.0, 20.0),
+                                     tol={}),
 }
 OTHER_CONFIGS = ["lorenz_tsit5_saveat_1m_f32", "lorenz_tsit5_final_1m", "robertson_rodas5p_1m", "robertson_rosenbrock23_1m",
-                 "pleiades_vern7_256k"]
-ALG_NAMES = {"tsit5": "ALG_TSIT5", "vern7": "ALG_VERN7", "ros23": "ALG_ROSENBROCK23", "rodas5p": "ALG_RODAS5P"}
+                 "pleiades_vern7_256k", "vdp_autotsit5_mixed_256k"]
+ALG_NAMES = {"tsit5": "ALG_TSIT5", "vern7": "ALG_VERN7", "ros23": "ALG_ROSENBROCK23", "rodas5p": "ALG_RODAS5P",
+             "autotsit5": "ALG_AUTOTSIT5_ROSENBROCK23"}
 
 
 def sources(pl, w, device=False):
@@ -80,6 +86,9 @@ def sources(pl, w, device=False):
     if w["problem"] == "robertson":
         r, j, tg = pl.robertson_sources(f32)
         return r, j, tg, 3, 3, None
+    if w["problem"] == "vdp_mixed":
+        r, j, tg, n, np_, _, _ = pl.stiff_sources("vdp", f32)
+        return r, j, tg, n, np_, None
     if w["problem"] == "pleiades":
         if device:
             return pl.pleiades_component_source(f32), None, None, 28, 0, "-DB200_COOP=1"
@@ -102,6 +111,10 @@ def inputs(pl, w, N, offset=0, idx=None, total=None):
         else:
             p[:, 1] = 28.0 * (0.5 + pl.splitmix64_uniform(idx, 0))
         return np.array([1.0, 0.0, 0.0]), (p.astype(np.float32) if f32 else p)
+    if w["problem"] == "vdp_mixed":
+        mu = 0.5 * (1000.0 ** pl.splitmix64_uniform(idx, 0))
+        p = mu.reshape(-1, 1)
+        return np.array([1.0, 1.0]), (p.astype(np.float32) if f32 else p)
     if w["problem"] == "robertson":
         base = np.array([0.04, 3.0e7, 1.0e4])
         p = np.empty((idx.shape[0], 3), dtype=np.float64)
@@ -644,7 +657,13 @@ def main():
                      "trajectories": wc["N"], "saveat": wc["saveat"], "tolerances": wc["tol"] or "defaults",
                      "value": wc["N"] * 3 / (tot * 1e-3), "unit": "trajectories/s", "ms_per_step": tot / 3, "steps": 3, "warmup": 3,
                      "attempted_steps_per_launch": att, "clocks": ck, "program": r.prog.info,
-                     "roofline": r.roofline(float(np.mean(sms)), att, traffic=ncu_traffic(name))}
+                     "roofline": r.roofline(float(np.mean(sms)), att, traffic=ncu_traffic(name))
+                     if (wc["problem"], wc["alg"]) in FLOPS else None}
+            if wc["alg"] == "autotsit5":
+                b = r.bufs
+                stiff_att = int(b.nw.to(torch.int64).sum().item())
+                entry["mix"] = {"attempts_rosenbrock23": stiff_att, "attempts_tsit5": att - stiff_att,
+                                "trajectories_that_used_rosenbrock23": int((b.nw > 0).sum().item())}
             if name == "lorenz_tsit5_saveat_1m_f32" and not args.no_e2e:
                 v, _ = e2e_host(pkg, torch, r, 3, 1, barrier, world, dev, dist)
                 v["api"] = "b200ode_solve (C ABI, pinned host buffers), FP32"

@@ -96,6 +96,24 @@ def build_jacobian_c(f, n, np_, fname="diffeqjac", f32=False, iip=False):
     return _emit(fname, "J", flat, u, p, t, f32), fname
 
 
+def build_matrix_c(f, n, np_, fname="diffeqjac", f32=False, iip=False):
+    """A user-supplied Jacobian callable jac(u, p, t) -> n x n (rows of rows, numpy array of expressions or sympy Matrix;
+    in-place form jac(J, u, p, t) fills a list of rows), emitted column-major like build_jacobian_c."""
+    u = [sp.Symbol("RHS1_%d" % i, real=True) for i in range(n)]
+    p = [sp.Symbol("RHS2_%d" % i, real=True) for i in range(np_)]
+    t = sp.Symbol("RHS3", real=True)
+    if iip:
+        M = [[0] * n for _ in range(n)]
+        f(M, u, p, t)
+    else:
+        M = f(u, p, t)
+    M = sp.Matrix(M)
+    if M.shape != (n, n):
+        raise ValueError("jac returned a %s matrix, expected %dx%d" % (M.shape, n, n))
+    flat = [M[i, j] for j in range(n) for i in range(n)]   # column major
+    return _emit(fname, "J", flat, u, p, t, f32), fname
+
+
 def build_tgrad_c(f, n, np_, fname="diffeqtgrad", f32=False, iip=False):
     """∂f/∂t."""
     exprs, u, p, t = trace(f, n, np_, iip)

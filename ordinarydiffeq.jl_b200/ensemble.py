@@ -229,7 +229,8 @@ class ODEFunction:
         jac = tg = None
         if need_jac:
             if self.jac is not None:
-                jac = one(self.jac, codegen.build_function_c, "diffeqjac")
+                # a Python jac(u, p, t) returns the n x n matrix (rows of rows / sympy Matrix): flattened column-major
+                jac = one(self.jac, codegen.build_matrix_c, "diffeqjac")
             elif not isinstance(self.f, CSource):
                 jac = codegen.build_jacobian_c(self.f, n, np_, f32=f32, iip=self.iip)
             else:
@@ -469,7 +470,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     # the reference's default is save_everystep = isempty(saveat) (solve.jl:138): ragged per-step output
     everystep = bool(kw.get("save_everystep", not has_saveat))
     adaptive = bool(kw.get("adaptive", True))
-    if not adaptive and kw.get("dt") is None and not kw.get("tstops"):
+    if not adaptive and kw.get("dt") is None and (kw.get("tstops") is None or len(kw["tstops"]) == 0):
         # solve.jl:277-280
         raise ValueError("Fixed timestep methods require a choice of dt or choosing the tstops")
     dense_kw = kw.get("dense", None)     # default: save_everystep && isempty(saveat) (solve.jl:144-145)
@@ -498,8 +499,10 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             raise ValueError("save_idxs out of range for a state of length %d" % n)
     tstops = kw.get("tstops", None)
     tstops = None if tstops is None or len(tstops) == 0 else [float(x) for x in tstops]
-    dense_ok = (everystep and not grid and save_start and save_idxs is None and tstops is None
-                and alg.alg_id != _lib.ALG_ROSENBROCK32 and dense_kw is not False)      # dense = save_everystep && isempty(saveat) (solve.jl:144)
+    # (the dense pass re-integrates with the default end-point handling: a solve with save_end = false keeps sol.t without
+    #  the row at tf, which the dense rows would include — declined rather than answered from different rows)
+    dense_ok = (everystep and not grid and save_start and save_idxs is None and tstops is None and save_end is not False
+                and alg.alg_id not in (_lib.ALG_ROSENBROCK32, _lib.ALG_AUTOTSIT5_ROSENBROCK23) and dense_kw is not False)      # dense = save_everystep && isempty(saveat) (solve.jl:144)
     if dense_kw and not dense_ok:
         raise NotImplementedError("dense=true is served for save_everystep solves without saveat / save_idxs / tstops "
                                   "(the stages are recomputed from the saved steps); not for Rosenbrock32")
