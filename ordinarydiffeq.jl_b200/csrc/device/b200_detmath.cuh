@@ -80,13 +80,23 @@ B200_HD double b200_log10_cr(double x) {
     b200_dd den = b200_two_sum(f, 1.0);
     b200_dd z = b200_dd_div(num, den);
     b200_dd z2 = b200_dd_mul(z, z);
-    // sum_{j=0}^{22} z2^j/(2j+1), Horner from the top; |z| <= 0.1716 -> z^47/47 < 3e-38
-    b200_dd s = b200_dd_make(1.0 / 45.0, 0.0);
-    // coefficients 1/(2j+1) are not exact doubles: build each as dd = 1/(2j+1)
-    for (int j = 21; j >= 0; --j) {
-        b200_dd c = b200_dd_div(b200_dd_make(1.0, 0.0), b200_dd_make((double)(2 * j + 1), 0.0));
-        s = b200_dd_add(b200_dd_mul(s, z2), c);
-    }
+    // sum_{j=0}^{22} z2^j/(2j+1), Horner from the top; |z| <= 0.1716 -> z^47/47 < 3e-38.  The coefficients 1/(2j+1) are
+    // double-double constants (rounded from 300-bit values): no division inside the series
+    const double LH[23] = {0x1.0000000000000p+0, 0x1.5555555555555p-2, 0x1.999999999999ap-3, 0x1.2492492492492p-3, 0x1.c71c71c71c71cp-4,
+                           0x1.745d1745d1746p-4, 0x1.3b13b13b13b14p-4, 0x1.1111111111111p-4, 0x1.e1e1e1e1e1e1ep-5, 0x1.af286bca1af28p-5,
+                           0x1.8618618618618p-5, 0x1.642c8590b2164p-5, 0x1.47ae147ae147bp-5, 0x1.2f684bda12f68p-5, 0x1.1a7b9611a7b96p-5,
+                           0x1.0842108421084p-5, 0x1.f07c1f07c1f08p-6, 0x1.d41d41d41d41dp-6, 0x1.bacf914c1bad0p-6, 0x1.a41a41a41a41ap-6,
+                           0x1.8f9c18f9c18fap-6, 0x1.7d05f417d05f4p-6, 0x1.6c16c16c16c17p-6};
+    const double LL[23] = {0x0.0p+0, 0x1.5555555555555p-56, -0x1.999999999999ap-57, 0x1.2492492492492p-57, 0x1.c71c71c71c71cp-58,
+                           -0x1.745d1745d1746p-59, -0x1.3b13b13b13b14p-58, 0x1.1111111111111p-60, 0x1.e1e1e1e1e1e1ep-61, 0x1.af286bca1af28p-59,
+                           0x1.8618618618618p-59, 0x1.642c8590b2164p-60, -0x1.eb851eb851eb8p-61, 0x1.2f684bda12f68p-59, 0x1.1a7b9611a7b96p-61,
+                           0x1.0842108421084p-60, -0x1.f07c1f07c1f08p-61, 0x1.0750750750750p-60, -0x1.bacf914c1bad0p-60, 0x1.0690690690690p-60,
+                           -0x1.f3831f3831f38p-61, 0x1.7d05f417d05f4p-62, -0x1.f49f49f49f49fp-61};
+    b200_dd s = b200_dd_make(LH[22], LL[22]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 21; j >= 0; --j) s = b200_dd_add(b200_dd_mul(s, z2), b200_dd_make(LH[j], LL[j]));
     b200_dd lnf = b200_dd_mul(z, s);
     lnf = b200_dd_make(lnf.hi * 2.0, lnf.lo * 2.0);
     const b200_dd INV_LN10 = b200_dd_make(0x1.bcb7b1526e50ep-2, 0x1.95355baaafad3p-57);
@@ -105,13 +115,21 @@ B200_HD double b200_exp10_cr(double y) {
     b200_dd r = b200_dd_add_d(t, -n);               // |r| <= 0.5 (+tiny)
     b200_dd w = b200_dd_mul(r, LN2);                // 2^r = exp(w), |w| <= 0.347
     w = b200_dd_make(w.hi * 0.125, w.lo * 0.125);   // exact scaling
-    // exp(w) Taylor to degree 17 (|w|<=0.0434: w^18/18! < 1e-40), Horner
-    b200_dd s = b200_dd_make(1.0, 0.0);
-    for (int j = 17; j >= 1; --j) {
-        // s = 1 + (w/j) * s
-        b200_dd wj = b200_dd_div(w, b200_dd_make((double)j, 0.0));
-        s = b200_dd_add_d(b200_dd_mul(wj, s), 1.0);
-    }
+    // exp(w) Taylor to degree 17 (|w|<=0.0434: w^18/18! < 1e-40), Horner over the double-double constants 1/j!
+    // (rounded from 300-bit values): no division — the r1 form `s = 1 + (w/j) s` spent 51 IEEE divisions here
+    const double EH[18] = {0x1.0000000000000p+0, 0x1.0000000000000p+0, 0x1.0000000000000p-1, 0x1.5555555555555p-3, 0x1.5555555555555p-5,
+                           0x1.1111111111111p-7, 0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13, 0x1.a01a01a01a01ap-16, 0x1.71de3a556c734p-19,
+                           0x1.27e4fb7789f5cp-22, 0x1.ae64567f544e4p-26, 0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33, 0x1.93974a8c07c9dp-37,
+                           0x1.ae7f3e733b81fp-41, 0x1.ae7f3e733b81fp-45, 0x1.952c77030ad4ap-49};
+    const double EL[18] = {0x0.0p+0, 0x0.0p+0, 0x0.0p+0, 0x1.5555555555555p-57, 0x1.5555555555555p-59, 0x1.1111111111111p-63,
+                           -0x1.f49f49f49f49fp-65, 0x1.a01a01a01a01ap-73, 0x1.a01a01a01a01ap-76, -0x1.c154f8ddc6c00p-73, 0x1.cbbc05b4fa99ap-76,
+                           -0x1.c062e06d1f209p-80, -0x1.2aec959e14c06p-83, 0x1.f28e0cc748ebep-87, 0x1.05d6f8a2efd1fp-92, 0x1.1d8656b0ee8cbp-97,
+                           0x1.1d8656b0ee8cbp-101, 0x1.ac981465ddc6cp-103};
+    b200_dd s = b200_dd_make(EH[17], EL[17]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 16; j >= 0; --j) s = b200_dd_add(b200_dd_mul(s, w), b200_dd_make(EH[j], EL[j]));
     s = b200_dd_mul(s, s); s = b200_dd_mul(s, s); s = b200_dd_mul(s, s);
     // scale by 2^n, n integer in the normal range
     int ni = (int)n;
