@@ -757,8 +757,11 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 for (int i = 0; i < n; ++i) uprev[i] = u[i];
                 dt = dtpropose;
                 // update_fsal! (:215-239): reeval_fsal / derivative_discontinuity => reset_fsal!
-                if constexpr (SupportsCallbacks<Alg>::value) {
-                    if (reeval_fsal) cache.reset_fsal(u, p, t, stats); else cache.update_fsal();
+                // (for every FSAL stepper initialize! IS "fsalfirst = f(u, p, t); nf += 1"; steppers that are not FSAL have
+                //  nothing to refresh; the composite algorithm re-evaluates in its current branch)
+                if (reeval_fsal) {
+                    if constexpr (IsComposite<Alg>::value) cache.reset_fsal(u, p, t, stats);
+                    else if (Alg::fsal_init()) cache.initialize(u, p, t, stats);
                 } else cache.update_fsal();
                 modify_dt_for_tstops();
             } else {
@@ -834,9 +837,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 dtpropose = dt;
             }
             // handle_callbacks! (integrator_utils.jl:1081-1132) -> savevalues! (:340-414)
-            if constexpr (SupportsCallbacks<Alg>::value) {
-                if (o.ncb > 0) handle_callbacks(); else savevalues(false);
-            } else savevalues(false);
+            if (o.ncb > 0) handle_callbacks(); else savevalues(false);
             if (terminated) break;                                      // terminate!: the tstops heap was emptied
             // handle_tstop! (integrator_utils.jl:1290-1314): pop every copy of a stop that was reached
             while (o.ntstops > 0 && t == cur_tstop && tstop_idx + 1 < o.ntstops) cur_tstop = o.tstops[++tstop_idx];
@@ -969,7 +970,9 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
             if (a.cbs[i].kind == 2) o.isout = a.cbs[i].condition; else real_cbs.push_back(a.cbs[i]);
         }
         if (!real_cbs.empty()) {
-            if (a.alg != ALG_TSIT5) return -5;                      // callbacks: Tsit5 only (first slice of SURVEY §8(f) row 4)
+            // ContinuousCallback needs the stepper's _ode_addsteps!(always_calc_begin = true): Tsit5 (first slice of SURVEY
+            // §8(f) row 4); DiscreteCallback works with every stepper
+            for (auto& c : real_cbs) if (c.kind == 1 && a.alg != ALG_TSIT5) return -5;
             o.cbs = real_cbs.data(); o.ncb = (int)real_cbs.size();
         }
     }

@@ -240,8 +240,8 @@ int callbacks_source(int alg, int dtype, const B200CallbackSrc* cbs, int ncb, bo
         }
     int ncc = 0;
     for (int i = 0; i < ncb; ++i) ncc += (cbs[i].kind == B200ODE_CB_CONTINUOUS);
-    if (!order.empty() && alg != B200ODE_ALG_TSIT5)
-        return fail(B200ODE_EUNSUPPORTED, "callbacks are available for Tsit5 (one trajectory per thread)");
+    if (ncc > 0 && alg != B200ODE_ALG_TSIT5)
+        return fail(B200ODE_EUNSUPPORTED, "continuous callbacks are available for Tsit5 (discrete callbacks and isoutofdomain: every stepper)");
     std::vector<std::string> emitted;
     auto add_fn = [&](const char* src, const char* name, bool is_condition) -> int {
         if (!is_identifier(name)) return fail(B200ODE_EINVAL, "callbacks: a function name is not an identifier");

@@ -1,5 +1,6 @@
 // b200_callbacks.cuh — events: ContinuousCallback (root finding on the step's interpolant) and DiscreteCallback,
-// per trajectory, inside the accepting step of b200_integrate.  First slice of SURVEY §8(f) row 4: Tsit5.
+// per trajectory, inside the accepting step of b200_integrate.  First slice of SURVEY §8(f) row 4: continuous callbacks
+// with Tsit5 (they need the stepper's _ode_addsteps!(always_calc_begin = true)), discrete callbacks with every stepper.
 //
 // Reference behaviour reproduced (file:line under /root/reference):
 //   handle_callbacks!                       lib/OrdinaryDiffEqCore/src/integrators/integrator_utils.jl:1081-1132
@@ -127,6 +128,13 @@ B200_D bool b200_savevalues(const B200Params& P, long long idx, B200Traj& T, boo
     return savedexactly;
 }
 
+B200_D void b200_run_affect(int k, bool neg, B200Traj& T) {
+    int term = 0;
+    b200_cb_affect(k, neg, T.u, T.p, T.t, &term);
+    if (term) { T.terminated = true; T.retcode = B200_RC_TERMINATED; }
+}
+
+#if B200_NCC > 0
 // get_condition
 B200_D real b200_get_condition(int k, B200Traj& T, real abst) {
     if (abst == T.t) return b200_cb_condition(k, T.u, T.p, abst);
@@ -181,11 +189,6 @@ B200_D bool b200_find_callback_time(int k, int callback_idx, B200Traj& T, real& 
     return occurred;
 }
 
-B200_D void b200_run_affect(int k, bool neg, B200Traj& T) {
-    int term = 0;
-    b200_cb_affect(k, neg, T.u, T.p, T.t, &term);
-    if (term) { T.terminated = true; T.retcode = B200_RC_TERMINATED; }
-}
 
 // apply_callback!
 B200_D void b200_apply_callback(const B200Params& P, long long idx, int k, B200Traj& T, real cb_time, real prev_sign,
@@ -216,6 +219,8 @@ B200_D void b200_apply_callback(const B200Params& P, long long idx, int k, B200T
         if (cb.save_after) { b200_savevalues(P, idx, T, true); saved_in_cb = true; }
     }
 }
+
+#endif  // B200_NCC > 0
 
 // handle_callbacks!
 B200_D void b200_handle_callbacks(const B200Params& P, long long idx, B200Traj& T) {

@@ -60,6 +60,8 @@ struct B200AutoTsit5Ros23 {
     }
 
     B200_D void accept() { if (current == 1) ns.accept(); else stf.accept(); }
+    // reset_fsal! after a callback modified u: fsalfirst = f(u, p, t) in the running branch, nf += 1
+    B200_D void reset_fsal(const real* u, const real* p, real t, int& nf) { if (current == 1) ns.init(u, p, t, nf); else stf.init(u, p, t, nf); }
     B200_D void dense_prepare(const real*, const real*, const real*, real, real) {}
     B200_D void interp(real th, real dt, const real* y0, const real* y1, real* out) const {
         if (current == 1) ns.interp(th, dt, y0, y1, out); else stf.interp(th, dt, y0, y1, out);

@@ -204,8 +204,11 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #if B200_VECTOR_TOL && B200_COOP
 #error "per-component tolerances are not available in the lane-group kernel"
 #endif
-#if B200_CALLBACKS && (B200_COOP || B200_ALG != B200_ALG_TSIT5)
-#error "callbacks are available for Tsit5"
+#if B200_CALLBACKS && B200_COOP
+#error "callbacks are not available in the lane-group kernel"
+#endif
+#if B200_CALLBACKS && B200_NCC > 0 && B200_ALG != B200_ALG_TSIT5
+#error "continuous callbacks are available for Tsit5 (discrete callbacks: every stepper)"
 #endif
 #if (B200_EVERYSTEP || defined(B200_SAVE_IDXS)) && B200_COOP
 #error "save_everystep / save_idxs are not available in the lane-group kernel"
@@ -547,8 +550,14 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
             for (int c = 0; c < B200_N; ++c) T.uprev[c] = T.u[c];
             T.dt = T.dtpropose;
 #if B200_CALLBACKS
-            // update_fsal! (integrator_utils.jl:215-239): reeval_fsal => reset_fsal!
+            // update_fsal! (integrator_utils.jl:215-239): reeval_fsal => reset_fsal!.  For every FSAL stepper init() IS
+            // "fsalfirst = f(u, p, t); nf += 1" and steppers that are not FSAL have nothing to refresh (their init() is
+            // empty); the composite algorithm re-evaluates in its running branch
+#if B200_COMPOSITE
             if (T.reeval_fsal) T.st.reset_fsal(T.u, T.p, T.t, T.nf); else T.st.accept();
+#else
+            if (T.reeval_fsal) T.st.init(T.u, T.p, T.t, T.nf); else T.st.accept();
+#endif
 #else
             T.st.accept();
 #endif

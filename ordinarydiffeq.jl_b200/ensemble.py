@@ -512,8 +512,8 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     if kw.get("callback") is not None:
         cbset = kw["callback"] if isinstance(kw["callback"], CallbackSet) else CallbackSet(kw["callback"])
         if cbset.callbacks:
-            if not isinstance(alg, Tsit5):
-                raise NotImplementedError("callbacks are available with Tsit5()")
+            if not isinstance(alg, Tsit5) and any(isinstance(c, ContinuousCallback) for c in cbset.callbacks):
+                raise NotImplementedError("continuous callbacks are available with Tsit5() (discrete callbacks: every algorithm)")
             cb_specs = [c.spec() for c in cbset.callbacks]
             if any(any(c.save_positions) for c in cbset.callbacks) and not everystep:
                 ragged, cb_flags = True, _lib.FLAG_NO_STEP_ROWS

@@ -1237,3 +1237,40 @@ def test_lane_group_rosenbrock23_shuffle_lu(pkg, handle, oracle, problem, f32):
             rr, jj, tt = pl.robertson_sources()
             handle.compile(pkg.ALG_ROSENBROCK23, pkg.F64, 3, 3, rr[0], rr[1], jj[0], jj[1], tt[0], tt[1],
                            extra_options=pkg._lib.OPT_COMPONENT_RHS)
+
+
+@pytest.mark.parametrize("name", ["Vern7", "DP5", "BS3", "Vern6", "Vern9", "Rosenbrock23", "Rodas5P", "AutoTsit5_Rosenbrock23"])
+def test_discrete_callbacks_with_every_stepper(pkg, handle, oracle, name):
+    """A one-shot kick (state jump + parameter change) once t >= 1, default save_positions, ragged rows: FSAL steppers
+    re-evaluate their first stage in the next loopheader! (reset_fsal!), the others have nothing to refresh."""
+    pl = pkg.problems_library
+    T = "double"
+    dcond = ("%s kick_c(const %s* u, const %s* p, const %s t) { return (t >= 1.0 && p[1] < 1e8) ? 1.0 : 0.0; }\n" % (T, T, T, T), "kick_c")
+    kick = ("void kick(%s* u, %s* p, const %s t, int* terminate) { p[1] = p[1] + 1e9; u[0] = u[0] * 0.5; }\n" % (T, T, T), "kick")
+    cbs = [dict(kind="discrete", condition=dcond, affect=kick)]
+    alg = getattr(pkg, "ALG_" + name.upper())
+    oalg = getattr(oracle, "ALG_" + name.upper())
+    stiff = name in ("Rosenbrock23", "Rodas5P", "AutoTsit5_Rosenbrock23")
+    N = 600
+    if stiff:
+        r, j, tg = pl.robertson_sources()
+        p = pl.robertson_params(N)
+        args = (r[0], r[1], j[0], j[1], tg[0], tg[1])
+        okw = dict(jac=j, tgrad=tg)
+        rhs, tspan, tol = r, (0.0, 50.0), dict(reltol=1e-6, abstol=1e-8)
+    else:
+        rhs = pl.lorenz_source()
+        p = pl.lorenz_params(N)
+        args = (rhs[0], rhs[1])
+        okw, tspan, tol = {}, (0.0, 3.0), {}
+    prog = handle.compile(alg, pkg.F64, 3, 3, *args, extra_options=pkg._lib.OPT_EVERYSTEP, callbacks=cbs)
+    try:
+        g = pkg.lowlevel.solve_host_everystep(prog, U0, p, tspan, saveat=[0.5, 2.0], **tol)
+        o = oracle.solve(oalg, rhs, U0, p, tspan, 3, 3, callbacks=cbs, save_everystep=True, saveat=[0.5, 2.0], **okw, **tol)
+        _assert_same_ragged(g, o)
+        assert (g["retcode"] == 1).all()
+    finally:
+        prog.close()
+    with pytest.raises(pkg.B200Error):          # continuous callbacks stay with Tsit5
+        handle.compile(alg, pkg.F64, 3, 3, *args, extra_options=pkg._lib.OPT_EVERYSTEP,
+                       callbacks=[dict(kind="continuous", condition=dcond, affect=kick)])
