@@ -113,6 +113,7 @@ OPT_TSTOPS = "-DB200_TSTOPS=1"
 OPT_VECTOR_TOL = "-DB200_VECTOR_TOL=1"
 OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
 OPT_COMPONENT_RHS = "-DB200_COOP=1"
+OPT_SMEM_STAGES = "-DB200_WIDE=1"
 
 
 def opt_save_idxs(idxs):

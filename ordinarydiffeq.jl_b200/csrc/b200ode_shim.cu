@@ -130,6 +130,7 @@ struct b200ode_program_s {
     std::vector<double> tolv_cached;   // the 2n tolerances currently resident in the module's B200_TOLV
     int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
+    int wide_nt = 0;             // > 0: shared-memory stage kernel (device/b200_vern7_wide.cuh): trajectories in flight per CTA
     B200ProgramInfo info{};
 };
 
@@ -306,7 +307,7 @@ int callbacks_source(int alg, int dtype, const B200CallbackSrc* cbs, int ncb, bo
 int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const char* rhs_name,
                 const char* jac_src, const char* jac_name, const char* tgrad_src, const char* tgrad_name,
                 const char* extra_options, std::vector<char>& cubin, std::string& log, double* ms, int* coop_l = nullptr,
-                const B200CallbackSrc* cbs = nullptr, int ncb = 0) {
+                const B200CallbackSrc* cbs = nullptr, int ncb = 0, size_t* dyn_smem_out = nullptr, int* wide_nt_out = nullptr) {
     int rc = validate_compile_args(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name);
     if (rc) return rc;
     std::string cb_text;
@@ -351,12 +352,19 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     // Lane-group kernel (device/b200_coop.cuh): opt-in with -DB200_COOP=1; the RHS is then in component form
     //     real NAME(int i, const real* u, const real* p, const real t)   returning du_i
     const bool coop = extra_options && strstr(extra_options, "-DB200_COOP=1");
+    // Shared-memory stage kernel (device/b200_vern7_wide.cuh): opt-in with -DB200_WIDE=1; the RHS keeps the
+    // full-vector form and is inlined once, compiled in the two arithmetic flavours described below
+    const bool wide = extra_options && strstr(extra_options, "-DB200_WIDE=1");
+    if (wide && (coop || alg != B200ODE_ALG_VERN7))
+        return fail(B200ODE_EUNSUPPORTED, "the shared-memory stage kernel (B200ODE_OPT_SMEM_STAGES) is available for Vern7 in the one-thread form");
+    if (wide && ncb > 0)
+        return fail(B200ODE_EUNSUPPORTED, "callbacks are not available in the shared-memory stage kernel");
     if (coop && alg != B200ODE_ALG_VERN7 && alg != B200ODE_ALG_ROSENBROCK23)
         return fail(B200ODE_EUNSUPPORTED, "the lane-group kernel (B200ODE_OPT_COMPONENT_RHS) is available for Vern7 and Rosenbrock23");
     if (coop && alg == B200ODE_ALG_ROSENBROCK23 && (n < 2 || n > 16 || n == 3))
         return fail(B200ODE_EUNSUPPORTED, "the lane-group Rosenbrock23 (warp-shuffle LU) serves n = 2 and 4..16; n = 3 uses the in-register "
                                           "inverse of the one-thread kernel");
-    if (!coop)
+    if (!coop && !wide)
     tu += std::string(rhs_inline ? "__device__ __forceinline__ void " : "__device__ __noinline__ void ") + rhs_name +
           "(real* du, const real* u, const real* p, const real t);\n";
     if (stiff && !coop) {
@@ -393,6 +401,24 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
             tu += std::string("#define B200_USER_JAC_NAME ") + jac_name + "\n";
             if (tgrad_src) tu += std::string("#define B200_USER_TGRAD_NAME ") + tgrad_name + "\n";
         }
+    } else if (wide) {
+        // Full-vector form, compiled twice as member functions (see the component form above): B200UserFast with
+        // sqrt / B200_DIV mapped to the flagged branch-free sequences, B200UserExact with the plain operators
+        const std::string body = strip_includes(rhs_src);
+        // (B200_WIDE_WINDOW: see b200_sqrt_window in device/b200_vern7_wide.cuh — the text's roots are started at most
+        //  that many root/quotient groups ahead, so the register allocator is not flooded by the scheduler)
+        tu += "#ifndef B200_WIDE_WINDOW\n#define B200_WIDE_WINDOW 0\n#endif\n"
+              "#include \"b200_window.cuh\"\n"
+              "struct B200UserFast {\n  bool b200_bad;\n  bool b200_win[B200_WIDE_WINDOW + 1];\n"
+              "#define B200_DIV(a, b) b200_div_fast((a), (b), b200_bad)\n"
+              "#define sqrt(x) b200_sqrt_window((x), b200_bad, b200_win)\n#define sqrtf(x) b200_sqrt_window((x), b200_bad, b200_win)\n"
+              "__device__ __forceinline__\n";
+        tu += body;
+        tu += "\n#undef B200_DIV\n#undef sqrt\n#undef sqrtf\n};\n";
+        tu += "struct B200UserExact {\n#define B200_DIV(a, b) ((a) / (b))\n__device__ __forceinline__\n";
+        tu += body;
+        tu += "\n#undef B200_DIV\n};\n";
+        tu += std::string("#define B200_USER_FULL_NAME ") + rhs_name + "\n";
     } else
     tu += strip_includes(rhs_src);
     if (stiff && !coop) {
@@ -406,6 +432,7 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     tu += cb_text;
     tu += "// ---- steppers ----\n";
     if (coop) tu += "#define B200_USER_RHS_COMP(i,u,p,t) (B200UserExact().B200_USER_COMP_NAME((i),(u),(p),(t)))\n";
+    else if (wide) tu += "#define B200_USER_RHS(du,u,p,t) (B200UserExact().B200_USER_FULL_NAME((du),(u),(p),(t)))\n";
     else tu += std::string("#define B200_USER_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
     if (stiff && !coop) {
         tu += std::string("#define B200_JAC(J,u,p,t) ") + jac_name + "((J),(u),(p),(t))\n";
@@ -455,6 +482,21 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
             return fail(B200ODE_EINVAL, "-DB200_L= must be a power of two in 2..32");
     }
     if (coop_l) *coop_l = coop_lanes;
+    if (wide) {
+        // threads per CTA that own a trajectory: 9 stage slots x n reals each, inside the 227 KB a CTA may opt in to
+        // on sm_100; a multiple of 16 (a half-filled last warp still adds trajectories), at most 512
+        const size_t per_thread = (size_t)9 * n * (dtype == B200ODE_F32 ? 4 : 8);
+        long long nt = (long long)(232448 / per_thread);
+        const char* at = strstr(extra_options, "-DB200_WIDE_NT=");
+        if (at) nt = std::min<long long>(nt, atoll(at + 15));
+        else nt = std::min<long long>(nt, 512) & ~15ll;
+        if (nt < 16) return fail(B200ODE_EUNSUPPORTED, "the shared-memory stage kernel needs at least 16 trajectories per SM: n is too large");
+        if (!at) opts.push_back("-DB200_WIDE_NT=" + std::to_string(nt));
+        if (!has_block) { opts.push_back("-DB200_BLOCK=" + std::to_string((nt + 31) / 32 * 32)); has_block = true; }
+        if (!has_minb) { opts.push_back("-DB200_MINBLOCKS=1"); has_minb = true; }
+        if (dyn_smem_out) *dyn_smem_out = per_thread * (size_t)nt;
+        if (wide_nt_out) *wide_nt_out = (int)nt;
+    }
     // measured launch shapes (scripts/sweep_dev.py): small explicit systems run best as one 512-thread
     // CTA per SM at 128 registers (FP64) / three 256-thread CTAs at 80 registers (FP32)
     const bool small_explicit = !stiff && words <= 8 &&
@@ -852,7 +894,17 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         CUDA_TRY(cudaLaunchKernel((const void*)prog->k_initdt, dim3(g), dim3(256), args, 0, stream));
     }
     unsigned grid;
-    if (prog->coop_l > 0) {
+    if (prog->wide_nt > 0) {
+        if (P.nsaveat > 0) {
+            // interior rows need the interpolant, whose lazy stages k11..k16 this variant does not store
+            for (int i = 0; i < o->nsaveat; ++i)
+                if ((R)o->saveat[i] > (R)dp->t0 && (R)o->saveat[i] < (R)dp->tf)
+                    return fail(B200ODE_EUNSUPPORTED, "saveat points inside (t0, tf) are not available in the shared-memory stage kernel "
+                                                      "(B200ODE_OPT_SMEM_STAGES): compile the program without it");
+        }
+        const long long need = (N + prog->wide_nt - 1) / prog->wide_nt;
+        grid = (unsigned)std::min<long long>(prog->info.grid, need > 0 ? need : 1);
+    } else if (prog->coop_l > 0) {
         const long long per_cta = (long long)(prog->info.block / prog->coop_l);      // trajectories in flight per CTA
         const long long need = (N + per_cta - 1) / per_cta;
         grid = (unsigned)std::min<long long>(prog->info.grid, need > 0 ? need : 1);
@@ -1011,7 +1063,7 @@ static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dty
     prog->h = h; prog->alg = alg; prog->dtype = dtype; prog->n = n; prog->np = np;
     std::string log; double ms = 0;
     int rc = nvrtc_build(alg, dtype, n, np, rhs_src, rhs_name, jac_src, jac_name, tgrad_src, tgrad_name,
-                         extra_options, prog->cubin, log, &ms, &prog->coop_l, cbs, ncb);
+                         extra_options, prog->cubin, log, &ms, &prog->coop_l, cbs, ncb, &prog->dyn_smem, &prog->wide_nt);
     if (rc) { delete prog; return rc; }
     prog->callbacks = false;
     for (int i = 0; i < ncb; ++i) prog->callbacks = prog->callbacks || (cbs[i].kind != B200ODE_CB_ISOUTOFDOMAIN);
@@ -1026,6 +1078,7 @@ static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dty
     prog->nsave = parse_save_idxs(extra_options, n);
     if (prog->nsave < 0) { delete prog; return fail(B200ODE_EINVAL, "-DB200_SAVE_IDXS= must list 0-based component indices below n, comma separated"); }
     if (prog->nsave == 0) prog->nsave = n;
+    if (prog->everystep && prog->wide_nt > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_everystep is not available in the shared-memory stage kernel"); }
     if (prog->nsave != n && prog->coop_l > 0) { delete prog; return fail(B200ODE_EUNSUPPORTED, "save_idxs is not available in the lane-group kernel"); }
     cudaError_t e = cudaLibraryLoadData(&prog->lib, prog->cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { delete prog; return fail(B200ODE_ECUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e)); }

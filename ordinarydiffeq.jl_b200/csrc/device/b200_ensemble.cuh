@@ -57,6 +57,13 @@
 #define B200_COOP 0           // 1: lane-group kernel (b200_coop.cuh): B200_L lanes per trajectory, component-form RHS
 #endif
 
+#ifndef B200_WIDE
+#define B200_WIDE 0           // 1: stage derivatives in shared memory (b200_vern7_wide.cuh); B200_WIDE_NT threads per CTA own a trajectory
+#endif
+#if B200_WIDE && (B200_COOP || B200_ALG != B200_ALG_VERN7)
+#error "the shared-memory stage kernel (B200ODE_OPT_SMEM_STAGES) is available for Vern7, one thread per trajectory"
+#endif
+
 #if B200_COOP
 // defined below, after B200Params (b200_coop.cuh)
 // the one-thread-per-trajectory initial-dt kernel evaluates the component form in a loop
@@ -65,6 +72,10 @@
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_tsit5.cuh"
 typedef B200Tsit5 B200Stepper;
+#elif B200_ALG == B200_ALG_VERN7 && B200_WIDE
+// stage derivatives in shared memory, one inlined RHS (b200_vern7_wide.cuh): wide states
+#include "b200_vern7_wide.cuh"
+typedef B200Vern7Wide B200Stepper;
 #elif B200_ALG == B200_ALG_VERN7
 #define B200_RHS(du, u, p, t) B200_USER_RHS(du, u, p, t)
 #include "b200_vern7.cuh"
@@ -206,6 +217,9 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #endif
 #if B200_CALLBACKS && B200_COOP
 #error "callbacks are not available in the lane-group kernel"
+#endif
+#if B200_WIDE && (B200_EVERYSTEP || B200_CALLBACKS)
+#error "save_everystep / callbacks are not available in the shared-memory stage kernel (no interpolant: k11..k16 are not stored)"
 #endif
 #if B200_CALLBACKS && B200_NCC > 0 && B200_ALG != B200_ALG_TSIT5
 #error "continuous callbacks are available for Tsit5 (discrete callbacks: every stepper)"
@@ -797,8 +811,15 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
     B200Traj T;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
+#if B200_WIDE
+    // only the first B200_WIDE_NT threads of the CTA have a shared-memory column: the others never take a trajectory
+    const bool lane_on = threadIdx.x < B200_WIDE_NT;
+    T.st.bind();
+#else
+    const bool lane_on = true;
+#endif
 
-    if (P.flags & B200_FLAG_STATIC_SCHEDULE) {
+    if (!B200_WIDE && (P.flags & B200_FLAG_STATIC_SCHEDULE)) {
         long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         bool live = idx < P.N;
         if (live) {
@@ -823,7 +844,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
     // was spilled to local memory and re-loaded at the top of every iteration.)
 #define B200_EXHAUSTED (pool_next >= P.N)
     for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        const unsigned need = __ballot_sync(0xffffffffu, !active && lane_on);
         // B200_REFILL_MIN idle lanes are collected before the (single-lane, divergent) begin path runs: fewer passes
         // through it against lanes that wait a few steps (measured)
         if (need != 0u && !B200_EXHAUSTED && (__popc(need) >= B200_REFILL_MIN || need == 0xffffffffu || (P.N - pool_next) < 64)) {
@@ -847,7 +868,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
                 // the old pool (if any) is a contiguous range that ends where this one
                 // may not begin; keep both ranges by handing out the old one first
                 long long old_left = pool_end - pool_next;
-                if (!active) {
+                if (!active && lane_on) {
                     int rank = __popc(need & lt_mask);
                     long long cand = (rank < old_left) ? (pool_next + rank) : (base + (rank - old_left));
                     if (cand < P.N) { idx = cand; active = true; b200_traj_begin(P, idx, T); }
@@ -856,7 +877,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
                 pool_end = got_end;
                 if (pool_end > P.N) pool_end = P.N > pool_next ? P.N : pool_next;
             } else {
-                if (!active) {
+                if (!active && lane_on) {
                     int rank = __popc(need & lt_mask);
                     idx = pool_next + rank; active = true;
                     b200_traj_begin(P, idx, T);

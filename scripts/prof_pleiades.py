@@ -9,7 +9,8 @@ opt = sys.argv[1] if len(sys.argv) > 1 else "-DB200_COOP=1"
 coop = "B200_COOP=1" in opt
 N = 1 << 16
 h = pkg.Handle(0)
-src = pl.pleiades_component_source() if coop else pl.pleiades_source(False, loops=True)
+wide = "B200_WIDE=1" in opt
+src = pl.pleiades_component_source() if coop else (pl.pleiades_pairs_source() if wide else pl.pleiades_source(False, loops=True))
 prog = h.compile(pkg.ALG_VERN7, pkg.F64, 28, 0, src[0], src[1], extra_options=opt)
 u0 = pl.pleiades_u0(N)
 for _ in range(2):

@@ -1,6 +1,7 @@
 """Pleiades/Vern7 (BASELINE config 4), 2^18 trajectories: the lane-group kernel at several launch shapes against the
 one-thread-per-trajectory kernel; parity of the first 512 trajectories against the oracle.
-python scripts/sweep_pleiades.py [variants...]   (a variant starting with 'T:' uses the one-thread kernel)"""
+python scripts/sweep_pleiades.py [variants...]   (a variant starting with 'T:' uses the one-thread kernel, 'W:' the
+shared-memory stage kernel with the pair-shared source, 'WP:' the same kernel with the reference's plain double loop)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -20,6 +21,10 @@ for v in variants:
     thread = v.startswith("T:")
     opt = v[2:] if thread else v
     src = pl.pleiades_source(False, loops=True) if thread else comp
+    if v.startswith("W:"):
+        opt = ("-DB200_WIDE=1 " + v[2:]).strip(); src = pl.pleiades_pairs_source(False)
+    if v.startswith("WP:"):
+        opt = ("-DB200_WIDE=1 " + v[3:]).strip(); src = pl.pleiades_source(False)
     prog = h.compile(pkg.ALG_VERN7, pkg.F64, 28, 0, src[0], src[1], extra_options=opt or None)
     best = 1e9
     for _ in range(3):

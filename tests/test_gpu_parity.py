@@ -958,6 +958,60 @@ def test_lane_group_kernel_other_shapes(pkg, handle, oracle):
         prog.close()
 
 
+@pytest.mark.parametrize("f32", [False, True])
+def test_smem_stage_kernel_pleiades_vern7(pkg, handle, oracle, f32):
+    """BASELINE config 4 through the shared-memory stage kernel (B200ODE_OPT_SMEM_STAGES, device/b200_vern7_wide.cuh):
+    the stage derivatives in shared memory, one inlined copy of the pair-shared Pleiades text compiled with the flagged
+    fast sqrt / division — bit-exact against the oracle run on the reference's plain double loop."""
+    pl = pkg.problems_library
+    N = 1500                     # more than one wave of 112 trajectories per CTA on a few CTAs, ragged tail
+    u0 = pl.pleiades_u0(N, f32=f32)
+    ref = pl.pleiades_source(f32)
+    dtype = pkg.F32 if f32 else pkg.F64
+    kw = dict(reltol=1e-4, abstol=1e-5) if f32 else dict(reltol=1e-6, abstol=1e-8)
+    for src, name in (pl.pleiades_pairs_source(f32), ref):
+        prog = handle.compile(pkg.ALG_VERN7, dtype, 28, 0, src, name, extra_options=pkg._lib.OPT_SMEM_STAGES)
+        try:
+            assert prog.info["local_bytes_integrate"] <= 512        # only the cold plain-operator copies
+            assert prog.info["smem_bytes_integrate"] > 200 * 1024
+            n_here = N if name != ref[1] else 300
+            for extra in ({}, {"saveat": [3.0], "save_start": True}, {"saveat": [3.0], "save_start": False, "save_end": False}):
+                g = pkg.lowlevel.solve_host(prog, u0[:n_here], None, (0.0, 3.0), **dict(kw, **extra))
+                o = oracle.solve(oracle.ALG_VERN7, ref, u0[:n_here], None, (0.0, 3.0), 28, 0, f32=f32, **dict(kw, **extra))
+                assert_same_result(g, o)
+                assert (g["nf"] == 2 + 10 * (g["naccept"] + g["nreject"])).all()
+            # default tolerances, and failure retcodes leave the other lanes running
+            g = pkg.lowlevel.solve_host(prog, u0[:200], None, (0.0, 3.0))
+            o = oracle.solve(oracle.ALG_VERN7, ref, u0[:200], None, (0.0, 3.0), 28, 0, f32=f32)
+            assert_same_result(g, o)
+            g = pkg.lowlevel.solve_host(prog, u0[:33], None, (0.0, 3.0), maxiters=7, **kw)
+            o = oracle.solve(oracle.ALG_VERN7, ref, u0[:33], None, (0.0, 3.0), 28, 0, f32=f32, maxiters=7, **kw)
+            assert_same_result(g, o)
+            assert (g["retcode"] == pkg._lib.RC_MAXITERS).all()
+            # interior saveat rows need the lazy stages this variant does not store: rejected loudly
+            with pytest.raises(pkg._lib.B200Error):
+                pkg.lowlevel.solve_host(prog, u0[:8], None, (0.0, 3.0), saveat=[1.0, 2.0])
+        finally:
+            prog.close()
+
+
+def test_smem_stage_kernel_small_system(pkg, handle, oracle):
+    """The same variant on a small system (Lorenz, n = 3: 512 trajectories per CTA) equals the default Vern7 kernel's
+    oracle, including a tstops-free run with user dt and dtmax."""
+    pl = pkg.problems_library
+    N = 3000
+    p = pl.lorenz_params(N)
+    src, name = pl.lorenz_source()
+    prog = handle.compile(pkg.ALG_VERN7, pkg.F64, 3, 3, src, name, extra_options=pkg._lib.OPT_SMEM_STAGES)
+    try:
+        for kw in ({}, {"reltol": 1e-9, "abstol": 1e-9}, {"dt": 0.01, "dtmax": 0.05}):
+            g = pkg.lowlevel.solve_host(prog, U0, p, (0.0, 10.0), **kw)
+            o = oracle.solve(oracle.ALG_VERN7, (src, name), U0, p, (0.0, 10.0), 3, 3, **kw)
+            assert_same_result(g, o)
+    finally:
+        prog.close()
+
+
 # ---- AutoTsit5(Rosenbrock23()): per-trajectory switching between Tsit5 and Rosenbrock23 ------------------------------
 def _vdp_mixed_params(pl, N, f32):
     """Van der Pol with mu spread over [0.5, 500]: the ensemble holds trajectories that never leave Tsit5, trajectories

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from helpers import counting_source, linear2d_source, linear_jac_sources, linear_source
+from helpers import assert_same_result, bits, counting_source, linear2d_source, linear_jac_sources, linear_source
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -881,3 +881,36 @@ def test_saving_callbacks_double_the_rows_like_the_reference():
     # every affect! counts as a modification: the FSAL derivative is re-evaluated once per accepted step
     # (reset_fsal! in the next loopheader!, so not after the last one)
     assert a["naccept"][0] == plain["naccept"][0] and a["nf"][0] == plain["nf"][0] + a["naccept"][0] - 1
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_pleiades_pair_shared_source_equals_the_reference_loop(pkg, f32):
+    """problems_library.pleiades_pairs_source (every unordered pair once, B200_DIV hints) produces the bits of the
+    reference's double loop (benchmark/benchmarks.jl:45-57, pleiades_source) — random states, clustered states, and the
+    oracle's own Vern7 solve through either text."""
+    import ctypes as C
+    pl = pkg.problems_library
+    a, an = pl.pleiades_source(f32)
+    b, bn = pl.pleiades_pairs_source(f32)
+    lib = oracle.compile_user([a, b])
+    dt = np.float32 if f32 else np.float64
+    ct = C.c_float if f32 else C.c_double
+    fa, fb = getattr(lib, an), getattr(lib, bn)
+    for f in (fa, fb):
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, ct]
+        f.restype = None
+    rng = np.random.default_rng(7)
+    for k in range(2000):
+        scale = 10.0 ** rng.uniform(-3, 1)
+        u = (rng.standard_normal(28) * scale).astype(dt)
+        if k % 5 == 0:
+            u[:14] = (u[:14] * 1e-3).astype(dt)       # near collisions: large, cancelling forces
+        da = np.zeros(28, dtype=dt); db = np.full(28, 7, dtype=dt)
+        fa(da.ctypes.data, u.ctypes.data, None, 0.0)
+        fb(db.ctypes.data, u.ctypes.data, None, 0.0)
+        assert np.array_equal(bits(da), bits(db)), k
+    u0 = pl.pleiades_u0(16, f32=f32)
+    kw = dict(reltol=1e-4, abstol=1e-5) if f32 else dict(reltol=1e-6, abstol=1e-8)
+    oa = oracle.solve(oracle.ALG_VERN7, (a, an), u0, None, (0.0, 3.0), 28, 0, f32=f32, **kw)
+    ob = oracle.solve(oracle.ALG_VERN7, (b, bn), u0, None, (0.0, 3.0), 28, 0, f32=f32, **kw)
+    assert_same_result(ob, oa)
