@@ -79,7 +79,8 @@ ALG_NAMES = {"tsit5": "ALG_TSIT5", "vern7": "ALG_VERN7", "ros23": "ALG_ROSENBROC
 
 def sources(pl, w, device=False):
     """(rhs, jac, tgrad, n, np, extra compile options).  device=True: the form the GPU program is compiled from
-    (Pleiades: component form for the lane-group kernel); otherwise the full-vector form the CPU oracle compiles."""
+    (Pleiades: the pair-shared full-vector text for the shared-memory stage kernel, bit-identical to the reference loop);
+    otherwise the plain full-vector form the CPU oracle compiles."""
     f32 = w["f32"]
     if w["problem"] in ("lorenz", "lorenz_sweep"):
         return pl.lorenz_source(f32), None, None, 3, 3, None
@@ -91,7 +92,7 @@ def sources(pl, w, device=False):
         return r, j, tg, n, np_, None
     if w["problem"] == "pleiades":
         if device:
-            return pl.pleiades_component_source(f32), None, None, 28, 0, "-DB200_COOP=1"
+            return pl.pleiades_pairs_source(f32), None, None, 28, 0, "-DB200_WIDE=1 -DB200_WIDE_WINDOW=4"
         return pl.pleiades_source(f32, loops=True), None, None, 28, 0, None
     raise ValueError(w["problem"])
 

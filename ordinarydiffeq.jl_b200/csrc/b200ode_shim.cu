@@ -494,6 +494,8 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         if (!at) opts.push_back("-DB200_WIDE_NT=" + std::to_string(nt));
         if (!has_block) { opts.push_back("-DB200_BLOCK=" + std::to_string((nt + 31) / 32 * 32)); has_block = true; }
         if (!has_minb) { opts.push_back("-DB200_MINBLOCKS=1"); has_minb = true; }
+        // software-pipelining window of the RHS's roots (device/b200_window.cuh): 3..4 measured best for Pleiades
+        if (!strstr(extra_options, "-DB200_WIDE_WINDOW=")) opts.push_back("-DB200_WIDE_WINDOW=4");
         if (dyn_smem_out) *dyn_smem_out = per_thread * (size_t)nt;
         if (wide_nt_out) *wide_nt_out = (int)nt;
     }

@@ -164,19 +164,34 @@ struct B200Vern7Wide {
 #pragma unroll
                 for (int i = 0; i < B200_N; ++i) x[i] = b200_fma(a, B200_WK(0, i), Kup[i * B200_WIDE_NT]);
             } else {
-                {
-                    const real a = W.coef[s][0];
-                    const real* Ks = Kt + W.slot[s][0] * (B200_N * B200_WIDE_NT);
-#pragma unroll
-                    for (int i = 0; i < B200_N; ++i) x[i] = a * Ks[i * B200_WIDE_NT];
-                }
+                // sum_j a_sj k_j in the reference's nesting (first product, then fmas in ascending j).  The loop over the
+                // terms is software pipelined by hand: the 28 loads of term j + 1 are issued before the 28 fmas of term j,
+                // so the shared-memory latency of a term hides behind the previous term's arithmetic (one warp per
+                // scheduler: nothing else would hide it).  Every stage has at least two terms.
                 const int nt = W.nterms[s];
-#pragma unroll 2
-                for (int j = 1; j < nt; ++j) {
-                    const real a = W.coef[s][j];
-                    const real* Ks = Kt + W.slot[s][j] * (B200_N * B200_WIDE_NT);
+                real cur[B200_N], nxt[B200_N];
+                {
+                    const real* K0 = Kt + W.slot[s][0] * (B200_N * B200_WIDE_NT);
+                    const real* K1 = Kt + W.slot[s][1] * (B200_N * B200_WIDE_NT);
 #pragma unroll
-                    for (int i = 0; i < B200_N; ++i) x[i] = b200_fma(a, Ks[i * B200_WIDE_NT], x[i]);
+                    for (int i = 0; i < B200_N; ++i) cur[i] = K0[i * B200_WIDE_NT];
+#pragma unroll
+                    for (int i = 0; i < B200_N; ++i) nxt[i] = K1[i * B200_WIDE_NT];
+                    const real a = W.coef[s][0];
+#pragma unroll
+                    for (int i = 0; i < B200_N; ++i) x[i] = a * cur[i];
+                }
+#pragma unroll 1
+                for (int j = 1; j < nt; ++j) {
+#pragma unroll
+                    for (int i = 0; i < B200_N; ++i) cur[i] = nxt[i];
+                    // (the last pass re-reads its own term: a harmless load that keeps the loop body branch-free)
+                    const real* Kn = Kt + W.slot[s][j + 1 < nt ? j + 1 : j] * (B200_N * B200_WIDE_NT);
+#pragma unroll
+                    for (int i = 0; i < B200_N; ++i) nxt[i] = Kn[i * B200_WIDE_NT];
+                    const real a = W.coef[s][j];
+#pragma unroll
+                    for (int i = 0; i < B200_N; ++i) x[i] = b200_fma(a, cur[i], x[i]);
                 }
 #pragma unroll
                 for (int i = 0; i < B200_N; ++i) x[i] = b200_fma(dt, x[i], Kup[i * B200_WIDE_NT]);

@@ -404,9 +404,11 @@ def _handle(device):
 
 
 def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True, callbacks=None,
-                vector_tol=False):
+                vector_tol=False, smem_stages=False):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
     extra = []
+    if smem_stages:
+        extra.append(_lib.OPT_SMEM_STAGES)
     if everystep:
         extra.append(_lib.OPT_EVERYSTEP)
     if tstops:
@@ -526,8 +528,13 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     for name in ("reltol", "abstol"):
         if np.ndim(kw.get(name)) > 0 and len(kw[name]) != n:
             raise ValueError("%s must be a number or a vector with one entry per component" % name)
+    # Vern7 on a wide state with nothing but start / end rows asked for: the stage derivatives do not fit a thread's
+    # registers, so the kernel that keeps them in shared memory runs (B200ODE_OPT_SMEM_STAGES; bit-identical results)
+    t0_, tf_ = float(prob.tspan[0]), float(prob.tspan[1])
+    smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 12 and not ragged and cb_specs is None
+                   and all(not (t0_ < float(g) < tf_) for g in (grid or [])))
     program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None, adaptive, cb_specs,
-                          vector_tol)
+                          vector_tol, smem_stages)
 
     def run(u0, p, ntraj, flags=0):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
