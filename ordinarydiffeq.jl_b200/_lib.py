@@ -114,6 +114,7 @@ OPT_VECTOR_TOL = "-DB200_VECTOR_TOL=1"
 OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
 OPT_COMPONENT_RHS = "-DB200_COOP=1"
 OPT_SMEM_STAGES = "-DB200_WIDE=1"
+OPT_STAGED_SAVEAT = "-DB200_STAGE_ROWS=1"
 
 
 def opt_save_idxs(idxs):

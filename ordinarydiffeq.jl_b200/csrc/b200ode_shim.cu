@@ -526,6 +526,31 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         else minb = (words <= 8) ? 4 : (words <= 16 ? 2 : 1);
         opts.push_back("-DB200_MINBLOCKS=" + std::to_string(minb));
     }
+    // Staged saveat queue (b200_stage_rows in device/b200_ensemble.cuh; B200ODE_OPT_STAGED_SAVEAT): Tsit5 programs with a
+    // rectangular output may pack their saveat rows through a per-warp shared-memory queue.  Opt-in: measured slower than
+    // the in-step loop on the headline workload.
+    {
+        const bool off = extra_options && strstr(extra_options, "-DB200_STAGE_ROWS=0");
+        const bool on_req = extra_options && strstr(extra_options, "-DB200_STAGE_ROWS=1");
+        const bool eligible = alg == B200ODE_ALG_TSIT5 && !coop && !wide && ncb == 0 && n <= 4 &&
+                              !(extra_options && (strstr(extra_options, "-DB200_EVERYSTEP=1") || strstr(extra_options, "-DB200_SAVE_IDXS=")));
+        if (on_req && !eligible) { nvrtcDestroyProgram(&prog); return fail(B200ODE_EUNSUPPORTED, "-DB200_STAGE_ROWS=1 needs Tsit5, n <= 4, no save_everystep / save_idxs / callbacks"); }
+        (void)off;
+        if (eligible && on_req) {
+            int block = 128, minb = 1;
+            for (auto& o : opts) {
+                if (o.rfind("-DB200_BLOCK=", 0) == 0) block = atoi(o.c_str() + 13);
+                if (o.rfind("-DB200_MINBLOCKS=", 0) == 0) minb = atoi(o.c_str() + 17);
+            }
+            const size_t rs = dtype == B200ODE_F32 ? 4 : 8;
+            const size_t per_warp = ((size_t)(8 * n + 2) * 56 * rs + 64 * (rs + 12) + 16 + 15) / 16 * 16;
+            const size_t bytes = per_warp * (size_t)(block / 32);
+            if (bytes * (size_t)minb <= 226 * 1024) {
+                if (!on_req) opts.push_back("-DB200_STAGE_ROWS=1");
+                if (dyn_smem_out) *dyn_smem_out = bytes;
+            } else if (on_req) { nvrtcDestroyProgram(&prog); return fail(B200ODE_EUNSUPPORTED, "-DB200_STAGE_ROWS=1: the row queues do not fit the SM's shared memory at this launch shape"); }
+        }
+    }
     std::vector<const char*> copts;
     for (auto& o : opts) copts.push_back(o.c_str());
     r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());

@@ -209,6 +209,12 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #ifndef B200_CALLBACKS
 #define B200_CALLBACKS 0      // 1: the program carries a CallbackSet (device/b200_callbacks.cuh; Tsit5)
 #endif
+#ifndef B200_STAGE_ROWS
+#define B200_STAGE_ROWS 0     // 1: saveat rows are packed through a per-warp shared-memory queue and interpolated at full lane occupancy (Tsit5)
+#endif
+#if B200_STAGE_ROWS && (B200_ALG != B200_ALG_TSIT5 || B200_EVERYSTEP || B200_CALLBACKS || defined(B200_SAVE_IDXS) || B200_COOP)
+#error "the staged saveat queue serves Tsit5 with a rectangular saveat output (no save_everystep / save_idxs / callbacks)"
+#endif
 #if defined(B200_ISOUT) && B200_COOP
 #error "isoutofdomain is not available in the lane-group kernel"
 #endif
@@ -695,6 +701,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         b200_handle_callbacks(P, idx, T);
         if (T.terminated) return true;                  // terminate! emptied the tstops
 #else
+#if !B200_STAGE_ROWS       // (staged programs interpolate in b200_stage_rows, after the step, with all lanes of the warp)
         {
             bool dense_ready = false;
             real rdt = (real)0;         // refined 1/dt, shared by the rows of this step
@@ -729,6 +736,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                 b200_emit(P, idx, T, T.t, T.u, dt_stages);
 #endif
         }
+#endif  // !B200_STAGE_ROWS
 #endif  // !B200_CALLBACKS
 #if B200_TSTOPS
         // handle_tstop! (integrator_utils.jl:1290-1314): pop every copy of a stop time that was reached;
@@ -794,6 +802,167 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
 #endif
 }
 
+
+#if B200_STAGE_ROWS
+// ---------------------------------------------------------------------------
+// savevalues! through shared memory (north_star "Output").  In the plain kernel every lane interpolates its own saveat
+// rows inside the accepting step: the `while (next_save <= t)` loop runs 1.9 passes per warp-step at 13 of 32 lanes
+// (18 lanes have one row, 4 a second, 0.6 a third), i.e. the interpolation's FP64 work is issued 2.4 times.  Here a
+// lane only DEPOSITS: once per step a snapshot of what the interpolant needs (uprev, k1..k7, dt, tprev) and per row
+// (grid time, destination, snapshot index) into a per-warp queue; whenever 32 rows are queued the whole warp —
+// including lanes that are waiting for a new trajectory — drains them, one row per lane, at full occupancy.
+// Layout per warp: snap[field][B200_SQ_SNAPS] (a deposit pass writes consecutive entries, a drain reads consecutive
+// or identical entries: conflict-free), row ring curt[64] / dest[64] / sidx[64].  Rows keep their destination, so the
+// order in which they are written does not matter; results are bit-identical to the in-step loop (same Theta sequence:
+// b200_rcp_refine + b200_div_rcp, same interpolant nesting).  Reference: _savevalues! integrator_utils.jl:340-414.
+#define B200_SQ_SNAPS 56
+#define B200_SQ_ROWS 64
+#define B200_SQ_FIELDS (8 * B200_N + 2)
+#define B200_SQ_WARP_BYTES ((B200_SQ_FIELDS * B200_SQ_SNAPS * (int)sizeof(real) + B200_SQ_ROWS * ((int)sizeof(real) + 12) + 16 + 15) / 16 * 16)
+extern __shared__ __align__(16) unsigned char b200_sq_smem[];
+// The ring positions live in the queue's own shared-memory header between calls (four ints per warp), so the step loop
+// carries no extra registers; a call loads them, works on warp-uniform copies and stores them back.
+struct B200RowQ {
+    real* snap; real* curt; unsigned long long* dest; int* sidx; int* hdr;
+    int rhead, rcount, shead, scount;     // warp-uniform
+};
+B200_D void b200_rowq_bind(B200RowQ& Q) {
+    unsigned char* base = b200_sq_smem + (size_t)(threadIdx.x >> 5) * B200_SQ_WARP_BYTES;
+    Q.snap = reinterpret_cast<real*>(base);
+    Q.dest = reinterpret_cast<unsigned long long*>(base + B200_SQ_FIELDS * B200_SQ_SNAPS * sizeof(real));
+    Q.curt = reinterpret_cast<real*>(base + B200_SQ_FIELDS * B200_SQ_SNAPS * sizeof(real) + B200_SQ_ROWS * 8);
+    Q.sidx = reinterpret_cast<int*>(base + B200_SQ_FIELDS * B200_SQ_SNAPS * sizeof(real) + B200_SQ_ROWS * (8 + sizeof(real)));
+    Q.hdr = Q.sidx + B200_SQ_ROWS;
+}
+B200_D void b200_rowq_load(B200RowQ& Q) {
+    b200_rowq_bind(Q);
+    const int4 h = *reinterpret_cast<const int4*>(Q.hdr);
+    Q.rhead = h.x; Q.rcount = h.y; Q.shead = h.z; Q.scount = h.w;
+}
+B200_D void b200_rowq_store(const B200RowQ& Q, unsigned lane) {
+    if (lane == 0) *reinterpret_cast<int4*>(Q.hdr) = make_int4(Q.rhead, Q.rcount, Q.shead, Q.scount);
+    __syncwarp();
+}
+// the oldest `nrows` (<= 32) queued rows, one per lane; every lane of the warp calls this
+#ifndef B200_SQ_NOINLINE
+#define B200_SQ_NOINLINE 0
+#endif
+#if B200_SQ_NOINLINE
+__device__ __noinline__ void b200_drain_rows(B200RowQ& Q, unsigned lane, int nrows) {
+#else
+B200_D void b200_drain_rows(B200RowQ& Q, unsigned lane, int nrows) {
+#endif
+    __syncwarp();
+    if ((int)lane < nrows) {
+        const int r = (Q.rhead + (int)lane) & (B200_SQ_ROWS - 1);
+        const real curt = Q.curt[r];
+        real* dst = reinterpret_cast<real*>(Q.dest[r]);
+        const real* S = Q.snap + Q.sidx[r];
+        const real dt = S[(8 * B200_N) * B200_SQ_SNAPS], tprev = S[(8 * B200_N + 1) * B200_SQ_SNAPS];
+        real th;
+        {   // Theta = (curt - tprev) / dt exactly as the in-step loop computes it
+            bool bad = false;
+            th = b200_div_rcp(curt - tprev, dt, b200_rcp_refine(dt), bad);
+            if (bad) th = b200_div_cold(curt - tprev, dt);
+        }
+        real b[7];
+        b200_tsit5_interp_weights(th, b);
+#pragma unroll
+        for (int i = 0; i < B200_N; ++i) {
+            real acc = S[(B200_N + i) * B200_SQ_SNAPS] * b[0];
+#pragma unroll
+            for (int j = 1; j < 7; ++j) acc = b200_fma(S[(B200_N * (j + 1) + i) * B200_SQ_SNAPS], b[j], acc);
+            dst[i] = b200_fma(dt, acc, S[i * B200_SQ_SNAPS]);
+        }
+    }
+    Q.rhead = (Q.rhead + nrows) & (B200_SQ_ROWS - 1);
+    Q.rcount -= nrows;
+    if (Q.rcount > 0) {         // snapshots older than the oldest outstanding row's are free
+        const int s0 = Q.sidx[Q.rhead];
+        int rel = s0 - Q.shead; if (rel < 0) rel += B200_SQ_SNAPS;
+        Q.shead = s0; Q.scount -= rel;
+    } else {
+        int e = Q.shead + Q.scount; if (e >= B200_SQ_SNAPS) e -= B200_SQ_SNAPS;
+        Q.shead = e; Q.scount = 0;
+    }
+    __syncwarp();
+}
+// after b200_traj_iterate, all 32 lanes: the rows of the step just accepted go into the queue
+B200_D void b200_stage_rows(const B200Params& P, long long idx, B200Traj& T, bool active, unsigned lane, unsigned lt_mask) {
+    bool pending = active && (T.next_save <= T.t);
+    if (__ballot_sync(0xffffffffu, pending) == 0u) return;
+    B200RowQ Q;
+    b200_rowq_load(Q);
+    int my_snap = -1;
+    for (;;) {
+        // room for one row and one snapshot per lane
+        while (Q.rcount > B200_SQ_ROWS - 32 || Q.scount > B200_SQ_SNAPS - 32) {
+            b200_drain_rows(Q, lane, Q.rcount < 32 ? Q.rcount : 32);
+            if (my_snap >= 0) {     // a snapshot whose rows have all been written is gone: the next row deposits it again
+                int pos = my_snap - Q.shead; if (pos < 0) pos += B200_SQ_SNAPS;
+                if (pos >= Q.scount) my_snap = -1;
+            }
+        }
+        bool store = false;
+        real curt = (real)0;
+        real* dst = nullptr;
+        if (pending) {
+            curt = T.next_save;
+            T.save_idx += 1;
+            T.next_save = (T.save_idx < P.nsaveat) ? P.saveat[T.save_idx] : b200_inf();
+            if (curt != T.t) {
+                store = (T.nsaved < P.nslots);
+                dst = T.row;
+                if (store) T.row += B200_N;
+                T.nsaved += 1;
+            } else if (!(curt == P.tf && !P.save_end)) {     // skip_saveat_at_tspan_end
+                b200_emit(P, idx, T, T.t, T.u);
+            }
+        }
+        const bool need_snap = store && my_snap < 0;
+        const unsigned nm = __ballot_sync(0xffffffffu, need_snap);
+        if (need_snap) {
+            int sidx = Q.shead + Q.scount + __popc(nm & lt_mask);
+            if (sidx >= B200_SQ_SNAPS) sidx -= B200_SQ_SNAPS;
+            if (sidx >= B200_SQ_SNAPS) sidx -= B200_SQ_SNAPS;
+            my_snap = sidx;
+            real* S = Q.snap + sidx;
+#pragma unroll
+            for (int i = 0; i < B200_N; ++i) {
+                S[i * B200_SQ_SNAPS] = T.uprev[i];
+                S[(B200_N + i) * B200_SQ_SNAPS] = T.st.k1[i];
+                S[(2 * B200_N + i) * B200_SQ_SNAPS] = T.st.k2[i];
+                S[(3 * B200_N + i) * B200_SQ_SNAPS] = T.st.k3[i];
+                S[(4 * B200_N + i) * B200_SQ_SNAPS] = T.st.k4[i];
+                S[(5 * B200_N + i) * B200_SQ_SNAPS] = T.st.k5[i];
+                S[(6 * B200_N + i) * B200_SQ_SNAPS] = T.st.k6[i];
+                S[(7 * B200_N + i) * B200_SQ_SNAPS] = T.st.k7[i];
+            }
+            S[(8 * B200_N) * B200_SQ_SNAPS] = T.dt;
+            S[(8 * B200_N + 1) * B200_SQ_SNAPS] = T.tprev;
+        }
+        Q.scount += __popc(nm);
+        const unsigned sm = __ballot_sync(0xffffffffu, store);
+        if (store) {
+            const int r = (Q.rhead + Q.rcount + __popc(sm & lt_mask)) & (B200_SQ_ROWS - 1);
+            Q.curt[r] = curt;
+            Q.dest[r] = reinterpret_cast<unsigned long long>(dst);
+            Q.sidx[r] = my_snap;
+        }
+        Q.rcount += __popc(sm);
+        pending = pending && (T.next_save <= T.t);
+        if (__ballot_sync(0xffffffffu, pending) == 0u) break;
+    }
+    b200_rowq_store(Q, lane);
+}
+// the end of the kernel: whatever is still queued
+B200_D void b200_flush_rows(unsigned lane) {
+    B200RowQ Q;
+    b200_rowq_load(Q);
+    while (Q.rcount > 0) b200_drain_rows(Q, lane, Q.rcount < 32 ? Q.rcount : 32);
+    b200_rowq_store(Q, lane);
+}
+#endif  // B200_STAGE_ROWS
 #ifndef B200_BLOCK
 #define B200_BLOCK 128
 #endif
@@ -811,6 +980,14 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
     B200Traj T;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
+#if B200_STAGE_ROWS
+    {   // empty queue
+        B200RowQ Q;
+        b200_rowq_bind(Q);
+        Q.rhead = 0; Q.rcount = 0; Q.shead = 0; Q.scount = 0;
+        b200_rowq_store(Q, lane);
+    }
+#endif
 #if B200_WIDE
     // only the first B200_WIDE_NT threads of the CTA have a shared-memory column: the others never take a trajectory
     const bool lane_on = threadIdx.x < B200_WIDE_NT;
@@ -830,8 +1007,16 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
         for (;;) {
             const unsigned am = __ballot_sync(0xffffffffu, live);
             if (am == 0u) break;
-            if (live && b200_traj_iterate(P, idx, T, am)) { b200_traj_end(P, idx, T); live = false; }
+            bool fin = false;
+            if (live) fin = b200_traj_iterate(P, idx, T, am);
+#if B200_STAGE_ROWS
+            b200_stage_rows(P, idx, T, live, lane, lt_mask);
+#endif
+            if (live && fin) { b200_traj_end(P, idx, T); live = false; }
         }
+#if B200_STAGE_ROWS
+        b200_flush_rows(lane);
+#endif
         return;
     }
 
@@ -892,13 +1077,19 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
             if (B200_EXHAUSTED || need == 0u) break;
             continue;
         }
-        if (active) {
-            if (b200_traj_iterate(P, idx, T, am)) {
-                b200_traj_end(P, idx, T);
-                active = false;
-            }
+        bool fin = false;
+        if (active) fin = b200_traj_iterate(P, idx, T, am);
+#if B200_STAGE_ROWS
+        b200_stage_rows(P, idx, T, active, lane, lt_mask);
+#endif
+        if (active && fin) {
+            b200_traj_end(P, idx, T);
+            active = false;
         }
     }
+#if B200_STAGE_ROWS
+    b200_flush_rows(lane);
+#endif
 }
 // (rows restricted by save_idxs cannot restart a step; Rosenbrock32's fsalfirst is f(uprev + dt k2) of the previous
 // step, not f of the saved row, so its stages are not recomputable from (row, dt) either)

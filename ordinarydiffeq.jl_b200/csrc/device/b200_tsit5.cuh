@@ -41,6 +41,26 @@ __constant__ B200Tsit5Coeffs B200_TSIT5_C = {
     (real)1.5, (real)-4.0, (real)2.5,
 };
 
+
+// the seven interpolation weights b_j(Theta) of _ode_interpolant(..., ::Tsit5ConstantCache, ..., Val{0}) — the same
+// expressions as B200Tsit5::interp below (used by the staged saveat queue, which reads the stages from shared memory)
+B200_D void b200_tsit5_interp_weights(real th, real* b) {
+#define B200_T5(name) const real name = B200_TSIT5_C.name
+    B200_T5(r11); B200_T5(r12); B200_T5(r13); B200_T5(r14); B200_T5(r22); B200_T5(r23); B200_T5(r24);
+    B200_T5(r32); B200_T5(r33); B200_T5(r34); B200_T5(r42); B200_T5(r43); B200_T5(r44);
+    B200_T5(r52); B200_T5(r53); B200_T5(r54); B200_T5(r62); B200_T5(r63); B200_T5(r64);
+    B200_T5(r72); B200_T5(r73); B200_T5(r74);
+#undef B200_T5
+    const real th2 = th * th;
+    b[0] = th * b200_fma(th, b200_fma(th, b200_fma(th, r14, r13), r12), r11);
+    b[1] = th2 * b200_fma(th, b200_fma(th, r24, r23), r22);
+    b[2] = th2 * b200_fma(th, b200_fma(th, r34, r33), r32);
+    b[3] = th2 * b200_fma(th, b200_fma(th, r44, r43), r42);
+    b[4] = th2 * b200_fma(th, b200_fma(th, r54, r53), r52);
+    b[5] = th2 * b200_fma(th, b200_fma(th, r64, r63), r62);
+    b[6] = th2 * b200_fma(th, b200_fma(th, r74, r73), r72);
+}
+
 struct B200Tsit5 {
     real k1[B200_N], k2[B200_N], k3[B200_N], k4[B200_N], k5[B200_N], k6[B200_N], k7[B200_N];
 

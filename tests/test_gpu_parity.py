@@ -1012,6 +1012,37 @@ def test_smem_stage_kernel_small_system(pkg, handle, oracle):
         prog.close()
 
 
+@pytest.mark.parametrize("f32", [False, True])
+def test_staged_saveat_queue_equals_in_step_interpolation(pkg, handle, oracle, f32):
+    """B200ODE_OPT_STAGED_SAVEAT: saveat rows packed through the per-warp shared-memory queue (snapshot + row entries,
+    drained 32 rows at a time by the whole warp) are the oracle's rows bit for bit — the headline grid, a fine grid with
+    many rows per step (queue overflow inside one step), grid points that coincide with step ends, a truncated tail of
+    failed trajectories, and both schedules."""
+    pl = pkg.problems_library
+    N = 4000
+    p = pl.lorenz_params(N, f32=f32)
+    src, name = pl.lorenz_source(f32)
+    dtype = pkg.F32 if f32 else pkg.F64
+    u0 = U0.astype(np.float32) if f32 else U0
+    prog = handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, src, name, extra_options=pkg._lib.OPT_STAGED_SAVEAT)
+    try:
+        assert prog.info["smem_bytes_integrate"] > 40 * 1024
+        cases = [dict(saveat=[0.1 * k for k in range(1, 101)]),
+                 dict(saveat=[0.005 * k for k in range(1, 401)], save_start=False),          # ~20 rows per step
+                 dict(saveat=[0.37, 0.371, 0.372, 1.0, 2.0], save_end=False),
+                 dict(saveat=[0.5 * k for k in range(1, 21)], maxiters=40),                  # failed trajectories: zero tail
+                 dict(saveat=[0.25 * k for k in range(1, 41)], flags=pkg._lib.FLAG_STATIC_SCHEDULE),
+                 dict()]
+        for kw in cases:
+            g = pkg.lowlevel.solve_host(prog, u0, p, (0.0, 2.0 if len(kw.get("saveat", [])) == 400 else 10.0), **kw)
+            kwo = {k: v for k, v in kw.items() if k != "flags"}
+            o = oracle.solve(oracle.ALG_TSIT5, (src, name), u0, p, (0.0, 2.0 if len(kw.get("saveat", [])) == 400 else 10.0), 3, 3,
+                             f32=f32, **kwo)
+            assert_same_result(g, o)
+    finally:
+        prog.close()
+
+
 # ---- AutoTsit5(Rosenbrock23()): per-trajectory switching between Tsit5 and Rosenbrock23 ------------------------------
 def _vdp_mixed_params(pl, N, f32):
     """Van der Pol with mu spread over [0.5, 500]: the ensemble holds trajectories that never leave Tsit5, trajectories
