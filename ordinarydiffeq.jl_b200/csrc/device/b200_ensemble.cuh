@@ -877,10 +877,21 @@ B200_D void b200_drain_rows(B200RowQ& Q, unsigned lane, int nrows) {
     }
     Q.rhead = (Q.rhead + nrows) & (B200_SQ_ROWS - 1);
     Q.rcount -= nrows;
-    if (Q.rcount > 0) {         // snapshots older than the oldest outstanding row's are free
-        const int s0 = Q.sidx[Q.rhead];
-        int rel = s0 - Q.shead; if (rel < 0) rel += B200_SQ_SNAPS;
-        Q.shead = s0; Q.scount -= rel;
+    if (Q.rcount > 0) {
+        // snapshots older than every outstanding row's are free.  (Not simply "older than the oldest row's": the second
+        // row of a step is queued after the first rows of its neighbours and refers to an older snapshot than they do.)
+        int d = B200_SQ_SNAPS;
+#pragma unroll
+        for (int j = 0; j < B200_SQ_ROWS; j += 32) {
+            if (j + (int)lane < Q.rcount) {
+                int e = Q.sidx[(Q.rhead + j + (int)lane) & (B200_SQ_ROWS - 1)] - Q.shead;
+                if (e < 0) e += B200_SQ_SNAPS;
+                d = e < d ? e : d;
+            }
+        }
+        const int rel = __reduce_min_sync(0xffffffffu, d);
+        int h = Q.shead + rel; if (h >= B200_SQ_SNAPS) h -= B200_SQ_SNAPS;
+        Q.shead = h; Q.scount -= rel;
     } else {
         int e = Q.shead + Q.scount; if (e >= B200_SQ_SNAPS) e -= B200_SQ_SNAPS;
         Q.shead = e; Q.scount = 0;

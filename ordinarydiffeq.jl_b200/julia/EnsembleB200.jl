@@ -366,6 +366,13 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     rtv = rtol isa AbstractVector ? collect(Float64, rtol) : Float64[]
     atv = atol isa AbstractVector ? collect(Float64, atol) : Float64[]
     (isempty(rtv) && isempty(atv)) || push!(extra, "-DB200_VECTOR_TOL=1")
+    # Vern7 on a wide state with nothing but start / end rows: the kernel that keeps k1..k10 in shared memory
+    # (B200ODE_OPT_SMEM_STAGES; bit-identical results, it serves no interior saveat rows and no callbacks)
+    if alg isa Vern7 && n >= 12 && !everystep && isempty(cbs)
+        t0w, tfw = prob.tspan
+        grid_pts = saveat isa Number ? (saveat > 0 && saveat < abs(tfw - t0w) ? (1,) : ()) : filter(t -> t0w < t < tfw, collect(saveat))
+        isempty(grid_pts) && push!(extra, "-DB200_WIDE=1")
+    end
     h = handle(ens)
     prog, multi = program(ens, h, alg, T, n, np, rhs, jac, tgr, join(extra, " "), cbs)
     # defaults of solve.jl:141-143,596-599 (the C ABI only sees the expanded grid)
