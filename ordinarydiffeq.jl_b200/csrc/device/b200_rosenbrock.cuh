@@ -55,17 +55,23 @@ struct B200WFact {
         y0[1] = x1[2] * x2[0] - x1[0] * x2[2];
         y0[2] = x1[0] * x2[1] - x1[1] * x2[0];
         const real d = (x0[0] * y0[0] + x0[1] * y0[1]) + x0[2] * y0[2];
-        // six quotients by the same d: one correctly rounded reciprocal + the exact residual
-        // correction each (b200_div_const; bit-identical to IEEE x / d), true division when d is
-        // outside the safe exponent window (singular or badly scaled W)
-        const real ad = b200_abs(d);
-        if (ad >= (real)1e-30 && ad <= (real)1e30) {
-            const real rd = (real)1 / d;
+        // six quotients by the same d: one correctly rounded reciprocal + the exact residual correction each
+        // (b200_div_const_fast; bit-identical to IEEE x / d).  The reciprocal is the flagged branch-free sequence, the
+        // exponent tests of the six dividends and the window test of d OR into the same flag, and ONE cold block redoes
+        // all seven with the plain operator (singular or badly scaled W) — seven branches of r1's form become one.
+        {
+            const real ad = b200_abs(d);
+            bool bad = !(ad >= (real)1e-30 && ad <= (real)1e30);
+            const real rd = b200_div_fast((real)1, d, bad);
+            real qx[3], qy[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { x0[i] = b200_div_const(x0[i], d, rd); y0[i] = b200_div_const(y0[i], d, rd); }
-        } else {
+            for (int i = 0; i < 3; ++i) { qx[i] = b200_div_const_fast(x0[i], d, rd, bad); qy[i] = b200_div_const_fast(y0[i], d, rd, bad); }
+            if (bad) {      // (unrolled: a rolled loop would index the register arrays dynamically)
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { x0[i] = x0[i] / d; y0[i] = y0[i] / d; }
+                for (int i = 0; i < 3; ++i) { qx[i] = b200_div_cold(x0[i], d); qy[i] = b200_div_cold(y0[i], d); }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { x0[i] = qx[i]; y0[i] = qy[i]; }
         }
         y1[0] = x2[1] * x0[2] - x2[2] * x0[1];
         y1[1] = x2[2] * x0[0] - x2[0] * x0[2];
@@ -134,8 +140,9 @@ struct B200WFact {
 // J, dT at (uprev, t); W = J - I * inv(dtgamma)
 // opnorm_out (composite algorithms only): receives opnorm(J, Inf) = the largest row sum of |J| (rows summed left to right),
 // which calc_W stores in integrator.eigen_est when the algorithm is a CompositeAlgorithm (derivative_utils.jl:996-999)
+// lam_in: inv(dtgamma) when the caller has it already (Rosenbrock23 needs the same quotient for its stages)
 B200_D void b200_build_W(const real* uprev, const real* p, real t, real dtgamma, real* dT, B200WFact& F,
-                         int& njacs, int& nw, real* opnorm_out = nullptr) {
+                         int& njacs, int& nw, real* opnorm_out = nullptr, const real* lam_in = nullptr) {
     real J[B200_N * B200_N];
     B200_JAC(J, uprev, p, t);
     if (opnorm_out != nullptr) {
@@ -157,7 +164,13 @@ B200_D void b200_build_W(const real* uprev, const real* p, real t, real dtgamma,
 #endif
     njacs += 2;
     nw += 1;
-    const real lam = (real)1 / dtgamma;
+    real lam;
+    if (lam_in != nullptr) lam = *lam_in;
+    else {   // inv(dtgamma): flagged branch-free IEEE quotient, the plain operator in the (cold) flagged case
+        bool bad = false;
+        lam = b200_div_fast((real)1, dtgamma, bad);
+        if (bad) lam = b200_div_cold((real)1, dtgamma);
+    }
 #pragma unroll
     for (int i = 0; i < B200_N; ++i) J[i + B200_N * i] = J[i + B200_N * i] - lam;
     F.factor(J);
@@ -190,12 +203,19 @@ struct B200Ros23 {
         const real d = (real)0.2928932188134525;       // convert(T, 1/(2+sqrt(2)))
         const real c32 = (real)7.414213562373095;      // convert(T, 6+sqrt(2))
         const real dtg = dt * d;
-        const real ninv = -((real)1 / dtg);
+        // -inv(dtγ), dt/2, dt/6: the two true quotients as one flagged group (dt/6 through the correctly rounded 1/6)
+        real lam, dto6;
+        {
+            bool bad = false;
+            lam = b200_div_fast((real)1, dtg, bad);
+            dto6 = b200_div_const_fast(dt, (real)6, (real)1 / (real)6, bad);
+            if (bad) { lam = b200_div_cold((real)1, dtg); dto6 = b200_div_cold(dt, (real)6); }
+        }
+        const real ninv = -lam;
         const real dto2 = dt / (real)2;
-        const real dto6 = dt / (real)6;
         real dT[B200_N], rhs[B200_N], tmp[B200_N], f1[B200_N], k3[B200_N];
         B200WFact F;
-        b200_build_W(uprev, p, t, dtg, dT, F, njacs, nw, opnorm_out);
+        b200_build_W(uprev, p, t, dtg, dT, F, njacs, nw, opnorm_out, &lam);
         if (!F.ok) return (real)2;
 #if B200_ROS_THIRD
 #pragma unroll
@@ -368,20 +388,13 @@ struct B200Rodas5P {
 
     B200_D void init(const real*, const real*, real, int&) {}    // not FSAL (alg_utils.jl:60)
 
-    B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt, real reltol, real abstol,
-                        int& nf, int& njacs, int& nw, int& nsolve, bool calck) {
+    // the S stages of one attempt (rosenbrock_perform_step.jl:431-559, RodasTableau form).  EXACT: dtC entries by the
+    // plain division (dt outside the window in which the reciprocal form is the IEEE quotient)
+    template <bool EXACT>
+    B200_D void stages(const real* uprev, const real* p, real t, real dt, real rdt, const real* dT, const B200WFact& F,
+                       real (*ks)[B200_N], int& nf, int& nsolve) {
         const B200Rodas5PCoeffs& T = B200_RODAS5P_TAB;
-        const real dtgamma = dt * T.gamma;
-        real dT[B200_N], du[B200_N], lt[B200_N], us[B200_N];
-        real ks[B200_RODAS_S][B200_N];
-        B200WFact F;
-        b200_build_W(uprev, p, t, dtgamma, dT, F, njacs, nw);
-        if (!F.ok) return (real)2;
-        // dtC = C ./ dt : all quotients share the divisor, so one correctly rounded
-        // reciprocal + the exact residual correction gives each correctly rounded quotient
-        // (same bits as IEEE division; see b200_div_const).
-        const real rdt = (real)1 / dt;
-        const bool fast_div = (b200_abs(dt) >= (real)1e-30 && b200_abs(dt) <= (real)1e30);
+        real du[B200_N], lt[B200_N], us[B200_N];
         B200_RHS(du, uprev, p, t);
         nf += 1;
 #pragma unroll
@@ -404,11 +417,11 @@ struct B200Rodas5P {
 #pragma unroll
             for (int j = 0; j < s; ++j) {
                 real q;
-                if (fast_div) {
+                if (EXACT) q = b200_div_cold(T.C[s][j], dt);
+                else {
                     const real q0 = T.C[s][j] * rdt;
-                    const real r = b200_fma(-dt, q0, T.C[s][j]);
-                    q = b200_fma(r, rdt, q0);
-                } else q = T.C[s][j] / dt;
+                    q = b200_fma(b200_fma(-dt, q0, T.C[s][j]), rdt, q0);
+                }
 #pragma unroll
                 for (int i = 0; i < B200_N; ++i) lt[i] = b200_fma(q, ks[j][i], lt[i]);
             }
@@ -418,6 +431,26 @@ struct B200Rodas5P {
             F.solve(lt, ks[s]);
             nsolve += 1;
         }
+    }
+
+    B200_D real attempt(const real* uprev, real* u, const real* p, real t, real dt, real reltol, real abstol,
+                        int& nf, int& njacs, int& nw, int& nsolve, bool calck) {
+        const B200Rodas5PCoeffs& T = B200_RODAS5P_TAB;
+        const real dtgamma = dt * T.gamma;
+        real dT[B200_N], du[B200_N], lt[B200_N], us[B200_N];
+        real ks[B200_RODAS_S][B200_N];
+        B200WFact F;
+        b200_build_W(uprev, p, t, dtgamma, dT, F, njacs, nw);
+        if (!F.ok) return (real)2;
+        // dtC = C ./ dt : all quotients share the divisor, so one correctly rounded reciprocal + the exact residual
+        // correction gives each correctly rounded quotient (same bits as IEEE division; see b200_div_const).  The
+        // reciprocal is the flagged branch-free sequence; its flag and the window test of dt are taken ONCE, and the
+        // (cold) flagged case runs a second copy of the stage loop that divides with the plain operator — r1 tested the
+        // window inside every unrolled (s, j) term, 28 branches per attempt.
+        bool bad = !(b200_abs(dt) >= (real)1e-30 && b200_abs(dt) <= (real)1e30);
+        const real rdt = b200_div_fast((real)1, dt, bad);
+        if (bad) stages<true>(uprev, p, t, dt, rdt, dT, F, ks, nf, nsolve);
+        else stages<false>(uprev, p, t, dt, rdt, dT, F, ks, nf, nsolve);
 #pragma unroll
         for (int i = 0; i < B200_N; ++i) u[i] = uprev[i];
 #pragma unroll
