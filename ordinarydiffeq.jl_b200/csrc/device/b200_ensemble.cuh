@@ -840,6 +840,7 @@ B200_D void b200_rowq_load(B200RowQ& Q) {
     Q.rhead = h.x; Q.rcount = h.y; Q.shead = h.z; Q.scount = h.w;
 }
 B200_D void b200_rowq_store(const B200RowQ& Q, unsigned lane) {
+    __syncwarp();       // every lane has read the header (b200_rowq_load) before lane 0 overwrites it
     if (lane == 0) *reinterpret_cast<int4*>(Q.hdr) = make_int4(Q.rhead, Q.rcount, Q.shead, Q.scount);
     __syncwarp();
 }

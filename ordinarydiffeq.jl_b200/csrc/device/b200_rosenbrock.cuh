@@ -56,7 +56,7 @@ struct B200WFact {
         y0[2] = x1[0] * x2[1] - x1[1] * x2[0];
         const real d = (x0[0] * y0[0] + x0[1] * y0[1]) + x0[2] * y0[2];
         // six quotients by the same d: one correctly rounded reciprocal + the exact residual correction each
-        // (b200_div_const_fast; bit-identical to IEEE x / d).  The reciprocal is the flagged branch-free sequence, the
+        // (b200_div_const_fast0: zero dividends — structural zeros of J — are exact too; bit-identical to IEEE x / d).  The reciprocal is the flagged branch-free sequence, the
         // exponent tests of the six dividends and the window test of d OR into the same flag, and ONE cold block redoes
         // all seven with the plain operator (singular or badly scaled W) — seven branches of r1's form become one.
         {
@@ -65,7 +65,7 @@ struct B200WFact {
             const real rd = b200_div_fast((real)1, d, bad);
             real qx[3], qy[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { qx[i] = b200_div_const_fast(x0[i], d, rd, bad); qy[i] = b200_div_const_fast(y0[i], d, rd, bad); }
+            for (int i = 0; i < 3; ++i) { qx[i] = b200_div_const_fast0(x0[i], d, rd, bad); qy[i] = b200_div_const_fast0(y0[i], d, rd, bad); }
             if (bad) {      // (unrolled: a rolled loop would index the register arrays dynamically)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { qx[i] = b200_div_cold(x0[i], d); qy[i] = b200_div_cold(y0[i], d); }
