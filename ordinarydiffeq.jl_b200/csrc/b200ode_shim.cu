@@ -514,6 +514,14 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         else { opts.push_back("-DB200_BLOCK=512"); opts.push_back("-DB200_MINBLOCKS=1"); }
         has_block = has_minb = true;
     }
+    // Rosenbrock-type steppers on small FP64 systems: one 512-thread CTA per SM at 128 registers, no spills (measured after
+    // the divisions were regrouped, scripts/sweep_rober.py, 2^20 Robertson trajectories: Rodas5P 7.84 ms against 8.03 ms at
+    // four 128-thread CTAs; Rosenbrock23 7.68 ms against 8.34 ms at five)
+    if (stiff && !coop && alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 && dtype == B200ODE_F64 && words <= 8 && real_cbs == 0 &&
+        !has_block && !has_minb) {
+        opts.push_back("-DB200_BLOCK=512"); opts.push_back("-DB200_MINBLOCKS=1");
+        has_block = has_minb = true;
+    }
     if (coop && !has_minb) { opts.push_back("-DB200_MINBLOCKS=4"); has_minb = true; }
     if (!has_block) opts.push_back("-DB200_BLOCK=128");
     if (!has_minb) {
