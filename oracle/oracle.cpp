@@ -61,6 +61,11 @@ template <typename R> static R jl_eps(R x) {
     return Bits<R>::from(Bits<R>::to(ax) + 1) - ax;
 }
 template <typename R> static R jl_nextfloat(R x) { return Bits<R>::from(Bits<R>::to(x) + 1); }  // x >= 0 finite
+// nextfloat(x) for a finite x of either sign (shift_past_discontinuity!, integrator_utils.jl:1188-1196, forward time)
+template <typename R> static R jl_nextfloat_signed(R x) {
+    if (x == (R)0) return Bits<R>::from(1);
+    return x > (R)0 ? Bits<R>::from(Bits<R>::to(x) + 1) : Bits<R>::from(Bits<R>::to(x) - 1);
+}
 // Base.max/min propagate NaN
 template <typename R> static R jl_max(R a, R b) { return std::isnan(a) ? a : (std::isnan(b) ? b : (a > b ? a : b)); }
 template <typename R> static R jl_min(R a, R b) { return std::isnan(a) ? a : (std::isnan(b) ? b : (a < b ? a : b)); }
@@ -218,6 +223,8 @@ template <typename R> struct Opts {
     bool save_everystep = false;   // solve.jl:138 (default isempty(saveat)); ragged rows, see Out::row_offsets
     // opts.tstops as initialize_tstops builds it (solve.jl:1021-1040): ascending, inside (t0, tf), tf last; NULL: {tf}
     const R* tstops = nullptr; int ntstops = 0;
+    // opts.d_discontinuities as reinit_d_discontinuities! builds it (solve.jl:1185-1197): entries >= t0, ascending
+    const R* disc = nullptr; int ndisc = 0;
     bool adaptive = true;          // false: fixed dt = opts.dt (dtcache), every step accepted
     // callbacks (CallbackSet: continuous callbacks first, then discrete ones, each group in the order given)
     const struct OracleCallback* cbs = nullptr; int ncb = 0;
@@ -530,6 +537,15 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
         stats.nf += 2;
     } else dt = o.dt;
     R dtpropose = dt;
+    // handle_starting_time_discontinuity! (solve.jl:872-901), the last act of init: a discontinuity at exactly t0 is popped,
+    // t moves one ulp into the span and a first-same-as-last stepper re-evaluates its first stage there (reset_fsal!)
+    int disc_idx = 0;
+    if (o.ndisc > 0 && o.disc[0] == t) {
+        disc_idx = 1;
+        t = jl_nextfloat_signed(t);
+        if constexpr (IsComposite<Alg>::value) cache.reset_fsal(u, p, t, stats);
+        else if (Alg::fsal_init()) cache.initialize(u, p, t, stats);
+    }
     // PIControllerCache (controllers.jl:793-803) and PIController defaults (alg_utils.jl)
     // beta2_default = 2//(5 order), beta1_default = 7//(10 order) (alg_utils.jl:766,788) unless the algorithm
     // overrides them (DP5); QT(rational) = correctly rounded quotient
@@ -759,7 +775,14 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 // update_fsal! (:215-239): reeval_fsal / derivative_discontinuity => reset_fsal!
                 // (for every FSAL stepper initialize! IS "fsalfirst = f(u, p, t); nf += 1"; steppers that are not FSAL have
                 //  nothing to refresh; the composite algorithm re-evaluates in its current branch)
-                if (reeval_fsal) {
+                // first branch (:216-220): has_discontinuity && first_discontinuity == t => pop it, shift t one ulp past
+                // it, reset_fsal! for a first-same-as-last stepper
+                if (disc_idx < o.ndisc && o.disc[disc_idx] == t) {
+                    disc_idx += 1;
+                    t = jl_nextfloat_signed(t);
+                    if constexpr (IsComposite<Alg>::value) cache.reset_fsal(u, p, t, stats);
+                    else if (Alg::fsal_init()) cache.initialize(u, p, t, stats);
+                } else if (reeval_fsal) {
                     if constexpr (IsComposite<Alg>::value) cache.reset_fsal(u, p, t, stats);
                     else if (Alg::fsal_init()) cache.initialize(u, p, t, stats);
                 } else cache.update_fsal();
@@ -939,6 +962,7 @@ struct OracleArgs {
     int fixed_dt;                           // 1: adaptive = false
     const OracleCallback* cbs; int ncb;     // the CallbackSet (Tsit5 only)
     const double* abstol_v; const double* reltol_v;    // per-component tolerances (n entries each) or NULL
+    const double* disc; int ndisc;          // the d_discontinuities keyword, unfiltered
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -977,15 +1001,24 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         }
     }
     if (!o.adaptive && a.dt == 0.0 && !(a.tstops && a.ntstops > 0)) return -4;     // solve.jl:277-280
-    std::vector<R> stops;
-    if (a.tstops && a.ntstops > 0) {
-        for (int i = 0; i < a.ntstops; ++i) {
+    std::vector<R> stops, discs;
+    if ((a.tstops && a.ntstops > 0) || (a.disc && a.ndisc > 0)) {
+        for (int i = 0; a.tstops && i < a.ntstops; ++i) {
             R v = (R)a.tstops[i];
             if (v > (R)a.t0 && v < (R)a.tf) stops.push_back(v);
         }
+        // d_discontinuities: the ones inside (t0, tf) are stops too (initialize_tstops, solve.jl:1033-1036); the heap of
+        // discontinuities keeps every entry >= t0 (reinit_d_discontinuities!, solve.jl:1185-1197)
+        for (int i = 0; a.disc && i < a.ndisc; ++i) {
+            R v = (R)a.disc[i];
+            if (v > (R)a.t0 && v < (R)a.tf) stops.push_back(v);
+            if (v >= (R)a.t0) discs.push_back(v);
+        }
         std::sort(stops.begin(), stops.end());
+        std::sort(discs.begin(), discs.end());
         stops.push_back((R)a.tf);
         o.tstops = stops.data(); o.ntstops = (int)stops.size();
+        o.disc = discs.data(); o.ndisc = (int)discs.size();
     }
     Out<R> out;
     out.row_offsets = a.row_offsets; out.ts_rag = (R*)a.ts_rag;

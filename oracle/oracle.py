@@ -50,7 +50,8 @@ class OracleArgs(C.Structure):
                 ("save_everystep", C.c_int), ("row_offsets", C.c_void_p), ("ts_rag", C.c_void_p),
                 ("save_idxs", C.c_void_p), ("nsave_idxs", C.c_int),
                 ("tstops", C.c_void_p), ("ntstops", C.c_int), ("fixed_dt", C.c_int),
-                ("cbs", C.c_void_p), ("ncb", C.c_int), ("abstol_v", C.c_void_p), ("reltol_v", C.c_void_p)]
+                ("cbs", C.c_void_p), ("ncb", C.c_int), ("abstol_v", C.c_void_p), ("reltol_v", C.c_void_p),
+                ("disc", C.c_void_p), ("ndisc", C.c_int)]
 
 
 class OracleCallback(C.Structure):
@@ -168,7 +169,7 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
 def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
           abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
           linsolve=0, nthreads=0, save_everystep=False, dense_tq=None, save_idxs=None, tstops=None, adaptive=True,
-          callbacks=None, ragged_saveat=False):
+          callbacks=None, ragged_saveat=False, d_discontinuities=None):
     """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host.
     save_everystep=True returns ragged rows (row_offsets, ts, us[total, n]) like lowlevel.solve_host_everystep."""
     L = lib()
@@ -228,6 +229,10 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     if tstops is not None and len(tstops) > 0:
         stops = np.ascontiguousarray(tstops, dtype=np.float64)
         a.tstops = stops.ctypes.data; a.ntstops = len(stops)
+    discs = None
+    if d_discontinuities is not None and len(d_discontinuities) > 0:
+        discs = np.ascontiguousarray(d_discontinuities, dtype=np.float64)
+        a.disc = discs.ctypes.data; a.ndisc = len(discs)
     a.u_final = out["u_final"].ctypes.data; a.t_final = out["t_final"].ctypes.data
     a.us = out["us"].ctypes.data if out["us"] is not None else None
     a.nslots = nslots

@@ -40,7 +40,8 @@ class B200Opts(C.Structure):
                 ("nsaveat", C.c_int32), ("save_start", C.c_int32), ("save_end", C.c_int32),
                 ("flags", C.c_int32), ("reserved", C.c_int32),
                 ("tstops", C.POINTER(C.c_double)), ("ntstops", C.c_int32), ("reserved2", C.c_int32),
-                ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double))]
+                ("abstol_vec", C.POINTER(C.c_double)), ("reltol_vec", C.POINTER(C.c_double)),
+                ("d_discontinuities", C.POINTER(C.c_double)), ("nd_discontinuities", C.c_int32), ("reserved3", C.c_int32)]
 
 
 class B200Result(C.Structure):
@@ -363,7 +364,7 @@ class MultiProgram:
 
 
 def make_opts(reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None,
-              save_start=None, save_end=None, flags=0, tstops=None):
+              save_start=None, save_end=None, flags=0, tstops=None, d_discontinuities=None):
     """Returns (B200Opts, keepalive)."""
     import numpy as np
     o = B200Opts()
@@ -399,4 +400,12 @@ def make_opts(reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiter
     else:
         o.tstops = None
         o.ntstops = 0
+    if d_discontinuities is not None and len(d_discontinuities) > 0:
+        keep_d = np.ascontiguousarray(d_discontinuities, dtype=np.float64)
+        o.d_discontinuities = keep_d.ctypes.data_as(C.POINTER(C.c_double))
+        o.nd_discontinuities = int(keep_d.shape[0])
+        keep = (keep, keep_d)
+    else:
+        o.d_discontinuities = None
+        o.nd_discontinuities = 0
     return o, (keep, keep_tol)

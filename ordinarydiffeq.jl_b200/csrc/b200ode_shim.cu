@@ -75,6 +75,7 @@ struct Params {
     const R* tstops;
     int ntstops;
     R fpe0, rfpe0;
+    const R* disc; int ndisc;
 };
 
 struct DevBuf {
@@ -859,7 +860,11 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     P.row_offsets = row_offsets; P.ts_rag = (R*)ts_rag; P.dts_rag = (R*)dts_rag;
     P.tstops = nullptr; P.ntstops = 0;
     const bool want_tstops = o->tstops && o->ntstops > 0;
+    const bool want_disc = o->d_discontinuities && o->nd_discontinuities > 0;
+    P.disc = nullptr; P.ndisc = 0;
     if (want_tstops && !prog->tstops) return fail(B200ODE_EINVAL, "opts.tstops needs a program compiled with -DB200_TSTOPS=1");
+    if (want_disc && !prog->tstops) return fail(B200ODE_EINVAL, "opts.d_discontinuities needs a program compiled with -DB200_TSTOPS=1");
+    if (want_disc && prog->callbacks) return fail(B200ODE_EUNSUPPORTED, "d_discontinuities are not combined with callbacks");
     if (prog->tstops) {
         // initialize_tstops: stops strictly inside (t0, tf), ascending, duplicates kept, tf last — in the real type
         std::vector<R> stops;
@@ -867,16 +872,28 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
             const R v = (R)o->tstops[i];
             if (v > (R)dp->t0 && v < (R)dp->tf) stops.push_back(v);
         }
+        // ... and the d_discontinuities inside (t0, tf) (initialize_tstops, solve.jl:1033-1036)
+        std::vector<R> discs;
+        for (int i = 0; want_disc && i < o->nd_discontinuities; ++i) {
+            const R v = (R)o->d_discontinuities[i];
+            if (v > (R)dp->t0 && v < (R)dp->tf) stops.push_back(v);
+            if (v >= (R)dp->t0) discs.push_back(v);          // reinit_d_discontinuities! (solve.jl:1185-1197)
+        }
+        std::sort(discs.begin(), discs.end());
         std::sort(stops.begin(), stops.end());
         stops.push_back((R)dp->tf);
+        const size_t nstops = stops.size();
+        stops.insert(stops.end(), discs.begin(), discs.end());      // one device buffer: [stops..., discontinuities...]
         std::vector<double> key(stops.begin(), stops.end());
+        key.push_back((double)nstops);
         if (h->tstops_cached_dtype != (int)sizeof(R) || key != h->tstops_cached) {      // re-uploaded only when it changes
             CUDA_TRY(cudaDeviceSynchronize());      // no launch may still be reading the old list
             CUDA_TRY(h->tstops.ensure(sizeof(R) * stops.size()));
             CUDA_TRY(cudaMemcpy(h->tstops.ptr, stops.data(), sizeof(R) * stops.size(), cudaMemcpyHostToDevice));
             h->tstops_cached = key; h->tstops_cached_dtype = (int)sizeof(R);
         }
-        P.tstops = (const R*)h->tstops.ptr; P.ntstops = (int)stops.size();
+        P.tstops = (const R*)h->tstops.ptr; P.ntstops = (int)nstops;
+        P.disc = P.tstops + nstops; P.ndisc = (int)discs.size();
     }
     P.saveat = nullptr;
     if (P.nsaveat > 0) {

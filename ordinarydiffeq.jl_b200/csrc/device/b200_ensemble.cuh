@@ -170,6 +170,10 @@ struct B200Params {
     // fastpower(qoldinit = 1e-4, beta2) and its correctly rounded reciprocal: the controller state every trajectory
     // starts from (setup_controller_cache, controllers.jl:793-803), computed once by the host
     real fpe0, rfpe0;
+    // d_discontinuities (tstops programs only): opts.d_discontinuities as reinit_d_discontinuities! builds it
+    // (solve.jl:1185-1197): every entry >= t0, ascending; the entries inside (t0, tf) are also stops of `tstops`
+    const real* disc;
+    int ndisc;
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
@@ -418,6 +422,7 @@ struct B200Traj {
 #if B200_TSTOPS
     real tstop;                 // first(opts.tstops)
     int tstop_idx;
+    int disc_idx;               // entries of opts.d_discontinuities already popped
 #endif
 #if B200_EVERYSTEP
     real* trow;                 // next entry of ts_rag
@@ -523,6 +528,19 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     T.next_save = (P.nsaveat > 0) ? P.saveat[0] : b200_inf();
 #if B200_TSTOPS
     T.tstop_idx = 0; T.tstop = P.tstops[0];
+    T.disc_idx = 0;
+    // handle_starting_time_discontinuity! (solve.jl:887-901): a discontinuity at exactly t0 is popped, t moves one ulp
+    // forward and a first-same-as-last stepper evaluates its first stage again on the new side (reset_fsal!: nf += 1).
+    // The initial dt was determined at t0 itself, the start row carries t0.
+    if (P.ndisc > 0 && P.disc[0] == T.t) {
+        T.disc_idx = 1;
+        T.t = b200_nextfloat_signed(T.t);
+#if B200_COMPOSITE
+        T.st.reset_fsal(T.u, T.p, T.t, T.nf);
+#else
+        T.st.init(T.u, T.p, T.t, T.nf);
+#endif
+    }
 #endif
     T.naccept = 0; T.nreject = 0;
     T.accept = false; T.tstop_flag = false;
@@ -549,6 +567,16 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     // iter = naccept + nreject and success_iter = naccept at every point they are read.
     const int iter0 = T.naccept + T.nreject;
 #if B200_TSTOPS
+    // update_fsal! (integrator_utils.jl:215-220), first branch: the step just accepted ended on the first entry of
+    // opts.d_discontinuities — pop it, move t one ulp past it (shift_past_discontinuity!) and, below, refresh the first
+    // stage of a first-same-as-last stepper at the new t instead of copying the last one.  (t does not enter update_uprev!
+    // or `dt = dtpropose`, so shifting before them is the reference's order of effects.)
+    bool disc_hit = false;
+    if (P.ndisc > 0 && iter0 > 0 && T.accept && T.disc_idx < P.ndisc && P.disc[T.disc_idx] == T.t) {
+        T.disc_idx += 1;
+        T.t = b200_nextfloat_signed(T.t);
+        disc_hit = true;
+    }
     const real tstop = T.tstop;
     const real dist = b200_abs(tstop - T.t);
     const real at = b200_abs(T.t), atf = b200_abs(tstop);
@@ -569,6 +597,15 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #pragma unroll
             for (int c = 0; c < B200_N; ++c) T.uprev[c] = T.u[c];
             T.dt = T.dtpropose;
+#if B200_TSTOPS
+            if (disc_hit) {         // get_current_isfsal && reset_fsal! (init() of a stepper that is not FSAL is empty)
+#if B200_COMPOSITE
+                T.st.reset_fsal(T.u, T.p, T.t, T.nf);
+#else
+                T.st.init(T.u, T.p, T.t, T.nf);
+#endif
+            } else
+#endif
 #if B200_CALLBACKS
             // update_fsal! (integrator_utils.jl:215-239): reeval_fsal => reset_fsal!.  For every FSAL stepper init() IS
             // "fsalfirst = f(u, p, t); nf += 1" and steppers that are not FSAL have nothing to refresh (their init() is

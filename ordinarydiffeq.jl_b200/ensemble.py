@@ -385,7 +385,7 @@ class EnsembleSolution:
 
 
 # ---- solve ------------------------------------------------------------------------------------
-_ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "save_idxs", "tstops", "reltol",
+_ALLOWED_KW = {"trajectories", "batch_size", "saveat", "save_start", "save_end", "save_everystep", "save_idxs", "tstops", "d_discontinuities", "reltol",
                "abstol", "dt", "dtmin", "dtmax", "maxiters", "adaptive", "dense", "dtype", "flags", "save_on", "callback"}
 # accepted and ignored: they do not change the numbers (logging / progress / error-statistics switches of solve.jl:166-181)
 _IGNORED_KW = {"verbose", "progress", "progress_steps", "progress_name", "progress_message", "progress_id",
@@ -501,9 +501,14 @@ def solve(eprob, alg, ensemblealg=None, **kw):
             raise ValueError("save_idxs out of range for a state of length %d" % n)
     tstops = kw.get("tstops", None)
     tstops = None if tstops is None or len(tstops) == 0 else [float(x) for x in tstops]
+    # d_discontinuities (solve.jl:136): stops at which t is moved one ulp on and the first stage is evaluated again
+    discs = kw.get("d_discontinuities", None)
+    discs = None if discs is None or len(discs) == 0 else [float(x) for x in discs]
+    if discs is not None and kw.get("callback") is not None:
+        raise NotImplementedError("d_discontinuities are not combined with callbacks")
     # (the dense pass re-integrates with the default end-point handling: a solve with save_end = false keeps sol.t without
     #  the row at tf, which the dense rows would include — declined rather than answered from different rows)
-    dense_ok = (everystep and not grid and save_start and save_idxs is None and tstops is None and save_end is not False
+    dense_ok = (everystep and not grid and save_start and save_idxs is None and tstops is None and discs is None and save_end is not False
                 and alg.alg_id not in (_lib.ALG_ROSENBROCK32, _lib.ALG_AUTOTSIT5_ROSENBROCK23) and dense_kw is not False)      # dense = save_everystep && isempty(saveat) (solve.jl:144)
     if dense_kw and not dense_ok:
         raise NotImplementedError("dense=true is served for save_everystep solves without saveat / save_idxs / tstops "
@@ -533,14 +538,14 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     t0_, tf_ = float(prob.tspan[0]), float(prob.tspan[1])
     smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 12 and not ragged and cb_specs is None
                    and all(not (t0_ < float(g) < tf_) for g in (grid or [])))
-    program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None, adaptive, cb_specs,
+    program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None or discs is not None, adaptive, cb_specs,
                           vector_tol, smem_stages)
 
     def run(u0, p, ntraj, flags=0):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
                       dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
                       saveat=grid if grid else None, save_start=save_start, save_end=save_end,
-                      flags=flags | cb_flags, tstops=tstops)
+                      flags=flags | cb_flags, tstops=tstops, d_discontinuities=discs)
         if ragged:
             return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
         return lowlevel.solve_host(program, u0, p, prob.tspan, **common)

@@ -54,6 +54,7 @@ struct B200Opts
     save_start::Int32; save_end::Int32; flags::Int32; reserved::Int32
     tstops::Ptr{Float64}; ntstops::Int32; reserved2::Int32
     abstol_vec::Ptr{Float64}; reltol_vec::Ptr{Float64}      # per-component tolerances or C_NULL
+    d_discontinuities::Ptr{Float64}; nd_discontinuities::Int32; reserved3::Int32
 end
 struct B200CallbackSrc       # include/b200ode.h
     kind::Int32; rootfind::Int32
@@ -256,7 +257,7 @@ function with_pinned(f, arrays...)
     end
 end
 
-const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :tstops, :reltol, :abstol,
+const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :save_everystep, :save_idxs, :tstops, :d_discontinuities, :reltol, :abstol,
                  :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense, :verbose, :progress, :callback)
 
 # One batch of trajectories I (global sim ids) with repeat counters `rep`: harvest prob_func, solve, wrap.
@@ -346,7 +347,8 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     everystep && push!(extra, "-DB200_EVERYSTEP=1")
     idxs === nothing || push!(extra, "-DB200_SAVE_IDXS=" * join(idxs .- 1, ","))   # the C side is 0-based
     tstops = collect(Float64, get(kw, :tstops, ()))
-    isempty(tstops) || push!(extra, "-DB200_TSTOPS=1")
+    discs = collect(Float64, get(kw, :d_discontinuities, ()))     # stops with a one-ulp shift and a fresh first stage
+    (isempty(tstops) && isempty(discs)) || push!(extra, "-DB200_TSTOPS=1")
     adaptive = get(kw, :adaptive, true)
     adaptive || push!(extra, "-DB200_ADAPTIVE=0")
     adaptive || get(kw, :dt, nothing) !== nothing || !isempty(tstops) ||
@@ -385,9 +387,10 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
                     isempty(grid) ? Ptr{Float64}(C_NULL) : pointer(grid), length(grid),
                     Int32(ss), se === nothing ? Int32(-1) : Int32(se), flags, 0,
                     isempty(tstops) ? Ptr{Float64}(C_NULL) : pointer(tstops), length(tstops), 0,
-                    isempty(atv) ? Ptr{Float64}(C_NULL) : pointer(atv), isempty(rtv) ? Ptr{Float64}(C_NULL) : pointer(rtv))
+                    isempty(atv) ? Ptr{Float64}(C_NULL) : pointer(atv), isempty(rtv) ? Ptr{Float64}(C_NULL) : pointer(rtv),
+                    isempty(discs) ? Ptr{Float64}(C_NULL) : pointer(discs), length(discs), 0)
     tstart = time()
-    tol_keep = (atv, rtv)          # opts points into these: keep them reachable until the last batch returns
+    tol_keep = (atv, rtv, discs)   # opts points into these: keep them reachable until the last batch returns
     u = eprob.u_init === nothing ? [] : eprob.u_init
     converged = false
     for b0 in 1:batch_size:trajectories

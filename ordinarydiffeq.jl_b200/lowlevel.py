@@ -17,7 +17,8 @@ def _np_real(dtype):
 
 
 def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None,
-               maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None, _meanvar=None, tstops=None, _mean=None):
+               maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None, _meanvar=None, tstops=None, _mean=None,
+               d_discontinuities=None):
     """Host arrays in, host arrays out (b200ode_solve; b200ode_multi_solve for a MultiProgram).
 
     u0: (N, n) or (n,) shared; p: (N, np) or (np,) shared or None.
@@ -48,7 +49,7 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
         if p_arr is None or p_arr.shape[-1] != npar or (not p_shared and p_arr.shape[0] != N):
             raise ValueError("p has wrong shape for np=%d" % npar)
     t0, tf = float(tspan[0]), float(tspan[1])
-    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops)
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops, d_discontinuities)
     prob = _lib.B200Problem()
     prob.trajectories = N
     prob.u0 = u0.ctypes.data
@@ -155,13 +156,13 @@ def solve_host_dense(program, u0, p, tspan, tq, trajectories=None, reltol=None, 
 
 
 def solve_host_everystep(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None,
-                         dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, tstops=None):
+                         dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, tstops=None, d_discontinuities=None):
     """save_everystep = true (b200ode_solve_everystep): returns the per-trajectory scalars plus the ragged
     rows — row_offsets[N+1], ts[total], us[total, n]; trajectory i's sol.t / sol.u are
     ts[row_offsets[i]:row_offsets[i+1]] and the same slice of us."""
     L = _lib.lib()
     N, n, rdt, prob, res, out, keep_in = _marshal_ragged(program, u0, p, tspan, trajectories)
-    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops)
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops, d_discontinuities)
     rag = _lib.B200Ragged()
     _lib.check(L.b200ode_solve_everystep(program.handle._h, program._p, C.byref(prob), C.byref(opts), C.byref(res),
                                          C.byref(rag)))
@@ -234,10 +235,10 @@ class DeviceBuffers:
 
 
 def solve_device(program, bufs, tspan, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None,
-                 saveat=None, save_start=None, save_end=None, flags=0, stream=None, tstops=None):
+                 saveat=None, save_start=None, save_end=None, flags=0, stream=None, tstops=None, d_discontinuities=None):
     """Launch the ensemble on buffers already in HBM (b200ode_solve_device); asynchronous."""
     L = _lib.lib()
-    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops)
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops, d_discontinuities)
     dp = _lib.B200DeviceProblem()
     dp.trajectories = bufs.N
     dp.u0 = bufs.u0.data_ptr(); dp.u0_shared = int(bufs.u0_shared); dp.u0_layout = bufs.layout
@@ -280,13 +281,13 @@ def timeseries_meanvar_device(handle, dtype, us, mean, var=None, stream=None):
 
 def solve_everystep_device(program, bufs, tspan, row_offsets=None, ts=None, dts=None, us=None, reltol=None, abstol=None,
                            dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
-                           flags=0, stream=None, tstops=None):
+                           flags=0, stream=None, tstops=None, d_discontinuities=None):
     """Device-resident save_everystep (b200ode_solve_everystep_device); asynchronous.
 
     Counting pass: row_offsets=None — fills bufs.nsaved.  Fill pass: row_offsets = int64[N+1] exclusive scan of those
     counts (e.g. torch.cumsum on the device), ts/dts = real[total], us = real[total, nsave], all device tensors."""
     L = _lib.lib()
-    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops)
+    opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops, d_discontinuities)
     dp = _lib.B200DeviceProblem()
     dp.trajectories = bufs.N
     dp.u0 = bufs.u0.data_ptr(); dp.u0_shared = int(bufs.u0_shared); dp.u0_layout = bufs.layout

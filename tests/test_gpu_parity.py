@@ -1043,6 +1043,79 @@ def test_staged_saveat_queue_equals_in_step_interpolation(pkg, handle, oracle, f
         prog.close()
 
 
+def _forced_sources(f32):
+    """u' = -p0 u + (t > 1 ? p1 : 0) + (t > 2.5 ? p2 : 0), v' = u - v: a right-hand side with two switching times."""
+    T = "float" if f32 else "double"
+    s = "f" if f32 else ""
+    rhs = ("void forced_rhs(%(T)s* du, const %(T)s* u, const %(T)s* p, const %(T)s t) {\n"
+           "  du[0] = -p[0] * u[0] + (t > 1.0%(s)s ? p[1] : 0.0%(s)s) + (t > 2.5%(s)s ? p[2] : 0.0%(s)s);\n"
+           "  du[1] = u[0] - u[1];\n}\n" % dict(T=T, s=s), "forced_rhs")
+    jac = ("void forced_jac(%(T)s* J, const %(T)s* u, const %(T)s* p, const %(T)s t) {\n"
+           "  J[0] = -p[0]; J[1] = 1.0%(s)s; J[2] = 0.0%(s)s; J[3] = -1.0%(s)s;\n}\n" % dict(T=T, s=s), "forced_jac")
+    tg = ("void forced_tgrad(%(T)s* dT, const %(T)s* u, const %(T)s* p, const %(T)s t) { dT[0] = 0.0%(s)s; dT[1] = 0.0%(s)s; }\n"
+          % dict(T=T, s=s), "forced_tgrad")
+    return rhs, jac, tg
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_d_discontinuities(pkg, handle, oracle, f32):
+    """The d_discontinuities keyword (solve.jl:136; update_fsal! integrator_utils.jl:215-220; starting-time form
+    solve.jl:887-901): the integrator stops on each declared time, moves one ulp past it and (FSAL steppers) evaluates
+    its first stage again.  Bit-exact GPU vs oracle for Tsit5 (FSAL), Vern7 (not FSAL), Rosenbrock23 and Rodas5P, with
+    saveat rows around the switching times, with the ragged per-step output, with a discontinuity at t0, combined with
+    tstops, and with entries outside the span."""
+    pl = pkg.problems_library
+    N = 300
+    idx = np.arange(N, dtype=np.uint64)
+    rdt = np.float32 if f32 else np.float64
+    p = np.stack([0.5 + pl.splitmix64_uniform(idx, 0), 1.0 + pl.splitmix64_uniform(idx, 1), -2.0 * pl.splitmix64_uniform(idx, 2)],
+                 axis=1).astype(rdt)
+    u0 = np.array([1.0, 0.0], dtype=rdt)
+    rhs, jac, tg = _forced_sources(f32)
+    dtype = pkg.F32 if f32 else pkg.F64
+    tspan = (0.0, 4.0)
+    grid = [0.5, 1.0, 1.25, 2.5, 2.75, 4.0]
+    cases = [dict(d_discontinuities=[1.0, 2.5], saveat=grid),
+             dict(d_discontinuities=[2.5, 1.0, -1.0, 7.0]),
+             dict(d_discontinuities=[0.0, 1.0], saveat=grid, save_start=False),
+             dict(d_discontinuities=[1.0], tstops=[2.5, 3.0], saveat=grid)]
+    for alg, oalg, stiff in ((pkg.ALG_TSIT5, oracle.ALG_TSIT5, False), (pkg.ALG_VERN7, oracle.ALG_VERN7, False),
+                             (pkg.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK23, True), (pkg.ALG_RODAS5P, oracle.ALG_RODAS5P, True)):
+        extra = dict(jac_src=jac[0], jac_name=jac[1], tgrad_src=tg[0], tgrad_name=tg[1]) if stiff else {}
+        prog = handle.compile(alg, dtype, 2, 3, rhs[0], rhs[1], extra_options=pkg._lib.OPT_TSTOPS, **extra)
+        okw = dict(jac=jac, tgrad=tg) if stiff else {}
+        try:
+            for kw in cases:
+                g = pkg.lowlevel.solve_host(prog, u0, p, tspan, **kw)
+                o = oracle.solve(oalg, rhs, u0, p, tspan, 2, 3, f32=f32, **dict(kw, **okw))
+                assert_same_result(g, o)
+                assert (g["retcode"] == 1).all()
+            # the declared discontinuity changes the step sequence (otherwise the test would prove nothing)
+            plain = pkg.lowlevel.solve_host(prog, u0, p, tspan, tstops=[1.0, 2.5])
+            with_d = pkg.lowlevel.solve_host(prog, u0, p, tspan, d_discontinuities=[1.0, 2.5])
+            if alg == pkg.ALG_TSIT5:
+                assert (plain["nf"] != with_d["nf"]).any()
+        finally:
+            prog.close()
+    # ragged per-step rows: the declared time is a row, the shifted time is not
+    prog = handle.compile(pkg.ALG_TSIT5, dtype, 2, 3, rhs[0], rhs[1], extra_options=pkg._lib.OPT_TSTOPS + " " + pkg._lib.OPT_EVERYSTEP)
+    try:
+        g = pkg.lowlevel.solve_host_everystep(prog, u0, p, tspan, d_discontinuities=[1.0, 2.5])
+        o = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, tspan, 2, 3, f32=f32, save_everystep=True, d_discontinuities=[1.0, 2.5])
+        assert np.array_equal(g["row_offsets"], o["row_offsets"]) and np.array_equal(g["ts"], o["ts"])
+        assert np.array_equal(bits(g["us"]), bits(o["us"]))
+        assert (np.asarray(g["ts"], dtype=np.float64) == 1.0).sum() == N
+    finally:
+        prog.close()
+    # a program without the tstops variant rejects the keyword
+    prog = handle.compile(pkg.ALG_TSIT5, dtype, 2, 3, rhs[0], rhs[1])
+    try:
+        with pytest.raises(pkg._lib.B200Error):
+            pkg.lowlevel.solve_host(prog, u0, p, tspan, d_discontinuities=[1.0])
+    finally:
+        prog.close()
+
+
 # ---- AutoTsit5(Rosenbrock23()): per-trajectory switching between Tsit5 and Rosenbrock23 ------------------------------
 def _vdp_mixed_params(pl, N, f32):
     """Van der Pol with mu spread over [0.5, 500]: the ensemble holds trajectories that never leave Tsit5, trajectories

@@ -914,3 +914,27 @@ def test_pleiades_pair_shared_source_equals_the_reference_loop(pkg, f32):
     oa = oracle.solve(oracle.ALG_VERN7, (a, an), u0, None, (0.0, 3.0), 28, 0, f32=f32, **kw)
     ob = oracle.solve(oracle.ALG_VERN7, (b, bn), u0, None, (0.0, 3.0), 28, 0, f32=f32, **kw)
     assert_same_result(ob, oa)
+
+
+def test_d_discontinuities_known_answers():
+    """test/InterfaceI/ode_tstops_tests.jl:227-248 (interior discontinuity, Tsit5, reltol 1e-12): u(10) = 5 and 5.0 in
+    sol.t; the starting-time variant of :250-262 with Tsit5.  With the discontinuity declared the step after t_d starts one
+    ulp past it with a fresh first stage: no rejection at all; as a plain tstop the stale FSAL stage costs dozens."""
+    src = ("void stepf(double* du, const double* u, const double* p, const double t) { du[0] = t > 5.0 ? 1.0 : 0.0; }\n", "stepf")
+    kw = dict(trajectories=1, reltol=1e-12, abstol=1e-14)
+    o = oracle.solve(oracle.ALG_TSIT5, src, np.array([0.0]), None, (0.0, 10.0), 1, 0, save_everystep=True,
+                     d_discontinuities=[5.0], **kw)
+    assert abs(o["u_final"][0, 0] - 5.0) < 1e-10 and o["retcode"][0] == 1
+    assert 5.0 in o["ts"] and np.nextafter(5.0, 6.0) not in o["ts"]        # the shifted time is never saved
+    assert o["nreject"][0] == 0
+    t_only = oracle.solve(oracle.ALG_TSIT5, src, np.array([0.0]), None, (0.0, 10.0), 1, 0, tstops=[5.0], **kw)
+    assert abs(t_only["u_final"][0, 0] - 5.0) < 1e-10 and t_only["nreject"][0] > 10
+    # entries before t0 are dropped, entries beyond tf never match, a duplicate blocks the entries behind it (pop! takes one)
+    o2 = oracle.solve(oracle.ALG_TSIT5, src, np.array([0.0]), None, (0.0, 10.0), 1, 0, save_everystep=True,
+                      d_discontinuities=[-3.0, 5.0, 12.0], **kw)
+    assert_same_result(o2, o)
+    src0 = ("void stepf0(double* du, const double* u, const double* p, const double t) { du[0] = t > 0.0 ? 1.0 : 0.0; }\n", "stepf0")
+    o3 = oracle.solve(oracle.ALG_TSIT5, src0, np.array([0.0]), None, (0.0, 5.0), 1, 0, d_discontinuities=[0.0], **kw)
+    o4 = oracle.solve(oracle.ALG_TSIT5, src0, np.array([0.0]), None, (0.0, 5.0), 1, 0, **kw)
+    assert abs(o3["u_final"][0, 0] - 5.0) < 1e-10 and abs(o4["u_final"][0, 0] - 5.0) < 1e-10
+    assert o3["nf"][0] < o4["nf"][0] // 2        # f(u0, t0) = 0 seeds a hopeless first step without the shift
