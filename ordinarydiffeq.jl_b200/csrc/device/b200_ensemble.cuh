@@ -738,7 +738,10 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         b200_handle_callbacks(P, idx, T);
         if (T.terminated) return true;                  // terminate! emptied the tstops
 #else
-#if !B200_STAGE_ROWS       // (staged programs interpolate in b200_stage_rows, after the step, with all lanes of the warp)
+#ifndef B200_NO_SAVEAT
+#define B200_NO_SAVEAT 0        // 1: the program is only launched without a saveat grid (final states / start-end rows)
+#endif
+#if !B200_STAGE_ROWS && !(B200_NO_SAVEAT && !B200_EVERYSTEP)      // (staged programs interpolate in b200_stage_rows, after the step, with all lanes of the warp)
         {
             bool dense_ready = false;
             real rdt = (real)0;         // refined 1/dt, shared by the rows of this step
@@ -773,7 +776,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                 b200_emit(P, idx, T, T.t, T.u, dt_stages);
 #endif
         }
-#endif  // !B200_STAGE_ROWS
+#endif  // !B200_STAGE_ROWS && !B200_NO_SAVEAT
 #endif  // !B200_CALLBACKS
 #if B200_TSTOPS
         // handle_tstop! (integrator_utils.jl:1290-1314): pop every copy of a stop time that was reached;
