@@ -48,9 +48,18 @@ struct B200AutoTsit5Ros23 {
         if (current == 1) {
             EEst = ns.attempt(uprev, u, p, t, dt, reltol, abstol, nf, g6);
             // Hairer II p. 22 with the Inf norm: norm(x, Inf) = mapreduce(abs, max, x), Base.max keeps NaN
-            real m = b200_abs((ns.k7[0] - ns.k6[0]) / (u[0] - g6[0]));
+            // (the n quotients as one flagged group; u == g6 in a component gives Inf / NaN through the plain operator)
+            real q[B200_N];
+            bool bad = false;
 #pragma unroll
-            for (int i = 1; i < B200_N; ++i) m = b200_max(m, b200_abs((ns.k7[i] - ns.k6[i]) / (u[i] - g6[i])));
+            for (int i = 0; i < B200_N; ++i) q[i] = b200_div_fast(ns.k7[i] - ns.k6[i], u[i] - g6[i], bad);
+            if (bad) {
+#pragma unroll
+                for (int i = 0; i < B200_N; ++i) q[i] = b200_div_cold(ns.k7[i] - ns.k6[i], u[i] - g6[i]);
+            }
+            real m = b200_abs(q[0]);
+#pragma unroll
+            for (int i = 1; i < B200_N; ++i) m = b200_max(m, b200_abs(q[i]));
             eigen_est = b200_abs(m);
         } else {
             // calc_W of a CompositeAlgorithm: integrator.eigen_est = opnorm(J, Inf) (derivative_utils.jl:996-999)
@@ -71,7 +80,12 @@ struct B200AutoTsit5Ros23 {
     // the controller caches).  dt may be doubled / halved (dtfac = 2).
     B200_D bool choose(real& dt, const real* uprev, const real* p, real t, int& nf) {
         // is_stiff: abs(eigen_est * dt / alg_stability_size(nonstiffalg)); the Float64 constant promotes the quotient
-        const double stiffness = fabs((double)(eigen_est * dt) / 3.5068);
+        double stiffness;
+        {
+            bool bad = false;
+            stiffness = fabs(b200_div_fast((double)(eigen_est * dt), 3.5068, bad));
+            if (bad) stiffness = fabs(b200_div_cold((double)(eigen_est * dt), 3.5068));
+        }
         const bool stiff = !(stiffness <= 0.9);                 // os * tol = 1.0 * 9//10 (both tolerances)
         const bool in_stiff = (current == 2);
         successive = stiff ? 0 : successive + 1;
