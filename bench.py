@@ -56,6 +56,10 @@ WORKLOADS = {
     "lorenz_tsit5_saveat_1m": dict(problem="lorenz", alg="tsit5", f32=False, N=1 << 20, saveat=0.1, tspan=(0.0, 10.0), tol={}),
     "lorenz_tsit5_saveat_1m_f32": dict(problem="lorenz", alg="tsit5", f32=True, N=1 << 20, saveat=0.1, tspan=(0.0, 10.0), tol={}),
     "lorenz_tsit5_final_1m": dict(problem="lorenz", alg="tsit5", f32=False, N=1 << 20, saveat=None, tspan=(0.0, 10.0), tol={}),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case (10 k trajectories, reltol 1e-8) — latency-, not
+    # throughput-bound on a GPU: 10 k trajectories are two warps per SM
+    "lorenz_tsit5_10k_reltol1e-8": dict(problem="lorenz", alg="tsit5", f32=False, N=10000, saveat=None, tspan=(0.0, 10.0),
+                                        tol=dict(reltol=1e-8)),
     "robertson_rodas5p_1m": dict(problem="robertson", alg="rodas5p", f32=False, N=1 << 20, saveat=None, tspan=(0.0, 1e5),
                                  tol=dict(reltol=1e-6, abstol=1e-8)),
     "robertson_rosenbrock23_1m": dict(problem="robertson", alg="ros23", f32=False, N=1 << 20, saveat=None, tspan=(0.0, 1e5),
@@ -71,7 +75,7 @@ WORKLOADS = {
     "vdp_autotsit5_mixed_256k": dict(problem="vdp_mixed", alg="autotsit5", f32=False, N=1 << 18, saveat=None, tspan=(0.0, 20.0),
                                      tol={}),
 }
-OTHER_CONFIGS = ["lorenz_tsit5_saveat_1m_f32", "lorenz_tsit5_final_1m", "robertson_rodas5p_1m", "robertson_rosenbrock23_1m",
+OTHER_CONFIGS = ["lorenz_tsit5_10k_reltol1e-8", "lorenz_tsit5_saveat_1m_f32", "lorenz_tsit5_final_1m", "robertson_rodas5p_1m", "robertson_rosenbrock23_1m",
                  "pleiades_vern7_256k", "vdp_autotsit5_mixed_256k"]
 ALG_NAMES = {"tsit5": "ALG_TSIT5", "vern7": "ALG_VERN7", "ros23": "ALG_ROSENBROCK23", "rodas5p": "ALG_RODAS5P",
              "autotsit5": "ALG_AUTOTSIT5_ROSENBROCK23"}

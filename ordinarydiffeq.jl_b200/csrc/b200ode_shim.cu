@@ -956,7 +956,7 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         unsigned g = (unsigned)((N + 255) / 256);
         CUDA_TRY(cudaLaunchKernel((const void*)prog->k_initdt, dim3(g), dim3(256), args, 0, stream));
     }
-    unsigned grid;
+    unsigned grid, small_block = 0;
     if (prog->wide_nt > 0) {
         if (P.nsaveat > 0) {
             // interior rows need the interpolant, whose lazy stages k11..k16 this variant does not store
@@ -976,6 +976,15 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         grid = (unsigned)prog->info.grid;
         long long need = (N + prog->info.block - 1) / prog->info.block;
         if ((long long)grid > need) grid = (unsigned)(need > 0 ? need : 1);
+        // Small ensembles (BASELINE configs[0]: 10 k trajectories): full CTAs would occupy N / block SMs with four warps per
+        // scheduler each while the other SMs idle; the launch bound is only a maximum, so the CTAs shrink until the
+        // trajectories spread over all SMs (one or two warps per scheduler finish a step in its latency, not in 4x it)
+        if (need < (long long)h->num_sms) {
+            const long long per_sm = (N + h->num_sms - 1) / h->num_sms;
+            small_block = (unsigned)std::max<long long>(32, (per_sm + 31) / 32 * 32);
+            if (small_block < (unsigned)prog->info.block) grid = (unsigned)std::max<long long>(1, (N + small_block - 1) / small_block);
+            else small_block = 0;
+        }
     }
     b200ode_program run = prog;
     if (P.nsaveat == 0 && prog->nosave_ok) {       // the build without saveat handling (made on first use)
@@ -983,7 +992,8 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
         if (!prog->nosave_tried) { prog->nosave_tried = true; if (g_compile_nosave) g_compile_nosave(prog); }
         if (prog->nosave) run = prog->nosave;
     }
-    CUDA_TRY(cudaLaunchKernel((const void*)run->k_integrate, dim3(grid), dim3(run->info.block), args, run->dyn_smem, stream));
+    CUDA_TRY(cudaLaunchKernel((const void*)run->k_integrate, dim3(grid), dim3(small_block ? small_block : run->info.block), args,
+                              run->dyn_smem, stream));
     return B200ODE_OK;
 }
 
