@@ -536,7 +536,9 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     # Vern7 on a wide state with nothing but start / end rows asked for: the stage derivatives do not fit a thread's
     # registers, so the kernel that keeps them in shared memory runs (B200ODE_OPT_SMEM_STAGES; bit-identical results)
     t0_, tf_ = float(prob.tspan[0]), float(prob.tspan[1])
-    smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 12 and not ragged and cb_specs is None
+    # (n >= 24: measured crossover on a cheap-RHS chain system, scripts/time_wide_threshold.py — below it the plain kernel's
+    #  local-memory stage vectors, served from L1 at full occupancy, are faster than 112-256 threads with shared-memory stages)
+    smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 24 and not ragged and cb_specs is None
                    and all(not (t0_ < float(g) < tf_) for g in (grid or [])))
     program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None or discs is not None, adaptive, cb_specs,
                           vector_tol, smem_stages)

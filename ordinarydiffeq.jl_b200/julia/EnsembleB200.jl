@@ -370,7 +370,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     (isempty(rtv) && isempty(atv)) || push!(extra, "-DB200_VECTOR_TOL=1")
     # Vern7 on a wide state with nothing but start / end rows: the kernel that keeps k1..k10 in shared memory
     # (B200ODE_OPT_SMEM_STAGES; bit-identical results, it serves no interior saveat rows and no callbacks)
-    if alg isa Vern7 && n >= 12 && !everystep && isempty(cbs)
+    if alg isa Vern7 && n >= 24 && !everystep && isempty(cbs)       # measured crossover: scripts/time_wide_threshold.py
         t0w, tfw = prob.tspan
         grid_pts = saveat isa Number ? (saveat > 0 && saveat < abs(tfw - t0w) ? (1,) : ()) : filter(t -> t0w < t < tfw, collect(saveat))
         isempty(grid_pts) && push!(extra, "-DB200_WIDE=1")
