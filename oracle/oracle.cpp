@@ -891,10 +891,17 @@ template <typename R, typename Alg>
 static void dense_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R tf, const Opts<R>& o, long long idx,
                       const Out<R>& out_in, const R* tq, int M, R* dense_out);
 
+// per-trajectory time spans (a prob_func that remakes the problem with its own tspan): (t0_i, tf_i) pairs or NULL;
+// dtmax_default: opts.dtmax was not given, so each trajectory's dtmax is its own tf_i - t0_i (solve.jl:152)
+static const double* g_tspans = nullptr;
+static bool g_dtmax_default = false;
+
 template <typename R, typename Alg>
 static void solve_batch(const ProblemFns<R>& P, long long N, const R* u0, int u0_shared, const R* p, int p_shared, R t0,
                         R tf, const Opts<R>& o, const Out<R>& out, int nthreads, const R* tq = nullptr, int M = 0,
                         R* dense_out = nullptr) {
+    const double* tspans = g_tspans;
+    const bool dtmax_default = g_dtmax_default;
     // the structural analogue of EnsembleThreads' Threads.@threads over trajectories
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -903,6 +910,20 @@ static void solve_batch(const ProblemFns<R>& P, long long N, const R* u0, int u0
     for (long long i = 0; i < N; ++i) {
         const R* ui = u0_shared ? u0 : u0 + (size_t)i * P.n;
         const R* pi = p_shared ? p : p + (size_t)i * P.np;
+        if (tspans != nullptr) {
+            // every trajectory is its own solve(prob_i, alg; kwargs...): its span, its default dtmax, and of a saveat
+            // list the entries inside (t0_i, tf_i] (solve.jl:1103-1124 filters the grid against the problem's own tspan)
+            const R t0i = (R)tspans[2 * i], tfi = (R)tspans[2 * i + 1];
+            Opts<R> oi = o;
+            if (dtmax_default) oi.dtmax = tfi - t0i;
+            int a = 0;
+            while (a < o.nsaveat && !(o.saveat[a] > t0i)) ++a;
+            int b = a;
+            while (b < o.nsaveat && o.saveat[b] <= tfi) ++b;
+            oi.saveat = o.saveat + a; oi.nsaveat = b - a;
+            solve_one<R, Alg>(P, ui, pi, t0i, tfi, oi, i, out);
+            continue;
+        }
         if (dense_out) dense_one<R, Alg>(P, ui, pi, t0, tf, o, i, out, tq, M, dense_out);
         else solve_one<R, Alg>(P, ui, pi, t0, tf, o, i, out);
     }
@@ -963,6 +984,7 @@ struct OracleArgs {
     const OracleCallback* cbs; int ncb;     // the CallbackSet (Tsit5 only)
     const double* abstol_v; const double* reltol_v;    // per-component tolerances (n entries each) or NULL
     const double* disc; int ndisc;          // the d_discontinuities keyword, unfiltered
+    const double* tspans;                   // per-trajectory (t0_i, tf_i) pairs or NULL
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -1020,6 +1042,8 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         o.tstops = stops.data(); o.ntstops = (int)stops.size();
         o.disc = discs.data(); o.ndisc = (int)discs.size();
     }
+    g_tspans = a.tspans; g_dtmax_default = !(a.dtmax > 0);
+    if (a.tspans && ((a.tstops && a.ntstops > 0) || (a.disc && a.ndisc > 0) || M > 0)) return -6;
     Out<R> out;
     out.row_offsets = a.row_offsets; out.ts_rag = (R*)a.ts_rag;
     if (a.save_idxs && a.nsave_idxs > 0) {

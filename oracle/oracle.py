@@ -51,7 +51,7 @@ class OracleArgs(C.Structure):
                 ("save_idxs", C.c_void_p), ("nsave_idxs", C.c_int),
                 ("tstops", C.c_void_p), ("ntstops", C.c_int), ("fixed_dt", C.c_int),
                 ("cbs", C.c_void_p), ("ncb", C.c_int), ("abstol_v", C.c_void_p), ("reltol_v", C.c_void_p),
-                ("disc", C.c_void_p), ("ndisc", C.c_int)]
+                ("disc", C.c_void_p), ("ndisc", C.c_int), ("tspans", C.c_void_p)]
 
 
 class OracleCallback(C.Structure):
@@ -179,12 +179,24 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     u0_shared = u0.ndim == 1
     p_arr = None if p is None else np.ascontiguousarray(p, dtype=rdt)
     p_shared = True if p_arr is None else p_arr.ndim == 1
+    tsp = np.asarray(tspan, dtype=np.float64)
+    tspans = np.ascontiguousarray(tsp) if tsp.ndim == 2 else None        # (N, 2): per-trajectory spans
     if trajectories is None:
-        trajectories = u0.shape[0] if not u0_shared else p_arr.shape[0]
+        if not u0_shared:
+            trajectories = u0.shape[0]
+        elif p_arr is not None and not p_shared:
+            trajectories = p_arr.shape[0]
+        else:
+            trajectories = tspans.shape[0]
     N = int(trajectories)
-    t0, tf = float(tspan[0]), float(tspan[1])
+    if tspans is None:
+        t0, tf = float(tspan[0]), float(tspan[1])
+    else:
+        assert tspans.shape == (N, 2)
+        t0, tf = float(tspans[:, 0].min()), float(tspans[:, 1].max())
     grid = None if saveat is None or len(saveat) == 0 else np.ascontiguousarray(saveat, dtype=np.float64)
-    nslots = nslots_for(t0, tf, grid, save_start, save_end)
+    # (per-trajectory spans: no rectangular rows — final states, statistics, or the ragged output)
+    nslots = nslots_for(t0, tf, grid, save_start, save_end) if tspans is None else 0
     idxs = None if save_idxs is None else np.ascontiguousarray(save_idxs, dtype=np.int32)
     w = n if idxs is None else len(idxs)          # components per saved row (save_idxs, 0-based)
     out = {
@@ -202,6 +214,7 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     a.u0 = u0.ctypes.data; a.u0_shared = int(u0_shared)
     a.p = p_arr.ctypes.data if p_arr is not None else None; a.p_shared = int(p_shared)
     a.t0, a.tf = t0, tf
+    a.tspans = tspans.ctypes.data if tspans is not None else None
     # abstol / reltol may be vectors (one entry per component)
     tolv = {}
     for key, val in (("abstol", abstol), ("reltol", reltol)):

@@ -31,7 +31,8 @@ class B200Error(RuntimeError):
 
 class B200Problem(C.Structure):
     _fields_ = [("trajectories", C.c_int64), ("u0", C.c_void_p), ("u0_shared", C.c_int32),
-                ("p", C.c_void_p), ("p_shared", C.c_int32), ("t0", C.c_double), ("tf", C.c_double)]
+                ("p", C.c_void_p), ("p_shared", C.c_int32), ("t0", C.c_double), ("tf", C.c_double),
+                ("tspans", C.c_void_p)]
 
 
 class B200Opts(C.Structure):
@@ -54,7 +55,7 @@ class B200Result(C.Structure):
 class B200DeviceProblem(C.Structure):
     _fields_ = [("trajectories", C.c_int64), ("u0", C.c_void_p), ("u0_shared", C.c_int32), ("u0_layout", C.c_int32),
                 ("p", C.c_void_p), ("p_shared", C.c_int32), ("p_layout", C.c_int32),
-                ("t0", C.c_double), ("tf", C.c_double)]
+                ("t0", C.c_double), ("tf", C.c_double), ("tspans", C.c_void_p)]
 
 
 class B200DeviceResult(C.Structure):
@@ -111,6 +112,7 @@ def callback_array(callbacks):
 
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
 OPT_TSTOPS = "-DB200_TSTOPS=1"
+OPT_TSPANS = "-DB200_TSPANS=1"
 OPT_VECTOR_TOL = "-DB200_VECTOR_TOL=1"
 OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
 OPT_COMPONENT_RHS = "-DB200_COOP=1"

@@ -77,6 +77,7 @@ struct Params {
     int ntstops;
     R fpe0, rfpe0;
     const R* disc; int ndisc;
+    const double* tspans; int dtmax_default;
 };
 
 struct DevBuf {
@@ -111,7 +112,7 @@ struct b200ode_handle_s {
     int saveat_cached_dtype = -1;        // ... in this real type
     std::vector<double> tstops_cached;   // same for the tstops list
     int tstops_cached_dtype = -1;
-    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out, scan_tiles, tstops;
+    DevBuf in_u0, in_p, out_uf, out_tf, out_us, out_i32, red_partial, stat_out, row_offsets, rag_dts, dense_tq, dense_out, scan_tiles, tstops, in_tspans;
     // pinned bounce buffers for large D2H copies into pageable caller memory (d2h_large)
     void* stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -129,6 +130,7 @@ struct b200ode_program_s {
     bool adaptive = true;        // false: compiled with -DB200_ADAPTIVE=0 (fixed dt)
     bool callbacks = false;      // compiled with a CallbackSet (b200ode_compile_callbacks)
     bool vector_tol = false;     // compiled with -DB200_VECTOR_TOL=1 (per-component abstol / reltol)
+    bool tspans = false;         // compiled with -DB200_TSPANS=1 (per-trajectory time spans)
     std::vector<double> tolv_cached;   // the 2n tolerances currently resident in the module's B200_TOLV
     int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
@@ -837,6 +839,12 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     else if (dp->p_layout == B200ODE_LAYOUT_SOA) { P.p_ts = 1; P.p_cs = N; }
     else { P.p_ts = np; P.p_cs = 1; }
     P.t0 = (R)dp->t0; P.tf = (R)dp->tf;
+    P.tspans = dp->tspans; P.dtmax_default = (o->dtmax > 0) ? 0 : 1;
+    if ((dp->tspans != nullptr) != prog->tspans)
+        return fail(B200ODE_EINVAL, prog->tspans ? "a program compiled with -DB200_TSPANS=1 needs problem.tspans"
+                                                 : "problem.tspans needs a program compiled with -DB200_TSPANS=1");
+    if (prog->tspans && dr->us && !prog->everystep)
+        return fail(B200ODE_EUNSUPPORTED, "per-trajectory time spans: the rectangular `us` output is not available (use the ragged output)");
     P.reltol = (R)(o->reltol > 0 ? o->reltol : 1e-3);
     P.abstol = (R)(o->abstol > 0 ? o->abstol : 1e-6);
     if ((o->abstol_vec || o->reltol_vec) && !prog->vector_tol)
@@ -939,7 +947,7 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     P.flags = o->flags;
     {   // tstop tolerance 100*eps(max(|t|,|tf|)) (integrator_utils.jl:277-286) is constant when |t0| <= |tf|
         const R at0 = std::fabs(P.t0), atf = std::fabs(P.tf);
-        P.tol_const = !(at0 > atf) ? 1 : 0;
+        P.tol_const = (!(at0 > atf) && dp->tspans == nullptr) ? 1 : 0;
         P.tol100_tf = (R)100 * (std::nextafter(atf, std::numeric_limits<R>::infinity()) - atf);
     }
     {   // controller start state: fastpower(qoldinit, beta2), beta2 = 2//(5 order) (4//100 for DP5) rounded to the real type
@@ -1061,7 +1069,7 @@ int b200ode_destroy(b200ode_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : {&h->counter, &h->dt0, &h->saveat, &h->scratch_t, &h->in_u0, &h->in_p, &h->out_uf, &h->out_tf,
-                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets, &h->rag_dts, &h->dense_tq, &h->dense_out, &h->scan_tiles, &h->tstops})
+                      &h->out_us, &h->out_i32, &h->red_partial, &h->stat_out, &h->row_offsets, &h->rag_dts, &h->dense_tq, &h->dense_out, &h->scan_tiles, &h->tstops, &h->in_tspans})
         b->release();
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1151,6 +1159,11 @@ static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dty
     prog->everystep = extra_options && strstr(extra_options, "-DB200_EVERYSTEP=1");
     prog->tstops = extra_options && strstr(extra_options, "-DB200_TSTOPS=1");
     prog->adaptive = !(extra_options && strstr(extra_options, "-DB200_ADAPTIVE=0"));
+    prog->tspans = extra_options && strstr(extra_options, "-DB200_TSPANS=1");
+    if (prog->tspans && (prog->tstops || prog->coop_l > 0 || prog->wide_nt > 0 || ncb > 0)) {
+        delete prog; return fail(B200ODE_EUNSUPPORTED, "per-trajectory time spans are not combined with tstops / d_discontinuities, callbacks, "
+                                                       "the lane-group or the shared-memory stage kernel");
+    }
     if ((!prog->adaptive || prog->tstops || prog->everystep) && prog->coop_l > 0) {
         delete prog; return fail(B200ODE_EUNSUPPORTED, "adaptive=false, tstops and save_everystep are not available in the lane-group kernel");
     }
@@ -1348,6 +1361,25 @@ static int d2h_large(b200ode_handle h, void* dst, const void* src, size_t bytes,
 
 // H2D, counting pass, host exclusive scan, fill pass.  Leaves the ragged rows in the handle's device
 // buffers (out_us, scratch_t = ts, rag_dts, row_offsets) and the scalars in out_uf/out_tf/out_i32.
+// B200Problem.tspans: validate the pairs, give check_problem the union of the spans, upload the pairs
+static int host_tspans(b200ode_handle h, const B200Problem* hp, double* tmin, double* tmax, const double** dev, cudaStream_t s) {
+    *dev = nullptr; *tmin = hp->t0; *tmax = hp->tf;
+    if (!hp->tspans || hp->trajectories <= 0) return B200ODE_OK;
+    double lo = hp->tspans[0], hi = hp->tspans[1];
+    for (int64_t i = 0; i < hp->trajectories; ++i) {
+        const double a = hp->tspans[2 * i], b = hp->tspans[2 * i + 1];
+        if (!std::isfinite(a) || !std::isfinite(b) || !(b > a))
+            return fail(B200ODE_EUNSUPPORTED, "tspans: every (t0_i, tf_i) must be finite with tf_i > t0_i (forward time)");
+        lo = std::min(lo, a); hi = std::max(hi, b);
+    }
+    *tmin = lo; *tmax = hi;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(h->in_tspans.ensure(sizeof(double) * 2 * (size_t)hp->trajectories));
+    CUDA_TRY(cudaMemcpyAsync(h->in_tspans.ptr, hp->tspans, sizeof(double) * 2 * (size_t)hp->trajectories, cudaMemcpyHostToDevice, s));
+    *dev = (const double*)h->in_tspans.ptr;
+    return B200ODE_OK;
+}
+
 static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Problem* hp, const B200Opts* o,
                          long long& total_out) {
     const long long N = hp->trajectories;
@@ -1375,6 +1407,12 @@ static int everystep_run(b200ode_handle h, b200ode_program prog, const B200Probl
     dp.u0 = h->in_u0.ptr; dp.u0_shared = hp->u0_shared; dp.u0_layout = B200ODE_LAYOUT_AOS;
     dp.p = np > 0 ? h->in_p.ptr : nullptr; dp.p_shared = hp->p_shared; dp.p_layout = B200ODE_LAYOUT_AOS;
     dp.t0 = hp->t0; dp.tf = hp->tf;
+    {
+        double tmin, tmax; const double* dev_tspans = nullptr;
+        int rc_t = host_tspans(h, hp, &tmin, &tmax, &dev_tspans, s);
+        if (rc_t) return rc_t;
+        dp.t0 = tmin; dp.tf = tmax; dp.tspans = dev_tspans;
+    }
     B200DeviceResult dr{};
     dr.u_final = h->out_uf.ptr; dr.u_final_layout = B200ODE_LAYOUT_AOS;
     dr.t_final = (double*)h->out_tf.ptr;
@@ -1445,7 +1483,16 @@ static int everystep_check(b200ode_handle h, b200ode_program prog, const B200Pro
     if (!h || !prog || !hp || !o || !res) return fail(B200ODE_EINVAL, "NULL argument");
     if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
     if (!prog->everystep) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
-    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, hp->t0, hp->tf, o);
+    double tmin = hp->t0, tmax = hp->tf;
+    if (hp->tspans) {
+        for (int64_t i = 0; i < hp->trajectories; ++i) {
+            const double a = hp->tspans[2 * i], b = hp->tspans[2 * i + 1];
+            if (!std::isfinite(a) || !std::isfinite(b) || !(b > a))
+                return fail(B200ODE_EUNSUPPORTED, "tspans: every (t0_i, tf_i) must be finite with tf_i > t0_i (forward time)");
+            tmin = i == 0 ? a : std::min(tmin, a); tmax = i == 0 ? b : std::max(tmax, b);
+        }
+    }
+    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, tmin, tmax, o);
     if (rc) return rc;
     if (!res->u_final) return fail(B200ODE_EINVAL, "result.u_final is required");
     return B200ODE_OK;
@@ -1543,6 +1590,7 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
     if (rc) return rc;
     if (o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "dense output excludes saveat (dense = save_everystep && isempty(saveat), solve.jl:139)");
     if (o->save_start == 0) return fail(B200ODE_EINVAL, "dense output needs save_start");
+    if (hp->tspans) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with per-trajectory time spans");
     if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows), for the composite algorithm or with callbacks");
     for (int j = 1; j < nq; ++j) if (!(tq[j] >= tq[j - 1])) return fail(B200ODE_EINVAL, "tq must be ascending");
     const long long N = hp->trajectories;
@@ -1587,8 +1635,13 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
                            double* mean, double* var, bool stats_only) {
     if (!h || !prog || !hp || !o || !res) return fail(B200ODE_EINVAL, "NULL argument");
     if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
-    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, hp->t0, hp->tf, o);
+    double tmin, tmax; const double* dev_tspans = nullptr;
+    int rc = host_tspans(h, hp, &tmin, &tmax, &dev_tspans, h->stream);
     if (rc) return rc;
+    rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, tmin, tmax, o);
+    if (rc) return rc;
+    if (hp->tspans && (res->us || stats_only))
+        return fail(B200ODE_EUNSUPPORTED, "per-trajectory time spans: the rectangular `us` output and its statistics are not available");
     if (!res->u_final) return fail(B200ODE_EINVAL, "result.u_final is required");
     const long long N = hp->trajectories;
     if (N == 0) return B200ODE_OK;
@@ -1637,7 +1690,8 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
         dp.u0_shared = hp->u0_shared; dp.u0_layout = B200ODE_LAYOUT_AOS;
         dp.p = np > 0 ? (char*)h->in_p.ptr + (hp->p_shared ? 0 : rs * np * (size_t)c0) : nullptr;
         dp.p_shared = hp->p_shared; dp.p_layout = B200ODE_LAYOUT_AOS;
-        dp.t0 = hp->t0; dp.tf = hp->tf;
+        dp.t0 = tmin; dp.tf = tmax;
+        dp.tspans = dev_tspans ? dev_tspans + 2 * (size_t)c0 : nullptr;
         B200DeviceResult dr{};
         dr.u_final = (char*)h->out_uf.ptr + rs * n * (size_t)c0; dr.u_final_layout = B200ODE_LAYOUT_AOS;
         dr.t_final = (double*)((char*)h->out_tf.ptr + rs * (size_t)c0);
@@ -1937,6 +1991,7 @@ static int multi_run(b200ode_multi m, b200ode_multi_program mp, const B200Proble
             sub.trajectories = cn;
             sub.u0 = hp->u0_shared ? hp->u0 : (const char*)hp->u0 + rs * n * (size_t)c0;
             sub.p = (np > 0 && !hp->p_shared) ? (const void*)((const char*)hp->p + rs * np * (size_t)c0) : hp->p;
+            sub.tspans = hp->tspans ? hp->tspans + 2 * (size_t)c0 : nullptr;
             B200Result r{};
             if (res) {
                 r = *res;

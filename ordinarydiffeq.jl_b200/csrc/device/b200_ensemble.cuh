@@ -174,6 +174,9 @@ struct B200Params {
     // (solve.jl:1185-1197): every entry >= t0, ascending; the entries inside (t0, tf) are also stops of `tstops`
     const real* disc;
     int ndisc;
+    // per-trajectory time spans (programs compiled with -DB200_TSPANS=1): (t0_i, tf_i) pairs, NULL otherwise
+    const double* tspans;
+    int dtmax_default;        // 1: opts.dtmax was not given, i.e. dtmax = tf_i - t0_i per trajectory (solve.jl:152)
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
@@ -213,10 +216,25 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #ifndef B200_CALLBACKS
 #define B200_CALLBACKS 0      // 1: the program carries a CallbackSet (device/b200_callbacks.cuh; Tsit5)
 #endif
+#ifndef B200_TSPANS
+#define B200_TSPANS 0         // 1: every trajectory has its own (t0, tf) (prob_func changed tspan): B200Params.tspans
+#endif
+#if B200_TSPANS && (B200_COOP || B200_TSTOPS || B200_CALLBACKS || B200_WIDE)
+#error "per-trajectory time spans are not combined with tstops / d_discontinuities, callbacks, the lane-group or the stage kernel"
+#endif
+#if B200_TSPANS
+#define B200_T0 (T.t0)
+#define B200_TF (T.tf)
+#define B200_DTMAX (T.dtmax)
+#else
+#define B200_T0 (P.t0)
+#define B200_TF (P.tf)
+#define B200_DTMAX (P.dtmax)
+#endif
 #ifndef B200_STAGE_ROWS
 #define B200_STAGE_ROWS 0     // 1: saveat rows are packed through a per-warp shared-memory queue and interpolated at full lane occupancy (Tsit5)
 #endif
-#if B200_STAGE_ROWS && (B200_ALG != B200_ALG_TSIT5 || B200_EVERYSTEP || B200_CALLBACKS || defined(B200_SAVE_IDXS) || B200_COOP)
+#if B200_STAGE_ROWS && (B200_ALG != B200_ALG_TSIT5 || B200_EVERYSTEP || B200_CALLBACKS || defined(B200_SAVE_IDXS) || B200_COOP || B200_TSPANS)
 #error "the staged saveat queue serves Tsit5 with a rectangular saveat output (no save_everystep / save_idxs / callbacks)"
 #endif
 #if defined(B200_ISOUT) && B200_COOP
@@ -328,12 +346,19 @@ extern "C" __global__ void __launch_bounds__(256) b200_initdt(B200Params P) {
     for (int c = 0; c < B200_NP; ++c) p[c] = P.p[i * P.p_ts + c * P.p_cs];
     // _determine_initdt: dtmax = min(|opts.dtmax|, |first_tstop - t|)
     // _determine_initdt: dtmax = min(|opts.dtmax|, |first_tstop - t|) (integrator_interface.jl:643-647)
+#if B200_TSPANS
+    const real t0i = (real)P.tspans[2 * i], tfi = (real)P.tspans[2 * i + 1];
+    const real dtmax_o = P.dtmax_default ? (tfi - t0i) : P.dtmax;
+    real dtmax = b200_min(b200_abs(dtmax_o), b200_abs(tfi - t0i));
+    P.dt0[i] = b200_initdt_one(u0, p, t0i, dtmax, P.abstol, P.reltol, P.dtmin, B200Stepper::order());
+#else
 #if B200_TSTOPS
     real dtmax = b200_min(b200_abs(P.dtmax), b200_abs(P.tstops[0] - P.t0));
 #else
     real dtmax = b200_min(b200_abs(P.dtmax), b200_abs(P.tf - P.t0));
 #endif
     P.dt0[i] = b200_initdt_one(u0, p, P.t0, dtmax, P.abstol, P.reltol, P.dtmin, B200Stepper::order());
+#endif
 }
 
 #if B200_ADAPTIVE
@@ -419,6 +444,9 @@ struct B200Traj {
     int retcode;
     bool accept, tstop_flag;
     real* row;                  // next row of us[idx][.][:] (running pointer: no 64-bit index arithmetic per row)
+#if B200_TSPANS
+    real t0, tf, dtmax;         // this trajectory's span and opts.dtmax (default tf - t0)
+#endif
 #if B200_TSTOPS
     real tstop;                 // first(opts.tstops)
     int tstop_idx;
@@ -490,14 +518,18 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     }
 #pragma unroll
     for (int c = 0; c < B200_NP; ++c) T.p[c] = P.p[idx * P.p_ts + c * P.p_cs];
-    T.t = P.t0; T.tprev = P.t0;
+#if B200_TSPANS
+    T.t0 = (real)P.tspans[2 * idx]; T.tf = (real)P.tspans[2 * idx + 1];
+    T.dtmax = P.dtmax_default ? (T.tf - T.t0) : P.dtmax;
+#endif
+    T.t = B200_T0; T.tprev = B200_T0;
     T.nf = 0;
 #if B200_IS_ROSENBROCK
     T.njacs = 0; T.nw = 0; T.nsolve = 0;
 #endif
     T.nsaved = 0; T.save_idx = 0;
 #if B200_EVERYSTEP
-    T.cap = 0; T.row = nullptr; T.trow = nullptr; T.drow = nullptr; T.last_t = P.t0;
+    T.cap = 0; T.row = nullptr; T.trow = nullptr; T.drow = nullptr; T.last_t = B200_T0;
     if (P.row_offsets != nullptr) {
         const long long o = P.row_offsets[idx];
         T.cap = (int)(P.row_offsets[idx + 1] - o);
@@ -526,6 +558,13 @@ B200_D void b200_traj_begin(const B200Params& P, long long idx, B200Traj& T) {
     T.rfpe_o = (real)1 / T.fpe_o;
 #endif
     T.next_save = (P.nsaveat > 0) ? P.saveat[0] : b200_inf();
+#if B200_TSPANS
+    // the shared list holds absolute times: this trajectory's grid is its part inside (t0_i, tf_i]
+    while (T.next_save <= T.t0) {
+        T.save_idx += 1;
+        T.next_save = (T.save_idx < P.nsaveat) ? P.saveat[T.save_idx] : b200_inf();
+    }
+#endif
 #if B200_TSTOPS
     T.tstop_idx = 0; T.tstop = P.tstops[0];
     T.disc_idx = 0;
@@ -582,9 +621,9 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     const real at = b200_abs(T.t), atf = b200_abs(tstop);
     const real tol100 = (real)100 * b200_eps_finite(at > atf ? at : atf);
 #else
-    const real tstop = P.tf;
-    const real dist = b200_abs(P.tf - T.t);
-    const real at = b200_abs(T.t), atf = b200_abs(P.tf);
+    const real tstop = B200_TF;
+    const real dist = b200_abs(B200_TF - T.t);
+    const real at = b200_abs(T.t), atf = b200_abs(B200_TF);
     // tstop tolerance 100*eps(max(|t|,|tf|)): a launch constant whenever |t0| <= |tf|
     const real tol100 = P.tol_const ? P.tol100_tf : (real)100 * b200_eps_finite(at > atf ? at : atf);
 #endif
@@ -633,7 +672,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
     }
 #endif
     // fix_dt_at_bounds!
-    T.dt = b200_min_c(P.dtmax, T.dt);
+    T.dt = b200_min_c(B200_DTMAX, T.dt);
     T.dt = b200_max_c(dtmin_t, T.dt);
     b200_modify_dt_for_tstops(P, T, dist, tol100);
     // ---- check_error ---- (flat predicates; the else-if order of the reference decides the code)
@@ -731,7 +770,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         const real dtnew = ctl.dtdiv;
         // calc_dt_propose!: eps at the NEW t
         const real eps_n = b200_eps_finite(T.t);
-        T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(P.dtmax), b200_abs(dtnew)));
+        T.dtpropose = b200_max_c(eps_n > P.dtmin ? eps_n : P.dtmin, b200_min_c(b200_abs(B200_DTMAX), b200_abs(dtnew)));
 #endif
         // handle_callbacks! -> savevalues!
 #if B200_CALLBACKS
@@ -766,13 +805,13 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
                     T.st.interp(th, T.dt, T.uprev, T.u, out);
                     b200_emit(P, idx, T, curt, out);
                 } else {
-                    if (curt == P.tf && !P.save_end) continue;   // skip_saveat_at_tspan_end
+                    if (curt == B200_TF && !P.save_end) continue;   // skip_saveat_at_tspan_end
                     b200_emit(P, idx, T, T.t, T.u);
                 }
             }
 #if B200_EVERYSTEP
             // save_everystep && (isempty(sol.t) || (t !== sol.t[end] || iszero(dt)) && (save_end || t !== tspan[2]))
-            if ((T.nsaved == 0 || ((T.t != T.last_t || T.dt == (real)0) && (P.save_end || T.t != P.tf))))
+            if ((T.nsaved == 0 || ((T.t != T.last_t || T.dt == (real)0) && (P.save_end || T.t != B200_TF))))
                 b200_emit(P, idx, T, T.t, T.u, dt_stages);
 #endif
         }
@@ -793,7 +832,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #endif
     }
     // while tdir*t < first_tstop
-    return !(T.t < P.tf);
+    return !(T.t < B200_TF);
 }
 
 // cold path (failed trajectories only): kept out of line so it costs the hot loop no registers
@@ -819,9 +858,9 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
 #if B200_EVERYSTEP
             const real last_t = T.last_t;
 #else
-            const real last_t = (T.save_idx > 0) ? P.saveat[T.save_idx - 1] : P.t0;
+            const real last_t = (T.save_idx > 0) ? P.saveat[T.save_idx - 1] : B200_T0;
 #endif
-            emit = (last_t != T.t) && (P.save_end == 2 || T.t == P.tf || P.nsaveat == 0);
+            emit = (last_t != T.t) && (P.save_end == 2 || T.t == B200_TF || P.nsaveat == 0);
         }
         if (emit) b200_emit(P, idx, T, T.t, T.u);
     }
@@ -1053,7 +1092,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
         bool live = idx < P.N;
         if (live) {
             b200_traj_begin(P, idx, T);
-            live = (T.t < P.tf);
+            live = (T.t < B200_TF);
             if (!live) b200_traj_end(P, idx, T);
         }
         for (;;) {
@@ -1122,7 +1161,7 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
                 pool_next += want;
             }
             // trajectories that are already finished at t0 >= tf
-            if (active && !(T.t < P.tf)) { b200_traj_end(P, idx, T); active = false; }
+            if (active && !(T.t < B200_TF)) { b200_traj_end(P, idx, T); active = false; }
         }
         const unsigned am = __ballot_sync(0xffffffffu, active);
         if (am == 0u) {

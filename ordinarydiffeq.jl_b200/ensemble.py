@@ -266,13 +266,15 @@ class TableProbFunc:
     Equivalent to `(prob, ctx) -> remake(prob; u0 = U0[ctx.sim_id], p = P[ctx.sim_id])` without
     a million host-side calls."""
 
-    def __init__(self, u0=None, p=None):
+    def __init__(self, u0=None, p=None, tspan=None):
         self.u0 = None if u0 is None else np.asarray(u0)
         self.p = None if p is None else np.asarray(p)
+        self.tspan = None if tspan is None else np.asarray(tspan, dtype=np.float64)     # (N, 2): remake(prob; tspan = ...)
 
     def __call__(self, prob, ctx):
         i = ctx.sim_id - 1
-        return remake(prob, u0=None if self.u0 is None else self.u0[i], p=None if self.p is None else self.p[i])
+        return remake(prob, u0=None if self.u0 is None else self.u0[i], p=None if self.p is None else self.p[i],
+                      tspan=None if self.tspan is None else tuple(self.tspan[i]))
 
 
 class EnsembleProblem:
@@ -349,7 +351,7 @@ class _LazySolutions:
             ts, us = [], []
             sel = (lambda v: v) if self.save_idxs is None else (lambda v: np.asarray(v)[self.save_idxs])
             if self.save_start:
-                ts.append(self.t0)
+                ts.append(self.t0 if np.ndim(self.t0) == 0 else self.t0[i])
                 us.append(sel(self.u0 if self.u0.ndim == 1 else self.u0[i]))
             if self.save_end:
                 ts.append(r["t_final"][i])
@@ -404,9 +406,11 @@ def _handle(device):
 
 
 def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True, callbacks=None,
-                vector_tol=False, smem_stages=False):
+                vector_tol=False, smem_stages=False, tspans=False):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
     extra = []
+    if tspans:
+        extra.append(_lib.OPT_TSPANS)
     if smem_stages:
         extra.append(_lib.OPT_SMEM_STAGES)
     if everystep:
@@ -430,25 +434,26 @@ def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, t
 
 
 def _harvest(eprob, I, repeat=1):
-    """Evaluate prob_func for sim_ids in I -> (u0 table or shared vector, p table or shared vector)."""
+    """Evaluate prob_func for sim_ids in I -> (u0 table or shared vector, p table or shared vector, per-trajectory
+    (t0, tf) table or None when every trajectory keeps the problem's tspan)."""
     prob, pf = eprob.prob, eprob.prob_func
     if pf is None:
-        return prob.u0, prob.p
+        return prob.u0, prob.p, None
     if isinstance(pf, TableProbFunc):
         idx = np.asarray(I) - 1
         u0 = prob.u0 if pf.u0 is None else pf.u0[idx]
         p = prob.p if pf.p is None else pf.p[idx]
-        return u0, p
-    u0s, ps = [], []
+        return u0, p, (None if pf.tspan is None else np.ascontiguousarray(pf.tspan[idx]))
+    u0s, ps, spans = [], [], []
     for i in I:
         q = pf(prob, EnsembleContext(int(i), repeat))
-        if tuple(q.tspan) != tuple(prob.tspan):
-            raise NotImplementedError("EnsembleB200: prob_func must not change tspan (all trajectories share it)")
+        spans.append((float(q.tspan[0]), float(q.tspan[1])))
         u0s.append(np.asarray(q.u0))
         ps.append(None if q.p is None else np.asarray(q.p))
     u0 = np.stack(u0s)
     p = None if ps[0] is None else np.stack(ps)
-    return u0, p
+    base = (float(prob.tspan[0]), float(prob.tspan[1]))
+    return u0, p, (None if all(sp == base for sp in spans) else np.array(spans, dtype=np.float64))
 
 
 def solve(eprob, alg, ensemblealg=None, **kw):
@@ -543,14 +548,31 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None or discs is not None, adaptive, cb_specs,
                           vector_tol, smem_stages)
 
-    def run(u0, p, ntraj, flags=0):
+    def run(u0, p, ntraj, flags=0, spans=None):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
                       dtmin=kw.get("dtmin"), dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"),
                       saveat=grid if grid else None, save_start=save_start, save_end=save_end,
                       flags=flags | cb_flags, tstops=tstops, d_discontinuities=discs)
+        if spans is None:
+            if ragged:
+                return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
+            return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
+        # prob_func changed tspan: every trajectory integrates over its own span (B200Problem.tspans).  The rows of
+        # different trajectories share no grid, so only final states (+ start / end rows) or the ragged output exist;
+        # a saveat list is taken as absolute times (each trajectory keeps the entries inside its span), a saveat step is not
+        # expressible as one list
+        if tstops is not None or discs is not None or cb_specs is not None:
+            raise NotImplementedError("per-trajectory tspan is not combined with tstops, d_discontinuities or callbacks")
+        sv = kw.get("saveat", None)
+        if sv is not None and not hasattr(sv, "__len__"):
+            raise NotImplementedError("per-trajectory tspan with saveat = step: pass the times as a list")
+        if grid and not ragged:
+            raise NotImplementedError("per-trajectory tspan with saveat needs the ragged output (save_everystep = true)")
+        prog_s = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, False, adaptive, None, vector_tol, False, True)
         if ragged:
-            return lowlevel.solve_host_everystep(program, u0, p, prob.tspan, **common)
-        return lowlevel.solve_host(program, u0, p, prob.tspan, **common)
+            common["saveat"] = None if sv is None or len(sv) == 0 else sorted(float(x) for x in sv)
+            return lowlevel.solve_host_everystep(prog_s, u0, p, spans, **common)
+        return lowlevel.solve_host(prog_s, u0, p, spans, **common)
 
     tol_kw = dict(reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"), dtmin=kw.get("dtmin"),
                   dtmax=kw.get("dtmax"), maxiters=kw.get("maxiters"))
@@ -572,15 +594,16 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     all_arrays = []
     for b0 in range(0, N, max(batch_size, 1)):
         I = np.arange(b0 + 1, min(b0 + batch_size, N) + 1)
-        u0, p = _harvest(eprob, I)
-        res = run(u0, p, len(I), kw.get("flags", 0))
+        u0, p, spans = _harvest(eprob, I)
+        res = run(u0, p, len(I), kw.get("flags", 0), spans)
         all_arrays.append(res)
-        mk = lambda r, u0_, p_=None: _LazySolutions(r, prob.tspan[0], alg, bool(grid), np.asarray(u0_),
-                                                    save_start, save_end is None or save_end,
-                                                    dense=dense_of(u0_, p_) if dense_ok else None,
-                                                    save_idxs=save_idxs)
-        batches_in.append((u0, p, len(I)))
-        sols = mk(res, u0, p)
+        mk = lambda r, u0_, p_=None, sp_=None: _LazySolutions(r, prob.tspan[0] if sp_ is None else sp_[:, 0], alg,
+                                                              bool(grid) and sp_ is None, np.asarray(u0_),
+                                                              save_start, save_end is None or save_end,
+                                                              dense=dense_of(u0_, p_) if (dense_ok and sp_ is None) else None,
+                                                              save_idxs=save_idxs)
+        batches_in.append((u0, p, len(I)) if spans is None else (u0, p, len(I), spans))
+        sols = mk(res, u0, p, spans)
         if output_func is None:
             batch = sols
         else:
@@ -591,9 +614,9 @@ def solve(eprob, alg, ensemblealg=None, **kw):
                 while rerun:
                     # re-solve this trajectory alone with repeat+1 (the driver's rerun loop)
                     repeat += 1
-                    u0r, pr = _harvest(eprob, [int(i)], repeat)
-                    r1 = run(u0r, pr, 1)
-                    out, rerun = output_func(mk(r1, u0r, pr)[0], EnsembleContext(int(i), repeat))
+                    u0r, pr, spr = _harvest(eprob, [int(i)], repeat)
+                    r1 = run(u0r, pr, 1, 0, spr)
+                    out, rerun = output_func(mk(r1, u0r, pr, spr)[0], EnsembleContext(int(i), repeat))
                 batch.append(out)
         if reduction is None:
             if isinstance(u_acc, list) and not u_acc and output_func is None and b0 + batch_size >= N and b0 == 0:
@@ -606,7 +629,7 @@ def solve(eprob, alg, ensemblealg=None, **kw):
                 break
     elapsed = time.perf_counter() - t_start
     dense_all = None
-    if dense_ok and reduction is None and output_func is None:
+    if dense_ok and reduction is None and output_func is None and all(len(b) == 3 for b in batches_in):
         def dense_all(tq):
             return np.concatenate([lowlevel.solve_host_dense(program, u0_, p_, prob.tspan, tq, trajectories=cnt, **tol_kw)["dense"]
                                    for (u0_, p_, cnt) in batches_in])

@@ -46,6 +46,7 @@ struct B200Problem
     u0::Ptr{Cvoid}; u0_shared::Int32
     p::Ptr{Cvoid}; p_shared::Int32
     t0::Float64; tf::Float64
+    tspans::Ptr{Float64}           # C_NULL, or (t0_i, tf_i) pairs: a prob_func that remakes tspan (B200ODE_OPT_TSPANS programs)
 end
 struct B200Opts
     reltol::Float64; abstol::Float64; dt::Float64; dtmin::Float64; dtmax::Float64
@@ -261,24 +262,30 @@ const ALLOWED = (:trajectories, :batch_size, :saveat, :save_start, :save_end, :s
                  :dt, :dtmin, :dtmax, :maxiters, :adaptive, :dense, :verbose, :progress, :callback)
 
 # One batch of trajectories I (global sim ids) with repeat counters `rep`: harvest prob_func, solve, wrap.
-function solve_ids(eprob, prob, alg, ens, h, prog, multi, opts, grid, tstops, everystep, idxs, w, n, np, T, t0, tf, I, rep)
+function solve_ids(eprob, prob, alg, ens, h, prog, multi, opts, grid, tstops, everystep, idxs, w, n, np, T, t0, tf, I, rep, tspans_variant = false)
     N = length(I)
     U0 = Matrix{T}(undef, n, N); P = Matrix{T}(undef, max(np, 1), N)
+    spans = Matrix{Float64}(undef, 2, N)
     for (k, i) in enumerate(I)
         q = eprob.prob_func(prob, SciMLBase.EnsembleContext(i, rep[k], nothing))
-        q.tspan == prob.tspan || throw(ArgumentError("EnsembleB200: prob_func must keep tspan (all trajectories share it)"))
+        spans[1, k], spans[2, k] = q.tspan
         U0[:, k] .= q.u0
         np > 0 && (P[:, k] .= q.p)
     end
-    cprob = B200Problem(N, pointer(U0), 0, pointer(P), 0, t0, tf)
+    # a prob_func that changes tspan: the program must be the per-trajectory-span variant (chosen by __solve from
+    # trajectory 1; a prob_func that changes tspan for some trajectories only is not served)
+    varying = any(spans[1, k] != t0 || spans[2, k] != tf for k in 1:N)
+    varying && !tspans_variant && throw(ArgumentError("EnsembleB200: prob_func changes tspan for some trajectories but not for trajectory 1"))
+    cprob = B200Problem(N, pointer(U0), 0, pointer(P), 0, t0, tf, tspans_variant ? pointer(spans) : Ptr{Float64}(C_NULL))
     nslots = ccall((:b200ode_nslots, LIB), Cint, (Ref{B200Problem}, Ref{B200Opts}), cprob, opts)
+    tspans_variant && (nslots = 0)      # no rectangular rows with per-trajectory spans: [t0_i, tf_i] / [u0_i, u(tf_i)] are built below
     uf = Matrix{T}(undef, n, N); tfin = Vector{Float64}(undef, N)
     us = Array{T, 3}(undef, w, max(nslots, 1), N); ts = Vector{Float64}(undef, max(nslots, 1))
     cnt = [zeros(Int32, N) for _ in 1:8]
     res = B200Result(pointer(uf), pointer(tfin), nslots > 0 ? pointer(us) : C_NULL, pointer(ts),
                      pointer.(cnt)..., 0.0, 0.0)
     rag = Ref(B200Ragged(0, C_NULL, C_NULL, C_NULL))
-    GC.@preserve U0 P grid tstops uf tfin us ts cnt begin
+    GC.@preserve U0 P spans grid tstops uf tfin us ts cnt begin
         with_pinned(us, uf) do
             if everystep     # ragged rows: trajectory k owns rows offs[k]+1 : offs[k+1]  (single device)
                 check(ccall((:b200ode_solve_everystep, LIB), Cint,
@@ -313,7 +320,7 @@ function solve_ids(eprob, prob, alg, ens, h, prog, multi, opts, grid, tstops, ev
             tk = ts[1:nsaved[k]]; uk = [SVector{w, T}(@view us[:, s, k]) for s in 1:nsaved[k]]
         else    # no saveat grid, save_everystep = false: the start and/or end point, as save_start / save_end say
             tk = Float64[]; uk = SVector{w, T}[]
-            ss && (push!(tk, t0); push!(uk, SVector{w, T}(sel(@view U0[:, k]))))
+            ss && (push!(tk, tspans_variant ? spans[1, k] : t0); push!(uk, SVector{w, T}(sel(@view U0[:, k]))))
             se && (push!(tk, tfin[k]); push!(uk, SVector{w, T}(sel(@view uf[:, k]))))
         end
         stats = SciMLBase.DEStats(Int(nf[k]), 0, 0, Int(nw[k]), Int(nsolve[k]), Int(njacs[k]), 0, 0, 0, 0,
@@ -368,6 +375,15 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     rtv = rtol isa AbstractVector ? collect(Float64, rtol) : Float64[]
     atv = atol isa AbstractVector ? collect(Float64, atol) : Float64[]
     (isempty(rtv) && isempty(atv)) || push!(extra, "-DB200_VECTOR_TOL=1")
+    # prob_func remakes tspan (probed on trajectory 1): per-trajectory spans — final states or the ragged output only
+    tspans_variant = eprob.prob_func(prob, SciMLBase.EnsembleContext(1, 1, nothing)).tspan != prob.tspan
+    if tspans_variant
+        (isempty(tstops) && isempty(discs) && isempty(cbs)) ||
+            throw(ArgumentError("EnsembleB200: per-trajectory tspan is not combined with tstops, d_discontinuities or callbacks"))
+        (everystep || isempty(saveat)) ||
+            throw(ArgumentError("EnsembleB200: per-trajectory tspan with saveat needs save_everystep = true (ragged output)"))
+        push!(extra, "-DB200_TSPANS=1")
+    end
     # Vern7 on a wide state with nothing but start / end rows: the kernel that keeps k1..k10 in shared memory
     # (B200ODE_OPT_SMEM_STAGES; bit-identical results, it serves no interior saveat rows and no callbacks)
     if alg isa Vern7 && n >= 24 && !everystep && isempty(cbs)       # measured crossover: scripts/time_wide_threshold.py
@@ -402,7 +418,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
         # served batch-wise: everything flagged is re-submitted to the GPU together until nothing is flagged
         while !isempty(pending)
             sols = solve_ids(eprob, prob, alg, ens, h, prog, multi, opts, grid, tstops, everystep, idxs, w, n, np, T, t0, tf,
-                             I[pending], rep[pending])
+                             I[pending], rep[pending], tspans_variant)
             again = Int[]
             for (j, pos) in enumerate(pending)
                 out, rerun = eprob.output_func(sols[j], SciMLBase.EnsembleContext(I[pos], rep[pos], nothing))

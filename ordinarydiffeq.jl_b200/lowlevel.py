@@ -16,6 +16,16 @@ def _np_real(dtype):
     return np.float32 if dtype == _lib.F32 else np.float64
 
 
+def _per_trajectory_spans(tspan):
+    """None for a shared (t0, tf); the contiguous float64 (N, 2) array when tspan holds one span per trajectory."""
+    a = np.asarray(tspan, dtype=np.float64)
+    if a.ndim == 1:
+        return None
+    if a.ndim != 2 or a.shape[1] != 2:
+        raise ValueError("tspan must be (t0, tf) or an (N, 2) array of per-trajectory spans")
+    return np.ascontiguousarray(a)
+
+
 def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None,
                maxiters=None, saveat=None, save_start=None, save_end=None, flags=0, out=None, _meanvar=None, tstops=None, _mean=None,
                d_discontinuities=None):
@@ -35,11 +45,14 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     else:
         p_arr = np.ascontiguousarray(p, dtype=rdt)
         p_shared = (p_arr.ndim == 1)
+    tspans = _per_trajectory_spans(tspan)       # (N, 2) array: every trajectory its own (t0_i, tf_i)
     if trajectories is None:
         if not u0_shared:
             trajectories = u0.shape[0]
         elif p_arr is not None and not p_shared:
             trajectories = p_arr.shape[0]
+        elif tspans is not None:
+            trajectories = tspans.shape[0]
         else:
             raise ValueError("trajectories must be given when both u0 and p are shared")
     N = int(trajectories)
@@ -48,7 +61,9 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     if npar > 0:
         if p_arr is None or p_arr.shape[-1] != npar or (not p_shared and p_arr.shape[0] != N):
             raise ValueError("p has wrong shape for np=%d" % npar)
-    t0, tf = float(tspan[0]), float(tspan[1])
+    if tspans is not None and tspans.shape[0] != N:
+        raise ValueError("tspan has %d rows for %d trajectories" % (tspans.shape[0], N))
+    t0, tf = (float(tspan[0]), float(tspan[1])) if tspans is None else (float(tspans[:, 0].min()), float(tspans[:, 1].max()))
     opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops, d_discontinuities)
     prob = _lib.B200Problem()
     prob.trajectories = N
@@ -57,12 +72,15 @@ def solve_host(program, u0, p, tspan, trajectories=None, reltol=None, abstol=Non
     prob.p = p_arr.ctypes.data if p_arr is not None else None
     prob.p_shared = int(p_shared)
     prob.t0, prob.tf = t0, tf
+    prob.tspans = tspans.ctypes.data if tspans is not None else None
     if getattr(program, "multi", False):
         # (a MultiProgram holds one program per device; the F64 rule differs from the F32 one only for grid points
         # within a float ulp of tf)
         nslots = L.b200ode_nslots(C.byref(prob), C.byref(opts))
     else:
         nslots = L.b200ode_nslots_program(program._p, C.byref(prob), C.byref(opts))
+    if tspans is not None:
+        nslots = 0          # per-trajectory spans: no rectangular rows (final states and statistics only; rows via the ragged output)
     out = {} if out is None else out
 
     def buf(name, shape, dtype):
@@ -111,11 +129,14 @@ def _marshal_ragged(program, u0, p, tspan, trajectories):
     u0_shared = (u0.ndim == 1)
     p_arr = None if p is None else np.ascontiguousarray(p, dtype=rdt)
     p_shared = True if p_arr is None else (p_arr.ndim == 1)
+    tspans = _per_trajectory_spans(tspan)
     if trajectories is None:
         if not u0_shared:
             trajectories = u0.shape[0]
         elif p_arr is not None and not p_shared:
             trajectories = p_arr.shape[0]
+        elif tspans is not None:
+            trajectories = tspans.shape[0]
         else:
             raise ValueError("trajectories must be given when both u0 and p are shared")
     N = int(trajectories)
@@ -123,11 +144,17 @@ def _marshal_ragged(program, u0, p, tspan, trajectories):
         raise ValueError("u0 has shape %s, expected (%d, %d) or (%d,)" % (u0.shape, N, n, n))
     if npar > 0 and (p_arr is None or p_arr.shape[-1] != npar or (not p_shared and p_arr.shape[0] != N)):
         raise ValueError("p has wrong shape for np=%d" % npar)
+    if tspans is not None and tspans.shape[0] != N:
+        raise ValueError("tspan has %d rows for %d trajectories" % (tspans.shape[0], N))
     prob = _lib.B200Problem()
     prob.trajectories = N
     prob.u0 = u0.ctypes.data; prob.u0_shared = int(u0_shared)
     prob.p = p_arr.ctypes.data if p_arr is not None else None; prob.p_shared = int(p_shared)
-    prob.t0, prob.tf = float(tspan[0]), float(tspan[1])
+    if tspans is None:
+        prob.t0, prob.tf = float(tspan[0]), float(tspan[1])
+    else:
+        prob.t0, prob.tf = float(tspans[:, 0].min()), float(tspans[:, 1].max())
+        prob.tspans = tspans.ctypes.data
     out = {"u_final": np.empty((N, n), dtype=rdt), "t_final": np.empty((N,), dtype=np.float64)}
     res = _lib.B200Result()
     res.u_final = out["u_final"].ctypes.data
@@ -135,7 +162,7 @@ def _marshal_ragged(program, u0, p, tspan, trajectories):
     for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         out[name] = np.empty((N,), dtype=np.int32)
         setattr(res, name, out[name].ctypes.data)
-    return N, n, rdt, prob, res, out, (u0, p_arr)
+    return N, n, rdt, prob, res, out, (u0, p_arr, tspans)
 
 
 def solve_host_dense(program, u0, p, tspan, tq, trajectories=None, reltol=None, abstol=None, dt=None, dtmin=None,

@@ -328,6 +328,35 @@ def test_high_level_solve_api(pkg, oracle):
     assert abs(float(s5[3].u[-1].sum()) - 1.0) < 1e-9
 
 
+def test_high_level_solve_with_prob_func_changing_tspan(pkg, oracle):
+    """solve(EnsembleProblem(prob; prob_func = (prob, ctx) -> remake(prob; p = ..., tspan = ...)), ...): every trajectory
+    is solved over its own span — as a closure, as a table, with final states only and with the default (every step) rows."""
+    P = pkg
+    pl = P.problems_library
+    N = 200
+    table = pl.lorenz_params(N)
+    idx = np.arange(N, dtype=np.uint64)
+    spans = np.stack([0.5 * pl.splitmix64_uniform(idx, 1), 1.0 + 4.0 * pl.splitmix64_uniform(idx, 2)], axis=1)
+    prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (0.0, 10.0), table[0])
+    ep1 = P.EnsembleProblem(prob, prob_func=lambda pr, ctx: P.remake(pr, p=table[ctx.sim_id - 1], tspan=tuple(spans[ctx.sim_id - 1])))
+    ep2 = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table, tspan=spans))
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, spans, 3, 3)
+    for ep in (ep1, ep2):
+        s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, save_everystep=False)
+        for i in (0, 7, N - 1):
+            assert s[i].retcode == "Success" and list(s[i].t) == [spans[i, 0], spans[i, 1]]
+            assert np.array_equal(bits(np.ascontiguousarray(s[i].u[-1])), bits(o["u_final"][i]))
+            assert s[i].stats.naccept == o["naccept"][i]
+    orag = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, spans, 3, 3, save_everystep=True)
+    s = P.solve(ep2, P.Tsit5(), P.EnsembleB200(), trajectories=N)          # default: every step
+    for i in (0, 7, N - 1):
+        a, b = orag["row_offsets"][i], orag["row_offsets"][i + 1]
+        assert np.array_equal(np.asarray(s[i].t), orag["ts"][a:b]) and s[i].t[0] == spans[i, 0] and s[i].t[-1] == spans[i, 1]
+        assert np.array_equal(bits(np.ascontiguousarray(s[i].u)), bits(orag["us"][a:b]))
+    with pytest.raises(NotImplementedError):
+        P.solve(ep2, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.1)
+
+
 def test_timeseries_meanvar_on_device(pkg, progs, oracle):
     """EnsembleAnalysis.timeseries_steps_meanvar evaluated on the device
     (reference: lib/DiffEqBase/test/downstream/ensemble_analysis.jl:12-33, m ≈ m2, v ≈ v4)."""
@@ -1112,6 +1141,63 @@ def test_d_discontinuities(pkg, handle, oracle, f32):
     try:
         with pytest.raises(pkg._lib.B200Error):
             pkg.lowlevel.solve_host(prog, u0, p, tspan, d_discontinuities=[1.0])
+    finally:
+        prog.close()
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_per_trajectory_tspans(pkg, handle, oracle, f32):
+    """B200Problem.tspans (program option B200ODE_OPT_TSPANS): every trajectory integrates over its own (t0_i, tf_i) — what
+    a prob_func that remakes tspan produces.  Final states and statistics through b200ode_solve, rows through the ragged
+    output (with a saveat list cut per trajectory); Tsit5, Vern7, Rodas5P; bit-exact against the oracle, whose per-trajectory
+    form equals one-trajectory solves (tests/test_oracle_properties.py)."""
+    pl = pkg.problems_library
+    N = 500
+    rdt = np.float32 if f32 else np.float64
+    idx = np.arange(N, dtype=np.uint64)
+    t0 = -1.0 + 2.0 * pl.splitmix64_uniform(idx, 1)
+    spans = np.stack([t0, t0 + 0.25 + 6.0 * pl.splitmix64_uniform(idx, 2)], axis=1)
+    dtype = pkg.F32 if f32 else pkg.F64
+    u0 = U0.astype(rdt)
+    for alg, oalg, problem in ((pkg.ALG_TSIT5, oracle.ALG_TSIT5, "lorenz"), (pkg.ALG_VERN7, oracle.ALG_VERN7, "lorenz"),
+                               (pkg.ALG_RODAS5P, oracle.ALG_RODAS5P, "robertson")):
+        if problem == "lorenz":
+            src = pl.lorenz_source(f32); p = pl.lorenz_params(N, f32=f32); okw = {}
+            csrc = (src[0], src[1])
+            sp = spans
+        else:
+            src, j, tg = pl.robertson_sources(f32); p = pl.robertson_params(N, f32=f32); okw = dict(jac=j, tgrad=tg)
+            csrc = (src[0], src[1], j[0], j[1], tg[0], tg[1])
+            sp = np.stack([np.zeros(N), 10.0 ** (1.0 + 3.0 * pl.splitmix64_uniform(idx, 3))], axis=1)
+        prog = handle.compile(alg, dtype, 3, 3, *csrc, extra_options=pkg._lib.OPT_TSPANS)
+        try:
+            for kw in ({}, {"reltol": 1e-5, "abstol": 1e-7} if not f32 else {"dt": 0.01}, {"dtmax": 0.3} if problem == "lorenz" else {"maxiters": 60}):
+                g = pkg.lowlevel.solve_host(prog, u0, p, sp, **kw)
+                o = oracle.solve(oalg, src, u0, p, sp, 3, 3, f32=f32, **dict(kw, **okw))
+                assert_same_result(g, o)
+                if "maxiters" not in kw:
+                    assert np.array_equal(g["t_final"], sp[:, 1].astype(rdt).astype(np.float64))
+            # a shared tspan is refused by such a program, and the rectangular rows are refused with spans
+            with pytest.raises(pkg._lib.B200Error):
+                pkg.lowlevel.solve_host(prog, u0, p, (0.0, 1.0))
+        finally:
+            prog.close()
+    # ragged rows, with a saveat list that every trajectory cuts to its own span
+    src = pl.lorenz_source(f32); p = pl.lorenz_params(N, f32=f32)
+    prog = handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, src[0], src[1], extra_options=pkg._lib.OPT_TSPANS + " " + pkg._lib.OPT_EVERYSTEP)
+    try:
+        for kw in ({}, {"saveat": [-0.5, 0.0, 0.5, 1.0, 2.0, 4.0]}, {"saveat": [0.25, 3.0], "save_start": False}):
+            g = pkg.lowlevel.solve_host_everystep(prog, u0, p, spans, **kw)
+            o = oracle.solve(oracle.ALG_TSIT5, src, u0, p, spans, 3, 3, f32=f32, save_everystep=True, **kw)
+            assert np.array_equal(g["row_offsets"], o["row_offsets"]) and np.array_equal(g["ts"], o["ts"])
+            assert np.array_equal(bits(g["us"]), bits(o["us"]))
+            assert np.array_equal(bits(g["u_final"]), bits(o["u_final"]))
+    finally:
+        prog.close()
+    prog = handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, src[0], src[1])
+    try:
+        with pytest.raises(pkg._lib.B200Error):
+            pkg.lowlevel.solve_host(prog, u0, p, spans)
     finally:
         prog.close()
 

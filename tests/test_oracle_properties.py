@@ -938,3 +938,28 @@ def test_d_discontinuities_known_answers():
     o4 = oracle.solve(oracle.ALG_TSIT5, src0, np.array([0.0]), None, (0.0, 5.0), 1, 0, **kw)
     assert abs(o3["u_final"][0, 0] - 5.0) < 1e-10 and abs(o4["u_final"][0, 0] - 5.0) < 1e-10
     assert o3["nf"][0] < o4["nf"][0] // 2        # f(u0, t0) = 0 seeds a hopeless first step without the shift
+
+
+def test_per_trajectory_tspans_equal_separate_solves(pkg):
+    """A prob_func that remakes the problem with its own tspan makes every trajectory an independent solve over its own
+    span (lib/DiffEqBase/test/downstream/ensemble.jl builds such ensembles with remake): the oracle's per-trajectory form
+    equals one-trajectory solves, including the default dtmax = tf_i - t0_i and a saveat list cut to (t0_i, tf_i]."""
+    pl = pkg.problems_library
+    N = 7
+    p = pl.lorenz_params(N)
+    u0 = np.array([1.0, 0.0, 0.0])
+    spans = np.array([[0.0, 1.0], [0.5, 2.0], [-1.0, 0.25], [0.0, 10.0], [2.0, 2.5], [0.0, 1.0], [3.0, 3.5]])
+    src = pl.lorenz_source()
+    o = oracle.solve(oracle.ALG_TSIT5, src, u0, p, spans, 3, 3)
+    assert o["us"] is None and np.array_equal(o["t_final"], spans[:, 1])
+    grid = [0.25, 0.5, 1.0, 2.0, 2.25]
+    orag = oracle.solve(oracle.ALG_TSIT5, src, u0, p, spans, 3, 3, save_everystep=True, saveat=grid)
+    for i in range(N):
+        oi = oracle.solve(oracle.ALG_TSIT5, src, u0, p[i:i + 1], tuple(spans[i]), 3, 3)
+        for k in ("naccept", "nreject", "nf", "retcode"):
+            assert o[k][i] == oi[k][0], (k, i)
+        assert np.array_equal(bits(o["u_final"][i]), bits(oi["u_final"][0]))
+        gi = [g for g in grid if spans[i, 0] < g <= spans[i, 1]]
+        ri = oracle.solve(oracle.ALG_TSIT5, src, u0, p[i:i + 1], tuple(spans[i]), 3, 3, save_everystep=True, saveat=gi or None)
+        a, b = orag["row_offsets"][i], orag["row_offsets"][i + 1]
+        assert np.array_equal(orag["ts"][a:b], ri["ts"]) and np.array_equal(bits(orag["us"][a:b]), bits(ri["us"]))
