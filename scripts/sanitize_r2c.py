@@ -38,4 +38,22 @@ for alg in (pkg.ALG_ROSENBROCK23, pkg.ALG_RODAS5P, pkg.ALG_RODAS4, pkg.ALG_ROSEN
     prog = h.compile(alg, pkg.F64, 3, 3, rr[0], rr[1], jj[0], jj[1], tt[0], tt[1])
     g = ll.solve_host(prog, U0, k, (0.0, 100.0), saveat=[10.0, 50.0], reltol=1e-6, abstol=1e-8, maxiters=2000)
     print("rosenbrock", alg, np.bincount(g["retcode"]))
+# d_discontinuities, per-trajectory spans (final states + ragged rows), the lazily built no-saveat variant, shrunken CTAs
+fs = ("void forced(double* du, const double* u, const double* p, const double t) { du[0] = -p[0] * u[0] + (t > 1.0 ? p[1] : 0.0); du[1] = u[0] - u[1]; }\n", "forced")
+fp = np.stack([0.5 + pl.splitmix64_uniform(np.arange(333, dtype=np.uint64), 0), 1.0 + pl.splitmix64_uniform(np.arange(333, dtype=np.uint64), 1)], axis=1)
+prog = h.compile(pkg.ALG_TSIT5, pkg.F64, 2, 2, fs[0], fs[1], extra_options=pkg._lib.OPT_TSTOPS)
+g = ll.solve_host(prog, np.array([1.0, 0.0]), fp, (0.0, 3.0), d_discontinuities=[0.0, 1.0], saveat=[0.5, 1.0, 2.0], tstops=[2.5])
+print("d_discontinuities", np.bincount(g["retcode"]), int(g["nsaved"].sum()))
+spans = np.stack([np.zeros(700), 0.5 + 2.0 * pl.splitmix64_uniform(np.arange(700, dtype=np.uint64), 3)], axis=1)
+prog = h.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, s, nm, extra_options=pkg._lib.OPT_TSPANS)
+g = ll.solve_host(prog, U0, lp, spans)
+print("tspans final", np.bincount(g["retcode"]))
+prog = h.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, s, nm, extra_options=pkg._lib.OPT_TSPANS + " " + pkg._lib.OPT_EVERYSTEP)
+g = ll.solve_host_everystep(prog, U0, lp, spans, saveat=[0.25, 1.0, 2.0])
+print("tspans ragged", int(g["row_offsets"][-1]))
+prog = h.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, s, nm)
+for N in (1, 33, 700):      # no saveat: the second build; few trajectories: CTAs of 32..64 threads
+    g = ll.solve_host(prog, U0, lp[:N], (0.0, 2.0), save_start=False)
+    g = ll.solve_host(prog, U0, lp[:N], (0.0, 2.0), saveat=[1.0, 2.0])
+    print("nosave variant / small CTAs", N, np.bincount(g["retcode"]))
 print("done")
