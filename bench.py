@@ -250,8 +250,8 @@ class DeviceRun:
             self.bufs.p.copy_(torch.from_numpy(np.ascontiguousarray(self.p)))
         self.kw = dict(saveat=self.grid, **w["tol"])
 
-    def step(self):
-        self.pkg.lowlevel.solve_device(self.prog, self.bufs, self.w["tspan"], **self.kw)
+    def step(self, first=0, count=None):
+        self.pkg.lowlevel.solve_device(self.prog, self.bufs, self.w["tspan"], first=first, count=count, **self.kw)
 
     def timed(self, steps, warmup, barrier):
         torch = self.torch
@@ -462,27 +462,65 @@ def sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barri
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     mean = None
 
+    # Pipelined exchange: the rank's shard is integrated in `groups` launches of whole rounds; the all-gathers of a
+    # finished group run on a second stream while the next group integrates (the gather writes disjoint slices of
+    # `full`, the kernels read and write disjoint rows of the shard), so only the last group's exchange is exposed.
+    rounds = (N // (world * block)) if in_place else 0
+    groups = 4 if (in_place and rounds >= 8 and rounds % 4 == 0) else 1
+    peer = None
+    if groups > 1 and os.environ.get("B200_SWEEP_GATHER", "peer") == "peer":
+        try:            # push over NVLink peer memory with the copy engines (distributed.PeerGather); NCCL otherwise
+            peer = d.PeerGather(N, (3,), torch.float64, dev, block)
+            full = peer.full
+        except Exception as e:      # symmetric memory not available on this box / build
+            sys.stderr.write("bench: PeerGather unavailable (%s: %s); NCCL all-gather after the integration\n" % (type(e).__name__, e))
+            peer = None
+    if peer is None:
+        groups = 1
+    gev = [torch.cuda.Event() for _ in range(groups)]
+
     def step(i=None):
         nonlocal mean
         if i is not None:
             ev[i][0].record()
-        run.step()
-        ll.reduce_sum_device(h, pkg.F64, run.bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
-        if i is not None:
-            ev[i][1].record()
-        if world > 1:
-            if in_place:
-                d.gather_in_place(run.bufs.u_final, N, block, out=full)
-            else:
-                full.copy_(d.gather_in_order(run.bufs.u_final, N, block=block))
-            mean = d.allreduce_mean(part, N)
+        if peer is not None:
+            cur = torch.cuda.current_stream()
+            rpg = rounds // groups
+            peer.begin(cur)
+            for g in range(groups):
+                run.step(first=g * rpg * block, count=rpg * block)
+                gev[g].record(cur)
+                peer.push(run.bufs.u_final, g * rpg, (g + 1) * rpg, gev[g])
+            ll.reduce_sum_device(h, pkg.F64, run.bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
+            if i is not None:
+                ev[i][1].record()
+            peer.finish(cur)
+            mean = d.allreduce_mean(part, N)        # also the barrier after which every rank's `full` is complete
         else:
-            mean = part / float(N)
+            run.step()
+            ll.reduce_sum_device(h, pkg.F64, run.bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
+            if i is not None:
+                ev[i][1].record()
+            if world > 1:
+                if in_place:
+                    d.gather_in_place(run.bufs.u_final, N, block, out=full)
+                else:
+                    full.copy_(d.gather_in_order(run.bufs.u_final, N, block=block))
+                mean = d.allreduce_mean(part, N)
+            else:
+                mean = part / float(N)
         if i is not None:
             ev[i][2].record()
     for _ in range(3):
         step()
     barrier()
+    if peer is not None:        # the pushed result equals NCCL's ordered all-gather, bit for bit (checked outside the timed region)
+        torch.cuda.synchronize()
+        ref = d.gather_in_place(run.bufs.u_final, N, block)
+        torch.cuda.synchronize()
+        assert torch.equal(ref, full), "PeerGather result differs from the NCCL all-gather"
+        del ref
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -510,6 +548,11 @@ def sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barri
            "trajectories_total": N, "trajectories_per_gpu": m, "steps": steps, "ms_per_step": ms / steps,
            "partition": "interleaved blocks of %d trajectories (block b -> rank b %% N)" % block,
            "collectives": "none (single GPU)" if world == 1 else
+                          ("push over NVLink peer memory: every rank copies each finished block of its shard into its final place "
+                           "in every rank's result (symmetric memory, device-to-peer cudaMemcpyAsync on the copy engines, %d blocks x "
+                           "%d peers per step) while the next of %d groups of rounds integrates; equal to the NCCL all-gather bit for bit "
+                           "(asserted before timing); + ncclAllReduce of the partial sums, which also closes the step across ranks. "
+                           "collective_ms = what remains exposed after the last kernel" % (rounds, world, groups)) if peer is not None else
                           "%d x ncclAllGather of the final states written in place (no un-interleave copy) + ncclAllReduce of the "
                           "partial sums, over NVLink" % (N // (world * block) if in_place else 1),
            "kernel_ms_per_rank": {"min": min(kms), "max": max(kms), "all": kms},

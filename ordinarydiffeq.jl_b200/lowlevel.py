@@ -262,21 +262,34 @@ class DeviceBuffers:
 
 
 def solve_device(program, bufs, tspan, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None,
-                 saveat=None, save_start=None, save_end=None, flags=0, stream=None, tstops=None, d_discontinuities=None):
-    """Launch the ensemble on buffers already in HBM (b200ode_solve_device); asynchronous."""
+                 saveat=None, save_start=None, save_end=None, flags=0, stream=None, tstops=None, d_discontinuities=None,
+                 first=0, count=None):
+    """Launch the ensemble on buffers already in HBM (b200ode_solve_device); asynchronous.
+    first / count: only trajectories first .. first+count-1 of the buffers (array-of-structures layout) — lets a caller
+    split one ensemble into several launches, e.g. to overlap a collective on the finished part with the rest."""
     L = _lib.lib()
     opts, keep = _lib.make_opts(reltol, abstol, dt, dtmin, dtmax, maxiters, saveat, save_start, save_end, flags, tstops, d_discontinuities)
+    first = int(first)
+    count = bufs.N - first if count is None else int(count)
+    if first != 0 or count != bufs.N:
+        if bufs.layout != _lib.LAYOUT_AOS:
+            raise ValueError("a sub-range launch needs the array-of-structures layout")
+        if first < 0 or count < 0 or first + count > bufs.N:
+            raise ValueError("sub-range outside the buffers")
+
+    def row(t, shared=False):      # device address of row `first`
+        return t.data_ptr() if (shared or first == 0) else t[first:].data_ptr()
     dp = _lib.B200DeviceProblem()
-    dp.trajectories = bufs.N
-    dp.u0 = bufs.u0.data_ptr(); dp.u0_shared = int(bufs.u0_shared); dp.u0_layout = bufs.layout
-    dp.p = bufs.p.data_ptr(); dp.p_shared = int(bufs.p_shared); dp.p_layout = bufs.layout
+    dp.trajectories = count
+    dp.u0 = row(bufs.u0, bufs.u0_shared); dp.u0_shared = int(bufs.u0_shared); dp.u0_layout = bufs.layout
+    dp.p = row(bufs.p, bufs.p_shared); dp.p_shared = int(bufs.p_shared); dp.p_layout = bufs.layout
     dp.t0, dp.tf = float(tspan[0]), float(tspan[1])
     dr = _lib.B200DeviceResult()
-    dr.u_final = bufs.u_final.data_ptr(); dr.u_final_layout = bufs.layout
-    dr.t_final = bufs.t_final.data_ptr()
-    dr.us = bufs.us.data_ptr() if bufs.us is not None else None
+    dr.u_final = row(bufs.u_final); dr.u_final_layout = bufs.layout
+    dr.t_final = row(bufs.t_final)
+    dr.us = row(bufs.us) if bufs.us is not None else None
     for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
-        setattr(dr, name, getattr(bufs, name).data_ptr())
+        setattr(dr, name, row(getattr(bufs, name)))
     if stream is None:
         import torch
         stream = torch.cuda.current_stream().cuda_stream

@@ -50,8 +50,31 @@ def _rank_main(rank, world, port, N, q):
     steps = d.gather_in_order((bufs.naccept + bufs.nreject).to(torch.int32), N)
     mean = d.allreduce_mean(part, N)
     torch.cuda.synchronize()
+    # the push over NVLink peer memory (PeerGather: sub-range launches + device-to-peer copies on per-peer streams, closed by
+    # the all-reduce) must give the same array as NCCL's gather; "unavailable" when symmetric memory cannot be set up
+    peer_ok = "n/a"
+    if N % (world * 1024) == 0:
+        try:
+            pg = d.PeerGather(N, (3,), torch.float64, dev, 1024)
+        except Exception as e:
+            pg, peer_ok = None, "unavailable: %s" % type(e).__name__
+        if pg is not None:
+            cur = torch.cuda.current_stream()
+            bufs.u_final.zero_()
+            rounds, groups = pg.rounds, 2 if pg.rounds % 2 == 0 else 1
+            rpg = rounds // groups
+            pg.begin(cur)
+            evs = [torch.cuda.Event() for _ in range(groups)]
+            for g in range(groups):
+                ll.solve_device(prog, bufs, (0.0, 10.0), first=g * rpg * 1024, count=rpg * 1024)
+                evs[g].record(cur)
+                pg.push(bufs.u_final, g * rpg, (g + 1) * rpg, evs[g])
+            pg.finish(cur)
+            d.allreduce_mean(part, N)
+            torch.cuda.synchronize()
+            peer_ok = bool(torch.equal(pg.full, full))
     if rank == 0:
-        q.put((full.cpu().numpy(), steps.cpu().numpy(), mean.cpu().numpy()))
+        q.put((full.cpu().numpy(), steps.cpu().numpy(), mean.cpu().numpy(), peer_ok))
     dist.barrier()
     dist.destroy_process_group()
     prog.close()
@@ -75,7 +98,8 @@ def test_two_rank_nccl_sweep_equals_single_gpu(pkg, handle, N):
     procs = [ctx.Process(target=_rank_main, args=(r, 2, port, N, q)) for r in range(2)]
     for p in procs:
         p.start()
-    full, steps, mean = q.get(timeout=300)
+    full, steps, mean, peer_ok = q.get(timeout=300)
+    assert peer_ok in (True, "n/a") or str(peer_ok).startswith("unavailable"), "PeerGather differs from the NCCL gather"
     for p in procs:
         p.join(timeout=300)
         assert p.exitcode == 0
