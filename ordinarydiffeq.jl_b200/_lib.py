@@ -135,7 +135,7 @@ EXPORTS = [
     "b200ode_dense_eval_device", "b200ode_solve_dense", "b200ode_selftest_fastmath",
     "b200ode_multi_create", "b200ode_multi_destroy", "b200ode_multi_device_count", "b200ode_multi_compile",
     "b200ode_multi_program_destroy", "b200ode_multi_solve", "b200ode_multi_reduce_mean",
-    "b200ode_compile_callbacks", "b200ode_compile_only_callbacks",
+    "b200ode_compile_callbacks", "b200ode_compile_only_callbacks", "b200ode_struct_size",
 ]
 
 _lib = None

@@ -1035,6 +1035,19 @@ int check_problem(int64_t N, const void* u0, const void* p, int np, double t0, d
 extern "C" {
 
 const char* b200ode_version(void) { return "b200ode 0.1.0 (sm_100a, NVRTC " "12.x" ")"; }
+int b200ode_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(B200Problem);
+        case 1: return (int)sizeof(B200Opts);
+        case 2: return (int)sizeof(B200Result);
+        case 3: return (int)sizeof(B200DeviceProblem);
+        case 4: return (int)sizeof(B200DeviceResult);
+        case 5: return (int)sizeof(B200ProgramInfo);
+        case 6: return (int)sizeof(B200CallbackSrc);
+        case 7: return (int)sizeof(B200Ragged);
+        default: return -1;
+    }
+}
 
 const char* b200ode_last_error(b200ode_handle) { return g_last_error.c_str(); }
 

@@ -123,6 +123,18 @@ isstiff(alg) = alg isa StiffAlgs
 const RETCODES = (ReturnCode.Default, ReturnCode.Success, ReturnCode.MaxIters, ReturnCode.DtLessThanMin,
                   ReturnCode.Unstable, ReturnCode.DtNaN, ReturnCode.Terminated)
 
+# the structs above against the library they are handed to (b200ode_struct_size), once per session
+const ABI_CHECKED = Ref(false)
+function check_abi()
+    ABI_CHECKED[] && return
+    for (which, S) in enumerate((B200Problem, B200Opts, B200Result, nothing, nothing, nothing, B200CallbackSrc, B200Ragged))
+        S === nothing && continue
+        n = ccall((:b200ode_struct_size, LIB), Cint, (Cint,), which - 1)
+        n == sizeof(S) || error("EnsembleB200: $(S) is $(sizeof(S)) bytes here and $n in $LIB — binding and library are out of step")
+    end
+    ABI_CHECKED[] = true
+end
+
 function check(rc)
     rc == 0 && return
     msg = unsafe_string(ccall((:b200ode_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))
@@ -337,6 +349,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     for k in keys(kw)
         k in ALLOWED || throw(ArgumentError("EnsembleB200 does not support the keyword $k"))
     end
+    check_abi()
     T = eltype(prob.u0)
     T <: Union{Float32, Float64} || throw(ArgumentError("EnsembleB200 supports Float32/Float64 states"))
     t0, tf = Float64.(prob.tspan)

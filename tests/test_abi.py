@@ -129,3 +129,17 @@ def test_nslots_agrees_with_rows_the_oracle_actually_saves(pkg):
             assert n == o["nslots"] == o["nsaved"][0], (grid, ss, se, n, o["nsaved"][0])
             if n > 0:
                 assert len(o["ts"]) == n and list(o["ts"]) == sorted(o["ts"])
+
+
+def test_binding_structs_have_the_library_sizes(pkg):
+    """The ctypes mirrors of the public structs (ordinarydiffeq.jl_b200/_lib.py) are as large as the C structs the library
+    was built with (b200ode_struct_size) — a field added on one side only fails here, not as memory corruption."""
+    L = pkg._lib.lib()
+    import ctypes as C
+    L.b200ode_struct_size.argtypes = [C.c_int]
+    L.b200ode_struct_size.restype = C.c_int
+    mirrors = [pkg._lib.B200Problem, pkg._lib.B200Opts, pkg._lib.B200Result, pkg._lib.B200DeviceProblem,
+               pkg._lib.B200DeviceResult, pkg._lib.B200ProgramInfo, pkg._lib.B200CallbackSrc, pkg._lib.B200Ragged]
+    for which, cls in enumerate(mirrors):
+        assert L.b200ode_struct_size(which) == C.sizeof(cls), cls.__name__
+    assert L.b200ode_struct_size(99) == -1
