@@ -469,12 +469,13 @@ def sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barri
     groups = 4 if (in_place and rounds >= 8 and rounds % 4 == 0) else 1
     peer = None
     if groups > 1 and os.environ.get("B200_SWEEP_GATHER", "peer") == "peer":
-        try:            # push over NVLink peer memory with the copy engines (distributed.PeerGather); NCCL otherwise
-            peer = d.PeerGather(N, (3,), torch.float64, dev, block)
+        # push over NVLink peer memory with the copy engines (distributed.PeerGather); NCCL when symmetric memory is not
+        # available (all ranks agree on that before anyone enters the collective rendezvous)
+        peer, why = d.PeerGather.create(N, (3,), torch.float64, dev, block)
+        if peer is not None:
             full = peer.full
-        except Exception as e:      # symmetric memory not available on this box / build
-            sys.stderr.write("bench: PeerGather unavailable (%s: %s); NCCL all-gather after the integration\n" % (type(e).__name__, e))
-            peer = None
+        elif rank == 0:
+            sys.stderr.write("bench: PeerGather unavailable (%s); NCCL all-gather after the integration\n" % why)
     if peer is None:
         groups = 1
     gev = [torch.cuda.Event() for _ in range(groups)]

@@ -108,7 +108,25 @@ class PeerGather:
     with; when that all-reduce has completed on a rank, every rank has passed its own copies, so `full` is complete
     everywhere.  Needs N % (world * block) == 0."""
 
-    def __init__(self, N, tail, dtype, device, block, group=None):
+    @classmethod
+    def create(cls, N, tail, dtype, device, block, group=None):
+        """PeerGather, or None when symmetric memory is not available — decided by ALL ranks together (the local
+        allocation is tried first and the outcome all-reduced, so that no rank enters the collective rendezvous alone)."""
+        import torch
+        import torch.distributed as dist
+        buf, err = None, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty((N,) + tuple(tail), dtype=dtype, device=device)
+        except Exception as e:      # not built in, no fabric / IPC support, out of memory
+            err = "%s: %s" % (type(e).__name__, e)
+        flag = torch.tensor([1 if buf is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            return None, (err or "symmetric memory unavailable on another rank")
+        return cls(N, tail, dtype, device, block, group, _buf=buf), ""
+
+    def __init__(self, N, tail, dtype, device, block, group=None, _buf=None):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -117,7 +135,7 @@ class PeerGather:
         assert N % (self.world * block) == 0, "PeerGather needs whole rounds"
         self.N, self.block, self.rounds = N, block, N // (self.world * block)
         shape = (N,) + tuple(tail)
-        self.full = symm.empty(shape, dtype=dtype, device=device)
+        self.full = _buf if _buf is not None else symm.empty(shape, dtype=dtype, device=device)
         self.handle = symm.rendezvous(self.full, self.group)
         self.peers = [self.full if r == self.rank else self.handle.get_buffer(r, shape, dtype) for r in range(self.world)]
         # one copy stream per destination: copies to different peers run on different copy engines / NVLink ports at once

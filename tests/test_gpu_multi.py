@@ -54,10 +54,9 @@ def _rank_main(rank, world, port, N, q):
     # the all-reduce) must give the same array as NCCL's gather; "unavailable" when symmetric memory cannot be set up
     peer_ok = "n/a"
     if N % (world * 1024) == 0:
-        try:
-            pg = d.PeerGather(N, (3,), torch.float64, dev, 1024)
-        except Exception as e:
-            pg, peer_ok = None, "unavailable: %s" % type(e).__name__
+        pg, why = d.PeerGather.create(N, (3,), torch.float64, dev, 1024)
+        if pg is None:
+            peer_ok = "unavailable: %s" % why
         if pg is not None:
             cur = torch.cuda.current_stream()
             bufs.u_final.zero_()
