@@ -250,8 +250,8 @@ class DeviceRun:
             self.bufs.p.copy_(torch.from_numpy(np.ascontiguousarray(self.p)))
         self.kw = dict(saveat=self.grid, **w["tol"])
 
-    def step(self, first=0, count=None):
-        self.pkg.lowlevel.solve_device(self.prog, self.bufs, self.w["tspan"], first=first, count=count, **self.kw)
+    def step(self, first=0, count=None, peer_out=None):
+        self.pkg.lowlevel.solve_device(self.prog, self.bufs, self.w["tspan"], first=first, count=count, peer_out=peer_out, **self.kw)
 
     def timed(self, steps, warmup, barrier):
         torch = self.torch
@@ -468,7 +468,8 @@ def sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barri
     rounds = (N // (world * block)) if in_place else 0
     groups = 4 if (in_place and rounds >= 8 and rounds % 4 == 0) else 1
     peer = None
-    if groups > 1 and os.environ.get("B200_SWEEP_GATHER", "peer") == "peer":
+    mode = os.environ.get("B200_SWEEP_GATHER", "fused")      # fused | copy | nccl
+    if groups > 1 and mode in ("fused", "copy"):
         # push over NVLink peer memory with the copy engines (distributed.PeerGather); NCCL when symmetric memory is not
         # available (all ranks agree on that before anyone enters the collective rendezvous)
         peer, why = d.PeerGather.create(N, (3,), torch.float64, dev, block)
@@ -478,13 +479,23 @@ def sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barri
             sys.stderr.write("bench: PeerGather unavailable (%s); NCCL all-gather after the integration\n" % why)
     if peer is None:
         groups = 1
+    # "fused": the integration kernel itself stores every final state at its global index into every rank's result
+    # (peer stores over NVLink, B200DeviceResult.peer_u_final) — one launch, no copies; "copy": the copy-engine push above
+    fused = peer is not None and mode == "fused"
+    peer_ptrs = ([t.data_ptr() for t in peer.peers], world, rank, block) if fused else None
     gev = [torch.cuda.Event() for _ in range(groups)]
 
     def step(i=None):
         nonlocal mean
         if i is not None:
             ev[i][0].record()
-        if peer is not None:
+        if fused:
+            run.step(peer_out=peer_ptrs)
+            ll.reduce_sum_device(h, pkg.F64, run.bufs.u_final, pkg._lib.LAYOUT_AOS, m, 3, part)
+            if i is not None:
+                ev[i][1].record()
+            mean = d.allreduce_mean(part, N)        # also the barrier after which every rank's `full` is complete
+        elif peer is not None:
             cur = torch.cuda.current_stream()
             rpg = rounds // groups
             peer.begin(cur)
@@ -549,6 +560,10 @@ def sweep_section(args, pkg, h, torch, dist, rank, world, local_rank, dev, barri
            "trajectories_total": N, "trajectories_per_gpu": m, "steps": steps, "ms_per_step": ms / steps,
            "partition": "interleaved blocks of %d trajectories (block b -> rank b %% N)" % block,
            "collectives": "none (single GPU)" if world == 1 else
+                          ("fused into the integration kernel: every finished trajectory's final state is stored at its global index "
+                           "into every rank's result (symmetric memory, peer stores over NVLink, B200DeviceResult.peer_u_final): no gather "
+                           "step, no copy; equal to the NCCL all-gather bit for bit (asserted before timing); + ncclAllReduce of the partial "
+                           "sums, which also closes the step across ranks") if fused else
                           ("push over NVLink peer memory: every rank copies each finished block of its shard into its final place "
                            "in every rank's result (symmetric memory, device-to-peer cudaMemcpyAsync on the copy engines, %d blocks x "
                            "%d peers per step) while the next of %d groups of rounds integrates; equal to the NCCL all-gather bit for bit "

@@ -62,7 +62,9 @@ class B200DeviceResult(C.Structure):
     _fields_ = [("u_final", C.c_void_p), ("u_final_layout", C.c_int32), ("pad0", C.c_int32),
                 ("t_final", C.c_void_p), ("us", C.c_void_p),
                 ("nsaved", C.c_void_p), ("naccept", C.c_void_p), ("nreject", C.c_void_p), ("nf", C.c_void_p),
-                ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p)]
+                ("njacs", C.c_void_p), ("nw", C.c_void_p), ("nsolve", C.c_void_p), ("retcode", C.c_void_p),
+                ("peer_u_final", C.c_void_p * 8), ("npeers", C.c_int32), ("peer_world", C.c_int32), ("peer_rank", C.c_int32),
+                ("pad1", C.c_int32), ("peer_block", C.c_int64)]
 
 
 class B200ProgramInfo(C.Structure):

@@ -78,6 +78,7 @@ struct Params {
     R fpe0, rfpe0;
     const R* disc; int ndisc;
     const double* tspans; int dtmax_default;
+    R* peer_out[8]; int npeer, peer_world, peer_rank; long long peer_block;
 };
 
 struct DevBuf {
@@ -934,6 +935,19 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     // starts and overwrites it with t_final when it ends), so the launch owns no handle-level scratch and launches on
     // different streams cannot disturb each other.
     P.dt0 = (R*)dr->t_final;
+    P.npeer = 0; P.peer_world = 1; P.peer_rank = 0; P.peer_block = 1;
+    for (int r = 0; r < 8; ++r) P.peer_out[r] = nullptr;
+    if (dr->npeers > 0) {
+        if (dr->npeers > 8 || dr->peer_world < 1 || dr->peer_rank < 0 || dr->peer_rank >= dr->peer_world || dr->peer_block < 1)
+            return fail(B200ODE_EINVAL, "result.peer_*: npeers in 1..8, 0 <= peer_rank < peer_world, peer_block >= 1");
+        if (prog->coop_l > 0 || prog->wide_nt > 0)
+            return fail(B200ODE_EUNSUPPORTED, "the fused peer gather is served by the one-thread kernels");
+        for (int r = 0; r < dr->npeers; ++r) {
+            if (!dr->peer_u_final[r]) return fail(B200ODE_EINVAL, "result.peer_u_final holds a NULL pointer");
+            P.peer_out[r] = (R*)dr->peer_u_final[r];
+        }
+        P.npeer = dr->npeers; P.peer_world = dr->peer_world; P.peer_rank = dr->peer_rank; P.peer_block = dr->peer_block;
+    }
     P.u_final = (R*)dr->u_final;
     if (dr->u_final_layout == B200ODE_LAYOUT_SOA) { P.uf_ts = 1; P.uf_cs = N; } else { P.uf_ts = n; P.uf_cs = 1; }
     P.t_final = (R*)dr->t_final;

@@ -177,6 +177,11 @@ struct B200Params {
     // per-trajectory time spans (programs compiled with -DB200_TSPANS=1): (t0_i, tf_i) pairs, NULL otherwise
     const double* tspans;
     int dtmax_default;        // 1: opts.dtmax was not given, i.e. dtmax = tf_i - t0_i per trajectory (solve.jl:152)
+    // fused ordered gather (B200DeviceResult.peer_u_final): the final state also goes, at the trajectory's global index,
+    // into the result arrays of npeer ranks (this GPU's own and its NVLink peers')
+    real* peer_out[8];
+    int npeer, peer_world, peer_rank;
+    long long peer_block;
 };
 
 #define B200_FLAG_STATIC_SCHEDULE 1   // one trajectory per thread, no refill (A/B baseline)
@@ -870,6 +875,15 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
 #endif
 #pragma unroll
     for (int c = 0; c < B200_N; ++c) P.u_final[idx * P.uf_ts + c * P.uf_cs] = T.u[c];
+    if (P.npeer > 0) {
+        // the ordered all-gather, fused: peer stores over NVLink straight into every rank's result, in global order
+        const long long g = ((idx / P.peer_block) * P.peer_world + P.peer_rank) * P.peer_block + (idx % P.peer_block);
+        for (int r = 0; r < P.npeer; ++r) {
+            real* dst = P.peer_out[r] + g * B200_N;
+#pragma unroll
+            for (int c = 0; c < B200_N; ++c) dst[c] = T.u[c];
+        }
+    }
     P.t_final[idx] = T.t;
     P.naccept[idx] = T.naccept;
     P.nreject[idx] = T.nreject;

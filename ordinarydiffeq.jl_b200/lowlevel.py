@@ -263,7 +263,7 @@ class DeviceBuffers:
 
 def solve_device(program, bufs, tspan, reltol=None, abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None,
                  saveat=None, save_start=None, save_end=None, flags=0, stream=None, tstops=None, d_discontinuities=None,
-                 first=0, count=None):
+                 first=0, count=None, peer_out=None):
     """Launch the ensemble on buffers already in HBM (b200ode_solve_device); asynchronous.
     first / count: only trajectories first .. first+count-1 of the buffers (array-of-structures layout) — lets a caller
     split one ensemble into several launches, e.g. to overlap a collective on the finished part with the rest."""
@@ -290,6 +290,15 @@ def solve_device(program, bufs, tspan, reltol=None, abstol=None, dt=None, dtmin=
     dr.us = row(bufs.us) if bufs.us is not None else None
     for name in ("nsaved", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode"):
         setattr(dr, name, row(getattr(bufs, name)))
+    if peer_out is not None:
+        # (device pointers of every rank's result [total, n], world, rank, block): the kernel stores each final state at
+        # its global index into all of them (B200DeviceResult.peer_u_final) — the ordered gather, fused
+        ptrs, world, rank, block = peer_out
+        if first != 0:
+            raise ValueError("the fused gather numbers the launch's trajectories from the start of the shard")
+        for r, ptr in enumerate(ptrs):
+            dr.peer_u_final[r] = int(ptr)
+        dr.npeers, dr.peer_world, dr.peer_rank, dr.peer_block = len(ptrs), int(world), int(rank), int(block)
     if stream is None:
         import torch
         stream = torch.cuda.current_stream().cuda_stream

@@ -72,6 +72,14 @@ def _rank_main(rank, world, port, N, q):
             d.allreduce_mean(part, N)
             torch.cuda.synchronize()
             peer_ok = bool(torch.equal(pg.full, full))
+            # ... and the gather fused into the kernel (B200DeviceResult.peer_u_final): one launch whose trajectory ends store
+            # into every rank's result at the global index
+            pg.full.zero_()
+            dist.barrier()
+            ll.solve_device(prog, bufs, (0.0, 10.0), peer_out=([t.data_ptr() for t in pg.peers], world, rank, 1024))
+            d.allreduce_mean(part, N)
+            torch.cuda.synchronize()
+            peer_ok = peer_ok and bool(torch.equal(pg.full, full))
     if rank == 0:
         q.put((full.cpu().numpy(), steps.cpu().numpy(), mean.cpu().numpy(), peer_ok))
     dist.barrier()
