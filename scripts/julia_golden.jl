@@ -119,6 +119,22 @@ let
     end
 end
 
+# keywords added in the last third of round 2: tstops + d_discontinuities (the stop, the one-ulp shift and the fresh first
+# stage change the step sequence even for an autonomous RHS), and a prob_func that remakes tspan
+let
+    P = [SVector(10.0, 28.0 * (0.5 + U(i - 1, 0)), 8 / 3) for i in 1:NTRAJ]
+    prob = ODEProblem{false}(lorenz, SVector(1.0, 0.0, 0.0), (0.0, 10.0), P[1])
+    run_case("lorenz_tsit5_d_discontinuities", prob, P, nothing, Tsit5(); d_discontinuities = [2.5, 5.0], tstops = [7.5],
+             saveat = 0.5)
+    run_case("lorenz_vern7_d_discontinuities", prob, P, nothing, Vern7(); d_discontinuities = [0.0, 2.5], save_everystep = false)
+    spans = [(0.0, 5.0 + 5.0 * U(i - 1, 1)) for i in 1:NTRAJ]
+    prob_func = (prob, ctx) -> remake(prob; p = P[ctx.sim_id], tspan = spans[ctx.sim_id])
+    sim = solve(EnsembleProblem(prob; prob_func, safetycopy = false), Tsit5(), EnsembleThreads(); trajectories = NTRAJ,
+                save_everystep = false)
+    dump("lorenz_tsit5_tspans", sim, ["case" => "lorenz_tsit5_tspans", "alg" => "Tsit5", "dtype" => "Float64",
+                                      "trajectories" => NTRAJ, "julia" => string(VERSION)])
+end
+
 # config 3: Robertson, Rodas5P and Rosenbrock23 (+ the RodasTableau family), jac + tgrad supplied
 let
     base = (0.04, 3.0e7, 1.0e4)

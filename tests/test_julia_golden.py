@@ -41,6 +41,9 @@ CASES = {
     "cfg3_robertson_rodas5p_saveat": ("ALG_RODAS5P", "robertson", False,
                                       dict(reltol=1e-6, abstol=1e-8, saveat=[100.0, 1000.0, 5.0e4])),
     "cfg4_pleiades_vern7": ("ALG_VERN7", "pleiades", False, dict(reltol=1e-6, abstol=1e-8)),
+    "lorenz_tsit5_d_discontinuities": ("ALG_TSIT5", "lorenz", False, dict(d_discontinuities=[2.5, 5.0], tstops=[7.5], saveat=0.5)),
+    "lorenz_vern7_d_discontinuities": ("ALG_VERN7", "lorenz", False, dict(d_discontinuities=[0.0, 2.5])),
+    "lorenz_tsit5_tspans": ("ALG_TSIT5", "lorenz", False, dict(_tspans=True)),
 }
 
 
@@ -60,6 +63,25 @@ def _setup(pkg, problem, f32, N):
         r, j, tg = pl.robertson_sources(f32)
         return r, j, tg, np.array([1.0, 0.0, 0.0]), pl.robertson_params(N, f32=f32), (0.0, 1e5), 3, 3
     return pl.pleiades_source(f32), None, None, pl.pleiades_u0(N, f32=f32), None, (0.0, 3.0), 28, 0
+
+
+def _spans(pkg, kw, tspan, N):
+    """tspan argument of the case: the shared span, or (cases with _tspans) the per-trajectory spans the generator's
+    prob_func builds: (0, 5 + 5 U(i, 1))."""
+    if not kw.get("_tspans"):
+        return tspan
+    idx = np.arange(N, dtype=np.uint64)
+    return np.stack([np.zeros(N), 5.0 + 5.0 * pkg.problems_library.splitmix64_uniform(idx, 1)], axis=1)
+
+
+def _options(pkg, kw):
+    """program options a case needs on the CUDA path"""
+    opts = []
+    if "tstops" in kw or "d_discontinuities" in kw:
+        opts.append(pkg._lib.OPT_TSTOPS)
+    if kw.get("_tspans"):
+        opts.append(pkg._lib.OPT_TSPANS)
+    return " ".join(opts) or None
 
 
 def _grid(pkg, kw, tspan):
@@ -103,8 +125,9 @@ def test_oracle_matches_julia_reference(pkg, stem):
     from oracle import oracle
     algname, problem, f32, kw = CASES[stem]
     rhs, jac, tg, u0, p, tspan, n, np_ = _setup(pkg, problem, f32, gold["trajectories"])
-    kw = _grid(pkg, kw, tspan)
-    o = oracle.solve(getattr(oracle, algname), rhs, u0, p, tspan, n, np_, f32=f32, jac=jac, tgrad=tg, **kw)
+    span = _spans(pkg, kw, tspan, gold["trajectories"])
+    kw = {k: v for k, v in _grid(pkg, kw, tspan).items() if not k.startswith("_")}
+    o = oracle.solve(getattr(oracle, algname), rhs, u0, p, span, n, np_, f32=f32, jac=jac, tgrad=tg, **kw)
     _compare(o, gold, f32, kw.get("reltol", 1e-3))
 
 
@@ -114,11 +137,14 @@ def test_cuda_path_matches_julia_reference(pkg, handle, stem):
     gold = _load(stem)
     algname, problem, f32, kw = CASES[stem]
     rhs, jac, tg, u0, p, tspan, n, np_ = _setup(pkg, problem, f32, gold["trajectories"])
-    kw = _grid(pkg, kw, tspan)
+    span = _spans(pkg, kw, tspan, gold["trajectories"])
+    extra = _options(pkg, kw)
+    kw = {k: v for k, v in _grid(pkg, kw, tspan).items() if not k.startswith("_")}
     prog = handle.compile(getattr(pkg, algname), pkg.F32 if f32 else pkg.F64, n, np_, rhs[0], rhs[1],
-                          jac[0] if jac else None, jac[1] if jac else None, tg[0] if tg else None, tg[1] if tg else None)
+                          jac[0] if jac else None, jac[1] if jac else None, tg[0] if tg else None, tg[1] if tg else None,
+                          extra_options=extra)
     try:
-        g = pkg.lowlevel.solve_host(prog, u0, p, tspan, **kw)
+        g = pkg.lowlevel.solve_host(prog, u0, p, span, **kw)
     finally:
         prog.close()
     _compare(g, gold, f32, kw.get("reltol", 1e-3))
