@@ -124,7 +124,16 @@ class PeerGather:
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         if int(flag.item()) == 0:
             return None, (err or "symmetric memory unavailable on another rank")
-        return cls(N, tail, dtype, device, block, group, _buf=buf), ""
+        obj = None
+        try:        # the rendezvous is collective; a failure that is a property of the box hits every rank alike
+            obj = cls(N, tail, dtype, device, block, group, _buf=buf)
+        except Exception as e:
+            err = "%s: %s" % (type(e).__name__, e)
+        flag.fill_(1 if obj is not None else 0)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            return None, (err or "peer mapping failed on another rank")
+        return obj, ""
 
     def __init__(self, N, tail, dtype, device, block, group=None, _buf=None):
         import torch
