@@ -963,3 +963,17 @@ def test_per_trajectory_tspans_equal_separate_solves(pkg):
         ri = oracle.solve(oracle.ALG_TSIT5, src, u0, p[i:i + 1], tuple(spans[i]), 3, 3, save_everystep=True, saveat=gi or None)
         a, b = orag["row_offsets"][i], orag["row_offsets"][i + 1]
         assert np.array_equal(orag["ts"][a:b], ri["ts"]) and np.array_equal(bits(orag["us"][a:b]), bits(ri["us"]))
+
+
+def test_d_discontinuities_exact_time_grid_of_the_reference():
+    """test/InterfaceI/ode_tstops_tests.jl:14-21, exact: a fixed step dt = 1//3 with tstops = [1/2] gives
+    sol.t == [0, 1/3, 1/2, 1/3 + 1/2, 1]; adding d_discontinuities = [-1/2, 1/2, 3/2] gives
+    sol.t == [0, 1/3, 1/2, nextfloat(1/2) + 1/3, 1] — the step after the discontinuity starts one ulp past it.  (The
+    reference runs RK4 there; the time grid of a fixed-step solve does not depend on the method.)"""
+    src = linear_source()
+    for alg in (oracle.ALG_TSIT5, oracle.ALG_BS3, oracle.ALG_DP5, oracle.ALG_VERN7):
+        kw = dict(trajectories=1, adaptive=False, dt=1 / 3, tstops=[0.5], save_everystep=True)
+        o = oracle.solve(alg, src, np.array([0.5]), None, (0.0, 1.0), 1, 0, **kw)
+        assert list(o["ts"]) == [0, 1 / 3, 1 / 2, 1 / 3 + 1 / 2, 1]
+        o = oracle.solve(alg, src, np.array([0.5]), None, (0.0, 1.0), 1, 0, d_discontinuities=[-0.5, 0.5, 1.5], **kw)
+        assert list(o["ts"]) == [0, 1 / 3, 1 / 2, np.nextafter(0.5, 1.0) + 1 / 3, 1]
