@@ -66,6 +66,9 @@ template <typename R> static R jl_nextfloat_signed(R x) {
     if (x == (R)0) return Bits<R>::from(1);
     return x > (R)0 ? Bits<R>::from(Bits<R>::to(x) + 1) : Bits<R>::from(Bits<R>::to(x) - 1);
 }
+// prevfloat(x), finite x of either sign; _shift_past_discontinuity! picks by tdir (integrator_utils.jl:1193-1195)
+template <typename R> static R jl_prevfloat_signed(R x) { return -jl_nextfloat_signed(-x); }
+template <typename R> static R jl_shift_past(R x, R tdir) { return tdir > (R)0 ? jl_nextfloat_signed(x) : jl_prevfloat_signed(x); }
 // Base.max/min propagate NaN
 template <typename R> static R jl_max(R a, R b) { return std::isnan(a) ? a : (std::isnan(b) ? b : (a > b ? a : b)); }
 template <typename R> static R jl_min(R a, R b) { return std::isnan(a) ? a : (std::isnan(b) ? b : (a < b ? a : b)); }
@@ -405,12 +408,13 @@ template <typename R> struct Tsit5 {
 #endif
 
 // ---------------------------------------------------------------------------
-// _ode_initdt_oop — lib/OrdinaryDiffEqCore/src/initdt.jl:346-459 (g === nothing, tdir = +1)
+// _ode_initdt_oop — lib/OrdinaryDiffEqCore/src/initdt.jl:346-459 (g === nothing); `dtmax` is the signed value of
+// auto_dt_reset! (integrator_interface.jl:645-648: tdir * min(|opts.dtmax|, |first_tstop - tdir t|)), the result carries tdir
 template <typename R>
 static R ode_initdt(const ProblemFns<R>& P, const R* u0, const R* p, R t, R dtmax, R abstol, R reltol, R opts_dtmin,
-                    int order, const R* abstol_v = nullptr, const R* reltol_v = nullptr) {
+                    int order, const R* abstol_v = nullptr, const R* reltol_v = nullptr, R tdir = (R)1) {
     const int n = P.n;
-    R dtmax_tdir = dtmax;
+    R dtmax_tdir = tdir * dtmax;
     R dtmin = jl_nextfloat(jl_max(opts_dtmin, jl_eps(t)));
     R smalldt = jl_max(dtmin, (R)1e-6);                 // convert(_tType, 1//10^6)
     R sk[ORACLE_MAXN], tmp[ORACLE_MAXN], f0[ORACLE_MAXN], f1[ORACLE_MAXN], u1[ORACLE_MAXN];
@@ -419,22 +423,22 @@ static R ode_initdt(const ProblemFns<R>& P, const R* u0, const R* p, R t, R dtma
     for (int i = 0; i < n; ++i) tmp[i] = u0[i] / sk[i];
     R d0 = rms(tmp, n);
     P.f(f0, u0, p, t);
-    for (int i = 0; i < n; ++i) if (std::isnan(f0[i])) return dtmin;                 // NAN_CHECK(f₀)
+    for (int i = 0; i < n; ++i) if (std::isnan(f0[i])) return tdir * dtmin;          // NAN_CHECK(f₀)
     for (int i = 0; i < n; ++i) tmp[i] = f0[i] / sk[i];
     R d1 = rms(tmp, n);
-    if (std::isnan(d1)) return dtmin;
+    if (std::isnan(d1)) return tdir * dtmin;
     R dt0;
     // d₀ < 1//10^5: the binary64 literal 1e-5 lies above the rational, so for any
     // binary64/binary32 operand "x < 1//10^5" == "(double)x < 1e-5"
     if ((double)d0 < 1e-5 || (double)d1 < 1e-5) dt0 = smalldt;
     else dt0 = (d0 / d1) / (R)100;
     dt0 = jl_min(dt0, dtmax_tdir);
-    R dt0_tdir = dt0;
+    R dt0_tdir = tdir * dt0;
     for (int i = 0; i < n; ++i) u1[i] = jl_fma(dt0_tdir, f0[i], u0[i]);
     P.f(f1, u1, p, t + dt0_tdir);
     bool eq = true;
     for (int i = 0; i < n; ++i) eq = eq && (f0[i] == f1[i]);
-    if (eq) return jl_max(dtmin, (R)100 * dt0);
+    if (eq) return tdir * jl_max(dtmin, (R)100 * dt0);
     for (int i = 0; i < n; ++i) tmp[i] = (f1[i] - f0[i]) / sk[i];
     R d2 = rms(tmp, n) / dt0;
     R max_d1d2 = jl_max(d1, d2);
@@ -447,7 +451,7 @@ static R ode_initdt(const ProblemFns<R>& P, const R* u0, const R* p, R t, R dtma
         R e = -((R)2 + l) / (R)order;
         dt1 = (R)cr_exp10((double)e);
     }
-    return jl_max(dtmin, jl_min(jl_min((R)100 * dt0, dt1), dtmax_tdir));
+    return tdir * jl_max(dtmin, jl_min(jl_min((R)100 * dt0, dt1), dtmax_tdir));
 }
 
 // ---------------------------------------------------------------------------
@@ -498,7 +502,12 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
     if (o.ncb > 0 && p_in != nullptr) { for (int i = 0; i < P.np; ++i) p_local[i] = p_in[i]; }
     const R* p = (o.ncb > 0 && p_in != nullptr) ? p_local : p_in;
     R t = t0, tprev = t0;
-    const R dtmax = o.dtmax, opts_dtmin = o.dtmin;
+    // tdir = sign(tspan[end] - tspan[1]) (solve.jl:273).  The internal queues of the reference hold tdir * time
+    // (initialize_tstops / initialize_saveat / initialize_d_discontinuities, solve.jl:1021-1197); here the lists keep the
+    // times themselves, in the order they are met, and every comparison multiplies both sides by tdir (exact)
+    const R tdir = tf > t0 ? (R)1 : (tf < t0 ? (R)-1 : (R)0);
+    // dtmax > 0 && tdir < 0 && (dtmax *= tdir) (solve.jl:401); dtmin is all abs
+    const R dtmax = (o.dtmax > (R)0 && tdir < (R)0) ? o.dtmax * tdir : o.dtmax, opts_dtmin = o.dtmin;
     int nsaved = 0, save_idx = 0;
     R last_saved_t = t0;
     auto emit = [&](R ts, const R* v) {
@@ -532,17 +541,18 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
     R dt;
     const R dtcache = o.dt;                                            // solve.jl:699
     if (o.dt == (R)0 && o.adaptive) {
-        R dtmax_init = jl_min(std::fabs(dtmax), std::fabs(cur_tstop - t));     // _determine_initdt: first_tstop
-        dt = ode_initdt(P, u, p, t, dtmax_init, o.abstol, o.reltol, opts_dtmin, Alg::order, o.abstol_v, o.reltol_v);
+        R dtmax_init = tdir * jl_min(std::fabs(dtmax), std::fabs(tdir * cur_tstop - tdir * t));     // auto_dt_reset!: first_tstop
+        dt = ode_initdt(P, u, p, t, dtmax_init, o.abstol, o.reltol, opts_dtmin, Alg::order, o.abstol_v, o.reltol_v, tdir);
         stats.nf += 2;
-    } else dt = o.dt;
+    } else if (o.adaptive && o.dt > (R)0 && tdir < (R)0) dt = o.dt * tdir;      // allow positive dt, but auto-convert (solve.jl:981-983)
+    else dt = o.dt;
     R dtpropose = dt;
     // handle_starting_time_discontinuity! (solve.jl:872-901), the last act of init: a discontinuity at exactly t0 is popped,
     // t moves one ulp into the span and a first-same-as-last stepper re-evaluates its first stage there (reset_fsal!)
     int disc_idx = 0;
     if (o.ndisc > 0 && o.disc[0] == t) {
         disc_idx = 1;
-        t = jl_nextfloat_signed(t);
+        t = jl_shift_past(t, tdir);
         if constexpr (IsComposite<Alg>::value) cache.reset_fsal(u, p, t, stats);
         else if (Alg::fsal_init()) cache.initialize(u, p, t, stats);
     }
@@ -577,29 +587,29 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
 
     // modify_dt_for_tstops! (integrator_utils.jl:268-324), adaptive branch
     auto modify_dt_for_tstops = [&]() {
-        R tdir_t = t, tdir_tstop = cur_tstop;                           // first_tstop(integrator)
+        R tdir_t = tdir * t, tdir_tstop = tdir * cur_tstop;             // first_tstop(integrator)
         R distance_to_tstop = std::fabs(tdir_tstop - tdir_t);
         R tstop_tol = (R)100 * jl_eps(jl_max(std::fabs(t), std::fabs(tdir_tstop)));
         if (o.adaptive) {
             R original_dt = std::fabs(dt);
-            dtpropose = original_dt;
+            dtpropose = tdir * original_dt;
             if (original_dt + tstop_tol < distance_to_tstop) next_step_tstop = false;
-            else { next_step_tstop = true; tstop_target = tdir_tstop; }
-            dt = jl_min(original_dt, distance_to_tstop);
+            else { next_step_tstop = true; tstop_target = tdir * tdir_tstop; }
+            dt = tdir * jl_min(original_dt, distance_to_tstop);
         } else if (dtcache == (R)0) {                                   // (:300-304) step from stop to stop
-            dt = distance_to_tstop;
-            next_step_tstop = true; tstop_target = tdir_tstop;
+            dt = tdir * distance_to_tstop;
+            next_step_tstop = true; tstop_target = tdir * tdir_tstop;
         } else {                                                        // (:305-316) dtchangeable, !force_stepfail
             if (std::fabs(dtcache) + tstop_tol < distance_to_tstop) next_step_tstop = false;
-            else { next_step_tstop = true; tstop_target = tdir_tstop; }
-            dt = jl_min(std::fabs(dtcache), distance_to_tstop);
+            else { next_step_tstop = true; tstop_target = tdir * tdir_tstop; }
+            dt = tdir * jl_min(std::fabs(dtcache), distance_to_tstop);
         }
     };
 
     // ---- savevalues! / _savevalues! (integrator_utils.jl:336-414); returns savedexactly
     auto savevalues = [&](bool force_save) -> bool {
         bool savedexactly = false, added = false;
-        while (save_idx < o.nsaveat && o.saveat[save_idx] <= t) {
+        while (save_idx < o.nsaveat && tdir * o.saveat[save_idx] <= tdir * t) {     // first(saveat) <= tdir_t; curt = tdir * pop!(saveat)
             R curt = o.saveat[save_idx++];
             if (curt != t) {
                 R Theta = (curt - tprev) / dt;
@@ -764,7 +774,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
 
     // solve! (solve.jl:904-946): `while !isempty(tstops); while t < first(tstops) ... end; handle_tstop! end`.
     // tf is the last stop, so the two loops collapse into this one plus the pop at the end of an accepted step.
-    while (t < tf) {
+    while (tdir * t < tdir * tf) {
         // ---- loopheader! (integrator_utils.jl:84-127)
         if (iter > 0) {
             if (accept_step || !o.adaptive) {                          // (:98-110)
@@ -779,7 +789,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 // it, reset_fsal! for a first-same-as-last stepper
                 if (disc_idx < o.ndisc && o.disc[disc_idx] == t) {
                     disc_idx += 1;
-                    t = jl_nextfloat_signed(t);
+                    t = jl_shift_past(t, tdir);
                     if constexpr (IsComposite<Alg>::value) cache.reset_fsal(u, p, t, stats);
                     else if (Alg::fsal_init()) cache.initialize(u, p, t, stats);
                 } else if (reeval_fsal) {
@@ -799,15 +809,17 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
             select_branch();
         }
         // fix_dt_at_bounds! (:1243-1256); timedepentdtmin = max(eps(t), dtmin)
-        dt = jl_min(dtmax, dt);
-        dt = jl_max(dt, jl_max(jl_eps(t), opts_dtmin));
+        // (for tdir < 0 the reference clamps with max(dtmax, dt) and then takes min(dt, dtmin) against the POSITIVE dtmin —
+        //  a no-op on a negative dt; restated as written)
+        if (tdir > (R)0) { dt = jl_min(dtmax, dt); dt = jl_max(dt, jl_max(jl_eps(t), opts_dtmin)); }
+        else { dt = jl_max(dtmax, dt); dt = jl_min(dt, std::fabs(jl_max(jl_eps(t), opts_dtmin))); }
         modify_dt_for_tstops();
         // ---- check_error (lib/DiffEqBase/src/check_error.jl:70-118); `integrator.do_error_check &&` (solve.jl:909)
         if (do_error_check) {
             int code = RC_SUCCESS;
             if (std::isnan(dt)) code = RC_DTNAN;
             else if (iter > o.maxiters) code = RC_MAXITERS;
-            else if (o.adaptive && std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < cur_tstop)) code = RC_DTLESSTHANMIN;
+            else if (o.adaptive && std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < cur_tstop)) code = RC_DTLESSTHANMIN;   // t + dt < tdir * first(opts.tstops), as written (check_error.jl:96)
             else if (o.adaptive && !accept_step && std::fabs(dt) <= std::fabs(jl_eps(t))) code = RC_UNSTABLE;
             else if (accept_step) {
                 for (int i = 0; i < n; ++i) if (!Bits<R>::finite(u[i])) code = RC_UNSTABLE;
@@ -854,8 +866,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 errold = jl_max(EEst, qoldinit);
                 R dtnew = dt / q;
                 // calc_dt_propose! (:1199-1210)
-                dtpropose = jl_min(std::fabs(dtmax), std::fabs(dtnew));
-                dtpropose = jl_max(std::fabs(dtpropose), jl_max(jl_eps(t), opts_dtmin));
+                dtpropose = tdir * jl_min(std::fabs(dtmax), std::fabs(dtnew));
+                dtpropose = tdir * jl_max(std::fabs(dtpropose), std::fabs(jl_max(jl_eps(t), opts_dtmin)));
             } else {
                 dtpropose = dt;
             }
@@ -1025,24 +1037,31 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     if (!o.adaptive && a.dt == 0.0 && !(a.tstops && a.ntstops > 0)) return -4;     // solve.jl:277-280
     std::vector<R> stops, discs;
     if ((a.tstops && a.ntstops > 0) || (a.disc && a.ndisc > 0)) {
+        // tdir_t0 < tdir * t < tdir_tf (solve.jl:1025-1036); the heaps order by tdir * t = the order the times are met
+        const R td = a.tf < a.t0 ? (R)-1 : (R)1;
         for (int i = 0; a.tstops && i < a.ntstops; ++i) {
             R v = (R)a.tstops[i];
-            if (v > (R)a.t0 && v < (R)a.tf) stops.push_back(v);
+            if (td * v > td * (R)a.t0 && td * v < td * (R)a.tf) stops.push_back(v);
         }
         // d_discontinuities: the ones inside (t0, tf) are stops too (initialize_tstops, solve.jl:1033-1036); the heap of
         // discontinuities keeps every entry >= t0 (reinit_d_discontinuities!, solve.jl:1185-1197)
         for (int i = 0; a.disc && i < a.ndisc; ++i) {
             R v = (R)a.disc[i];
-            if (v > (R)a.t0 && v < (R)a.tf) stops.push_back(v);
-            if (v >= (R)a.t0) discs.push_back(v);
+            if (td * v > td * (R)a.t0 && td * v < td * (R)a.tf) stops.push_back(v);
+            if (td * v >= td * (R)a.t0) discs.push_back(v);
         }
-        std::sort(stops.begin(), stops.end());
-        std::sort(discs.begin(), discs.end());
+        auto met_first = [td](R x, R y) { return td * x < td * y; };
+        std::sort(stops.begin(), stops.end(), met_first);
+        std::sort(discs.begin(), discs.end(), met_first);
         stops.push_back((R)a.tf);
         o.tstops = stops.data(); o.ntstops = (int)stops.size();
         o.disc = discs.data(); o.ndisc = (int)discs.size();
     }
     g_tspans = a.tspans; g_dtmax_default = !(a.dtmax > 0);
+    // reverse time (tf < t0): the integrator core above is direction-aware; callbacks (rightfloat / the tdir-ordered event
+    // search, callbacks.jl:65,201,320-345), post-hoc dense evaluation and per-trajectory spans are restated forward only
+    if (a.tf < a.t0 && (o.ncb > 0 || M > 0 || a.tspans)) return -7;
+    if (a.tspans) for (long long i = 0; i < a.N; ++i) if (!(a.tspans[2 * i + 1] > a.tspans[2 * i])) return -7;
     if (a.tspans && ((a.tstops && a.ntstops > 0) || (a.disc && a.ndisc > 0) || M > 0)) return -6;
     Out<R> out;
     out.row_offsets = a.row_offsets; out.ts_rag = (R*)a.ts_rag;
@@ -1120,6 +1139,6 @@ double oracle_exp10(double x) { return cr_exp10(x); }
 double oracle_initdt(void* rhs, int n, int np, const double* u0, const double* p, double t0, double tf, double abstol,
                      double reltol, int order) {
     ProblemFns<double> P; P.f = (Fn<double>::rhs_t)rhs; P.n = n; P.np = np;
-    return ode_initdt<double>(P, u0, p, t0, tf - t0, abstol, reltol, 0.0, order);
+    return ode_initdt<double>(P, u0, p, t0, tf - t0, abstol, reltol, 0.0, order, nullptr, nullptr, tf < t0 ? -1.0 : 1.0);
 }
 }

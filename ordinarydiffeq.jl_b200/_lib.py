@@ -115,6 +115,7 @@ def callback_array(callbacks):
 OPT_EVERYSTEP = "-DB200_EVERYSTEP=1"
 OPT_TSTOPS = "-DB200_TSTOPS=1"
 OPT_TSPANS = "-DB200_TSPANS=1"
+OPT_REVERSE_TIME = "-DB200_REVERSE=1"      # tspan[2] < tspan[1] (tdir = -1): mirrored-time kernels
 OPT_VECTOR_TOL = "-DB200_VECTOR_TOL=1"
 OPT_FIXED_DT = "-DB200_ADAPTIVE=0"
 OPT_COMPONENT_RHS = "-DB200_COOP=1"

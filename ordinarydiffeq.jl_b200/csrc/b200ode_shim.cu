@@ -132,6 +132,7 @@ struct b200ode_program_s {
     bool callbacks = false;      // compiled with a CallbackSet (b200ode_compile_callbacks)
     bool vector_tol = false;     // compiled with -DB200_VECTOR_TOL=1 (per-component abstol / reltol)
     bool tspans = false;         // compiled with -DB200_TSPANS=1 (per-trajectory time spans)
+    bool reverse = false;        // compiled with -DB200_REVERSE=1 (tf < t0): the kernels run in mirrored time
     std::vector<double> tolv_cached;   // the 2n tolerances currently resident in the module's B200_TOLV
     int nsave = 0;               // components per saved row: n, or the length of -DB200_SAVE_IDXS=...
     size_t dyn_smem = 0;
@@ -371,6 +372,17 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         return fail(B200ODE_EUNSUPPORTED, "the shared-memory stage kernel (B200ODE_OPT_SMEM_STAGES) is available for Vern7 in the one-thread form");
     if (wide && ncb > 0)
         return fail(B200ODE_EUNSUPPORTED, "callbacks are not available in the shared-memory stage kernel");
+    // Reverse time (B200ODE_OPT_REVERSE_TIME; tdir = -1, solve.jl:273): the kernels integrate du/ds = -f(u, p, -s) over
+    // (-t0, -tf) — see device/b200_ensemble.cuh.  The user's functions are wrapped below.
+    const bool reverse = extra_options && strstr(extra_options, "-DB200_REVERSE=1");
+    if (reverse && (coop || wide))
+        return fail(B200ODE_EUNSUPPORTED, "reverse-time integration is served by the one-thread-per-trajectory kernel");
+    if (reverse && extra_options && strstr(extra_options, "-DB200_TSPANS=1"))
+        return fail(B200ODE_EUNSUPPORTED, "reverse-time integration is not combined with per-trajectory time spans");
+    if (reverse)
+        for (int i = 0; i < ncb; ++i)
+            if (cbs[i].kind != B200ODE_CB_ISOUTOFDOMAIN)
+                return fail(B200ODE_EUNSUPPORTED, "reverse-time integration is not combined with callbacks (isoutofdomain is)");
     if (coop && alg != B200ODE_ALG_VERN7 && alg != B200ODE_ALG_ROSENBROCK23)
         return fail(B200ODE_EUNSUPPORTED, "the lane-group kernel (B200ODE_OPT_COMPONENT_RHS) is available for Vern7 and Rosenbrock23");
     if (coop && alg == B200ODE_ALG_ROSENBROCK23 && (n < 2 || n > 16 || n == 3))
@@ -445,8 +457,20 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
     tu += "// ---- steppers ----\n";
     if (coop) tu += "#define B200_USER_RHS_COMP(i,u,p,t) (B200UserExact().B200_USER_COMP_NAME((i),(u),(p),(t)))\n";
     else if (wide) tu += "#define B200_USER_RHS(du,u,p,t) (B200UserExact().B200_USER_FULL_NAME((du),(u),(p),(t)))\n";
+    else if (reverse) {
+        // g(u, p, s) = -f(u, p, -s);  dg/du = -J(u, p, -s);  dg/ds = +f_t(u, p, -s)  (negation is exact)
+        tu += std::string("__device__ __forceinline__ void b200_rev_rhs(real* du, const real* u, const real* p, const real s) {\n    ") +
+              rhs_name + "(du, u, p, -s);\n#pragma unroll\n    for (int i = 0; i < B200_N; ++i) du[i] = -du[i];\n}\n"
+              "#define B200_USER_RHS(du,u,p,t) b200_rev_rhs((du),(u),(p),(t))\n";
+        if (stiff) {
+            tu += std::string("__device__ __forceinline__ void b200_rev_jac(real* J, const real* u, const real* p, const real s) {\n    ") +
+                  jac_name + "(J, u, p, -s);\n#pragma unroll\n    for (int i = 0; i < B200_N * B200_N; ++i) J[i] = -J[i];\n}\n"
+                  "#define B200_JAC(J,u,p,t) b200_rev_jac((J),(u),(p),(t))\n";
+            if (tgrad_src) tu += std::string("#define B200_TGRAD(dT,u,p,t) ") + tgrad_name + "((dT),(u),(p),-(t))\n";
+        }
+    }
     else tu += std::string("#define B200_USER_RHS(du,u,p,t) ") + rhs_name + "((du),(u),(p),(t))\n";
-    if (stiff && !coop) {
+    if (stiff && !coop && !reverse) {
         tu += std::string("#define B200_JAC(J,u,p,t) ") + jac_name + "((J),(u),(p),(t))\n";
         if (tgrad_src) tu += std::string("#define B200_TGRAD(dT,u,p,t) ") + tgrad_name + "((dT),(u),(p),(t))\n";
     }
@@ -824,9 +848,36 @@ __global__ void __launch_bounds__(256) k_fma_peak(R* out, int iters, R a, R b) {
 int (*g_compile_nosave)(b200ode_program) = nullptr;
 
 template <typename R>
+int launch_solve_fwd(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
+                     B200DeviceResult* dr, cudaStream_t stream, const long long* row_offsets, void* ts_rag, void* dts_rag);
+
+// Reverse-time programs (prog->reverse, tf < t0): the launch is that of the mirrored problem — span (-t0, -tf), every time
+// list negated (the descending saveat list becomes ascending), |dt| — the kernels hand times back through B200_USER_T.
+template <typename R>
 int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
                  B200DeviceResult* dr, cudaStream_t stream, const long long* row_offsets = nullptr, void* ts_rag = nullptr,
                  void* dts_rag = nullptr) {
+    if (!prog->reverse) return launch_solve_fwd<R>(h, prog, dp, o, dr, stream, row_offsets, ts_rag, dts_rag);
+    B200DeviceProblem dm = *dp;
+    dm.t0 = -dp->t0; dm.tf = -dp->tf;
+    B200Opts om = *o;
+    auto mirrored = [](const double* v, int nv) {
+        std::vector<double> out(v && nv > 0 ? nv : 0);
+        for (size_t i = 0; i < out.size(); ++i) out[i] = -v[i];
+        return out;
+    };
+    const std::vector<double> sa = mirrored(o->saveat, o->nsaveat), st = mirrored(o->tstops, o->ntstops),
+                              dd = mirrored(o->d_discontinuities, o->nd_discontinuities);
+    if (!sa.empty()) om.saveat = sa.data();
+    if (!st.empty()) om.tstops = st.data();
+    if (!dd.empty()) om.d_discontinuities = dd.data();
+    om.dt = std::fabs(o->dt);         // a positive dt is converted, a negative one is the direction's own (solve.jl:981-983)
+    return launch_solve_fwd<R>(h, prog, &dm, &om, dr, stream, row_offsets, ts_rag, dts_rag);
+}
+
+template <typename R>
+int launch_solve_fwd(b200ode_handle h, b200ode_program prog, const B200DeviceProblem* dp, const B200Opts* o,
+                     B200DeviceResult* dr, cudaStream_t stream, const long long* row_offsets, void* ts_rag, void* dts_rag) {
     const int n = prog->n, np = prog->np;
     const long long N = dp->trajectories;
     Params<R> P{};
@@ -1019,26 +1070,32 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     return B200ODE_OK;
 }
 
-int check_problem(int64_t N, const void* u0, const void* p, int np, double t0, double tf, const B200Opts* o) {
+int check_problem(int64_t N, const void* u0, const void* p, int np, double t0, double tf, const B200Opts* o, bool reverse = false) {
     if (N < 0) return fail(B200ODE_EINVAL, "trajectories must be >= 0");
     if (!u0) return fail(B200ODE_EINVAL, "u0 is NULL");
     if (np > 0 && !p) return fail(B200ODE_EINVAL, "p is NULL but the program has np > 0");
-    if (!(tf > t0)) return fail(B200ODE_EUNSUPPORTED, "only forward time integration (tf > t0) is supported");
+    if (!reverse && tf < t0)
+        return fail(B200ODE_EUNSUPPORTED, "tf < t0 needs a program compiled with B200ODE_OPT_REVERSE_TIME");
+    if (reverse && tf > t0)
+        return fail(B200ODE_EINVAL, "a program compiled with B200ODE_OPT_REVERSE_TIME integrates reversed spans (tf < t0)");
+    if (!(tf > t0) && !(tf < t0)) return fail(B200ODE_EINVAL, "tspan must have tf != t0 (finite)");
     if (!o) return fail(B200ODE_EINVAL, "opts is NULL");
     if (o->nsaveat < 0) return fail(B200ODE_EINVAL, "nsaveat < 0");
     if (o->saveat) {
-        double prev = t0;
+        const double td = reverse ? -1.0 : 1.0;          // the list is given in the order the integrator meets it
+        double prev = td * t0;
         for (int i = 0; i < o->nsaveat; ++i) {
-            double s = o->saveat[i];
-            if (!(s >= prev) || !(s > t0) || !(s <= tf))
-                return fail(B200ODE_EINVAL, "saveat must be ascending with every entry in (t0, tf]");
+            double s = td * o->saveat[i];
+            if (!(s >= prev) || !(s > td * t0) || !(s <= td * tf))
+                return fail(B200ODE_EINVAL, reverse ? "saveat must be descending with every entry in [tf, t0) (reverse time)"
+                                                    : "saveat must be ascending with every entry in (t0, tf]");
             prev = s;
         }
     }
     if (o->ntstops < 0 || (o->ntstops > 0 && !o->tstops)) return fail(B200ODE_EINVAL, "bad tstops");
     for (int i = 0; i < o->ntstops; ++i)
         if (!std::isfinite(o->tstops[i])) return fail(B200ODE_EINVAL, "tstops must be finite");
-    if (o->dt < 0) return fail(B200ODE_EINVAL, "dt must be >= 0 (0 = automatic)");
+    if (o->dt < 0 && !reverse) return fail(B200ODE_EINVAL, "dt must be >= 0 (0 = automatic)");
     if (o->dtmin < 0) return fail(B200ODE_EINVAL, "dtmin must be >= 0");
     return B200ODE_OK;
 }
@@ -1187,6 +1244,7 @@ static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dty
     prog->tstops = extra_options && strstr(extra_options, "-DB200_TSTOPS=1");
     prog->adaptive = !(extra_options && strstr(extra_options, "-DB200_ADAPTIVE=0"));
     prog->tspans = extra_options && strstr(extra_options, "-DB200_TSPANS=1");
+    prog->reverse = extra_options && strstr(extra_options, "-DB200_REVERSE=1");
     if (prog->tspans && (prog->tstops || prog->coop_l > 0 || prog->wide_nt > 0 || ncb > 0)) {
         delete prog; return fail(B200ODE_EUNSUPPORTED, "per-trajectory time spans are not combined with tstops / d_discontinuities, callbacks, "
                                                        "the lane-group or the shared-memory stage kernel");
@@ -1204,7 +1262,7 @@ static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dty
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&prog->k_initdt, prog->lib, "b200_initdt");
     if (e == cudaSuccess && prog->everystep && prog->nsave == n && alg != B200ODE_ALG_ROSENBROCK32 &&
-        alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 && !prog->callbacks)
+        alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 && !prog->callbacks && !prog->reverse)
         e = cudaLibraryGetKernel(&prog->k_dense, prog->lib, "b200_dense_eval");
     if (e != cudaSuccess) {
         cudaLibraryUnload(prog->lib); delete prog;
@@ -1304,7 +1362,7 @@ int b200ode_solve_device(b200ode_handle h, b200ode_program prog, const B200Devic
                          B200DeviceResult* dr, void* stream) {
     if (!h || !prog || !dp || !o || !dr) return fail(B200ODE_EINVAL, "NULL argument");
     if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
-    int rc = check_problem(dp->trajectories, dp->u0, dp->p, prog->np, dp->t0, dp->tf, o);
+    int rc = check_problem(dp->trajectories, dp->u0, dp->p, prog->np, dp->t0, dp->tf, o, prog->reverse);
     if (rc) return rc;
     if (!dr->u_final || !dr->t_final || !dr->naccept || !dr->nreject || !dr->nf || !dr->retcode || !dr->nsaved)
         return fail(B200ODE_EINVAL, "device result arrays u_final,t_final,naccept,nreject,nf,retcode,nsaved are required");
@@ -1324,7 +1382,7 @@ int b200ode_solve_everystep_device(b200ode_handle h, b200ode_program prog, const
     if (!h || !prog || !dp || !o || !dr) return fail(B200ODE_EINVAL, "NULL argument");
     if (prog->h != h) return fail(B200ODE_EINVAL, "program was compiled for a different handle");
     if (!prog->everystep) return fail(B200ODE_EINVAL, "program was not compiled with -DB200_EVERYSTEP=1");
-    int rc = check_problem(dp->trajectories, dp->u0, dp->p, prog->np, dp->t0, dp->tf, o);
+    int rc = check_problem(dp->trajectories, dp->u0, dp->p, prog->np, dp->t0, dp->tf, o, prog->reverse);
     if (rc) return rc;
     if (!dr->u_final || !dr->t_final || !dr->naccept || !dr->nreject || !dr->nf || !dr->retcode || !dr->nsaved)
         return fail(B200ODE_EINVAL, "device result arrays u_final,t_final,naccept,nreject,nf,retcode,nsaved are required");
@@ -1519,7 +1577,7 @@ static int everystep_check(b200ode_handle h, b200ode_program prog, const B200Pro
             tmin = i == 0 ? a : std::min(tmin, a); tmax = i == 0 ? b : std::max(tmax, b);
         }
     }
-    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, tmin, tmax, o);
+    int rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, tmin, tmax, o, prog->reverse);
     if (rc) return rc;
     if (!res->u_final) return fail(B200ODE_EINVAL, "result.u_final is required");
     return B200ODE_OK;
@@ -1618,7 +1676,7 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
     if (o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "dense output excludes saveat (dense = save_everystep && isempty(saveat), solve.jl:139)");
     if (o->save_start == 0) return fail(B200ODE_EINVAL, "dense output needs save_start");
     if (hp->tspans) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with per-trajectory time spans");
-    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows), for the composite algorithm or with callbacks");
+    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows), for the composite algorithm, with callbacks or in reverse time");
     for (int j = 1; j < nq; ++j) if (!(tq[j] >= tq[j - 1])) return fail(B200ODE_EINVAL, "tq must be ascending");
     const long long N = hp->trajectories;
     if (N == 0) return B200ODE_OK;
@@ -1665,7 +1723,7 @@ static int solve_host_impl(b200ode_handle h, b200ode_program prog, const B200Pro
     double tmin, tmax; const double* dev_tspans = nullptr;
     int rc = host_tspans(h, hp, &tmin, &tmax, &dev_tspans, h->stream);
     if (rc) return rc;
-    rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, tmin, tmax, o);
+    rc = check_problem(hp->trajectories, hp->u0, hp->p, prog->np, tmin, tmax, o, prog->reverse);
     if (rc) return rc;
     if (hp->tspans && (res->us || stats_only))
         return fail(B200ODE_EUNSUPPORTED, "per-trajectory time spans: the rectangular `us` output and its statistics are not available");
@@ -1997,7 +2055,7 @@ static int multi_run(b200ode_multi m, b200ode_multi_program mp, const B200Proble
     const b200ode_program p0 = mp->prog[0];
     const int n = p0->n, np = p0->np, nsave = p0->nsave;
     const size_t rs = real_size(p0->dtype);
-    int rc = check_problem(N, hp->u0, hp->p, np, hp->t0, hp->tf, o);
+    int rc = check_problem(N, hp->u0, hp->p, np, hp->t0, hp->tf, o, p0->reverse);
     if (rc) return rc;
     if (!mean && (!res || !res->u_final)) return fail(B200ODE_EINVAL, "result.u_final is required");
     const int nslots = nslots_typed(hp, o, p0->dtype);

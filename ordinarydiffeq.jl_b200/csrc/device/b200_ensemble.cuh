@@ -211,6 +211,18 @@ template <int... I> struct B200IdxList { static constexpr int n = (int)sizeof...
 #ifndef B200_TSTOPS
 #define B200_TSTOPS 0         // 1: the tstops keyword (several stop times); 0: tstops = {tf}
 #endif
+
+// B200_REVERSE = 1 (B200ODE_OPT_REVERSE_TIME): tspan[2] < tspan[1], tdir = -1 (solve.jl:273).  The kernels integrate the
+// mirrored problem du/ds = -f(u, p, -s) over (-t0, -tf): every operation of the integrator is an IEEE operation that
+// commutes with negation (round-to-nearest is symmetric), the reference's tdir bookkeeping multiplies both sides of each
+// comparison by tdir, so the mirrored run reproduces the reverse run bit for bit — states, stage derivatives (negated),
+// step sizes (negated), statistics.  The shim wraps the user's functions (RHS and Jacobian negated, every user function
+// sees t = -s: B200_USER_T) and hands the kernels mirrored times; the kernels store times through B200_USER_T.  The two
+// places where the reference itself is not symmetric in tdir (fix_dt_at_bounds!'s dtmin clamp, check_error's tstop
+// comparison) are compiled as the reference writes them for tdir < 0 (see b200_traj_iterate).
+#if B200_REVERSE && (B200_COOP || B200_WIDE)
+#error "reverse-time integration (B200ODE_OPT_REVERSE_TIME) is available in the one-thread-per-trajectory kernel"
+#endif
 #if B200_TSTOPS && B200_COOP
 #error "tstops are not available in the lane-group kernel"
 #endif
@@ -480,8 +492,8 @@ B200_D void b200_emit(const B200Params& P, long long idx, B200Traj& T, real ts, 
 #pragma unroll
         for (int c = 0; c < B200_NSAVE; ++c) T.row[c] = v[B200_SAVE_COMP(c)];
         T.row += B200_NSAVE;
-        *T.trow++ = ts;
-        *T.drow++ = dt_stages;
+        *T.trow++ = B200_USER_T(ts);                 // reverse-time programs run in mirrored time (B200_REVERSE)
+        *T.drow++ = B200_USER_T(dt_stages);
     }
     T.last_t = ts;
 #else
@@ -678,13 +690,22 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
 #endif
     // fix_dt_at_bounds!
     T.dt = b200_min_c(B200_DTMAX, T.dt);
+#if !B200_REVERSE
     T.dt = b200_max_c(dtmin_t, T.dt);
+#endif
+    // (B200_REVERSE: for tdir < 0 the reference takes min(dt, dtmin) against the positive dtmin, integrator_utils.jl:1250-1254 —
+    //  no lower bound on |dt|; only steps that check_error ends anyway can tell the difference)
     b200_modify_dt_for_tstops(P, T, dist, tol100);
     // ---- check_error ---- (flat predicates; the else-if order of the reference decides the code)
     const bool c_nan = b200_isnan(T.dt);
     const bool c_max = ((long long)iter0 + 1 > P.maxiters);
 #if B200_ADAPTIVE
+#if B200_REVERSE
+    // check_error.jl:96 compares `t + dt < tdir * first(opts.tstops)` in both directions; in mirrored time that reads s + ds > stop
+    const bool c_min = (b200_abs(T.dt) <= b200_abs(P.dtmin)) & (!T.accept | (T.t + T.dt > tstop));
+#else
     const bool c_min = (b200_abs(T.dt) <= b200_abs(P.dtmin)) & (!T.accept | (T.t + T.dt < tstop));   // first(opts.tstops) (check_error.jl:93-99)
+#endif
 #else
     const bool c_min = false;
 #endif
@@ -740,7 +761,7 @@ B200_D bool b200_traj_iterate(const B200Params& P, long long idx, B200Traj& T, u
         const B200CtlCfg cfg = b200_ctl_cfg_static();
 #endif
 #ifdef B200_ISOUT
-        const bool isout = B200_ISOUT(T.u, T.p, ttmp) != (real)0;      // opts.isoutofdomain(u, p, ttmp)
+        const bool isout = B200_ISOUT(T.u, T.p, B200_USER_T(ttmp)) != (real)0;      // opts.isoutofdomain(u, p, ttmp)
 #else
         const bool isout = false;
 #endif
@@ -884,7 +905,7 @@ B200_D void b200_traj_end(const B200Params& P, long long idx, B200Traj& T) {
             for (int c = 0; c < B200_N; ++c) dst[c] = T.u[c];
         }
     }
-    P.t_final[idx] = T.t;
+    P.t_final[idx] = B200_USER_T(T.t);
     P.naccept[idx] = T.naccept;
     P.nreject[idx] = T.nreject;
     P.nf[idx] = T.nf;

@@ -406,9 +406,11 @@ def _handle(device):
 
 
 def get_program(handle, alg, fn, n, np_, f32, everystep=False, save_idxs=None, tstops=False, adaptive=True, callbacks=None,
-                vector_tol=False, smem_stages=False, tspans=False):
+                vector_tol=False, smem_stages=False, tspans=False, reverse=False):
     rhs, jac, tg = fn.sources(n, np_, f32, alg.stiff)
     extra = []
+    if reverse:
+        extra.append(_lib.OPT_REVERSE_TIME)
     if tspans:
         extra.append(_lib.OPT_TSPANS)
     if smem_stages:
@@ -541,12 +543,20 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     # Vern7 on a wide state with nothing but start / end rows asked for: the stage derivatives do not fit a thread's
     # registers, so the kernel that keeps them in shared memory runs (B200ODE_OPT_SMEM_STAGES; bit-identical results)
     t0_, tf_ = float(prob.tspan[0]), float(prob.tspan[1])
+    # tspan[2] < tspan[1]: tdir = -1 (solve.jl:273) — a program compiled with B200ODE_OPT_REVERSE_TIME (mirrored-time kernels)
+    reverse = tf_ < t0_
+    if reverse:
+        if cb_specs is not None:
+            raise NotImplementedError("reverse-time integration is not combined with callbacks")
+        if dense_kw:
+            raise NotImplementedError("dense=true is not available in reverse time")
+        dense_ok = False
     # (n >= 24: measured crossover on a cheap-RHS chain system, scripts/time_wide_threshold.py — below it the plain kernel's
     #  local-memory stage vectors, served from L1 at full occupancy, are faster than 112-256 threads with shared-memory stages)
-    smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 24 and not ragged and cb_specs is None
+    smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 24 and not ragged and cb_specs is None and not reverse
                    and all(not (t0_ < float(g) < tf_) for g in (grid or [])))
     program = get_program(handle, alg, prob.f, n, np_, f32, ragged, save_idxs, tstops is not None or discs is not None, adaptive, cb_specs,
-                          vector_tol, smem_stages)
+                          vector_tol, smem_stages, False, reverse)
 
     def run(u0, p, ntraj, flags=0, spans=None):
         common = dict(trajectories=ntraj, reltol=kw.get("reltol"), abstol=kw.get("abstol"), dt=kw.get("dt"),
@@ -563,6 +573,8 @@ def solve(eprob, alg, ensemblealg=None, **kw):
         # expressible as one list
         if tstops is not None or discs is not None or cb_specs is not None:
             raise NotImplementedError("per-trajectory tspan is not combined with tstops, d_discontinuities or callbacks")
+        if reverse or np.any(spans[:, 1] <= spans[:, 0]):
+            raise NotImplementedError("per-trajectory tspan: forward spans only")
         sv = kw.get("saveat", None)
         if sv is not None and not hasattr(sv, "__len__"):
             raise NotImplementedError("per-trajectory tspan with saveat = step: pass the times as a list")

@@ -353,10 +353,13 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     T = eltype(prob.u0)
     T <: Union{Float32, Float64} || throw(ArgumentError("EnsembleB200 supports Float32/Float64 states"))
     t0, tf = Float64.(prob.tspan)
-    tf > t0 || throw(ArgumentError("EnsembleB200 integrates forward in time only"))
+    tf != t0 || throw(ArgumentError("EnsembleB200: tspan must have tf != t0"))
+    # tspan[2] < tspan[1] (tdir = -1, solve.jl:273): a program compiled with B200ODE_OPT_REVERSE_TIME; the saveat list is
+    # handed over in the order the integrator meets it (initialize_saveat, solve.jl:1103-1124)
+    tdir = sign(tf - t0)
     saveat = get(kw, :saveat, ())
-    grid = saveat isa Number ? collect(Float64, (t0 + abs(saveat)):abs(saveat):tf) :
-           sort!(Float64[s for s in saveat if t0 < s <= tf])
+    grid = saveat isa Number ? collect(Float64, (t0 + tdir * abs(saveat)):(tdir * abs(saveat)):tf) :
+           sort!(Float64[s for s in saveat if tdir * t0 < tdir * s <= tdir * tf]; rev = tdir < 0)
     everystep = get(kw, :save_everystep, isempty(grid))            # solve.jl:138
     everystep && ismulti(ens) && throw(ArgumentError("EnsembleB200: save_everystep output is ragged and single-device; pass one device"))
     n, np, rhs, jac, tgr = c_sources(prob, alg, T)
@@ -364,6 +367,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     idxs isa Integer && (idxs = [idxs])
     w = idxs === nothing ? n : length(idxs)                        # components per saved row
     extra = String[]
+    tdir < 0 && push!(extra, "-DB200_REVERSE=1")
     everystep && push!(extra, "-DB200_EVERYSTEP=1")
     idxs === nothing || push!(extra, "-DB200_SAVE_IDXS=" * join(idxs .- 1, ","))   # the C side is 0-based
     tstops = collect(Float64, get(kw, :tstops, ()))
@@ -390,6 +394,8 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     (isempty(rtv) && isempty(atv)) || push!(extra, "-DB200_VECTOR_TOL=1")
     # prob_func remakes tspan (probed on trajectory 1): per-trajectory spans — final states or the ragged output only
     tspans_variant = eprob.prob_func(prob, SciMLBase.EnsembleContext(1, 1, nothing)).tspan != prob.tspan
+    tdir < 0 && (tspans_variant || !isempty(cbs)) &&
+        throw(ArgumentError("EnsembleB200: reverse-time integration is not combined with callbacks or per-trajectory tspan"))
     if tspans_variant
         (isempty(tstops) && isempty(discs) && isempty(cbs)) ||
             throw(ArgumentError("EnsembleB200: per-trajectory tspan is not combined with tstops, d_discontinuities or callbacks"))
@@ -399,7 +405,7 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     end
     # Vern7 on a wide state with nothing but start / end rows: the kernel that keeps k1..k10 in shared memory
     # (B200ODE_OPT_SMEM_STAGES; bit-identical results, it serves no interior saveat rows and no callbacks)
-    if alg isa Vern7 && n >= 24 && !everystep && isempty(cbs)       # measured crossover: scripts/time_wide_threshold.py
+    if alg isa Vern7 && n >= 24 && !everystep && isempty(cbs) && tdir > 0       # measured crossover: scripts/time_wide_threshold.py
         t0w, tfw = prob.tspan
         grid_pts = saveat isa Number ? (saveat > 0 && saveat < abs(tfw - t0w) ? (1,) : ()) : filter(t -> t0w < t < tfw, collect(saveat))
         isempty(grid_pts) && push!(extra, "-DB200_WIDE=1")

@@ -71,17 +71,21 @@ def julia_range(start, step, stop):
 
 
 def saveat_grid(saveat, tspan):
-    """initialize_saveat (lib/OrdinaryDiffEqCore/src/solve.jl:1103-1124), forward time.
+    """initialize_saveat (lib/OrdinaryDiffEqCore/src/solve.jl:1103-1124).
 
-    Returns the ascending list of save times in (t0, tf]."""
+    Returns the save times in the order the integrator meets them — ascending for tf > t0, descending for a reversed
+    span (the reference's heap orders by tdir * t): a number h gives (t0 + tdir |h|):(tdir |h|):tf, a list keeps its
+    entries with tdir t0 < tdir t <= tdir tf."""
     t0, tf = float(tspan[0]), float(tspan[1])
+    tdir = -1.0 if tf < t0 else 1.0
     if saveat is None:
         return []
     if isinstance(saveat, (int, float)):
-        h = abs(float(saveat))
+        h = tdir * abs(float(saveat))                   # directional_saveat
         return julia_range(t0 + h, h, tf)
     vals = [float(t) for t in saveat]
-    return [t for t in vals if t0 < t <= tf]
+    kept = [t for t in vals if tdir * t0 < tdir * t <= tdir * tf]
+    return kept if tdir > 0 else sorted(kept, reverse=True)
 
 
 def resolve_save_flags(saveat, tspan, save_everystep, save_start=None, save_end=None):

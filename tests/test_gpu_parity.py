@@ -1518,3 +1518,155 @@ def test_discrete_callbacks_with_every_stepper(pkg, handle, oracle, name):
     with pytest.raises(pkg.B200Error):          # continuous callbacks stay with Tsit5
         handle.compile(alg, pkg.F64, 3, 3, *args, extra_options=pkg._lib.OPT_EVERYSTEP,
                        callbacks=[dict(kind="continuous", condition=dcond, affect=kick)])
+
+
+def _nonautonomous_sources(f32):
+    """A non-autonomous 3-state kinetics-like system with analytic Jacobian and time gradient (the reverse-time tests need
+    every user function to depend on t)."""
+    T = "float" if f32 else "double"
+    s = "f" if f32 else ""
+    d = dict(T=T, s=s)
+    rhs = ("void na_rhs(%(T)s* du, const %(T)s* u, const %(T)s* p, const %(T)s t) {\n"
+           "  du[0] = -p[0]*u[0] + p[1]*u[1]*u[2] + t*u[2];\n"
+           "  du[1] = p[0]*u[0] - p[1]*u[1]*u[2] - p[2]*u[1]*u[1] + t*t;\n"
+           "  du[2] = p[2]*u[1]*u[1] - 0.5%(s)s*u[2]*t;\n}\n" % d, "na_rhs")
+    jac = ("void na_jac(%(T)s* J, const %(T)s* u, const %(T)s* p, const %(T)s t) {\n"
+           "  J[0] = -p[0]; J[1] = p[0]; J[2] = 0.0%(s)s;\n"
+           "  J[3] = p[1]*u[2]; J[4] = -p[1]*u[2] - 2.0%(s)s*p[2]*u[1]; J[5] = 2.0%(s)s*p[2]*u[1];\n"
+           "  J[6] = p[1]*u[1] + t; J[7] = -p[1]*u[1]; J[8] = -0.5%(s)s*t;\n}\n" % d, "na_jac")
+    tg = ("void na_tgrad(%(T)s* dT, const %(T)s* u, const %(T)s* p, const %(T)s t) {\n"
+          "  dT[0] = u[2]; dT[1] = 2.0%(s)s*t; dT[2] = -0.5%(s)s*u[2];\n}\n" % d, "na_tgrad")
+    return rhs, jac, tg
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_reverse_time(pkg, handle, oracle, f32):
+    """tspan[2] < tspan[1] (tdir = -1): programs compiled with B200ODE_OPT_REVERSE_TIME integrate the mirrored problem
+    du/ds = -f(u, p, -s); the oracle restates the reference's direction handling natively (solve.jl:273,401,1025-1037,
+    1107-1120; integrator_utils.jl:268-324,343-348,1193-1207,1243-1256; initdt.jl) and replays its reverse-time known
+    answers (tests/test_oracle_properties.py).  Bit-exact GPU vs oracle: final states, statistics, times; rectangular
+    saveat rows (descending list), tstops + d_discontinuities, a user dt of either sign, dtmax, fixed steps, ragged
+    rows, isoutofdomain; Tsit5, Vern7, DP5, Rosenbrock23, Rodas5P, AutoTsit5(Rosenbrock23())."""
+    L = pkg._lib
+    rdt = np.float32 if f32 else np.float64
+    dtype = pkg.F32 if f32 else pkg.F64
+    rng = np.random.default_rng(5)
+    N = 400
+    u0 = rng.uniform(0.1, 1.0, (N, 3)).astype(rdt)
+    p = rng.uniform(0.5, 3.0, (N, 3)); p[:, 1] *= 30; p = p.astype(rdt)
+    rhs, jac, tg = _nonautonomous_sources(f32)
+    tspan = (2.0, 0.25)
+    grid = [1.75, 1.5, 1.0, 0.3, 0.25]
+    tol = dict(reltol=1e-4, abstol=1e-6) if f32 else dict(reltol=1e-6, abstol=1e-8)
+    R = L.OPT_REVERSE_TIME
+    algs = [(pkg.ALG_TSIT5, oracle.ALG_TSIT5, False), (pkg.ALG_VERN7, oracle.ALG_VERN7, False), (pkg.ALG_DP5, oracle.ALG_DP5, False),
+            (pkg.ALG_ROSENBROCK23, oracle.ALG_ROSENBROCK23, True), (pkg.ALG_RODAS5P, oracle.ALG_RODAS5P, True),
+            (pkg.ALG_AUTOTSIT5_ROSENBROCK23, oracle.ALG_AUTOTSIT5_ROSENBROCK23, True)]
+    for alg, oalg, stiff in algs:
+        extra = dict(jac_src=jac[0], jac_name=jac[1], tgrad_src=tg[0], tgrad_name=tg[1]) if stiff else {}
+        okw = dict(jac=jac, tgrad=tg) if stiff else {}
+        prog = handle.compile(alg, dtype, 3, 3, rhs[0], rhs[1], extra_options=R + " " + L.OPT_TSTOPS, **extra)
+        try:
+            for kw in (dict(), dict(saveat=grid), dict(saveat=grid, save_start=False, save_end=False),
+                       dict(saveat=grid, tstops=[1.2, 0.7, 5.0], d_discontinuities=[1.0, 2.0]),
+                       dict(dtmax=0.05), dict(dt=0.01, saveat=grid), dict(dt=-0.01)):
+                g = pkg.lowlevel.solve_host(prog, u0, p, tspan, **dict(kw, **tol))
+                o = oracle.solve(oalg, rhs, u0, p, tspan, 3, 3, f32=f32, **dict(kw, **tol, **okw))
+                assert_same_result(g, o)
+                assert (g["retcode"] == 1).all() and (g["t_final"] == tspan[1]).all()
+            # forward spans are refused by a reverse-time program, reversed spans by an ordinary one
+            with pytest.raises(L.B200Error):
+                pkg.lowlevel.solve_host(prog, u0, p, (0.25, 2.0))
+        finally:
+            prog.close()
+    plain = handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, rhs[0], rhs[1])
+    try:
+        with pytest.raises(L.B200Error):
+            pkg.lowlevel.solve_host(plain, u0, p, tspan)
+    finally:
+        plain.close()
+    # fixed steps (adaptive = false): dt = -1/64 with a stop that is not a multiple of it
+    prog = handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, rhs[0], rhs[1], extra_options=" ".join((R, L.OPT_TSTOPS, L.OPT_FIXED_DT)))
+    try:
+        kw = dict(dt=-1.0 / 64, tstops=[1.01], saveat=grid)
+        g = pkg.lowlevel.solve_host(prog, u0, p, tspan, **kw)
+        o = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, tspan, 3, 3, f32=f32, adaptive=False, **kw)
+        assert_same_result(g, o)
+    finally:
+        prog.close()
+    # ragged per-step rows: times come back as the caller's (descending), Tsit5 and Rodas5P
+    for alg, oalg, stiff in (algs[0], algs[4]):
+        extra = dict(jac_src=jac[0], jac_name=jac[1], tgrad_src=tg[0], tgrad_name=tg[1]) if stiff else {}
+        okw = dict(jac=jac, tgrad=tg) if stiff else {}
+        prog = handle.compile(alg, dtype, 3, 3, rhs[0], rhs[1], extra_options=R + " " + L.OPT_EVERYSTEP, **extra)
+        try:
+            g = pkg.lowlevel.solve_host_everystep(prog, u0, p, tspan, saveat=[1.5, 1.0], **tol)
+            o = oracle.solve(oalg, rhs, u0, p, tspan, 3, 3, f32=f32, save_everystep=True, saveat=[1.5, 1.0], **tol, **okw)
+            assert np.array_equal(g["row_offsets"], o["row_offsets"]) and np.array_equal(g["ts"], o["ts"])
+            assert np.array_equal(bits(g["us"]), bits(o["us"]))
+            assert np.all(np.diff(np.asarray(g["ts"][:o["row_offsets"][1]], dtype=np.float64)) < 0)
+            with pytest.raises(L.B200Error):       # no dense output in reverse time
+                pkg.lowlevel.solve_host_dense(prog, u0, p, tspan, [1.0])
+        finally:
+            prog.close()
+    # isoutofdomain sees the caller's time: reject every step that ends in (0.9, 1.1) with u[0] above a threshold
+    T = "float" if f32 else "double"
+    dom = ("%s na_dom(const %s* u, const %s* p, const %s t) { return (t < 1.1 && t > 0.9 && u[0] > 0.05) ? 1 : 0; }\n" % (T, T, T, T), "na_dom")
+    cbs = [dict(kind="isoutofdomain", condition=dom)]
+    prog = handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, rhs[0], rhs[1], extra_options=R, callbacks=cbs)
+    try:
+        g = pkg.lowlevel.solve_host(prog, u0, p, tspan, maxiters=3000, **tol)
+        o = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, tspan, 3, 3, f32=f32, callbacks=cbs, maxiters=3000, **tol)
+        assert_same_result(g, o)
+        ref = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, tspan, 3, 3, f32=f32, **tol)
+        assert (o["nreject"] != ref["nreject"]).any()          # the domain test did act
+    finally:
+        prog.close()
+    # combinations that are declined at compile time
+    from helpers import ball_sources
+    ball = ball_sources(f32)
+    with pytest.raises(L.B200Error):
+        handle.compile(pkg.ALG_TSIT5, dtype, 2, 2, ball[0][0], ball[0][1], extra_options=R + " " + L.OPT_EVERYSTEP,
+                       callbacks=[dict(kind="continuous", condition=ball[1], affect=ball[2])])
+    with pytest.raises(L.B200Error):
+        handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, rhs[0], rhs[1], extra_options=R + " " + L.OPT_TSPANS)
+
+
+def test_high_level_solve_in_reverse_time(pkg, oracle):
+    """solve(EnsembleProblem(ODEProblem(f, u0, (10.0, 0.0), p); prob_func), alg, EnsembleB200(); saveat = 0.1, ...): the grid is
+    (t0 - h):-h:tf in the reference's range arithmetic, sol.t runs downwards; explicit and stiff stepper."""
+    P = pkg
+    pl = P.problems_library
+    N = 128
+    table = pl.lorenz_params(N)
+    prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (1.0, 0.0), table[0])
+    ep = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table))
+    grid = P.ranges.saveat_grid(0.1, (1.0, 0.0))
+    assert grid == P.ranges.julia_range(0.9, -0.1, 0.0) and grid[-1] == 0.0
+    o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (1.0, 0.0), 3, 3, saveat=grid)
+    s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.1)
+    for i in (0, 5, N - 1):
+        assert s[i].retcode == "Success" and list(s[i].t) == [1.0] + grid
+        assert np.array_equal(bits(np.ascontiguousarray(s[i].u)), bits(o["us"][i]))
+        assert s[i].stats.naccept == o["naccept"][i] and s[i].stats.nreject == o["nreject"][i]
+    # default output (every step), a list saveat given in ascending order, tstops
+    oe = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (1.0, 0.0), 3, 3, save_everystep=True, tstops=[0.5])
+    s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, tstops=[0.5])
+    a, b = oe["row_offsets"][3], oe["row_offsets"][4]
+    assert np.array_equal(np.asarray(s[3].t), oe["ts"][a:b]) and 0.5 in list(s[3].t) and s[3].t[0] == 1.0 and s[3].t[-1] == 0.0
+    assert np.array_equal(bits(np.ascontiguousarray(s[3].u)), bits(oe["us"][a:b]))
+    s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=[0.0, 0.25, 0.5, 1.0])
+    assert list(s[0].t) == [1.0, 0.5, 0.25, 0.0]
+    with pytest.raises(NotImplementedError):
+        P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, dense=True)
+    # Robertson backwards over a short span with Rodas5P
+    (r, rn), (j, jn), (tg, tgn) = pl.robertson_sources()
+    pr = pl.robertson_params(N)
+    u1 = np.array([0.9, 2e-5, 0.1])
+    probr = P.ODEProblem(P.ODEFunction(P.CSource(r, rn), jac=P.CSource(j, jn), tgrad=P.CSource(tg, tgn)), u1, (1.0, 0.99), pr[0])
+    epr = P.EnsembleProblem(probr, prob_func=P.TableProbFunc(p=pr))
+    orr = oracle.solve(oracle.ALG_RODAS5P, (r, rn), u1, pr, (1.0, 0.99), 3, 3, jac=(j, jn), tgrad=(tg, tgn))
+    s = P.solve(epr, P.Rodas5P(), P.EnsembleB200(), trajectories=N, save_everystep=False)
+    for i in (0, N - 1):
+        assert list(s[i].t) == [1.0, 0.99] and np.array_equal(bits(np.ascontiguousarray(s[i].u[-1])), bits(orr["u_final"][i]))
+        assert s[i].stats.naccept == orr["naccept"][i] and s[i].retcode == "Success"

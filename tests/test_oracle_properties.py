@@ -518,6 +518,95 @@ def test_reference_tstops_known_answers():
     assert len(got) == 11 and got[-1] == 1.0
 
 
+def test_reference_backwards_known_answers():
+    """Reverse time (tspan[2] < tspan[1], tdir = -1), the reference's own known answers:
+    test/InterfaceI/ode_backwards_test.jl:8-15, ode_tstops_tests.jl:264-276 (d_discontinuities shift with prevfloat),
+    :290-294 (fixed dt = -0.1 hits tspan[end] cleanly), ode_initdt_tests.jl:134-152 (the initial-dt probe respects the
+    first stop).  The step grid of fixed-step runs is algorithm independent, so the RK4 / Euler expectations hold for Tsit5."""
+    s = linear_source()
+    u0 = np.array([[0.5]])
+
+    def ts(alg, **kw):
+        return list(oracle.solve(alg, s, u0, None, (1.0, 0.0), 1, 0, save_everystep=True, **kw)["ts"])
+    # sol = solve(prob2, DP5(), dt = -1/4, tstops = [0.5]);  sol.t == [1.0, 0.75, 0.5, 0]
+    assert ts(oracle.ALG_DP5, dt=-0.25, tstops=[0.5]) == [1.0, 0.75, 0.5, 0.0]
+    # RK4, dt = -1/4, adaptive = false  =>  [1.0, 0.75, 0.5, 0.25, 0]
+    assert ts(oracle.ALG_TSIT5, dt=-0.25, adaptive=False) == [1.0, 0.75, 0.5, 0.25, 0.0]
+    # tstops = [0.5, 0.33], adaptive = false  =>  ≈ [1.0, 0.75, 0.5, 0.33, 0.08, 0]
+    got = ts(oracle.ALG_TSIT5, dt=-0.25, tstops=[0.5, 0.33], adaptive=False)
+    assert len(got) == 6 and np.allclose(got, [1.0, 0.75, 0.5, 0.33, 0.08, 0.0], rtol=1e-8, atol=1e-14)
+    # ode_tstops_tests.jl:290-294: 11 rows, the last one is tspan[end]
+    got = ts(oracle.ALG_TSIT5, dt=-0.1, adaptive=False)
+    assert len(got) == 11 and got[-1] == 0.0
+    # ode_tstops_tests.jl:264-276: f = t > 5 ? 1 : 0, u(10) = 5 integrated back to t = 0 with the discontinuity declared
+    step = ("void stepf(double* du, const double* u, const double* p, const double t) { du[0] = t > 5.0 ? 1.0 : 0.0; }\n", "stepf")
+    o = oracle.solve(oracle.ALG_TSIT5, step, np.array([[5.0]]), None, (10.0, 0.0), 1, 0, d_discontinuities=[5.0],
+                     reltol=1e-12, abstol=1e-14, save_everystep=True)
+    assert o["retcode"][0] == 1 and abs(o["u_final"][0, 0]) <= 1e-10
+    k = list(o["ts"]).index(5.0)
+    # the step after the stop starts one ulp BELOW 5 (prevfloat), where the slope is 0: u stays put from there on and 5.0
+    # is followed by prevfloat(5.0) + dt (the step INTO the stop evaluates its last stage at exactly 5, on the other side of
+    # the jump, so rejections before it are the problem's own)
+    assert np.all(o["us"][k:, 0] == o["us"][k, 0]) and o["ts"][k + 1] < 5.0
+    # ode_initdt_tests.jl:134-152: no RHS evaluation of init() lies beyond the first stop, in either direction
+    probe = ("#include <stdio.h>\nvoid probe(double* du, const double* u, const double* p, const double t) {\n"
+             "  du[0] = (t < 9.999) ? 0.0 / 0.0 : -u[0]; }\n", "probe")      # NaN beyond the stop: the run would fail at once
+    for kwd in ("tstops", "d_discontinuities"):
+        o = oracle.solve(oracle.ALG_TSIT5, probe, np.array([[1.0]]), None, (10.0, 0.0), 1, 0, maxiters=1, **{kwd: [9.999]})
+        assert o["naccept"][0] == 1 and o["t_final"][0] >= np.nextafter(9.999, 0.0) and np.isfinite(o["u_final"][0, 0])
+
+
+_MIRROR_F = """void mf(double* du, const double* u, const double* p, const double t) {
+  du[0] = -p[0]*u[0] + p[1]*u[1]*u[2] + t*u[2];
+  du[1] = p[0]*u[0] - p[1]*u[1]*u[2] - p[2]*u[1]*u[1] + t*t;
+  du[2] = p[2]*u[1]*u[1] - 0.5*u[2]*t; }
+void mjac(double* J, const double* u, const double* p, const double t) {
+  J[0] = -p[0]; J[1] = p[0]; J[2] = 0.0;
+  J[3] = p[1]*u[2]; J[4] = -p[1]*u[2] - 2.0*p[2]*u[1]; J[5] = 2.0*p[2]*u[1];
+  J[6] = p[1]*u[1] + t; J[7] = -p[1]*u[1]; J[8] = -0.5*t; }
+void mtg(double* dT, const double* u, const double* p, const double t) {
+  dT[0] = u[2]; dT[1] = 2.0*t; dT[2] = -0.5*u[2]; }
+"""
+# the mirrored problem: g(u, s) = -f(u, -s), dg/du = -J(u, -s), dg/ds = +f_t(u, -s)
+_MIRROR_G = _MIRROR_F.replace("void mf(", "static void f0(").replace("void mjac(", "static void jac0(").replace("void mtg(", "static void tg0(") + """
+void mf(double* du, const double* u, const double* p, const double s) { f0(du, u, p, -s); for (int i = 0; i < 3; ++i) du[i] = -du[i]; }
+void mjac(double* J, const double* u, const double* p, const double s) { jac0(J, u, p, -s); for (int i = 0; i < 9; ++i) J[i] = -J[i]; }
+void mtg(double* dT, const double* u, const double* p, const double s) { tg0(dT, u, p, -s); }
+"""
+
+
+@pytest.mark.parametrize("alg", ["TSIT5", "VERN7", "DP5", "BS3", "VERN9", "ROSENBROCK23", "ROSENBROCK32", "RODAS5P", "RODAS4", "RODAS3P",
+                                 "AUTOTSIT5_ROSENBROCK23"])
+def test_reverse_time_equals_the_mirrored_forward_problem(alg):
+    """The property the CUDA path's reverse-time programs rest on (B200ODE_OPT_REVERSE_TIME): the oracle's direction-aware
+    integrator (tdir = -1 restated from the reference) on (t0, tf), tf < t0, gives bit for bit what its forward integrator
+    gives for du/ds = -f(u, p, -s) on (-t0, -tf) — states, rows, statistics; times negated — with tstops,
+    d_discontinuities, dtmax, a user dt and fixed steps; non-autonomous RHS, Jacobian and time gradient."""
+    a = getattr(oracle, "ALG_" + alg)
+    stiff = alg.startswith("RO") or alg.startswith("AUTO")
+    rng = np.random.default_rng(1)
+    N = 24
+    u0 = rng.uniform(0.1, 1.0, (N, 3)); p = rng.uniform(0.5, 3.0, (N, 3)); p[:, 1] *= 30
+    t0, tf = 2.0, 0.25
+    sa = [1.75, 1.5, 1.0, 0.3, 0.25]
+    kw = dict(jac=("", "mjac"), tgrad=("", "mtg")) if stiff else {}
+    keys = ("u_final", "us", "naccept", "nreject", "nf", "njacs", "nw", "nsolve", "retcode", "nsaved")
+    for extra in (dict(), dict(tstops=[1.2, 0.7], d_discontinuities=[1.0]), dict(dtmax=0.05), dict(dt=0.01),
+                  dict(adaptive=False, dt=-0.01), dict(save_everystep=True)):
+        em = dict(extra)
+        for k in ("tstops", "d_discontinuities"):
+            if k in em:
+                em[k] = [-x for x in em[k]]
+        if em.get("adaptive") is False:
+            em["dt"] = -em["dt"]
+        r = oracle.solve(a, (_MIRROR_F, "mf"), u0, p, (t0, tf), 3, 3, saveat=sa, reltol=1e-6, abstol=1e-8, **kw, **extra)
+        m = oracle.solve(a, (_MIRROR_G, "mf"), u0, p, (-t0, -tf), 3, 3, saveat=[-x for x in sa], reltol=1e-6, abstol=1e-8, **kw, **em)
+        for k in keys:
+            assert np.array_equal(r[k], m[k]), (alg, extra, k)
+        assert np.array_equal(r["t_final"], -m["t_final"]) and np.array_equal(r["ts"], -np.asarray(m["ts"])), (alg, extra)
+        assert np.all(r["retcode"] == 1) and np.all(r["t_final"] == tf)
+
+
 def test_reference_saveat_bookkeeping_known_answers():
     # test/InterfaceI/ode_saveat_tests.jl:214-220: save_everystep = false keeps [t0, tf]; with maxiters = 3 the failed
     # solve still has two entries (start + the point it reached)
@@ -529,12 +618,13 @@ def test_reference_saveat_bookkeeping_known_answers():
     assert o["nsaved"][0] == 2 and o["retcode"][0] == 2 and o["t_final"][0] < 1.0
 
 
-def test_reference_saveat_defaults_known_answers(pkg):
-    """test/InterfaceI/ode_saveat_tests.jl:11-41 replayed through the host layer's keyword resolution
-    (ranges.saveat_grid + ranges.resolve_save_flags) and the oracle, with DP5 and dt = 1/4 as in the reference."""
+@pytest.mark.parametrize("span", [(0.0, 1.0), (1.0, 0.0)])
+def test_reference_saveat_defaults_known_answers(pkg, span):
+    """test/InterfaceI/ode_saveat_tests.jl:5-41 (`for prob in [prob_forward, prob_reverse]`) replayed through the host
+    layer's keyword resolution (ranges.saveat_grid + ranges.resolve_save_flags) and the oracle, with DP5 and dt = 1/4
+    (positive in both directions, auto-converted for the reversed span) as in the reference."""
     s = linear_source()
     u0 = np.array([[0.5]])
-    span = (0.0, 1.0)
 
     def sol_t(saveat=None, tstops=None, save_everystep=None):
         has = saveat is not None and not (hasattr(saveat, "__len__") and len(saveat) == 0)
@@ -546,17 +636,19 @@ def test_reference_saveat_defaults_known_answers(pkg):
         if every:
             return list(o["ts"])
         if not grid:                                    # no saveat: the final-only path reports [t0, t_end]
-            return ([0.0] if ss else []) + ([float(o["t_final"][0])] if se is None or se else [])
+            return ([span[0]] if ss else []) + ([float(o["t_final"][0])] if se is None or se else [])
         return list(o["ts"][:o["nsaved"][0]])
     base = sol_t(save_everystep=False)
-    assert base == [0.0, 1.0]
+    assert base == [span[0], span[1]]
     assert sorted(set(base) ^ set(sol_t(saveat=[0.5], save_everystep=False))) == [0.0, 0.5, 1.0]      # :12-14
     assert sorted(set(base) ^ set(sol_t(saveat=[0.0, 0.5, 1.0], save_everystep=False))) == [0.5]      # :16-21
     assert sorted(set(base) ^ set(sol_t(saveat=0.5, save_everystep=False))) == [0.5]                  # :23-25
     assert sol_t(saveat=[0.5], tstops=[0.5], save_everystep=False) == [0.5]                           # :27-32
-    assert sol_t(saveat=[0.0, 0.5, 1.0], tstops=[0.5]) == [0.0, 0.5, 1.0]                             # :34-36
-    # :38-41  saveat = 1/10, tstops = [1/2]  =>  sol3.t == collect(0.0:0.1:1.0) (exactly the range's values)
-    assert sol_t(saveat=0.1, tstops=[0.5]) == pkg.ranges.julia_range(0.0, 0.1, 1.0)
+    # :34-36  tdir > 0 ? sol3.t == [0.0, 1/2, 1.0] : sol3.t == [1.0, 1/2, 0.0]
+    assert sol_t(saveat=[0.0, 0.5, 1.0], tstops=[0.5]) == ([0.0, 0.5, 1.0] if span[1] > span[0] else [1.0, 0.5, 0.0])
+    # :38-41  saveat = 1/10, tstops = [1/2]  =>  sol3.t == collect(0.0:0.1:1.0) / collect(1.0:-0.1:0.0) (exactly the range's values)
+    step = 0.1 if span[1] > span[0] else -0.1
+    assert sol_t(saveat=0.1, tstops=[0.5]) == pkg.ranges.julia_range(span[0], step, span[1])
 
 
 @pytest.mark.parametrize("alg", ["ros23", "ros32", "rodas4", "rodas4p", "rodas5", "rodas5p", "rodas5pe", "rodas42", "rodas4p2"])
