@@ -1588,10 +1588,14 @@ def test_reverse_time(pkg, handle, oracle, f32):
     # fixed steps (adaptive = false): dt = -1/64 with a stop that is not a multiple of it
     prog = handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, rhs[0], rhs[1], extra_options=" ".join((R, L.OPT_TSTOPS, L.OPT_FIXED_DT)))
     try:
-        kw = dict(dt=-1.0 / 64, tstops=[1.01], saveat=grid)
+        kw = dict(dt=-1.0 / 256, tstops=[1.01], saveat=grid)
         g = pkg.lowlevel.solve_host(prog, u0, p, tspan, **kw)
         o = oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, tspan, 3, 3, f32=f32, adaptive=False, **kw)
-        assert_same_result(g, o)
+        # (a fixed-step run of a stiff member may blow up: the sign bit of a NaN is the one thing negation does not mirror)
+        fin = np.isfinite(o["u_final"]).all(axis=1)
+        assert fin.sum() > N // 2 and np.array_equal(np.isfinite(g["u_final"]).all(axis=1), fin)
+        assert_same_result({k: (v[fin] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in g.items()},
+                           {k: (v[fin] if isinstance(v, np.ndarray) and v.shape[:1] == (N,) else v) for k, v in o.items()})
     finally:
         prog.close()
     # ragged per-step rows: times come back as the caller's (descending), Tsit5 and Rodas5P
@@ -1667,6 +1671,8 @@ def test_high_level_solve_in_reverse_time(pkg, oracle):
     epr = P.EnsembleProblem(probr, prob_func=P.TableProbFunc(p=pr))
     orr = oracle.solve(oracle.ALG_RODAS5P, (r, rn), u1, pr, (1.0, 0.99), 3, 3, jac=(j, jn), tgrad=(tg, tgn))
     s = P.solve(epr, P.Rodas5P(), P.EnsembleB200(), trajectories=N, save_everystep=False)
-    for i in (0, N - 1):
-        assert list(s[i].t) == [1.0, 0.99] and np.array_equal(bits(np.ascontiguousarray(s[i].u[-1])), bits(orr["u_final"][i]))
-        assert s[i].stats.naccept == orr["naccept"][i] and s[i].retcode == "Success"
+    assert (orr["retcode"] == 1).sum() > N // 2 and (orr["retcode"] != 1).any()     # backwards Robertson is unstable for some members
+    for i in (0, 1, int(np.argmax(orr["retcode"] != 1)), N - 1):
+        assert list(s[i].t) == [1.0, orr["t_final"][i]] and np.array_equal(bits(np.ascontiguousarray(s[i].u[-1])), bits(orr["u_final"][i]))
+        assert s[i].stats.naccept == orr["naccept"][i] and s[i].stats.nreject == orr["nreject"][i]
+        assert (s[i].retcode == "Success") == (orr["retcode"][i] == 1) and (orr["retcode"][i] != 1 or s[i].t[-1] == 0.99)
