@@ -135,6 +135,20 @@ let
                                       "trajectories" => NTRAJ, "julia" => string(VERSION)])
 end
 
+# reverse time (tspan[2] < tspan[1], tdir = -1): Lorenz backwards with a saveat step and a stop, Robertson backwards over
+# a short span with Rodas5P (the CUDA path integrates the mirrored problem, B200ODE_OPT_REVERSE_TIME)
+let
+    P = [SVector(10.0, 28.0 * (0.5 + U(i - 1, 0)), 8 / 3) for i in 1:NTRAJ]
+    prob = ODEProblem{false}(lorenz, SVector(1.0, 0.0, 0.0), (1.0, 0.0), P[1])
+    run_case("lorenz_tsit5_reverse", prob, P, nothing, Tsit5(); saveat = 0.1, tstops = [0.5])
+    run_case("lorenz_vern7_reverse", prob, P, nothing, Vern7(); reltol = 1e-8, abstol = 1e-10, save_everystep = false)
+    base = (0.04, 3.0e7, 1.0e4)
+    PR = [SVector(ntuple(j -> base[j] * (0.5 + U(i - 1, j - 1)), 3)) for i in 1:NTRAJ]
+    f = ODEFunction{false}(rober; jac = rober_jac, tgrad = rober_tgrad)
+    probr = ODEProblem(f, SVector(1.0, 0.0, 0.0), (1.0e-3, 0.0), PR[1])
+    run_case("robertson_rodas5p_reverse", probr, PR, nothing, Rodas5P(); reltol = 1e-6, abstol = 1e-8, save_everystep = false)
+end
+
 # config 3: Robertson, Rodas5P and Rosenbrock23 (+ the RodasTableau family), jac + tgrad supplied
 let
     base = (0.04, 3.0e7, 1.0e4)

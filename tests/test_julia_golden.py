@@ -44,6 +44,10 @@ CASES = {
     "lorenz_tsit5_d_discontinuities": ("ALG_TSIT5", "lorenz", False, dict(d_discontinuities=[2.5, 5.0], tstops=[7.5], saveat=0.5)),
     "lorenz_vern7_d_discontinuities": ("ALG_VERN7", "lorenz", False, dict(d_discontinuities=[0.0, 2.5])),
     "lorenz_tsit5_tspans": ("ALG_TSIT5", "lorenz", False, dict(_tspans=True)),
+    # reverse time (tspan[2] < tspan[1]); _tspan overrides the problem's span
+    "lorenz_tsit5_reverse": ("ALG_TSIT5", "lorenz", False, dict(_tspan=(1.0, 0.0), saveat=0.1, tstops=[0.5])),
+    "lorenz_vern7_reverse": ("ALG_VERN7", "lorenz", False, dict(_tspan=(1.0, 0.0), reltol=1e-8, abstol=1e-10)),
+    "robertson_rodas5p_reverse": ("ALG_RODAS5P", "robertson", False, dict(_tspan=(1e-3, 0.0), reltol=1e-6, abstol=1e-8)),
 }
 
 
@@ -68,6 +72,8 @@ def _setup(pkg, problem, f32, N):
 def _spans(pkg, kw, tspan, N):
     """tspan argument of the case: the shared span, or (cases with _tspans) the per-trajectory spans the generator's
     prob_func builds: (0, 5 + 5 U(i, 1))."""
+    if kw.get("_tspan"):
+        return kw["_tspan"]
     if not kw.get("_tspans"):
         return tspan
     idx = np.arange(N, dtype=np.uint64)
@@ -81,6 +87,8 @@ def _options(pkg, kw):
         opts.append(pkg._lib.OPT_TSTOPS)
     if kw.get("_tspans"):
         opts.append(pkg._lib.OPT_TSPANS)
+    if kw.get("_tspan") and kw["_tspan"][1] < kw["_tspan"][0]:
+        opts.append(pkg._lib.OPT_REVERSE_TIME)
     return " ".join(opts) or None
 
 
@@ -126,7 +134,7 @@ def test_oracle_matches_julia_reference(pkg, stem):
     algname, problem, f32, kw = CASES[stem]
     rhs, jac, tg, u0, p, tspan, n, np_ = _setup(pkg, problem, f32, gold["trajectories"])
     span = _spans(pkg, kw, tspan, gold["trajectories"])
-    kw = {k: v for k, v in _grid(pkg, kw, tspan).items() if not k.startswith("_")}
+    kw = {k: v for k, v in _grid(pkg, kw, kw.get("_tspan", tspan)).items() if not k.startswith("_")}
     o = oracle.solve(getattr(oracle, algname), rhs, u0, p, span, n, np_, f32=f32, jac=jac, tgrad=tg, **kw)
     _compare(o, gold, f32, kw.get("reltol", 1e-3))
 
@@ -139,7 +147,7 @@ def test_cuda_path_matches_julia_reference(pkg, handle, stem):
     rhs, jac, tg, u0, p, tspan, n, np_ = _setup(pkg, problem, f32, gold["trajectories"])
     span = _spans(pkg, kw, tspan, gold["trajectories"])
     extra = _options(pkg, kw)
-    kw = {k: v for k, v in _grid(pkg, kw, tspan).items() if not k.startswith("_")}
+    kw = {k: v for k, v in _grid(pkg, kw, kw.get("_tspan", tspan)).items() if not k.startswith("_")}
     prog = handle.compile(getattr(pkg, algname), pkg.F32 if f32 else pkg.F64, n, np_, rhs[0], rhs[1],
                           jac[0] if jac else None, jac[1] if jac else None, tg[0] if tg else None, tg[1] if tg else None,
                           extra_options=extra)
