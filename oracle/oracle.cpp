@@ -954,13 +954,14 @@ static void dense_one(const ProblemFns<R>& P, const R* u0, const R* p, R t0, R t
     solve_one<R, Alg>(P, u0, p, t0, tf, o, idx, out);
     const int n = P.n;
     const int nrows = (int)sink.ts.size();
+    const R tdir = tf < t0 ? (R)-1 : (R)1;
     R* dst = dense_out + (size_t)idx * M * n;
     int hi = 1;
     for (int j = 0; j < M; ++j) {
         const R t = tq[j];
         R* v = dst + (size_t)j * n;
         if (nrows < 2) { for (int i = 0; i < n; ++i) v[i] = nrows == 1 ? sink.us[i] : (R)0; continue; }
-        while (hi < nrows - 1 && sink.ts[hi] < t) hi += 1;
+        while (hi < nrows - 1 && tdir * sink.ts[hi] < tdir * t) hi += 1;     // searchsortedfirst by tdir * t (generic_dense.jl:838-849)
         const int ip = hi, im = hi - 1;
         const R dt = sink.ts[ip] - sink.ts[im];
         const R Theta = (dt == (R)0) ? (R)1 : (t - sink.ts[im]) / dt;
@@ -1059,8 +1060,8 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     }
     g_tspans = a.tspans; g_dtmax_default = !(a.dtmax > 0);
     // reverse time (tf < t0): the integrator core above is direction-aware; callbacks (rightfloat / the tdir-ordered event
-    // search, callbacks.jl:65,201,320-345), post-hoc dense evaluation and per-trajectory spans are restated forward only
-    if (a.tf < a.t0 && (o.ncb > 0 || M > 0 || a.tspans)) return -7;
+    // search, callbacks.jl:65,201,320-345), and per-trajectory spans are restated forward only
+    if (a.tf < a.t0 && (o.ncb > 0 || a.tspans)) return -7;
     if (a.tspans) for (long long i = 0; i < a.N; ++i) if (!(a.tspans[2 * i + 1] > a.tspans[2 * i])) return -7;
     if (a.tspans && ((a.tstops && a.ntstops > 0) || (a.disc && a.ndisc > 0) || M > 0)) return -6;
     Out<R> out;

@@ -1262,7 +1262,7 @@ static int compile_impl(b200ode_handle h, b200ode_program* out, int alg, int dty
     e = cudaLibraryGetKernel(&prog->k_integrate, prog->lib, "b200_integrate");
     if (e == cudaSuccess) e = cudaLibraryGetKernel(&prog->k_initdt, prog->lib, "b200_initdt");
     if (e == cudaSuccess && prog->everystep && prog->nsave == n && alg != B200ODE_ALG_ROSENBROCK32 &&
-        alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 && !prog->callbacks && !prog->reverse)
+        alg != B200ODE_ALG_AUTOTSIT5_ROSENBROCK23 && !prog->callbacks)
         e = cudaLibraryGetKernel(&prog->k_dense, prog->lib, "b200_dense_eval");
     if (e != cudaSuccess) {
         cudaLibraryUnload(prog->lib); delete prog;
@@ -1676,8 +1676,11 @@ int b200ode_solve_dense(b200ode_handle h, b200ode_program prog, const B200Proble
     if (o->saveat && o->nsaveat > 0) return fail(B200ODE_EINVAL, "dense output excludes saveat (dense = save_everystep && isempty(saveat), solve.jl:139)");
     if (o->save_start == 0) return fail(B200ODE_EINVAL, "dense output needs save_start");
     if (hp->tspans) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with per-trajectory time spans");
-    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows), for the composite algorithm, with callbacks or in reverse time");
-    for (int j = 1; j < nq; ++j) if (!(tq[j] >= tq[j - 1])) return fail(B200ODE_EINVAL, "tq must be ascending");
+    if (!prog->k_dense) return fail(B200ODE_EUNSUPPORTED, "dense output is not available with save_idxs, for Rosenbrock32 (its stages are not recomputable from the saved rows), for the composite algorithm or with callbacks");
+    // the queries come in the order the integration meets them (ode_interpolation sorts by tdir * t, generic_dense.jl:838)
+    for (int j = 1; j < nq; ++j)
+        if (prog->reverse ? !(tq[j] <= tq[j - 1]) : !(tq[j] >= tq[j - 1]))
+            return fail(B200ODE_EINVAL, prog->reverse ? "tq must be descending (reverse time)" : "tq must be ascending");
     const long long N = hp->trajectories;
     if (N == 0) return B200ODE_OK;
     CUDA_TRY(cudaSetDevice(h->device));

@@ -1229,6 +1229,10 @@ extern "C" __global__ void __launch_bounds__(B200_BLOCK, B200_MINBLOCKS) b200_in
 // values are bit-identical — which costs one perform_step! per visited interval instead of 8-17x
 // the HBM footprint.  Lazy extra stages (Vern7 k11..k16) use dt = ts[i+] - ts[i-] as the reference's
 // post-hoc _ode_addsteps! does.  tq must be ascending (the reference sorts the queries first).
+// Reverse-time programs (B200_REVERSE): the rows hold the caller's descending times, the kernel works on their mirror images
+// (B200_TS / B200_DTS; ode_interpolation searches by tdir * t, generic_dense.jl:838-849) and takes tq descending.
+#define B200_TS(i) B200_USER_T(ts[i])
+#define B200_DTS(i) B200_USER_T(dts[i])
 struct B200DenseParams {
     long long N;
     const real* p; long long p_ts, p_cs;
@@ -1257,7 +1261,7 @@ extern "C" __global__ void __launch_bounds__(128) b200_dense_eval(B200DenseParam
     int njacs = 0, nw = 0, nsolve = 0;
 #endif
     for (int j = 0; j < D.M; ++j) {
-        const real t = D.tq[j];
+        const real t = B200_USER_T(D.tq[j]);
         real* o = out + (size_t)j * B200_N;
         if (nrows < 2) {      // a single row: i- = i+, dt = 0 => the interpolant collapses to that row
 #pragma unroll
@@ -1265,20 +1269,20 @@ extern "C" __global__ void __launch_bounds__(128) b200_dense_eval(B200DenseParam
             continue;
         }
         // i+ = min(lastindex, max(previous i+, first i with ts[i] >= t)); i- = i+ - 1
-        while (hi < nrows - 1 && ts[hi] < t) hi += 1;
+        while (hi < nrows - 1 && B200_TS(hi) < t) hi += 1;
         const int ip = hi, im = hi - 1;
-        const real dt = ts[ip] - ts[im];
-        const real th = (dt == (real)0) ? (real)1 : (t - ts[im]) / dt;
+        const real dt = B200_TS(ip) - B200_TS(im);
+        const real th = (dt == (real)0) ? (real)1 : (t - B200_TS(im)) / dt;
         if (ip != cur) {
 #pragma unroll
             for (int c = 0; c < B200_N; ++c) { uprev[c] = us[(size_t)im * B200_N + c]; u[c] = us[(size_t)ip * B200_N + c]; }
-            st.init(uprev, p, ts[im], nf);                                   // FSAL k1 = f(u[i-], ts[i-])
+            st.init(uprev, p, B200_TS(im), nf);                                   // FSAL k1 = f(u[i-], ts[i-])
 #if B200_IS_ROSENBROCK
-            st.attempt(uprev, scratch, p, ts[im], dts[ip], D.reltol, D.abstol, nf, njacs, nw, nsolve, true);
+            st.attempt(uprev, scratch, p, B200_TS(im), B200_DTS(ip), D.reltol, D.abstol, nf, njacs, nw, nsolve, true);
 #else
-            st.attempt(uprev, scratch, p, ts[im], dts[ip], D.reltol, D.abstol, nf);
+            st.attempt(uprev, scratch, p, B200_TS(im), B200_DTS(ip), D.reltol, D.abstol, nf);
 #endif
-            st.dense_prepare(uprev, u, p, ts[im], dt);
+            st.dense_prepare(uprev, u, p, B200_TS(im), dt);
             cur = ip;
         }
         real val[B200_N];

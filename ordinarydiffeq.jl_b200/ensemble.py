@@ -308,7 +308,9 @@ class ODESolution:
             raise NotImplementedError("this solution has no dense output (solve with save_everystep and no saveat)")
         scalar = np.isscalar(t)
         tq = np.atleast_1d(np.asarray(t, dtype=np.float64))
-        order = np.argsort(tq, kind="stable")
+        # ode_interpolation evaluates the queries in the order the integration met them (sorted by tdir * t, generic_dense.jl:838)
+        tdir = -1.0 if (len(self.t) > 1 and self.t[-1] < self.t[0]) else 1.0
+        order = np.argsort(tdir * tq, kind="stable")
         vals = self._interp(tq[order])
         out = np.empty_like(vals)
         out[order] = vals
@@ -374,7 +376,7 @@ class EnsembleSolution:
 
     def at(self, tq):
         """[sol(tq) for sol in ensemble] as one array [trajectories, len(tq), n] in a single device pass
-        (b200ode_solve_dense); tq ascending."""
+        (b200ode_solve_dense); tq in the order the integration meets the times (ascending; descending for a reversed tspan)."""
         if self._dense_all is None:
             raise NotImplementedError("dense output needs save_everystep, no saveat, and the default reduction")
         return self._dense_all(np.asarray(tq, dtype=np.float64))
@@ -548,9 +550,6 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     if reverse:
         if cb_specs is not None:
             raise NotImplementedError("reverse-time integration is not combined with callbacks")
-        if dense_kw:
-            raise NotImplementedError("dense=true is not available in reverse time")
-        dense_ok = False
     # (n >= 24: measured crossover on a cheap-RHS chain system, scripts/time_wide_threshold.py — below it the plain kernel's
     #  local-memory stage vectors, served from L1 at full occupancy, are faster than 112-256 threads with shared-memory stages)
     smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 24 and not ragged and cb_specs is None and not reverse

@@ -1609,8 +1609,15 @@ def test_reverse_time(pkg, handle, oracle, f32):
             assert np.array_equal(g["row_offsets"], o["row_offsets"]) and np.array_equal(g["ts"], o["ts"])
             assert np.array_equal(bits(g["us"]), bits(o["us"]))
             assert np.all(np.diff(np.asarray(g["ts"][:o["row_offsets"][1]], dtype=np.float64)) < 0)
-            with pytest.raises(L.B200Error):       # no dense output in reverse time
-                pkg.lowlevel.solve_host_dense(prog, u0, p, tspan, [1.0])
+            # dense output: sol_i(tq) from the recomputed stages, queries in the order the integration meets them
+            # (descending), extrapolation beyond both ends included
+            tq = [2.1, 2.0, 1.9, 1.3, 1.0001, 0.7, 0.25, 0.2]
+            gd = pkg.lowlevel.solve_host_dense(prog, u0, p, tspan, tq, **tol)
+            od = oracle.solve(oalg, rhs, u0, p, tspan, 3, 3, f32=f32, dense_tq=tq, **tol, **okw)
+            assert np.array_equal(bits(gd["dense"]), bits(od["dense"]))
+            assert np.array_equal(bits(gd["dense"][:, 1]), bits(u0))          # Θ = 0 on the first interval
+            with pytest.raises(L.B200Error):       # ascending queries are refused by a reverse-time program
+                pkg.lowlevel.solve_host_dense(prog, u0, p, tspan, [0.5, 1.0])
         finally:
             prog.close()
     # isoutofdomain sees the caller's time: reject every step that ends in (0.9, 1.1) with u[0] above a threshold
@@ -1646,7 +1653,7 @@ def test_high_level_solve_in_reverse_time(pkg, oracle):
     prob = P.ODEProblem(P.CSource(*pl.lorenz_source()), U0, (1.0, 0.0), table[0])
     ep = P.EnsembleProblem(prob, prob_func=P.TableProbFunc(p=table))
     grid = P.ranges.saveat_grid(0.1, (1.0, 0.0))
-    assert grid == P.ranges.julia_range(0.9, -0.1, 0.0) and grid[-1] == 0.0
+    assert grid == P.ranges.julia_range(0.9, -0.1, 0.0) and grid[-1] == 0.0 and len(grid) == 10
     o = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (1.0, 0.0), 3, 3, saveat=grid)
     s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=0.1)
     for i in (0, 5, N - 1):
@@ -1661,8 +1668,11 @@ def test_high_level_solve_in_reverse_time(pkg, oracle):
     assert np.array_equal(bits(np.ascontiguousarray(s[3].u)), bits(oe["us"][a:b]))
     s = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, saveat=[0.0, 0.25, 0.5, 1.0])
     assert list(s[0].t) == [1.0, 0.5, 0.25, 0.0]
-    with pytest.raises(NotImplementedError):
-        P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N, dense=True)
+    # sol(t) in reverse time: any query order (sorted by tdir * t before the device pass)
+    sd = P.solve(ep, P.Tsit5(), P.EnsembleB200(), trajectories=N)
+    od = oracle.solve(oracle.ALG_TSIT5, pl.lorenz_source(), U0, table, (1.0, 0.0), 3, 3, dense_tq=[0.9, 0.5, 0.123])
+    assert np.array_equal(bits(np.ascontiguousarray(sd[5]([0.5, 0.123, 0.9]))), bits(od["dense"][5][[1, 2, 0]]))
+    assert np.array_equal(bits(np.ascontiguousarray(sd.at([0.9, 0.5, 0.123]))), bits(od["dense"]))
     # Robertson backwards over a short span with Rodas5P
     (r, rn), (j, jn), (tg, tgn) = pl.robertson_sources()
     pr = pl.robertson_params(N)
