@@ -605,6 +605,12 @@ def test_reverse_time_equals_the_mirrored_forward_problem(alg):
             assert np.array_equal(r[k], m[k]), (alg, extra, k)
         assert np.array_equal(r["t_final"], -m["t_final"]) and np.array_equal(r["ts"], -np.asarray(m["ts"])), (alg, extra)
         assert np.all(r["retcode"] == 1) and np.all(r["t_final"] == tf)
+    # post-hoc dense evaluation (ode_interpolation searches by tdir * t, generic_dense.jl:838-849), extrapolation included
+    if alg not in ("ROSENBROCK32", "AUTOTSIT5_ROSENBROCK23"):
+        tq = [2.1, 2.0, 1.9, 1.3, 1.0001, 0.7, 0.25, 0.2]
+        r = oracle.solve(a, (_MIRROR_F, "mf"), u0, p, (t0, tf), 3, 3, dense_tq=tq, reltol=1e-6, abstol=1e-8, **kw)
+        m = oracle.solve(a, (_MIRROR_G, "mf"), u0, p, (-t0, -tf), 3, 3, dense_tq=[-x for x in tq], reltol=1e-6, abstol=1e-8, **kw)
+        assert np.array_equal(r["dense"], m["dense"]) and np.array_equal(r["dense"][:, 1], u0)
 
 
 def test_reference_saveat_bookkeeping_known_answers():
