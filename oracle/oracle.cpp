@@ -685,10 +685,11 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
             // find_root (:478-491): IntervalNonlinearProblem solved with ModAB(), abstol = reltol = 0 — EXT
             // (BracketingNonlinearSolve).  With zero tolerances every bracketing method ends on the pair of adjacent
             // floats around the sign change, so plain bisection is used; an exact zero counts as the far side.
+            // (backward integration: tup[1] > tup[2], "left" / "right" keep the order of the tuple — find_root's docstring)
             R left = bottom_t, right = top_t;
             for (;;) {
                 R mid = left + (right - left) / (R)2;
-                if (!(left < mid && mid < right)) break;
+                if (!(tdir * left < tdir * mid && tdir * mid < tdir * right)) break;
                 R sm = jl_sign(get_condition(cb, mid));
                 if (sm == bottom_sign) left = mid; else right = mid;
             }
@@ -711,7 +712,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
     };
     // apply_callback! (callbacks.jl:557-637)
     auto apply_callback = [&](const OracleCallback& cb, R cb_time, R prev_sign, bool& saved_in_cb) -> bool {
-        if (o.adaptive) dtpropose = jl_max(jl_nextfloat(opts_dtmin), dt);      // set_proposed_dt!(max(nextfloat(dtmin), dtrelax*dt)), dtrelax = 1
+        if (o.adaptive) dtpropose = tdir * jl_max(jl_nextfloat(opts_dtmin), tdir * dt);   // set_proposed_dt!(tdir * max(nextfloat(dtmin), tdir * dtrelax * dt)), dtrelax = 1
         // change_t_via_interpolation! (integrator_interface.jl:5-39)
         if (cb_time != t) {
             R val[ORACLE_MAXN];
@@ -746,7 +747,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
                 R t2, s2, r2;
                 bool occ2 = find_callback_time(o.cbs[k], ci, t2, s2, r2);
                 if (ci == 1) { tmin = t2; upcrossing = s2; residual = r2; event_occurred = occ2; identified = k; }
-                else if (occ2 && (!event_occurred || t2 < tmin)) {
+                else if (occ2 && (!event_occurred || tdir * t2 < tdir * tmin)) {
                     tmin = t2; upcrossing = s2; residual = r2; event_occurred = true; identified = k;
                 }
                 if (event_occurred && identified == k) evc = ci;
@@ -1059,9 +1060,9 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         o.disc = discs.data(); o.ndisc = (int)discs.size();
     }
     g_tspans = a.tspans; g_dtmax_default = !(a.dtmax > 0);
-    // reverse time (tf < t0): the integrator core above is direction-aware; callbacks (rightfloat / the tdir-ordered event
-    // search, callbacks.jl:65,201,320-345), and per-trajectory spans are restated forward only
-    if (a.tf < a.t0 && (o.ncb > 0 || a.tspans)) return -7;
+    // reverse time (tf < t0): the integrator core, the callbacks (callbacks.jl:201,478-491,565-567) and the dense evaluation
+    // above are direction-aware; per-trajectory spans are restated forward only
+    if (a.tf < a.t0 && a.tspans) return -7;
     if (a.tspans) for (long long i = 0; i < a.N; ++i) if (!(a.tspans[2 * i + 1] > a.tspans[2 * i])) return -7;
     if (a.tspans && ((a.tstops && a.ntstops > 0) || (a.disc && a.ndisc > 0) || M > 0)) return -6;
     Out<R> out;

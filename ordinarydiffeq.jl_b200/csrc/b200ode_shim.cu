@@ -300,10 +300,10 @@ int callbacks_source(int alg, int dtype, const B200CallbackSrc* cbs, int ncb, bo
         snprintf(buf, sizeof buf, "{%d, %d, %d, %d, %d, %d, %d, %.17g, (real)%.17g}, ", cont ? 1 : 0, has_aff ? 1 : 0,
                  has_neg ? 1 : 0, rootfind, ip, c.save_before ? 1 : 0, c.save_after ? 1 : 0, abstol, nudge);
         table += buf;
-        cond += "        case " + std::to_string(k) + ": return " + c.condition_name + "(u, p, t);\n";
+        cond += "        case " + std::to_string(k) + ": return " + c.condition_name + "(u, p, B200_USER_T(t));\n";   // reverse-time programs: the caller's t
         aff += "        case " + std::to_string(k) + ": ";
-        if (has_neg) aff += std::string("if (neg) { ") + c.affect_neg_name + "(u, p, t, terminate); break; } ";
-        if (has_aff) aff += std::string("if (!neg) { ") + c.affect_name + "(u, p, t, terminate); } ";
+        if (has_neg) aff += std::string("if (neg) { ") + c.affect_neg_name + "(u, p, B200_USER_T(t), terminate); break; } ";
+        if (has_aff) aff += std::string("if (!neg) { ") + c.affect_name + "(u, p, B200_USER_T(t), terminate); } ";
         aff += "break;\n";
     }
     table += "}\n";
@@ -379,10 +379,6 @@ int nvrtc_build(int alg, int dtype, int n, int np, const char* rhs_src, const ch
         return fail(B200ODE_EUNSUPPORTED, "reverse-time integration is served by the one-thread-per-trajectory kernel");
     if (reverse && extra_options && strstr(extra_options, "-DB200_TSPANS=1"))
         return fail(B200ODE_EUNSUPPORTED, "reverse-time integration is not combined with per-trajectory time spans");
-    if (reverse)
-        for (int i = 0; i < ncb; ++i)
-            if (cbs[i].kind != B200ODE_CB_ISOUTOFDOMAIN)
-                return fail(B200ODE_EUNSUPPORTED, "reverse-time integration is not combined with callbacks (isoutofdomain is)");
     if (coop && alg != B200ODE_ALG_VERN7 && alg != B200ODE_ALG_ROSENBROCK23)
         return fail(B200ODE_EUNSUPPORTED, "the lane-group kernel (B200ODE_OPT_COMPONENT_RHS) is available for Vern7 and Rosenbrock23");
     if (coop && alg == B200ODE_ALG_ROSENBROCK23 && (n < 2 || n > 16 || n == 3))

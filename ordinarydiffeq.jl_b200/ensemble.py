@@ -547,9 +547,6 @@ def solve(eprob, alg, ensemblealg=None, **kw):
     t0_, tf_ = float(prob.tspan[0]), float(prob.tspan[1])
     # tspan[2] < tspan[1]: tdir = -1 (solve.jl:273) — a program compiled with B200ODE_OPT_REVERSE_TIME (mirrored-time kernels)
     reverse = tf_ < t0_
-    if reverse:
-        if cb_specs is not None:
-            raise NotImplementedError("reverse-time integration is not combined with callbacks")
     # (n >= 24: measured crossover on a cheap-RHS chain system, scripts/time_wide_threshold.py — below it the plain kernel's
     #  local-memory stage vectors, served from L1 at full occupancy, are faster than 112-256 threads with shared-memory stages)
     smem_stages = (alg.alg_id == _lib.ALG_VERN7 and n >= 24 and not ragged and cb_specs is None and not reverse

@@ -394,8 +394,8 @@ function __solve(eprob::AbstractEnsembleProblem, alg::B200Algs, ens::EnsembleB20
     (isempty(rtv) && isempty(atv)) || push!(extra, "-DB200_VECTOR_TOL=1")
     # prob_func remakes tspan (probed on trajectory 1): per-trajectory spans — final states or the ragged output only
     tspans_variant = eprob.prob_func(prob, SciMLBase.EnsembleContext(1, 1, nothing)).tspan != prob.tspan
-    tdir < 0 && (tspans_variant || !isempty(cbs)) &&
-        throw(ArgumentError("EnsembleB200: reverse-time integration is not combined with callbacks or per-trajectory tspan"))
+    tdir < 0 && tspans_variant &&
+        throw(ArgumentError("EnsembleB200: reverse-time integration is not combined with per-trajectory tspan"))
     if tspans_variant
         (isempty(tstops) && isempty(discs) && isempty(cbs)) ||
             throw(ArgumentError("EnsembleB200: per-trajectory tspan is not combined with tstops, d_discontinuities or callbacks"))

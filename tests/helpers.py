@@ -63,6 +63,25 @@ def ball_sources(f32=False):
     return rhs, cond, bounce, stop
 
 
+def moving_floor_sources(f32=False, mirror=False):
+    """A ball over a floor that rises with time, every user function time dependent: RHS (y' = v + 0.01 t), condition
+    (y - 0.1 t), continuous affect (v -> -e v + 0.001 t), discrete condition (t < 7 && v > 3) and affect (halves v, changes
+    the trajectory's own restitution, terminates for t < 0.5).  mirror = True gives the same problem in mirrored time s = -t
+    (RHS negated, every function reads -s): what a reverse-time program integrates."""
+    T = "float" if f32 else "double"
+    f = "f" if f32 else ""
+    tt = "(-t)" if mirror else "t"
+    sg = "-" if mirror else ""
+    d = dict(T=T, f=f, tt=tt, sg=sg)
+    rhs = ("void mf_rhs(%(T)s* du, const %(T)s* u, const %(T)s* p, const %(T)s t) { du[0] = %(sg)s(u[1] + 0.01%(f)s*%(tt)s); du[1] = %(sg)s(-p[0]); }\n" % d, "mf_rhs")
+    cond = ("%(T)s mf_cond(const %(T)s* u, const %(T)s* p, const %(T)s t) { return u[0] - 0.1%(f)s*%(tt)s; }\n" % d, "mf_cond")
+    bounce = ("void mf_bounce(%(T)s* u, %(T)s* p, const %(T)s t, int* terminate) { u[1] = -p[1] * u[1] + 0.001%(f)s*%(tt)s; }\n" % d, "mf_bounce")
+    disc = ("%(T)s mf_dc(const %(T)s* u, const %(T)s* p, const %(T)s t) { return (%(tt)s < 7.0%(f)s && u[1] > 3.0%(f)s) ? 1 : 0; }\n" % d, "mf_dc")
+    damp = ("void mf_damp(%(T)s* u, %(T)s* p, const %(T)s t, int* terminate) { u[1] = 0.5%(f)s * u[1]; p[1] = 0.9%(f)s * p[1]; "
+            "if (%(tt)s < 0.5%(f)s) *terminate = 1; }\n" % d, "mf_damp")
+    return rhs, cond, bounce, disc, damp
+
+
 def always_true_source(f32=False, name="cb_true"):
     T = "float" if f32 else "double"
     return ("%s %s(const %s* u, const %s* p, const %s t) { return 1; }\n" % (T, name, T, T, T), name)

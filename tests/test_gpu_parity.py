@@ -1633,12 +1633,29 @@ def test_reverse_time(pkg, handle, oracle, f32):
         assert (o["nreject"] != ref["nreject"]).any()          # the domain test did act
     finally:
         prog.close()
+    # events in reverse time: a ball over a rising floor, every user function time dependent (the callbacks see the caller's t);
+    # root finding left / right, save_positions rows, a discrete callback that changes u and p and terminates
+    from helpers import moving_floor_sources
+    mrhs, cond, bounce, disc, damp = moving_floor_sources(f32)
+    pb = np.stack([9.81 * (0.5 + rng.uniform(size=N)), 0.8 + 0.2 * rng.uniform(size=N)], axis=1).astype(rdt)
+    ub = np.array([50.0, 0.0], dtype=rdt)
+    cbs = [dict(kind="continuous", condition=cond, affect=bounce, save_positions=(True, True)),
+           dict(kind="discrete", condition=disc, affect=damp, save_positions=(False, True))]
+    for cb, flags, kw in ((cbs, 0, dict()), (cbs, L.FLAG_NO_STEP_ROWS, dict(saveat=[14.0, 12.5, 9.0, 3.0, 1.0])),
+                          ([dict(cbs[0], interp_points=0, rootfind="right")], 0, dict())):
+        prog = handle.compile(pkg.ALG_TSIT5, dtype, 2, 2, mrhs[0], mrhs[1], extra_options=R + " " + L.OPT_EVERYSTEP, callbacks=cb)
+        try:
+            g = pkg.lowlevel.solve_host_everystep(prog, ub, pb, (15.0, 0.0), flags=flags, **kw)
+            okw = dict(ragged_saveat=True) if flags else dict(save_everystep=True)
+            o = oracle.solve(oracle.ALG_TSIT5, mrhs, ub, pb, (15.0, 0.0), 2, 2, f32=f32, callbacks=cb, **okw, **kw)
+            assert np.array_equal(g["row_offsets"], o["row_offsets"]) and np.array_equal(g["ts"], o["ts"])
+            assert np.array_equal(bits(g["us"]), bits(o["us"])) and np.array_equal(bits(g["u_final"]), bits(o["u_final"]))
+            for k in ("naccept", "nreject", "nf", "retcode", "nsaved"):
+                assert np.array_equal(g[k], o[k]), k
+            assert (o["nsaved"] > (0 if flags else o["naccept"] + 1)).all()
+        finally:
+            prog.close()
     # combinations that are declined at compile time
-    from helpers import ball_sources
-    ball = ball_sources(f32)
-    with pytest.raises(L.B200Error):
-        handle.compile(pkg.ALG_TSIT5, dtype, 2, 2, ball[0][0], ball[0][1], extra_options=R + " " + L.OPT_EVERYSTEP,
-                       callbacks=[dict(kind="continuous", condition=ball[1], affect=ball[2])])
     with pytest.raises(L.B200Error):
         handle.compile(pkg.ALG_TSIT5, dtype, 3, 3, rhs[0], rhs[1], extra_options=R + " " + L.OPT_TSPANS)
 

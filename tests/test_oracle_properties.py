@@ -613,6 +613,36 @@ def test_reverse_time_equals_the_mirrored_forward_problem(alg):
         assert np.array_equal(r["dense"], m["dense"]) and np.array_equal(r["dense"][:, 1], u0)
 
 
+def test_reverse_time_callbacks_equal_the_mirrored_forward_problem():
+    """Events in reverse time (callbacks.jl:201 the tdir-ordered first event, :478-491 find_root on (bottom_t, top_t) with
+    tup[1] > tup[2] and left / right in the tuple's order, :565-567 set_proposed_dt!(tdir * max(nextfloat(dtmin), tdir * dt))):
+    the oracle's native tdir = -1 run equals its forward run of the mirrored problem bit for bit — continuous callback with
+    root finding (left / right, with and without interp_points), save_positions rows, a discrete callback that changes u, p
+    and terminates; ragged rows with and without the per-step rows."""
+    from helpers import moving_floor_sources
+    N = 64
+    rng = np.random.default_rng(3)
+    p = np.stack([9.81 * (0.5 + rng.uniform(size=N)), 0.8 + 0.2 * rng.uniform(size=N)], axis=1)
+    u0 = np.array([50.0, 0.0])
+    res = []
+    for mirror in (False, True):
+        rhs, cond, bounce, disc, damp = moving_floor_sources(False, mirror)
+        span = (-15.0, 0.0) if mirror else (15.0, 0.0)
+        sgn = -1.0 if mirror else 1.0
+        cbs = [dict(kind="continuous", condition=cond, affect=bounce, save_positions=(True, True)),
+               dict(kind="discrete", condition=disc, affect=damp, save_positions=(False, True))]
+        res.append([oracle.solve(oracle.ALG_TSIT5, rhs, u0, p, span, 2, 2, callbacks=cb, **kw) for cb, kw in (
+            (cbs, dict(save_everystep=True)),
+            (cbs, dict(ragged_saveat=True, saveat=[sgn * x for x in (14.0, 12.5, 9.0, 3.0, 1.0)])),
+            ([dict(cbs[0], interp_points=0, rootfind="right")], dict(save_everystep=True)))])
+    for r, m in zip(*res):
+        for k in ("u_final", "us", "naccept", "nreject", "nf", "retcode", "nsaved", "row_offsets"):
+            assert np.array_equal(r[k], m[k]), k
+        assert np.array_equal(r["ts"], -m["ts"]) and np.array_equal(r["t_final"], -m["t_final"])
+        assert (r["nsaved"] > r["naccept"] + 1).all()            # events did happen (rows forced by save_positions)
+    assert set(np.unique(res[0][0]["retcode"])) == {1, 6}         # Success and Terminated members
+
+
 def test_reference_saveat_bookkeeping_known_answers():
     # test/InterfaceI/ode_saveat_tests.jl:214-220: save_everystep = false keeps [t0, tf]; with maxiters = 3 the failed
     # solve still has two entries (start + the point it reached)
