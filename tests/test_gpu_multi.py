@@ -148,6 +148,23 @@ def test_multi_device_c_abi_equals_single_device(pkg, handle, ndev):
         m = ll.solve_host_mean(progm, u0, p, (0.0, 4.0))
         assert np.array_equal(a["u_final"].view(np.uint64), m["u_final"].view(np.uint64))
         assert np.allclose(m["mean"], a["u_final"].mean(axis=0), rtol=1e-12, atol=0)
+        # a reverse-time program (tspan[2] < tspan[1], B200ODE_OPT_REVERSE_TIME) through the multi-device entry points
+        R = pkg._lib.OPT_REVERSE_TIME
+        pr1 = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1], extra_options=R)
+        prm = mh.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1], extra_options=R)
+        try:
+            for kw in ({}, {"saveat": [0.3, 0.2, 0.05, 0.0]}):
+                a = ll.solve_host(pr1, u0, p, (0.4, 0.0), **kw)
+                b = ll.solve_host(prm, u0, p, (0.4, 0.0), **kw)
+                for k in ("naccept", "nreject", "nf", "retcode", "nsaved"):
+                    assert np.array_equal(a[k], b[k]), k
+                assert np.array_equal(a["u_final"].view(np.uint64), b["u_final"].view(np.uint64))
+                assert (b["t_final"] == 0.0).all() and (b["retcode"] == 1).all()
+                if "saveat" in kw:
+                    assert np.array_equal(a["us"].view(np.uint64), b["us"].view(np.uint64)) and list(b["ts"]) == [0.4, 0.3, 0.2, 0.05, 0.0]
+        finally:
+            prm.close()
+            pr1.close()
     finally:
         progm.close()
         mh.close()
