@@ -17,7 +17,8 @@
 //   Julia Base            eps, nextfloat, log10, ^, exp2(Float32)
 //
 // Each trajectory is the out-of-place / SVector form of the reference
-// (ConstantCache steppers), forward time, adaptive, PI controller, no callbacks.
+// (ConstantCache steppers), either time direction (tdir = sign(tf - t0) carried the way the reference carries it),
+// adaptive PI control or fixed steps, tstops / d_discontinuities, callbacks (Tsit5), post-hoc dense evaluation.
 //
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp ... -lquadmath).
 

@@ -15,7 +15,8 @@
 //       268-333,340-414,597-677,1027-1034,1199-1256
 //   lib/OrdinaryDiffEqCore/src/integrators/controllers.jl:245-250,288-293,805-843
 //   lib/DiffEqBase/src/check_error.jl:70-118
-// for forward time, adaptive stepping, PI controller, no callbacks, tstops = {tf}.
+// written for forward time (reverse-time programs run the mirrored problem through the same code: B200_REVERSE below);
+// adaptive PI control; the variants (fixed steps, tstops, ragged rows, callbacks, ...) are compile-time options.
 //
 // Compile-time configuration (set by the shim before this file):
 //   B200_N, B200_NP      state / parameter dimension
