@@ -882,6 +882,41 @@ def test_reference_tstops_with_adaptive_steppers(pkg):
     # the harmonic part has the closed form x(t) = x0 cos(0.1 t) + v0 sin(0.1 t)/0.1 up to the 1e-6 forcing
     x = 1.0 * math.cos(0.2) + 0.01 * math.sin(0.2) / 0.1
     assert abs(o["u_final"][0, 0] - x) < 1e-6
+    # :155-170 ("Backward integration with tstop flags"): u' = -0.1 u over (2.0, 0.0) with Vern9, tstops = [1.5, 1.0, 0.5]
+    s_dec = ("void dec(double* du, const double* u, const double* p, const double t) { du[0] = -0.1 * u[0]; }\n", "dec")
+    o = oracle.solve(oracle.ALG_VERN9, s_dec, np.array([[1.0]]), None, (2.0, 0.0), 1, 0, reltol=1e-12, abstol=1e-15,
+                     tstops=[1.5, 1.0, 0.5], save_everystep=True)
+    assert o["retcode"][0] == 1 and {1.5, 1.0, 0.5} <= set(o["ts"]) and o["ts"][0] == 2.0 and o["ts"][-1] == 0.0
+    assert abs(o["u_final"][0, 0] - math.exp(0.2)) < 1e-12
+    # :203-221 ("Multiple close tstops with StaticArrays"): stops 1e-15 .. 1e-13 apart; Success, 1.0 / 2.0 / 3.0 are hit
+    s_osc = ("void osc(double* du, const double* u, const double* p, const double t) { du[0] = u[1]; du[1] = -u[0]; }\n", "osc")
+    close = [1.0, 1.0 + 1.0e-14, 1.0 + 2.0e-14, 1.0 + 5.0e-14, 2.0, 2.0 + 1.0e-15, 2.0 + 1.0e-14, 3.0, 3.0 + 1.0e-13]
+    o = oracle.solve(oracle.ALG_VERN9, s_osc, np.array([[1.0, 0.0]]), None, (0.0, 4.0), 2, 0, reltol=1e-12, abstol=1e-15,
+                     tstops=close, save_everystep=True)
+    assert o["retcode"][0] == 1 and all(np.any(np.abs(o["ts"] - x) < 1e-10) for x in (1.0, 2.0, 3.0))
+    assert abs(o["u_final"][0, 0] - math.cos(4.0)) < 1e-10 and set(close) <= set(o["ts"])
+    # :296-298: a fixed dt that does not divide the span still ends on tspan[end]
+    o = oracle.solve(oracle.ALG_TSIT5, linear_source(), np.array([[0.5]]), None, (0.0, 1.0), 1, 0, dt=0.3, adaptive=False, save_everystep=True)
+    assert o["ts"][-1] == 1.0 and len(o["ts"]) == 5
+    # :64-81 ("Tstops Eps"): saveat = [0.0, 0.0094777, 1.5574], tstops = 0.010823, a discrete callback that fires at the
+    # stop, tspan (-1, 3): sol.t[end] == 1.5574 (neither end of the span is in saveat, so neither is saved)
+    s_de = ("void de2(double* du, const double* u, const double* p, const double t) { du[0] = p[0] * u[0]; du[1] = p[1] * u[1]; }\n", "de2")
+    cond = ("double at_stop(const double* u, const double* p, const double t) { return t == 0.010823; }\n", "at_stop")
+    aff = ("void bump(double* u, double* p, const double t, int* terminate) { u[0] += 1.0; }\n", "bump")
+    saveat = [0.0, 0.0094777, 1.5574]
+    ss, se = pkg.ranges.resolve_save_flags(saveat, (-1.0, 3.0), False)
+    o = oracle.solve(oracle.ALG_TSIT5, s_de, np.zeros((1, 2)), np.array([[0.3, 0.7]]), (-1.0, 3.0), 2, 2, saveat=saveat, tstops=[0.010823],
+                     callbacks=[dict(kind="discrete", condition=cond, affect=aff, save_positions=(False, False))],
+                     save_start=ss, save_end=se)
+    assert (ss, se) == (False, False) and o["nsaved"][0] == 3 and list(o["ts"]) == saveat and o["retcode"][0] == 1
+    assert o["us"][0, 1, 0] == 0.0 and o["us"][0, 2, 0] > 1.0          # the affect acted between the second and third row
+    # ... and with DiscreteCallback's default save_positions = (true, true), as the reference test has it: the stop is saved
+    # before and after the affect, the last row is still the last saveat point
+    o = oracle.solve(oracle.ALG_TSIT5, s_de, np.zeros((1, 2)), np.array([[0.3, 0.7]]), (-1.0, 3.0), 2, 2, saveat=saveat, tstops=[0.010823],
+                     callbacks=[dict(kind="discrete", condition=cond, affect=aff, save_positions=(True, True))],
+                     save_start=ss, save_end=se, ragged_saveat=True)
+    assert list(o["ts"]) == [0.0, 0.0094777, 0.010823, 0.010823, 1.5574] and o["ts"][-1] == 1.5574
+    assert o["us"][2, 0] == 0.0 and o["us"][3, 0] == 1.0
 
 
 # ---- SVector stiff systems of the reference's static-array tests (the StaticWOperator path with n != 3) ----
