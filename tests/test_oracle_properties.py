@@ -461,6 +461,29 @@ def test_tstops_are_hit_exactly_and_saved():
     assert np.array_equal(same["ts"], plain["ts"]) and np.array_equal(same["us"], plain["us"])
 
 
+def test_reference_reverse_everystep_saveat_symdiff():
+    """test/InterfaceI/ode_saveat_tests.jl:70-95, the prob_reverse half: with save_everystep = true over (1.0, 0.0), adding
+    saveat = [0.8, 0.61, 0.6, 0.125] inserts exactly those times, in that order — fixed steps (RK4 there; the grid does not
+    depend on the stepper) and adaptive Rosenbrock32, both with the POSITIVE dt = 1/4 the reference passes."""
+    rhs = linear_source()
+    jac, tg = linear_jac_sources()
+    u0 = np.array([[0.5]])
+    grid = [0.8, 0.61, 0.6, 0.125]
+    for alg, kw in ((oracle.ALG_TSIT5, dict(adaptive=False)), (oracle.ALG_ROSENBROCK32, dict(jac=jac, tgrad=tg)),
+                    (oracle.ALG_DP5, dict())):
+        base = oracle.solve(alg, rhs, u0, None, (1.0, 0.0), 1, 0, dt=0.25, save_everystep=True, **kw)
+        more = oracle.solve(alg, rhs, u0, None, (1.0, 0.0), 1, 0, dt=0.25, save_everystep=True, saveat=grid, **kw)
+        assert base["retcode"][0] == 1 and more["retcode"][0] == 1
+        assert [t for t in more["ts"] if t not in set(base["ts"])] == grid and set(base["ts"]) <= set(more["ts"])
+        assert list(more["ts"]) == sorted(more["ts"], reverse=True) and base["ts"][0] == 1.0 and base["ts"][-1] == 0.0
+        if not kw.get("adaptive", True):
+            assert list(base["ts"]) == [1.0, 0.75, 0.5, 0.25, 0.0]
+        # the rows at the inserted times are the interpolant's: close to the exact solution 0.5 exp(1.01 (t - 1))
+        for t in grid:
+            k = list(more["ts"]).index(t)
+            assert abs(more["us"][k, 0] - 0.5 * math.exp(1.01 * (t - 1.0))) < (2e-3 if alg == oracle.ALG_ROSENBROCK32 else 1e-4)
+
+
 # ---- adaptive = false ----------------------------------------------------------------------------
 def test_fixed_step_mode():
     s = linear_source()
