@@ -60,6 +60,7 @@ class OracleCallback(C.Structure):
                 ("save_before", C.c_int), ("save_after", C.c_int)]
 
 
+RC_SUCCESS, RC_MAXITERS, RC_DTLESSTHANMIN, RC_UNSTABLE, RC_DTNAN = 1, 2, 3, 4, 5
 RC_TERMINATED = 6
 
 

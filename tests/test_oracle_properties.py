@@ -775,6 +775,32 @@ def test_reference_initdt_tiny_timespan_succeeds():
     assert o["retcode"][0] == 1 and o["t_final"][0] == 1.0e-19
 
 
+def test_reference_initdt_known_answers():
+    """test/InterfaceI/ode_initdt_tests.jl:7-22 (the automatic first step of the linear problems lies in (1e-7, 0.1)),
+    :72-76 (u0 = 0, t0 = 20, reversed Float32 span: |dt| > eps(t)), :122-133 (an RHS that returns NaN ends the solve with
+    DtNaN or Unstable, a healthy one succeeds)."""
+    from helpers import linear2d_source
+    jac, tg = linear_jac_sources()
+    o = oracle.solve(oracle.ALG_ROSENBROCK32, linear_source(), np.array([[0.5]]), None, (0.0, 1.0), 1, 0, jac=jac, tgrad=tg, save_everystep=True)
+    assert o["retcode"][0] == 1 and 1.0e-7 < o["ts"][1] < 0.1
+    u2 = np.array([[0.5 + 0.1 * k for k in range(8)]])
+    o = oracle.solve(oracle.ALG_BS3, linear2d_source(), u2, None, (0.0, 1.0), 8, 0, save_everystep=True)
+    assert o["retcode"][0] == 1 and 1.0e-7 < o["ts"][1] < 0.1
+    o = oracle.solve(oracle.ALG_VERN8, linear2d_source(), u2, None, (0.0, 1.0), 8, 0, save_everystep=True)      # DormandPrince8 there
+    assert o["retcode"][0] == 1 and 1.0e-7 < o["ts"][1] < 0.3
+    # u' = u, u0 = 0f0, tspan (20f0, 0f0): the first step is longer than eps(20f0) and points backwards
+    sf = ("void idf(float* du, const float* u, const float* p, const float t) { du[0] = u[0]; }\n", "idf")
+    o = oracle.solve(oracle.ALG_TSIT5, sf, np.zeros((1, 1), dtype=np.float32), None, (20.0, 0.0), 1, 0, f32=True, save_everystep=True)
+    eps20 = float(np.spacing(np.float32(20.0)))
+    assert o["retcode"][0] == 1 and o["ts"][1] < 20.0 and 20.0 - o["ts"][1] > eps20 and o["ts"][-1] == 0.0
+    # f(u, p, t) = [NaN]
+    sn = ("void fnan(double* du, const double* u, const double* p, const double t) { du[0] = 0.0 / 0.0; }\n", "fnan")
+    o = oracle.solve(oracle.ALG_TSIT5, sn, np.array([[1.0]]), None, (0.0, 1.0), 1, 0)
+    assert o["retcode"][0] in (oracle.RC_DTNAN, oracle.RC_UNSTABLE)
+    so = ("void fok(double* du, const double* u, const double* p, const double t) { du[0] = -u[0]; }\n", "fok")
+    assert oracle.solve(oracle.ALG_TSIT5, so, np.array([[1.0]]), None, (0.0, 1.0), 1, 0)["retcode"][0] == 1
+
+
 @pytest.mark.parametrize("name,S", [("Vern6", 9), ("Vern7Gen", 10), ("Vern8", 13), ("Vern9", 16)])
 def test_generated_verner_code_satisfies_tableau_identities(name, S):
     """Independent of how scripts/gen_verner.py assembled them: the emitted stage lines must satisfy the identities
