@@ -590,7 +590,8 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
     auto modify_dt_for_tstops = [&]() {
         R tdir_t = tdir * t, tdir_tstop = tdir * cur_tstop;             // first_tstop(integrator)
         R distance_to_tstop = std::fabs(tdir_tstop - tdir_t);
-        R tstop_tol = (R)100 * jl_eps(jl_max(std::fabs(t), std::fabs(tdir_tstop)));
+        // tstop_tol = 100 eps(max(|t|, |tstop|)) when both are finite, else zero (integrator_utils.jl:277-286)
+        R tstop_tol = (Bits<R>::finite(tdir_tstop) && Bits<R>::finite(t)) ? (R)100 * jl_eps(jl_max(std::fabs(t), std::fabs(tdir_tstop))) : (R)0;
         if (o.adaptive) {
             R original_dt = std::fabs(dt);
             dtpropose = tdir * original_dt;

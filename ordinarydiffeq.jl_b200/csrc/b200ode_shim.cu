@@ -1075,6 +1075,9 @@ int check_problem(int64_t N, const void* u0, const void* p, int np, double t0, d
     if (reverse && tf > t0)
         return fail(B200ODE_EINVAL, "a program compiled with B200ODE_OPT_REVERSE_TIME integrates reversed spans (tf < t0)");
     if (!(tf > t0) && !(tf < t0)) return fail(B200ODE_EINVAL, "tspan must have tf != t0 (finite)");
+    // (the reference integrates towards an infinite tf until the solution blows up, test/InterfaceI/inf_handling.jl; the kernels'
+    //  stop tolerance 100 eps(max(|t|, |tf|)) is written for finite spans, so an infinite span is declined, not mis-stepped)
+    if (!std::isfinite(t0) || !std::isfinite(tf)) return fail(B200ODE_EUNSUPPORTED, "tspan must be finite");
     if (!o) return fail(B200ODE_EINVAL, "opts is NULL");
     if (o->nsaveat < 0) return fail(B200ODE_EINVAL, "nsaveat < 0");
     if (o->saveat) {

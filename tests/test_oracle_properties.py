@@ -291,6 +291,16 @@ def test_failure_retcodes():
     nan_rhs = ("void nan_rhs(double* du, const double* u, const double* p, const double t) { du[0] = u[0] / (t - t); }\n", "nan_rhs")
     o = oracle.solve(oracle.ALG_TSIT5, nan_rhs, np.array([0.5]), None, (0.0, 1.0), 1, 0, trajectories=1, dt=0.1)
     assert o["retcode"][0] in (3, 4, 5)                                        # never Success
+    # test/Integrators_I/check_error.jl:5-16: u' = exp(u), u(0) = 0 explodes at t = 1; reltol = abstol = 1e-8 over (0, 10)
+    # must end with MaxIters or Unstable
+    blow = ("#include <math.h>\nvoid blow(double* du, const double* u, const double* p, const double t) { du[0] = exp(u[0]); }\n", "blow")
+    o = oracle.solve(oracle.ALG_TSIT5, blow, np.array([0.0]), None, (0.0, 10.0), 1, 0, trajectories=1, reltol=1e-8, abstol=1e-8)
+    assert o["retcode"][0] in (oracle.RC_MAXITERS, oracle.RC_UNSTABLE) and 0.99 < o["t_final"][0] < 1.01
+    # test/InterfaceI/inf_handling.jl: tspan = (0, Inf), adaptive = false, dt = 0.1: "shouldn't error, but should go unstable
+    # and abort" (the stop tolerance is zero for an infinite stop, integrator_utils.jl:277-286)
+    o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([0.5]), None, (0.0, float("inf")), 1, 0, trajectories=1, reltol=1e-8,
+                     abstol=1e-8, adaptive=False, dt=0.1)
+    assert o["retcode"][0] == oracle.RC_UNSTABLE and np.isfinite(o["t_final"][0]) and o["t_final"][0] > 100.0
 
 
 # ---- regression pins of the oracle itself -----------------------------------------------------
