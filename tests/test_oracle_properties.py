@@ -785,6 +785,28 @@ def test_reference_initdt_tiny_timespan_succeeds():
     assert o["retcode"][0] == 1 and o["t_final"][0] == 1.0e-19
 
 
+def test_reference_event_repeat_and_long_bounce_known_answers():
+    """test/Integrators_I/event_repeat_tests.jl:3-16 ("Event Repeat Test 1": u' = u over 100 eps with fixed dt = 4.7 eps, the
+    condition u - exp(70 eps) fires exactly once) and event_detection_tests.jl:59-79 ("Bouncing Ball": 10 000 time units of
+    elastic bounces with Tsit5 never fall through the floor, minimum(Array(sol)) > -40)."""
+    from helpers import ball_sources
+    eps = 2.0 ** -52
+    rhs = ("void er(double* du, const double* u, const double* p, const double t) { du[0] = u[0]; du[1] = 0.0; }\n", "er")
+    cond = ("double erc(const double* u, const double* p, const double t) { return u[0] - %r; }\n" % math.exp(70 * eps), "erc")
+    count = ("void era(double* u, double* p, const double t, int* terminate) { u[1] += 1.0; }\n", "era")     # c[] += 1
+    for sp in ((True, True), (False, False)):
+        o = oracle.solve(oracle.ALG_TSIT5, rhs, np.array([[1.0, 0.0]]), None, (0.0, 100 * eps), 2, 0, adaptive=False, dt=4.7 * eps,
+                         callbacks=[dict(kind="continuous", condition=cond, affect=count, save_positions=sp)], ragged_saveat=True)
+        assert o["retcode"][0] == 1 and o["u_final"][0, 1] == 1.0 and o["t_final"][0] == 100 * eps
+    brhs, bcond, _, _ = ball_sources()
+    flip = ("void flip(double* u, double* p, const double t, int* terminate) { u[1] = -u[1]; }\n", "flip")
+    o = oracle.solve(oracle.ALG_TSIT5, brhs, np.array([[50.0, 0.0]]), np.array([[9.8, 1.0]]), (0.0, 10000.0), 2, 2, save_everystep=True,
+                     callbacks=[dict(kind="continuous", condition=bcond, affect=flip, save_positions=(True, True))])
+    bounces = o["nsaved"][0] - o["naccept"][0] - 1          # the step row doubles as the save-before row: one extra row per event
+    assert o["retcode"][0] == 1 and o["us"].min() > -40 and o["us"][:, 0].min() > -1e-9
+    assert abs(bounces - 10000.0 / (2 * math.sqrt(2 * 50 / 9.8))) < 2          # one bounce per period 2 sqrt(2 h / g)
+
+
 def test_reference_initdt_known_answers():
     """test/InterfaceI/ode_initdt_tests.jl:7-22 (the automatic first step of the linear problems lies in (1e-7, 0.1)),
     :72-76 (u0 = 0, t0 = 20, reversed Float32 span: |dt| > eps(t)), :122-133 (an RHS that returns NaN ends the solve with
