@@ -16,6 +16,15 @@ def test_julia_range_matches_twice_precision_values(pkg):
     assert r.julia_range(1.0, 1.0, 0.5) == []
     assert r.saveat_grid([0.0, 0.5, 1.0, 2.0], (0.0, 1.0)) == [0.5, 1.0]      # t0 < t <= tf
     assert r.saveat_grid(None, (0.0, 1.0)) == []
+    # reversed spans (tdir = -1, solve.jl:1107-1120): the range runs downwards in the same twice-precision arithmetic — each
+    # element is the negation of the mirrored forward range's — and lists come back in the order the integrator meets them
+    down = r.julia_range(0.9, -0.1, 0.0)
+    assert down == [0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.3, 0.2, 0.1, 0.0] and down == [-x for x in r.julia_range(-0.9, 0.1, 0.0)]
+    assert r.saveat_grid(0.1, (1.0, 0.0)) == down and r.saveat_grid(-0.1, (1.0, 0.0)) == down      # tdir * abs(saveat)
+    assert r.saveat_grid([0.0, 0.5, 1.0, 2.0], (1.0, 0.0)) == [0.5, 0.0]                           # tdir t0 < tdir t <= tdir tf
+    assert r.saveat_grid(0.3, (1.0, 0.0)) == [-x for x in r.julia_range(-0.7, 0.3, 0.0)] and len(r.saveat_grid(0.3, (1.0, 0.0))) == 3
+    assert r.resolve_save_flags([0.0, 0.5, 1.0], (1.0, 0.0), False) == (True, None)
+    assert r.resolve_save_flags([0.5], (1.0, 0.0), False) == (False, False)
 
 
 def test_codegen_matches_handwritten_lorenz(pkg):
