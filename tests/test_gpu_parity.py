@@ -1703,3 +1703,34 @@ def test_high_level_solve_in_reverse_time(pkg, oracle):
         assert list(s[i].t) == [1.0, orr["t_final"][i]] and np.array_equal(bits(np.ascontiguousarray(s[i].u[-1])), bits(orr["u_final"][i]))
         assert s[i].stats.naccept == orr["naccept"][i] and s[i].stats.nreject == orr["nreject"][i]
         assert (s[i].retcode == "Success") == (orr["retcode"][i] == 1) and (orr["retcode"][i] != 1 or s[i].t[-1] == 0.99)
+
+
+def test_reverse_time_meanvar_and_infinite_span(pkg, handle, oracle):
+    """timeseries_steps_meanvar on the device for a reverse-time program (rows on a descending grid), and the C ABI's answer
+    to an infinite span (declined: the kernels' stop tolerance is written for finite spans; the oracle follows the
+    reference's inf_handling.jl)."""
+    pl, ll, L = pkg.problems_library, pkg.lowlevel, pkg._lib
+    N = 3000
+    p = pl.lorenz_params(N)
+    rhs = pl.lorenz_source(False)
+    grid = pkg.ranges.saveat_grid(0.05, (0.5, 0.0))
+    prog = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1], extra_options=L.OPT_REVERSE_TIME)
+    try:
+        full = ll.solve_host(prog, U0, p, (0.5, 0.0), saveat=grid)
+        st = ll.solve_host_meanvar(prog, U0, p, (0.5, 0.0), grid)
+        us = full["us"].astype(np.float64)
+        assert st["mean"].shape == (11, 3) and list(full["ts"]) == [0.5] + grid and grid[-1] == 0.0
+        assert np.allclose(st["mean"], us.mean(axis=0), rtol=1e-12, atol=1e-13)
+        assert np.allclose(st["var"], us.var(axis=0, ddof=1), rtol=1e-10, atol=1e-12)
+        o = oracle.solve(oracle.ALG_TSIT5, rhs, U0, p, (0.5, 0.0), 3, 3, saveat=grid)
+        assert np.array_equal(bits(full["us"]), bits(o["us"])) and np.array_equal(st["naccept"], o["naccept"])
+        with pytest.raises(L.B200Error):
+            ll.solve_host(prog, U0, p, (0.5, -np.inf))
+    finally:
+        prog.close()
+    plain = handle.compile(pkg.ALG_TSIT5, pkg.F64, 3, 3, rhs[0], rhs[1])
+    try:
+        with pytest.raises(L.B200Error):
+            ll.solve_host(plain, U0, p, (0.0, np.inf))
+    finally:
+        plain.close()
