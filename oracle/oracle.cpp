@@ -1013,7 +1013,8 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.reltol = (R)(a.reltol > 0 ? a.reltol : 1e-3);
     o.abstol = (R)(a.abstol > 0 ? a.abstol : 1e-6);
     o.dt = (R)a.dt; o.dtmin = (R)a.dtmin;
-    o.dtmax = (R)(a.dtmax > 0 ? a.dtmax : (a.tf - a.t0));
+    // dtmax: the default is tspan[2] - tspan[1] (signed, solve.jl:152); for a reversed span either sign may be given (solve.jl:401)
+    o.dtmax = (R)((a.dtmax > 0 || (a.dtmax < 0 && a.tf < a.t0)) ? a.dtmax : (a.tf - a.t0));
     o.maxiters = a.maxiters > 0 ? a.maxiters : 1000000;
     std::vector<R> atv, rtv;
     if (a.abstol_v) { atv.assign(a.abstol_v, a.abstol_v + a.n); o.abstol_v = atv.data(); }
@@ -1061,7 +1062,7 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
         o.tstops = stops.data(); o.ntstops = (int)stops.size();
         o.disc = discs.data(); o.ndisc = (int)discs.size();
     }
-    g_tspans = a.tspans; g_dtmax_default = !(a.dtmax > 0);
+    g_tspans = a.tspans; g_dtmax_default = !(a.dtmax > 0 || (a.dtmax < 0 && a.tf < a.t0));
     // reverse time (tf < t0): the integrator core, the callbacks (callbacks.jl:201,478-491,565-567) and the dense evaluation
     // above are direction-aware; per-trajectory spans are restated forward only
     if (a.tf < a.t0 && a.tspans) return -7;

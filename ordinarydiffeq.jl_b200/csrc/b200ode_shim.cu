@@ -868,6 +868,7 @@ int launch_solve(b200ode_handle h, b200ode_program prog, const B200DeviceProblem
     if (!st.empty()) om.tstops = st.data();
     if (!dd.empty()) om.d_discontinuities = dd.data();
     om.dt = std::fabs(o->dt);         // a positive dt is converted, a negative one is the direction's own (solve.jl:981-983)
+    om.dtmax = std::fabs(o->dtmax);   // likewise dtmax (solve.jl:401: a positive dtmax is converted); 0 stays the default
     return launch_solve_fwd<R>(h, prog, &dm, &om, dr, stream, row_offsets, ts_rag, dts_rag);
 }
 
