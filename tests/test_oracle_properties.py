@@ -807,6 +807,26 @@ def test_reference_event_repeat_and_long_bounce_known_answers():
     assert abs(bounces - 10000.0 / (2 * math.sqrt(2 * 50 / 9.8))) < 2          # one bounce per period 2 sqrt(2 h / g)
 
 
+def test_reference_adaptive_regression_on_2dlinear():
+    """test/Regression_I/ode_adaptive_tests.jl:8-27: on prob_ode_2Dlinear at the default tolerances the third-order
+    Bogacki–Shampine pair needs more steps than Dormand–Prince 5(4), which needs at least as many as an eighth-order pair
+    (RKF8 there, Vern8 here), every solve succeeds and the final error stays below 2e-3; Rosenbrock32 with dt = 1/16 runs."""
+    from helpers import linear2d_source
+    u0 = np.array([[0.3 + 0.09 * k for k in range(8)]])
+    exact = u0[0] * math.exp(1.01)
+    lens, errs = [], []
+    for alg in (oracle.ALG_BS3, oracle.ALG_DP5, oracle.ALG_VERN8):
+        o = oracle.solve(alg, linear2d_source(), u0, None, (0.0, 1.0), 8, 0, save_everystep=True)
+        assert o["retcode"][0] == 1
+        lens.append(len(o["ts"])); errs.append(np.abs(o["u_final"][0] - exact).max())
+    assert lens[0] > lens[1] >= lens[2] and max(errs) < 2.0e-3
+    jac = ("void l2j(double* J, const double* u, const double* p, const double t) { for (int i = 0; i < 64; ++i) J[i] = 0.0; "
+           "for (int i = 0; i < 8; ++i) J[i * 9] = 1.01; }\n", "l2j")
+    tg = ("void l2t(double* dT, const double* u, const double* p, const double t) { for (int i = 0; i < 8; ++i) dT[i] = 0.0; }\n", "l2t")
+    o = oracle.solve(oracle.ALG_ROSENBROCK32, linear2d_source(), u0, None, (0.0, 1.0), 8, 0, dt=1 / 16, jac=jac, tgrad=tg, linsolve=1)
+    assert o["retcode"][0] == 1 and np.abs(o["u_final"][0] - exact).max() < 2.0e-2
+
+
 def test_reference_initdt_known_answers():
     """test/InterfaceI/ode_initdt_tests.jl:7-22 (the automatic first step of the linear problems lies in (1e-7, 0.1)),
     :72-76 (u0 = 0, t0 = 20, reversed Float32 span: |dt| > eps(t)), :122-133 (an RHS that returns NaN ends the solve with
