@@ -143,3 +143,40 @@ def test_binding_structs_have_the_library_sizes(pkg):
     for which, cls in enumerate(mirrors):
         assert L.b200ode_struct_size(which) == C.sizeof(cls), cls.__name__
     assert L.b200ode_struct_size(99) == -1
+
+
+def test_reverse_time_program_variants_compile_without_gpu(pkg):
+    """B200ODE_OPT_REVERSE_TIME: the wrapped user functions (RHS, Jacobian, time gradient, callbacks, isoutofdomain) compile for
+    sm_100a in both precisions with the variants they combine with; the combinations the header rules out are refused by the
+    compile entry point, not at launch."""
+    L, pl = pkg._lib, pkg.problems_library
+    R = L.OPT_REVERSE_TIME
+    for f32 in (False, True):
+        dt = pkg.F32 if f32 else pkg.F64
+        src, name = pl.lorenz_source(f32)
+        (r, rn), (j, jn), (tg, tgn) = pl.robertson_sources(f32)
+        for extra in (R, R + " " + L.OPT_TSTOPS, R + " " + L.OPT_EVERYSTEP, R + " " + L.OPT_FIXED_DT, R + " " + L.OPT_VECTOR_TOL,
+                      R + " " + L.opt_save_idxs([0, 2])):
+            cubin, _ = pkg.compile_only(pkg.ALG_TSIT5, dt, 3, 3, src, name, extra_options=extra)
+            assert len(cubin) > 1000
+        for alg in (pkg.ALG_ROSENBROCK23, pkg.ALG_RODAS5P, pkg.ALG_AUTOTSIT5_ROSENBROCK23):
+            cubin, _ = pkg.compile_only(alg, dt, 3, 3, r, rn, j, jn, tg, tgn, extra_options=R + " " + L.OPT_TSTOPS)
+            assert len(cubin) > 1000
+        cubin, _ = pkg.compile_only(pkg.ALG_ROSENBROCK23, dt, 3, 3, r, rn, j, jn, extra_options=R)       # no time gradient given
+        assert len(cubin) > 1000
+    from helpers import moving_floor_sources
+    mrhs, cond, bounce, disc, damp = moving_floor_sources(False)
+    cbs = [dict(kind="continuous", condition=cond, affect=bounce, save_positions=(True, True)),
+           dict(kind="discrete", condition=disc, affect=damp, save_positions=(False, True)),
+           dict(kind="isoutofdomain", condition=("double neg(const double* u, const double* p, const double t) { return u[0] < -1.0 && t < 1.0; }\n", "neg"))]
+    cubin, _ = pkg.compile_only(pkg.ALG_TSIT5, pkg.F64, 2, 2, mrhs[0], mrhs[1], extra_options=R + " " + L.OPT_EVERYSTEP, callbacks=cbs)
+    assert len(cubin) > 1000
+    src, name = pl.lorenz_source(False)
+    for bad in (R + " " + L.OPT_TSPANS, ):
+        with pytest.raises(pkg.B200Error) as e:
+            pkg.compile_only(pkg.ALG_TSIT5, pkg.F64, 3, 3, src, name, extra_options=bad)
+        assert e.value.code == L.EUNSUPPORTED
+    psrc, pname = pl.pleiades_pairs_source(False)
+    with pytest.raises(pkg.B200Error) as e:
+        pkg.compile_only(pkg.ALG_VERN7, pkg.F64, 28, 0, psrc, pname, extra_options=R + " " + L.OPT_SMEM_STAGES)
+    assert e.value.code == L.EUNSUPPORTED
