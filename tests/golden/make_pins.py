@@ -33,6 +33,11 @@ cases.append(dict(name="robertson ros32 (mildly stiff span)", problem="robertson
 for a in ("rodas5", "rodas4", "rodas42", "rodas4p", "rodas4p2"):
     cases.append(dict(name="robertson %s" % a, problem="robertson", alg=a, f32=False, N=4, tf=1e4,
                       kw=dict(reltol=1e-6, abstol=1e-8)))
+# reverse time (tspan[2] < tspan[1])
+cases.append(dict(name="lorenz tsit5 backwards", problem="lorenz", alg="tsit5", f32=False, N=8, tspan=[1.0, 0.0], kw=dict()))
+cases.append(dict(name="lorenz vern7 backwards f32", problem="lorenz", alg="vern7", f32=True, N=8, tspan=[0.5, 0.0], kw=dict()))
+cases.append(dict(name="robertson rodas5p backwards", problem="robertson", alg="rodas5p", f32=False, N=4, tspan=[1.0e-3, 0.0],
+                  kw=dict(reltol=1e-6, abstol=1e-8)))
 for c in cases:
     o = _run_pin_case(pkg.problems_library, c)
     c["naccept"] = [int(x) for x in o["naccept"]]

@@ -326,12 +326,12 @@ def _run_pin_case(pl, case):
     f32 = case["f32"]
     N = case["N"]
     if case["problem"] == "lorenz":
-        return oracle.solve(alg, pl.lorenz_source(f32), np.array([1.0, 0, 0]), pl.lorenz_params(N, f32=f32), (0.0, 10.0),
-                            3, 3, f32=f32, **case["kw"])
+        return oracle.solve(alg, pl.lorenz_source(f32), np.array([1.0, 0, 0]), pl.lorenz_params(N, f32=f32),
+                            tuple(case.get("tspan", (0.0, 10.0))), 3, 3, f32=f32, **case["kw"])
     if case["problem"] == "robertson":
         r, j, tg = pl.robertson_sources(f32)
-        return oracle.solve(alg, r, np.array([1.0, 0, 0]), pl.robertson_params(N, f32=f32), (0.0, case["tf"]), 3, 3,
-                            f32=f32, jac=j, tgrad=tg, **case["kw"])
+        return oracle.solve(alg, r, np.array([1.0, 0, 0]), pl.robertson_params(N, f32=f32),
+                            tuple(case.get("tspan", (0.0, case.get("tf")))), 3, 3, f32=f32, jac=j, tgrad=tg, **case["kw"])
     if case["problem"] == "pleiades":
         return oracle.solve(alg, pl.pleiades_source(f32), pl.pleiades_u0(N, f32=f32), None, (0.0, 3.0), 28, 0, f32=f32,
                             **case["kw"])
