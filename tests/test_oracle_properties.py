@@ -646,6 +646,26 @@ def test_reverse_time_equals_the_mirrored_forward_problem(alg):
         assert np.array_equal(r["dense"], m["dense"]) and np.array_equal(r["dense"][:, 1], u0)
 
 
+@pytest.mark.parametrize("alg", ["TSIT5", "VERN7", "VERN9", "DP5", "RODAS5P", "ROSENBROCK23"])
+def test_forward_then_backward_round_trip(alg):
+    """A size-independent property of the direction handling that does not lean on the mirror argument: integrating
+    (0 -> T) and then (T -> 0) from the state reached returns to u0 within the tolerance budget — non-autonomous RHS, so a
+    wrong sign of t, dt or the time gradient anywhere in the backward run would show."""
+    a = getattr(oracle, "ALG_" + alg)
+    stiff = alg.startswith("RO")
+    rng = np.random.default_rng(11)
+    N = 16
+    u0 = rng.uniform(0.2, 1.0, (N, 3)); p = rng.uniform(0.5, 2.0, (N, 3))
+    kw = dict(jac=("", "mjac"), tgrad=("", "mtg")) if stiff else {}
+    tol = dict(reltol=1e-6, abstol=1e-8) if alg == "ROSENBROCK23" else dict(reltol=1e-10, abstol=1e-12)
+    T = 0.75
+    f = oracle.solve(a, (_MIRROR_F, "mf"), u0, p, (0.0, T), 3, 3, **tol, **kw)
+    b = oracle.solve(a, (_MIRROR_F, "mf"), f["u_final"], p, (T, 0.0), 3, 3, **tol, **kw)
+    assert (f["retcode"] == 1).all() and (b["retcode"] == 1).all() and (b["t_final"] == 0.0).all()
+    assert np.abs(f["u_final"] - u0).max() > 1e-2                                   # the state did move
+    assert np.abs(b["u_final"] - u0).max() < (2e-4 if alg == "ROSENBROCK23" else 2e-8)
+
+
 def test_reverse_time_callbacks_equal_the_mirrored_forward_problem():
     """Events in reverse time (callbacks.jl:201 the tdir-ordered first event, :478-491 find_root on (bottom_t, top_t) with
     tup[1] > tup[2] and left / right in the tuple's order, :565-567 set_proposed_dt!(tdir * max(nextfloat(dtmin), tdir * dt))):
