@@ -234,6 +234,11 @@ template <typename R> struct Opts {
     const struct OracleCallback* cbs = nullptr; int ncb = 0;
     // isoutofdomain(u, p, t) (solve.jl:166): R f(const R* u, const R* p, R t), non-zero = outside; NULL: never
     void* isout = nullptr;
+    // Test switch (tests/test_oracle_properties.py): this FORWARD run stands for the mirror image of a reverse-time run, the
+    // way the CUDA path's B200_REVERSE programs integrate it — the two places where the reference is not symmetric in tdir
+    // (fix_dt_at_bounds!'s dtmin clamp, check_error's tstop comparison) then act as they do for tdir < 0.  Lets the CPU suite
+    // check "mirrored forward + these two switches == native reverse" where they matter (dtmin > 0).
+    bool mirror_of_reverse = false;
 };
 
 // ODE_DEFAULT_NORM(u::StaticArray, t) = sqrt_fast(real(sum(abs2,u)) / max(length(u),1))
@@ -814,7 +819,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
         // fix_dt_at_bounds! (:1243-1256); timedepentdtmin = max(eps(t), dtmin)
         // (for tdir < 0 the reference clamps with max(dtmax, dt) and then takes min(dt, dtmin) against the POSITIVE dtmin —
         //  a no-op on a negative dt; restated as written)
-        if (tdir > (R)0) { dt = jl_min(dtmax, dt); dt = jl_max(dt, jl_max(jl_eps(t), opts_dtmin)); }
+        if (tdir > (R)0) { dt = jl_min(dtmax, dt); if (!o.mirror_of_reverse) dt = jl_max(dt, jl_max(jl_eps(t), opts_dtmin)); }
         else { dt = jl_max(dtmax, dt); dt = jl_min(dt, std::fabs(jl_max(jl_eps(t), opts_dtmin))); }
         modify_dt_for_tstops();
         // ---- check_error (lib/DiffEqBase/src/check_error.jl:70-118); `integrator.do_error_check &&` (solve.jl:909)
@@ -822,7 +827,7 @@ static void solve_one(const ProblemFns<R>& P, const R* u0, const R* p_in, R t0, 
             int code = RC_SUCCESS;
             if (std::isnan(dt)) code = RC_DTNAN;
             else if (iter > o.maxiters) code = RC_MAXITERS;
-            else if (o.adaptive && std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || t + dt < cur_tstop)) code = RC_DTLESSTHANMIN;   // t + dt < tdir * first(opts.tstops), as written (check_error.jl:96)
+            else if (o.adaptive && std::fabs(dt) <= std::fabs(opts_dtmin) && (!accept_step || (o.mirror_of_reverse ? t + dt > cur_tstop : t + dt < cur_tstop))) code = RC_DTLESSTHANMIN;   // t + dt < tdir * first(opts.tstops), as written (check_error.jl:96)
             else if (o.adaptive && !accept_step && std::fabs(dt) <= std::fabs(jl_eps(t))) code = RC_UNSTABLE;
             else if (accept_step) {
                 for (int i = 0; i < n; ++i) if (!Bits<R>::finite(u[i])) code = RC_UNSTABLE;
@@ -1001,6 +1006,7 @@ struct OracleArgs {
     const double* abstol_v; const double* reltol_v;    // per-component tolerances (n entries each) or NULL
     const double* disc; int ndisc;          // the d_discontinuities keyword, unfiltered
     const double* tspans;                   // per-trajectory (t0_i, tf_i) pairs or NULL
+    int mirror_of_reverse;                  // test switch, see Opts::mirror_of_reverse
 };
 
 template <typename R> static int run(const OracleArgs& a, const double* tq64 = nullptr, int M = 0, void* dense_out = nullptr) {
@@ -1026,6 +1032,7 @@ template <typename R> static int run(const OracleArgs& a, const double* tq64 = n
     o.linsolve = a.linsolve;
     o.save_everystep = a.save_everystep == 1;      // 2: ragged rows without the per-step rows (callbacks + saveat)
     o.adaptive = a.fixed_dt == 0;
+    o.mirror_of_reverse = a.mirror_of_reverse != 0;
     std::vector<OracleCallback> real_cbs;
     if (a.ncb > 0) {
         if (!a.cbs) return -5;

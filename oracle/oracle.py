@@ -51,7 +51,8 @@ class OracleArgs(C.Structure):
                 ("save_idxs", C.c_void_p), ("nsave_idxs", C.c_int),
                 ("tstops", C.c_void_p), ("ntstops", C.c_int), ("fixed_dt", C.c_int),
                 ("cbs", C.c_void_p), ("ncb", C.c_int), ("abstol_v", C.c_void_p), ("reltol_v", C.c_void_p),
-                ("disc", C.c_void_p), ("ndisc", C.c_int), ("tspans", C.c_void_p)]
+                ("disc", C.c_void_p), ("ndisc", C.c_int), ("tspans", C.c_void_p),
+                ("mirror_of_reverse", C.c_int)]
 
 
 class OracleCallback(C.Structure):
@@ -170,7 +171,7 @@ def nslots_for(t0, tf, saveat, save_start=None, save_end=None):
 def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None, tgrad=None, reltol=None,
           abstol=None, dt=None, dtmin=None, dtmax=None, maxiters=None, saveat=None, save_start=None, save_end=None,
           linsolve=0, nthreads=0, save_everystep=False, dense_tq=None, save_idxs=None, tstops=None, adaptive=True,
-          callbacks=None, ragged_saveat=False, d_discontinuities=None):
+          callbacks=None, ragged_saveat=False, d_discontinuities=None, mirror_of_reverse=False):
     """rhs/jac/tgrad: (source, name) tuples.  Arrays as in lowlevel.solve_host.
     save_everystep=True returns ragged rows (row_offsets, ts, us[total, n]) like lowlevel.solve_host_everystep."""
     L = lib()
@@ -235,6 +236,7 @@ def solve(alg, rhs, u0, p, tspan, n, np_, trajectories=None, f32=False, jac=None
     if idxs is not None:
         a.save_idxs = idxs.ctypes.data; a.nsave_idxs = len(idxs)
     a.fixed_dt = 0 if adaptive else 1
+    a.mirror_of_reverse = int(bool(mirror_of_reverse))      # test switch (Opts::mirror_of_reverse in oracle.cpp)
     cb_arr = None
     if callbacks:
         cb_arr = _callback_array(user, callbacks)

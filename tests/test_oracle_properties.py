@@ -666,6 +666,31 @@ def test_forward_then_backward_round_trip(alg):
     assert np.abs(b["u_final"] - u0).max() < (2e-4 if alg == "ROSENBROCK23" else 2e-8)
 
 
+@pytest.mark.parametrize("alg", ["TSIT5", "RODAS5P"])
+def test_reverse_time_with_dtmin_needs_the_two_asymmetric_spots(alg):
+    """With a user dtmin > 0 the reference is NOT symmetric in tdir: fix_dt_at_bounds! takes min(dt, dtmin) against the
+    positive dtmin for tdir < 0 (no lower bound on |dt|), and check_error compares t + dt < tdir * first(tstops) in both
+    directions (integrator_utils.jl:1243-1256, check_error.jl:93-99).  The plain mirror image then differs from the native
+    reverse run; the mirror image with those two spots acting as for tdir < 0 — what B200_REVERSE compiles into the kernels,
+    Opts::mirror_of_reverse here — equals it bit for bit, including the members that end with DtLessThanMin."""
+    a = getattr(oracle, "ALG_" + alg)
+    rng = np.random.default_rng(1)
+    N = 64
+    u0 = rng.uniform(0.1, 1.0, (N, 3)); p = rng.uniform(0.5, 3.0, (N, 3)); p[:, 1] *= 30
+    kw = dict(jac=("", "mjac"), tgrad=("", "mtg")) if alg == "RODAS5P" else {}
+    plain_differs = False
+    for dtmin in (1e-3, 5e-3, 2e-2):
+        common = dict(reltol=1e-6, abstol=1e-8, dtmin=dtmin, **kw)
+        r = oracle.solve(a, (_MIRROR_F, "mf"), u0, p, (2.0, 0.25), 3, 3, tstops=[1.0], **common)
+        m0 = oracle.solve(a, (_MIRROR_G, "mf"), u0, p, (-2.0, -0.25), 3, 3, tstops=[-1.0], **common)
+        m1 = oracle.solve(a, (_MIRROR_G, "mf"), u0, p, (-2.0, -0.25), 3, 3, tstops=[-1.0], mirror_of_reverse=True, **common)
+        for k in ("u_final", "naccept", "nreject", "nf", "retcode"):
+            assert np.array_equal(r[k], m1[k], equal_nan=True) if k == "u_final" else np.array_equal(r[k], m1[k]), (dtmin, k)
+        assert np.array_equal(r["t_final"], -m1["t_final"])
+        plain_differs = plain_differs or not np.array_equal(r["naccept"], m0["naccept"])
+    assert plain_differs and (r["retcode"] == oracle.RC_DTLESSTHANMIN).any()
+
+
 def test_reverse_time_callbacks_equal_the_mirrored_forward_problem():
     """Events in reverse time (callbacks.jl:201 the tdir-ordered first event, :478-491 find_root on (bottom_t, top_t) with
     tup[1] > tup[2] and left / right in the tuple's order, :565-567 set_proposed_dt!(tdir * max(nextfloat(dtmin), tdir * dt))):
